@@ -1,0 +1,22 @@
+"""crdpn_b200 -- B200-native hot path of 3DAug-Pose's contrastive distillation step.
+
+Two drop-in modules behind the reference's Python surface, both thin shims over the C ABI of
+``libcrdpn_b200.so`` (``include/crdpn_b200.h``, hand-written sm_100a CUDA):
+
+* ``CRDLoss(opt)(f_s, f_t, idx, contrast_idx)`` -- CRD memory-bank NCE step (``crd.py``)
+* ``ShapeEncoderPC(feature_dim)(shapes[B,3,P]) -> [B,feature_dim]`` -- the teacher's PointNet encoder
+  (``pointnet.py``; reference ``auxiliary/model.py:154-180``)
+
+The directory name is fixed by the build harness and is not a Python identifier; load it with
+``__graft_entry__.load_package()`` (registers it as ``crdpn_b200``).
+There is no CPU fallback anywhere in this package.
+"""
+from . import _native  # noqa: F401
+from .crd import AliasMethod, ContrastLoss, ContrastMemory, CRDLoss, Embed, Normalize  # noqa: F401
+
+__all__ = ["AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize"]
+try:  # added with the PointNet kernels
+    from .pointnet import ShapeEncoderPC  # noqa: F401
+    __all__.append("ShapeEncoderPC")
+except ImportError:  # pragma: no cover
+    pass

@@ -1,0 +1,89 @@
+"""ctypes binding of libcrdpn_b200.so (C ABI in include/crdpn_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc on first use, and if that is
+impossible a RuntimeError is raised.  Every wrapper raises RuntimeError on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+_LIB = None
+
+F32, BF16 = 0, 1
+
+# name -> (restype, argtypes); mirrors include/crdpn_b200.h one-to-one
+_SIGNATURES = {
+    "crdpn_abi_version": (c_int, []),
+    "crdpn_last_error": (ctypes.c_char_p, []),
+    "crdpn_launch_count": (c_uint64, []),
+    "crdpn_alias_build": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "crdpn_alias_draw": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),
+    "crdpn_alias_draw_contrast": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_uint64,
+                                          c_uint64, c_void_p, c_void_p]),
+    "crdpn_crd_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
+    "crdpn_crd_score": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                c_float, c_float, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_size_t, c_int, c_void_p]),
+    "crdpn_crd_momentum_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
+    "crdpn_pointnet_packed_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
+    "crdpn_pointnet_pack": (c_int, [c_void_p] * 18 + [c_float, c_int64, c_void_p, c_void_p]),
+    "crdpn_pointnet_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
+    "crdpn_pointnet_forward_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                            c_size_t, c_int, c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _PKG / "libcrdpn_b200.so"
+
+
+def declared_symbols() -> list[str]:
+    """Symbols declared in include/crdpn_b200.h (parsed, so the header stays the single source of truth)."""
+    import re
+    text = (_PKG.parent / "include" / "crdpn_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(crdpn_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not path.exists():
+        try:
+            from importlib import util as _u
+            spec = _u.spec_from_file_location("_crdpn_build", _PKG / "build.py")
+            mod = _u.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as exc:  # no fallback: fail loudly
+            raise RuntimeError(f"libcrdpn_b200.so is missing and could not be built ({exc}); "
+                               "this package has no CPU or eager fallback") from exc
+    handle = ctypes.CDLL(str(path))
+    for name in declared_symbols():
+        if not hasattr(handle, name):
+            raise RuntimeError(f"{path} does not export {name} (stale build? run build.py --force)")
+        if name in _SIGNATURES:
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = _SIGNATURES[name]
+    if handle.crdpn_abi_version() != 1:
+        raise RuntimeError("libcrdpn_b200.so ABI version mismatch")
+    _LIB = handle
+    return handle
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().crdpn_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().crdpn_launch_count())

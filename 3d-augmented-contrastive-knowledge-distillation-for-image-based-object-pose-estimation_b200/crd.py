@@ -1,0 +1,372 @@
+"""CRD memory-bank NCE loss -- host-side mirror of the published CRD module surface, on B200 kernels.
+
+The reference repository calls this path ``--crd`` (``trainingKD.py:127,282-283`` ->
+``KD/common/base_class.py:303-436``) but ships no memory-bank code; the surface kept here
+is the one ``BASELINE.json`` names and the published CRD algorithm defines:
+
+    CRDLoss(opt).forward(f_s, f_t, idx, contrast_idx=None) -> loss
+    Embed, Normalize, ContrastMemory, ContrastLoss, AliasMethod
+
+with the same constructor arguments, parameter / buffer names (``embed_s.linear.weight``,
+``contrast.memory_v1``, ``contrast.params`` ...) and semantics, so that it drops into the KD loop next to
+``representation_loss`` (``KD/vision/vanilla/vanilla_kd.py:158-160``; call at ``base_class.py:387``).
+
+All heavy work goes through the C ABI of ``libcrdpn_b200.so`` (``include/crdpn_b200.h``): one fused
+gather-dot-exp-loss-backward pass, one deterministic reduction, one momentum-update launch.  There is no
+CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import _native
+
+EPS = 1e-7
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: this package has no CPU fallback")
+
+
+# ----------------------------------------------------------------------------------------------------------
+class AliasMethod:
+    """Alias-method sampler (published CRD ``AliasMethod``): ``draw(N)`` returns N int64 indices.
+
+    Tables are built on the host by ``crdpn_alias_build`` (Vose stack pairing, fp32); draws run on the GPU
+    with a counter-based Philox stream keyed by ``seed`` so they are reproducible and bit-exact against the
+    oracle.  ``offset`` advances by the number of values drawn.
+    """
+
+    def __init__(self, probs: torch.Tensor, seed: int | None = None):
+        probs = probs.detach().to("cpu", torch.float32).contiguous()  # normalised inside crdpn_alias_build
+        n = probs.numel()
+        self.prob = torch.zeros(n, dtype=torch.float32)
+        self.alias = torch.zeros(n, dtype=torch.int64)
+        _native.check(_native.lib().crdpn_alias_build(probs.data_ptr(), n, self.prob.data_ptr(),
+                                                      self.alias.data_ptr()), "crdpn_alias_build")
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self.offset = 0
+
+    def cuda(self, device=None):
+        self.prob = self.prob.cuda(device)
+        self.alias = self.alias.cuda(device)
+        return self
+
+    def to(self, device):
+        self.prob = self.prob.to(device)
+        self.alias = self.alias.to(device)
+        return self
+
+    def draw(self, N: int) -> torch.Tensor:
+        _require_cuda(self.prob, "AliasMethod tables (call .cuda() first)")
+        out = torch.empty(N, dtype=torch.int64, device=self.prob.device)
+        with torch.cuda.device(self.prob.device):
+            _native.check(_native.lib().crdpn_alias_draw(self.prob.data_ptr(), self.alias.data_ptr(),
+                                                         self.prob.numel(), N, self.seed, self.offset,
+                                                         out.data_ptr(), _stream_ptr(self.prob.device)),
+                          "crdpn_alias_draw")
+        self.offset += N
+        return out
+
+    def draw_contrast(self, y: torch.Tensor, K1: int) -> torch.Tensor:
+        """[B, K1] contrast indices with column 0 = y (ContrastMemory.forward when idx is None)."""
+        _require_cuda(self.prob, "AliasMethod tables (call .cuda() first)")
+        y = y.contiguous()
+        B = y.numel()
+        out = torch.empty(B, K1, dtype=torch.int64, device=self.prob.device)
+        with torch.cuda.device(self.prob.device):
+            _native.check(_native.lib().crdpn_alias_draw_contrast(self.prob.data_ptr(), self.alias.data_ptr(),
+                                                                  self.prob.numel(), y.data_ptr(), B, K1,
+                                                                  self.seed, self.offset, out.data_ptr(),
+                                                                  _stream_ptr(self.prob.device)),
+                          "crdpn_alias_draw_contrast")
+        self.offset += B * K1
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+class Normalize(nn.Module):
+    """x / ||x||_p along dim 1 (no epsilon), as in the published Embed tail."""
+
+    def __init__(self, power: int = 2):
+        super().__init__()
+        self.power = power
+
+    def forward(self, x):
+        norm = x.pow(self.power).sum(1, keepdim=True).pow(1.0 / self.power)
+        return x.div(norm)
+
+
+class Embed(nn.Module):
+    """flatten -> Linear(dim_in, dim_out) -> L2 normalise."""
+
+    def __init__(self, dim_in: int = 1024, dim_out: int = 128):
+        super().__init__()
+        self.linear = nn.Linear(dim_in, dim_out)
+        self.l2norm = Normalize(2)
+
+    def forward(self, x):
+        x = x.view(x.shape[0], -1)
+        return self.l2norm(self.linear(x))
+
+
+class ContrastLoss(nn.Module):
+    """NCE criterion on normalised scores x[B, K+1, 1] (column 0 positive); unfused reference form.
+
+    CRDLoss does not call this (the fused kernel computes the same sum); it is kept for API parity and
+    for users who call ContrastMemory directly."""
+
+    def __init__(self, n_data: int):
+        super().__init__()
+        self.n_data = n_data
+
+    def forward(self, x):
+        bsz, m = x.shape[0], x.size(1) - 1
+        Pn = 1.0 / float(self.n_data)
+        P_pos = x.select(1, 0)
+        log_D1 = torch.div(P_pos, P_pos.add(m * Pn + EPS)).log_()
+        P_neg = x.narrow(1, 1, m)
+        log_D0 = torch.div(P_neg.clone().fill_(m * Pn), P_neg.add(m * Pn + EPS)).log_()
+        return -(log_D1.sum(0) + log_D0.view(-1, 1).sum(0)) / bsz
+
+
+# ----------------------------------------------------------------------------------------------------------
+class _FusedCRDFunction(torch.autograd.Function):
+    """loss = NCE(out_v1) + NCE(out_v2); gradients w.r.t. v1, v2 come out of the same kernel pass."""
+
+    @staticmethod
+    def forward(ctx, v1, v2, y, contrast_idx, mem):
+        loss, g1, g2 = mem._score_and_update(v1.detach(), v2.detach(), y, contrast_idx)
+        ctx.save_for_backward(g1, g2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g1, g2 = ctx.saved_tensors
+        return grad_out * g1, grad_out * g2, None, None, None
+
+
+class ContrastMemory(nn.Module):
+    """Two momentum memory banks with NCE scoring (published CRD ``ContrastMemory``).
+
+    Buffers (state_dict-compatible): ``params`` = [K, T, Z_v1, Z_v2, momentum], ``memory_v1``,
+    ``memory_v2`` of shape [n_rows, inputSize].  HBM layout: both banks live interleaved in one
+    [n_rows, 2, inputSize] allocation (``memory_v1``/``memory_v2`` are strided views of it) so one sampled
+    index touches one contiguous span; the kernels accept any common row pitch, so separately allocated
+    banks keep working.
+
+    Sharding: with ``row_begin/row_end`` set, this rank holds rows [row_begin,row_end) of a global
+    ``outputSize``-row bank and scores / updates only those (see sharded.py for the collectives).
+    """
+
+    def __init__(self, inputSize: int, outputSize: int, K: int, T: float = 0.07, momentum: float = 0.5,
+                 row_begin: int = 0, row_end: int | None = None, bank_dtype: torch.dtype = torch.float32,
+                 interleave: bool = True, seed: int | None = None):
+        super().__init__()
+        self.nLem = outputSize
+        self.row_begin = int(row_begin)
+        self.row_end = int(outputSize if row_end is None else row_end)
+        self.interleave = interleave
+        self.unigrams = torch.ones(self.nLem)
+        self.multinomial = AliasMethod(self.unigrams, seed=seed)
+        self.K = K
+        self.variant = 0
+        self.register_buffer("params", torch.tensor([K, T, -1, -1, momentum], dtype=torch.float32))
+        stdv = 1.0 / math.sqrt(inputSize / 3)
+        rows = self.row_end - self.row_begin
+        m1 = torch.rand(rows, inputSize).mul_(2 * stdv).add_(-stdv).to(bank_dtype)
+        m2 = torch.rand(rows, inputSize).mul_(2 * stdv).add_(-stdv).to(bank_dtype)
+        self.register_buffer("memory_v1", m1)
+        self.register_buffer("memory_v2", m2)
+        self._relayout()
+        self._ws = None
+        self._ws_key = None
+        self._res = None
+        # host mirror of params (avoids a device->host read per step once Z is frozen)
+        self._host = None
+
+    # -- layout ---------------------------------------------------------------------------------------
+    def _relayout(self):
+        m1, m2 = self._buffers["memory_v1"], self._buffers["memory_v2"]
+        if self.interleave:
+            bank = torch.stack([m1, m2], dim=1).contiguous()  # [rows, 2, D]
+            self._buffers["memory_v1"] = bank[:, 0, :]
+            self._buffers["memory_v2"] = bank[:, 1, :]
+        else:
+            self._buffers["memory_v1"] = m1.contiguous()
+            self._buffers["memory_v2"] = m2.contiguous()
+
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        self._relayout()  # .cuda()/.to() de-interleave the two views; put them back in one allocation
+        self.multinomial.to(self._buffers["memory_v1"].device)
+        self._ws = None
+        self._host = None
+        return self
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._host = None
+
+    def _banks(self):
+        m1, m2 = self.memory_v1, self.memory_v2
+        if m1.stride(1) != 1 or m2.stride(1) != 1 or m1.stride(0) != m2.stride(0) or m1.dtype != m2.dtype:
+            self._relayout()
+            m1, m2 = self.memory_v1, self.memory_v2
+        dt = _native.F32 if m1.dtype == torch.float32 else _native.BF16
+        if m1.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError("memory banks must be float32 or bfloat16")
+        return m1, m2, m1.stride(0), dt
+
+    def _host_params(self):
+        if self._host is None:
+            p = self.params.detach().cpu().tolist()
+            self._host = SimpleNamespace(K=int(p[0]), T=float(p[1]), Z1=float(p[2]), Z2=float(p[3]), m=float(p[4]))
+        return self._host
+
+    def _workspace(self, B, K1, D, device):
+        key = (B, K1, D, device)
+        if self._ws_key != key or self._ws is None:
+            n = ctypes.c_size_t(0)
+            _native.check(_native.lib().crdpn_crd_workspace_bytes(B, K1, D, device.index or 0, ctypes.byref(n)),
+                          "crdpn_crd_workspace_bytes")
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=device)
+            self._ws_key = key
+        if self._res is None or self._res.device != device:
+            self._res = torch.zeros(8, dtype=torch.float64, device=device)
+        return self._ws
+
+    # -- kernel calls ---------------------------------------------------------------------------------
+    def _score(self, v1, v2, idx, Z1, Z2, want_out=False, result=None):
+        """One crdpn_crd_score call. Returns (result[8] f64 device tensor, grad_v1, grad_v2, out_v1, out_v2)."""
+        m1, m2, stride, dt = self._banks()
+        B, K1 = idx.shape
+        D = v1.shape[1]
+        dev = v1.device
+        ws = self._workspace(B, K1, D, dev)
+        res = self._res if result is None else result
+        full = Z1 > 0 and Z2 > 0
+        g1 = torch.empty_like(v1) if full else None
+        g2 = torch.empty_like(v2) if full else None
+        o1 = torch.empty(B, K1, dtype=torch.float32, device=dev) if want_out else None
+        o2 = torch.empty(B, K1, dtype=torch.float32, device=dev) if want_out else None
+        hp = self._host_params()
+        with torch.cuda.device(dev):
+            rc = _native.lib().crdpn_crd_score(
+                m1.data_ptr(), m2.data_ptr(), stride, dt, v1.data_ptr(), v2.data_ptr(), idx.data_ptr(),
+                B, K1, D, self.nLem, self.row_begin, self.row_end,
+                hp.T, Z1, Z2, EPS,
+                o1.data_ptr() if want_out else None, o2.data_ptr() if want_out else None,
+                res.data_ptr(), g1.data_ptr() if full else None, g2.data_ptr() if full else None,
+                ws.data_ptr(), ws.numel(), self.variant, _stream_ptr(dev))
+        _native.check(rc, "crdpn_crd_score")
+        return res, g1, g2, o1, o2
+
+    def _update(self, v1, v2, y):
+        m1, m2, stride, dt = self._banks()
+        hp = self._host_params()
+        m32 = hp.m  # read back from the fp32 `params` buffer, so already an exact fp32 value
+        with torch.cuda.device(v1.device):
+            rc = _native.lib().crdpn_crd_momentum_update(
+                m1.data_ptr(), m2.data_ptr(), stride, dt, v1.data_ptr(), v2.data_ptr(), y.data_ptr(),
+                v1.shape[0], v1.shape[1], self.row_begin, self.row_end, m32, 1.0 - m32, _stream_ptr(v1.device))
+        _native.check(rc, "crdpn_crd_momentum_update")
+
+    def _reduce_sums(self, res):
+        """Hook for the sharded subclass: sum the first-call (sum_e1, sum_e2, count) over ranks."""
+        return res
+
+    def _reduce_partials(self, res, g1, g2):
+        """Hook for the sharded subclass: sum loss partials and grad_v over ranks."""
+        return res, g1, g2
+
+    def _prepare(self, v1, v2, y, idx):
+        for t, name in ((v1, "v1"), (v2, "v2"), (y, "y")):
+            _require_cuda(t, name)
+        if v1.dtype != torch.float32 or v2.dtype != torch.float32:
+            raise RuntimeError("embeddings must be float32")
+        v1, v2, y = v1.contiguous(), v2.contiguous(), y.contiguous().to(torch.int64)
+        K1 = self._host_params().K + 1
+        if idx is None:
+            idx = self.multinomial.draw_contrast(y, K1)
+        else:
+            _require_cuda(idx, "contrast_idx")
+            idx = idx.contiguous().to(torch.int64)
+            if idx.shape != (v1.shape[0], K1):
+                raise RuntimeError(f"contrast_idx must have shape [B, K+1] = {(v1.shape[0], K1)}, got {tuple(idx.shape)}")
+        return v1, v2, y, idx
+
+    def _freeze_z(self, v1, v2, idx):
+        """First call: Z = mean(exp(s/T)) * n_data, stored as constants (one device->host read, as in the
+        published algorithm)."""
+        hp = self._host_params()
+        if hp.Z1 > 0 and hp.Z2 > 0:
+            return
+        res, *_ = self._score(v1, v2, idx, -1.0, -1.0)
+        res = self._reduce_sums(res.clone())
+        s1, s2, cnt = res[2].item(), res[3].item(), res[4].item()
+        if hp.Z1 <= 0:
+            hp.Z1 = float(torch.tensor(s1 / cnt * self.nLem, dtype=torch.float32).item())
+            self.params[2] = hp.Z1
+            print("normalization constant Z_v1 is set to {:.1f}".format(hp.Z1))
+        if hp.Z2 <= 0:
+            hp.Z2 = float(torch.tensor(s2 / cnt * self.nLem, dtype=torch.float32).item())
+            self.params[3] = hp.Z2
+            print("normalization constant Z_v2 is set to {:.1f}".format(hp.Z2))
+
+    def _score_and_update(self, v1, v2, y, idx):
+        """Fused path used by CRDLoss: returns (loss 0-dim f32, grad_v1, grad_v2) and updates the banks."""
+        self._freeze_z(v1, v2, idx)
+        hp = self._host_params()
+        res, g1, g2, _, _ = self._score(v1, v2, idx, hp.Z1, hp.Z2)
+        res, g1, g2 = self._reduce_partials(res, g1, g2)
+        loss = (res[0] + res[1]).to(torch.float32)
+        self._update(v1, v2, y)
+        return loss, g1, g2
+
+    def fused_loss(self, v1, v2, y, idx=None):
+        v1c, v2c, y, idx = self._prepare(v1, v2, y, idx)
+        return _FusedCRDFunction.apply(v1c, v2c, y, idx, self)
+
+    def forward(self, v1, v2, y, idx=None):
+        """Published surface: returns (out_v1, out_v2), each [B, K+1, 1], and updates the banks.
+
+        The outputs are produced by the same fused pass; they carry no autograd graph (use
+        ``fused_loss`` / ``CRDLoss`` for training, which is what the KD loop calls)."""
+        v1c, v2c, y, idx = self._prepare(v1.detach(), v2.detach(), y, idx)
+        self._freeze_z(v1c, v2c, idx)
+        hp = self._host_params()
+        _, _, _, o1, o2 = self._score(v1c, v2c, idx, hp.Z1, hp.Z2, want_out=True)
+        self._update(v1c, v2c, y)
+        return o1.unsqueeze(-1), o2.unsqueeze(-1)
+
+
+class CRDLoss(nn.Module):
+    """CRD loss with two symmetric parts (published ``CRDLoss``).
+
+    Args (``opt`` attributes): s_dim, t_dim, feat_dim, n_data, nce_k, nce_t, nce_m.
+    forward(f_s [B,s_dim], f_t [B,t_dim], idx [B] int64, contrast_idx [B, nce_k+1] int64 or None) -> 0-dim loss.
+    """
+
+    def __init__(self, opt, **memory_kwargs):
+        super().__init__()
+        self.embed_s = Embed(opt.s_dim, opt.feat_dim)
+        self.embed_t = Embed(opt.t_dim, opt.feat_dim)
+        self.contrast = ContrastMemory(opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m, **memory_kwargs)
+        self.criterion_t = ContrastLoss(opt.n_data)
+        self.criterion_s = ContrastLoss(opt.n_data)
+
+    def forward(self, f_s, f_t, idx, contrast_idx=None):
+        f_s = self.embed_s(f_s)
+        f_t = self.embed_t(f_t)
+        return self.contrast.fused_loss(f_s, f_t, idx, contrast_idx)

@@ -1,0 +1,697 @@
+// crd_kernels.cu -- CRD memory-bank NCE step on B200 (sm_100a).
+//
+// Work the published CRD algorithm does with index_select + bmm + exp + div + autograd + index_copy_
+// (ContrastMemory.forward / ContrastLoss.forward; reference insertion point KD/common/base_class.py:387,
+// KD/vision/vanilla/vanilla_kd.py:158-160) is done here in three launches:
+//   1. crd_score_kernel     one pass over the B*(K+1) sampled bank rows: both dot products, exp, NCE loss
+//                           terms and the closed-form dL/ds applied straight back onto the row while it is
+//                           still in registers (grad_v accumulates in registers).  HBM-bound: each sampled
+//                           row of each bank is read exactly once; nothing of size B*K*D is ever written.
+//   2. crd_finalize_kernel  deterministic fixed-order reduction of the per-warp partials.
+//   3. crd_update_kernel    momentum + L2 renormalisation of the B positive rows (after all scoring).
+//
+// Data layout in HBM: a bank row is D contiguous elements (fp32 or bf16), 16-byte aligned, row pitch
+// `row_stride` elements.  The Python module allocates both banks interleaved as [N][2][D] so that one
+// sampled index touches one contiguous 2*D*sizeof(elem) span.
+//
+// Partitioning: the flat pair space P = B*K1 is cut into NW equal contiguous ranges, one per resident warp
+// (grid = SMs x blocks/SM, all resident).  Warps never synchronise with each other.  A warp walks its range
+// anchor by anchor; per anchor it scans 32 contrast indices at a time, drops entries that fall outside
+// this rank's bank shard, compacts the survivors into a per-warp shared-memory queue and consumes the
+// queue R rows x U steps at a time with all 2*CH*U 128-bit loads of a step group issued before first use.
+#include "common.cuh"
+
+namespace crdpn {
+
+constexpr int kWarps = 8;          // warps per CTA
+constexpr int kThreads = kWarps * 32;
+constexpr int kQueueCap = 128;     // per-warp compaction queue (entries, power of two)
+constexpr int kSlotExtra = 8;      // scalar partials appended to each slot (ls, lt, se1, se2, cnt, pad)
+constexpr int kMaxBlocksPerSM = 4; // upper bound used for workspace sizing
+
+struct ScoreParams {
+  const char* bank1;
+  const char* bank2;
+  long long row_stride_bytes;
+  const float* v1;
+  const float* v2;
+  const long long* idx;
+  int B, K1, D;
+  long long row_begin, row_end;
+  float k_exp;          // log2(e) / T
+  float inv_Z1, inv_Z2; // 1/Z (full mode)
+  float c;              // K*Pn + eps
+  float inv_mPn;        // 1 / (K*Pn)
+  float eps_over_mPn;   // (c - K*Pn) / (K*Pn)
+  float inv_BT;         // 1 / (B*T)
+  float* out_v1;
+  float* out_v2;
+  float* slots;
+  int maxseg;
+  unsigned int* ticket;
+};
+
+struct FinalizeParams {
+  const float* slots;
+  int maxseg;
+  long long NW;
+  int B, K1, D;
+  int full;
+  float* grad_v1;
+  float* grad_v2;
+  double* anchor_part;  // [B][8]
+  double* result;       // [8]
+  unsigned int* ticket;
+};
+
+__device__ __forceinline__ uint4 ld16_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// log(1+x), x >= 0: alternating series below 2^-5 (truncation < 2e-9 relative), libm above.
+__device__ __forceinline__ float log1p_pos(float x) {
+  if (x < 0.03125f) {
+    float t = fmaf(x, 0.2f, -0.25f);
+    t = fmaf(x, t, 0.33333334f);
+    t = fmaf(x, t, -0.5f);
+    t = fmaf(x, t, 1.0f);
+    return x * t;
+  }
+  return log1pf(x);
+}
+
+template <typename T> struct Unpack;
+template <> struct Unpack<float> {
+  static constexpr int VEC = 4;
+  static __device__ __forceinline__ void run(const uint4& u, float* f) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y);
+    f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+};
+template <> struct Unpack<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  static __device__ __forceinline__ void run(const uint4& u, float* f) {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+  }
+};
+
+// T: bank element; LPR: lanes cooperating on one row; CH: 16-byte chunks per lane per row;
+// U: row-steps whose loads are issued together; BPS: resident CTAs per SM; FULL: loss+grad vs. sums only.
+template <typename T, int LPR, int CH, int U, int BPS, bool FULL>
+__global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScoreParams p) {
+  constexpr int VEC = Unpack<T>::VEC;
+  constexpr int R = 32 / LPR;
+  constexpr int NV = VEC * CH;
+  constexpr unsigned kFull = 0xffffffffu;
+  static_assert(R * U + 32 <= kQueueCap, "queue too small");
+
+  __shared__ int2 queue_smem[kWarps][kQueueCap];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / LPR, j = lane % LPR;
+  const long long NW = (long long)gridDim.x * kWarps;
+  const long long gw = (long long)blockIdx.x * kWarps + warp;
+  const long long P = (long long)p.B * p.K1;
+  long long lo = P * gw / NW;
+  const long long hi = P * (gw + 1) / NW;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.ticket = 0u;  // finalize runs after us in stream order
+  int2* q = queue_smem[warp];
+  const bool store_out = (p.out_v1 != nullptr);
+  int seg = 0;
+
+  while (lo < hi) {
+    const int b = (int)(lo / p.K1);
+    const long long anchor_base = (long long)b * p.K1;
+    const long long seg_hi = (hi < anchor_base + p.K1) ? hi : (anchor_base + p.K1);
+    const int pos_off = (anchor_base == lo) ? 0 : -1;  // queue offset of the positive (k == 0) entry
+
+    float v1c[NV], v2c[NV];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int e0 = (j + LPR * i) * VEC;
+#pragma unroll
+      for (int t = 0; t < VEC; t += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(p.v1 + (long long)b * p.D + e0 + t);
+        const float4 c4 = *reinterpret_cast<const float4*>(p.v2 + (long long)b * p.D + e0 + t);
+        v1c[i * VEC + t + 0] = a.x; v1c[i * VEC + t + 1] = a.y; v1c[i * VEC + t + 2] = a.z; v1c[i * VEC + t + 3] = a.w;
+        v2c[i * VEC + t + 0] = c4.x; v2c[i * VEC + t + 1] = c4.y; v2c[i * VEC + t + 2] = c4.z; v2c[i * VEC + t + 3] = c4.w;
+      }
+    }
+    float g1[NV], g2[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) { g1[n] = 0.f; g2[n] = 0.f; }
+    float ls = 0.f, lt = 0.f, se1 = 0.f, se2 = 0.f, cnt = 0.f;
+
+    int qhead = 0, qtail = 0;
+
+    // consume up to R*U queue entries; `avail` >= R*U unless draining
+    auto consume = [&](int avail) {
+      int2 ent[U];
+      bool ev[U];
+      uint4 w1r[U][CH], w2r[U][CH];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int qi = u * R + g;
+        ev[u] = qi < avail;
+        ent[u] = q[(qhead + qi) & (kQueueCap - 1)];
+        const long long roff = (long long)ent[u].x * p.row_stride_bytes + (long long)j * 16;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          if (ev[u]) {
+            w1r[u][i] = ld16_stream(p.bank1 + roff + (long long)(LPR * i) * 16);
+            w2r[u][i] = ld16_stream(p.bank2 + roff + (long long)(LPR * i) * 16);
+          } else {
+            w1r[u][i] = make_uint4(0u, 0u, 0u, 0u);
+            w2r[u][i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float w1f[NV], w2f[NV];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          Unpack<T>::run(w1r[u][i], &w1f[i * VEC]);
+          Unpack<T>::run(w2r[u][i], &w2f[i * VEC]);
+        }
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+          a1 = fmaf(w2f[n], v1c[n], a1);  // out_v1 direction: bank2 row . v1
+          a2 = fmaf(w1f[n], v2c[n], a2);  // out_v2 direction: bank1 row . v2
+        }
+#pragma unroll
+        for (int off = LPR / 2; off >= 1; off >>= 1) {
+          a1 += __shfl_xor_sync(kFull, a1, off);
+          a2 += __shfl_xor_sync(kFull, a2, off);
+        }
+        const float e1 = ex2_approx(a1 * p.k_exp);
+        const float e2 = ex2_approx(a2 * p.k_exp);
+        const float m = ev[u] ? 1.f : 0.f;
+        se1 = fmaf(e1, m, se1);
+        se2 = fmaf(e2, m, se2);
+        cnt += m;
+        if constexpr (FULL) {
+          const bool is_pos = (ent[u].y == pos_off);
+          const float o1 = e1 * p.inv_Z1, o2 = e2 * p.inv_Z2;
+          const float rc1 = rcp_approx(o1 + p.c), rc2 = rcp_approx(o2 + p.c);
+          const float sc = p.inv_BT * m;
+          const float d1 = (is_pos ? -p.c : o1) * rc1 * sc;
+          const float d2 = (is_pos ? -p.c : o2) * rc2 * sc;
+          float t1, t2;
+          if (is_pos) {
+            t1 = logf(__fdiv_rn(o1, o1 + p.c));
+            t2 = logf(__fdiv_rn(o2, o2 + p.c));
+          } else {
+            t1 = -log1p_pos(fmaf(o1, p.inv_mPn, p.eps_over_mPn));
+            t2 = -log1p_pos(fmaf(o2, p.inv_mPn, p.eps_over_mPn));
+          }
+          ls = fmaf(t1, m, ls);
+          lt = fmaf(t2, m, lt);
+#pragma unroll
+          for (int n = 0; n < NV; ++n) {
+            g1[n] = fmaf(d1, w2f[n], g1[n]);
+            g2[n] = fmaf(d2, w1f[n], g2[n]);
+          }
+          if (store_out && ev[u] && j == 0) {
+            p.out_v1[lo + ent[u].y] = o1;
+            p.out_v2[lo + ent[u].y] = o2;
+          }
+        } else {
+          if (store_out && ev[u] && j == 0) {
+            p.out_v1[lo + ent[u].y] = e1;
+            p.out_v2[lo + ent[u].y] = e2;
+          }
+        }
+      }
+    };
+
+    long long base = lo;
+    long long r_next = (base + lane < seg_hi) ? p.idx[base + lane] : -1;
+    while (base < seg_hi) {
+      const long long r = r_next;
+      const long long pidx = base + lane;
+      const long long nbase = base + 32;
+      r_next = (nbase + lane < seg_hi) ? p.idx[nbase + lane] : -1;  // prefetch the next 32 indices
+      const bool inrange = pidx < seg_hi;
+      const bool valid = inrange && r >= p.row_begin && r < p.row_end;
+      const unsigned mask = __ballot_sync(kFull, valid);
+      if (valid) {
+        const int slot = (qtail + __popc(mask & ((1u << lane) - 1u))) & (kQueueCap - 1);
+        q[slot] = make_int2((int)(r - p.row_begin), (int)(pidx - lo));
+      } else if (inrange && store_out) {
+        p.out_v1[pidx] = 0.f;
+        p.out_v2[pidx] = 0.f;
+      }
+      qtail += __popc(mask);
+      __syncwarp();
+      while (qtail - qhead >= R * U) {
+        consume(R * U);
+        qhead += R * U;
+      }
+      __syncwarp();
+      base = nbase;
+    }
+    while (qtail - qhead > 0) {
+      const int avail = qtail - qhead;
+      consume(avail);
+      qhead += (avail < R * U) ? avail : R * U;
+    }
+    __syncwarp();
+
+    // ---- flush this (warp, anchor) partial ----
+#pragma unroll
+    for (int off = 16; off >= LPR; off >>= 1) {
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        g1[n] += __shfl_xor_sync(kFull, g1[n], off);
+        g2[n] += __shfl_xor_sync(kFull, g2[n], off);
+      }
+      ls += __shfl_xor_sync(kFull, ls, off);
+      lt += __shfl_xor_sync(kFull, lt, off);
+      se1 += __shfl_xor_sync(kFull, se1, off);
+      se2 += __shfl_xor_sync(kFull, se2, off);
+      cnt += __shfl_xor_sync(kFull, cnt, off);
+    }
+    float* slot = p.slots + ((long long)gw * p.maxseg + seg) * (2 * p.D + kSlotExtra);
+    if (g == 0) {
+      if constexpr (FULL) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int e0 = (j + LPR * i) * VEC;
+#pragma unroll
+          for (int t = 0; t < VEC; t += 4) {
+            *reinterpret_cast<float4*>(slot + e0 + t) =
+                make_float4(g1[i * VEC + t], g1[i * VEC + t + 1], g1[i * VEC + t + 2], g1[i * VEC + t + 3]);
+            *reinterpret_cast<float4*>(slot + p.D + e0 + t) =
+                make_float4(g2[i * VEC + t], g2[i * VEC + t + 1], g2[i * VEC + t + 2], g2[i * VEC + t + 3]);
+          }
+        }
+      }
+      if (j == 0) {
+        *reinterpret_cast<float4*>(slot + 2 * p.D) = make_float4(ls, lt, se1, se2);
+        *reinterpret_cast<float4*>(slot + 2 * p.D + 4) = make_float4(cnt, 0.f, 0.f, 0.f);
+      }
+    }
+    lo = seg_hi;
+    ++seg;
+  }
+}
+
+// One CTA per anchor: fixed-order sum of the warp partials that intersect the anchor's K1 pairs; the last
+// CTA to finish folds the per-anchor scalars into result[] (also in fixed order) -> bit-reproducible.
+__global__ void __launch_bounds__(256) crd_finalize_kernel(const FinalizeParams f) {
+  const int b = blockIdx.x;
+  const long long P = (long long)f.B * f.K1;
+  const long long p0 = (long long)b * f.K1, p1 = p0 + f.K1;
+  long long first = (p0 * f.NW) / P;
+  while (first > 0 && (P * first) / f.NW > p0) --first;
+  while (first + 1 < f.NW && (P * (first + 1)) / f.NW <= p0) ++first;
+  const int slot_w = 2 * f.D + kSlotExtra;
+  const int ncols = 2 * f.D;
+  for (int col = threadIdx.x; col < ncols + 5; col += blockDim.x) {
+    if (!f.full && col < ncols) continue;
+    double acc = 0.0;
+    for (long long w = first; w < f.NW; ++w) {
+      const long long lo = (P * w) / f.NW;
+      if (lo >= p1) break;
+      const long long hi = (P * (w + 1)) / f.NW;
+      if (hi <= p0 || hi <= lo) continue;
+      const int seg = b - (int)(lo / f.K1);
+      acc += (double)f.slots[(w * f.maxseg + seg) * slot_w + col];
+    }
+    if (col < f.D) f.grad_v1[(long long)b * f.D + col] = (float)acc;
+    else if (col < ncols) f.grad_v2[(long long)b * f.D + (col - f.D)] = (float)acc;
+    else f.anchor_part[b * 8 + (col - ncols)] = acc;
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(f.ticket, 1u);
+    is_last = (t == (unsigned)(f.B - 1));
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < 5) {
+      double s = 0.0;
+      for (int a = 0; a < f.B; ++a) s += __ldcg(&f.anchor_part[a * 8 + threadIdx.x]);
+      f.result[threadIdx.x] = (threadIdx.x < 2) ? (f.full ? -s / (double)f.B : 0.0) : s;
+    } else if (threadIdx.x < 8) {
+      f.result[threadIdx.x] = 0.0;
+    }
+  }
+}
+
+// Momentum update: one warp per (anchor, bank).  Canonical order: element e -> lane (e/4)%32, per-lane
+// fmaf fold in increasing e, xor butterfly 16..1 (bit-identical to oracle/crd_oracle.c canonical_sumsq).
+template <typename T>
+__global__ void __launch_bounds__(128) crd_update_kernel(char* bank1, char* bank2, long long row_stride_bytes,
+                                                         const float* v1, const float* v2, const long long* y,
+                                                         int B, int D, long long row_begin, long long row_end,
+                                                         float m, float om) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= 2 * B) return;
+  const int b = wid >> 1;
+  const int which = wid & 1;
+  const long long r = y[b];
+  if (r < row_begin || r >= row_end) return;
+  bool dup = false;
+  for (int b2 = b + 1 + lane; b2 < B; b2 += 32) dup |= (y[b2] == r);
+  if (__any_sync(0xffffffffu, dup)) return;  // a later occurrence of the same index wins
+  char* rowp = (which ? bank2 : bank1) + (r - row_begin) * row_stride_bytes;
+  const float* v = (which ? v2 : v1) + (long long)b * D;
+  constexpr int kMaxQ = 8;  // D <= 1024
+  float4 pv[kMaxQ];
+  float acc = 0.f;
+  const int nq = D >> 2;
+#pragma unroll
+  for (int t = 0; t < kMaxQ; ++t) {
+    const int qd = lane + 32 * t;
+    if (qd < nq) {
+      float4 mem;
+      if constexpr (sizeof(T) == 4) {
+        mem = *reinterpret_cast<const float4*>(rowp + (long long)qd * 16);
+      } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(rowp + (long long)qd * 8);
+        mem = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                          __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+      }
+      const float4 vv = *reinterpret_cast<const float4*>(v + qd * 4);
+      float4 pp;
+      pp.x = __fadd_rn(__fmul_rn(m, mem.x), __fmul_rn(om, vv.x));
+      pp.y = __fadd_rn(__fmul_rn(m, mem.y), __fmul_rn(om, vv.y));
+      pp.z = __fadd_rn(__fmul_rn(m, mem.z), __fmul_rn(om, vv.z));
+      pp.w = __fadd_rn(__fmul_rn(m, mem.w), __fmul_rn(om, vv.w));
+      acc = __fmaf_rn(pp.x, pp.x, acc);
+      acc = __fmaf_rn(pp.y, pp.y, acc);
+      acc = __fmaf_rn(pp.z, pp.z, acc);
+      acc = __fmaf_rn(pp.w, pp.w, acc);
+      pv[t] = pp;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+  const float nrm = __fsqrt_rn(acc);
+#pragma unroll
+  for (int t = 0; t < kMaxQ; ++t) {
+    const int qd = lane + 32 * t;
+    if (qd < nq) {
+      float4 o;
+      o.x = __fdiv_rn(pv[t].x, nrm); o.y = __fdiv_rn(pv[t].y, nrm);
+      o.z = __fdiv_rn(pv[t].z, nrm); o.w = __fdiv_rn(pv[t].w, nrm);
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(rowp + (long long)qd * 16) = o;
+      } else {
+        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(o.x, o.y);
+        const __nv_bfloat162 hi2 = __floats2bfloat162_rn(o.z, o.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const unsigned*>(&lo2);
+        u.y = *reinterpret_cast<const unsigned*>(&hi2);
+        *reinterpret_cast<uint2*>(rowp + (long long)qd * 8) = u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Alias-method draw: one Philox4x32-10 block per output (identical stream to oracle/crd_oracle.c).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned long long seed, unsigned long long ctr, unsigned out[4]) {
+  unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0u, c3 = 0u;
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256) alias_draw_kernel(const float* __restrict__ prob,
+                                                         const long long* __restrict__ alias, long long n,
+                                                         long long count, unsigned long long seed,
+                                                         unsigned long long offset, const long long* __restrict__ y,
+                                                         long long K1, long long* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    if (y != nullptr && (i % K1) == 0) {
+      out[i] = y[i / K1];
+      continue;
+    }
+    unsigned r[4];
+    philox4x32_10(seed, offset + (unsigned long long)i, r);
+    const unsigned long long bits = ((unsigned long long)r[0] << 32) | (unsigned long long)r[1];
+    const long long kk = (long long)__umul64hi(bits, (unsigned long long)n);
+    const float u = (float)(r[2] >> 8) * 5.9604644775390625e-08f;
+    out[i] = (u < prob[kk]) ? kk : alias[kk];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------
+using ScoreKernel = void (*)(const ScoreParams);
+struct Variant {
+  ScoreKernel full, sums;
+  int bps;
+};
+
+template <typename T, int LPR, int CH, int U, int BPS>
+static Variant make_variant() {
+  return Variant{crd_score_kernel<T, LPR, CH, U, BPS, true>, crd_score_kernel<T, LPR, CH, U, BPS, false>, BPS};
+}
+
+// (dtype, D, variant) -> kernel.  variant 0 is the tuned default for that D.
+static bool pick_variant(int dtype, int D, int variant, Variant* out) {
+  if (dtype == CRDPN_F32) {
+    switch (D) {
+      case 32:
+        *out = make_variant<float, 8, 1, 4, 2>(); return variant == 0;
+      case 64:
+        if (variant == 0 || variant == 1) { *out = make_variant<float, 8, 2, 4, 2>(); return true; }
+        if (variant == 2) { *out = make_variant<float, 16, 1, 4, 2>(); return true; }
+        return false;
+      case 128:
+        if (variant == 0 || variant == 1) { *out = make_variant<float, 16, 2, 4, 2>(); return true; }
+        if (variant == 2) { *out = make_variant<float, 8, 4, 2, 1>(); return true; }
+        if (variant == 3) { *out = make_variant<float, 32, 1, 4, 2>(); return true; }
+        if (variant == 4) { *out = make_variant<float, 32, 1, 8, 2>(); return true; }
+        if (variant == 5) { *out = make_variant<float, 16, 2, 2, 3>(); return true; }
+        if (variant == 6) { *out = make_variant<float, 8, 4, 2, 2>(); return true; }
+        if (variant == 7) { *out = make_variant<float, 16, 2, 8, 1>(); return true; }
+        return false;
+      case 256:
+        if (variant == 0 || variant == 1) { *out = make_variant<float, 32, 2, 4, 2>(); return true; }
+        if (variant == 2) { *out = make_variant<float, 16, 4, 2, 1>(); return true; }
+        return false;
+      case 512:
+        *out = make_variant<float, 32, 4, 2, 1>(); return variant == 0;
+      default: return false;
+    }
+  } else if (dtype == CRDPN_BF16) {
+    switch (D) {
+      case 64:
+        *out = make_variant<__nv_bfloat16, 8, 1, 4, 2>(); return variant == 0;
+      case 128:
+        if (variant == 0 || variant == 1) { *out = make_variant<__nv_bfloat16, 8, 2, 4, 2>(); return true; }
+        if (variant == 2) { *out = make_variant<__nv_bfloat16, 16, 1, 8, 2>(); return true; }
+        if (variant == 3) { *out = make_variant<__nv_bfloat16, 4, 4, 2, 2>(); return true; }
+        return false;
+      case 256:
+        if (variant == 0 || variant == 1) { *out = make_variant<__nv_bfloat16, 16, 2, 4, 2>(); return true; }
+        if (variant == 2) { *out = make_variant<__nv_bfloat16, 8, 4, 2, 1>(); return true; }
+        return false;
+      case 512:
+        *out = make_variant<__nv_bfloat16, 32, 2, 4, 2>(); return variant == 0;
+      default: return false;
+    }
+  }
+  return false;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int maxseg_for(long long P, long long NW, long long K1) {
+  const long long len_max = (P + NW - 1) / NW;
+  return (int)((len_max + K1 - 1) / K1 + 1);
+}
+
+static size_t workspace_bytes_for(long long B, long long K1, long long D, long long NW) {
+  const long long P = B * K1;
+  const size_t head = 16 + align_up((size_t)B * 8 * sizeof(double), 16);
+  const size_t slots = (size_t)NW * (size_t)maxseg_for(P, NW, K1) * (size_t)(2 * D + kSlotExtra) * sizeof(float);
+  return head + slots;
+}
+
+}  // namespace crdpn
+
+using namespace crdpn;
+
+extern "C" int crdpn_crd_workspace_bytes(int64_t B, int64_t K1, int64_t D, int device, size_t* bytes) {
+  if (!bytes || B <= 0 || K1 <= 0 || D <= 0) return fail(CRDPN_E_BADARG, "crdpn_crd_workspace_bytes: bad argument");
+  DeviceInfo di;
+  int rc = device_info(device, &di);
+  if (rc) return rc;
+  *bytes = workspace_bytes_for(B, K1, D, (long long)di.sms * kMaxBlocksPerSM * kWarps);
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
+                               const float* v1, const float* v2, const int64_t* contrast_idx,
+                               int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                               int64_t row_begin, int64_t row_end,
+                               float T, float Z1, float Z2, float eps,
+                               float* out_v1, float* out_v2, double* result, float* grad_v1, float* grad_v2,
+                               void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  if (!v1 || !v2 || !contrast_idx || !result || !workspace)
+    return fail(CRDPN_E_BADARG, "crdpn_crd_score: null pointer");
+  if (B <= 0 || K1 <= 0 || D <= 0 || n_data <= 0 || row_end < row_begin || !(T > 0.f))
+    return fail(CRDPN_E_BADARG, "crdpn_crd_score: bad size");
+  if (row_end > row_begin && (!bank1 || !bank2)) return fail(CRDPN_E_BADARG, "crdpn_crd_score: null bank");
+  if ((out_v1 == nullptr) != (out_v2 == nullptr)) return fail(CRDPN_E_BADARG, "crdpn_crd_score: out_v1/out_v2 must both be set or both null");
+  if (B * K1 >= (1ll << 31) || row_end - row_begin >= (1ll << 31))
+    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_score: B*K1 and local rows must be < 2^31");
+  const bool full = (Z1 > 0.f && Z2 > 0.f);
+  if (full && (!grad_v1 || !grad_v2)) return fail(CRDPN_E_BADARG, "crdpn_crd_score: null grad buffer");
+  const size_t esz = (bank_dtype == CRDPN_BF16) ? 2 : 4;
+  if (bank_dtype != CRDPN_F32 && bank_dtype != CRDPN_BF16) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_score: bank dtype");
+  if (((uintptr_t)bank1 | (uintptr_t)bank2 | (uintptr_t)v1 | (uintptr_t)v2 | (uintptr_t)workspace) & 15 ||
+      ((size_t)row_stride * esz) % 16 != 0 || (D * 4) % 16 != 0)
+    return fail(CRDPN_E_ALIGN, "crdpn_crd_score: banks, embeddings, workspace and row pitch must be 16-byte aligned");
+  Variant var;
+  if (!pick_variant(bank_dtype, (int)D, variant, &var))
+    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_score: no kernel for this (dtype, feat_dim, variant); feat_dim in {32,64,128,256,512}");
+
+  int device = 0;
+  CRDPN_CUDA(cudaGetDevice(&device));
+  DeviceInfo di;
+  int rc = device_info(device, &di);
+  if (rc) return rc;
+  const int grid = di.sms * var.bps;
+  const long long NW = (long long)grid * kWarps;
+  const long long P = B * K1;
+  const size_t need = workspace_bytes_for(B, K1, D, NW);
+  if (workspace_bytes < need) return fail(CRDPN_E_WORKSPACE, "crdpn_crd_score: workspace too small");
+
+  char* ws = (char*)workspace;
+  unsigned int* ticket = (unsigned int*)ws;
+  double* anchor_part = (double*)(ws + 16);
+  float* slots = (float*)(ws + 16 + align_up((size_t)B * 8 * sizeof(double), 16));
+
+  const double Kd = (double)(K1 - 1);
+  const double Pn = 1.0 / (double)n_data;
+  const float mPn_f = (float)(Kd * Pn);
+  const float c_f = (float)(Kd * Pn + (double)eps);
+
+  ScoreParams sp;
+  sp.bank1 = (const char*)bank1;
+  sp.bank2 = (const char*)bank2;
+  sp.row_stride_bytes = (long long)row_stride * (long long)esz;
+  sp.v1 = v1; sp.v2 = v2;
+  sp.idx = (const long long*)contrast_idx;
+  sp.B = (int)B; sp.K1 = (int)K1; sp.D = (int)D;
+  sp.row_begin = row_begin; sp.row_end = row_end;
+  sp.k_exp = (float)(1.4426950408889634 / (double)T);
+  sp.inv_Z1 = full ? (float)(1.0 / (double)Z1) : 0.f;
+  sp.inv_Z2 = full ? (float)(1.0 / (double)Z2) : 0.f;
+  sp.c = c_f;
+  sp.inv_mPn = (K1 > 1) ? (float)(1.0 / (double)mPn_f) : 0.f;
+  sp.eps_over_mPn = (K1 > 1) ? (float)(((double)c_f - (double)mPn_f) / (double)mPn_f) : 0.f;
+  sp.inv_BT = (float)(1.0 / ((double)B * (double)T));
+  sp.out_v1 = out_v1; sp.out_v2 = out_v2;
+  sp.slots = slots;
+  sp.maxseg = maxseg_for(P, NW, K1);
+  sp.ticket = ticket;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  (full ? var.full : var.sums)<<<grid, kThreads, 0, st>>>(sp);
+  CRDPN_LAUNCH_CHECK("crd_score_kernel");
+
+  FinalizeParams fp;
+  fp.slots = slots; fp.maxseg = sp.maxseg; fp.NW = NW;
+  fp.B = (int)B; fp.K1 = (int)K1; fp.D = (int)D; fp.full = full ? 1 : 0;
+  fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2;
+  fp.anchor_part = anchor_part; fp.result = result; fp.ticket = ticket;
+  crd_finalize_kernel<<<(int)B, 256, 0, st>>>(fp);
+  CRDPN_LAUNCH_CHECK("crd_finalize_kernel");
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+                                         const float* v1, const float* v2, const int64_t* y,
+                                         int64_t B, int64_t D, int64_t row_begin, int64_t row_end,
+                                         float momentum, float one_minus_momentum, void* stream) {
+  if (!v1 || !v2 || !y) return fail(CRDPN_E_BADARG, "crdpn_crd_momentum_update: null pointer");
+  if (B <= 0 || D <= 0 || row_end < row_begin) return fail(CRDPN_E_BADARG, "crdpn_crd_momentum_update: bad size");
+  if (row_end == row_begin) return CRDPN_OK;
+  if (!bank1 || !bank2) return fail(CRDPN_E_BADARG, "crdpn_crd_momentum_update: null bank");
+  if (D % 4 != 0 || D > 1024) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_momentum_update: feat_dim must be a multiple of 4, <= 1024");
+  const size_t esz = (bank_dtype == CRDPN_BF16) ? 2 : 4;
+  if (bank_dtype != CRDPN_F32 && bank_dtype != CRDPN_BF16) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_momentum_update: bank dtype");
+  if (((uintptr_t)bank1 | (uintptr_t)bank2 | (uintptr_t)v1 | (uintptr_t)v2) & 15 || ((size_t)row_stride * esz) % 16 != 0)
+    return fail(CRDPN_E_ALIGN, "crdpn_crd_momentum_update: 16-byte alignment required");
+  const int warps = 4;
+  const int grid = (int)((2 * B + warps - 1) / warps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bank_dtype == CRDPN_F32)
+    crd_update_kernel<float><<<grid, warps * 32, 0, st>>>((char*)bank1, (char*)bank2, (long long)row_stride * 4, v1, v2,
+                                                         (const long long*)y, (int)B, (int)D, row_begin, row_end,
+                                                         momentum, one_minus_momentum);
+  else
+    crd_update_kernel<__nv_bfloat16><<<grid, warps * 32, 0, st>>>((char*)bank1, (char*)bank2, (long long)row_stride * 2, v1, v2,
+                                                                 (const long long*)y, (int)B, (int)D, row_begin, row_end,
+                                                                 momentum, one_minus_momentum);
+  CRDPN_LAUNCH_CHECK("crd_update_kernel");
+  return CRDPN_OK;
+}
+
+static int alias_draw_impl(const float* prob, const int64_t* alias, int64_t n, int64_t count, uint64_t seed,
+                           uint64_t offset, const int64_t* y, int64_t K1, int64_t* out, void* stream) {
+  if (!prob || !alias || !out || n <= 0 || count < 0) return fail(CRDPN_E_BADARG, "crdpn_alias_draw: bad argument");
+  if (count == 0) return CRDPN_OK;
+  int device = 0;
+  CRDPN_CUDA(cudaGetDevice(&device));
+  DeviceInfo di;
+  int rc = device_info(device, &di);
+  if (rc) return rc;
+  long long blocks = (count + 255) / 256;
+  const long long cap = (long long)di.sms * 8;
+  if (blocks > cap) blocks = cap;
+  alias_draw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(prob, (const long long*)alias, n, count, seed, offset,
+                                                                  (const long long*)y, K1, (long long*)out);
+  CRDPN_LAUNCH_CHECK("alias_draw_kernel");
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_alias_draw(const float* prob, const int64_t* alias, int64_t n, int64_t count,
+                                uint64_t seed, uint64_t offset, int64_t* out, void* stream) {
+  return alias_draw_impl(prob, alias, n, count, seed, offset, nullptr, 1, out, stream);
+}
+
+extern "C" int crdpn_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t n, const int64_t* y,
+                                         int64_t B, int64_t K1, uint64_t seed, uint64_t offset, int64_t* out,
+                                         void* stream) {
+  if (!y || B <= 0 || K1 <= 0) return fail(CRDPN_E_BADARG, "crdpn_alias_draw_contrast: bad argument");
+  return alias_draw_impl(prob, alias, n, B * K1, seed, offset, y, K1, out, stream);
+}

@@ -1,0 +1,106 @@
+/*
+ * crdpn_b200.h -- C ABI of libcrdpn_b200.so: the B200 (sm_100a) hot path of 3DAug-Pose's contrastive
+ * distillation step: CRD memory-bank NCE (score + loss + closed-form backward + momentum update +
+ * alias-method negative sampling) and the teacher's PointNet encoder (shared MLP + max-pool).
+ *
+ * The reference (/root/reference) is pure Python/PyTorch and has NO plugin / FFI interface; its only
+ * extension seam is duck-typing on nn.Module.  Each entry point below therefore names
+ * the reference interface (file:line) whose work it performs; the Python classes that call them mirror
+ * those interfaces one-to-one (package crd.py / pointnet.py) and INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.  All *device* pointers unless marked host.
+ *   - the caller owns every buffer (banks, workspaces, outputs); nothing is allocated or freed here.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, no hidden sync.
+ *   - return 0 on success; CRDPN_E_* (>= 1000) for argument errors; otherwise the cudaError_t of the
+ *     failed runtime call.  crdpn_last_error() returns a static description of the last failure of the
+ *     calling thread.
+ *   - bank shard: rows [row_begin,row_end) of the global [n_data, D] bank are resident; bank pointers
+ *     address local row 0 == global row `row_begin`; contrast entries outside the shard are skipped.
+ */
+#ifndef CRDPN_B200_H_
+#define CRDPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRDPN_ABI_VERSION 1
+
+enum {
+  CRDPN_OK = 0,
+  CRDPN_E_BADARG = 1000,      /* null pointer / non-positive size */
+  CRDPN_E_UNSUPPORTED = 1001, /* feature dimension or dtype without a compiled kernel */
+  CRDPN_E_WORKSPACE = 1002,   /* workspace too small */
+  CRDPN_E_ALIGN = 1003        /* pointer / stride not 16-byte aligned */
+};
+
+enum { CRDPN_F32 = 0, CRDPN_BF16 = 1 };
+
+int crdpn_abi_version(void);
+const char* crdpn_last_error(void);
+/* number of kernels this library has launched since load (process-wide); feeds bench.py's gpu_launches */
+uint64_t crdpn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Alias-method negative sampler.
+ * Replaces: AliasMethod.__init__ / AliasMethod.draw of the published CRD algorithm (crd/memory.py in
+ * HobbitLong/RepDistiller -- NOT vendored by the reference); in the reference the
+ * consumer would be the KD loop at KD/common/base_class.py:339-387.
+ * ------------------------------------------------------------------------------------------------- */
+/* HOST pointers. Vose stack pairing in fp32; prob_out[n] fp32, alias_out[n] int64. */
+int crdpn_alias_build(const float* probs_host, int64_t n, float* prob_out_host, int64_t* alias_out_host);
+/* out[i] = draw(Philox4x32-10 block (seed, offset+i)), i < count. */
+int crdpn_alias_draw(const float* prob, const int64_t* alias, int64_t n, int64_t count,
+                     uint64_t seed, uint64_t offset, int64_t* out, void* stream);
+/* contrast_idx[B,K1]: as crdpn_alias_draw over B*K1 entries, then column 0 <- y[b]
+ * (ContrastMemory.forward when idx is None). */
+int crdpn_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t n, const int64_t* y,
+                              int64_t B, int64_t K1, uint64_t seed, uint64_t offset, int64_t* out,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * CRD scoring: fused gather . dot . exp . NCE loss . closed-form backward.  Never materialises the
+ * B x K1 x D gathered tensor.
+ * Replaces: ContrastMemory.forward (index_select + bmm + exp + div) and ContrastLoss.forward of the
+ * published CRD algorithm and their autograd backward; reference insertion point
+ * KD/vision/vanilla/vanilla_kd.py:158-160, called at KD/common/base_class.py:387.
+ *
+ *   s1[b,k] = <bank2[idx[b,k]], v1[b]>   s2[b,k] = <bank1[idx[b,k]], v2[b]>     e = exp(s/T)
+ *   mode (Z1>0 && Z2>0): o = e/Z, loss_s/loss_t, grad_v1/grad_v2 (for upstream gradient 1)
+ *   mode (otherwise)   : only sum(e1), sum(e2), count  (first call: Z = mean(e) * n_data)
+ *
+ * bank1/bank2: [row_end-row_begin, D] rows of `bank_dtype`, row_stride in ELEMENTS (both banks share it;
+ *              an interleaved [N,2,D] allocation is bank2 = bank1 + D, row_stride = 2D).
+ * v1,v2 [B,D] f32; contrast_idx [B,K1] int64 (column 0 = positive); K = K1-1.
+ * out_v1/out_v2: optional [B,K1] f32 (o, or raw e in sum mode; 0 for entries outside the shard).
+ * result: 8 doubles {loss_s, loss_t, sum_e1, sum_e2, count, 0,0,0}.  grad_v1/grad_v2 [B,D] f32 (written
+ * only in full mode).  variant: 0 = default kernel; other values select tuning variants (bench only).
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_crd_workspace_bytes(int64_t B, int64_t K1, int64_t D, int device, size_t* bytes);
+int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
+                    const float* v1, const float* v2, const int64_t* contrast_idx,
+                    int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                    int64_t row_begin, int64_t row_end,
+                    float T, float Z1, float Z2, float eps,
+                    float* out_v1, float* out_v2, double* result, float* grad_v1, float* grad_v2,
+                    void* workspace, size_t workspace_bytes, int variant, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Momentum update of both banks (ContrastMemory.forward, torch.no_grad block: index_select, mul_, add_,
+ * pow/sum/pow, div, index_copy_).  bank[y] <- normalise(m*bank[y] + (1-m)*v), canonical reduction order
+ * (oracle/crd_oracle.c), last duplicate of y wins, rows outside the shard untouched.
+ * Must be enqueued after crdpn_crd_score on the same stream (scores read the pre-update banks).
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+                              const float* v1, const float* v2, const int64_t* y,
+                              int64_t B, int64_t D, int64_t row_begin, int64_t row_end,
+                              float momentum, float one_minus_momentum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRDPN_B200_H_ */
