@@ -19,6 +19,8 @@ _SIGNATURES = {
     "crdpn_abi_version": (c_int, []),
     "crdpn_last_error": (ctypes.c_char_p, []),
     "crdpn_launch_count": (c_uint64, []),
+    "crdpn_timing_enable": (c_int, [c_int]),
+    "crdpn_timing_read": (c_int, [c_int, POINTER(c_double), POINTER(c_uint64)]),
     "crdpn_alias_build": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "crdpn_alias_draw": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),
     "crdpn_alias_draw_contrast": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_uint64,

@@ -38,6 +38,17 @@ inline int cuda_fail(cudaError_t e, const char* where) {
     if (_e != cudaSuccess) return ::crdpn::cuda_fail(_e, name);     \
   } while (0)
 
+// optional per-launch event bracketing of the dominant kernels (see crdpn_timing_enable)
+extern std::atomic<int> g_timing_on;
+void timing_mark(int kernel_id, bool begin, cudaStream_t st);
+struct ScopedKernelTimer {
+  int id; cudaStream_t st; bool on;
+  ScopedKernelTimer(int id_, cudaStream_t st_) : id(id_), st(st_), on(g_timing_on.load(std::memory_order_relaxed) != 0) {
+    if (on) timing_mark(id, true, st);
+  }
+  ~ScopedKernelTimer() { if (on) timing_mark(id, false, st); }
+};
+
 struct DeviceInfo {
   int sms;
   int max_smem_optin;

@@ -625,7 +625,10 @@ extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row
   sp.ticket = ticket;
 
   cudaStream_t st = (cudaStream_t)stream;
-  (full ? var.full : var.sums)<<<grid, kThreads, 0, st>>>(sp);
+  {
+    ScopedKernelTimer tm(CRDPN_K_CRD_SCORE, st);
+    (full ? var.full : var.sums)<<<grid, kThreads, 0, st>>>(sp);
+  }
   CRDPN_LAUNCH_CHECK("crd_score_kernel");
 
   FinalizeParams fp;

@@ -9,6 +9,35 @@ namespace crdpn {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 
+std::atomic<int> g_timing_on{0};
+namespace {
+struct EventPair { cudaEvent_t a = nullptr, b = nullptr; };
+std::mutex g_tmu;
+std::vector<EventPair> g_pairs[CRDPN_K_COUNT];
+size_t g_used[CRDPN_K_COUNT] = {0};
+constexpr size_t kMaxPairs = 1 << 15;
+}  // namespace
+
+void timing_mark(int kid, bool begin, cudaStream_t st) {
+  if (kid < 0 || kid >= CRDPN_K_COUNT) return;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  auto& v = g_pairs[kid];
+  size_t& used = g_used[kid];
+  if (begin) {
+    if (used >= kMaxPairs) return;
+    if (used == v.size()) {
+      EventPair ep;
+      if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return;
+      v.push_back(ep);
+    }
+    cudaEventRecord(v[used].a, st);
+  } else {
+    if (used >= v.size()) return;
+    cudaEventRecord(v[used].b, st);
+    ++used;
+  }
+}
+
 int device_info(int device, DeviceInfo* out) {
   static std::mutex mu;
   static DeviceInfo cache[64];
@@ -40,6 +69,27 @@ using namespace crdpn;
 extern "C" int crdpn_abi_version(void) { return CRDPN_ABI_VERSION; }
 extern "C" const char* crdpn_last_error(void) { return g_err; }
 extern "C" uint64_t crdpn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int crdpn_timing_enable(int on) {
+  g_timing_on.store(on ? 1 : 0);
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_timing_read(int kid, double* total_ms, uint64_t* launches) {
+  if (kid < 0 || kid >= CRDPN_K_COUNT || !total_ms || !launches) return fail(CRDPN_E_BADARG, "crdpn_timing_read: bad argument");
+  std::lock_guard<std::mutex> lk(g_tmu);
+  double tot = 0.0;
+  for (size_t i = 0; i < g_used[kid]; ++i) {
+    CRDPN_CUDA(cudaEventSynchronize(g_pairs[kid][i].b));
+    float ms = 0.f;
+    CRDPN_CUDA(cudaEventElapsedTime(&ms, g_pairs[kid][i].a, g_pairs[kid][i].b));
+    tot += (double)ms;
+  }
+  *total_ms = tot;
+  *launches = (uint64_t)g_used[kid];
+  g_used[kid] = 0;
+  return CRDPN_OK;
+}
 
 // Vose alias tables with the stack pairing of the published CRD sampler (AliasMethod.__init__): fp32
 // arithmetic throughout; probabilities are normalised only when their sum exceeds 1.

@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract in the build prompt; BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one CRD memory-bank NCE step (score + loss + closed-form backward + momentum update) over one
+synthetic batch.  Headline workload (BASELINE.json configs[3] on one GPU, the HBM-honest case because the
+banks are 8x larger than L2): B=46 anchors, D=128, K=65536 negatives, N=1M rows x 2 banks, fp32, tau=0.07.
+The JSON line also carries configs[0] (B=46, K=16384, N=90k: L2-resident) and, once built, configs[1]
+(PointNet encoder, B=160, P=2500) under "also".
+
+metric = CRD negatives scored per second = 2*B*(K+1)/t  (both directions, positives included).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+HEADLINE = dict(B=46, D=128, K=65536, N=1_000_000, s_dim=2048, t_dim=1024, T=0.07, m=0.5)
+CONFIG0 = dict(B=46, D=128, K=16384, N=90_000, s_dim=2048, t_dim=1024, T=0.07, m=0.5)
+SEED = 46
+
+
+def workload_name(c, R=1):
+    return f"crd_B{c['B']}_D{c['D']}_K{c['K']}_N{c['N']}x2_fp32_tau{c['T']}" + (f"_shards{R}" if R > 1 else "")
+
+
+def algorithmic_bytes(c):
+    """row gathers of both banks + int64 contrast indices read once + update r/w."""
+    B, K1, D = c["B"], c["K"] + 1, c["D"]
+    return 2 * B * K1 * D * 4 + B * K1 * 8 + 2 * 2 * B * D * 4
+
+
+def scores_per_step(c):
+    return 2 * c["B"] * (c["K"] + 1)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    _NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+              0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+              0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def synth_inputs(c, torch, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(SEED)
+    B, K1 = c["B"], c["K"] + 1
+    f_s = torch.randn(B, c["s_dim"], generator=g)
+    f_t = torch.randn(B, c["t_dim"], generator=g)
+    y = torch.randperm(c["N"], generator=g)[:B]
+    cidx = torch.randint(0, c["N"], (B, K1), generator=g)
+    cidx[:, 0] = y
+    out = [f_s, f_t, y, cidx]
+    if pin:
+        out = [t.pin_memory() for t in out]
+    return out
+
+
+def make_opt(c):
+    return type("Opt", (), dict(s_dim=c["s_dim"], t_dim=c["t_dim"], feat_dim=c["D"], n_data=c["N"], nce_k=c["K"],
+                                nce_t=c["T"], nce_m=c["m"]))()
+
+
+def time_crd_resident(pkg, torch, dev, c, steps, warmup, flush_l2=False, variant=0, interleave=True, dist=None):
+    """Device-resident inputs; returns dict(total_ms, kernel_ms_avg, launches)."""
+    torch.manual_seed(SEED)
+    crit = pkg.CRDLoss(make_opt(c), interleave=interleave).to(dev)
+    crit.contrast.variant = variant
+    f_s, f_t, y, cidx = [t.to(dev) for t in synth_inputs(c, torch)]
+    with torch.no_grad():
+        v1 = crit.embed_s(f_s).contiguous()
+        v2 = crit.embed_t(f_t).contiguous()
+    mem = crit.contrast
+    mem._freeze_z(v1, v2, cidx)
+    hp = mem._host_params()
+    lib = pkg._native.lib()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
+
+    def step():
+        mem._score(v1, v2, cidx, hp.Z1, hp.Z2)
+        mem._update(v1, v2, y)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    lib.crdpn_timing_enable(1)
+    tot = ctypes.c_double()
+    n = ctypes.c_uint64()
+    lib.crdpn_timing_read(0, ctypes.byref(tot), ctypes.byref(n))  # reset
+    l0 = pkg._native.launch_count()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if flush_l2:
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            e0.record()
+            step()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+    else:
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        total = e0.elapsed_time(e1)
+    if dist is not None:
+        dist.barrier()
+    l1 = pkg._native.launch_count()
+    lib.crdpn_timing_read(0, ctypes.byref(tot), ctypes.byref(n))
+    lib.crdpn_timing_enable(0)
+    return dict(total_ms=total, kernel_ms_avg=tot.value / max(n.value, 1), kernel_launches=int(n.value),
+                launches=l1 - l0)
+
+
+def time_crd_e2e(pkg, torch, dev, c, steps, warmup):
+    """Public API, pinned HOST inputs: H2D of (f_s, f_t, idx, contrast_idx) + forward + backward + D2H of the loss."""
+    torch.manual_seed(SEED)
+    crit = pkg.CRDLoss(make_opt(c)).to(dev)
+    host = synth_inputs(c, torch, pin=True)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def step():
+        f_s, f_t, y, cidx = [t.to(dev, non_blocking=True) for t in host]
+        f_s.requires_grad_()
+        crit.zero_grad(set_to_none=True)
+        loss = crit(f_s, f_t, y, cidx)
+        loss.backward()
+        return loss.item()  # D2H read of the step's result
+
+    for _ in range(max(warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    ms = max(e0.elapsed_time(e1), wall)  # host-side stalls (the .item() sync) count
+    return dict(ms_per_step=ms / steps, h2d=h2d, d2h=4)
+
+
+def cpu_stock_crd(c, torch, steps, warmup, sample_B=None):
+    """CPU baseline: the stock index_select+bmm formulation (oracle port) on the host cores."""
+    from oracle.crd_oracle import StockCRD
+    cc = dict(c)
+    if sample_B:
+        cc["B"] = sample_B
+    stock = StockCRD(c["s_dim"], c["t_dim"], c["D"], c["N"], c["K"], c["T"], c["m"], seed=SEED)
+    f_s, f_t, y, cidx = synth_inputs(cc, torch)
+    f_s.requires_grad_()
+    for _ in range(warmup):
+        stock.step(f_s, f_t, y, cidx)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        stock.step(f_s, f_t, y, cidx)
+    dt = (time.perf_counter() - t0) / steps
+    return scores_per_step(cc) / dt, dt, cc["B"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference-side CPU implementation of the path on the host cores.
+
+    The reference ships no CRD code and is not an installable package, so this arm runs the
+    oracle's stock-formulation port (oracle/crd_oracle.py StockCRD) -- kind "port"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = HEADLINE
+    sample_B = int(os.environ.get("CRDPN_REF_SAMPLE_B", "8"))
+    val, dt, b = cpu_stock_crd(c, torch, args.steps, args.warmup, sample_B=sample_B)
+    sample = f"{b} of {c['B']} anchors per step (all K+1={c['K']+1} entries each, full N), fwd+bwd+update"
+    line = {
+        "impl": "reference", "metric": "crd_negatives_scored_per_sec", "value": val, "unit": "scores/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(c), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "scores/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_own(args):
+    import torch
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pkg = ge.load_package()
+    pkg._native.lib()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    hbm_peak, tf_peak, peak_kind = measured_peaks()
+
+    if world > 1:
+        from bench_multi import run_multi  # sharded banks, one NCCL exchange per step
+        run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind)
+        return
+
+    c = HEADLINE
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    r = time_crd_resident(pkg, torch, dev, c, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_step = r["total_ms"] / args.steps
+    value = scores_per_step(c) / (ms_step * 1e-3)
+    abytes = algorithmic_bytes(c)
+    achieved = abytes / (r["kernel_ms_avg"] * 1e-3) / 1e9
+    if os.environ.get("CRDPN_BENCH_QUICK"):  # profiling runs: just the timed loop
+        print(json.dumps({"quick": True, "ms_per_step": ms_step, "value": value, "kernel_ms": r["kernel_ms_avg"],
+                          "achieved_gbs": achieved}))
+        return
+    e2e = time_crd_e2e(pkg, torch, dev, c, max(args.steps // 4, 5), args.warmup)
+
+    also = {}
+    r0 = time_crd_resident(pkg, torch, dev, CONFIG0, args.steps, args.warmup, flush_l2=True)
+    also["config0_l2_flushed"] = {
+        "workload": workload_name(CONFIG0), "ms_per_step": r0["total_ms"] / args.steps,
+        "value": scores_per_step(CONFIG0) / (r0["total_ms"] / args.steps * 1e-3), "unit": "scores/s",
+        "kernel_ms": r0["kernel_ms_avg"], "achieved_gbs": algorithmic_bytes(CONFIG0) / (r0["kernel_ms_avg"] * 1e-3) / 1e9,
+        "note": "banks (92 MB) fit L2; 256 MB written between steps to evict them"}
+    r0w = time_crd_resident(pkg, torch, dev, CONFIG0, args.steps, args.warmup, flush_l2=False)
+    also["config0_l2_warm"] = {
+        "workload": workload_name(CONFIG0), "ms_per_step": r0w["total_ms"] / args.steps,
+        "value": scores_per_step(CONFIG0) / (r0w["total_ms"] / args.steps * 1e-3), "unit": "scores/s",
+        "kernel_ms": r0w["kernel_ms_avg"], "achieved_gbs": algorithmic_bytes(CONFIG0) / (r0w["kernel_ms_avg"] * 1e-3) / 1e9,
+        "note": "rows served from L2 (each row reused ~8x per step): above-HBM figure is expected"}
+    if os.environ.get("CRDPN_BENCH_VARIANTS"):
+        sweep = {}
+        for v in [int(x) for x in os.environ["CRDPN_BENCH_VARIANTS"].split(",")]:
+            for il in (True, False):
+                rv = time_crd_resident(pkg, torch, dev, c, max(args.steps // 2, 10), 3, variant=v, interleave=il)
+                sweep[f"v{v}_{'il' if il else 'sep'}"] = round(rv["kernel_ms_avg"], 4)
+        also["variant_sweep_kernel_ms"] = sweep
+    try:
+        from bench_pointnet import bench_pointnet
+        also["pointnet"] = bench_pointnet(pkg, torch, dev, args, tf_peak, peak_kind)
+    except ImportError:
+        pass
+
+    # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_B = int(os.environ.get("CRDPN_REF_SAMPLE_B", "8"))
+    cval, cdt, cb = cpu_stock_crd(c, torch, 2, 1, sample_B=sample_B)
+
+    line = {
+        "metric": "crd_negatives_scored_per_sec", "value": value, "unit": "scores/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(c), "B": c["B"], "D": c["D"], "K": c["K"], "N": c["N"], "banks": 2,
+                   "bank_layout": "interleaved [N,2,D] fp32", "l2": "inputs larger than L2 (1.02 GB of banks, random rows); no flush",
+                   "step": "score+loss+backward (1 fused pass) + finalize + momentum update"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_kind": peak_kind, "kernel": "crd_score_kernel",
+                     "kernel_ms": r["kernel_ms_avg"], "algorithmic_bytes": abytes},
+        "cpu_baseline": {"value": cval, "unit": "scores/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{cb} of {c['B']} anchors per step, full K and N, fwd+bwd+update, 2 steps ({cdt:.2f} s/step)"},
+        "e2e": {"value": scores_per_step(c) / (e2e["ms_per_step"] * 1e-3), "unit": "scores/s",
+                "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms_per_step"],
+                "api": "CRDLoss(f_s, f_t, idx, contrast_idx).backward() with pinned host inputs"},
+        "gpu_launches": r["launches"],
+        "clocks": clocks,
+        "also": also,
+    }
+    traffic = ROOT / "profiles" / "traffic.json"
+    if traffic.exists():
+        try:
+            line["roofline"]["traffic"] = json.loads(traffic.read_text()).get("crd_score_kernel_bytes_per_launch")
+        except Exception:
+            pass
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,13 @@ const char* crdpn_last_error(void);
 /* number of kernels this library has launched since load (process-wide); feeds bench.py's gpu_launches */
 uint64_t crdpn_launch_count(void);
 
+/* Measurement aid (bench.py's roofline): when enabled, every launch of a dominant kernel (CRDPN_K_*) is
+ * bracketed by cudaEventRecord on its own stream.  crdpn_timing_read synchronises those events, returns the
+ * summed device time and launch count since the last read, and resets.  Off by default; no effect on results. */
+enum { CRDPN_K_CRD_SCORE = 0, CRDPN_K_POINTNET_FWD = 1, CRDPN_K_COUNT = 2 };
+int crdpn_timing_enable(int on);
+int crdpn_timing_read(int kernel_id, double* total_ms, uint64_t* launches);
+
 /* ---------------------------------------------------------------------------------------------------
  * Alias-method negative sampler.
  * Replaces: AliasMethod.__init__ / AliasMethod.draw of the published CRD algorithm (crd/memory.py in

@@ -1,0 +1,341 @@
+"""GPU parity tests of the CRD hot path: CUDA kernels (through the C ABI / the CRDLoss module) vs the CPU oracle.
+
+Tolerances (BASELINE.json north_star): indices and memory-row updates bit-exact; loss, gradients and
+scores within 1e-4 relative in fp32, 1e-2 with bf16 banks.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL32 = 1e-4
+RELBF = 1e-2
+
+
+def _rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want).max() / (np.abs(want).max() + 1e-30)
+
+
+def _case(B, K1, D, N, seed=0, dup_positive=False):
+    g = torch.Generator().manual_seed(seed)
+    stdv = 1.0 / (D / 3) ** 0.5
+    bank = (torch.rand(N, 2, D, generator=g) * 2 * stdv - stdv)
+    v1 = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1)
+    v2 = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1)
+    y = torch.randperm(N, generator=g)[:B] if B <= N else torch.randint(0, N, (B,), generator=g)
+    idx = torch.randint(0, N, (B, K1), generator=g)
+    idx[:, 0] = y
+    if dup_positive and K1 > 3 and B > 1:
+        idx[1, 3] = y[0]  # anchor 0's positive row is anchor 1's negative
+        idx[0, 2] = idx[0, 1]  # repeated negative
+    return bank, v1, v2, y, idx
+
+
+def _score(pkg, dev, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=0, row_end=None, want_out=True, variant=0,
+           dtype=torch.float32, interleaved=True):
+    """Direct C-ABI call. `bank` is the FULL [N,2,D] fp32 CPU tensor; the shard slice is uploaded."""
+    lib = pkg._native.lib()
+    row_end = N if row_end is None else row_end
+    B, K1 = idx.shape
+    D = v1.shape[1]
+    shard = bank[row_begin:row_end].to(dtype)
+    if interleaved:
+        dbank = shard.contiguous().to(dev)
+        b1, b2, stride = dbank[:, 0, :], dbank[:, 1, :], 2 * D
+    else:
+        b1, b2, stride = shard[:, 0, :].contiguous().to(dev), shard[:, 1, :].contiguous().to(dev), D
+    dv1, dv2, didx = v1.to(dev), v2.to(dev), idx.to(dev)
+    n = ctypes.c_size_t(0)
+    pkg._native.check(lib.crdpn_crd_workspace_bytes(B, K1, D, 0, ctypes.byref(n)), "ws")
+    ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
+    res = torch.full((8,), -7.0, dtype=torch.float64, device=dev)
+    g1 = torch.full((B, D), float("nan"), device=dev)
+    g2 = torch.full((B, D), float("nan"), device=dev)
+    o1 = torch.full((B, K1), float("nan"), device=dev) if want_out else None
+    o2 = torch.full((B, K1), float("nan"), device=dev) if want_out else None
+    rc = lib.crdpn_crd_score(b1.data_ptr() if row_end > row_begin else None, b2.data_ptr() if row_end > row_begin else None,
+                             stride, 0 if dtype == torch.float32 else 1,
+                             dv1.data_ptr(), dv2.data_ptr(), didx.data_ptr(), B, K1, D, N, row_begin, row_end,
+                             T, Z1, Z2, 1e-7, o1.data_ptr() if want_out else None, o2.data_ptr() if want_out else None,
+                             res.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), ws.numel(), variant,
+                             torch.cuda.current_stream().cuda_stream)
+    pkg._native.check(rc, "crdpn_crd_score")
+    torch.cuda.synchronize()
+    return dict(res=res.cpu().numpy(), g1=g1.cpu().numpy(), g2=g2.cpu().numpy(),
+                o1=None if o1 is None else o1.cpu().numpy(), o2=None if o2 is None else o2.cpu().numpy())
+
+
+def _oracle_score(oracle, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=0, row_end=None, dtype=torch.float32):
+    row_end = N if row_end is None else row_end
+    sh = bank[row_begin:row_end].to(dtype).float().numpy()
+    return oracle.crd_score(sh[:, 0, :], sh[:, 1, :], v1.numpy(), v2.numpy(), idx.numpy(), N, T, Z1, Z2,
+                            row_begin=row_begin, row_end=row_end)
+
+
+def _check_full(got, want, rel):
+    assert _rel(got["res"][0], want["loss_s"]) < rel
+    assert _rel(got["res"][1], want["loss_t"]) < rel
+    assert _rel(got["res"][2], want["sum_e1"]) < rel and _rel(got["res"][3], want["sum_e2"]) < rel
+    assert got["res"][4] == want["count"]
+    assert _rel(got["g1"], want["grad_v1"]) < rel and _rel(got["g2"], want["grad_v2"]) < rel
+    if got["o1"] is not None:
+        assert _rel(got["o1"], want["out_v1"]) < rel and _rel(got["o2"], want["out_v2"]) < rel
+        assert np.array_equal(got["o1"] == 0, want["out_v1"] == 0)  # same set of skipped (out-of-shard) entries
+
+
+@pytest.mark.parametrize("B,K1,D,N", [
+    (1, 1, 128, 16),          # a single positive, no negatives
+    (3, 2, 128, 8),           # fewer pairs than warps
+    (5, 33, 64, 100),         # ragged: K1 not a multiple of 32
+    (7, 257, 128, 1000),
+    (46, 1025, 128, 5000),    # many anchors per warp boundary
+    (4, 4097, 256, 3000),
+    (9, 130, 32, 64),
+    (2, 70, 512, 300),
+    (300, 17, 128, 500),      # more anchors than CTAs per anchor: several anchors per warp range
+    (6000, 3, 64, 100),       # each warp range spans several anchors (maxseg > 2); duplicate positives
+])
+def test_score_parity_shapes(pkg, oracle, cuda, B, K1, D, N):
+    bank, v1, v2, y, idx = _case(B, K1, D, N, seed=B + K1, dup_positive=True)
+    T, Z1, Z2 = 0.07, 37.5 * N / 100, 21.0 * N / 100
+    want = _oracle_score(oracle, bank, v1, v2, idx, N, T, Z1, Z2)
+    got = _score(pkg, cuda, bank, v1, v2, idx, N, T, Z1, Z2)
+    _check_full(got, want, REL32)
+    # separately allocated (non-interleaved) banks give bit-identical results
+    got2 = _score(pkg, cuda, bank, v1, v2, idx, N, T, Z1, Z2, interleaved=False)
+    for k in ("res", "g1", "g2", "o1", "o2"):
+        assert np.array_equal(got[k], got2[k]), k
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+def test_score_parity_all_tuning_variants_d128(pkg, oracle, cuda, variant):
+    bank, v1, v2, y, idx = _case(11, 777, 128, 2000, seed=variant, dup_positive=True)
+    T, Z1, Z2 = 0.07, 600.0, 900.0
+    want = _oracle_score(oracle, bank, v1, v2, idx, 2000, T, Z1, Z2)
+    got = _score(pkg, cuda, bank, v1, v2, idx, 2000, T, Z1, Z2, variant=variant)
+    _check_full(got, want, REL32)
+
+
+@pytest.mark.parametrize("D,variant", [(64, 2), (256, 2)])
+def test_score_parity_other_variants(pkg, oracle, cuda, D, variant):
+    bank, v1, v2, y, idx = _case(6, 300, D, 700, seed=D)
+    want = _oracle_score(oracle, bank, v1, v2, idx, 700, 0.07, 300.0, 200.0)
+    got = _score(pkg, cuda, bank, v1, v2, idx, 700, 0.07, 300.0, 200.0, variant=variant)
+    _check_full(got, want, REL32)
+
+
+def test_sum_mode_first_call(pkg, oracle, cuda):
+    bank, v1, v2, y, idx = _case(8, 513, 128, 4000, seed=3)
+    want = _oracle_score(oracle, bank, v1, v2, idx, 4000, 0.07, -1.0, -1.0)
+    got = _score(pkg, cuda, bank, v1, v2, idx, 4000, 0.07, -1.0, -1.0)
+    assert got["res"][0] == 0 and got["res"][1] == 0
+    assert _rel(got["res"][2], want["sum_e1"]) < REL32 and _rel(got["res"][3], want["sum_e2"]) < REL32
+    assert got["res"][4] == 8 * 513
+    assert _rel(got["o1"], want["out_v1"]) < REL32   # raw exponentials in sum mode
+    assert np.isnan(got["g1"]).all()                  # gradients are not touched in sum mode
+
+
+def test_sharded_partials_sum_to_unsharded_and_match_oracle(pkg, oracle, cuda):
+    N, R = 1003, 4
+    bank, v1, v2, y, idx = _case(10, 400, 128, N, seed=9, dup_positive=True)
+    T, Z1, Z2 = 0.07, 300.0, 350.0
+    full = _score(pkg, cuda, bank, v1, v2, idx, N, T, Z1, Z2)
+    acc = None
+    for r in range(R):
+        lo, hi = N * r // R, N * (r + 1) // R
+        part = _score(pkg, cuda, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=lo, row_end=hi)
+        want = _oracle_score(oracle, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=lo, row_end=hi)
+        _check_full(part, want, REL32)
+        acc = part if acc is None else {k: acc[k] + part[k] for k in part}
+    for k in ("res", "g1", "g2", "o1", "o2"):
+        assert _rel(acc[k], full[k]) < 1e-5, k
+    # an empty shard contributes exactly nothing
+    empty = _score(pkg, cuda, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=500, row_end=500)
+    assert not empty["res"][:5].any() and not empty["g1"].any() and not empty["o1"].any()
+
+
+def test_deterministic_bitwise(pkg, cuda):
+    bank, v1, v2, y, idx = _case(46, 2049, 128, 9000, seed=1)
+    a = _score(pkg, cuda, bank, v1, v2, idx, 9000, 0.07, 2000.0, 2500.0)
+    b = _score(pkg, cuda, bank, v1, v2, idx, 9000, 0.07, 2000.0, 2500.0)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_bf16_banks_within_bf16_tolerance(pkg, oracle, cuda):
+    bank, v1, v2, y, idx = _case(12, 600, 128, 3000, seed=4)
+    T, Z1, Z2 = 0.07, 1000.0, 1200.0
+    # kernel on bf16 banks vs the oracle on the same bf16-rounded rows: fp32-level agreement
+    want_same = _oracle_score(oracle, bank, v1, v2, idx, 3000, T, Z1, Z2, dtype=torch.bfloat16)
+    for variant in (0, 2, 3):
+        got = _score(pkg, cuda, bank, v1, v2, idx, 3000, T, Z1, Z2, dtype=torch.bfloat16, variant=variant)
+        _check_full(got, want_same, REL32)
+    # and vs the fp32-bank oracle: bf16 tolerance
+    want32 = _oracle_score(oracle, bank, v1, v2, idx, 3000, T, Z1, Z2)
+    assert _rel(got["res"][0] + got["res"][1], want32["loss_s"] + want32["loss_t"]) < RELBF
+    assert _rel(got["g1"], want32["grad_v1"]) < RELBF
+
+
+def _update(pkg, dev, bank, v1, v2, y, m, row_begin=0, row_end=None, dtype=torch.float32):
+    lib = pkg._native.lib()
+    N, _, D = bank.shape
+    row_end = N if row_end is None else row_end
+    dbank = bank[row_begin:row_end].to(dtype).contiguous().to(dev)
+    dv1, dv2, dy = v1.to(dev), v2.to(dev), y.to(dev)
+    m32 = float(np.float32(m))
+    esz = 4 if dtype == torch.float32 else 2
+    rc = lib.crdpn_crd_momentum_update(dbank.data_ptr(), dbank.data_ptr() + D * esz, 2 * D, 0 if esz == 4 else 1,
+                                       dv1.data_ptr(), dv2.data_ptr(), dy.data_ptr(), len(y), D, row_begin, row_end,
+                                       m32, 1.0 - m32, torch.cuda.current_stream().cuda_stream)
+    pkg._native.check(rc, "update")
+    torch.cuda.synchronize()
+    return dbank.cpu()
+
+
+@pytest.mark.parametrize("D", [32, 64, 128, 256, 512])
+def test_momentum_update_bit_exact(pkg, oracle, cuda, D):
+    bank, v1, v2, y, idx = _case(13, 4, D, 200, seed=D)
+    y[5] = y[2]      # duplicate sample index: last occurrence wins
+    y[11] = y[2]
+    got = _update(pkg, cuda, bank, v1, v2, y, 0.5).numpy()
+    want = bank.numpy().copy()
+    oracle.momentum_update(want[:, 0, :], v1.numpy(), y.numpy(), 0.5)
+    oracle.momentum_update(want[:, 1, :], v2.numpy(), y.numpy(), 0.5)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # vs the torch formula (different reduction order): within 2 ulp
+    pos = bank[y, 0, :] * 0.5 + v1 * 0.5
+    t = (pos / pos.pow(2).sum(1, keepdim=True).pow(0.5)).numpy()
+    keep = [i for i in range(13) if i not in (2, 5)]
+    assert np.max(np.abs(got[y.numpy()[keep], 0, :] - t[keep]) / np.spacing(np.abs(t[keep]))) <= 2
+
+
+def test_momentum_update_shard_and_bf16(pkg, oracle, cuda):
+    bank, v1, v2, y, idx = _case(16, 4, 128, 100, seed=2)
+    got = _update(pkg, cuda, bank, v1, v2, y, 0.3, row_begin=40, row_end=90).numpy()
+    want = bank[40:90].numpy().copy()
+    oracle.momentum_update(want[:, 0, :], v1.numpy(), y.numpy(), 0.3, row_begin=40, row_end=90)
+    oracle.momentum_update(want[:, 1, :], v2.numpy(), y.numpy(), 0.3, row_begin=40, row_end=90)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # bf16 banks: the fp32 canonical result rounded to nearest-even bf16
+    gotb = _update(pkg, cuda, bank, v1, v2, y, 0.5, dtype=torch.bfloat16)
+    wb = bank.to(torch.bfloat16).float().numpy().copy()
+    oracle.momentum_update(wb[:, 0, :], v1.numpy(), y.numpy(), 0.5)
+    oracle.momentum_update(wb[:, 1, :], v2.numpy(), y.numpy(), 0.5)
+    assert torch.equal(gotb, torch.from_numpy(wb).to(torch.bfloat16))
+
+
+def test_alias_draw_bit_exact(pkg, oracle, cuda):
+    probs = torch.rand(1000, generator=torch.Generator().manual_seed(3)) ** 2
+    am = pkg.AliasMethod(probs.clone(), seed=1234)
+    prob, alias = oracle.alias_build(probs.numpy())
+    assert np.array_equal(am.prob.numpy(), prob) and np.array_equal(am.alias.numpy(), alias)
+    am.cuda()
+    a = am.draw(100003).cpu().numpy()
+    b = am.draw(77).cpu().numpy()
+    assert np.array_equal(a, oracle.alias_draw(prob, alias, 100003, seed=1234, offset=0))
+    assert np.array_equal(b, oracle.alias_draw(prob, alias, 77, seed=1234, offset=100003))
+    y = torch.tensor([5, 999, 0, 17], device=cuda)
+    c = am.draw_contrast(y, 1025).cpu().numpy()
+    assert np.array_equal(c, oracle.alias_draw_contrast(prob, alias, y.cpu().numpy(), 1025, seed=1234, offset=100080))
+    # uniform unigrams over a large N: every value in range, all residues reachable
+    am2 = pkg.AliasMethod(torch.ones(90000), seed=7).cuda()
+    d = am2.draw(1 << 20)
+    assert int(d.min()) >= 0 and int(d.max()) < 90000 and d.unique().numel() > 89000
+
+
+def _opt(**kw):
+    base = dict(s_dim=200, t_dim=200, feat_dim=128, n_data=5000, nce_k=1024, nce_t=0.07, nce_m=0.5)
+    base.update(kw)
+    return type("Opt", (), base)()
+
+
+def test_crdloss_module_matches_stock_formulation_two_steps(pkg, oracle, cuda):
+    """Drop-in check: same weights and banks, fixed contrast_idx -> same loss, same gradients on inputs and
+    embed parameters, same Z, bit-exact bank rows vs the canonical oracle, over two consecutive steps."""
+    from oracle.crd_oracle import StockCRD
+    opt = _opt()
+    torch.manual_seed(46)
+    crit = pkg.CRDLoss(opt).to(cuda)
+    stock = StockCRD(opt.s_dim, opt.t_dim, opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m)
+    with torch.no_grad():
+        crit.embed_s.linear.weight.copy_(stock.Ws); crit.embed_s.linear.bias.copy_(stock.bs)
+        crit.embed_t.linear.weight.copy_(stock.Wt); crit.embed_t.linear.bias.copy_(stock.bt)
+        crit.contrast.memory_v1.copy_(stock.memory_v1); crit.contrast.memory_v2.copy_(stock.memory_v2)
+    B = 46
+    for step in range(2):
+        g = torch.Generator().manual_seed(100 + step)
+        f_s = torch.randn(B, opt.s_dim, generator=g)
+        f_t = torch.randn(B, opt.t_dim, generator=g)
+        y = torch.randperm(opt.n_data, generator=g)[:B]
+        cidx = torch.randint(0, opt.n_data, (B, opt.nce_k + 1), generator=g)
+        cidx[:, 0] = y
+        canon1 = crit.contrast.memory_v1.detach().cpu().numpy().copy()
+        canon2 = crit.contrast.memory_v2.detach().cpu().numpy().copy()
+        fs_d = f_s.to(cuda).requires_grad_()
+        ft_d = f_t.to(cuda).requires_grad_()
+        crit.zero_grad()
+        loss = crit(fs_d, ft_d, y.to(cuda), cidx.to(cuda))
+        assert loss.dim() == 0 and loss.dtype == torch.float32
+        (loss * 0.8).backward()
+        fs_c, ft_c = f_s.clone().requires_grad_(), f_t.clone().requires_grad_()
+        for p in (stock.Ws, stock.bs, stock.Wt, stock.bt):
+            p.grad = None
+        want = stock.loss(fs_c, ft_c, y, cidx)
+        (want * 0.8).backward()
+        assert _rel(loss.item(), want.item()) < REL32
+        assert _rel(crit.contrast.params[2].item(), stock.Z1) < REL32 and _rel(crit.contrast.params[3].item(), stock.Z2) < REL32
+        assert _rel(fs_d.grad.cpu(), fs_c.grad) < REL32 and _rel(ft_d.grad.cpu(), ft_c.grad) < REL32
+        assert _rel(crit.embed_s.linear.weight.grad.cpu(), stock.Ws.grad) < REL32
+        assert _rel(crit.embed_t.linear.bias.grad.cpu(), stock.bt.grad) < REL32
+        # bank rows: bit-exact vs canonical oracle applied to the GPU's own embeddings; <=2 ulp vs torch
+        with torch.no_grad():
+            v1 = crit.embed_s(fs_d).cpu().numpy()
+            v2 = crit.embed_t(ft_d).cpu().numpy()
+        oracle.momentum_update(canon1, v1, y.numpy(), 0.5)
+        oracle.momentum_update(canon2, v2, y.numpy(), 0.5)
+        got1 = crit.contrast.memory_v1.detach().cpu().numpy()
+        assert np.array_equal(got1.view(np.uint32), canon1.view(np.uint32))
+        assert np.array_equal(crit.contrast.memory_v2.detach().cpu().numpy().view(np.uint32), canon2.view(np.uint32))
+        assert _rel(got1, stock.memory_v1.numpy()) < 1e-5
+        # keep the two implementations in lock-step for the next iteration
+        with torch.no_grad():
+            stock.memory_v1.copy_(torch.from_numpy(got1))
+            stock.memory_v2.copy_(crit.contrast.memory_v2.detach().cpu())
+
+
+def test_contrast_memory_forward_surface_and_internal_sampling(pkg, oracle, cuda):
+    torch.manual_seed(1)
+    mem = pkg.ContrastMemory(128, 3000, 511, seed=99).to(cuda)
+    assert mem.memory_v1.stride(0) == 256 and mem.memory_v2.data_ptr() - mem.memory_v1.data_ptr() == 512
+    v1 = torch.nn.functional.normalize(torch.randn(6, 128, device=cuda), dim=1)
+    v2 = torch.nn.functional.normalize(torch.randn(6, 128, device=cuda), dim=1)
+    y = torch.tensor([5, 17, 2999, 0, 44, 1000], device=cuda)
+    b1 = mem.memory_v1.cpu().numpy().copy(); b2 = mem.memory_v2.cpu().numpy().copy()
+    o1, o2 = mem(v1, v2, y)                      # idx=None -> on-device alias draw, column 0 <- y
+    assert o1.shape == (6, 512, 1) and o2.shape == (6, 512, 1)
+    prob, alias = oracle.alias_build(np.ones(3000, np.float32))
+    cidx = oracle.alias_draw_contrast(prob, alias, y.cpu().numpy(), 512, seed=99, offset=0)
+    Z1, Z2 = mem.params[2].item(), mem.params[3].item()
+    want = oracle.crd_score(b1, b2, v1.cpu().numpy(), v2.cpu().numpy(), cidx, 3000, 0.07, Z1, Z2)
+    assert _rel(o1.cpu().numpy()[:, :, 0], want["out_v1"]) < REL32
+    assert _rel(o2.cpu().numpy()[:, :, 0], want["out_v2"]) < REL32
+    # unfused criterion on those outputs == fused loss on the same inputs
+    crit = pkg.ContrastLoss(3000)
+    unfused = (crit(o1) + crit(o2)).item()
+    assert _rel(unfused, want["loss_s"] + want["loss_t"]) < REL32
+
+
+def test_config1_full_size_vs_oracle(pkg, oracle, cuda):
+    """BASELINE config 1 at full size: B=46, D=128, K=16384, N=90k x 2, tau=0.07 (oracle takes a few seconds)."""
+    B, K1, D, N = 46, 16385, 128, 90000
+    bank, v1, v2, y, idx = _case(B, K1, D, N, seed=46)
+    r0 = _score(pkg, cuda, bank, v1, v2, idx, N, 0.07, -1.0, -1.0, want_out=False)
+    Z1 = float(np.float32(r0["res"][2] / r0["res"][4] * N))
+    Z2 = float(np.float32(r0["res"][3] / r0["res"][4] * N))
+    got = _score(pkg, cuda, bank, v1, v2, idx, N, 0.07, Z1, Z2, want_out=False)
+    want = _oracle_score(oracle, bank, v1, v2, idx, N, 0.07, Z1, Z2)
+    _check_full(got, want, REL32)
