@@ -31,6 +31,10 @@ _SIGNATURES = {
                                 c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_size_t, c_int, c_void_p]),
+    "crdpn_crd_step": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                               c_float, c_float, c_float, c_float, c_float, c_float,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "crdpn_crd_momentum_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     "crdpn_pointnet_packed_bytes": (c_int, [c_int64, POINTER(c_size_t)]),

@@ -282,6 +282,24 @@ class ContrastMemory(nn.Module):
                 v1.shape[0], v1.shape[1], self.row_begin, self.row_end, m32, 1.0 - m32, _stream_ptr(v1.device))
         _native.check(rc, "crdpn_crd_momentum_update")
 
+    def _step(self, v1, v2, y, idx, Z1, Z2):
+        """crdpn_crd_step: score + loss + backward, then reduction and momentum update in one launch."""
+        m1, m2, stride, dt = self._banks()
+        B, K1 = idx.shape
+        D = v1.shape[1]
+        dev = v1.device
+        ws = self._workspace(B, K1, D, dev)
+        res = self._res
+        g1, g2 = torch.empty_like(v1), torch.empty_like(v2)
+        hp = self._host_params()
+        with torch.cuda.device(dev):
+            rc = _native.lib().crdpn_crd_step(
+                m1.data_ptr(), m2.data_ptr(), stride, dt, v1.data_ptr(), v2.data_ptr(), idx.data_ptr(), y.data_ptr(),
+                B, K1, D, self.nLem, self.row_begin, self.row_end, hp.T, Z1, Z2, EPS, hp.m, 1.0 - hp.m,
+                res.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), ws.numel(), self.variant, _stream_ptr(dev))
+        _native.check(rc, "crdpn_crd_step")
+        return res, g1, g2
+
     def _reduce_sums(self, res):
         """Hook for the sharded subclass: sum the first-call (sum_e1, sum_e2, count) over ranks."""
         return res
@@ -328,10 +346,9 @@ class ContrastMemory(nn.Module):
         """Fused path used by CRDLoss: returns (loss 0-dim f32, grad_v1, grad_v2) and updates the banks."""
         self._freeze_z(v1, v2, idx)
         hp = self._host_params()
-        res, g1, g2, _, _ = self._score(v1, v2, idx, hp.Z1, hp.Z2)
+        res, g1, g2 = self._step(v1, v2, y, idx, hp.Z1, hp.Z2)
         res, g1, g2 = self._reduce_partials(res, g1, g2)
         loss = (res[0] + res[1]).to(torch.float32)
-        self._update(v1, v2, y)
         return loss, g1, g2
 
     def fused_loss(self, v1, v2, y, idx=None):

@@ -9,6 +9,7 @@
 //                           row of each bank is read exactly once; nothing of size B*K*D is ever written.
 //   2. crd_finalize_kernel  deterministic fixed-order reduction of the per-warp partials.
 //   3. crd_update_kernel    momentum + L2 renormalisation of the B positive rows (after all scoring).
+// crdpn_crd_step runs 2 and 3 as ONE launch (crd_finalize_update_kernel): two launches per training step.
 //
 // Data layout in HBM: a bank row is D contiguous elements (fp32 or bf16), 16-byte aligned, row pitch
 // `row_stride` elements.  The Python module allocates both banks interleaved as [N][2][D] so that one
@@ -315,31 +316,69 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
 
 // One CTA per anchor: fixed-order sum of the warp partials that intersect the anchor's K1 pairs; the last
 // CTA to finish folds the per-anchor scalars into result[] (also in fixed order) -> bit-reproducible.
-__global__ void __launch_bounds__(256) crd_finalize_kernel(const FinalizeParams f) {
-  const int b = blockIdx.x;
+// The slot offsets are computed once per CTA into shared memory (no 64-bit divisions in the summation loop).
+constexpr int kFinalizeThreads = 256;
+constexpr int kFinalizeList = 1024;
+
+__device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int b) {
+  __shared__ long long s_off[kFinalizeList];
+  __shared__ long long s_first, s_last;
+  __shared__ bool is_last;
   const long long P = (long long)f.B * f.K1;
   const long long p0 = (long long)b * f.K1, p1 = p0 + f.K1;
-  long long first = (p0 * f.NW) / P;
-  while (first > 0 && (P * first) / f.NW > p0) --first;
-  while (first + 1 < f.NW && (P * (first + 1)) / f.NW <= p0) ++first;
+  if (threadIdx.x == 0) {
+    long long first = (p0 * f.NW) / P;
+    while (first > 0 && (P * first) / f.NW > p0) --first;
+    while (first + 1 < f.NW && (P * (first + 1)) / f.NW <= p0) ++first;
+    long long last = (p1 * f.NW + P - 1) / P - 1;  // largest w with floor(P*w/NW) < p1
+    if (last >= f.NW) last = f.NW - 1;
+    while (last + 1 < f.NW && (P * (last + 1)) / f.NW < p1) ++last;
+    while (last > first && (P * last) / f.NW >= p1) --last;
+    s_first = first;
+    s_last = last;
+  }
+  __syncthreads();
+  const long long first = s_first, last = s_last;
   const int slot_w = 2 * f.D + kSlotExtra;
   const int ncols = 2 * f.D;
-  for (int col = threadIdx.x; col < ncols + 5; col += blockDim.x) {
-    if (!f.full && col < ncols) continue;
-    double acc = 0.0;
-    for (long long w = first; w < f.NW; ++w) {
+  constexpr int kMaxCols = 5;  // columns per thread: ceil((2*512 + 5) / 256)
+  double acc[kMaxCols];
+#pragma unroll
+  for (int c = 0; c < kMaxCols; ++c) acc[c] = 0.0;
+  for (long long chunk = first; chunk <= last; chunk += kFinalizeList) {
+    const int n = (int)((last - chunk + 1 < kFinalizeList) ? (last - chunk + 1) : kFinalizeList);
+    for (int i = threadIdx.x; i < n; i += kFinalizeThreads) {
+      const long long w = chunk + i;
       const long long lo = (P * w) / f.NW;
-      if (lo >= p1) break;
       const long long hi = (P * (w + 1)) / f.NW;
-      if (hi <= p0 || hi <= lo) continue;
-      const int seg = b - (int)(lo / f.K1);
-      acc += (double)f.slots[(w * f.maxseg + seg) * slot_w + col];
+      const bool valid = hi > p0 && hi > lo && lo < p1;
+      s_off[i] = valid ? (w * f.maxseg + (b - (int)(lo / f.K1))) * (long long)slot_w : -1;
     }
-    if (col < f.D) f.grad_v1[(long long)b * f.D + col] = (float)acc;
-    else if (col < ncols) f.grad_v2[(long long)b * f.D + (col - f.D)] = (float)acc;
-    else f.anchor_part[b * 8 + (col - ncols)] = acc;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c) {
+      const int col = threadIdx.x + c * kFinalizeThreads;
+      if (col < ncols + 5 && (f.full || col >= ncols)) {
+        double a = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+          const long long off = s_off[i];
+          if (off >= 0) a += (double)f.slots[off + col];
+        }
+        acc[c] += a;
+      }
+    }
+    __syncthreads();
   }
-  __shared__ bool is_last;
+#pragma unroll
+  for (int c = 0; c < kMaxCols; ++c) {
+    const int col = threadIdx.x + c * kFinalizeThreads;
+    if (col < ncols + 5 && (f.full || col >= ncols)) {
+      if (col < f.D) f.grad_v1[(long long)b * f.D + col] = (float)acc[c];
+      else if (col < ncols) f.grad_v2[(long long)b * f.D + (col - f.D)] = (float)acc[c];
+      else f.anchor_part[b * 8 + (col - ncols)] = acc[c];
+    }
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -359,18 +398,34 @@ __global__ void __launch_bounds__(256) crd_finalize_kernel(const FinalizeParams 
   }
 }
 
+struct UpdateParams {
+  char* bank1;
+  char* bank2;
+  long long row_stride_bytes;
+  const float* v1;
+  const float* v2;
+  const long long* y;
+  int B, D;
+  long long row_begin, row_end;
+  float m, om;
+};
+
 // Momentum update: one warp per (anchor, bank).  Canonical order: element e -> lane (e/4)%32, per-lane
 // fmaf fold in increasing e, xor butterfly 16..1 (bit-identical to oracle/crd_oracle.c canonical_sumsq).
 template <typename T>
-__global__ void __launch_bounds__(128) crd_update_kernel(char* bank1, char* bank2, long long row_stride_bytes,
-                                                         const float* v1, const float* v2, const long long* y,
-                                                         int B, int D, long long row_begin, long long row_end,
-                                                         float m, float om) {
+__device__ __forceinline__ void update_body(const UpdateParams& u, const int wid) {
   const int lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wid >= 2 * B) return;
+  if (wid >= 2 * u.B) return;
   const int b = wid >> 1;
   const int which = wid & 1;
+  const long long* y = u.y;
+  const int B = u.B, D = u.D;
+  const long long row_begin = u.row_begin, row_end = u.row_end, row_stride_bytes = u.row_stride_bytes;
+  char* bank1 = u.bank1;
+  char* bank2 = u.bank2;
+  const float* v1 = u.v1;
+  const float* v2 = u.v2;
+  const float m = u.m, om = u.om;
   const long long r = y[b];
   if (r < row_begin || r >= row_end) return;
   bool dup = false;
@@ -429,6 +484,23 @@ __global__ void __launch_bounds__(128) crd_update_kernel(char* bank1, char* bank
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(kFinalizeThreads) crd_finalize_kernel(const FinalizeParams f) {
+  finalize_body(f, blockIdx.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFinalizeThreads) crd_update_kernel(const UpdateParams u) {
+  update_body<T>(u, blockIdx.x * (kFinalizeThreads / 32) + (threadIdx.x >> 5));
+}
+
+// finalize (blocks [0,B)) and momentum update (remaining blocks) in one launch: both only depend on the score
+// kernel having finished, and touch disjoint memory.
+template <typename T>
+__global__ void __launch_bounds__(kFinalizeThreads) crd_finalize_update_kernel(const FinalizeParams f, const UpdateParams u) {
+  if ((int)blockIdx.x < f.B) finalize_body(f, blockIdx.x);
+  else update_body<T>(u, ((int)blockIdx.x - f.B) * (kFinalizeThreads / 32) + (threadIdx.x >> 5));
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -557,13 +629,38 @@ extern "C" int crdpn_crd_workspace_bytes(int64_t B, int64_t K1, int64_t D, int d
   return CRDPN_OK;
 }
 
-extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
-                               const float* v1, const float* v2, const int64_t* contrast_idx,
-                               int64_t B, int64_t K1, int64_t D, int64_t n_data,
-                               int64_t row_begin, int64_t row_end,
-                               float T, float Z1, float Z2, float eps,
-                               float* out_v1, float* out_v2, double* result, float* grad_v1, float* grad_v2,
-                               void* workspace, size_t workspace_bytes, int variant, void* stream) {
+static int check_update_args(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
+                             const float* v1, const float* v2, const int64_t* y, int64_t B, int64_t D,
+                             int64_t row_begin, int64_t row_end) {
+  if (!v1 || !v2 || !y) return fail(CRDPN_E_BADARG, "crdpn momentum update: null pointer");
+  if (B <= 0 || D <= 0 || row_end < row_begin) return fail(CRDPN_E_BADARG, "crdpn momentum update: bad size");
+  if (row_end > row_begin && (!bank1 || !bank2)) return fail(CRDPN_E_BADARG, "crdpn momentum update: null bank");
+  if (D % 4 != 0 || D > 1024) return fail(CRDPN_E_UNSUPPORTED, "crdpn momentum update: feat_dim must be a multiple of 4, <= 1024");
+  if (bank_dtype != CRDPN_F32 && bank_dtype != CRDPN_BF16) return fail(CRDPN_E_UNSUPPORTED, "crdpn momentum update: bank dtype");
+  const size_t esz = (bank_dtype == CRDPN_BF16) ? 2 : 4;
+  if (((uintptr_t)bank1 | (uintptr_t)bank2 | (uintptr_t)v1 | (uintptr_t)v2) & 15 || ((size_t)row_stride * esz) % 16 != 0)
+    return fail(CRDPN_E_ALIGN, "crdpn momentum update: 16-byte alignment required");
+  return CRDPN_OK;
+}
+
+static UpdateParams make_update_params(void* bank1, void* bank2, int64_t row_stride, int bank_dtype, const float* v1,
+                                       const float* v2, const int64_t* y, int64_t B, int64_t D, int64_t row_begin,
+                                       int64_t row_end, float m, float om) {
+  UpdateParams u;
+  u.bank1 = (char*)bank1; u.bank2 = (char*)bank2;
+  u.row_stride_bytes = (long long)row_stride * ((bank_dtype == CRDPN_BF16) ? 2 : 4);
+  u.v1 = v1; u.v2 = v2; u.y = (const long long*)y;
+  u.B = (int)B; u.D = (int)D; u.row_begin = row_begin; u.row_end = row_end; u.m = m; u.om = om;
+  return u;
+}
+
+// score (+ finalize); when `upd` is given the momentum update rides in the finalize launch.
+static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
+                      const float* v1, const float* v2, const int64_t* contrast_idx,
+                      int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t row_begin, int64_t row_end,
+                      float T, float Z1, float Z2, float eps, float* out_v1, float* out_v2, double* result,
+                      float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes, int variant,
+                      const UpdateParams* upd, void* stream) {
   if (!v1 || !v2 || !contrast_idx || !result || !workspace)
     return fail(CRDPN_E_BADARG, "crdpn_crd_score: null pointer");
   if (B <= 0 || K1 <= 0 || D <= 0 || n_data <= 0 || row_end < row_begin || !(T > 0.f))
@@ -636,35 +733,63 @@ extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row
   fp.B = (int)B; fp.K1 = (int)K1; fp.D = (int)D; fp.full = full ? 1 : 0;
   fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2;
   fp.anchor_part = anchor_part; fp.result = result; fp.ticket = ticket;
-  crd_finalize_kernel<<<(int)B, 256, 0, st>>>(fp);
-  CRDPN_LAUNCH_CHECK("crd_finalize_kernel");
+  if (upd != nullptr && upd->row_end > upd->row_begin) {
+    const int ublocks = (int)((2 * B + (kFinalizeThreads / 32) - 1) / (kFinalizeThreads / 32));
+    if (bank_dtype == CRDPN_F32)
+      crd_finalize_update_kernel<float><<<(int)B + ublocks, kFinalizeThreads, 0, st>>>(fp, *upd);
+    else
+      crd_finalize_update_kernel<__nv_bfloat16><<<(int)B + ublocks, kFinalizeThreads, 0, st>>>(fp, *upd);
+    CRDPN_LAUNCH_CHECK("crd_finalize_update_kernel");
+  } else {
+    crd_finalize_kernel<<<(int)B, kFinalizeThreads, 0, st>>>(fp);
+    CRDPN_LAUNCH_CHECK("crd_finalize_kernel");
+  }
   return CRDPN_OK;
+}
+
+extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
+                               const float* v1, const float* v2, const int64_t* contrast_idx,
+                               int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                               int64_t row_begin, int64_t row_end,
+                               float T, float Z1, float Z2, float eps,
+                               float* out_v1, float* out_v2, double* result, float* grad_v1, float* grad_v2,
+                               void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, row_begin, row_end,
+                    T, Z1, Z2, eps, out_v1, out_v2, result, grad_v1, grad_v2, workspace, workspace_bytes, variant,
+                    nullptr, stream);
+}
+
+extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+                              const float* v1, const float* v2, const int64_t* contrast_idx, const int64_t* y,
+                              int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                              int64_t row_begin, int64_t row_end,
+                              float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+                              double* result, float* grad_v1, float* grad_v2,
+                              void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  if (!(Z1 > 0.f && Z2 > 0.f)) return fail(CRDPN_E_BADARG, "crdpn_crd_step: Z1 and Z2 must be frozen (> 0) before a full step");
+  int rc = check_update_args(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end);
+  if (rc) return rc;
+  const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end,
+                                            momentum, one_minus_momentum);
+  return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, row_begin, row_end,
+                    T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant,
+                    &u, stream);
 }
 
 extern "C" int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
                                          const float* v1, const float* v2, const int64_t* y,
                                          int64_t B, int64_t D, int64_t row_begin, int64_t row_end,
                                          float momentum, float one_minus_momentum, void* stream) {
-  if (!v1 || !v2 || !y) return fail(CRDPN_E_BADARG, "crdpn_crd_momentum_update: null pointer");
-  if (B <= 0 || D <= 0 || row_end < row_begin) return fail(CRDPN_E_BADARG, "crdpn_crd_momentum_update: bad size");
+  int rc = check_update_args(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end);
+  if (rc) return rc;
   if (row_end == row_begin) return CRDPN_OK;
-  if (!bank1 || !bank2) return fail(CRDPN_E_BADARG, "crdpn_crd_momentum_update: null bank");
-  if (D % 4 != 0 || D > 1024) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_momentum_update: feat_dim must be a multiple of 4, <= 1024");
-  const size_t esz = (bank_dtype == CRDPN_BF16) ? 2 : 4;
-  if (bank_dtype != CRDPN_F32 && bank_dtype != CRDPN_BF16) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_momentum_update: bank dtype");
-  if (((uintptr_t)bank1 | (uintptr_t)bank2 | (uintptr_t)v1 | (uintptr_t)v2) & 15 || ((size_t)row_stride * esz) % 16 != 0)
-    return fail(CRDPN_E_ALIGN, "crdpn_crd_momentum_update: 16-byte alignment required");
-  const int warps = 4;
-  const int grid = (int)((2 * B + warps - 1) / warps);
+  const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end,
+                                            momentum, one_minus_momentum);
+  const int wpb = kFinalizeThreads / 32;
+  const int grid = (int)((2 * B + wpb - 1) / wpb);
   cudaStream_t st = (cudaStream_t)stream;
-  if (bank_dtype == CRDPN_F32)
-    crd_update_kernel<float><<<grid, warps * 32, 0, st>>>((char*)bank1, (char*)bank2, (long long)row_stride * 4, v1, v2,
-                                                         (const long long*)y, (int)B, (int)D, row_begin, row_end,
-                                                         momentum, one_minus_momentum);
-  else
-    crd_update_kernel<__nv_bfloat16><<<grid, warps * 32, 0, st>>>((char*)bank1, (char*)bank2, (long long)row_stride * 2, v1, v2,
-                                                                 (const long long*)y, (int)B, (int)D, row_begin, row_end,
-                                                                 momentum, one_minus_momentum);
+  if (bank_dtype == CRDPN_F32) crd_update_kernel<float><<<grid, kFinalizeThreads, 0, st>>>(u);
+  else crd_update_kernel<__nv_bfloat16><<<grid, kFinalizeThreads, 0, st>>>(u);
   CRDPN_LAUNCH_CHECK("crd_update_kernel");
   return CRDPN_OK;
 }

@@ -62,7 +62,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
@@ -136,8 +136,7 @@ def time_crd_resident(pkg, torch, dev, c, steps, warmup, flush_l2=False, variant
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
 
     def step():
-        mem._score(v1, v2, cidx, hp.Z1, hp.Z2)
-        mem._update(v1, v2, y)
+        mem._step(v1, v2, y, cidx, hp.Z1, hp.Z2)
 
     for _ in range(warmup):
         step()
@@ -329,7 +328,7 @@ def run_own(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(c), "B": c["B"], "D": c["D"], "K": c["K"], "N": c["N"], "banks": 2,
                    "bank_layout": "interleaved [N,2,D] fp32", "l2": "inputs larger than L2 (1.02 GB of banks, random rows); no flush",
-                   "step": "score+loss+backward (1 fused pass) + finalize + momentum update"},
+                   "step": "crdpn_crd_step: score+loss+backward (1 fused pass), then reduction+momentum update (1 launch)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": None, "peak_kind": peak_kind, "kernel": "crd_score_kernel",
                      "kernel_ms": r["kernel_ms_avg"], "algorithmic_bytes": abytes},

@@ -96,6 +96,17 @@ int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row_stride, in
                     float* out_v1, float* out_v2, double* result, float* grad_v1, float* grad_v2,
                     void* workspace, size_t workspace_bytes, int variant, void* stream);
 
+/* One full training step = crdpn_crd_score (full mode, no out_v) followed by crdpn_crd_momentum_update, in two
+ * launches instead of three: the momentum update rides in the reduction launch (both only need the scoring
+ * pass to have finished).  Z1, Z2 must already be frozen.  Same results, bit for bit, as the two calls. */
+int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+                   const float* v1, const float* v2, const int64_t* contrast_idx, const int64_t* y,
+                   int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                   int64_t row_begin, int64_t row_end,
+                   float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+                   double* result, float* grad_v1, float* grad_v2,
+                   void* workspace, size_t workspace_bytes, int variant, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Momentum update of both banks (ContrastMemory.forward, torch.no_grad block: index_select, mul_, add_,
  * pow/sum/pow, div, index_copy_).  bank[y] <- normalise(m*bank[y] + (1-m)*v), canonical reduction order
