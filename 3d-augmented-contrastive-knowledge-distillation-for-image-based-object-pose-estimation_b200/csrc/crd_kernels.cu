@@ -317,11 +317,13 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
 // One CTA per anchor: fixed-order sum of the warp partials that intersect the anchor's K1 pairs; the last
 // CTA to finish folds the per-anchor scalars into result[] (also in fixed order) -> bit-reproducible.
 // The slot offsets are computed once per CTA into shared memory (no 64-bit divisions in the summation loop).
-constexpr int kFinalizeThreads = 256;
+constexpr int kFinalizeThreads = 1024;
 constexpr int kFinalizeList = 1024;
+constexpr int kFinalizeScratch = 4096;  // doubles
 
 __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int b) {
   __shared__ long long s_off[kFinalizeList];
+  __shared__ double s_part[kFinalizeScratch];
   __shared__ long long s_first, s_last;
   __shared__ bool is_last;
   const long long P = (long long)f.B * f.K1;
@@ -340,11 +342,12 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
   __syncthreads();
   const long long first = s_first, last = s_last;
   const int slot_w = 2 * f.D + kSlotExtra;
-  const int ncols = 2 * f.D;
-  constexpr int kMaxCols = 5;  // columns per thread: ceil((2*512 + 5) / 256)
-  double acc[kMaxCols];
-#pragma unroll
-  for (int c = 0; c < kMaxCols; ++c) acc[c] = 0.0;
+  const int ncol4 = slot_w / 4;                       // float4 columns per slot (grad_v1 | grad_v2 | scalars)
+  int parts = kFinalizeThreads / ncol4;               // entry-parallel groups of ncol4 threads
+  if (parts > kFinalizeScratch / slot_w) parts = kFinalizeScratch / slot_w;
+  const int part = threadIdx.x / ncol4, c4 = threadIdx.x % ncol4;
+  const bool active = part < parts;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   for (long long chunk = first; chunk <= last; chunk += kFinalizeList) {
     const int n = (int)((last - chunk + 1 < kFinalizeList) ? (last - chunk + 1) : kFinalizeList);
     for (int i = threadIdx.x; i < n; i += kFinalizeThreads) {
@@ -355,28 +358,35 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
       s_off[i] = valid ? (w * f.maxseg + (b - (int)(lo / f.K1))) * (long long)slot_w : -1;
     }
     __syncthreads();
-#pragma unroll
-    for (int c = 0; c < kMaxCols; ++c) {
-      const int col = threadIdx.x + c * kFinalizeThreads;
-      if (col < ncols + 5 && (f.full || col >= ncols)) {
-        double a = 0.0;
-#pragma unroll 4
-        for (int i = 0; i < n; ++i) {
-          const long long off = s_off[i];
-          if (off >= 0) a += (double)f.slots[off + col];
+    if (active) {
+      // entries part, part+parts, ...: independent 128-bit loads, all in flight together
+#pragma unroll 8
+      for (int i = part; i < n; i += parts) {
+        const long long off = s_off[i];
+        if (off >= 0) {
+          const float4 v = *reinterpret_cast<const float4*>(f.slots + off + 4 * c4);
+          a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
         }
-        acc[c] += a;
       }
     }
     __syncthreads();
   }
-#pragma unroll
-  for (int c = 0; c < kMaxCols; ++c) {
-    const int col = threadIdx.x + c * kFinalizeThreads;
-    if (col < ncols + 5 && (f.full || col >= ncols)) {
-      if (col < f.D) f.grad_v1[(long long)b * f.D + col] = (float)acc[c];
-      else if (col < ncols) f.grad_v2[(long long)b * f.D + (col - f.D)] = (float)acc[c];
-      else f.anchor_part[b * 8 + (col - ncols)] = acc[c];
+  if (active) {
+    double* dst = s_part + part * slot_w + 4 * c4;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+  }
+  __syncthreads();
+  const int ncols = 2 * f.D;
+  for (int col = threadIdx.x; col < ncols + 5; col += kFinalizeThreads) {
+    double acc = 0.0;
+    for (int q = 0; q < parts; ++q) acc += s_part[q * slot_w + col];  // fixed order -> deterministic
+    if (col < ncols) {
+      if (f.full) {
+        if (col < f.D) f.grad_v1[(long long)b * f.D + col] = (float)acc;
+        else f.grad_v2[(long long)b * f.D + (col - f.D)] = (float)acc;
+      }
+    } else {
+      f.anchor_part[b * 8 + (col - ncols)] = acc;
     }
   }
   __threadfence();

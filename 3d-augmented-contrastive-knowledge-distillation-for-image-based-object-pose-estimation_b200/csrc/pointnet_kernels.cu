@@ -1,0 +1,556 @@
+// pointnet_kernels.cu -- the teacher's PointNet encoder (ShapeEncoderPC.forward, auxiliary/model.py:174-180)
+// as ONE fused sm_100a kernel: shared MLP 3->64->128->F on points + channel-wise max over points.
+//
+//   layer 1 (3->64,  0.07% of FLOPs)  CUDA cores, fp32 in, BN1 folded, ReLU, bf16 out -> smem (UMMA operand)
+//   layer 2 (64->128, 6%)             tcgen05.mma, M = 128 points, N = 128 channels, K = 64; epilogue adds the
+//                                     folded bias, ReLU, bf16 -> smem as the K-major B operand of layer 3
+//   layer 3 (128->F, 94%)             tcgen05.mma "swap-AB": M = 128 channels (one W3 slab), N = 128 points,
+//                                     K = 128; accumulator lanes are channels, so the max over points is a
+//                                     per-thread reduction over TMEM columns; BN3 (scale folded into W3, shift
+//                                     added after the max) commutes with the max because max(a*y) with the sign
+//                                     of a folded into W3 is just max of the folded product.
+// Nothing of size B*F*P is ever written: the [B,1024,2500] activation the stock path materialises (1.64 GB)
+// lives only in TMEM, 128x128 fp32 at a time.
+//
+// Work decomposition: a unit = 256 consecutive points of one cloud (two 128-point halves; the ragged tail is
+// padded by repeating the last real point -- max is idempotent).  Units are cut into equal contiguous ranges,
+// one per SM (persistent CTAs).  Each W3 slab (128 channels x 128 k, 32 KB bf16, pre-swizzled image in global
+// memory, L2 resident) is streamed by 1-D bulk async copies through a 3-stage ring and used for both halves.
+//
+// Warp roles (384 threads): w0 bulk-copy producer | w1 MMA issuer | w2 TMEM allocator | w3 idle
+//                           w4-7  layer-3 epilogue (TMEM -> running max)
+//                           w8-11 front end (layer 1 on CUDA cores, layer-2 epilogue)
+// TMEM (512 columns): [0,256) two layer-3 accumulators (ring), [256,512) layer-2 accumulators (one per half).
+#include "common.cuh"
+
+namespace crdpn {
+namespace pn {
+
+constexpr int kThreads = 384;
+constexpr int kHalfPts = 128;
+constexpr int kUnitPts = 256;
+constexpr int kStages = 3;
+constexpr uint32_t kSlabBytes = 32768;   // 128 rows x 128 k bf16 = two 16 KB K-blocks
+constexpr uint32_t kKBlockBytes = 16384; // 128 rows x 64 k bf16 (one 128-byte swizzle span per row)
+constexpr uint32_t kW2Bytes = 16384;
+
+// shared memory map (offsets from a 1024-aligned base)
+constexpr uint32_t kOffW3 = 0;
+constexpr uint32_t kOffH2 = kOffW3 + kStages * kSlabBytes;   // 2 halves x 32 KB
+constexpr uint32_t kOffH1 = kOffH2 + 2 * kSlabBytes;         // 2 halves x 16 KB
+constexpr uint32_t kOffW2 = kOffH1 + 2 * kKBlockBytes;
+constexpr uint32_t kOffPar = kOffW2 + kW2Bytes;              // W1p[64][4] f32, b2f[128] f32
+constexpr uint32_t kParBytes = 64 * 16 + 128 * 4;
+constexpr uint32_t kOffBar = kOffPar + kParBytes;
+constexpr uint32_t kNumBars = 32;
+constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16;
+constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;           // slack for manual 1024-byte alignment
+
+enum Bar : int {
+  W3_FULL = 0,   // [3]
+  W3_EMPTY = 3,  // [3]
+  H1_FULL = 6,   // [2]
+  H1_EMPTY = 8,  // [2]
+  A2_FULL = 10,  // [2]
+  A2_EMPTY = 12, // [2]
+  H2_FULL = 14,  // [2]
+  H2_EMPTY = 16, // [1]
+  A3_FULL = 17,  // [2]
+  A3_EMPTY = 19, // [2]
+  W2_FULL = 21   // [1]
+};
+
+// packed parameter buffer (global), produced by pointnet_pack_kernel
+__host__ __device__ inline size_t packed_off_w3() { return kW2Bytes; }
+__host__ __device__ inline size_t packed_off_par(int F) { return kW2Bytes + (size_t)(F / 128) * kSlabBytes; }
+__host__ __device__ inline size_t packed_bytes(int F) { return packed_off_par(F) + kParBytes + (size_t)F * 4; }
+
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B tile of 64 bf16 per row
+__host__ __device__ inline uint32_t sw128_off(int row, int k) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+// ---------------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ unsigned int g_pointnet_timeout = 0;  // set when a wait gives up (kernel then traps instead of hanging)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s: a protocol bug, never a legitimate wait
+      atomicExch(&g_pointnet_timeout, 1u + (bar & 0xffffu));
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO(ignored)=1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+// kind::f16, A = B = bf16, D = f32, both K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// relu + round-to-nearest-even bf16 pack: low half <- a, high half <- b
+__device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t enc_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+struct FwdParams {
+  const float* x;        // [B,3,P]
+  int B, P, F;
+  const char* packed;
+  uint32_t* enc;         // [B,F] order-preserving encoding of the running max (zeroed before launch)
+  int tiles_per_cloud;
+  int total_units;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+template <int NSLAB>
+__global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar0 = base + kOffBar;
+  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kOffBar + kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const int u_begin = (int)(((long long)p.total_units * blockIdx.x) / G);
+  const int u_end = (int)(((long long)p.total_units * (blockIdx.x + 1)) / G);
+  const int NU = u_end - u_begin;
+
+  // ---- one-time setup ----
+  {
+    const float* par = reinterpret_cast<const float*>(p.packed + packed_off_par(p.F));
+    float* spar = reinterpret_cast<float*>(sm + kOffPar);
+    for (int i = threadIdx.x; i < (int)(kParBytes / 4); i += kThreads) spar[i] = par[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar(W3_FULL + i), 1); mbar_init(bar(W3_EMPTY + i), 1); }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar(H1_FULL + h), kHalfPts); mbar_init(bar(H1_EMPTY + h), 1);
+      mbar_init(bar(A2_FULL + h), 1);        mbar_init(bar(A2_EMPTY + h), kHalfPts);
+      mbar_init(bar(H2_FULL + h), kHalfPts);
+      mbar_init(bar(A3_FULL + h), 1);        mbar_init(bar(A3_EMPTY + h), kHalfPts);
+    }
+    mbar_init(bar(H2_EMPTY), 1);
+    mbar_init(bar(W2_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== bulk-copy producer ===========================
+    if (lane == 0 && NU > 0) {
+      mbar_expect_tx(bar(W2_FULL), kW2Bytes);
+      bulk_g2s(base + kOffW2, p.packed, kW2Bytes, bar(W2_FULL));
+      const char* w3 = p.packed + packed_off_w3();
+      uint32_t n = 0;
+      for (int u = 0; u < NU; ++u) {
+        for (int s = 0; s < NSLAB; ++s, ++n) {
+          const uint32_t stage = n % kStages, use = n / kStages;
+          mbar_wait(bar(W3_EMPTY + stage), (use & 1u) ^ 1u);
+          mbar_expect_tx(bar(W3_FULL + stage), kSlabBytes);
+          const uint32_t dst = base + kOffW3 + stage * kSlabBytes;
+          const char* src = w3 + (size_t)s * kSlabBytes;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) bulk_g2s(dst + c * 8192u, src + c * 8192, 8192u, bar(W3_FULL + stage));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0 && NU > 0) {
+      mbar_wait(bar(W2_FULL), 0);
+      const uint64_t w2_desc = umma_desc_sw128(base + kOffW2);
+      uint32_t acc_n = 0, slab_n = 0;
+      for (int u = 0; u < NU; ++u) {
+        const uint32_t uph = (uint32_t)u & 1u;
+        // layer 2: D2[point][channel] = h1[point][k] * W2'[channel][k]^T
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar(H1_FULL + h), uph);
+          mbar_wait(bar(A2_EMPTY + h), uph ^ 1u);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(base + kOffH1 + h * kKBlockBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + 256u + 128u * h, a_desc + 2u * k, w2_desc + 2u * k, k > 0);
+          umma_commit(bar(A2_FULL + h));
+          umma_commit(bar(H1_EMPTY + h));
+        }
+        // layer 3: D3[channel][point] = W3'[channel][k] * h2[point][k]^T, slab by slab, both halves per slab
+        for (int s = 0; s < NSLAB; ++s, ++slab_n) {
+          const uint32_t stage = slab_n % kStages;
+          mbar_wait(bar(W3_FULL + stage), (slab_n / kStages) & 1u);
+          const uint64_t a0 = umma_desc_sw128(base + kOffW3 + stage * kSlabBytes);
+          for (int h = 0; h < 2; ++h, ++acc_n) {
+            if (s == 0) mbar_wait(bar(H2_FULL + h), uph);
+            const uint32_t buf = acc_n & 1u;
+            mbar_wait(bar(A3_EMPTY + buf), ((acc_n >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint64_t b0 = umma_desc_sw128(base + kOffH2 + h * kSlabBytes);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint32_t koff = (uint32_t)(kk >> 2) * (kKBlockBytes >> 4) + (uint32_t)(kk & 3) * 2u;
+              umma_bf16(tmem + 128u * buf, a0 + koff, b0 + koff, kk > 0);
+            }
+            umma_commit(bar(A3_FULL + buf));
+          }
+          umma_commit(bar(W3_EMPTY + stage));
+        }
+        umma_commit(bar(H2_EMPTY));
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =========================== layer-3 epilogue: running max over points ===========================
+    const int q = warp & 3;
+    float rmax[NSLAB];
+#pragma unroll
+    for (int s = 0; s < NSLAB; ++s) rmax[s] = -INFINITY;
+    int cur_cloud = -1;
+    uint32_t acc_n = 0;
+    auto flush = [&](int cloud) {
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) {
+        atomicMax(p.enc + (size_t)cloud * p.F + s * 128 + q * 32 + lane, enc_ordered(rmax[s]));
+        rmax[s] = -INFINITY;
+      }
+    };
+    for (int u = 0; u < NU; ++u) {
+      const int cloud = (u_begin + u) / p.tiles_per_cloud;
+      if (cloud != cur_cloud) {
+        if (cur_cloud >= 0) flush(cur_cloud);
+        cur_cloud = cloud;
+      }
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h, ++acc_n) {
+          const uint32_t buf = acc_n & 1u;
+          mbar_wait(bar(A3_FULL + buf), (acc_n >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 128u * buf;
+          float m = rmax[s];
+#pragma unroll
+          for (int c = 0; c < 4; c += 2) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + 32u * c, r0);
+            tmem_ld32(taddr + 32u * (c + 1), r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              m = max3(m, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+              m = max3(m, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar(A3_EMPTY + buf));
+          rmax[s] = m;
+        }
+      }
+    }
+    if (cur_cloud >= 0) flush(cur_cloud);
+  } else if (warp >= 8) {
+    // =========================== front end: layer 1 + layer-2 epilogue ===========================
+    const int t = threadIdx.x - 256;  // point row inside a half; also the TMEM lane
+    const int q = warp & 3;
+    const float4* w1p = reinterpret_cast<const float4*>(sm + kOffPar);
+    const float4* b2f = reinterpret_cast<const float4*>(sm + kOffPar + 64 * 16);
+
+    auto layer1 = [&](int u) {
+      const int unit = u_begin + u;
+      const int cloud = unit / p.tiles_per_cloud;
+      const int p_base = (unit - cloud * p.tiles_per_cloud) * kUnitPts;
+      const uint32_t uph = (uint32_t)u & 1u;
+      const float* xc = p.x + (size_t)cloud * 3 * p.P;
+      for (int h = 0; h < 2; ++h) {
+        int pt = p_base + h * kHalfPts + t;
+        pt = pt < p.P ? pt : p.P - 1;  // ragged tail: repeat the last real point (max is idempotent)
+        const float x0 = __ldg(xc + pt), x1 = __ldg(xc + p.P + pt), x2 = __ldg(xc + 2 * p.P + pt);
+        mbar_wait(bar(H1_EMPTY + h), uph ^ 1u);
+        uint8_t* dst = sm + kOffH1 + h * kKBlockBytes;
+#pragma unroll
+        for (int cg = 0; cg < 8; ++cg) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = w1p[cg * 8 + j];
+            v[j] = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
+          }
+          uint4 o;
+          o.x = pack_relu_bf16(v[0], v[1]); o.y = pack_relu_bf16(v[2], v[3]);
+          o.z = pack_relu_bf16(v[4], v[5]); o.w = pack_relu_bf16(v[6], v[7]);
+          *reinterpret_cast<uint4*>(dst + sw128_off(t, cg * 8)) = o;
+        }
+        fence_proxy_async();
+        mbar_arrive(bar(H1_FULL + h));
+      }
+    };
+
+    if (NU > 0) layer1(0);
+    for (int u = 0; u < NU; ++u) {
+      const uint32_t uph = (uint32_t)u & 1u;
+      mbar_wait(bar(H2_EMPTY), uph ^ 1u);  // layer 3 of the previous unit has finished reading h2
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(bar(A2_FULL + h), uph);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u + 128u * h;
+        uint8_t* dst = sm + kOffH2 + h * kSlabBytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // 32 channels per TMEM load
+          uint32_t r[32];
+          tmem_ld32(taddr + 32u * c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int ch = c * 32 + g8 * 8;
+            const float4 ba = b2f[ch / 4], bb = b2f[ch / 4 + 1];
+            uint4 o;
+            o.x = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 0]) + ba.x, __uint_as_float(r[g8 * 8 + 1]) + ba.y);
+            o.y = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 2]) + ba.z, __uint_as_float(r[g8 * 8 + 3]) + ba.w);
+            o.z = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 4]) + bb.x, __uint_as_float(r[g8 * 8 + 5]) + bb.y);
+            o.w = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 6]) + bb.z, __uint_as_float(r[g8 * 8 + 7]) + bb.w);
+            *reinterpret_cast<uint4*>(dst + (ch >> 6) * kKBlockBytes + sw128_off(t, ch & 63)) = o;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar(A2_EMPTY + h));
+        fence_proxy_async();
+        mbar_arrive(bar(H2_FULL + h));
+      }
+      if (u + 1 < NU) layer1(u + 1);  // overlaps with layer 3 of unit u on the tensor pipe
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// out[b,c] = max over points (decoded) + folded BN3 shift
+__global__ void __launch_bounds__(256) pointnet_finalize_kernel(const uint32_t* __restrict__ enc,
+                                                                const float* __restrict__ shift3, int B, int F,
+                                                                float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * F) out[i] = dec_ordered(enc[i]) + shift3[i % F];
+}
+
+struct PackParams {
+  const float *c1w, *c1b, *c2w, *c2b, *c3w, *c3b;
+  const float *g1, *be1, *m1, *v1, *g2, *be2, *m2, *v2, *g3, *be3, *m3, *v3;
+  float eps;
+  int F;
+  char* packed;
+};
+
+// Fold eval-mode BN into the convolutions (fp32) and write the bf16 operand images + fp32 side parameters.
+__global__ void __launch_bounds__(256) pointnet_pack_kernel(const PackParams a) {
+  const int F = a.F;
+  const int nW2 = 128 * 64, nW3 = F * 128, nW1 = 64, nB2 = 128, nS3 = F;
+  const int total = nW2 + nW3 + nW1 + nB2 + nS3;
+  __nv_bfloat16* w2img = reinterpret_cast<__nv_bfloat16*>(a.packed);
+  char* w3img = a.packed + packed_off_w3();
+  float* par = reinterpret_cast<float*>(a.packed + packed_off_par(F));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < nW2) {
+      const int c = i / 64, k = i % 64;
+      const float sc = a.g2[c] * rsqrtf(a.v2[c] + a.eps);
+      *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(w2img) + sw128_off(c, k)) =
+          __float2bfloat16_rn(a.c2w[c * 64 + k] * sc);
+    } else if (i < nW2 + nW3) {
+      const int j = i - nW2;
+      const int c = j / 128, k = j % 128;
+      const float sc = a.g3[c] * rsqrtf(a.v3[c] + a.eps);
+      char* slab = w3img + (size_t)(c / 128) * kSlabBytes + (size_t)(k / 64) * kKBlockBytes;
+      *reinterpret_cast<__nv_bfloat16*>(slab + sw128_off(c % 128, k % 64)) = __float2bfloat16_rn(a.c3w[c * 128 + k] * sc);
+    } else if (i < nW2 + nW3 + nW1) {
+      const int c = i - nW2 - nW3;
+      const float sc = a.g1[c] * rsqrtf(a.v1[c] + a.eps);
+      par[c * 4 + 0] = a.c1w[c * 3 + 0] * sc;
+      par[c * 4 + 1] = a.c1w[c * 3 + 1] * sc;
+      par[c * 4 + 2] = a.c1w[c * 3 + 2] * sc;
+      par[c * 4 + 3] = (a.c1b[c] - a.m1[c]) * sc + a.be1[c];
+    } else if (i < nW2 + nW3 + nW1 + nB2) {
+      const int c = i - nW2 - nW3 - nW1;
+      const float sc = a.g2[c] * rsqrtf(a.v2[c] + a.eps);
+      par[64 * 4 + c] = (a.c2b[c] - a.m2[c]) * sc + a.be2[c];
+    } else {
+      const int c = i - nW2 - nW3 - nW1 - nB2;
+      const float sc = a.g3[c] * rsqrtf(a.v3[c] + a.eps);
+      par[64 * 4 + 128 + c] = (a.c3b[c] - a.m3[c]) * sc + a.be3[c];
+    }
+  }
+}
+
+}  // namespace pn
+}  // namespace crdpn
+
+using namespace crdpn;
+
+static bool pointnet_f_ok(int64_t F) { return F == 128 || F == 256 || F == 512 || F == 1024; }
+
+extern "C" int crdpn_pointnet_packed_bytes(int64_t F, size_t* bytes) {
+  if (!bytes) return fail(CRDPN_E_BADARG, "crdpn_pointnet_packed_bytes: null pointer");
+  if (!pointnet_f_ok(F)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet: feature_dim must be 128, 256, 512 or 1024");
+  *bytes = pn::packed_bytes((int)F);
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_pointnet_pack(const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+                                   const float* conv3_w, const float* conv3_b,
+                                   const float* bn1_w, const float* bn1_b, const float* bn1_mean, const float* bn1_var,
+                                   const float* bn2_w, const float* bn2_b, const float* bn2_mean, const float* bn2_var,
+                                   const float* bn3_w, const float* bn3_b, const float* bn3_mean, const float* bn3_var,
+                                   float bn_eps, int64_t F, void* packed, void* stream) {
+  if (!conv1_w || !conv1_b || !conv2_w || !conv2_b || !conv3_w || !conv3_b || !bn1_w || !bn1_b || !bn1_mean || !bn1_var ||
+      !bn2_w || !bn2_b || !bn2_mean || !bn2_var || !bn3_w || !bn3_b || !bn3_mean || !bn3_var || !packed)
+    return fail(CRDPN_E_BADARG, "crdpn_pointnet_pack: null pointer");
+  if (!pointnet_f_ok(F)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet: feature_dim must be 128, 256, 512 or 1024");
+  if ((uintptr_t)packed & 15) return fail(CRDPN_E_ALIGN, "crdpn_pointnet_pack: packed buffer must be 16-byte aligned");
+  pn::PackParams a{conv1_w, conv1_b, conv2_w, conv2_b, conv3_w, conv3_b, bn1_w, bn1_b, bn1_mean, bn1_var,
+                   bn2_w, bn2_b, bn2_mean, bn2_var, bn3_w, bn3_b, bn3_mean, bn3_var, bn_eps, (int)F, (char*)packed};
+  pn::pointnet_pack_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(a);
+  CRDPN_LAUNCH_CHECK("pointnet_pack_kernel");
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_pointnet_workspace_bytes(int64_t B, int64_t P, int64_t F, int device, size_t* bytes) {
+  (void)device;
+  if (!bytes || B <= 0 || P <= 0) return fail(CRDPN_E_BADARG, "crdpn_pointnet_workspace_bytes: bad argument");
+  if (!pointnet_f_ok(F)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet: feature_dim must be 128, 256, 512 or 1024");
+  *bytes = (size_t)B * (size_t)F * 4;
+  return CRDPN_OK;
+}
+
+template <int NSLAB>
+static int launch_pointnet(const pn::FwdParams& fp, int grid, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int device = 0;
+  CRDPN_CUDA(cudaGetDevice(&device));
+  if (!attr_set[device]) {
+    CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_eval_kernel<NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)pn::kSmemAlloc));
+    attr_set[device] = true;
+  }
+  {
+    ScopedKernelTimer tm(CRDPN_K_POINTNET_FWD, st);
+    pn::pointnet_fwd_eval_kernel<NSLAB><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);
+  }
+  CRDPN_LAUNCH_CHECK("pointnet_fwd_eval_kernel");
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_pointnet_forward_eval(const float* x, int64_t B, int64_t P, int64_t F, const void* packed,
+                                           float* out, void* workspace, size_t workspace_bytes, int variant,
+                                           void* stream) {
+  (void)variant;
+  if (!x || !packed || !out || !workspace) return fail(CRDPN_E_BADARG, "crdpn_pointnet_forward_eval: null pointer");
+  if (B <= 0 || P <= 0) return fail(CRDPN_E_BADARG, "crdpn_pointnet_forward_eval: bad size");
+  if (!pointnet_f_ok(F)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet: feature_dim must be 128, 256, 512 or 1024");
+  if (workspace_bytes < (size_t)B * (size_t)F * 4) return fail(CRDPN_E_WORKSPACE, "crdpn_pointnet_forward_eval: workspace too small");
+  if (((uintptr_t)packed & 15) || ((uintptr_t)workspace & 3)) return fail(CRDPN_E_ALIGN, "crdpn_pointnet_forward_eval: alignment");
+  if (B * ((P + pn::kUnitPts - 1) / pn::kUnitPts) >= (1ll << 30)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet_forward_eval: too many tiles");
+  int device = 0;
+  CRDPN_CUDA(cudaGetDevice(&device));
+  DeviceInfo di;
+  int rc = device_info(device, &di);
+  if (rc) return rc;
+  if (di.max_smem_optin < (int)pn::kSmemAlloc) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet_forward_eval: not enough shared memory");
+  cudaStream_t st = (cudaStream_t)stream;
+  pn::FwdParams fp;
+  fp.x = x; fp.B = (int)B; fp.P = (int)P; fp.F = (int)F;
+  fp.packed = (const char*)packed;
+  fp.enc = (uint32_t*)workspace;
+  fp.tiles_per_cloud = (int)((P + pn::kUnitPts - 1) / pn::kUnitPts);
+  fp.total_units = (int)B * fp.tiles_per_cloud;
+  CRDPN_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * (size_t)F * 4, st));
+  const int grid = fp.total_units < di.sms ? fp.total_units : di.sms;
+  switch (F / 128) {
+    case 1: rc = launch_pointnet<1>(fp, grid, st); break;
+    case 2: rc = launch_pointnet<2>(fp, grid, st); break;
+    case 4: rc = launch_pointnet<4>(fp, grid, st); break;
+    default: rc = launch_pointnet<8>(fp, grid, st); break;
+  }
+  if (rc) return rc;
+  const float* shift3 = reinterpret_cast<const float*>((const char*)packed + pn::packed_off_par((int)F) + 64 * 16 + 128 * 4);
+  const int n = (int)(B * F);
+  pn::pointnet_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint32_t*)workspace, shift3, (int)B, (int)F, out);
+  CRDPN_LAUNCH_CHECK("pointnet_finalize_kernel");
+  return CRDPN_OK;
+}

@@ -1,0 +1,107 @@
+"""PointNet point-cloud encoder -- drop-in for the reference's ``ShapeEncoderPC`` on B200 kernels.
+
+Mirrors ``auxiliary/model.py:154-180``: same constructor (``feature_dim=1024``), same sub-module /
+parameter / buffer names and shapes (``conv1.weight[64,3,1]`` ... ``bn3.running_var[F]``,
+``num_batches_tracked``), same default initialisation (the holders ARE ``nn.Conv1d`` / ``nn.BatchNorm1d``),
+so checkpoints load by key under the ``shape_encoder.`` prefix (``auxiliary/utils.py:56-73``) and the module
+slots into ``PoseEstimator`` at ``model.py:222-223,257``.
+
+forward(shapes[B,3,P] float32) -> [B, feature_dim] float32.
+
+* ``.eval()`` (the KD-time teacher, ``KD/common/base_class.py:317``): one fused sm_100a kernel
+  (``crdpn_pointnet_forward_eval``): BN folded into the weights, layers 2-3 on tcgen05 tensor cores in bf16
+  with fp32 accumulation, max over points fused into the GEMM epilogue.  The output carries no autograd
+  graph (the teacher is frozen in the KD loop; its gradients are never consumed).
+* ``.train()``: batch-statistics BatchNorm needs global per-channel statistics between layers; see
+  ``forward_train`` (added with the train-mode kernels).
+
+No CPU fallback: inputs must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _native
+
+BN_EPS = 1e-5
+
+
+class ShapeEncoderPC(nn.Module):
+    """Shape Encoder using point cloud (reference docstring: returns a tensor of size NxC)."""
+
+    def __init__(self, feature_dim: int = 1024):
+        super().__init__()
+        self.conv1 = torch.nn.Conv1d(3, 64, 1)
+        self.conv2 = torch.nn.Conv1d(64, 128, 1)
+        self.conv3 = torch.nn.Conv1d(128, feature_dim, 1)
+        self.bn1 = torch.nn.BatchNorm1d(64)
+        self.bn2 = torch.nn.BatchNorm1d(128)
+        self.bn3 = torch.nn.BatchNorm1d(feature_dim)
+        self.feature_dim = feature_dim
+        self.variant = 0
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+
+    # -- eval path -------------------------------------------------------------------------------------
+    def _pack_sources(self):
+        return [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv3.weight,
+                self.conv3.bias,
+                self.bn1.weight, self.bn1.bias, self.bn1.running_mean, self.bn1.running_var,
+                self.bn2.weight, self.bn2.bias, self.bn2.running_mean, self.bn2.running_var,
+                self.bn3.weight, self.bn3.bias, self.bn3.running_mean, self.bn3.running_var]
+
+    def _packed_params(self, device):
+        """bf16 tensor-core operand images with eval-mode BN folded in; rebuilt whenever a source tensor changes."""
+        src = self._pack_sources()
+        key = (device,) + tuple((t.data_ptr(), t._version) for t in src)
+        if key != self._packed_key:
+            for t in src:
+                if t.device != device or t.dtype != torch.float32:
+                    raise RuntimeError("ShapeEncoderPC parameters must be float32 on the input's CUDA device")
+            n = ctypes.c_size_t(0)
+            _native.check(_native.lib().crdpn_pointnet_packed_bytes(self.feature_dim, ctypes.byref(n)),
+                          "crdpn_pointnet_packed_bytes")
+            if self._packed is None or self._packed.numel() != n.value or self._packed.device != device:
+                self._packed = torch.empty(n.value, dtype=torch.uint8, device=device)
+            ptrs = [t.detach().contiguous().data_ptr() for t in src]
+            with torch.cuda.device(device):
+                rc = _native.lib().crdpn_pointnet_pack(*ptrs, BN_EPS, self.feature_dim, self._packed.data_ptr(),
+                                                       torch.cuda.current_stream(device).cuda_stream)
+            _native.check(rc, "crdpn_pointnet_pack")
+            self._packed_key = key
+        return self._packed
+
+    def forward_eval(self, shapes: torch.Tensor) -> torch.Tensor:
+        if not shapes.is_cuda:
+            raise RuntimeError("ShapeEncoderPC input must be a CUDA tensor: this package has no CPU fallback")
+        if shapes.dim() != 3 or shapes.shape[1] != 3:
+            raise RuntimeError(f"expected shapes[B,3,P], got {tuple(shapes.shape)}")
+        x = shapes.detach().to(torch.float32).contiguous()
+        B, _, P = x.shape
+        dev = x.device
+        packed = self._packed_params(dev)
+        n = ctypes.c_size_t(0)
+        _native.check(_native.lib().crdpn_pointnet_workspace_bytes(B, P, self.feature_dim, dev.index or 0,
+                                                                   ctypes.byref(n)), "crdpn_pointnet_workspace_bytes")
+        if self._ws is None or self._ws.numel() < n.value or self._ws.device != dev:
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
+        out = torch.empty(B, self.feature_dim, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _native.lib().crdpn_pointnet_forward_eval(x.data_ptr(), B, P, self.feature_dim, packed.data_ptr(),
+                                                           out.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                                           self.variant, torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(rc, "crdpn_pointnet_forward_eval")
+        return out.view(-1, self.feature_dim)
+
+    def forward(self, shapes: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            return self.forward_train(shapes)
+        return self.forward_eval(shapes)
+
+    def forward_train(self, shapes: torch.Tensor) -> torch.Tensor:
+        raise RuntimeError("ShapeEncoderPC: train-mode (batch-statistics BatchNorm) kernels are not built yet; "
+                           "call .eval() (the KD-time teacher configuration). There is no eager fallback.")

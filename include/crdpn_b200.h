@@ -118,6 +118,27 @@ int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int 
                               int64_t B, int64_t D, int64_t row_begin, int64_t row_end,
                               float momentum, float one_minus_momentum, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * PointNet encoder, eval-mode BatchNorm (the KD-time teacher, KD/common/base_class.py:317,363).
+ * Replaces: ShapeEncoderPC.forward, auxiliary/model.py:174-180 (conv1/bn1/relu, conv2/bn2/relu,
+ * conv3/bn3, max over points), BN folded into the weights by crdpn_pointnet_pack.
+ * ------------------------------------------------------------------------------------------------- */
+/* Fold BN (eval statistics) into the three 1x1 convolutions and pack the bf16 tensor-core operand images.
+ * All inputs f32 device pointers with the reference's state_dict shapes (model.py:162-172);
+ * F = feature_dim in {128,256,512,1024}. packed: crdpn_pointnet_packed_bytes(F) bytes, 16-byte aligned. */
+int crdpn_pointnet_packed_bytes(int64_t F, size_t* bytes);
+int crdpn_pointnet_pack(const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+                        const float* conv3_w, const float* conv3_b,
+                        const float* bn1_w, const float* bn1_b, const float* bn1_mean, const float* bn1_var,
+                        const float* bn2_w, const float* bn2_b, const float* bn2_mean, const float* bn2_var,
+                        const float* bn3_w, const float* bn3_b, const float* bn3_mean, const float* bn3_var,
+                        float bn_eps, int64_t F, void* packed, void* stream);
+/* x [B,3,P] f32 channel-first contiguous; out [B,F] f32. workspace: crdpn_pointnet_workspace_bytes. */
+int crdpn_pointnet_workspace_bytes(int64_t B, int64_t P, int64_t F, int device, size_t* bytes);
+int crdpn_pointnet_forward_eval(const float* x, int64_t B, int64_t P, int64_t F, const void* packed,
+                                float* out, void* workspace, size_t workspace_bytes, int variant,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif
