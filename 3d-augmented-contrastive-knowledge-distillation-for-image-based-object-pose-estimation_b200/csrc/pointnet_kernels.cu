@@ -273,6 +273,9 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
         }
         umma_commit(bar(H2_EMPTY));
       }
+      // commits retire in order: once the last one has landed no asynchronous arrive can hit this CTA's
+      // shared memory after it exits
+      mbar_wait(bar(H2_EMPTY), (uint32_t)(NU - 1) & 1u);
     }
   } else if (warp >= 4 && warp < 8) {
     // =========================== layer-3 epilogue: running max over points ===========================
