@@ -17,22 +17,26 @@
 // one per SM (persistent CTAs).  Each W3 slab (128 channels x 128 k, 32 KB bf16, pre-swizzled image in global
 // memory, L2 resident) is streamed by 1-D bulk async copies through a 3-stage ring and used for both halves.
 //
-// Warp roles (384 threads): w0 bulk-copy producer | w1 MMA issuer | w2 TMEM allocator | w3 idle
-//                           w4-7  layer-3 epilogue (TMEM -> running max)
-//                           w8-11 front end (layer 1 on CUDA cores, layer-2 epilogue)
+// Warp roles (512 threads): w0 bulk-copy producer | w1 MMA issuer | w2 TMEM allocator | w3 idle
+//                           w4-7   layer-3 epilogue A (accumulator ring slot 0 = first half of each unit)
+//                           w8-11  front end (layer 1 on CUDA cores, layer-2 epilogue)
+//                           w12-15 layer-3 epilogue B (ring slot 1 = second half)
+// The layer-2 MMAs of unit u+1 are issued before the last W3 slab of unit u, and h2 is released per half, so
+// the layer-2 epilogue of the next unit overlaps the tail of layer 3 instead of stalling the tensor pipe.
 // TMEM (512 columns): [0,256) two layer-3 accumulators (ring), [256,512) layer-2 accumulators (one per half).
 #include "common.cuh"
 
 namespace crdpn {
 namespace pn {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 constexpr int kHalfPts = 128;
 constexpr int kUnitPts = 256;
 constexpr int kStages = 3;
 constexpr uint32_t kSlabBytes = 32768;   // 128 rows x 128 k bf16 = two 16 KB K-blocks
 constexpr uint32_t kKBlockBytes = 16384; // 128 rows x 64 k bf16 (one 128-byte swizzle span per row)
 constexpr uint32_t kW2Bytes = 16384;
+constexpr size_t kDbgBytes = 256 * 32 * 8;  // optional per-CTA cycle counters behind the max buffer
 
 // shared memory map (offsets from a 1024-aligned base)
 constexpr uint32_t kOffW3 = 0;
@@ -54,10 +58,10 @@ enum Bar : int {
   A2_FULL = 10,  // [2]
   A2_EMPTY = 12, // [2]
   H2_FULL = 14,  // [2]
-  H2_EMPTY = 16, // [1]
-  A3_FULL = 17,  // [2]
-  A3_EMPTY = 19, // [2]
-  W2_FULL = 21   // [1]
+  H2_EMPTY = 16, // [2]
+  A3_FULL = 18,  // [2]
+  A3_EMPTY = 20, // [2]
+  W2_FULL = 22   // [1]
 };
 
 // packed parameter buffer (global), produced by pointnet_pack_kernel
@@ -98,6 +102,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -140,6 +149,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// exactly one lane of a converged warp (lets ptxas issue the uniform-datapath tcgen05 ops without a per-lane loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -166,6 +185,8 @@ struct FwdParams {
   uint32_t* enc;         // [B,F] order-preserving encoding of the running max (zeroed before launch)
   int tiles_per_cloud;
   int total_units;
+  long long* dbg;         // optional [grid][32] cycle counters (flags bit2), else null
+  int flags;             // bit0: rotate the slab order per CTA; bit1 (diagnostic, wrong results): load each ring stage once
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -184,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
   const int u_begin = (int)(((long long)p.total_units * blockIdx.x) / G);
   const int u_end = (int)(((long long)p.total_units * (blockIdx.x + 1)) / G);
   const int NU = u_end - u_begin;
+  const int rot = (p.flags & 1) ? (int)(blockIdx.x % NSLAB) : 0;  // CTAs walk the W3 slabs out of phase
 
   // ---- one-time setup ----
   {
@@ -196,10 +218,9 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar(H1_FULL + h), kHalfPts); mbar_init(bar(H1_EMPTY + h), 1);
       mbar_init(bar(A2_FULL + h), 1);        mbar_init(bar(A2_EMPTY + h), kHalfPts);
-      mbar_init(bar(H2_FULL + h), kHalfPts);
+      mbar_init(bar(H2_FULL + h), kHalfPts); mbar_init(bar(H2_EMPTY + h), 1);
       mbar_init(bar(A3_FULL + h), 1);        mbar_init(bar(A3_EMPTY + h), kHalfPts);
     }
-    mbar_init(bar(H2_EMPTY), 1);
     mbar_init(bar(W2_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -216,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
   if (warp == 0) {
     // =========================== bulk-copy producer ===========================
     if (lane == 0 && NU > 0) {
+      long long dw_p = 0;
       mbar_expect_tx(bar(W2_FULL), kW2Bytes);
       bulk_g2s(base + kOffW2, p.packed, kW2Bytes, bar(W2_FULL));
       const char* w3 = p.packed + packed_off_w3();
@@ -223,75 +245,102 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
       for (int u = 0; u < NU; ++u) {
         for (int s = 0; s < NSLAB; ++s, ++n) {
           const uint32_t stage = n % kStages, use = n / kStages;
-          mbar_wait(bar(W3_EMPTY + stage), (use & 1u) ^ 1u);
+          mbar_wait_t(bar(W3_EMPTY + stage), (use & 1u) ^ 1u, dw_p);
+          if ((p.flags & 2) && n >= kStages) { mbar_arrive(bar(W3_FULL + stage)); continue; }
           mbar_expect_tx(bar(W3_FULL + stage), kSlabBytes);
           const uint32_t dst = base + kOffW3 + stage * kSlabBytes;
-          const char* src = w3 + (size_t)s * kSlabBytes;
+          const char* src = w3 + (size_t)((s + rot) % NSLAB) * kSlabBytes;
 #pragma unroll
           for (int c = 0; c < 4; ++c) bulk_g2s(dst + c * 8192u, src + c * 8192, 8192u, bar(W3_FULL + stage));
         }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 32 + 6] = dw_p;
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (one thread) ===========================
-    if (lane == 0 && NU > 0) {
+    // =========================== MMA issuer (whole warp converged; one elected lane issues) ==============
+    if (NU > 0) {
+      long long dw[8] = {0};
+      const long long t_role = clock64();
       mbar_wait(bar(W2_FULL), 0);
-      const uint64_t w2_desc = umma_desc_sw128(base + kOffW2);
-      uint32_t acc_n = 0, slab_n = 0;
+      const uint32_t w2_lo = base + kOffW2;
+      uint32_t slab_n = 0;
+      // layer 2 of unit u: D2[point][channel] = h1[point][k] * W2'[channel][k]^T  (acc2[h] <- 4 MMAs, K = 64)
+      auto issue_layer2 = [&](int u) {
+        const uint32_t uph = (uint32_t)u & 1u;
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait_t(bar(H1_FULL + h), uph, dw[0]);
+          mbar_wait_t(bar(A2_EMPTY + h), uph ^ 1u, dw[1]);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_desc = umma_desc_sw128(base + kOffH1 + h * kKBlockBytes);
+            const uint64_t w2_desc = umma_desc_sw128(w2_lo);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem + 256u + 128u * h, a_desc + 2u * k, w2_desc + 2u * k, k > 0);
+            umma_commit(bar(A2_FULL + h));
+            umma_commit(bar(H1_EMPTY + h));
+          }
+          __syncwarp();
+        }
+      };
+      issue_layer2(0);
       for (int u = 0; u < NU; ++u) {
         const uint32_t uph = (uint32_t)u & 1u;
-        // layer 2: D2[point][channel] = h1[point][k] * W2'[channel][k]^T
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar(H1_FULL + h), uph);
-          mbar_wait(bar(A2_EMPTY + h), uph ^ 1u);
-          tc_fence_after();
-          const uint64_t a_desc = umma_desc_sw128(base + kOffH1 + h * kKBlockBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + 256u + 128u * h, a_desc + 2u * k, w2_desc + 2u * k, k > 0);
-          umma_commit(bar(A2_FULL + h));
-          umma_commit(bar(H1_EMPTY + h));
-        }
-        // layer 3: D3[channel][point] = W3'[channel][k] * h2[point][k]^T, slab by slab, both halves per slab
+        // layer 3: D3[channel][point] = W3'[channel][k] * h2[point][k]^T, slab by slab, both halves per slab;
+        // half h always lands in accumulator ring slot h (epilogue group h drains it)
         for (int s = 0; s < NSLAB; ++s, ++slab_n) {
+          if (s == NSLAB - 1 && u + 1 < NU) issue_layer2(u + 1);  // its epilogue overlaps the last slab below
           const uint32_t stage = slab_n % kStages;
-          mbar_wait(bar(W3_FULL + stage), (slab_n / kStages) & 1u);
-          const uint64_t a0 = umma_desc_sw128(base + kOffW3 + stage * kSlabBytes);
-          for (int h = 0; h < 2; ++h, ++acc_n) {
-            if (s == 0) mbar_wait(bar(H2_FULL + h), uph);
-            const uint32_t buf = acc_n & 1u;
-            mbar_wait(bar(A3_EMPTY + buf), ((acc_n >> 1) & 1u) ^ 1u);
+          mbar_wait_t(bar(W3_FULL + stage), (slab_n / kStages) & 1u, dw[2]);
+          const uint32_t use = (uint32_t)u * NSLAB + (uint32_t)s;  // per-slot use counter
+          for (int h = 0; h < 2; ++h) {
+            if (s == 0) mbar_wait_t(bar(H2_FULL + h), uph, dw[3]);
+            mbar_wait_t(bar(A3_EMPTY + h), (use & 1u) ^ 1u, dw[4]);
             tc_fence_after();
-            const uint64_t b0 = umma_desc_sw128(base + kOffH2 + h * kSlabBytes);
+            if (elect_one()) {
+              const uint64_t a0 = umma_desc_sw128(base + kOffW3 + stage * kSlabBytes);
+              const uint64_t b0 = umma_desc_sw128(base + kOffH2 + h * kSlabBytes);
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint32_t koff = (uint32_t)(kk >> 2) * (kKBlockBytes >> 4) + (uint32_t)(kk & 3) * 2u;
-              umma_bf16(tmem + 128u * buf, a0 + koff, b0 + koff, kk > 0);
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint32_t koff = (uint32_t)(kk >> 2) * (kKBlockBytes >> 4) + (uint32_t)(kk & 3) * 2u;
+                umma_bf16(tmem + 128u * h, a0 + koff, b0 + koff, kk > 0);
+              }
+              umma_commit(bar(A3_FULL + h));
+              if (s == NSLAB - 1) umma_commit(bar(H2_EMPTY + h));  // this half of h2 may be overwritten
+              if (h == 1) umma_commit(bar(W3_EMPTY + stage));
             }
-            umma_commit(bar(A3_FULL + buf));
+            __syncwarp();
           }
-          umma_commit(bar(W3_EMPTY + stage));
         }
-        umma_commit(bar(H2_EMPTY));
       }
       // commits retire in order: once the last one has landed no asynchronous arrive can hit this CTA's
       // shared memory after it exits
-      mbar_wait(bar(H2_EMPTY), (uint32_t)(NU - 1) & 1u);
+      const uint32_t last = slab_n - 1u;  // W3_EMPTY of the last slab is the very last commit
+      mbar_wait(bar(W3_EMPTY + last % kStages), (last / kStages) & 1u);
+      if (p.dbg && lane == 0) {
+        for (int i = 0; i < 5; ++i) p.dbg[blockIdx.x * 32 + i] = dw[i];
+        p.dbg[blockIdx.x * 32 + 5] = clock64() - t_role;
+      }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
     // =========================== layer-3 epilogue: running max over points ===========================
+    // group h (warps 4-7: h = 0, warps 12-15: h = 1) drains accumulator ring slot h
     const int q = warp & 3;
+    const int h = warp >= 12 ? 1 : 0;
     float rmax[NSLAB];
 #pragma unroll
     for (int s = 0; s < NSLAB; ++s) rmax[s] = -INFINITY;
     int cur_cloud = -1;
-    uint32_t acc_n = 0;
+    uint32_t use = 0;
+    long long dwait = 0;
+    const long long t_role = clock64();
     auto flush = [&](int cloud) {
 #pragma unroll
       for (int s = 0; s < NSLAB; ++s) {
-        atomicMax(p.enc + (size_t)cloud * p.F + s * 128 + q * 32 + lane, enc_ordered(rmax[s]));
+        atomicMax(p.enc + (size_t)cloud * p.F + ((s + rot) % NSLAB) * 128 + q * 32 + lane, enc_ordered(rmax[s]));
         rmax[s] = -INFINITY;
       }
     };
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 128u * h;
     for (int u = 0; u < NU; ++u) {
       const int cloud = (u_begin + u) / p.tiles_per_cloud;
       if (cloud != cur_cloud) {
@@ -299,39 +348,42 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
         cur_cloud = cloud;
       }
 #pragma unroll
-      for (int s = 0; s < NSLAB; ++s) {
+      for (int s = 0; s < NSLAB; ++s, ++use) {
+        mbar_wait_t(bar(A3_FULL + h), use & 1u, dwait);
+        tc_fence_after();
+        float m0 = rmax[s], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four independent chains
 #pragma unroll
-        for (int h = 0; h < 2; ++h, ++acc_n) {
-          const uint32_t buf = acc_n & 1u;
-          mbar_wait(bar(A3_FULL + buf), (acc_n >> 1) & 1u);
-          tc_fence_after();
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 128u * buf;
-          float m = rmax[s];
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + 32u * c, r0);
+          tmem_ld32(taddr + 32u * (c + 1), r1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 4; c += 2) {
-            uint32_t r0[32], r1[32];
-            tmem_ld32(taddr + 32u * c, r0);
-            tmem_ld32(taddr + 32u * (c + 1), r1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              m = max3(m, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
-              m = max3(m, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
-            }
+          for (int i = 0; i < 16; i += 2) {
+            m0 = max3(m0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+            m1 = max3(m1, __uint_as_float(r0[16 + i]), __uint_as_float(r0[17 + i]));
+            m2 = max3(m2, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+            m3 = max3(m3, __uint_as_float(r1[16 + i]), __uint_as_float(r1[17 + i]));
           }
-          tc_fence_before();
-          mbar_arrive(bar(A3_EMPTY + buf));
-          rmax[s] = m;
         }
+        tc_fence_before();
+        mbar_arrive(bar(A3_EMPTY + h));
+        rmax[s] = fmaxf(max3(m0, m1, m2), m3);
       }
     }
     if (cur_cloud >= 0) flush(cur_cloud);
-  } else if (warp >= 8) {
+    if (p.dbg && q == 0 && lane == 0) {
+      p.dbg[blockIdx.x * 32 + 8 + 2 * h] = dwait;
+      p.dbg[blockIdx.x * 32 + 9 + 2 * h] = clock64() - t_role;
+    }
+  } else if (warp >= 8 && warp < 12) {
     // =========================== front end: layer 1 + layer-2 epilogue ===========================
     const int t = threadIdx.x - 256;  // point row inside a half; also the TMEM lane
     const int q = warp & 3;
     const float4* w1p = reinterpret_cast<const float4*>(sm + kOffPar);
     const float4* b2f = reinterpret_cast<const float4*>(sm + kOffPar + 64 * 16);
+    long long dw[8] = {0};
+    const long long t_role = clock64();
 
     auto layer1 = [&](int u) {
       const int unit = u_begin + u;
@@ -343,7 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
         int pt = p_base + h * kHalfPts + t;
         pt = pt < p.P ? pt : p.P - 1;  // ragged tail: repeat the last real point (max is idempotent)
         const float x0 = __ldg(xc + pt), x1 = __ldg(xc + p.P + pt), x2 = __ldg(xc + 2 * p.P + pt);
-        mbar_wait(bar(H1_EMPTY + h), uph ^ 1u);
+        mbar_wait_t(bar(H1_EMPTY + h), uph ^ 1u, dw[0]);
+        const long long t_l1 = clock64();
         uint8_t* dst = sm + kOffH1 + h * kKBlockBytes;
 #pragma unroll
         for (int cg = 0; cg < 8; ++cg) {
@@ -360,15 +413,17 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
         }
         fence_proxy_async();
         mbar_arrive(bar(H1_FULL + h));
+        dw[4] += clock64() - t_l1;
       }
     };
 
     if (NU > 0) layer1(0);
     for (int u = 0; u < NU; ++u) {
       const uint32_t uph = (uint32_t)u & 1u;
-      mbar_wait(bar(H2_EMPTY), uph ^ 1u);  // layer 3 of the previous unit has finished reading h2
       for (int h = 0; h < 2; ++h) {
-        mbar_wait(bar(A2_FULL + h), uph);
+        mbar_wait_t(bar(A2_FULL + h), uph, dw[1]);
+        mbar_wait_t(bar(H2_EMPTY + h), uph ^ 1u, dw[2]);  // layer 3 of the previous unit has finished reading this half
+        const long long t_e2 = clock64();
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u + 128u * h;
         uint8_t* dst = sm + kOffH2 + h * kSlabBytes;
@@ -393,8 +448,14 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
         mbar_arrive(bar(A2_EMPTY + h));
         fence_proxy_async();
         mbar_arrive(bar(H2_FULL + h));
+        dw[5] += clock64() - t_e2;
       }
       if (u + 1 < NU) layer1(u + 1);  // overlaps with layer 3 of unit u on the tensor pipe
+    }
+    if (p.dbg && t == 0) {
+      p.dbg[blockIdx.x * 32 + 12] = dw[0]; p.dbg[blockIdx.x * 32 + 13] = dw[1]; p.dbg[blockIdx.x * 32 + 14] = dw[2];
+      p.dbg[blockIdx.x * 32 + 15] = clock64() - t_role; p.dbg[blockIdx.x * 32 + 16] = dw[4]; p.dbg[blockIdx.x * 32 + 17] = dw[5];
+      p.dbg[blockIdx.x * 32 + 18] = NU;
     }
   }
 
@@ -497,7 +558,7 @@ extern "C" int crdpn_pointnet_workspace_bytes(int64_t B, int64_t P, int64_t F, i
   (void)device;
   if (!bytes || B <= 0 || P <= 0) return fail(CRDPN_E_BADARG, "crdpn_pointnet_workspace_bytes: bad argument");
   if (!pointnet_f_ok(F)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet: feature_dim must be 128, 256, 512 or 1024");
-  *bytes = (size_t)B * (size_t)F * 4;
+  *bytes = (size_t)B * (size_t)F * 4 + pn::kDbgBytes;
   return CRDPN_OK;
 }
 
@@ -522,11 +583,10 @@ static int launch_pointnet(const pn::FwdParams& fp, int grid, cudaStream_t st) {
 extern "C" int crdpn_pointnet_forward_eval(const float* x, int64_t B, int64_t P, int64_t F, const void* packed,
                                            float* out, void* workspace, size_t workspace_bytes, int variant,
                                            void* stream) {
-  (void)variant;
   if (!x || !packed || !out || !workspace) return fail(CRDPN_E_BADARG, "crdpn_pointnet_forward_eval: null pointer");
   if (B <= 0 || P <= 0) return fail(CRDPN_E_BADARG, "crdpn_pointnet_forward_eval: bad size");
   if (!pointnet_f_ok(F)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet: feature_dim must be 128, 256, 512 or 1024");
-  if (workspace_bytes < (size_t)B * (size_t)F * 4) return fail(CRDPN_E_WORKSPACE, "crdpn_pointnet_forward_eval: workspace too small");
+  if (workspace_bytes < (size_t)B * (size_t)F * 4 + ((variant & 4) ? pn::kDbgBytes : 0)) return fail(CRDPN_E_WORKSPACE, "crdpn_pointnet_forward_eval: workspace too small");
   if (((uintptr_t)packed & 15) || ((uintptr_t)workspace & 3)) return fail(CRDPN_E_ALIGN, "crdpn_pointnet_forward_eval: alignment");
   if (B * ((P + pn::kUnitPts - 1) / pn::kUnitPts) >= (1ll << 30)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet_forward_eval: too many tiles");
   int device = 0;
@@ -542,6 +602,8 @@ extern "C" int crdpn_pointnet_forward_eval(const float* x, int64_t B, int64_t P,
   fp.enc = (uint32_t*)workspace;
   fp.tiles_per_cloud = (int)((P + pn::kUnitPts - 1) / pn::kUnitPts);
   fp.total_units = (int)B * fp.tiles_per_cloud;
+  fp.flags = variant;
+  fp.dbg = (variant & 4) ? (long long*)((char*)workspace + (((size_t)B * (size_t)F * 4 + 15) & ~(size_t)15)) : nullptr;
   CRDPN_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * (size_t)F * 4, st));
   const int grid = fp.total_units < di.sms ? fp.total_units : di.sms;
   switch (F / 128) {
