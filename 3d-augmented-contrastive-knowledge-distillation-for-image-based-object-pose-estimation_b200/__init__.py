@@ -14,7 +14,10 @@ There is no CPU fallback anywhere in this package.
 from . import _native  # noqa: F401
 from .crd import AliasMethod, ContrastLoss, ContrastMemory, CRDLoss, Embed, Normalize  # noqa: F401
 
-__all__ = ["AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize"]
+from .sharded import ShardedContrastMemory, ShardedCRDLoss, shard_bounds  # noqa: F401
+
+__all__ = ["AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize",
+           "ShardedContrastMemory", "ShardedCRDLoss", "shard_bounds"]
 try:  # added with the PointNet kernels
     from .pointnet import ShapeEncoderPC  # noqa: F401
     __all__.append("ShapeEncoderPC")

@@ -27,12 +27,12 @@ _SIGNATURES = {
                                           c_uint64, c_void_p, c_void_p]),
     "crdpn_crd_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
     "crdpn_crd_score": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
-                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                 c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_size_t, c_int, c_void_p]),
     "crdpn_crd_step": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                               c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                c_float, c_float, c_float, c_float, c_float, c_float,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "crdpn_crd_momentum_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,

@@ -180,6 +180,7 @@ class ContrastMemory(nn.Module):
         self.unigrams = torch.ones(self.nLem)
         self.multinomial = AliasMethod(self.unigrams, seed=seed)
         self.K = K
+        self.k_total = 0   # negatives per anchor over all shards (0: the K+1 columns of contrast_idx are all of them)
         self.variant = 0
         self.register_buffer("params", torch.tensor([K, T, -1, -1, momentum], dtype=torch.float32))
         stdv = 1.0 / math.sqrt(inputSize / 3)
@@ -264,7 +265,7 @@ class ContrastMemory(nn.Module):
         with torch.cuda.device(dev):
             rc = _native.lib().crdpn_crd_score(
                 m1.data_ptr(), m2.data_ptr(), stride, dt, v1.data_ptr(), v2.data_ptr(), idx.data_ptr(),
-                B, K1, D, self.nLem, self.row_begin, self.row_end,
+                B, K1, D, self.nLem, self.k_total, self.row_begin, self.row_end,
                 hp.T, Z1, Z2, EPS,
                 o1.data_ptr() if want_out else None, o2.data_ptr() if want_out else None,
                 res.data_ptr(), g1.data_ptr() if full else None, g2.data_ptr() if full else None,
@@ -295,7 +296,7 @@ class ContrastMemory(nn.Module):
         with torch.cuda.device(dev):
             rc = _native.lib().crdpn_crd_step(
                 m1.data_ptr(), m2.data_ptr(), stride, dt, v1.data_ptr(), v2.data_ptr(), idx.data_ptr(), y.data_ptr(),
-                B, K1, D, self.nLem, self.row_begin, self.row_end, hp.T, Z1, Z2, EPS, hp.m, 1.0 - hp.m,
+                B, K1, D, self.nLem, self.k_total, self.row_begin, self.row_end, hp.T, Z1, Z2, EPS, hp.m, 1.0 - hp.m,
                 res.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), ws.numel(), self.variant, _stream_ptr(dev))
         _native.check(rc, "crdpn_crd_step")
         return res, g1, g2
@@ -308,9 +309,12 @@ class ContrastMemory(nn.Module):
         """Hook for the sharded subclass: sum loss partials and grad_v over ranks."""
         return res, g1, g2
 
+    def _check_device(self, t, name):
+        _require_cuda(t, name)
+
     def _prepare(self, v1, v2, y, idx):
         for t, name in ((v1, "v1"), (v2, "v2"), (y, "y")):
-            _require_cuda(t, name)
+            self._check_device(t, name)
         if v1.dtype != torch.float32 or v2.dtype != torch.float32:
             raise RuntimeError("embeddings must be float32")
         v1, v2, y = v1.contiguous(), v2.contiguous(), y.contiguous().to(torch.int64)
@@ -318,7 +322,7 @@ class ContrastMemory(nn.Module):
         if idx is None:
             idx = self.multinomial.draw_contrast(y, K1)
         else:
-            _require_cuda(idx, "contrast_idx")
+            self._check_device(idx, "contrast_idx")
             idx = idx.contiguous().to(torch.int64)
             if idx.shape != (v1.shape[0], K1):
                 raise RuntimeError(f"contrast_idx must have shape [B, K+1] = {(v1.shape[0], K1)}, got {tuple(idx.shape)}")

@@ -667,7 +667,7 @@ static UpdateParams make_update_params(void* bank1, void* bank2, int64_t row_str
 // score (+ finalize); when `upd` is given the momentum update rides in the finalize launch.
 static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
                       const float* v1, const float* v2, const int64_t* contrast_idx,
-                      int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t row_begin, int64_t row_end,
+                      int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
                       float T, float Z1, float Z2, float eps, float* out_v1, float* out_v2, double* result,
                       float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes, int variant,
                       const UpdateParams* upd, void* stream) {
@@ -706,7 +706,8 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   double* anchor_part = (double*)(ws + 16);
   float* slots = (float*)(ws + 16 + align_up((size_t)B * 8 * sizeof(double), 16));
 
-  const double Kd = (double)(K1 - 1);
+  if (k_total < 0) return fail(CRDPN_E_BADARG, "crdpn_crd_score: k_total must be >= 0");
+  const double Kd = (double)(k_total > 0 ? k_total : (K1 - 1));  // negatives per anchor over ALL shards
   const double Pn = 1.0 / (double)n_data;
   const float mPn_f = (float)(Kd * Pn);
   const float c_f = (float)(Kd * Pn + (double)eps);
@@ -723,8 +724,8 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.inv_Z1 = full ? (float)(1.0 / (double)Z1) : 0.f;
   sp.inv_Z2 = full ? (float)(1.0 / (double)Z2) : 0.f;
   sp.c = c_f;
-  sp.inv_mPn = (K1 > 1) ? (float)(1.0 / (double)mPn_f) : 0.f;
-  sp.eps_over_mPn = (K1 > 1) ? (float)(((double)c_f - (double)mPn_f) / (double)mPn_f) : 0.f;
+  sp.inv_mPn = (Kd > 0) ? (float)(1.0 / (double)mPn_f) : 0.f;
+  sp.eps_over_mPn = (Kd > 0) ? (float)(((double)c_f - (double)mPn_f) / (double)mPn_f) : 0.f;
   sp.inv_BT = (float)(1.0 / ((double)B * (double)T));
   sp.out_v1 = out_v1; sp.out_v2 = out_v2;
   sp.slots = slots;
@@ -759,19 +760,19 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
 
 extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
                                const float* v1, const float* v2, const int64_t* contrast_idx,
-                               int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                               int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
                                int64_t row_begin, int64_t row_end,
                                float T, float Z1, float Z2, float eps,
                                float* out_v1, float* out_v2, double* result, float* grad_v1, float* grad_v2,
                                void* workspace, size_t workspace_bytes, int variant, void* stream) {
-  return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, row_begin, row_end,
+  return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin, row_end,
                     T, Z1, Z2, eps, out_v1, out_v2, result, grad_v1, grad_v2, workspace, workspace_bytes, variant,
                     nullptr, stream);
 }
 
 extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
                               const float* v1, const float* v2, const int64_t* contrast_idx, const int64_t* y,
-                              int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                              int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
                               int64_t row_begin, int64_t row_end,
                               float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
                               double* result, float* grad_v1, float* grad_v2,
@@ -781,7 +782,7 @@ extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int 
   if (rc) return rc;
   const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end,
                                             momentum, one_minus_momentum);
-  return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, row_begin, row_end,
+  return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin, row_end,
                     T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant,
                     &u, stream);
 }

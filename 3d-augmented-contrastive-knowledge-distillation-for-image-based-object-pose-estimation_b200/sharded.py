@@ -1,0 +1,174 @@
+"""Row-sharded CRD memory banks over 1/2/4/8 GPUs of one box (one process per GPU, torch.distributed / NCCL).
+
+The reference is single-process, single-GPU; this is the build's data-parallel
+extension of the CRD step:
+
+* both banks are sharded by sample index: rank r owns the contiguous rows ``shard_bounds(n_data, R, r)``;
+* the batch is data parallel: every rank embeds its own ``B_loc`` anchors;
+* exchange 1 (before the kernel): ONE all-gather of the packed ``(v1, v2, idx)`` rows -> all ``B`` anchors;
+* every rank scores all ``B`` anchors against the negatives that live in ITS shard (``crdpn_crd_step`` with
+  ``row_begin/row_end``; entries of other shards are dropped inside the kernel before any row is loaded) and
+  momentum-updates the positive rows it owns;
+* exchange 2 (after the kernel): ONE all-reduce of a packed fp64 buffer ``[loss_s, loss_t, sum_e1, sum_e2, count,
+  grad_v1[B,D], grad_v2[B,D]]`` (about 94 KB at B=46, D=128).
+
+Negatives: either a replicated ``contrast_idx[B, K+1]`` (parity mode: every rank scans the whole list and keeps
+what it owns -- results equal the unsharded module up to fp32 summation order), or ``local_negatives=True``:
+each rank draws / receives ``K_loc`` negatives inside its own shard (``contrast_idx[B, K_loc+1]`` per rank, column
+0 still the global positive index, which non-owners skip), so no rank ever touches another rank's index list and
+the per-rank bytes are exactly ``1/R`` of the total.  The NCE constant uses ``K = sum_r K_loc``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from .crd import ContrastMemory, Embed, _FusedCRDFunction
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous near-equal split of n rows: rank r owns [n*r//world, n*(r+1)//world)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def pack_anchor_rows(v1: torch.Tensor, v2: torch.Tensor, y: torch.Tensor, rows: int) -> torch.Tensor:
+    """[rows, 2D+2] fp32: v1 | v2 | y as two bit-cast fp32 words.  Rows beyond len(y) are padding (y = -1)."""
+    b, d = v1.shape
+    buf = torch.zeros(rows, 2 * d + 2, dtype=torch.float32, device=v1.device)
+    buf[:b, :d] = v1
+    buf[:b, d:2 * d] = v2
+    yy = torch.full((rows,), -1, dtype=torch.int64, device=v1.device)
+    yy[:b] = y
+    buf[:, 2 * d:] = yy.view(-1, 1).view(torch.float32).view(rows, 2)
+    return buf
+
+
+def unpack_anchor_rows(buf: torch.Tensor, counts: list[int], rows: int, d: int):
+    """Inverse of pack_anchor_rows over the gathered [world*rows, 2D+2] buffer -> (v1[B,D], v2[B,D], y[B])."""
+    keep = torch.cat([torch.arange(r * rows, r * rows + c, device=buf.device) for r, c in enumerate(counts)])
+    sel = buf.index_select(0, keep)
+    y = sel[:, 2 * d:].contiguous().view(torch.int64).view(-1)
+    return sel[:, :d].contiguous(), sel[:, d:2 * d].contiguous(), y
+
+
+class _GatherAnchors(torch.autograd.Function):
+    """All-gather of the local (v1, v2) rows; backward hands each rank the gradient rows of its own anchors
+    (the gradients are already summed over ranks by the packed all-reduce of the step)."""
+
+    @staticmethod
+    def forward(ctx, v1, v2, y, owner):
+        ctx.owner = owner
+        ctx.b_loc = v1.shape[0]
+        g1, g2, gy = owner._gather(v1, v2, y)
+        ctx.mark_non_differentiable(gy)
+        return g1, g2, gy
+
+    @staticmethod
+    def backward(ctx, d1, d2, _dy):
+        lo = ctx.owner._anchor_offset
+        return d1[lo:lo + ctx.b_loc].contiguous(), d2[lo:lo + ctx.b_loc].contiguous(), None, None
+
+
+class ShardedContrastMemory(ContrastMemory):
+    """ContrastMemory holding rows [row_begin,row_end) of the global banks; collectives on ``group``."""
+
+    def __init__(self, inputSize, outputSize, K, T=0.07, momentum=0.5, group=None, rank=None, world_size=None,
+                 local_negatives=False, **kw):
+        self.group = group
+        self.world_size = dist.get_world_size(group) if world_size is None else world_size
+        self.rank = dist.get_rank(group) if rank is None else rank
+        lo, hi = shard_bounds(outputSize, self.world_size, self.rank)
+        super().__init__(inputSize, outputSize, K, T, momentum, row_begin=lo, row_end=hi, **kw)
+        self.local_negatives = local_negatives
+        if local_negatives:
+            self.k_total = K * self.world_size  # every rank contributes K in-shard negatives per anchor
+        self._counts = None
+
+    # -- collectives (the only places that talk to torch.distributed) ---------------------------------------
+    def _all_reduce(self, t):
+        if self.world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def _all_gather_rows(self, buf):
+        out = torch.empty(self.world_size * buf.shape[0], buf.shape[1], dtype=buf.dtype, device=buf.device)
+        if self.world_size > 1:
+            dist.all_gather_into_tensor(out, buf, group=self.group)
+        else:
+            out.copy_(buf)
+        return out
+
+    def _reduce_sums(self, res):
+        return self._all_reduce(res)
+
+    def _reduce_partials(self, res, g1, g2):
+        B, D = g1.shape
+        buf = torch.empty(8 + 2 * B * D, dtype=torch.float64, device=g1.device)
+        buf[:8] = res
+        buf[8:8 + B * D] = g1.reshape(-1)
+        buf[8 + B * D:] = g2.reshape(-1)
+        self._all_reduce(buf)  # ONE packed exchange after the kernel
+        return (buf[:8], buf[8:8 + B * D].to(torch.float32).view(B, D),
+                buf[8 + B * D:].to(torch.float32).view(B, D))
+
+    def _gather(self, v1, v2, y):
+        """ONE packed exchange before the kernel: local anchors -> all anchors (uneven B_loc allowed)."""
+        b_loc = torch.tensor([v1.shape[0]], dtype=torch.int64, device=v1.device)
+        if self._counts is None or self._counts[self.rank] != v1.shape[0]:
+            cnt = torch.zeros(self.world_size, dtype=torch.int64, device=v1.device)
+            cnt[self.rank] = b_loc[0]
+            self._counts = self._all_reduce(cnt).tolist()  # once per batch-shape change
+        counts = self._counts
+        rows = max(counts)
+        self._anchor_offset = sum(counts[:self.rank])
+        gathered = self._all_gather_rows(pack_anchor_rows(v1, v2, y, rows))
+        return unpack_anchor_rows(gathered, counts, rows, v1.shape[1])
+
+    def _prepare(self, v1, v2, y, idx):
+        if idx is None and self.local_negatives:
+            # in-shard negatives from this rank's own Philox stream; column 0 stays the global positive index
+            rows = self.row_end - self.row_begin
+            K1 = self._host_params().K + 1
+            if getattr(self, "_local_sampler", None) is None:
+                from .crd import AliasMethod
+                self._local_sampler = AliasMethod(torch.ones(rows), seed=self.multinomial.seed + 7919 * (self.rank + 1))
+                self._local_sampler.to(v1.device)
+            idx = self._local_sampler.draw_contrast(y.contiguous().to(torch.int64), K1)
+            idx[:, 1:] += self.row_begin
+        return super()._prepare(v1, v2, y, idx)
+
+    def fused_loss(self, v1, v2, y, idx=None):
+        """v1, v2, y: this rank's LOCAL anchors; idx: replicated [B, K+1] or per-rank [B, K_loc+1]."""
+        g1, g2, gy = _GatherAnchors.apply(v1, v2, y, self)
+        g1c, g2c, gy, idx = self._prepare(g1, g2, gy, idx)
+        return _FusedCRDFunction.apply(g1c, g2c, gy, idx, self)
+
+
+class ShardedCRDLoss(nn.Module):
+    """CRDLoss over row-sharded banks.  forward(f_s_local, f_t_local, idx_local, contrast_idx) -> global loss.
+
+    The returned loss is the loss of the WHOLE batch (identical on every rank); its gradient w.r.t. the local
+    features and this rank's embed parameters covers the local anchors only, so embed-parameter gradients must be
+    SUMMED over ranks (``allreduce_embed_grads``) to equal the single-GPU gradients."""
+
+    def __init__(self, opt, group=None, rank=None, world_size=None, local_negatives=False, **memory_kwargs):
+        super().__init__()
+        self.embed_s = Embed(opt.s_dim, opt.feat_dim)
+        self.embed_t = Embed(opt.t_dim, opt.feat_dim)
+        self.contrast = ShardedContrastMemory(opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m, group=group,
+                                              rank=rank, world_size=world_size, local_negatives=local_negatives,
+                                              **memory_kwargs)
+
+    def forward(self, f_s, f_t, idx, contrast_idx=None):
+        return self.contrast.fused_loss(self.embed_s(f_s), self.embed_t(f_t), idx, contrast_idx)
+
+    def allreduce_embed_grads(self):
+        grads = [p.grad for p in list(self.embed_s.parameters()) + list(self.embed_t.parameters()) if p.grad is not None]
+        if grads and self.contrast.world_size > 1:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, group=self.contrast.group)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()

@@ -1,0 +1,131 @@
+"""Multi-GPU leg of bench.py (launched by torchrun, one rank per GPU, NCCL).
+
+Weak scaling of the CRD step (BASELINE.json configs[3] generalised): every rank owns a 1M-row shard of both banks
+(global N = R x 1M) and scores the B=46 anchors of the global batch against K_loc = 65536 negatives drawn inside its
+own shard (global K = R x 65536).  Per step: one packed all-gather of the anchors' embeddings, one fused
+score+loss+backward pass per rank over its shard, one packed all-reduce of the partials, owner-only momentum update.
+value = scores of ALL ranks / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import time
+
+from bench import (HEADLINE, SEED, ClockSampler, algorithmic_bytes, make_opt, scores_per_step, workload_name)
+
+
+def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
+    c = dict(HEADLINE)
+    K_loc, N_loc, B, D = c["K"], c["N"], c["B"], c["D"]
+    cg = dict(c, N=N_loc * world)                       # global bank
+    opt = make_opt(cg)
+    torch.manual_seed(SEED + rank)
+    crit = pkg.ShardedCRDLoss(opt, local_negatives=True).to(dev)
+    mem = crit.contrast
+    lo, hi = mem.row_begin, mem.row_end
+    # global batch, identical on every rank (seeded); each rank embeds its slice of the anchors
+    g = torch.Generator().manual_seed(SEED)
+    f_s = torch.randn(B, c["s_dim"], generator=g)
+    f_t = torch.randn(B, c["t_dim"], generator=g)
+    y = torch.randperm(cg["N"], generator=g)[:B]
+    counts = [B * (r + 1) // world - B * r // world for r in range(world)]
+    a0 = sum(counts[:rank])
+    sl = slice(a0, a0 + counts[rank])
+    gl = torch.Generator().manual_seed(SEED * 1000 + rank)
+    cidx = torch.randint(lo, hi, (B, K_loc + 1), generator=gl)
+    cidx[:, 0] = y
+    for p_ in list(crit.embed_s.parameters()) + list(crit.embed_t.parameters()):  # same heads on every rank
+        dist.broadcast(p_.data, src=0)
+    f_s_d, f_t_d, y_d, cidx_d = f_s[sl].to(dev), f_t[sl].to(dev), y[sl].to(dev), cidx.to(dev)
+    with torch.no_grad():
+        v1 = crit.embed_s(f_s_d).contiguous()
+        v2 = crit.embed_t(f_t_d).contiguous()
+
+    def step():
+        g1, g2, gy = mem._gather(v1, v2, y_d)                      # exchange 1
+        mem._freeze_z(g1, g2, cidx_d)
+        hp = mem._host_params()
+        res, d1, d2 = mem._step(g1, g2, gy, cidx_d, hp.Z1, hp.Z2)   # local shard
+        return mem._reduce_partials(res, d1, d2)                   # exchange 2
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    lib = pkg._native.lib()
+    lib.crdpn_timing_enable(1)
+    tot, n = ctypes.c_double(), ctypes.c_uint64()
+    lib.crdpn_timing_read(0, ctypes.byref(tot), ctypes.byref(n))
+    l0 = pkg._native.launch_count()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / args.steps
+    lib.crdpn_timing_read(0, ctypes.byref(tot), ctypes.byref(n))
+    lib.crdpn_timing_enable(0)
+    kms = torch.tensor([tot.value / max(n.value, 1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    launches = pkg._native.launch_count() - l0
+
+    # end to end through the public API with pinned HOST inputs on every rank
+    host = [t.pin_memory() for t in (f_s[sl].contiguous(), f_t[sl].contiguous(), y[sl].contiguous(), cidx)]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def e2e_step():
+        a, b, yy, ci = [t.to(dev, non_blocking=True) for t in host]
+        a.requires_grad_()
+        crit.zero_grad(set_to_none=True)
+        loss = crit(a, b, yy, ci)
+        loss.backward()
+        return loss.item()
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    esteps = max(args.steps // 4, 5)
+    for _ in range(esteps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / esteps], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+
+    total_scores = 2 * B * (K_loc * world + 1)
+    per_rank_bytes = algorithmic_bytes(c)
+    achieved = per_rank_bytes / (kms.item() * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "crd_negatives_scored_per_sec", "value": total_scores / (ms_step * 1e-3), "unit": "scores/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(c, world), "B": B, "D": D, "K_per_rank": K_loc, "K_global": K_loc * world,
+                       "N_per_rank": N_loc, "N_global": N_loc * world, "banks": 2, "parallelism": f"bank-shard{world}",
+                       "bank_layout": "interleaved [N_loc,2,D] fp32 per rank",
+                       "l2": "inputs larger than L2 (1.02 GB of banks per rank, random rows); no flush",
+                       "step": "all-gather(anchors) + crdpn_crd_step on the local shard + packed all-reduce(partials)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "crd_score_kernel (per rank, slowest rank)",
+                         "kernel_ms": kms.item(), "algorithmic_bytes": per_rank_bytes},
+            "e2e": {"value": total_scores / (e2e_ms.item() * 1e-3), "unit": "scores/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms.item(),
+                    "api": "ShardedCRDLoss(f_s_loc, f_t_loc, idx_loc, contrast_idx_loc).backward(), pinned host inputs"},
+            "gpu_launches": launches, "collectives_per_step": 2,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()

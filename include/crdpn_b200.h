@@ -82,7 +82,8 @@ int crdpn_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t n
  *
  * bank1/bank2: [row_end-row_begin, D] rows of `bank_dtype`, row_stride in ELEMENTS (both banks share it;
  *              an interleaved [N,2,D] allocation is bank2 = bank1 + D, row_stride = 2D).
- * v1,v2 [B,D] f32; contrast_idx [B,K1] int64 (column 0 = positive); K = K1-1.
+ * v1,v2 [B,D] f32; contrast_idx [B,K1] int64 (column 0 = positive).  k_total = number of negatives per anchor
+ * over ALL shards (the K of the NCE constant K*Pn); pass 0 for "K1-1" (single shard, or a replicated index list).
  * out_v1/out_v2: optional [B,K1] f32 (o, or raw e in sum mode; 0 for entries outside the shard).
  * result: 8 doubles {loss_s, loss_t, sum_e1, sum_e2, count, 0,0,0}.  grad_v1/grad_v2 [B,D] f32 (written
  * only in full mode).  variant: 0 = default kernel; other values select tuning variants (bench only).
@@ -90,7 +91,7 @@ int crdpn_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t n
 int crdpn_crd_workspace_bytes(int64_t B, int64_t K1, int64_t D, int device, size_t* bytes);
 int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
                     const float* v1, const float* v2, const int64_t* contrast_idx,
-                    int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                    int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
                     int64_t row_begin, int64_t row_end,
                     float T, float Z1, float Z2, float eps,
                     float* out_v1, float* out_v2, double* result, float* grad_v1, float* grad_v2,
@@ -101,7 +102,7 @@ int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row_stride, in
  * pass to have finished).  Z1, Z2 must already be frozen.  Same results, bit for bit, as the two calls. */
 int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
                    const float* v1, const float* v2, const int64_t* contrast_idx, const int64_t* y,
-                   int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                   int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
                    int64_t row_begin, int64_t row_end,
                    float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
                    double* result, float* grad_v1, float* grad_v2,

@@ -108,7 +108,8 @@ void oracle_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t
 /* ------------------------------------------------------------------------------------------------
  * ContrastMemory.forward scoring + ContrastLoss + closed-form backward, fp64 accumulation.
  *   s1[b,k] = <bank2[idx[b,k]], v1[b]>,  s2[b,k] = <bank1[idx[b,k]], v2[b]>
- *   e = exp(s / T);  o = e / Z;  c = K*Pn + eps,  Pn = 1/n_data,  K = K1-1
+ *   e = exp(s / T);  o = e / Z;  c = K*Pn + eps,  Pn = 1/n_data,  K = K1-1 (or k_total when the
+ *   negatives of an anchor are split over several shards, each with its own index list)
  *   loss_x = -( sum_b log(o_b0/(o_b0+c)) + sum_b sum_{k>=1} log(K*Pn/(o_bk+c)) ) / B
  *   dL/ds: positive -c/(B*T*(o+c)), negative +o/(B*T*(o+c));  grad_v1[b] = sum_k dL/ds1 * bank2[row], ...
  * Rows outside [row_begin,row_end) are skipped (bank shard); bank pointers address the local shard,
@@ -118,11 +119,11 @@ void oracle_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t
  * ---------------------------------------------------------------------------------------------- */
 void oracle_crd_score(const float* bank1, const float* bank2, int64_t row_stride,
                       const float* v1, const float* v2, const int64_t* idx,
-                      int64_t B, int64_t K1, int64_t D, int64_t n_data,
+                      int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
                       int64_t row_begin, int64_t row_end,
                       double T, double Z1, double Z2, double eps,
                       double* out_v1, double* out_v2, double* res, double* grad_v1, double* grad_v2) {
-  const double K = (double)(K1 - 1);
+  const double K = (double)(k_total > 0 ? k_total : (K1 - 1)); /* negatives per anchor over all shards */
   const double Pn = 1.0 / (double)n_data;
   const double c = K * Pn + eps;
   const double mPn = K * Pn;

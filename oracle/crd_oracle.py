@@ -89,7 +89,7 @@ def alias_draw_contrast(prob, alias, y: np.ndarray, K1: int, seed: int, offset: 
 
 def crd_score(bank1: np.ndarray, bank2: np.ndarray, v1: np.ndarray, v2: np.ndarray, idx: np.ndarray,
               n_data: int, T: float, Z1: float, Z2: float, eps: float = 1e-7,
-              row_begin: int = 0, row_end: int | None = None, want_out: bool = True):
+              row_begin: int = 0, row_end: int | None = None, want_out: bool = True, k_total: int = 0):
     """fp64 scorer. bank1/bank2: [N_local, D] fp32 (any row stride, last dim contiguous).
     Returns dict(loss_s, loss_t, sum_e1, sum_e2, count, out_v1, out_v2, grad_v1, grad_v2)."""
     assert bank1.dtype == np.float32 and bank2.dtype == np.float32
@@ -108,7 +108,7 @@ def crd_score(bank1: np.ndarray, bank2: np.ndarray, v1: np.ndarray, v2: np.ndarr
     g2 = np.zeros((B, D), dtype=np.float64)
     lib().oracle_crd_score(_p(bank1), _p(bank2), ctypes.c_int64(bank1.strides[0] // 4), _p(v1), _p(v2), _p(idx),
                            ctypes.c_int64(B), ctypes.c_int64(K1), ctypes.c_int64(D), ctypes.c_int64(n_data),
-                           ctypes.c_int64(row_begin), ctypes.c_int64(row_end),
+                           ctypes.c_int64(k_total), ctypes.c_int64(row_begin), ctypes.c_int64(row_end),
                            ctypes.c_double(T), ctypes.c_double(Z1), ctypes.c_double(Z2), ctypes.c_double(eps),
                            _p(out1) if want_out else None, _p(out2) if want_out else None,
                            _p(res), _p(g1), _p(g2))

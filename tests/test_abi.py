@@ -33,7 +33,7 @@ def test_host_alias_build_matches_oracle(pkg, oracle):
 def test_argument_errors_are_codes_not_crashes(pkg):
     lib = pkg._native.lib()
     assert lib.crdpn_alias_build(None, 5, None, None) == 1000
-    rc = lib.crdpn_crd_score(None, None, 128, 0, None, None, None, 1, 1, 128, 10, 0, 10, 0.07, 1.0, 1.0, 1e-7,
+    rc = lib.crdpn_crd_score(None, None, 128, 0, None, None, None, 1, 1, 128, 10, 0, 0, 10, 0.07, 1.0, 1.0, 1e-7,
                              None, None, None, None, None, None, 0, 0, None)
     assert rc == 1000 and b"null" in lib.crdpn_last_error()
     rc = lib.crdpn_crd_momentum_update(None, None, 128, 0, None, None, None, 1, 128, 0, 10, 0.5, 0.5, None)

@@ -36,7 +36,7 @@ def _case(B, K1, D, N, seed=0, dup_positive=False):
 
 
 def _score(pkg, dev, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=0, row_end=None, want_out=True, variant=0,
-           dtype=torch.float32, interleaved=True):
+           dtype=torch.float32, interleaved=True, k_total=0):
     """Direct C-ABI call. `bank` is the FULL [N,2,D] fp32 CPU tensor; the shard slice is uploaded."""
     lib = pkg._native.lib()
     row_end = N if row_end is None else row_end
@@ -59,7 +59,7 @@ def _score(pkg, dev, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=0, row_end=None,
     o2 = torch.full((B, K1), float("nan"), device=dev) if want_out else None
     rc = lib.crdpn_crd_score(b1.data_ptr() if row_end > row_begin else None, b2.data_ptr() if row_end > row_begin else None,
                              stride, 0 if dtype == torch.float32 else 1,
-                             dv1.data_ptr(), dv2.data_ptr(), didx.data_ptr(), B, K1, D, N, row_begin, row_end,
+                             dv1.data_ptr(), dv2.data_ptr(), didx.data_ptr(), B, K1, D, N, k_total, row_begin, row_end,
                              T, Z1, Z2, 1e-7, o1.data_ptr() if want_out else None, o2.data_ptr() if want_out else None,
                              res.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), ws.numel(), variant,
                              torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,122 @@
+"""GPU tests of the sharded CRD path: world_size 1 (runs on the driver's single B200) must reproduce CRDLoss
+bit for bit; world_size 2 over NCCL (needs 2 GPUs: `gpurun --gpus 2`) must match the unsharded module."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt(**kw):
+    base = dict(s_dim=64, t_dim=48, feat_dim=128, n_data=6000, nce_k=2048, nce_t=0.07, nce_m=0.5)
+    base.update(kw)
+    return type("Opt", (), base)()
+
+
+def _inputs(opt, B, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    f_s, f_t = torch.randn(B, opt.s_dim, generator=g), torch.randn(B, opt.t_dim, generator=g)
+    y = torch.randperm(opt.n_data, generator=g)[:B]
+    cidx = torch.randint(0, opt.n_data, (B, opt.nce_k + 1), generator=g)
+    cidx[:, 0] = y
+    return f_s, f_t, y, cidx
+
+
+def test_world1_sharded_equals_unsharded_bitwise(pkg, cuda):
+    opt = _opt()
+    torch.manual_seed(1)
+    a = pkg.CRDLoss(opt).to(cuda)
+    b = pkg.ShardedCRDLoss(opt, rank=0, world_size=1).to(cuda)
+    b.load_state_dict(a.state_dict(), strict=False)
+    f_s, f_t, y, cidx = [t.to(cuda) for t in _inputs(opt, 46)]
+    for step in range(2):
+        fa, fb = f_s.clone().requires_grad_(), f_s.clone().requires_grad_()
+        la = a(fa, f_t, y, cidx); la.backward()
+        lb = b(fb, f_t, y, cidx); lb.backward()
+        assert torch.equal(la, lb) and torch.equal(fa.grad, fb.grad)
+        assert torch.equal(a.contrast.memory_v1, b.contrast.memory_v1)
+        assert torch.equal(a.contrast.params, b.contrast.params)
+
+
+def test_local_negatives_world1_matches_oracle(pkg, oracle, cuda):
+    """local_negatives with internal sampling: indices are in-shard draws of the rank's own Philox stream."""
+    opt = _opt(nce_k=512)
+    torch.manual_seed(2)
+    m = pkg.ShardedCRDLoss(opt, rank=0, world_size=1, local_negatives=True, seed=77).to(cuda)
+    f_s, f_t, y, _ = [t.to(cuda) for t in _inputs(opt, 8)]
+    b1 = m.contrast.memory_v1.cpu().numpy().copy(); b2 = m.contrast.memory_v2.cpu().numpy().copy()
+    loss = m(f_s, f_t, y, None)
+    import numpy as np
+    prob, alias = oracle.alias_build(np.ones(opt.n_data, np.float32))
+    cidx = oracle.alias_draw_contrast(prob, alias, y.cpu().numpy(), 513, seed=77 + 7919, offset=0)
+    with torch.no_grad():
+        v1 = m.embed_s(f_s).cpu().numpy(); v2 = m.embed_t(f_t).cpu().numpy()
+    Z1, Z2 = m.contrast.params[2].item(), m.contrast.params[3].item()
+    want = oracle.crd_score(b1, b2, v1, v2, cidx, opt.n_data, 0.07, Z1, Z2)
+    assert abs(loss.item() - (want["loss_s"] + want["loss_t"])) < 1e-4 * abs(want["loss_s"] + want["loss_t"])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, q):
+    try:
+        import torch.distributed as dist
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import __graft_entry__ as ge
+        pkg = ge.load_package()
+        opt = _opt(n_data=6001)
+        torch.manual_seed(1)
+        ref = pkg.CRDLoss(opt).to(dev)                       # the unsharded module, same weights on every rank
+        sh = pkg.ShardedCRDLoss(opt).to(dev)
+        lo, hi = sh.contrast.row_begin, sh.contrast.row_end
+        with torch.no_grad():
+            for n_ in ("embed_s", "embed_t"):
+                getattr(sh, n_).load_state_dict(getattr(ref, n_).state_dict())
+            sh.contrast.memory_v1.copy_(ref.contrast.memory_v1[lo:hi]); sh.contrast.memory_v2.copy_(ref.contrast.memory_v2[lo:hi])
+        B = 46
+        f_s, f_t, y, cidx = [t.to(dev) for t in _inputs(opt, B)]
+        counts = [B * (r + 1) // world - B * r // world for r in range(world)]
+        a0 = sum(counts[:rank]); sl = slice(a0, a0 + counts[rank])
+        rel = lambda a, b: ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30)).item()
+        for step in range(2):
+            fr = f_s.clone().requires_grad_()
+            lr = ref(fr, f_t, y, cidx); lr.backward()
+            fl = f_s[sl].clone().requires_grad_()
+            ls = sh(fl, f_t[sl], y[sl], cidx); ls.backward()
+            assert rel(ls, lr) < 1e-5, (ls.item(), lr.item())
+            assert rel(fl.grad, fr.grad[sl]) < 1e-4
+            assert rel(sh.contrast.params[2:4], ref.contrast.params[2:4]) < 1e-5
+            # owner-only momentum update: shard rows are BIT-identical to the unsharded bank's rows
+            assert torch.equal(sh.contrast.memory_v1, ref.contrast.memory_v1[lo:hi])
+            assert torch.equal(sh.contrast.memory_v2, ref.contrast.memory_v2[lo:hi])
+        dist.barrier()
+        q.put((rank, "ok"))
+        dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_world2_nccl_matches_unsharded(pkg):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}: {msg}"
