@@ -291,7 +291,7 @@ class ContrastMemory(nn.Module):
         dev = v1.device
         ws = self._workspace(B, K1, D, dev)
         res = self._res
-        g1, g2 = torch.empty_like(v1), torch.empty_like(v2)
+        g1, g2 = self._grad_buffers(v1, v2)
         hp = self._host_params()
         with torch.cuda.device(dev):
             rc = _native.lib().crdpn_crd_step(
@@ -300,6 +300,11 @@ class ContrastMemory(nn.Module):
                 res.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), ws.numel(), self.variant, _stream_ptr(dev))
         _native.check(rc, "crdpn_crd_step")
         return res, g1, g2
+
+    def _grad_buffers(self, v1, v2):
+        """Where the kernel writes grad_v1 / grad_v2 (the sharded subclass hands out slices of its packed
+        all-reduce buffer so nothing has to be copied before the exchange)."""
+        return torch.empty_like(v1), torch.empty_like(v2)
 
     def _reduce_sums(self, res):
         """Hook for the sharded subclass: sum the first-call (sum_e1, sum_e2, count) over ranks."""

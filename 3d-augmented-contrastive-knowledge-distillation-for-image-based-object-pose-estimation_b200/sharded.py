@@ -9,8 +9,8 @@ extension of the CRD step:
 * every rank scores all ``B`` anchors against the negatives that live in ITS shard (``crdpn_crd_step`` with
   ``row_begin/row_end``; entries of other shards are dropped inside the kernel before any row is loaded) and
   momentum-updates the positive rows it owns;
-* exchange 2 (after the kernel): ONE all-reduce of a packed fp64 buffer ``[loss_s, loss_t, sum_e1, sum_e2, count,
-  grad_v1[B,D], grad_v2[B,D]]`` (about 94 KB at B=46, D=128).
+* exchange 2 (after the kernel): ONE all-reduce of a packed fp32 buffer ``[grad_v1[B,D], grad_v2[B,D], loss_s,
+  loss_t, ...]`` (about 47 KB at B=46, D=128) that the kernel's reduction writes in place.
 
 Negatives: either a replicated ``contrast_idx[B, K+1]`` (parity mode: every rank scans the whole list and keeps
 what it owns -- results equal the unsharded module up to fp32 summation order), or ``local_negatives=True``:
@@ -102,28 +102,40 @@ class ShardedContrastMemory(ContrastMemory):
     def _reduce_sums(self, res):
         return self._all_reduce(res)
 
+    def _grad_buffers(self, v1, v2):
+        # one fp32 buffer [grad_v1 | grad_v2 | 8 scalars]: the kernel writes the gradients straight into it
+        B, D = v1.shape
+        self._packed = torch.empty(2 * B * D + 8, dtype=torch.float32, device=v1.device)
+        return self._packed[:B * D].view(B, D), self._packed[B * D:2 * B * D].view(B, D)
+
     def _reduce_partials(self, res, g1, g2):
         B, D = g1.shape
-        buf = torch.empty(8 + 2 * B * D, dtype=torch.float64, device=g1.device)
-        buf[:8] = res
-        buf[8:8 + B * D] = g1.reshape(-1)
-        buf[8 + B * D:] = g2.reshape(-1)
-        self._all_reduce(buf)  # ONE packed exchange after the kernel
-        return (buf[:8], buf[8:8 + B * D].to(torch.float32).view(B, D),
-                buf[8 + B * D:].to(torch.float32).view(B, D))
+        packed = getattr(self, "_packed", None)
+        if packed is None or g1.data_ptr() != packed.data_ptr():  # gradients were not produced in place
+            packed = torch.empty(2 * B * D + 8, dtype=torch.float32, device=g1.device)
+            packed[:B * D] = g1.reshape(-1)
+            packed[B * D:2 * B * D] = g2.reshape(-1)
+        packed[2 * B * D:] = res  # fp64 -> fp32 (1e-7 relative on the loss partials)
+        self._all_reduce(packed)  # ONE packed exchange after the kernel
+        return packed[2 * B * D:], packed[:B * D].view(B, D), packed[B * D:2 * B * D].view(B, D)
 
     def _gather(self, v1, v2, y):
         """ONE packed exchange before the kernel: local anchors -> all anchors (uneven B_loc allowed)."""
-        b_loc = torch.tensor([v1.shape[0]], dtype=torch.int64, device=v1.device)
         if self._counts is None or self._counts[self.rank] != v1.shape[0]:
             cnt = torch.zeros(self.world_size, dtype=torch.int64, device=v1.device)
-            cnt[self.rank] = b_loc[0]
+            cnt[self.rank] = v1.shape[0]
             self._counts = self._all_reduce(cnt).tolist()  # once per batch-shape change
         counts = self._counts
         rows = max(counts)
         self._anchor_offset = sum(counts[:self.rank])
+        d = v1.shape[1]
+        if min(counts) == rows:  # even split: no padding, no compaction
+            buf = torch.cat([v1, v2, y.contiguous().view(-1, 1).view(torch.float32)], dim=1)
+            out = self._all_gather_rows(buf)
+            return (out[:, :d].contiguous(), out[:, d:2 * d].contiguous(),
+                    out[:, 2 * d:].contiguous().view(torch.int64).view(-1))
         gathered = self._all_gather_rows(pack_anchor_rows(v1, v2, y, rows))
-        return unpack_anchor_rows(gathered, counts, rows, v1.shape[1])
+        return unpack_anchor_rows(gathered, counts, rows, d)
 
     def _prepare(self, v1, v2, y, idx):
         if idx is None and self.local_negatives:
