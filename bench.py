@@ -264,13 +264,16 @@ def run_own(args):
     pkg = ge.load_package()
     pkg._native.lib()
     dist = None
-    if world > 1:
+    force_multi = bool(os.environ.get("CRDPN_FORCE_MULTI"))  # exercise the sharded leg with a 1-rank NCCL group
+    if force_multi and "MASTER_ADDR" not in os.environ:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", RANK="0", WORLD_SIZE="1")
+    if world > 1 or force_multi:
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
     hbm_peak, tf_peak, peak_kind = measured_peaks()
 
-    if world > 1:
+    if world > 1 or force_multi:
         from bench_multi import run_multi  # sharded banks, one NCCL exchange per step
         run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind)
         return

@@ -17,6 +17,9 @@ from bench import (HEADLINE, SEED, ClockSampler, algorithmic_bytes, make_opt, sc
 
 
 def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
+    import faulthandler
+    import sys
+    faulthandler.dump_traceback_later(120, exit=True, file=sys.stderr)  # a stuck collective must not eat the box time
     c = dict(HEADLINE)
     K_loc, N_loc, B, D = c["K"], c["N"], c["B"], c["D"]
     cg = dict(c, N=N_loc * world)                       # global bank
@@ -60,13 +63,17 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     use_graph = os.environ.get("CRDPN_NO_GRAPH") is None
+    run = step
     if use_graph:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step()
-        run = graph.replay
-    else:
-        run = step
+        try:  # thread_local: NCCL's watchdog thread polls events while we capture
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                step()
+            run = graph.replay
+        except Exception as exc:  # keep measuring, eagerly, and say so
+            print(f"[bench_multi] CUDA graph capture failed on rank {rank}: {exc}", file=sys.stderr)
+            use_graph = False
+            torch.cuda.synchronize()
     for _ in range(3):
         run()
     lib = pkg._native.lib()
@@ -149,5 +156,6 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
             "clocks": clocks,
         }
         print(json.dumps(line))
+    faulthandler.cancel_dump_traceback_later()
     dist.barrier()
     dist.destroy_process_group()

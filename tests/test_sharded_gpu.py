@@ -24,7 +24,9 @@ def _inputs(opt, B, seed=5):
     return f_s, f_t, y, cidx
 
 
-def test_world1_sharded_equals_unsharded_bitwise(pkg, cuda):
+def test_world1_sharded_equals_unsharded(pkg, cuda):
+    """Same kernels, same order: gradients and bank rows are bit-identical; the loss goes through the packed fp32
+    exchange buffer in the sharded module (fp64 -> fp32 once), so it agrees to fp32 rounding."""
     opt = _opt()
     torch.manual_seed(1)
     a = pkg.CRDLoss(opt).to(cuda)
@@ -35,7 +37,7 @@ def test_world1_sharded_equals_unsharded_bitwise(pkg, cuda):
         fa, fb = f_s.clone().requires_grad_(), f_s.clone().requires_grad_()
         la = a(fa, f_t, y, cidx); la.backward()
         lb = b(fb, f_t, y, cidx); lb.backward()
-        assert torch.equal(la, lb) and torch.equal(fa.grad, fb.grad)
+        assert abs(la.item() - lb.item()) <= 2e-7 * abs(la.item()) and torch.equal(fa.grad, fb.grad)
         assert torch.equal(a.contrast.memory_v1, b.contrast.memory_v1)
         assert torch.equal(a.contrast.params, b.contrast.params)
 
