@@ -157,5 +157,16 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
         }
         print(json.dumps(line))
     faulthandler.cancel_dump_traceback_later()
+    # teardown: drop the captured graph before the communicator; never let a stuck teardown eat box time
+    import threading
+    sys.stdout.flush()
+    killer = threading.Timer(20.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
+    if use_graph:
+        graph.reset()
+        del graph, run
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
+    killer.cancel()
