@@ -50,6 +50,7 @@ constexpr uint32_t kNumBars = 32;
 constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16;
 constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;           // slack for manual 1024-byte alignment
 
+namespace v1 {
 enum Bar : int {
   W3_FULL = 0,   // [3]
   W3_EMPTY = 3,  // [3]
@@ -63,6 +64,7 @@ enum Bar : int {
   A3_EMPTY = 20, // [2]
   W2_FULL = 22   // [1]
 };
+}  // namespace v1
 
 // packed parameter buffer (global), produced by pointnet_pack_kernel
 __host__ __device__ inline size_t packed_off_w3() { return kW2Bytes; }
@@ -192,6 +194,7 @@ struct FwdParams {
 // ---------------------------------------------------------------------------------------------------------
 template <int NSLAB>
 __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const FwdParams p) {
+  using namespace v1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -467,6 +470,342 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const Fw
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v2: layer 3 issues N = 256 MMAs (both halves of a unit in one instruction: 12 KB of shared-memory operands per
+// 128-cycle instruction = 96 B/clk instead of the 128 B/clk that N = 128 needs -- the shared-memory port was the
+// limiter of v1).  TMEM = ring of two 256-column slots shared by ALL accumulator jobs: per unit one layer-2 job
+// (half 0 -> columns [0,128), half 1 -> [128,256) of its slot, drained by the two front-end groups) and NSLAB
+// layer-3 jobs (drained by the epilogue warps).  The layer-2 job of unit u+1 is issued before the last slab of unit
+// u; the front end pulls it into registers (bias, ReLU, bf16) right away and only the 16 STS.128 per thread wait for
+// h2 to be released.
+// Warp roles (512 threads): w0 producer | w1 MMA issuer | w2 TMEM allocator | w3 idle | w4-7 layer-3 epilogue |
+//                           w8-11 front end for half 0 | w12-15 front end for half 1
+// ---------------------------------------------------------------------------------------------------------
+namespace v2 {
+enum Bar2 : int {
+  W3_FULL = 0,    // [3]
+  W3_EMPTY = 3,   // [3]
+  H1_FULL = 6,    // [2] 128 arrivals
+  H1_EMPTY = 8,   // [2] commit
+  H2_FULL = 10,   // [2] 128 arrivals
+  H2_EMPTY = 12,  // [1] commit
+  S_FULL = 13,    // [2] commit: a layer-3 job landed in slot i (phase = number of layer-3 jobs seen on that slot)
+  ACC_EMPTY = 15, // [2] 256 arrivals: slot i drained (every job, in order -- only the MMA issuer waits on it)
+  W2_FULL = 17,   // [1]
+  A2_FULL = 18    // [1] commit: the layer-2 job of unit u landed (phase = u)
+  // NOTE: a waiter may only use parity waits on a barrier whose EVERY phase it observes; the front end skips the
+  // layer-3 jobs and the epilogue skips the layer-2 jobs, hence the separate FULL barriers per job type.
+};
+constexpr uint32_t kIdescN128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescN256 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kH2KBlockBytes = 32768;  // 256 rows x 64 k bf16
+
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+}  // namespace v2
+
+template <int NSLAB>
+__global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel_v2(const FwdParams p) {
+  using namespace v2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar0 = base + kOffBar;
+  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kOffBar + kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const int u_begin = (int)(((long long)p.total_units * blockIdx.x) / G);
+  const int u_end = (int)(((long long)p.total_units * (blockIdx.x + 1)) / G);
+  const int NU = u_end - u_begin;
+  // job numbering (identical in every role): L2(0)=0; unit u's slabs follow at u(NS+1)+1+s, except that the
+  // layer-2 job of unit u+1 is slotted in right before slab kL2At of unit u (two slabs before the end, so its
+  // epilogue has two slab-times to pull the accumulator into registers before h2 is released)
+  constexpr int kL2At = NSLAB >= 2 ? NSLAB - 2 : 0;
+  auto job_l2 = [&](int u) -> uint32_t { return u == 0 ? 0u : (uint32_t)((u - 1) * (NSLAB + 1) + 1 + kL2At); };
+  auto job_s = [&](int u, int s) -> uint32_t {
+    return (uint32_t)(u * (NSLAB + 1) + 1 + s + ((s >= kL2At && u + 1 < NU) ? 1 : 0));
+  };
+
+  {
+    const float* par = reinterpret_cast<const float*>(p.packed + packed_off_par(p.F));
+    float* spar = reinterpret_cast<float*>(sm + kOffPar);
+    for (int i = threadIdx.x; i < (int)(kParBytes / 4); i += kThreads) spar[i] = par[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar(W3_FULL + i), 1); mbar_init(bar(W3_EMPTY + i), 1); }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar(H1_FULL + h), kHalfPts); mbar_init(bar(H1_EMPTY + h), 1);
+      mbar_init(bar(H2_FULL + h), kHalfPts);
+      mbar_init(bar(S_FULL + h), 1);         mbar_init(bar(ACC_EMPTY + h), 2 * kHalfPts);
+    }
+    mbar_init(bar(H2_EMPTY), 1);
+    mbar_init(bar(W2_FULL), 1);
+    mbar_init(bar(A2_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== bulk-copy producer ===========================
+    if (lane == 0 && NU > 0) {
+      mbar_expect_tx(bar(W2_FULL), kW2Bytes);
+      bulk_g2s(base + kOffW2, p.packed, kW2Bytes, bar(W2_FULL));
+      const char* w3 = p.packed + packed_off_w3();
+      uint32_t n = 0;
+      for (int u = 0; u < NU; ++u) {
+        for (int s = 0; s < NSLAB; ++s, ++n) {
+          const uint32_t stage = n % kStages, use = n / kStages;
+          mbar_wait(bar(W3_EMPTY + stage), (use & 1u) ^ 1u);
+          mbar_expect_tx(bar(W3_FULL + stage), kSlabBytes);
+          const uint32_t dst = base + kOffW3 + stage * kSlabBytes;
+          const char* src = w3 + (size_t)s * kSlabBytes;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) bulk_g2s(dst + c * 8192u, src + c * 8192, 8192u, bar(W3_FULL + stage));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (converged warp, one elected lane issues) ===========================
+    if (NU > 0) {
+      long long dw[5] = {0, 0, 0, 0, 0};
+      const long long t_role = clock64();
+      mbar_wait(bar(W2_FULL), 0);
+      uint32_t j = 0, slab_n = 0;
+      auto issue_layer2 = [&](int u) {  // one job: both halves into the two column halves of slot j&1
+        const uint32_t uph = (uint32_t)u & 1u, slot = j & 1u;
+        mbar_wait_t(bar(H1_FULL + 0), uph, dw[0]);
+        mbar_wait_t(bar(H1_FULL + 1), uph, dw[0]);
+        mbar_wait_t(bar(ACC_EMPTY + slot), ((j >> 1) & 1u) ^ 1u, dw[1]);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t w2_desc = umma_desc_sw128(base + kOffW2);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t a_desc = umma_desc_sw128(base + kOffH1 + h * kKBlockBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma(tmem + 256u * slot + 128u * h, a_desc + 2u * k, w2_desc + 2u * k, kIdescN128, k > 0);
+          }
+          umma_commit(bar(A2_FULL));
+          umma_commit(bar(H1_EMPTY + 0));
+          umma_commit(bar(H1_EMPTY + 1));
+        }
+        __syncwarp();
+        ++j;
+      };
+      issue_layer2(0);
+      for (int u = 0; u < NU; ++u) {
+        const uint32_t uph = (uint32_t)u & 1u;
+        for (int s = 0; s < NSLAB; ++s, ++slab_n) {
+          if (s == kL2At && u + 1 < NU) issue_layer2(u + 1);
+          const uint32_t stage = slab_n % kStages, slot = j & 1u;
+          mbar_wait_t(bar(W3_FULL + stage), (slab_n / kStages) & 1u, dw[2]);
+          if (s == 0) {
+            mbar_wait_t(bar(H2_FULL + 0), uph, dw[3]);
+            mbar_wait_t(bar(H2_FULL + 1), uph, dw[3]);
+          }
+          mbar_wait_t(bar(ACC_EMPTY + slot), ((j >> 1) & 1u) ^ 1u, dw[4]);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a0 = umma_desc_sw128(base + kOffW3 + stage * kSlabBytes);
+            const uint64_t b0 = umma_desc_sw128(base + kOffH2);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint32_t ka = (uint32_t)(kk >> 2) * (kKBlockBytes >> 4) + (uint32_t)(kk & 3) * 2u;
+              const uint32_t kb = (uint32_t)(kk >> 2) * (kH2KBlockBytes >> 4) + (uint32_t)(kk & 3) * 2u;
+              umma(tmem + 256u * slot, a0 + ka, b0 + kb, kIdescN256, kk > 0);
+            }
+            umma_commit(bar(S_FULL + slot));
+            umma_commit(bar(W3_EMPTY + stage));
+            if (s == NSLAB - 1) umma_commit(bar(H2_EMPTY));
+          }
+          __syncwarp();
+          ++j;
+        }
+      }
+      // wait until the epilogue has drained the last job (this warp has observed every phase of ACC_EMPTY, so the
+      // parity wait is exact): by then every MMA, and every commit queued behind the last one, has retired
+      mbar_wait(bar(ACC_EMPTY + ((j - 1u) & 1u)), ((j - 1u) >> 1) & 1u);
+      if (p.dbg && lane == 0) {
+        for (int i = 0; i < 5; ++i) p.dbg[blockIdx.x * 32 + i] = dw[i];
+        p.dbg[blockIdx.x * 32 + 5] = clock64() - t_role;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =========================== layer-3 epilogue: running max over the 256 points of a job ===================
+    const int q = warp & 3;
+    float rmax[NSLAB];
+#pragma unroll
+    for (int s = 0; s < NSLAB; ++s) rmax[s] = -INFINITY;
+    int cur_cloud = -1;
+    uint32_t seen0 = 0, seen1 = 0;
+    long long dwait = 0;
+    const long long t_role = clock64();
+    auto flush = [&](int cloud) {
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) {
+        atomicMax(p.enc + (size_t)cloud * p.F + s * 128 + q * 32 + lane, enc_ordered(rmax[s]));
+        rmax[s] = -INFINITY;
+      }
+    };
+    for (int u = 0; u < NU; ++u) {
+      const int cloud = (u_begin + u) / p.tiles_per_cloud;
+      if (cloud != cur_cloud) {
+        if (cur_cloud >= 0) flush(cur_cloud);
+        cur_cloud = cloud;
+      }
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) {
+        const uint32_t j = job_s(u, s), slot = j & 1u;
+        const uint32_t seen = slot ? seen1 : seen0;  // layer-3 jobs already drained from this slot
+        mbar_wait_t(bar(S_FULL + slot), seen & 1u, dwait);
+        if (slot) ++seen1; else ++seen0;
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u * slot;
+        float m0 = rmax[s], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        // software pipeline over 8 chunks of 32 columns: the load of chunk c+1 is in flight while chunk c is reduced
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t* cur = (c & 1) ? rb : ra;
+          uint32_t* nxt = (c & 1) ? ra : rb;
+          if (c + 1 < 8) tmem_ld32(taddr + 32u * (c + 1), nxt);
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            m0 = max3(m0, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+            m1 = max3(m1, __uint_as_float(cur[8 + i]), __uint_as_float(cur[9 + i]));
+            m2 = max3(m2, __uint_as_float(cur[16 + i]), __uint_as_float(cur[17 + i]));
+            m3 = max3(m3, __uint_as_float(cur[24 + i]), __uint_as_float(cur[25 + i]));
+          }
+          if (c + 1 < 8) tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive_n(bar(ACC_EMPTY + slot), 2u);  // 128 epilogue threads stand in for the slot's 256 arrivals
+        rmax[s] = fmaxf(max3(m0, m1, m2), m3);
+      }
+    }
+    if (cur_cloud >= 0) flush(cur_cloud);
+    if (p.dbg && q == 0 && lane == 0) {
+      p.dbg[blockIdx.x * 32 + 8] = dwait;
+      p.dbg[blockIdx.x * 32 + 9] = clock64() - t_role;
+    }
+  } else if (warp >= 8) {
+    // =========================== front end, group g = half g: layer 1 + layer-2 epilogue ======================
+    const int g = warp >= 12 ? 1 : 0;
+    const int t = (threadIdx.x - 256) & 127;  // point row inside the half; also the TMEM lane
+    const int q = warp & 3;
+    const float4* w1p = reinterpret_cast<const float4*>(sm + kOffPar);
+    const float4* b2f = reinterpret_cast<const float4*>(sm + kOffPar + 64 * 16);
+    long long dw[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_role = clock64();
+
+    auto layer1 = [&](int u) {
+      const int unit = u_begin + u;
+      const int cloud = unit / p.tiles_per_cloud;
+      const int p_base = (unit - cloud * p.tiles_per_cloud) * kUnitPts;
+      const uint32_t uph = (uint32_t)u & 1u;
+      const float* xc = p.x + (size_t)cloud * 3 * p.P;
+      int pt = p_base + g * kHalfPts + t;
+      pt = pt < p.P ? pt : p.P - 1;  // ragged tail: repeat the last real point (max is idempotent)
+      const float x0 = __ldg(xc + pt), x1 = __ldg(xc + p.P + pt), x2 = __ldg(xc + 2 * p.P + pt);
+      mbar_wait_t(bar(H1_EMPTY + g), uph ^ 1u, dw[0]);
+      const long long t_l1 = clock64();
+      uint8_t* dst = sm + kOffH1 + g * kKBlockBytes;
+#pragma unroll
+      for (int cg = 0; cg < 8; ++cg) {
+        float v[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float4 w = w1p[cg * 8 + jj];
+          v[jj] = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
+        }
+        uint4 o;
+        o.x = pack_relu_bf16(v[0], v[1]); o.y = pack_relu_bf16(v[2], v[3]);
+        o.z = pack_relu_bf16(v[4], v[5]); o.w = pack_relu_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(dst + sw128_off(t, cg * 8)) = o;
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(H1_FULL + g));
+      dw[4] += clock64() - t_l1;
+    };
+
+    if (NU > 0) layer1(0);
+    for (int u = 0; u < NU; ++u) {
+      const uint32_t uph = (uint32_t)u & 1u;
+      const uint32_t j = job_l2(u), slot = j & 1u;
+      mbar_wait_t(bar(A2_FULL), uph, dw[1]);
+      tc_fence_after();
+      const long long t_e2 = clock64();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u * slot + 128u * g;
+      uint4 pk[16];  // this point's 128 layer-2 channels: bias + ReLU + bf16, 8 channels per 16 bytes
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + 32u * c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int ch = c * 32 + g8 * 8;
+          const float4 ba = b2f[ch / 4], bb = b2f[ch / 4 + 1];
+          uint4 o;
+          o.x = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 0]) + ba.x, __uint_as_float(r[g8 * 8 + 1]) + ba.y);
+          o.y = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 2]) + ba.z, __uint_as_float(r[g8 * 8 + 3]) + ba.w);
+          o.z = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 4]) + bb.x, __uint_as_float(r[g8 * 8 + 5]) + bb.y);
+          o.w = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 6]) + bb.z, __uint_as_float(r[g8 * 8 + 7]) + bb.w);
+          pk[c * 4 + g8] = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar(ACC_EMPTY + slot));   // the slot is free again; the values live in registers now
+      dw[5] += clock64() - t_e2;
+      mbar_wait_t(bar(H2_EMPTY), uph ^ 1u, dw[2]);  // layer 3 of the previous unit has finished reading h2
+      uint8_t* dst = sm + kOffH2;
+      const int row = g * kHalfPts + t;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int ch = i * 8;
+        *reinterpret_cast<uint4*>(dst + (ch >> 6) * kH2KBlockBytes + sw128_off(row, ch & 63)) = pk[i];
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(H2_FULL + g));
+      if (u + 1 < NU) layer1(u + 1);  // overlaps with layer 3 of unit u on the tensor pipe
+    }
+    if (p.dbg && t == 0 && g == 0) {
+      p.dbg[blockIdx.x * 32 + 12] = dw[0]; p.dbg[blockIdx.x * 32 + 13] = dw[1]; p.dbg[blockIdx.x * 32 + 14] = dw[2];
+      p.dbg[blockIdx.x * 32 + 15] = clock64() - t_role; p.dbg[blockIdx.x * 32 + 16] = dw[4]; p.dbg[blockIdx.x * 32 + 17] = dw[5];
+      p.dbg[blockIdx.x * 32 + 18] = NU;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 // out[b,c] = max over points (decoded) + folded BN3 shift
 __global__ void __launch_bounds__(256) pointnet_finalize_kernel(const uint32_t* __restrict__ enc,
                                                                 const float* __restrict__ shift3, int B, int F,
@@ -570,11 +909,14 @@ static int launch_pointnet(const pn::FwdParams& fp, int grid, cudaStream_t st) {
   if (!attr_set[device]) {
     CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_eval_kernel<NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)pn::kSmemAlloc));
+    CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_eval_kernel_v2<NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)pn::kSmemAlloc));
     attr_set[device] = true;
   }
   {
     ScopedKernelTimer tm(CRDPN_K_POINTNET_FWD, st);
-    pn::pointnet_fwd_eval_kernel<NSLAB><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);
+    if (fp.flags & 8) pn::pointnet_fwd_eval_kernel<NSLAB><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);       // v1: N=128
+    else pn::pointnet_fwd_eval_kernel_v2<NSLAB><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);                  // v2: N=256
   }
   CRDPN_LAUNCH_CHECK("pointnet_fwd_eval_kernel");
   return CRDPN_OK;

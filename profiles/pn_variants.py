@@ -8,7 +8,7 @@ st = po.random_state(1024, seed=46)
 enc = pkg.ShapeEncoderPC(1024); enc.load_state_dict(st); enc = enc.to(dev).eval()
 x = po.random_clouds(160, 2500, seed=46).to(dev)
 ref = None
-for variant in (0, 1, 2, 3):
+for variant in (0, 8):
     enc.variant = variant
     for _ in range(5): out = enc(x)
     torch.cuda.synchronize()
