@@ -30,16 +30,6 @@
 namespace crdpn {
 namespace pn {
 
-struct FwdParams {
-  const float* x;        // [B,3,P]
-  int B, P, F;
-  const char* packed;
-  uint32_t* enc;         // [B,F] order-preserving encoding of the running max (zeroed before launch)
-  int tiles_per_cloud;
-  int total_units;
-  long long* dbg;         // optional [grid][32] cycle counters (flags bit2), else null
-  int flags;             // bit0: rotate the slab order per CTA; bit1 (diagnostic, wrong results): load each ring stage once
-};
 
 // ---------------------------------------------------------------------------------------------------------
 template <int NSLAB>
@@ -362,8 +352,8 @@ __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
 }
 }  // namespace v2
 
-template <int NSLAB>
-__global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel_v2(const FwdParams p) {
+template <int NSLAB, bool TRAIN>
+__global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_kernel_v2(const FwdParams p) {
   using namespace v2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -388,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel_v2(const
   };
 
   {
-    const float* par = reinterpret_cast<const float*>(p.packed + packed_off_par(p.F));
+    const float* par = TRAIN ? p.train_par : reinterpret_cast<const float*>(p.packed + packed_off_par(p.F));
     float* spar = reinterpret_cast<float*>(sm + kOffPar);
     for (int i = threadIdx.x; i < (int)(kParBytes / 4); i += kThreads) spar[i] = par[i];
   }
@@ -501,6 +491,84 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel_v2(const
       }
     }
   } else if (warp >= 4 && warp < 8) {
+   if constexpr (TRAIN) {
+    // ============ layer-3 epilogue, train mode: running max + arg-max point per (cloud, channel), and the
+    // per-channel sum / sum of squares over all real points (BN3 batch statistics) =======================
+    const int q = warp & 3;
+    float rmax[NSLAB], rs[NSLAB], rq[NSLAB];
+    int ridx[NSLAB];
+#pragma unroll
+    for (int s = 0; s < NSLAB; ++s) { rmax[s] = -INFINITY; rs[s] = 0.f; rq[s] = 0.f; ridx[s] = 0; }
+    int cur_cloud = -1;
+    uint32_t seen0 = 0, seen1 = 0;
+    auto flush = [&](int cloud) {
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) {
+        const unsigned long long key = ((unsigned long long)enc_ordered(rmax[s]) << 32) |
+                                       (unsigned long long)(0xffffffffu - (uint32_t)ridx[s]);
+        atomicMax(p.enc64 + (size_t)cloud * p.F + s * 128 + q * 32 + lane, key);
+        rmax[s] = -INFINITY;
+      }
+    };
+    for (int u = 0; u < NU; ++u) {
+      const int unit = u_begin + u;
+      const int cloud = unit / p.tiles_per_cloud;
+      const int p_base = (unit - cloud * p.tiles_per_cloud) * kUnitPts;
+      const int ndup = p_base + kUnitPts > p.P ? p_base + kUnitPts - p.P : 0;  // padded columns repeat the last point
+      if (cloud != cur_cloud) {
+        if (cur_cloud >= 0) flush(cur_cloud);
+        cur_cloud = cloud;
+      }
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) {
+        const uint32_t j = job_s(u, s), slot = j & 1u;
+        const uint32_t seen = slot ? seen1 : seen0;
+        mbar_wait(bar(S_FULL + slot), seen & 1u);
+        if (slot) ++seen1; else ++seen0;
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u * slot;
+        float m = rmax[s];
+        int ml = -1;
+        unsigned long long s2 = 0ull, q2 = 0ull;
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          uint32_t* cur = (c & 1) ? rb : ra;
+          uint32_t* nxt = (c & 1) ? ra : rb;
+          if (c + 1 < 16) tmem_ld16(taddr + 16u * (c + 1), nxt);
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float a = __uint_as_float(cur[i]), b = __uint_as_float(cur[i + 1]);
+            if (a > m) { m = a; ml = 16 * c + i; }
+            if (b > m) { m = b; ml = 16 * c + i + 1; }
+            add2(s2, cur[i], cur[i + 1]);
+            sq2(q2, cur[i], cur[i + 1]);
+          }
+          if (c + 1 < 16) tmem_ld_wait();
+        }
+        const float ylast = __uint_as_float(rb[15]);  // column 255: the last real point whenever ndup > 0
+        tc_fence_before();
+        mbar_arrive_n(bar(ACC_EMPTY + slot), 2u);
+        rs[s] += pair_sum(s2) - (float)ndup * ylast;
+        rq[s] += pair_sum(q2) - (float)ndup * ylast * ylast;
+        if (ml >= 0) {
+          rmax[s] = m;
+          const int pt = p_base + ml;
+          ridx[s] = pt < p.P ? pt : p.P - 1;
+        }
+      }
+    }
+    if (cur_cloud >= 0) flush(cur_cloud);
+    if (NU > 0) {
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) {
+        atomicAdd(p.sum3 + s * 128 + q * 32 + lane, (double)rs[s]);
+        atomicAdd(p.sq3 + s * 128 + q * 32 + lane, (double)rq[s]);
+      }
+    }
+   } else {
     // =========================== layer-3 epilogue: running max over the 256 points of a job ===================
     const int q = warp & 3;
     float rmax[NSLAB];
@@ -560,6 +628,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel_v2(const
       p.dbg[blockIdx.x * 32 + 8] = dwait;
       p.dbg[blockIdx.x * 32 + 9] = clock64() - t_role;
     }
+   }
   } else if (warp >= 8) {
     // =========================== front end, group g = half g: layer 1 + layer-2 epilogue ======================
     const int g = warp >= 12 ? 1 : 0;
@@ -619,10 +688,18 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel_v2(const
           const int ch = c * 32 + g8 * 8;
           const float4 ba = b2f[ch / 4], bb = b2f[ch / 4 + 1];
           uint4 o;
-          o.x = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 0]) + ba.x, __uint_as_float(r[g8 * 8 + 1]) + ba.y);
-          o.y = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 2]) + ba.z, __uint_as_float(r[g8 * 8 + 3]) + ba.w);
-          o.z = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 4]) + bb.x, __uint_as_float(r[g8 * 8 + 5]) + bb.y);
-          o.w = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 6]) + bb.z, __uint_as_float(r[g8 * 8 + 7]) + bb.w);
+          if constexpr (TRAIN) {  // BN2 with batch statistics: z2 = sc2 * (raw W2 . h1) + sh2
+            const float4 sa = b2f[32 + ch / 4], sb = b2f[32 + ch / 4 + 1];
+            o.x = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 0]), sa.x, ba.x), fmaf(__uint_as_float(r[g8 * 8 + 1]), sa.y, ba.y));
+            o.y = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 2]), sa.z, ba.z), fmaf(__uint_as_float(r[g8 * 8 + 3]), sa.w, ba.w));
+            o.z = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 4]), sb.x, bb.x), fmaf(__uint_as_float(r[g8 * 8 + 5]), sb.y, bb.y));
+            o.w = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 6]), sb.z, bb.z), fmaf(__uint_as_float(r[g8 * 8 + 7]), sb.w, bb.w));
+          } else {
+            o.x = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 0]) + ba.x, __uint_as_float(r[g8 * 8 + 1]) + ba.y);
+            o.y = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 2]) + ba.z, __uint_as_float(r[g8 * 8 + 3]) + ba.w);
+            o.z = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 4]) + bb.x, __uint_as_float(r[g8 * 8 + 5]) + bb.y);
+            o.w = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 6]) + bb.z, __uint_as_float(r[g8 * 8 + 7]) + bb.w);
+          }
           pk[c * 4 + g8] = o;
         }
       }
@@ -639,6 +716,14 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel_v2(const
       }
       fence_proxy_async();
       mbar_arrive(bar(H2_FULL + g));
+      if constexpr (TRAIN) {  // keep this tile of h2 for backward, in the same swizzled operand image
+        char* gt = p.h2img + ((size_t)(u_begin + u) * 2 + g) * kTileBytes;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int ch = i * 8;
+          *reinterpret_cast<uint4*>(gt + (ch >> 6) * kKBlockBytes + sw128_off(t, ch & 63)) = pk[i];
+        }
+      }
       if (u + 1 < NU) layer1(u + 1);  // overlaps with layer 3 of unit u on the tensor pipe
     }
     if (p.dbg && t == 0 && g == 0) {
@@ -716,7 +801,7 @@ __global__ void __launch_bounds__(256) pointnet_pack_kernel(const PackParams a) 
 
 using namespace crdpn;
 
-static bool pointnet_f_ok(int64_t F) { return F == 128 || F == 256 || F == 512 || F == 1024; }
+using crdpn::pn::pointnet_f_ok;
 
 extern "C" int crdpn_pointnet_packed_bytes(int64_t F, size_t* bytes) {
   if (!bytes) return fail(CRDPN_E_BADARG, "crdpn_pointnet_packed_bytes: null pointer");
@@ -759,17 +844,29 @@ static int launch_pointnet(const pn::FwdParams& fp, int grid, cudaStream_t st) {
   if (!attr_set[device]) {
     CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_eval_kernel<NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)pn::kSmemAlloc));
-    CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_eval_kernel_v2<NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_kernel_v2<NSLAB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)pn::kSmemAlloc));
+    CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_kernel_v2<NSLAB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)pn::kSmemAlloc));
     attr_set[device] = true;
   }
   {
     ScopedKernelTimer tm(CRDPN_K_POINTNET_FWD, st);
     if (fp.flags & 8) pn::pointnet_fwd_eval_kernel<NSLAB><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);       // v1: N=128
-    else pn::pointnet_fwd_eval_kernel_v2<NSLAB><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);                  // v2: N=256
+    else if (fp.train_par) pn::pointnet_fwd_kernel_v2<NSLAB, true><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);  // train
+    else pn::pointnet_fwd_kernel_v2<NSLAB, false><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);                // v2: N=256
   }
   CRDPN_LAUNCH_CHECK("pointnet_fwd_eval_kernel");
   return CRDPN_OK;
+}
+
+int crdpn::pn::launch_fwd(const FwdParams& fp, int grid, cudaStream_t st) {
+  switch (fp.F / 128) {
+    case 1: return launch_pointnet<1>(fp, grid, st);
+    case 2: return launch_pointnet<2>(fp, grid, st);
+    case 4: return launch_pointnet<4>(fp, grid, st);
+    default: return launch_pointnet<8>(fp, grid, st);
+  }
 }
 
 extern "C" int crdpn_pointnet_forward_eval(const float* x, int64_t B, int64_t P, int64_t F, const void* packed,
@@ -795,15 +892,11 @@ extern "C" int crdpn_pointnet_forward_eval(const float* x, int64_t B, int64_t P,
   fp.tiles_per_cloud = (int)((P + pn::kUnitPts - 1) / pn::kUnitPts);
   fp.total_units = (int)B * fp.tiles_per_cloud;
   fp.flags = variant;
+  fp.train_par = nullptr; fp.h2img = nullptr; fp.enc64 = nullptr; fp.sum3 = nullptr; fp.sq3 = nullptr;
   fp.dbg = (variant & 4) ? (long long*)((char*)workspace + (((size_t)B * (size_t)F * 4 + 15) & ~(size_t)15)) : nullptr;
   CRDPN_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * (size_t)F * 4, st));
   const int grid = fp.total_units < di.sms ? fp.total_units : di.sms;
-  switch (F / 128) {
-    case 1: rc = launch_pointnet<1>(fp, grid, st); break;
-    case 2: rc = launch_pointnet<2>(fp, grid, st); break;
-    case 4: rc = launch_pointnet<4>(fp, grid, st); break;
-    default: rc = launch_pointnet<8>(fp, grid, st); break;
-  }
+  rc = pn::launch_fwd(fp, grid, st);
   if (rc) return rc;
   const float* shift3 = reinterpret_cast<const float*>((const char*)packed + pn::packed_off_par((int)F) + 64 * 16 + 128 * 4);
   const int n = (int)(B * F);

@@ -12,8 +12,10 @@ forward(shapes[B,3,P] float32) -> [B, feature_dim] float32.
   (``crdpn_pointnet_forward_eval``): BN folded into the weights, layers 2-3 on tcgen05 tensor cores in bf16
   with fp32 accumulation, max over points fused into the GEMM epilogue.  The output carries no autograd
   graph (the teacher is frozen in the KD loop; its gradients are never consumed).
-* ``.train()``: batch-statistics BatchNorm needs global per-channel statistics between layers; see
-  ``forward_train`` (added with the train-mode kernels).
+* ``.train()`` (teacher training, ``training.py:30,47,75``): batch-statistics BatchNorm forward
+  (``crdpn_pointnet_forward_train``: analytic BN1 statistics, a tensor-core statistics pass for BN2, the fused
+  kernel with BN3's statistics / max / arg-max in the epilogue) and its backward (``crdpn_pointnet_backward``),
+  wired into autograd for the 12 parameters; running statistics are updated in place like ``nn.BatchNorm1d``.
 
 No CPU fallback: inputs must be CUDA tensors.
 """
@@ -102,6 +104,89 @@ class ShapeEncoderPC(nn.Module):
             return self.forward_train(shapes)
         return self.forward_eval(shapes)
 
+    # -- train path ------------------------------------------------------------------------------------
+    _PARAM_ORDER = ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias",
+                    "bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias", "bn3.weight", "bn3.bias")
+
+    def _train_params(self):
+        return [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv3.weight,
+                self.conv3.bias, self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias,
+                self.bn3.weight, self.bn3.bias]
+
     def forward_train(self, shapes: torch.Tensor) -> torch.Tensor:
-        raise RuntimeError("ShapeEncoderPC: train-mode (batch-statistics BatchNorm) kernels are not built yet; "
-                           "call .eval() (the KD-time teacher configuration). There is no eager fallback.")
+        """Batch-statistics BatchNorm forward (``training.py:30,47``); differentiable w.r.t. the 12 parameters
+        (``training.py:75``); running statistics and ``num_batches_tracked`` are updated in place."""
+        if not shapes.is_cuda:
+            raise RuntimeError("ShapeEncoderPC input must be a CUDA tensor: this package has no CPU fallback")
+        if shapes.dim() != 3 or shapes.shape[1] != 3:
+            raise RuntimeError(f"expected shapes[B,3,P], got {tuple(shapes.shape)}")
+        if shapes.requires_grad:
+            raise RuntimeError("ShapeEncoderPC: gradients w.r.t. the input point cloud are not provided (it is data)")
+        for bn in (self.bn1, self.bn2, self.bn3):
+            if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+                raise RuntimeError("ShapeEncoderPC train mode expects nn.BatchNorm1d defaults (momentum, running stats, affine)")
+        return _PointNetTrainFunction.apply(self, shapes, *self._train_params()).view(-1, self.feature_dim)
+
+
+def _aligned(nbytes: int, device) -> tuple[torch.Tensor, int]:
+    """A uint8 buffer with a 1024-byte aligned start; returns (owner tensor, aligned pointer)."""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    return buf, (buf.data_ptr() + 1023) & ~1023
+
+
+class _PointNetTrainFunction(torch.autograd.Function):
+    """ctypes glue around ``crdpn_pointnet_forward_train`` / ``crdpn_pointnet_backward``."""
+
+    @staticmethod
+    def forward(ctx, module, shapes, *params):
+        lib = _native.lib()
+        x = shapes.detach().to(torch.float32).contiguous()
+        B, _, P = x.shape
+        F = module.feature_dim
+        dev = x.device
+        for t in params:
+            if t.device != dev or t.dtype != torch.float32:
+                raise RuntimeError("ShapeEncoderPC parameters must be float32 on the input's CUDA device")
+        p = [t.detach().contiguous() for t in params]
+        n = ctypes.c_size_t(0)
+        _native.check(lib.crdpn_pointnet_train_ctx_bytes(B, P, F, ctypes.byref(n)), "crdpn_pointnet_train_ctx_bytes")
+        owner, cptr = _aligned(n.value, dev)
+        out = torch.empty(B, F, dtype=torch.float32, device=dev)
+        bns = (module.bn1, module.bn2, module.bn3)
+        args = [x.data_ptr(), B, P, F] + [t.data_ptr() for t in p[:6]]
+        for i, bn in enumerate(bns):
+            args += [p[6 + 2 * i].data_ptr(), p[7 + 2 * i].data_ptr(), bn.running_mean.data_ptr(),
+                     bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr()]
+        with torch.cuda.device(dev):
+            rc = lib.crdpn_pointnet_forward_train(*args, float(module.bn1.eps), float(module.bn1.momentum),
+                                                  out.data_ptr(), cptr, n.value, module.variant,
+                                                  torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(rc, "crdpn_pointnet_forward_train")
+        ctx.save_for_backward(x, *p)
+        ctx.train_ctx = (owner, cptr, n.value)
+        ctx.dims = (B, P, F)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.lib()
+        x, *p = ctx.saved_tensors
+        owner, cptr, cbytes = ctx.train_ctx
+        B, P, F = ctx.dims
+        dev = x.device
+        g = grad_out.detach().to(torch.float32).contiguous()
+        n = ctypes.c_size_t(0)
+        _native.check(lib.crdpn_pointnet_backward_workspace_bytes(B, P, F, ctypes.byref(n)),
+                      "crdpn_pointnet_backward_workspace_bytes")
+        ws_owner, wptr = _aligned(n.value, dev)
+        grads = [torch.empty_like(t) for t in p]
+        c1w, c1b, c2w, c2b, c3w, c3b, g1, b1, g2, b2, g3, b3 = p
+        with torch.cuda.device(dev):
+            rc = lib.crdpn_pointnet_backward(
+                x.data_ptr(), B, P, F, c1w.data_ptr(), c2w.data_ptr(), c3w.data_ptr(),
+                g1.data_ptr(), b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), g3.data_ptr(), b3.data_ptr(),
+                g.data_ptr(), cptr, cbytes, *[t.data_ptr() for t in grads], wptr, n.value,
+                torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(rc, "crdpn_pointnet_backward")
+        del owner, ws_owner
+        return (None, None, *grads)

@@ -140,6 +140,41 @@ int crdpn_pointnet_forward_eval(const float* x, int64_t B, int64_t P, int64_t F,
                                 float* out, void* workspace, size_t workspace_bytes, int variant,
                                 void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * PointNet encoder, train-mode BatchNorm (teacher training: model.train() at training.py:30, forward at
+ * training.py:47 -> auxiliary/model.py:257 -> ShapeEncoderPC.forward model.py:174-180; backward via
+ * loss.backward() at training.py:75).
+ * BatchNorm uses the statistics of this batch (over all B*P points, biased variance); running_mean / running_var
+ * are updated in place with `bn_momentum` (unbiased variance) and num_batches_tracked += 1, exactly as
+ * nn.BatchNorm1d does.  `ctx` is a caller-owned buffer (crdpn_pointnet_train_ctx_bytes, 1024-byte aligned) that
+ * carries what backward needs (batch statistics, arg-max point per (cloud, channel), h2 in bf16); it must stay
+ * untouched between the forward and its backward.
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_pointnet_train_ctx_bytes(int64_t B, int64_t P, int64_t F, size_t* bytes);
+int crdpn_pointnet_forward_train(
+    const float* x, int64_t B, int64_t P, int64_t F,
+    const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+    const float* conv3_w, const float* conv3_b,
+    const float* bn1_w, const float* bn1_b, float* bn1_mean, float* bn1_var, int64_t* bn1_num_batches_tracked,
+    const float* bn2_w, const float* bn2_b, float* bn2_mean, float* bn2_var, int64_t* bn2_num_batches_tracked,
+    const float* bn3_w, const float* bn3_b, float* bn3_mean, float* bn3_var, int64_t* bn3_num_batches_tracked,
+    float bn_eps, float bn_momentum, float* out, void* ctx, size_t ctx_bytes, int variant, void* stream);
+/* Backward of the train-mode forward (autograd of model.py:174-180): grad_out [B,F] f32 -> gradients of the 12
+ * parameter tensors (same shapes as the parameters; the input x needs no gradient -- it is data).  The max over
+ * points makes layer 3's backward sparse (one point per (cloud, channel)) plus a rank-structured dense term from
+ * BatchNorm's batch coupling, so the B*F*P tensor is never formed here either.
+ * workspace: crdpn_pointnet_backward_workspace_bytes, 1024-byte aligned, scratch. */
+int crdpn_pointnet_backward_workspace_bytes(int64_t B, int64_t P, int64_t F, size_t* bytes);
+int crdpn_pointnet_backward(
+    const float* x, int64_t B, int64_t P, int64_t F,
+    const float* conv1_w, const float* conv2_w, const float* conv3_w,
+    const float* bn1_w, const float* bn1_b, const float* bn2_w, const float* bn2_b,
+    const float* bn3_w, const float* bn3_b,
+    const float* grad_out, const void* ctx, size_t ctx_bytes,
+    float* d_conv1_w, float* d_conv1_b, float* d_conv2_w, float* d_conv2_b, float* d_conv3_w, float* d_conv3_b,
+    float* d_bn1_w, float* d_bn1_b, float* d_bn2_w, float* d_bn2_b, float* d_bn3_w, float* d_bn3_b,
+    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

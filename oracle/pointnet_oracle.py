@@ -137,3 +137,24 @@ def make_reference_module(st: dict, feature_dim: int, training: bool):
     m.load_state_dict({k: v.clone() for k, v in st.items()})
     m.train(training)
     return m
+
+
+def _ste_bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 in the forward, identity in the backward (straight-through)."""
+    return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
+def forward_train_bf16_emulated(x: torch.Tensor, st: dict, dtype=torch.float64) -> torch.Tensor:
+    """Train-mode forward with the train kernels' precision recipe (differentiable, straight-through rounding):
+    layer 1 in full precision, h1 / h2 / W2 / W3 rounded to bf16, batch statistics taken from the rounded
+    pipeline exactly where the kernels take them.  Separates bf16 effects (above all arg-max flips between
+    near-tied points, which re-route gradients discontinuously) from real bugs."""
+    h = x.to(dtype)
+    for n in (1, 2, 3):
+        W = st[f"conv{n}.weight"].to(dtype)[:, :, 0]
+        if n > 1:
+            W = _ste_bf16(W)
+        y = torch.einsum("oc,bcp->bop", W, h) + st[f"conv{n}.bias"].to(dtype)[None, :, None]
+        y = _bn(y, st, n, True, None)
+        h = _ste_bf16(torch.relu(y)) if n < 3 else y
+    return h.max(dim=2).values
