@@ -27,10 +27,12 @@ namespace pn {
 
 constexpr int kPartFloats = 128 * 64 + 128 * 128 + 128 * 128;  // per-CTA partials: T2 | M2 | M1
 constexpr int kPartT2 = 0, kPartM2 = 128 * 64, kPartM1 = 128 * 64 + 128 * 128;
+constexpr int kCov2 = 0, kCov1 = 128 * 128, kCovM2 = kCov1 + 64 * 64, kCovM1 = kCovM2 + 128, kCovFloats = kCovM1 + 64;
 
 struct BwdWs {
   size_t zero_begin, S2, acc2, acc1, zero_end;  // doubles: S2[128] | dbeta2[128], gzh2[128] | db1[64], gzh1[64], T1[64][3]
   size_t red;      // float[kPartFloats]: reduced T2 | M2 | M1
+  size_t cov;      // float[kCovFloats]: Cov(h2) | Cov(h1) | mean h2 | mean h1
   size_t Gs;       // float[F*128]
   size_t vec;      // float[512]: uprime[128] | a2[128] | u1prime[64] | pad
   size_t qimg;     // bf16 [128][128] operand image of Q (32 KB)
@@ -47,6 +49,7 @@ struct BwdWs {
     acc1 = o; o += 64 * 5 * 8;
     zero_end = o;
     red = o; o += (size_t)kPartFloats * 4;
+    cov = o; o += (size_t)kCovFloats * 4;
     Gs = o; o += (size_t)F * 128 * 4;
     vec = o; o += 512 * 4;
     o = up(o, 1024);
@@ -129,13 +132,24 @@ __global__ void __launch_bounds__(128) pn_bwd_q_kernel(const QParams a) {
   }
   const int k = blockIdx.x, j = t;
   const float* istd3 = a.stats + kStatIstd3(a.F);
-  float q = 0.f, u = 0.f;
-  for (int c = 0; c < a.F; ++c) {
+  __shared__ float cqw[1024], cuw[1024];  // per channel c: coefficient * W3[c][k]
+  for (int c = t; c < a.F; c += 128) {
     const float a3 = a.g3[c] * istd3[c];
-    const float wk = a.c3w[c * 128 + k];
-    q = fmaf(a3 * a.dgamma3[c] * istd3[c] * wk, a.c3w[c * 128 + j], q);
-    if ((c & 127) == j) u = fmaf(a3 * a.dbeta3[c], wk, u);
+    const float wk = __ldg(a.c3w + c * 128 + k);
+    cqw[c] = a3 * a.dgamma3[c] * istd3[c] * wk;
+    cuw[c] = a3 * a.dbeta3[c] * wk;
   }
+  __syncthreads();
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, u = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < a.F; c += 4) {
+    q0 = fmaf(cqw[c + 0], __ldg(a.c3w + (c + 0) * 128 + j), q0);
+    q1 = fmaf(cqw[c + 1], __ldg(a.c3w + (c + 1) * 128 + j), q1);
+    q2 = fmaf(cqw[c + 2], __ldg(a.c3w + (c + 2) * 128 + j), q2);
+    q3 = fmaf(cqw[c + 3], __ldg(a.c3w + (c + 3) * 128 + j), q3);
+  }
+  const float q = (q0 + q1) + (q2 + q3);
+  for (int c = j; c < a.F; c += 128) u += cuw[c];
   const float invM = (float)(-1.0 / a.M);
   const __nv_bfloat16 qb = __float2bfloat16_rn(q * invM);
   *reinterpret_cast<__nv_bfloat16*>(a.qimg + (j >> 6) * kKBlockBytes + sw128_off(k, j & 63)) = qb;
@@ -149,23 +163,29 @@ __global__ void __launch_bounds__(128) pn_bwd_q_kernel(const QParams a) {
   if (t == 0) a.vec[k] = red[0];
 }
 
-// Gs[c][k] = sum_b g[b,c] * h2[argmax[b,c]][k]      (one warp per channel, lanes over k)
+// Gs[c][k] = sum_b g[b,c] * h2[argmax[b,c]][k]      (one block per channel: 8 warps split the batch, lanes over k)
 __global__ void __launch_bounds__(256) pn_bwd_gs_kernel(const float* __restrict__ g, const int* __restrict__ argmax,
                                                         const char* __restrict__ h2img, int B, int F, int tiles2,
                                                         float* __restrict__ Gs) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (c >= F) return;
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = lane * 4;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const int n = argmax[(size_t)b * F + c];
-    const float gv = g[(size_t)b * F + c];
+  for (int b = warp; b < B; b += 8) {
+    const int n = __ldg(argmax + (size_t)b * F + c);
+    const float gv = __ldg(g + (size_t)b * F + c);
     const char* tb = h2img + ((size_t)b * tiles2 + (n >> 7)) * kTileBytes + (k0 >> 6) * kKBlockBytes;
     const uint2 v = *reinterpret_cast<const uint2*>(tb + sw128_off(n & 127, k0 & 63));
     a0 = fmaf(gv, bf16_lo(v.x), a0); a1 = fmaf(gv, bf16_hi(v.x), a1);
     a2 = fmaf(gv, bf16_lo(v.y), a2); a3 = fmaf(gv, bf16_hi(v.y), a3);
   }
-  *reinterpret_cast<float4*>(Gs + (size_t)c * 128 + k0) = make_float4(a0, a1, a2, a3);
+  __shared__ float4 red[8][32];
+  red[warp][lane] = make_float4(a0, a1, a2, a3);
+  __syncthreads();
+  if (warp == 0) {
+    float4 r = red[0][lane];
+    for (int w = 1; w < 8; ++w) { const float4 v = red[w][lane]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+    *reinterpret_cast<float4*>(Gs + (size_t)c * 128 + k0) = r;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -279,8 +299,9 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
       const long long e = (long long)(tile - p.nA) * 128 + r;
       uint8_t* dst = sm + kP2H2 + part * kKBlockBytes;
       if (r < nvalid) {
-        const int bb = (int)(e / p.F), c = (int)(e - (long long)bb * p.F);
-        const int n = p.argmax[e];
+        const int c = (int)(e / p.B), bb = (int)(e - (long long)c * p.B);   // channel-major: a tile sees <= 2 channels
+        const size_t ge = (size_t)bb * p.F + c;
+        const int n = p.argmax[ge];
         const char* src = p.h2img + ((size_t)bb * p.tiles2 + (n >> 7)) * kTileBytes + part * kKBlockBytes;
         const int sr = n & 127;
 #pragma unroll
@@ -290,7 +311,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
           const float* xc = p.x + (size_t)bb * 3 * p.P;
           xs[r] = __ldg(xc + n); xs[128 + r] = __ldg(xc + p.P + n); xs[256 + r] = __ldg(xc + 2 * p.P + n);
           centry[r] = c;
-          coefs[r] = p.g3[c] * istd3[c] * p.g[e];
+          coefs[r] = p.g3[c] * istd3[c] * p.g[ge];
         }
       } else {
 #pragma unroll
@@ -354,13 +375,30 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
       const uint8_t* h2row = sm + kP2H2 + (k >> 6) * kKBlockBytes;
       const int kk = k & 63;
+      int w3c = -1;
+      float w3v = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int nb = 64 * hf + 32 * half;
         uint32_t acc[32];
+        if (A) tmem_ld32(trow + (uint32_t)nb, acc);
+        // all shared-memory reads of this half first (h2 is overwritten in place below, so the compiler must not be
+        // left to interleave them with the stores)
+        uint32_t hb[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) hb[i] = *reinterpret_cast<const uint16_t*>(h2row + sw128_off(nb + i, kk));
+        float v[32];
         if (A) {
-          tmem_ld32(trow + (uint32_t)nb, acc);
           tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + upk;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int ce = centry[nb + i];
+            if (ce != w3c) { w3c = ce; w3v = __ldg(p.c3w + (size_t)ce * 128 + k); }  // warp-uniform, <= 2 per tile
+            v[i] = coefs[nb + i] * w3v;
+          }
         }
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -369,17 +407,12 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int n = nb + g8 * 8 + i;
-            uint8_t* hp = const_cast<uint8_t*>(h2row) + sw128_off(n, kk);
-            const uint32_t hb = *reinterpret_cast<const uint16_t*>(hp);
-            const float h = __uint_as_float(hb << 16);
-            float v;
-            if (A) v = __uint_as_float(acc[g8 * 8 + i]) + upk;
-            else v = coefs[n] * __ldg(p.c3w + (size_t)centry[n] * 128 + k);
-            const bool on = (n < nvalid) && (h > 0.f);
-            gz[i] = on ? v : 0.f;
-            hraw[i] = (n < nvalid) ? hb : 0u;
+            const uint32_t hbits = hb[g8 * 8 + i];
+            const bool on = (n < nvalid) && (__uint_as_float(hbits << 16) > 0.f);
+            gz[i] = on ? v[g8 * 8 + i] : 0.f;
+            hraw[i] = (n < nvalid) ? hbits : 0u;
             s_b2 += gz[i];
-            *reinterpret_cast<__nv_bfloat16*>(hp) = __float2bfloat16_rn(a2k * gz[i]);  // GY[n][k], in place of h2
+            *reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(h2row) + sw128_off(n, kk)) = __float2bfloat16_rn(a2k * gz[i]);  // GY[n][k]
           }
           const int n8 = nb + g8 * 8;
           const uint32_t off = (uint32_t)(n8 >> 6) * kKBlockBytes + sw128_off(k, n8 & 63);
@@ -486,9 +519,35 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
 __global__ void __launch_bounds__(256) pn_bwd_reduce_partials_kernel(const float* __restrict__ part, int nparts, float* __restrict__ red) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kPartFloats) return;
-  float s = 0.f;
-  for (int c = 0; c < nparts; ++c) s += part[(size_t)c * kPartFloats + i];
-  red[i] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 3 < nparts; c += 4) {
+    s0 += part[(size_t)(c + 0) * kPartFloats + i]; s1 += part[(size_t)(c + 1) * kPartFloats + i];
+    s2 += part[(size_t)(c + 2) * kPartFloats + i]; s3 += part[(size_t)(c + 3) * kPartFloats + i];
+  }
+  for (; c < nparts; ++c) s0 += part[(size_t)c * kPartFloats + i];
+  red[i] = (s0 + s1) + (s2 + s3);
+}
+
+// cov2[j][k] = M2[j][k]/M - m2[j] m2[k] (128 x 128), cov1[i][j] likewise (64 x 64, m1 = column 64 of M1), m2, m1
+__global__ void __launch_bounds__(256) pn_bwd_cov_kernel(const float* __restrict__ red, const double* __restrict__ S2, double M,
+                                                         float* __restrict__ cov) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float invM = (float)(1.0 / M);
+  if (i < 128 * 128) {
+    const int j = i >> 7, k = i & 127;
+    cov[kCov2 + i] = red[kPartM2 + i] * invM - (float)(S2[j] / M) * (float)(S2[k] / M);
+  } else if (i < 128 * 128 + 64 * 64) {
+    const int r = i - 128 * 128;
+    const int a = r >> 6, b = r & 63;
+    cov[kCov1 + r] = red[kPartM1 + a * 128 + b] * invM - (red[kPartM1 + a * 128 + 64] * invM) * (red[kPartM1 + b * 128 + 64] * invM);
+  } else if (i < 128 * 128 + 64 * 64 + 128) {
+    const int k = i - 128 * 128 - 64 * 64;
+    cov[kCovM2 + k] = (float)(S2[k] / M);
+  } else if (i < 128 * 128 + 64 * 64 + 128 + 64) {
+    const int j = i - 128 * 128 - 64 * 64 - 128;
+    cov[kCovM1 + j] = red[kPartM1 + j * 128 + 64] * invM;
+  }
 }
 
 // dgamma2 / dbeta2, then Q1[j][i] = -(1/M) sum_k a2 dgamma2 istd2 W2[k][j] W2[k][i] (operand image, rows >= 64 zero)
@@ -496,7 +555,8 @@ __global__ void __launch_bounds__(256) pn_bwd_reduce_partials_kernel(const float
 struct MidParams {
   const float *c2w, *g2, *stats;
   const double* acc2;
-  const float* red;  // M1 (column 64 = S1)
+  const float* red;  // T2
+  const float* cov;  // mean h1
   double M;
   char* q1img;
   float* vec;
@@ -529,7 +589,7 @@ __global__ void __launch_bounds__(64) pn_bwd_mid_kernel(const MidParams a) {
   const __nv_bfloat16 qb = __float2bfloat16_rn(qv * invM);
   *reinterpret_cast<__nv_bfloat16*>(a.q1img + sw128_off(j, i)) = qb;
   *reinterpret_cast<__nv_bfloat16*>(a.q1img + sw128_off(64 + j, i)) = __float2bfloat16_rn(0.f);
-  const float m1 = (float)((double)a.red[kPartM1 + i * 128 + 64] / a.M);
+  const float m1 = a.cov[kCovM1 + i];
   red[i] = uv * invM - __bfloat162float(qb) * m1;
   __syncthreads();
   for (int off = 32; off >= 1; off >>= 1) {
@@ -668,7 +728,7 @@ struct FinalParams {
   const float *c1w, *c2w, *c3w, *g1, *be1, *g2, *g3;
   const float* stats;
   const double *S2, *acc2, *acc1, *xstat;
-  const float *red, *Gs;
+  const float *red, *cov, *Gs;
   double M;
   int F;
   const float *dgamma3, *dbeta3;   // = d_bn3_w, d_bn3_b (already written)
@@ -683,32 +743,28 @@ __global__ void __launch_bounds__(128) pn_bwd_final_kernel(const FinalParams a) 
     const int c = blockIdx.x, k = t;
     wrow[t] = a.c3w[c * 128 + t];
     __syncthreads();
-    const float m2k = (float)(a.S2[k] / M);
-    float acc = 0.f;
-    for (int j = 0; j < 128; ++j) {  // (W3 Cov2)[c][k], Cov2 = M2/M - m2 m2^T
-      const float cov = (float)((double)a.red[kPartM2 + j * 128 + k] / M) - (float)(a.S2[j] / M) * m2k;
-      acc = fmaf(wrow[j], cov, acc);
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 128; j += 2) {  // (W3 Cov2)[c][k]
+      acc0 = fmaf(wrow[j], __ldg(a.cov + kCov2 + j * 128 + k), acc0);
+      acc1 = fmaf(wrow[j + 1], __ldg(a.cov + kCov2 + (j + 1) * 128 + k), acc1);
     }
     const float istd = a.stats[kStatIstd3(a.F) + c];
     const float a3 = a.g3[c] * istd;
-    a.d_c3w[c * 128 + k] = a3 * (a.Gs[(size_t)c * 128 + k] - a.dbeta3[c] * m2k - a.dgamma3[c] * istd * acc);
+    a.d_c3w[c * 128 + k] = a3 * (a.Gs[(size_t)c * 128 + k] - a.dbeta3[c] * a.cov[kCovM2 + k] - a.dgamma3[c] * istd * (acc0 + acc1));
     if (t == 0) a.d_c3b[c] = 0.f;
   } else if ((int)blockIdx.x < a.F + 128) {
     const int k = blockIdx.x - a.F, j = t;
     if (t < 64) wrow[t] = a.c2w[k * 64 + t];
     __syncthreads();
     if (j < 64) {
-      const float m1j = (float)((double)a.red[kPartM1 + j * 128 + 64] / M);
       float acc = 0.f;
-      for (int i = 0; i < 64; ++i) {
-        const float m1i = (float)((double)a.red[kPartM1 + i * 128 + 64] / M);
-        const float cov = (float)((double)a.red[kPartM1 + i * 128 + j] / M) - m1i * m1j;
-        acc = fmaf(wrow[i], cov, acc);
-      }
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) acc = fmaf(wrow[i], __ldg(a.cov + kCov1 + i * 64 + j), acc);
       const float istd = a.stats[kStatIstd2 + k];
       const float dbeta = (float)a.acc2[k];
       const float dgamma = a.dgamma2[k];
-      a.d_c2w[k * 64 + j] = a.g2[k] * istd * (a.red[kPartT2 + k * 64 + j] - dbeta * m1j - dgamma * istd * acc);
+      a.d_c2w[k * 64 + j] = a.g2[k] * istd * (a.red[kPartT2 + k * 64 + j] - dbeta * a.cov[kCovM1 + j] - dgamma * istd * acc);
     }
     if (t == 0) a.d_c2b[k] = 0.f;
   } else {
@@ -817,7 +873,7 @@ extern "C" int crdpn_pointnet_backward(
   pn::QParams qp{conv3_w, bn3_w, d_bn3_w, d_bn3_b, stats, conv2_w, bn2_w, S2, M, (int)F, w + W.qimg, w + W.w2timg, vec};
   pn::pn_bwd_q_kernel<<<129, 128, 0, st>>>(qp);
   CRDPN_LAUNCH_CHECK("pn_bwd_q_kernel");
-  pn::pn_bwd_gs_kernel<<<(int)((F + 7) / 8), 256, 0, st>>>(grad_out, argmax, h2img, (int)B, (int)F, L.tiles2, Gs);
+  pn::pn_bwd_gs_kernel<<<(int)F, 256, 0, st>>>(grad_out, argmax, h2img, (int)B, (int)F, L.tiles2, Gs);
   CRDPN_LAUNCH_CHECK("pn_bwd_gs_kernel");
 
   pn::Pass2Params p2;
@@ -832,14 +888,16 @@ extern "C" int crdpn_pointnet_backward(
   CRDPN_LAUNCH_CHECK("pn_bwd_pass2_kernel");
   pn::pn_bwd_reduce_partials_kernel<<<(pn::kPartFloats + 255) / 256, 256, 0, st>>>((const float*)(w + W.part), grid, red);
   CRDPN_LAUNCH_CHECK("pn_bwd_reduce_partials_kernel");
-  pn::MidParams mp{conv2_w, bn2_w, stats, acc2, red, M, w + W.q1img, vec, d_bn2_w, d_bn2_b};
+  pn::pn_bwd_cov_kernel<<<(128 * 128 + 64 * 64 + 192 + 255) / 256, 256, 0, st>>>(red, S2, M, (float*)(w + W.cov));
+  CRDPN_LAUNCH_CHECK("pn_bwd_cov_kernel");
+  pn::MidParams mp{conv2_w, bn2_w, stats, acc2, red, (const float*)(w + W.cov), M, w + W.q1img, vec, d_bn2_w, d_bn2_b};
   pn::pn_bwd_mid_kernel<<<64, 64, 0, st>>>(mp);
   CRDPN_LAUNCH_CHECK("pn_bwd_mid_kernel");
   pn::Pass3Params p3{x, (int)B, (int)P, L.tiles2, p2.nA, train_par, w + W.q1img, vec, acc1};
   pn::pn_bwd_pass3_kernel<<<grid, 256, pn::kP3Smem, st>>>(p3);
   CRDPN_LAUNCH_CHECK("pn_bwd_pass3_kernel");
   pn::FinalParams fp{conv1_w, conv2_w, conv3_w, bn1_w, bn1_b, bn2_w, bn3_w, stats, S2, acc2, acc1, (const double*)(c + L.xstat),
-                     red, Gs, M, (int)F, d_bn3_w, d_bn3_b, d_bn2_w,
+                     red, (const float*)(w + W.cov), Gs, M, (int)F, d_bn3_w, d_bn3_b, d_bn2_w,
                      d_conv1_w, d_conv1_b, d_conv2_w, d_conv2_b, d_conv3_w, d_conv3_b, d_bn1_w, d_bn1_b};
   pn::pn_bwd_final_kernel<<<(int)F + 129, 128, 0, st>>>(fp);
   CRDPN_LAUNCH_CHECK("pn_bwd_final_kernel");

@@ -492,8 +492,12 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_kernel_v2(const FwdP
     }
   } else if (warp >= 4 && warp < 8) {
    if constexpr (TRAIN) {
-    // ============ layer-3 epilogue, train mode: running max + arg-max point per (cloud, channel), and the
-    // per-channel sum / sum of squares over all real points (BN3 batch statistics) =======================
+    // ============ layer-3 epilogue, train mode:
+    // running max + arg-max point per (cloud, channel) and the per-channel sum / sum of squares over all real
+    // points (BN3 batch statistics).  The arg-max rides in the low byte of the value: each accumulator word gets
+    // its position inside the 16-column chunk in place of its 8 lowest mantissa bits (one PRMT), then the usual
+    // 3-input max tree runs on those words; one compare per chunk tracks the chunk.  No per-value compare/select
+    // chain.  The returned maximum is exact to 2^-15 relative.
     const int q = warp & 3;
     float rmax[NSLAB], rs[NSLAB], rq[NSLAB];
     int ridx[NSLAB];
@@ -504,7 +508,8 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_kernel_v2(const FwdP
     auto flush = [&](int cloud) {
 #pragma unroll
       for (int s = 0; s < NSLAB; ++s) {
-        const unsigned long long key = ((unsigned long long)enc_ordered(rmax[s]) << 32) |
+        const float v = __uint_as_float(__float_as_uint(rmax[s]) & 0xffffff00u);
+        const unsigned long long key = ((unsigned long long)enc_ordered(v) << 32) |
                                        (unsigned long long)(0xffffffffu - (uint32_t)ridx[s]);
         atomicMax(p.enc64 + (size_t)cloud * p.F + s * 128 + q * 32 + lane, key);
         rmax[s] = -INFINITY;
@@ -527,35 +532,45 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_kernel_v2(const FwdP
         if (slot) ++seen1; else ++seen0;
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u * slot;
-        float m = rmax[s];
-        int ml = -1;
-        unsigned long long s2 = 0ull, q2 = 0ull;
+        float m = -INFINITY;
+        int mc = 0;
+        unsigned long long sa = 0ull, sb = 0ull, qa = 0ull, qb = 0ull;
         uint32_t ra[16], rb[16];
+        // one 16-column chunk: position inside the chunk -> low byte, 3-input max tree, one compare per chunk
+        auto chunk = [&](const uint32_t* cur, int c) {
+          float w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = __uint_as_float(__byte_perm(cur[i], (uint32_t)i, 0x3214));
+          const float t0 = max3(w[0], w[1], w[2]), t1 = max3(w[3], w[4], w[5]), t2 = max3(w[6], w[7], w[8]);
+          const float t3 = max3(w[9], w[10], w[11]), t4 = max3(w[12], w[13], w[14]);
+          const float cm = fmaxf(max3(t0, t1, t2), max3(t3, t4, w[15]));
+          if (cm > m) { m = cm; mc = c; }
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            add2(sa, cur[i], cur[i + 1]);     add2(sb, cur[i + 2], cur[i + 3]);
+            sq2(qa, cur[i], cur[i + 1]);      sq2(qb, cur[i + 2], cur[i + 3]);
+          }
+        };
         tmem_ld16(taddr, ra);
         tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          uint32_t* cur = (c & 1) ? rb : ra;
-          uint32_t* nxt = (c & 1) ? ra : rb;
-          if (c + 1 < 16) tmem_ld16(taddr + 16u * (c + 1), nxt);
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float a = __uint_as_float(cur[i]), b = __uint_as_float(cur[i + 1]);
-            if (a > m) { m = a; ml = 16 * c + i; }
-            if (b > m) { m = b; ml = 16 * c + i + 1; }
-            add2(s2, cur[i], cur[i + 1]);
-            sq2(q2, cur[i], cur[i + 1]);
-          }
-          if (c + 1 < 16) tmem_ld_wait();
+        // rolled (the fully unrolled epilogue was instruction-fetch bound: 136 KB of straight-line code per unit)
+#pragma unroll 1
+        for (int c = 0; c < 16; c += 2) {
+          tmem_ld16(taddr + 16u * (uint32_t)(c + 1), rb);
+          chunk(ra, c);
+          tmem_ld_wait();
+          if (c + 2 < 16) tmem_ld16(taddr + 16u * (uint32_t)(c + 2), ra);
+          chunk(rb, c + 1);
+          tmem_ld_wait();
         }
         const float ylast = __uint_as_float(rb[15]);  // column 255: the last real point whenever ndup > 0
         tc_fence_before();
-        mbar_arrive_n(bar(ACC_EMPTY + slot), 2u);
-        rs[s] += pair_sum(s2) - (float)ndup * ylast;
-        rq[s] += pair_sum(q2) - (float)ndup * ylast * ylast;
-        if (ml >= 0) {
+        mbar_arrive_n(bar(ACC_EMPTY + slot), 2u);  // 128 epilogue threads stand in for the slot's 256 arrivals
+        rs[s] += pair_sum(sa) + pair_sum(sb) - (float)ndup * ylast;
+        rq[s] += pair_sum(qa) + pair_sum(qb) - (float)ndup * ylast * ylast;
+        if (m > rmax[s]) {
           rmax[s] = m;
-          const int pt = p_base + ml;
+          const int pt = p_base + 16 * mc + (int)(__float_as_uint(m) & 0xfu);
           ridx[s] = pt < p.P ? pt : p.P - 1;
         }
       }
@@ -630,9 +645,11 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_kernel_v2(const FwdP
     }
    }
   } else if (warp >= 8) {
-    // =========================== front end, group g = half g: layer 1 + layer-2 epilogue ======================
-    const int g = warp >= 12 ? 1 : 0;
-    const int t = (threadIdx.x - 256) & 127;  // point row inside the half; also the TMEM lane
+    // =========================== front end: layer 1 + layer-2 epilogue ======================================
+    // two groups of 4 warps, group g owns half g of every unit
+    constexpr int NG = 1;
+    const int g0 = warp >= 12 ? 1 : 0;
+    const int t = threadIdx.x & 127;  // point row inside the half; also the TMEM lane
     const int q = warp & 3;
     const float4* w1p = reinterpret_cast<const float4*>(sm + kOffPar);
     const float4* b2f = reinterpret_cast<const float4*>(sm + kOffPar + 64 * 16);
@@ -645,28 +662,32 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_kernel_v2(const FwdP
       const int p_base = (unit - cloud * p.tiles_per_cloud) * kUnitPts;
       const uint32_t uph = (uint32_t)u & 1u;
       const float* xc = p.x + (size_t)cloud * 3 * p.P;
-      int pt = p_base + g * kHalfPts + t;
-      pt = pt < p.P ? pt : p.P - 1;  // ragged tail: repeat the last real point (max is idempotent)
-      const float x0 = __ldg(xc + pt), x1 = __ldg(xc + p.P + pt), x2 = __ldg(xc + 2 * p.P + pt);
-      mbar_wait_t(bar(H1_EMPTY + g), uph ^ 1u, dw[0]);
-      const long long t_l1 = clock64();
-      uint8_t* dst = sm + kOffH1 + g * kKBlockBytes;
 #pragma unroll
-      for (int cg = 0; cg < 8; ++cg) {
-        float v[8];
+      for (int gi = 0; gi < NG; ++gi) {
+        const int g = g0 + gi;
+        int pt = p_base + g * kHalfPts + t;
+        pt = pt < p.P ? pt : p.P - 1;  // ragged tail: repeat the last real point (max is idempotent)
+        const float x0 = __ldg(xc + pt), x1 = __ldg(xc + p.P + pt), x2 = __ldg(xc + 2 * p.P + pt);
+        mbar_wait_t(bar(H1_EMPTY + g), uph ^ 1u, dw[0]);
+        const long long t_l1 = clock64();
+        uint8_t* dst = sm + kOffH1 + g * kKBlockBytes;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const float4 w = w1p[cg * 8 + jj];
-          v[jj] = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
+        for (int cg = 0; cg < 8; ++cg) {
+          float v[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 w = w1p[cg * 8 + jj];
+            v[jj] = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
+          }
+          uint4 o;
+          o.x = pack_relu_bf16(v[0], v[1]); o.y = pack_relu_bf16(v[2], v[3]);
+          o.z = pack_relu_bf16(v[4], v[5]); o.w = pack_relu_bf16(v[6], v[7]);
+          *reinterpret_cast<uint4*>(dst + sw128_off(t, cg * 8)) = o;
         }
-        uint4 o;
-        o.x = pack_relu_bf16(v[0], v[1]); o.y = pack_relu_bf16(v[2], v[3]);
-        o.z = pack_relu_bf16(v[4], v[5]); o.w = pack_relu_bf16(v[6], v[7]);
-        *reinterpret_cast<uint4*>(dst + sw128_off(t, cg * 8)) = o;
+        fence_proxy_async();
+        mbar_arrive(bar(H1_FULL + g));
+        dw[4] += clock64() - t_l1;
       }
-      fence_proxy_async();
-      mbar_arrive(bar(H1_FULL + g));
-      dw[4] += clock64() - t_l1;
     };
 
     if (NU > 0) layer1(0);
@@ -676,57 +697,67 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_kernel_v2(const FwdP
       mbar_wait_t(bar(A2_FULL), uph, dw[1]);
       tc_fence_after();
       const long long t_e2 = clock64();
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u * slot + 128u * g;
-      uint4 pk[16];  // this point's 128 layer-2 channels: bias + ReLU + bf16, 8 channels per 16 bytes
+      uint4 pk[NG][16];  // this point's 128 layer-2 channels per half: bias + ReLU + bf16, 8 channels per 16 bytes
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + 32u * c, r);
-        tmem_ld_wait();
+      for (int gi = 0; gi < NG; ++gi) {
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u * slot + 128u * (g0 + gi);
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int ch = c * 32 + g8 * 8;
-          const float4 ba = b2f[ch / 4], bb = b2f[ch / 4 + 1];
-          uint4 o;
-          if constexpr (TRAIN) {  // BN2 with batch statistics: z2 = sc2 * (raw W2 . h1) + sh2
-            const float4 sa = b2f[32 + ch / 4], sb = b2f[32 + ch / 4 + 1];
-            o.x = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 0]), sa.x, ba.x), fmaf(__uint_as_float(r[g8 * 8 + 1]), sa.y, ba.y));
-            o.y = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 2]), sa.z, ba.z), fmaf(__uint_as_float(r[g8 * 8 + 3]), sa.w, ba.w));
-            o.z = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 4]), sb.x, bb.x), fmaf(__uint_as_float(r[g8 * 8 + 5]), sb.y, bb.y));
-            o.w = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 6]), sb.z, bb.z), fmaf(__uint_as_float(r[g8 * 8 + 7]), sb.w, bb.w));
-          } else {
-            o.x = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 0]) + ba.x, __uint_as_float(r[g8 * 8 + 1]) + ba.y);
-            o.y = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 2]) + ba.z, __uint_as_float(r[g8 * 8 + 3]) + ba.w);
-            o.z = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 4]) + bb.x, __uint_as_float(r[g8 * 8 + 5]) + bb.y);
-            o.w = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 6]) + bb.z, __uint_as_float(r[g8 * 8 + 7]) + bb.w);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + 32u * c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int ch = c * 32 + g8 * 8;
+            const float4 ba = b2f[ch / 4], bb = b2f[ch / 4 + 1];
+            uint4 o;
+            if constexpr (TRAIN) {  // BN2 with batch statistics: z2 = sc2 * (raw W2 . h1) + sh2
+              const float4 sa = b2f[32 + ch / 4], sb = b2f[32 + ch / 4 + 1];
+              o.x = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 0]), sa.x, ba.x), fmaf(__uint_as_float(r[g8 * 8 + 1]), sa.y, ba.y));
+              o.y = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 2]), sa.z, ba.z), fmaf(__uint_as_float(r[g8 * 8 + 3]), sa.w, ba.w));
+              o.z = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 4]), sb.x, bb.x), fmaf(__uint_as_float(r[g8 * 8 + 5]), sb.y, bb.y));
+              o.w = pack_relu_bf16(fmaf(__uint_as_float(r[g8 * 8 + 6]), sb.z, bb.z), fmaf(__uint_as_float(r[g8 * 8 + 7]), sb.w, bb.w));
+            } else {
+              o.x = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 0]) + ba.x, __uint_as_float(r[g8 * 8 + 1]) + ba.y);
+              o.y = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 2]) + ba.z, __uint_as_float(r[g8 * 8 + 3]) + ba.w);
+              o.z = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 4]) + bb.x, __uint_as_float(r[g8 * 8 + 5]) + bb.y);
+              o.w = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 6]) + bb.z, __uint_as_float(r[g8 * 8 + 7]) + bb.w);
+            }
+            pk[gi][c * 4 + g8] = o;
           }
-          pk[c * 4 + g8] = o;
         }
+        tc_fence_before();
+        mbar_arrive(bar(ACC_EMPTY + slot));   // this half of the slot is free again; the values live in registers now
       }
-      tc_fence_before();
-      mbar_arrive(bar(ACC_EMPTY + slot));   // the slot is free again; the values live in registers now
       dw[5] += clock64() - t_e2;
       mbar_wait_t(bar(H2_EMPTY), uph ^ 1u, dw[2]);  // layer 3 of the previous unit has finished reading h2
-      uint8_t* dst = sm + kOffH2;
-      const int row = g * kHalfPts + t;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int ch = i * 8;
-        *reinterpret_cast<uint4*>(dst + (ch >> 6) * kH2KBlockBytes + sw128_off(row, ch & 63)) = pk[i];
-      }
-      fence_proxy_async();
-      mbar_arrive(bar(H2_FULL + g));
-      if constexpr (TRAIN) {  // keep this tile of h2 for backward, in the same swizzled operand image
-        char* gt = p.h2img + ((size_t)(u_begin + u) * 2 + g) * kTileBytes;
+      for (int gi = 0; gi < NG; ++gi) {
+        const int g = g0 + gi;
+        uint8_t* dst = sm + kOffH2;
+        const int row = g * kHalfPts + t;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int ch = i * 8;
-          *reinterpret_cast<uint4*>(gt + (ch >> 6) * kKBlockBytes + sw128_off(t, ch & 63)) = pk[i];
+          *reinterpret_cast<uint4*>(dst + (ch >> 6) * kH2KBlockBytes + sw128_off(row, ch & 63)) = pk[gi][i];
+        }
+        fence_proxy_async();
+        mbar_arrive(bar(H2_FULL + g));
+      }
+      if constexpr (TRAIN) {  // keep these tiles of h2 for backward, in the same swizzled operand image
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+          char* gt = p.h2img + ((size_t)(u_begin + u) * 2 + g0 + gi) * kTileBytes;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int ch = i * 8;
+            *reinterpret_cast<uint4*>(gt + (ch >> 6) * kKBlockBytes + sw128_off(t, ch & 63)) = pk[gi][i];
+          }
         }
       }
       if (u + 1 < NU) layer1(u + 1);  // overlaps with layer 3 of unit u on the tensor pipe
     }
-    if (p.dbg && t == 0 && g == 0) {
+    if (p.dbg && t == 0 && g0 == 0) {
       p.dbg[blockIdx.x * 32 + 12] = dw[0]; p.dbg[blockIdx.x * 32 + 13] = dw[1]; p.dbg[blockIdx.x * 32 + 14] = dw[2];
       p.dbg[blockIdx.x * 32 + 15] = clock64() - t_role; p.dbg[blockIdx.x * 32 + 16] = dw[4]; p.dbg[blockIdx.x * 32 + 17] = dw[5];
       p.dbg[blockIdx.x * 32 + 18] = NU;

@@ -51,6 +51,7 @@ def bench_pointnet(pkg, torch, dev, args, tf_peak, peak_kind, B=160, P=2500, F=1
                         "peak_kind": peak_kind, "kernel": "pointnet_fwd_eval_kernel"},
            "e2e": {"value": B * P / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": x_host.numel() * 4,
                    "d2h_bytes_per_step": B * F * 4}}
+    out["train"] = bench_pointnet_train(pkg, torch, dev, st, x, steps, warmup, tf_peak, B, P, F)
     if not os.environ.get("CRDPN_BENCH_QUICK"):
         torch.set_num_threads(os.cpu_count() or 1)
         xs = x_host[:16]
@@ -60,4 +61,50 @@ def bench_pointnet(pkg, torch, dev, args, tf_peak, peak_kind, B=160, P=2500, F=1
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": 16 * P / dt, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"16 of {B} clouds, fp32 torch ops on CPU (oracle restatement of ShapeEncoderPC)"}
+        # train-mode CPU baseline: forward + backward of the restated module on a sample of the clouds
+        p = {k: (v.clone().requires_grad_() if v.is_floating_point() and "running" not in k else v.clone()) for k, v in st.items()}
+        po.forward(xs, p, training=True, dtype=torch.float32).sum().backward()
+        t0 = time.perf_counter()
+        po.forward(xs, p, training=True, dtype=torch.float32).sum().backward()
+        dt = time.perf_counter() - t0
+        out["train"]["cpu_baseline"] = {"value": 16 * P / dt, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+                                        "sample": f"16 of {B} clouds, train-mode forward+backward, fp32 torch autograd on CPU"}
     return out
+
+
+def bench_pointnet_train(pkg, torch, dev, st, x, steps, warmup, tf_peak, B, P, F):
+    """Train-mode step (training.py:47,75): batch-statistics forward, then backward for the 12 parameter tensors."""
+    enc = pkg.ShapeEncoderPC(F)
+    enc.load_state_dict(st)
+    enc = enc.to(dev).train()
+    gout = torch.randn(B, F, device=dev)
+
+    def fwd():
+        with torch.no_grad():
+            enc(x)
+
+    def step():
+        for p in enc.parameters():
+            p.grad = None
+        enc(x).backward(gout)
+
+    res = {}
+    for name, fn in (("forward", fwd), ("forward_backward", step)):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        l0 = pkg._native.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[name] = {"ms_per_step": ms, "points_per_sec": B * P / (ms * 1e-3),
+                     "launches_per_step": (pkg._native.launch_count() - l0) // steps}
+    res["workload"] = f"pointnet_train_B{B}_P{P}_3-64-128-{F}_bf16"
+    res["forward"]["tflops_fwd_equiv"] = FLOP_PER_POINT * B * P / (res["forward"]["ms_per_step"] * 1e-3) / 1e12
+    res["note"] = ("backward never forms the B*F*P tensor: sparse arg-max stream + affine dense stream (128x128 and 64x64 "
+                   "per point) on tcgen05; the stock autograd chain needs 2 x 111.6 GFLOP of dgrad/wgrad plus ~10 passes over 1.64 GB")
+    return res

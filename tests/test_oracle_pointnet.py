@@ -81,3 +81,54 @@ def test_max_commutes_with_bn3_sign_trick(gold):
     out = (pick - st["bn3.running_mean"].double()) * scale + st["bn3.bias"].double()
     np.testing.assert_allclose(out.numpy(), po.forward(x, st).numpy(), rtol=1e-10, atol=1e-10)
     assert (scale < 0).sum() > 100
+
+
+def _grads(fn, x, st, gout):
+    p = {k: (v.clone().double().requires_grad_() if v.is_floating_point() and "running" not in k else v) for k, v in st.items()}
+    out = fn(x, p)
+    (out * gout).sum().backward()
+    return out.detach(), {k: v.grad for k, v in p.items() if getattr(v, "grad", None) is not None}
+
+
+def test_bf16_emulated_train_oracle_is_the_oracle_without_rounding(gold, monkeypatch):
+    """forward_train_bf16_emulated == forward(training=True) once rounding is switched off: same graph, so it
+    inherits the pin to the reference; with rounding on, features stay within the bf16 tolerance."""
+    g, st = gold
+    x, gout = torch.from_numpy(g["x"]), torch.from_numpy(g["gout"]).double()
+    o_ref, g_ref = _grads(lambda a, p: po.forward(a, p, training=True), x, st, gout)
+    o_emu, _ = _grads(po.forward_train_bf16_emulated, x, st, gout)
+    assert ((o_emu - o_ref).abs().max() / o_ref.abs().max()).item() < 1e-2
+    monkeypatch.setattr(po, "_ste_bf16", lambda t: t)
+    o_id, g_id = _grads(po.forward_train_bf16_emulated, x, st, gout)
+    assert torch.allclose(o_id, o_ref, rtol=1e-12, atol=1e-12)
+    for k in g_ref:
+        assert torch.allclose(g_id[k], g_ref[k], rtol=1e-9, atol=1e-12), k
+
+
+def test_bf16_gradient_deviation_is_routing_not_arithmetic(gold):
+    """Why train-mode GRADIENTS of a bf16 pipeline cannot meet 1e-2 against the fp32 reference while the features
+    do: max-pool and ReLU route gradients discontinuously, and bf16 rounding flips near-tied arg-max points / ReLU
+    gates.  Evidence: conv3.weight's gradient differs by >3% between the fp and the bf16-recipe oracle, but by
+    <1.5% once the fp oracle is forced to route through the bf16 run's arg-max points."""
+    g, st = gold
+    x, gout = torch.from_numpy(g["x"]), torch.from_numpy(g["gout"]).double()
+
+    def body(a, p, rounded):
+        h = a.double()
+        for n in (1, 2, 3):
+            W = p[f"conv{n}.weight"].double()[:, :, 0]
+            if rounded and n > 1:
+                W = po._ste_bf16(W)
+            y = torch.einsum("oc,bcp->bop", W, h) + p[f"conv{n}.bias"].double()[None, :, None]
+            y = po._bn(y, p, n, True, None)
+            h = (po._ste_bf16(torch.relu(y)) if rounded else torch.relu(y)) if n < 3 else y
+        return h
+
+    idx = body(x, {k: v for k, v in st.items()}, True).argmax(dim=2)
+    _, g_fp = _grads(lambda a, p: po.forward(a, p, training=True), x, st, gout)
+    _, g_emu = _grads(po.forward_train_bf16_emulated, x, st, gout)
+    _, g_forced = _grads(lambda a, p: body(a, p, False).gather(2, idx[:, :, None])[:, :, 0], x, st, gout)
+    nrel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    k = "conv3.weight"
+    assert nrel(g_emu[k], g_fp[k]) > 3e-2
+    assert nrel(g_emu[k], g_forced[k]) < 1.5e-2

@@ -74,7 +74,7 @@ def test_permutation_and_duplication_invariance_bitwise(pkg, cuda):
     assert torch.equal(a[1:2], d)
 
 
-def test_repack_after_parameter_change_and_train_mode_is_loud(pkg, cuda):
+def test_repack_after_parameter_change_and_cpu_input_is_loud(pkg, cuda):
     st = po.random_state(1024, seed=3)
     x = po.random_clouds(2, 300, seed=4)
     enc = _encoder(pkg, st, 1024, cuda)
@@ -83,9 +83,6 @@ def test_repack_after_parameter_change_and_train_mode_is_loud(pkg, cuda):
         enc.bn3.bias.add_(1.0)
     b = enc(x.to(cuda))
     assert torch.allclose(b, a + 1.0, atol=1e-5)
-    enc.train()
-    with pytest.raises(RuntimeError, match="train-mode"):
-        enc(x.to(cuda))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         enc.eval()(x)
 
