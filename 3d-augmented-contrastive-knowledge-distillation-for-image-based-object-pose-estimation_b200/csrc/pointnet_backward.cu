@@ -21,6 +21,7 @@
 //   | mid (dgamma2, Q1, u1') | pass3 (tcgen05: BN2's dense term through layer 1) | final (dW3, dW2, dW1, BN grads)
 #include "pointnet_common.cuh"
 #include "pointnet_train.cuh"
+#include <stdlib.h>
 
 namespace crdpn {
 namespace pn {
@@ -121,10 +122,10 @@ __global__ void __launch_bounds__(128) pn_bwd_q_kernel(const QParams a) {
   const int t = threadIdx.x;
   __shared__ float red[128];
   if (blockIdx.x == 128) {
-    // W2T[j][k] = W2[k][j]; rows j >= 64 are zero
+    // W2T[j][k] = a2[k] W2[k][j], a2 = gamma2 * istd2 (BN2's scale on the way back); rows j >= 64 are zero
     for (int i = t; i < 128 * 128; i += 128) {
       const int j = i >> 7, k = i & 127;
-      const float v = j < 64 ? a.c2w[k * 64 + j] : 0.f;
+      const float v = j < 64 ? a.c2w[k * 64 + j] * (a.g2[k] * a.stats[kStatIstd2 + k]) : 0.f;
       *reinterpret_cast<__nv_bfloat16*>(a.w2timg + (k >> 6) * kKBlockBytes + sw128_off(j, k & 63)) = __float2bfloat16_rn(v);
     }
     a.vec[128 + t] = a.g2[t] * a.stats[kStatIstd2 + t];
@@ -211,6 +212,7 @@ struct Pass2Params {
   const float* vec;          // uprime[128] | a2[128]
   double *acc2, *acc1;
   float* part;
+  int debug;   // CRDPN_PN_DEBUG: block 0 prints per-phase cycle totals
 };
 constexpr uint32_t kP2H2 = 0, kP2Q = 32768, kP2H2T = 65536, kP2GZT = 98304, kP2H1T = 131072, kP2W2T = 163840;
 constexpr uint32_t kP2X = 196608, kP2Par = kP2X + 1536, kP2Ent = kP2Par + 2048, kP2Bar = kP2Ent + 1024;
@@ -219,6 +221,74 @@ constexpr uint32_t kP2Smem = kP2Bar + 64 + 1024;
 __device__ __forceinline__ uint32_t koff128(int kk) {  // descriptor offset of the kk-th K=16 step (two 64-wide K-blocks)
   return (uint32_t)(kk >> 2) * (kKBlockBytes >> 4) + (uint32_t)(kk & 3) * 2u;
 }
+
+// epilogue 1 of pass 2: thread = layer-2 channel k (TMEM lane), its 64 of the tile's 128 points (columns).
+//   gz2[n][k] = grad_h2[n][k] where h2[n][k] > 0;  written three ways: GY[n][k] (bf16, in place of h2: B operand of
+//   D3 = (a2 W2)^T gz2^T), GZT[k][n] (A operand of T2 += gz2^T h1), and for stream A the transposed h2 image H2T[k][n].
+// A: real points (grad_h2 = Q h2 + u' from TMEM); !A: virtual points (coef[e] * W3[c_e][k]).  FULL: no padding rows.
+template <bool A, bool FULL>
+__device__ __forceinline__ void pass2_epilogue1(uint8_t* sm, uint32_t trow, int k, int hf, float upk, int nvalid,
+                                                const int* centry, const float* coefs, const float* __restrict__ c3w) {
+  uint8_t* h2row = sm + kP2H2 + (k >> 6) * kKBlockBytes;
+  const int kk = k & 63;
+  int w3c = -1;
+  float w3v = 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int nb = 64 * hf + 32 * half;
+    uint32_t acc[32];
+    if (A) tmem_ld32(trow + (uint32_t)nb, acc);
+    // every shared-memory read of this half first: h2 is overwritten in place below
+    uint32_t hb[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) hb[i] = *reinterpret_cast<const uint16_t*>(h2row + sw128_off(nb + i, kk));
+    if (!FULL) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) hb[i] = (nb + i < nvalid) ? hb[i] : 0u;  // padding rows repeat a real point: gate them off
+    }
+    float v[32];
+    if (A) {
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + upk;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ce = centry[nb + i];
+        if (ce != w3c) { w3c = ce; w3v = __ldg(c3w + (size_t)ce * 128 + k); }  // warp-uniform, <= 2 per tile
+        v[i] = coefs[nb + i] * w3v;
+      }
+    }
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const int n = nb + g8 * 8 + i;
+        // h2 is a ReLU output (never negative): h2 > 0  <=>  its bf16 bits are non-zero
+        const float g0 = hb[g8 * 8 + i] ? v[g8 * 8 + i] : 0.f;
+        const float g1 = hb[g8 * 8 + i + 1] ? v[g8 * 8 + i + 1] : 0.f;
+        const uint32_t w = pack_bf16(g0, g1);
+        pk[i >> 1] = w;
+        *reinterpret_cast<uint16_t*>(h2row + sw128_off(n, kk)) = (uint16_t)w;               // GY[n][k]
+        *reinterpret_cast<uint16_t*>(h2row + sw128_off(n + 1, kk)) = (uint16_t)(w >> 16);   // GY[n+1][k]
+      }
+      const int n8 = nb + g8 * 8;
+      const uint32_t off = (uint32_t)(n8 >> 6) * kKBlockBytes + sw128_off(k, n8 & 63);
+      *reinterpret_cast<uint4*>(sm + kP2GZT + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (A) {
+        uint4 t;
+        t.x = hb[g8 * 8 + 0] | (hb[g8 * 8 + 1] << 16); t.y = hb[g8 * 8 + 2] | (hb[g8 * 8 + 3] << 16);
+        t.z = hb[g8 * 8 + 4] | (hb[g8 * 8 + 5] << 16); t.w = hb[g8 * 8 + 6] | (hb[g8 * 8 + 7] << 16);
+        *reinterpret_cast<uint4*>(sm + kP2H2T + off) = t;
+      }
+    }
+  }
+}
+
+// TMEM columns of pass 2: [0,128) D1 then D3 | [128,208) T2 (64 h1 channels + the ones column = dbeta2) |
+// [208,336) M2 | [336,464) M1
+constexpr uint32_t kTmT2 = 128, kTmM2 = 208, kTmM1 = 336;
 
 __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -231,7 +301,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
   const int q = warp & 3, hf = warp >> 2;
 
   float* xs = reinterpret_cast<float*>(sm + kP2X);          // [3][128]
-  float* par = reinterpret_cast<float*>(sm + kP2Par);        // uprime[128] | a2[128] | W1p[256]
+  float* par = reinterpret_cast<float*>(sm + kP2Par);        // uprime[128] | (unused)[128] | W1p[256]
   int* centry = reinterpret_cast<int*>(sm + kP2Ent);         // [128]
   float* coefs = reinterpret_cast<float*>(sm + kP2Ent + 512);  // [128]
 
@@ -256,43 +326,62 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
   const uint32_t tmem = *tmem_slot;
   const float4* w1p = reinterpret_cast<const float4*>(par + 256);
   const float* istd3 = p.stats + kStatIstd3(p.F);
-  constexpr uint32_t kI128 = make_idesc(128, 128), kI64 = make_idesc(128, 64);
+  constexpr uint32_t kI128 = make_idesc(128, 128), kI80 = make_idesc(128, 80);
 
   uint32_t n_ld = 0, n_mma = 0;       // completed phases of the two barriers (uniform across the CTA)
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tph = clock64();
+  auto mark = [&](int i) { if (p.debug) { const long long t = clock64(); ph[i] += t - tph; tph = t; } };
+  int ntiles_done = 0;
   bool t2_started = false, m_started = false;
-  float s_b2 = 0.f;                    // channel k = 32q+lane, this thread's column half
-  float s_b1 = 0.f, s_t0 = 0.f, s_t1 = 0.f, s_t2 = 0.f;  // channel j = 32q+lane (q < 2)
+  float s_b1 = 0.f, s_t0 = 0.f, s_t1 = 0.f, s_t2 = 0.f;  // layer-1 channel j = 32q+lane (q < 2), this thread's column half
   const int k = q * 32 + lane;
-  const float upk = par[k], a2k = par[128 + k];
+  const float upk = par[k];
+  const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+  const int ntot = p.nA + p.nB;
 
-  for (int tile = blockIdx.x; tile < p.nA + p.nB; tile += gridDim.x) {
-    const bool A = tile < p.nA;
-    int nvalid;
-    if (A) {
-      const int tl = tile % p.tiles2;
-      nvalid = p.P - tl * 128;
-      nvalid = nvalid > 128 ? 128 : nvalid;
-      if (nvalid <= 0) continue;  // a tile of pure padding
-    } else {
-      const long long e0 = (long long)(tile - p.nA) * 128;
-      nvalid = (int)(p.E - e0 < 128 ? p.E - e0 : 128);
+  auto tile_valid = [&](int tile) -> int {  // number of real rows of a tile (0: skip it)
+    if (tile < p.nA) {
+      const int nv = p.P - (tile % p.tiles2) * 128;
+      return nv > 128 ? 128 : (nv < 0 ? 0 : nv);
     }
+    const long long left = p.E - (long long)(tile - p.nA) * 128;
+    return (int)(left < 128 ? left : 128);
+  };
+  auto next_tile = [&](int tile) -> int {
+    tile += gridDim.x;
+    while (tile < ntot && tile_valid(tile) == 0) tile += gridDim.x;
+    return tile;
+  };
+  int tile = (int)blockIdx.x - (int)gridDim.x;
+  tile = next_tile(tile);
+  bool h2_prefetched = false, x_prefetched = false;
+  float px0 = 0.f, px1 = 0.f, px2 = 0.f;
+
+  while (tile < ntot) {
+    const bool A = tile < p.nA;
+    const int nvalid = tile_valid(tile);
+    const int nxt = next_tile(tile);
+    ++ntiles_done;
     // ---- load phase
     if (A) {
       const int b = tile / p.tiles2, tl = tile % p.tiles2;
-      if (tid == 0) {
+      if (tid == 0 && !h2_prefetched) {
         mbar_expect_tx(bar_ld, kTileBytes);
         const char* src = p.h2img + (size_t)tile * kTileBytes;
 #pragma unroll
         for (int c = 0; c < 4; ++c) bulk_g2s(base + kP2H2 + c * 8192u, src + c * 8192, 8192u, bar_ld);
       }
       if (tid < 128) {
-        const int n = tl * 128 + tid;
-        const float* xc = p.x + (size_t)b * 3 * p.P;
-        const bool ok = tid < nvalid;
-        xs[tid] = ok ? __ldg(xc + n) : 0.f;
-        xs[128 + tid] = ok ? __ldg(xc + p.P + n) : 0.f;
-        xs[256 + tid] = ok ? __ldg(xc + 2 * p.P + n) : 0.f;
+        if (!x_prefetched) {
+          const int n = tl * 128 + tid;
+          const float* xc = p.x + (size_t)b * 3 * p.P;
+          const bool ok = tid < nvalid;
+          px0 = ok ? __ldg(xc + n) : 0.f;
+          px1 = ok ? __ldg(xc + p.P + n) : 0.f;
+          px2 = ok ? __ldg(xc + 2 * p.P + n) : 0.f;
+        }
+        xs[tid] = px0; xs[128 + tid] = px1; xs[256 + tid] = px2;
       }
     } else {
       const int r = tid >> 1, part = tid & 1;
@@ -304,9 +393,11 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
         const int n = p.argmax[ge];
         const char* src = p.h2img + ((size_t)bb * p.tiles2 + (n >> 7)) * kTileBytes + part * kKBlockBytes;
         const int sr = n & 127;
+        uint4 row[8];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-          *reinterpret_cast<uint4*>(dst + sw128_off(r, jj * 8)) = *reinterpret_cast<const uint4*>(src + sw128_off(sr, jj * 8));
+        for (int jj = 0; jj < 8; ++jj) row[jj] = *reinterpret_cast<const uint4*>(src + sw128_off(sr, jj * 8));
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(dst + sw128_off(r, jj * 8)) = row[jj];
         if (part == 0) {
           const float* xc = p.x + (size_t)bb * 3 * p.P;
           xs[r] = __ldg(xc + n); xs[128 + r] = __ldg(xc + p.P + n); xs[256 + r] = __ldg(xc + 2 * p.P + n);
@@ -319,22 +410,30 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
         if (part == 0) { xs[r] = 0.f; xs[128 + r] = 0.f; xs[256 + r] = 0.f; centry[r] = 0; coefs[r] = 0.f; }
       }
     }
+    h2_prefetched = false;
+    x_prefetched = false;
     __syncthreads();
+    mark(0);
     // ---- h1^T operand image: rows j < 64 = relu(bn1(conv1 x)) (bf16), row 64 = 1 for real points
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int item = tid + 256 * it;
       const int j = item >> 4, ch = item & 15;
       const float4 w = w1p[j];
+      const float4 xa0 = *reinterpret_cast<const float4*>(xs + ch * 8), xb0 = *reinterpret_cast<const float4*>(xs + ch * 8 + 4);
+      const float4 xa1 = *reinterpret_cast<const float4*>(xs + 128 + ch * 8), xb1 = *reinterpret_cast<const float4*>(xs + 128 + ch * 8 + 4);
+      const float4 xa2 = *reinterpret_cast<const float4*>(xs + 256 + ch * 8), xb2 = *reinterpret_cast<const float4*>(xs + 256 + ch * 8 + 4);
+      const float x0[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xb0.x, xb0.y, xb0.z, xb0.w};
+      const float x1[8] = {xa1.x, xa1.y, xa1.z, xa1.w, xb1.x, xb1.y, xb1.z, xb1.w};
+      const float x2[8] = {xa2.x, xa2.y, xa2.z, xa2.w, xb2.x, xb2.y, xb2.z, xb2.w};
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int n = ch * 8 + i;
-        const float z = fmaf(w.x, xs[n], fmaf(w.y, xs[128 + n], fmaf(w.z, xs[256 + n], w.w)));
-        v[i] = (n < nvalid && z > 0.f) ? z : 0.f;
+        const float z = fmaf(w.x, x0[i], fmaf(w.y, x1[i], fmaf(w.z, x2[i], w.w)));
+        v[i] = (ch * 8 + i < nvalid) ? z : 0.f;
       }
       uint4 o;
-      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      o.x = pack_relu_bf16(v[0], v[1]); o.y = pack_relu_bf16(v[2], v[3]); o.z = pack_relu_bf16(v[4], v[5]); o.w = pack_relu_bf16(v[6], v[7]);
       *reinterpret_cast<uint4*>(sm + kP2H1T + (ch >> 3) * kKBlockBytes + sw128_off(j, (ch & 7) * 8)) = o;
     }
     if (tid < 16) {
@@ -350,6 +449,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mark(1);
     // ---- MMA phase 1 (stream A): D1 = Q h2^T, M1 += h1^T h1
     if (A) {
       mbar_wait(bar_ld, n_ld & 1u);
@@ -361,7 +461,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) umma_f16(tmem, dq + koff128(kk), dh2 + koff128(kk), kI128, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + 320u, dh1t + koff128(kk), dh1t + koff128(kk), kI128, (m_started || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + kTmM1, dh1t + koff128(kk), dh1t + koff128(kk), kI128, (m_started || kk > 0) ? 1u : 0u);
           umma_commit(bar_mma);
         }
         __syncwarp();
@@ -370,82 +470,33 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
       ++n_mma;
       tc_fence_after();
     }
-    // ---- epilogue 1: thread = channel k, its half of the tile's points
-    {
-      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-      const uint8_t* h2row = sm + kP2H2 + (k >> 6) * kKBlockBytes;
-      const int kk = k & 63;
-      int w3c = -1;
-      float w3v = 0.f;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int nb = 64 * hf + 32 * half;
-        uint32_t acc[32];
-        if (A) tmem_ld32(trow + (uint32_t)nb, acc);
-        // all shared-memory reads of this half first (h2 is overwritten in place below, so the compiler must not be
-        // left to interleave them with the stores)
-        uint32_t hb[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) hb[i] = *reinterpret_cast<const uint16_t*>(h2row + sw128_off(nb + i, kk));
-        float v[32];
-        if (A) {
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + upk;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int ce = centry[nb + i];
-            if (ce != w3c) { w3c = ce; w3v = __ldg(p.c3w + (size_t)ce * 128 + k); }  // warp-uniform, <= 2 per tile
-            v[i] = coefs[nb + i] * w3v;
-          }
-        }
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float gz[8];
-          uint32_t hraw[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int n = nb + g8 * 8 + i;
-            const uint32_t hbits = hb[g8 * 8 + i];
-            const bool on = (n < nvalid) && (__uint_as_float(hbits << 16) > 0.f);
-            gz[i] = on ? v[g8 * 8 + i] : 0.f;
-            hraw[i] = (n < nvalid) ? hbits : 0u;
-            s_b2 += gz[i];
-            *reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(h2row) + sw128_off(n, kk)) = __float2bfloat16_rn(a2k * gz[i]);  // GY[n][k]
-          }
-          const int n8 = nb + g8 * 8;
-          const uint32_t off = (uint32_t)(n8 >> 6) * kKBlockBytes + sw128_off(k, n8 & 63);
-          uint4 o;
-          o.x = pack_bf16(gz[0], gz[1]); o.y = pack_bf16(gz[2], gz[3]); o.z = pack_bf16(gz[4], gz[5]); o.w = pack_bf16(gz[6], gz[7]);
-          *reinterpret_cast<uint4*>(sm + kP2GZT + off) = o;
-          if (A) {
-            uint4 t;
-            t.x = hraw[0] | (hraw[1] << 16); t.y = hraw[2] | (hraw[3] << 16);
-            t.z = hraw[4] | (hraw[5] << 16); t.w = hraw[6] | (hraw[7] << 16);
-            *reinterpret_cast<uint4*>(sm + kP2H2T + off) = t;
-          }
-        }
-      }
+    mark(2);
+    // ---- epilogue 1
+    if (A) {
+      if (nvalid == 128) pass2_epilogue1<true, true>(sm, trow, k, hf, upk, nvalid, centry, coefs, p.c3w);
+      else pass2_epilogue1<true, false>(sm, trow, k, hf, upk, nvalid, centry, coefs, p.c3w);
+    } else {
+      pass2_epilogue1<false, true>(sm, trow, k, hf, upk, nvalid, centry, coefs, p.c3w);  // padding rows are zero rows
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // ---- MMA phase 2: T2 += gz2^T h1 ; (A) M2 += h2^T h2 ; D3 = W2^T (a2 gz2)^T
+    mark(3);
+    // ---- MMA phase 2: T2 += gz2^T [h1 | 1] ; (A) M2 += h2^T h2 ; D3 = (a2 W2)^T gz2^T
     if (warp == 0) {
       if (elect_one()) {
         const uint64_t dgzt = umma_desc_sw128(base + kP2GZT), dh1t = umma_desc_sw128(base + kP2H1T);
         const uint64_t dh2t = umma_desc_sw128(base + kP2H2T), dw2t = umma_desc_sw128(base + kP2W2T);
         const uint64_t dgy = umma_desc_sw128(base + kP2H2);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + 128u, dgzt + koff128(kk), dh1t + koff128(kk), kI64, (t2_started || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tmem, dw2t + koff128(kk), dgy + koff128(kk), kI128, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + kTmT2, dgzt + koff128(kk), dh1t + koff128(kk), kI80, (t2_started || kk > 0) ? 1u : 0u);
         if (A) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + 192u, dh2t + koff128(kk), dh2t + koff128(kk), kI128, (m_started || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + kTmM2, dh2t + koff128(kk), dh2t + koff128(kk), kI128, (m_started || kk > 0) ? 1u : 0u);
         }
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_f16(tmem, dw2t + koff128(kk), dgy + koff128(kk), kI128, kk > 0);
         umma_commit(bar_mma);
       }
       __syncwarp();
@@ -455,11 +506,30 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
     mbar_wait(bar_mma, n_mma & 1u);
     ++n_mma;
     tc_fence_after();
+    mark(4);
+    // the h2 buffer is free again: start the next real tile's loads now, under epilogue 3
+    if (nxt < p.nA) {
+      if (tid == 0) {
+        mbar_expect_tx(bar_ld, kTileBytes);
+        const char* src = p.h2img + (size_t)nxt * kTileBytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bulk_g2s(base + kP2H2 + c * 8192u, src + c * 8192, 8192u, bar_ld);
+      }
+      h2_prefetched = true;
+      x_prefetched = true;
+      if (tid < 128) {
+        const int b = nxt / p.tiles2, tl = nxt % p.tiles2;
+        const int n = tl * 128 + tid;
+        const float* xc = p.x + (size_t)b * 3 * p.P;
+        const bool ok = tid < tile_valid(nxt);
+        px0 = ok ? __ldg(xc + n) : 0.f;
+        px1 = ok ? __ldg(xc + p.P + n) : 0.f;
+        px2 = ok ? __ldg(xc + 2 * p.P + n) : 0.f;
+      }
+    }
     // ---- epilogue 3: thread = layer-1 channel j < 64, its half of the points
     if (q < 2) {
-      const int j = k;
-      const float4 w = w1p[j];
-      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+      const float4 w = w1p[k];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int nb = 64 * hf + 32 * half;
@@ -467,40 +537,55 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
         tmem_ld32(trow + (uint32_t)nb, acc);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int n = nb + i;
-          const float x0 = xs[n], x1 = xs[128 + n], x2 = xs[256 + n];
-          const float z = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
-          const float gz1 = (n < nvalid && z > 0.f) ? __uint_as_float(acc[i]) : 0.f;
-          s_b1 += gz1;
-          s_t0 = fmaf(gz1, x0, s_t0); s_t1 = fmaf(gz1, x1, s_t1); s_t2 = fmaf(gz1, x2, s_t2);
+        for (int i4 = 0; i4 < 32; i4 += 4) {
+          const float4 a0 = *reinterpret_cast<const float4*>(xs + nb + i4);
+          const float4 a1 = *reinterpret_cast<const float4*>(xs + 128 + nb + i4);
+          const float4 a2 = *reinterpret_cast<const float4*>(xs + 256 + nb + i4);
+          const float x0[4] = {a0.x, a0.y, a0.z, a0.w}, x1[4] = {a1.x, a1.y, a1.z, a1.w}, x2[4] = {a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float z = fmaf(w.x, x0[i], fmaf(w.y, x1[i], fmaf(w.z, x2[i], w.w)));
+            // padding rows carry gz2 = 0, so D3 is already 0 there
+            const float gz1 = z > 0.f ? __uint_as_float(acc[i4 + i]) : 0.f;
+            s_b1 += gz1;
+            s_t0 = fmaf(gz1, x0[i], s_t0); s_t1 = fmaf(gz1, x1[i], s_t1); s_t2 = fmaf(gz1, x2[i], s_t2);
+          }
         }
       }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mark(5);
+    tile = nxt;
   }
 
+  if (p.debug && blockIdx.x == 0 && (tid == 0 || tid == 255))
+    printf("pass2 cta0 t%d tiles %d cycles: load %lld h1t %lld mma1 %lld e1 %lld mma2 %lld e3+sync %lld\n", tid, ntiles_done,
+           ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]);
   // ---- flush: per-CTA partials of the three persistent accumulators, per-thread channel sums
   {
     float* part = p.part + (size_t)blockIdx.x * kPartFloats;
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t r[32];
-    if (t2_started) { tmem_ld32(trow + 128u + 32u * hf, r); tmem_ld_wait(); }
+    if (t2_started) { tmem_ld32(trow + kTmT2 + 32u * hf, r); tmem_ld_wait(); }
 #pragma unroll
     for (int i = 0; i < 32; ++i) part[kPartT2 + k * 64 + 32 * hf + i] = t2_started ? __uint_as_float(r[i]) : 0.f;
+    if (t2_started && hf == 0) {   // column 64 of the T2 accumulator: gz2^T 1 = dbeta2
+      uint32_t d;
+      tmem_ld1(trow + kTmT2 + 64u, d);
+      tmem_ld_wait();
+      atomicAdd(p.acc2 + k, (double)__uint_as_float(d));
+    }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int cb = 64 * hf + 32 * half;
-      if (m_started) { tmem_ld32(trow + 192u + (uint32_t)cb, r); tmem_ld_wait(); }
+      if (m_started) { tmem_ld32(trow + kTmM2 + (uint32_t)cb, r); tmem_ld_wait(); }
 #pragma unroll
       for (int i = 0; i < 32; ++i) part[kPartM2 + k * 128 + cb + i] = m_started ? __uint_as_float(r[i]) : 0.f;
-      if (m_started) { tmem_ld32(trow + 320u + (uint32_t)cb, r); tmem_ld_wait(); }
+      if (m_started) { tmem_ld32(trow + kTmM1 + (uint32_t)cb, r); tmem_ld_wait(); }
 #pragma unroll
       for (int i = 0; i < 32; ++i) part[kPartM1 + k * 128 + cb + i] = m_started ? __uint_as_float(r[i]) : 0.f;
     }
-    atomicAdd(p.acc2 + k, (double)s_b2);
     if (q < 2) {
       atomicAdd(p.acc1 + k, (double)s_b1);
       atomicAdd(p.acc1 + 128 + k * 3 + 0, (double)s_t0);
@@ -642,30 +727,50 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass3_kernel(const Pass3Params 
   float s_b1 = 0.f, s_t0 = 0.f, s_t1 = 0.f, s_t2 = 0.f;
   const int j = q * 32 + lane;
 
-  for (int tile = blockIdx.x; tile < p.nA; tile += gridDim.x) {
+  auto tile_valid = [&](int tile) -> int {
+    const int nv = p.P - (tile % p.tiles2) * 128;
+    return nv > 128 ? 128 : (nv < 0 ? 0 : nv);
+  };
+  auto next_tile = [&](int tile) -> int {
+    tile += gridDim.x;
+    while (tile < p.nA && tile_valid(tile) == 0) tile += gridDim.x;
+    return tile;
+  };
+  const int row = tid & 127, cgh = tid >> 7;   // h1 image: every thread builds half of one point's 64 channels
+  auto load_x = [&](int tile, float& x0, float& x1, float& x2) {
     const int b = tile / p.tiles2, tl = tile % p.tiles2;
-    int nvalid = p.P - tl * 128;
-    nvalid = nvalid > 128 ? 128 : nvalid;
-    if (nvalid <= 0) continue;
-    if (tid < 128) {
-      const int n = tl * 128 + tid;
-      const float* xc = p.x + (size_t)b * 3 * p.P;
-      const bool ok = tid < nvalid;
-      const float x0 = ok ? __ldg(xc + n) : 0.f, x1 = ok ? __ldg(xc + p.P + n) : 0.f, x2 = ok ? __ldg(xc + 2 * p.P + n) : 0.f;
-      xs[tid] = x0; xs[128 + tid] = x1; xs[256 + tid] = x2;
+    const int n = tl * 128 + row;
+    const float* xc = p.x + (size_t)b * 3 * p.P;
+    const bool ok = row < tile_valid(tile);
+    x0 = ok ? __ldg(xc + n) : 0.f;
+    x1 = ok ? __ldg(xc + p.P + n) : 0.f;
+    x2 = ok ? __ldg(xc + 2 * p.P + n) : 0.f;
+  };
+  int tile = next_tile((int)blockIdx.x - (int)gridDim.x);
+  float px0 = 0.f, px1 = 0.f, px2 = 0.f;
+  if (tile < p.nA) load_x(tile, px0, px1, px2);
+
+  while (tile < p.nA) {
+    const int nvalid = tile_valid(tile);
+    const int nxt = next_tile(tile);
+    {
+      const float x0 = px0, x1 = px1, x2 = px2;
+      if (cgh == 0) { xs[row] = x0; xs[128 + row] = x1; xs[256 + row] = x2; }
+      const bool ok = row < nvalid;
       // h1 operand image [n][i] (K-major over the 64 layer-1 channels), zero rows for padding
 #pragma unroll
-      for (int cg = 0; cg < 8; ++cg) {
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int cg = cgh * 4 + c4;
         float v[8];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const float4 w = w1p[cg * 8 + jj];
           const float z = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
-          v[jj] = (ok && z > 0.f) ? z : 0.f;
+          v[jj] = ok ? z : 0.f;
         }
         uint4 o;
-        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-        *reinterpret_cast<uint4*>(sm + kP3H1 + sw128_off(tid, cg * 8)) = o;
+        o.x = pack_relu_bf16(v[0], v[1]); o.y = pack_relu_bf16(v[2], v[3]); o.z = pack_relu_bf16(v[4], v[5]); o.w = pack_relu_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(sm + kP3H1 + sw128_off(row, cg * 8)) = o;
       }
     }
     fence_proxy_async();
@@ -681,6 +786,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass3_kernel(const Pass3Params 
       }
       __syncwarp();
     }
+    if (nxt < p.nA) load_x(nxt, px0, px1, px2);   // in flight under the MMA and the epilogue
     mbar_wait(bar_mma, n_mma & 1u);
     ++n_mma;
     tc_fence_after();
@@ -695,19 +801,25 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass3_kernel(const Pass3Params 
         tmem_ld32(trow + (uint32_t)nb, acc);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int n = nb + i;
-          const float x0 = xs[n], x1 = xs[128 + n], x2 = xs[256 + n];
-          const float z = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
-          const float gz1 = (n < nvalid && z > 0.f) ? __uint_as_float(acc[i]) + u1 : 0.f;
-          s_b1 += gz1;
-          s_t0 = fmaf(gz1, x0, s_t0); s_t1 = fmaf(gz1, x1, s_t1); s_t2 = fmaf(gz1, x2, s_t2);
+        for (int i4 = 0; i4 < 32; i4 += 4) {
+          const float4 a0 = *reinterpret_cast<const float4*>(xs + nb + i4);
+          const float4 a1 = *reinterpret_cast<const float4*>(xs + 128 + nb + i4);
+          const float4 a2 = *reinterpret_cast<const float4*>(xs + 256 + nb + i4);
+          const float x0[4] = {a0.x, a0.y, a0.z, a0.w}, x1[4] = {a1.x, a1.y, a1.z, a1.w}, x2[4] = {a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float z = fmaf(w.x, x0[i], fmaf(w.y, x1[i], fmaf(w.z, x2[i], w.w)));
+            const float gz1 = (nb + i4 + i < nvalid && z > 0.f) ? __uint_as_float(acc[i4 + i]) + u1 : 0.f;
+            s_b1 += gz1;
+            s_t0 = fmaf(gz1, x0[i], s_t0); s_t1 = fmaf(gz1, x1[i], s_t1); s_t2 = fmaf(gz1, x2[i], s_t2);
+          }
         }
       }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    tile = nxt;
   }
   if (q < 2) {
     atomicAdd(p.acc1 + j, (double)s_b1);
@@ -884,6 +996,7 @@ extern "C" int crdpn_pointnet_backward(
   p2.h2img = h2img; p2.argmax = argmax; p2.g = grad_out; p2.c3w = conv3_w; p2.g3 = bn3_w; p2.stats = stats;
   p2.train_par = train_par; p2.qimg = w + W.qimg; p2.w2timg = w + W.w2timg; p2.vec = vec;
   p2.acc2 = acc2; p2.acc1 = acc1; p2.part = (float*)(w + W.part);
+  p2.debug = getenv("CRDPN_PN_DEBUG") ? 1 : 0;
   pn::pn_bwd_pass2_kernel<<<grid, 256, pn::kP2Smem, st>>>(p2);
   CRDPN_LAUNCH_CHECK("pn_bwd_pass2_kernel");
   pn::pn_bwd_reduce_partials_kernel<<<(pn::kPartFloats + 255) / 256, 256, 0, st>>>((const float*)(w + W.part), grid, red);
