@@ -402,8 +402,15 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
       double s = 0.0;
       for (int a = 0; a < f.B; ++a) s += __ldcg(&f.anchor_part[a * 8 + threadIdx.x]);
       f.result[threadIdx.x] = (threadIdx.x < 2) ? (f.full ? -s / (double)f.B : 0.0) : s;
-    } else if (threadIdx.x < 8) {
-      f.result[threadIdx.x] = 0.0;
+    } else if (threadIdx.x == 5) {  // total loss, also as float32 (slot 6) so the caller needs no cast kernel
+      double s0 = 0.0, s1 = 0.0;
+      for (int a = 0; a < f.B; ++a) { s0 += __ldcg(&f.anchor_part[a * 8]); s1 += __ldcg(&f.anchor_part[a * 8 + 1]); }
+      const double tot = f.full ? (-s0 / (double)f.B) + (-s1 / (double)f.B) : 0.0;
+      f.result[5] = tot;
+      f.result[6] = 0.0;
+      reinterpret_cast<float*>(&f.result[6])[0] = (float)tot;
+    } else if (threadIdx.x == 7) {
+      f.result[7] = 0.0;
     }
   }
 }

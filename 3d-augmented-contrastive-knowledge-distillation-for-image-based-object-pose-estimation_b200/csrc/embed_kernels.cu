@@ -1,0 +1,156 @@
+// embed_kernels.cu -- the CRD embed heads (published `Embed`: flatten -> Linear(dim_in, D) -> x / ||x||_2),
+// forward and backward, as a handful of small kernels instead of the ~25 library / elementwise launches the eager
+// module costs per step (B = 46 rows: the work is launch-bound, not FLOP-bound).
+//   forward : pre = x W^T + b (warp per output, float4 loads);  v = pre / ||pre||_2, 1/norm kept for backward
+//   backward: d_pre = (g - v (g . v)) / norm;  dW = d_pre^T x;  db = sum_b d_pre;  dx = d_pre W (optional)
+#include "common.cuh"
+
+namespace crdpn {
+namespace embed {
+
+// grid (ceil(D/8), B), 256 threads: warp w of block (bx, b) computes output d = 8 bx + w of row b
+__global__ void __launch_bounds__(256) embed_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, int B, int dim_in, int D,
+                                                           float* __restrict__ pre) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = blockIdx.x * 8 + warp;
+  if (d >= D) return;
+  const float* wr = W + (size_t)d * dim_in;
+  const int b0 = blockIdx.y, b1 = min(b0 + 1, B);
+  const bool vec = (dim_in & 3) == 0;
+  for (int b = b0; b < b1; ++b) {
+    const float* xr = x + (size_t)b * dim_in;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (vec) {
+      for (int i = lane * 4; i < dim_in; i += 128) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + i));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + i));
+        a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
+      }
+    } else {
+      for (int i = lane; i < dim_in; i += 32) a0 = fmaf(__ldg(xr + i), __ldg(wr + i), a0);
+    }
+    float s = (a0 + a1) + (a2 + a3);
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) pre[(size_t)b * D + d] = s + bias[d];
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < nw; ++w) s += red[w];
+  return s;
+}
+
+// grid B, 256 threads: v = pre / ||pre||
+__global__ void __launch_bounds__(256) embed_normalize_kernel(const float* __restrict__ pre, int D, float* __restrict__ v,
+                                                              float* __restrict__ inv_norm) {
+  __shared__ float red[8];
+  const float* pr = pre + (size_t)blockIdx.x * D;
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) ss = fmaf(pr[d], pr[d], ss);
+  ss = block_sum(ss, red);
+  const float norm = sqrtf(ss);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) v[(size_t)blockIdx.x * D + d] = pr[d] / norm;
+  if (threadIdx.x == 0) inv_norm[blockIdx.x] = 1.0f / norm;
+}
+
+// grid B, 256 threads: d_pre = scale * (g - v (g . v)) / norm   (scale: optional device scalar, the upstream gradient)
+__global__ void __launch_bounds__(256) embed_bwd_prep_kernel(const float* __restrict__ g, const float* __restrict__ v,
+                                                             const float* __restrict__ inv_norm, const float* __restrict__ scale,
+                                                             int D, float* __restrict__ d_pre) {
+  __shared__ float red[8];
+  const size_t o = (size_t)blockIdx.x * D;
+  float dot = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) dot = fmaf(g[o + d], v[o + d], dot);
+  dot = block_sum(dot, red);
+  const float inv = inv_norm[blockIdx.x] * (scale ? *scale : 1.0f);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) d_pre[o + d] = (g[o + d] - v[o + d] * dot) * inv;
+}
+
+// grid (D, ceil(dim_in/256)), 256 threads: dW[d][i] = sum_b d_pre[b][d] x[b][i];  db[d] = sum_b d_pre[b][d]
+__global__ void __launch_bounds__(256) embed_bwd_wgrad_kernel(const float* __restrict__ d_pre, const float* __restrict__ x,
+                                                              int B, int dim_in, int D, float* __restrict__ dW, float* __restrict__ db) {
+  const int d = blockIdx.x, i = blockIdx.y * 256 + threadIdx.x;
+  if (i < dim_in) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = 0;
+    for (; b + 3 < B; b += 4) {
+      a0 = fmaf(__ldg(d_pre + (size_t)b * D + d), __ldg(x + (size_t)b * dim_in + i), a0);
+      a1 = fmaf(__ldg(d_pre + (size_t)(b + 1) * D + d), __ldg(x + (size_t)(b + 1) * dim_in + i), a1);
+      a2 = fmaf(__ldg(d_pre + (size_t)(b + 2) * D + d), __ldg(x + (size_t)(b + 2) * dim_in + i), a2);
+      a3 = fmaf(__ldg(d_pre + (size_t)(b + 3) * D + d), __ldg(x + (size_t)(b + 3) * dim_in + i), a3);
+    }
+    for (; b < B; ++b) a0 = fmaf(__ldg(d_pre + (size_t)b * D + d), __ldg(x + (size_t)b * dim_in + i), a0);
+    a0 += a2; a1 += a3;
+    dW[(size_t)d * dim_in + i] = a0 + a1;
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += d_pre[(size_t)b * D + d];
+    db[d] = s;
+  }
+}
+
+// grid (B, ceil(dim_in/256)), 256 threads: dx[b][i] = sum_d d_pre[b][d] W[d][i]
+__global__ void __launch_bounds__(256) embed_bwd_dgrad_kernel(const float* __restrict__ d_pre, const float* __restrict__ W,
+                                                              int dim_in, int D, float* __restrict__ dx) {
+  const int b = blockIdx.x, i = blockIdx.y * 256 + threadIdx.x;
+  if (i >= dim_in) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int d = 0;
+#pragma unroll 2
+  for (; d + 3 < D; d += 4) {
+    a0 = fmaf(__ldg(d_pre + (size_t)b * D + d), __ldg(W + (size_t)d * dim_in + i), a0);
+    a1 = fmaf(__ldg(d_pre + (size_t)b * D + d + 1), __ldg(W + (size_t)(d + 1) * dim_in + i), a1);
+    a2 = fmaf(__ldg(d_pre + (size_t)b * D + d + 2), __ldg(W + (size_t)(d + 2) * dim_in + i), a2);
+    a3 = fmaf(__ldg(d_pre + (size_t)b * D + d + 3), __ldg(W + (size_t)(d + 3) * dim_in + i), a3);
+  }
+  for (; d < D; ++d) a0 = fmaf(__ldg(d_pre + (size_t)b * D + d), __ldg(W + (size_t)d * dim_in + i), a0);
+  a0 += a2; a1 += a3;
+  dx[(size_t)b * dim_in + i] = a0 + a1;
+}
+
+}  // namespace embed
+}  // namespace crdpn
+
+using namespace crdpn;
+
+extern "C" int crdpn_embed_forward(const float* x, const float* W, const float* b, int64_t B, int64_t dim_in, int64_t D,
+                                   float* pre, float* v, float* inv_norm, void* stream) {
+  if (!x || !W || !b || !pre || !v || !inv_norm) return fail(CRDPN_E_BADARG, "crdpn_embed_forward: null pointer");
+  if (B <= 0 || dim_in <= 0 || D <= 0 || B > 65535 || dim_in >= (1ll << 31) || D >= (1ll << 24))
+    return fail(CRDPN_E_BADARG, "crdpn_embed_forward: bad size");
+  if ((dim_in & 3) == 0 && (((uintptr_t)x | (uintptr_t)W) & 15)) return fail(CRDPN_E_ALIGN, "crdpn_embed_forward: x / W must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((D + 7) / 8), (unsigned)B);
+  embed::embed_linear_kernel<<<grid, 256, 0, st>>>(x, W, b, (int)B, (int)dim_in, (int)D, pre);
+  CRDPN_LAUNCH_CHECK("embed_linear_kernel");
+  embed::embed_normalize_kernel<<<(unsigned)B, 256, 0, st>>>(pre, (int)D, v, inv_norm);
+  CRDPN_LAUNCH_CHECK("embed_normalize_kernel");
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_embed_backward(const float* x, const float* W, const float* v, const float* inv_norm,
+                                    const float* grad_v, const float* scale, int64_t B, int64_t dim_in, int64_t D,
+                                    float* dW, float* db, float* dx, float* d_pre, void* stream) {
+  if (!x || !W || !v || !inv_norm || !grad_v || !dW || !db || !d_pre) return fail(CRDPN_E_BADARG, "crdpn_embed_backward: null pointer");
+  if (B <= 0 || dim_in <= 0 || D <= 0 || B > 65535 || D > 65535 * 1 || dim_in >= (1ll << 31))
+    return fail(CRDPN_E_BADARG, "crdpn_embed_backward: bad size");
+  cudaStream_t st = (cudaStream_t)stream;
+  embed::embed_bwd_prep_kernel<<<(unsigned)B, 256, 0, st>>>(grad_v, v, inv_norm, scale, (int)D, d_pre);
+  CRDPN_LAUNCH_CHECK("embed_bwd_prep_kernel");
+  const unsigned tiles = (unsigned)((dim_in + 255) / 256);
+  embed::embed_bwd_wgrad_kernel<<<dim3((unsigned)D, tiles), 256, 0, st>>>(d_pre, x, (int)B, (int)dim_in, (int)D, dW, db);
+  CRDPN_LAUNCH_CHECK("embed_bwd_wgrad_kernel");
+  if (dx) {
+    embed::embed_bwd_dgrad_kernel<<<dim3((unsigned)B, tiles), 256, 0, st>>>(d_pre, W, (int)dim_in, (int)D, dx);
+    CRDPN_LAUNCH_CHECK("embed_bwd_dgrad_kernel");
+  }
+  return CRDPN_OK;
+}

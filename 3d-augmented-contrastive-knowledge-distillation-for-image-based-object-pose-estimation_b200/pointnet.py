@@ -70,7 +70,7 @@ class ShapeEncoderPC(nn.Module):
             if self._packed is None or self._packed.numel() != n.value or self._packed.device != device:
                 self._packed = torch.empty(n.value, dtype=torch.uint8, device=device)
             ptrs = [t.detach().contiguous().data_ptr() for t in src]
-            with torch.cuda.device(device):
+            with _native.on_device(device):
                 rc = _native.lib().crdpn_pointnet_pack(*ptrs, BN_EPS, self.feature_dim, self._packed.data_ptr(),
                                                        torch.cuda.current_stream(device).cuda_stream)
             _native.check(rc, "crdpn_pointnet_pack")
@@ -92,7 +92,7 @@ class ShapeEncoderPC(nn.Module):
         if self._ws is None or self._ws.numel() < n.value or self._ws.device != dev:
             self._ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
         out = torch.empty(B, self.feature_dim, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _native.on_device(dev):
             rc = _native.lib().crdpn_pointnet_forward_eval(x.data_ptr(), B, P, self.feature_dim, packed.data_ptr(),
                                                            out.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                                            self.variant, torch.cuda.current_stream(dev).cuda_stream)
@@ -157,7 +157,7 @@ class _PointNetTrainFunction(torch.autograd.Function):
         for i, bn in enumerate(bns):
             args += [p[6 + 2 * i].data_ptr(), p[7 + 2 * i].data_ptr(), bn.running_mean.data_ptr(),
                      bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr()]
-        with torch.cuda.device(dev):
+        with _native.on_device(dev):
             rc = lib.crdpn_pointnet_forward_train(*args, float(module.bn1.eps), float(module.bn1.momentum),
                                                   out.data_ptr(), cptr, n.value, module.variant,
                                                   torch.cuda.current_stream(dev).cuda_stream)
@@ -181,7 +181,7 @@ class _PointNetTrainFunction(torch.autograd.Function):
         ws_owner, wptr = _aligned(n.value, dev)
         grads = [torch.empty_like(t) for t in p]
         c1w, c1b, c2w, c2b, c3w, c3b, g1, b1, g2, b2, g3, b3 = p
-        with torch.cuda.device(dev):
+        with _native.on_device(dev):
             rc = lib.crdpn_pointnet_backward(
                 x.data_ptr(), B, P, F, c1w.data_ptr(), c2w.data_ptr(), c3w.data_ptr(),
                 g1.data_ptr(), b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), g3.data_ptr(), b3.data_ptr(),

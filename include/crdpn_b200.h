@@ -70,6 +70,21 @@ int crdpn_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t n
                               void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Embed heads: flatten -> Linear(dim_in, D) -> x / ||x||_2  (published CRD `Embed` + `Normalize`, crd/criterion.py;
+ * the reference's own heads are the `projector` MLPs, auxiliary/model.py:41-42, 238-241, whose 200-d output is what
+ * these heads consume at KD/common/base_class.py:359,363).  x [B,dim_in], W [D,dim_in], b [D] f32.
+ * forward : pre [B,D] = x W^T + b;  v [B,D] = pre / ||pre||_2 (no epsilon);  inv_norm [B] = 1 / ||pre||_2.
+ * backward: given grad_v [B,D] and an optional device scalar `scale` (the upstream gradient of the loss; NULL = 1):
+ *           dW [D,dim_in], db [D], dx [B,dim_in] (dx may be NULL: the teacher side needs none);
+ *           d_pre [B,D] is caller-provided scratch.
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_embed_forward(const float* x, const float* W, const float* b, int64_t B, int64_t dim_in, int64_t D,
+                        float* pre, float* v, float* inv_norm, void* stream);
+int crdpn_embed_backward(const float* x, const float* W, const float* v, const float* inv_norm, const float* grad_v,
+                         const float* scale, int64_t B, int64_t dim_in, int64_t D, float* dW, float* db, float* dx,
+                         float* d_pre, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * CRD scoring: fused gather . dot . exp . NCE loss . closed-form backward.  Never materialises the
  * B x K1 x D gathered tensor.
  * Replaces: ContrastMemory.forward (index_select + bmm + exp + div) and ContrastLoss.forward of the
@@ -85,7 +100,8 @@ int crdpn_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t n
  * v1,v2 [B,D] f32; contrast_idx [B,K1] int64 (column 0 = positive).  k_total = number of negatives per anchor
  * over ALL shards (the K of the NCE constant K*Pn); pass 0 for "K1-1" (single shard, or a replicated index list).
  * out_v1/out_v2: optional [B,K1] f32 (o, or raw e in sum mode; 0 for entries outside the shard).
- * result: 8 doubles {loss_s, loss_t, sum_e1, sum_e2, count, 0,0,0}.  grad_v1/grad_v2 [B,D] f32 (written
+ * result: 8 doubles {loss_s, loss_t, sum_e1, sum_e2, count, loss_s+loss_t, [float32 (loss_s+loss_t) in the first
+ * 4 bytes of slot 6], 0}.  grad_v1/grad_v2 [B,D] f32 (written
  * only in full mode).  variant: 0 = default kernel; other values select tuning variants (bench only).
  * ------------------------------------------------------------------------------------------------- */
 int crdpn_crd_workspace_bytes(int64_t B, int64_t K1, int64_t D, int device, size_t* bytes);

@@ -363,3 +363,29 @@ def test_fused_step_equals_score_then_update_bitwise(pkg, cuda):
     assert torch.equal(res_a, res_b) and torch.equal(g1a, g1b) and torch.equal(g2a, g2b)
     assert torch.equal(a.memory_v1, b.memory_v1) and torch.equal(a.memory_v2, b.memory_v2)
     assert not torch.equal(a.memory_v1[y[0]], torch.zeros(128, device=cuda))
+
+
+@pytest.mark.parametrize("B,dim_in,D", [(46, 2048, 128), (46, 200, 128), (138, 1024, 128), (5, 37, 32), (64, 513, 256)])
+def test_fused_embed_head_matches_eager_linear_l2norm(pkg, cuda, B, dim_in, D):
+    """Embed = Linear + x/||x||_2 (published crd/criterion.py Embed/Normalize): fused kernels vs the eager
+    sub-modules of the same module, forward and all three gradients, <= 1e-4 relative (fp32)."""
+    torch.manual_seed(B + dim_in)
+    emb = pkg.Embed(dim_in, D).to(cuda)
+    x = torch.randn(B, dim_in, device=cuda)
+    g = torch.randn(B, D, device=cuda)
+    xa = x.clone().requires_grad_()
+    va = emb(xa)                                                  # fused path
+    va.backward(g)
+    got = (va.detach(), xa.grad.clone(), emb.linear.weight.grad.clone(), emb.linear.bias.grad.clone())
+    emb.zero_grad()
+    xb = x.clone().requires_grad_()
+    vb = emb.l2norm(emb.linear(xb))                               # eager sub-modules
+    vb.backward(g)
+    want = (vb.detach(), xb.grad, emb.linear.weight.grad, emb.linear.bias.grad)
+    for a, b in zip(got, want):
+        assert ((a - b).abs().max() / b.abs().max()).item() < 1e-4
+    assert torch.allclose(va.detach().norm(dim=1), torch.ones(B, device=cuda), atol=1e-5)
+    # no input gradient requested -> the dgrad kernel is skipped and autograd still gets the parameter gradients
+    emb.zero_grad()
+    emb(x).backward(g)
+    assert ((emb.linear.weight.grad - want[2]).abs().max() / want[2].abs().max()).item() < 1e-4
