@@ -46,6 +46,16 @@ _SIGNATURES = {
                                     c_void_p, c_void_p]),
     "crdpn_embed_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "crdpn_p2p_buffer_bytes": (c_int, [c_int64, c_int64, c_int, POINTER(c_size_t)]),
+    "crdpn_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "crdpn_p2p_free": (c_int, [c_void_p]),
+    "crdpn_p2p_export": (c_int, [c_void_p, c_void_p]),
+    "crdpn_p2p_import": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "crdpn_p2p_close": (c_int, [c_void_p]),
+    "crdpn_p2p_allgather_anchors": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
+                                            c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "crdpn_p2p_allreduce_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64,
+                                        c_void_p]),
     "crdpn_pointnet_train_ctx_bytes": (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t)]),
     "crdpn_pointnet_forward_train": (c_int, [c_void_p, c_int64, c_int64, c_int64] + [c_void_p] * 21 +
                                      [c_float, c_float, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

@@ -24,7 +24,10 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from .crd import ContrastMemory, Embed, _FusedCRDFunction
+import ctypes
+
+from . import _native
+from .crd import ContrastMemory, Embed, _FusedCRDFunction, _stream_ptr
 
 
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
@@ -70,11 +73,93 @@ class _GatherAnchors(torch.autograd.Function):
         return d1[lo:lo + ctx.b_loc].contiguous(), d2[lo:lo + ctx.b_loc].contiguous(), None, None
 
 
+class PeerExchange:
+    """NVLink peer-memory exchange buffers for one group of ranks on one box (CUDA IPC; ``crdpn_p2p_*``).
+
+    Setup is collective: every rank allocates its buffer, the 64-byte IPC handles travel through
+    ``dist.all_gather_object``, every rank maps its peers' buffers.  ``allgather`` / ``allreduce`` then are single
+    kernel launches on the current stream (no NCCL call, CUDA-graph capturable)."""
+
+    def __init__(self, group, rank, world, device, Bmax, Dmax):
+        lib = _native.lib()
+        self.rank, self.world, self.device, self.Bmax, self.Dmax = rank, world, device, int(Bmax), int(Dmax)
+        n = ctypes.c_size_t(0)
+        _native.check(lib.crdpn_p2p_buffer_bytes(self.Bmax, self.Dmax, world, ctypes.byref(n)), "crdpn_p2p_buffer_bytes")
+        own = ctypes.c_void_p()
+        with _native.on_device(device):
+            _native.check(lib.crdpn_p2p_alloc(n.value, ctypes.byref(own)), "crdpn_p2p_alloc")
+            handle = ctypes.create_string_buffer(64)
+            _native.check(lib.crdpn_p2p_export(own, handle), "crdpn_p2p_export")
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self._own = own
+            self._imported = []
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(own.value)
+                    continue
+                peer = ctypes.c_void_p()
+                _native.check(lib.crdpn_p2p_import(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(peer)),
+                              "crdpn_p2p_import")
+                self._imported.append(peer)
+                ptrs.append(peer.value)
+        self._ptrs = (ctypes.c_void_p * world)(*ptrs)
+        dist.barrier(group=group)  # nobody starts writing before every mapping exists
+
+    def allgather(self, v1, v2, y, counts):
+        B, D = sum(counts), v1.shape[1]
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        out1 = torch.empty(B, D, dtype=torch.float32, device=v1.device)
+        out2 = torch.empty(B, D, dtype=torch.float32, device=v1.device)
+        outy = torch.empty(B, dtype=torch.int64, device=v1.device)
+        offs_c = (ctypes.c_int32 * (self.world + 1))(*offs)
+        with _native.on_device(v1.device):
+            rc = _native.lib().crdpn_p2p_allgather_anchors(
+                v1.data_ptr(), v2.data_ptr(), y.data_ptr(), D, offs_c, self._ptrs, self.rank, self.world,
+                self.Bmax, self.Dmax, out1.data_ptr(), out2.data_ptr(), outy.data_ptr(), _stream_ptr(v1.device))
+        _native.check(rc, "crdpn_p2p_allgather_anchors")
+        return out1, out2, outy
+
+    def allreduce(self, partial, tail_f64=None):
+        """Sum of `partial` (fp32) over the ranks, in rank order; `tail_f64` (optional fp64 vector) rides behind it
+        as fp32 words, so the step's result scalars need no separate cast / copy kernel."""
+        n_tail = 0 if tail_f64 is None else tail_f64.numel()
+        out = torch.empty(partial.numel() + n_tail, dtype=torch.float32, device=partial.device)
+        with _native.on_device(partial.device):
+            rc = _native.lib().crdpn_p2p_allreduce_f32(partial.data_ptr(), partial.numel(),
+                                                       tail_f64.data_ptr() if n_tail else None, n_tail,
+                                                       out.data_ptr(), self._ptrs,
+                                                       self.rank, self.world, self.Bmax, self.Dmax,
+                                                       _stream_ptr(partial.device))
+        _native.check(rc, "crdpn_p2p_allreduce_f32")
+        return out
+
+    def close(self):
+        lib = _native.lib()
+        if getattr(self, "_own", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with _native.on_device(self.device):
+            for peer in self._imported:
+                lib.crdpn_p2p_close(peer)
+            lib.crdpn_p2p_free(self._own)
+        self._own, self._imported = None, []
+
+
 class ShardedContrastMemory(ContrastMemory):
     """ContrastMemory holding rows [row_begin,row_end) of the global banks; collectives on ``group``."""
 
     def __init__(self, inputSize, outputSize, K, T=0.07, momentum=0.5, group=None, rank=None, world_size=None,
-                 local_negatives=False, **kw):
+                 local_negatives=False, comm="dist", **kw):
+        """comm: "dist" = torch.distributed collectives (NCCL on GPUs, gloo in the CPU tests);
+        "p2p" = the two per-step exchanges as single kernels over NVLink peer memory (``PeerExchange``)."""
+        if comm not in ("dist", "p2p"):
+            raise ValueError("comm must be 'dist' or 'p2p'")
+        self.comm = comm
+        self._px = None
         self.group = group
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         self.rank = dist.get_rank(group) if rank is None else rank
@@ -115,9 +200,20 @@ class ShardedContrastMemory(ContrastMemory):
             packed = torch.empty(2 * B * D + 8, dtype=torch.float32, device=g1.device)
             packed[:B * D] = g1.reshape(-1)
             packed[B * D:2 * B * D] = g2.reshape(-1)
-        packed[2 * B * D:] = res  # fp64 -> fp32 (1e-7 relative on the loss partials)
-        self._all_reduce(packed)  # ONE packed exchange after the kernel
+        if self.comm == "p2p" and self.world_size > 1:
+            # one kernel over NVLink peer memory; the 8 fp64 result scalars ride along as fp32 words
+            packed = self._peer_exchange(B, D, g1.device).allreduce(packed[:2 * B * D], res)
+        else:
+            packed[2 * B * D:] = res  # fp64 -> fp32 (1e-7 relative on the loss partials)
+            self._all_reduce(packed)  # ONE packed exchange after the kernel
         return packed[2 * B * D:], packed[:B * D].view(B, D), packed[B * D:2 * B * D].view(B, D)
+
+    def _peer_exchange(self, B, D, device):
+        if self._px is None or self._px.Bmax < B or self._px.Dmax < D:
+            if self._px is not None:
+                self._px.close()
+            self._px = PeerExchange(self.group, self.rank, self.world_size, device, max(B, 64), max(D, 128))
+        return self._px
 
     def _gather(self, v1, v2, y):
         """ONE packed exchange before the kernel: local anchors -> all anchors (uneven B_loc allowed)."""
@@ -129,6 +225,9 @@ class ShardedContrastMemory(ContrastMemory):
         rows = max(counts)
         self._anchor_offset = sum(counts[:self.rank])
         d = v1.shape[1]
+        if self.comm == "p2p" and self.world_size > 1:
+            return self._peer_exchange(sum(counts), d, v1.device).allgather(
+                v1.contiguous(), v2.contiguous(), y.contiguous().to(torch.int64), counts)
         if min(counts) == rows:  # even split: no padding, no compaction
             buf = torch.cat([v1, v2, y.contiguous().view(-1, 1).view(torch.float32)], dim=1)
             out = self._all_gather_rows(buf)
@@ -164,13 +263,14 @@ class ShardedCRDLoss(nn.Module):
     features and this rank's embed parameters covers the local anchors only, so embed-parameter gradients must be
     SUMMED over ranks (``allreduce_embed_grads``) to equal the single-GPU gradients."""
 
-    def __init__(self, opt, group=None, rank=None, world_size=None, local_negatives=False, **memory_kwargs):
+    def __init__(self, opt, group=None, rank=None, world_size=None, local_negatives=False, comm="dist",
+                 **memory_kwargs):
         super().__init__()
         self.embed_s = Embed(opt.s_dim, opt.feat_dim)
         self.embed_t = Embed(opt.t_dim, opt.feat_dim)
         self.contrast = ShardedContrastMemory(opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m, group=group,
                                               rank=rank, world_size=world_size, local_negatives=local_negatives,
-                                              **memory_kwargs)
+                                              comm=comm, **memory_kwargs)
 
     def forward(self, f_s, f_t, idx, contrast_idx=None):
         return self.contrast.fused_loss(self.embed_s(f_s), self.embed_t(f_t), idx, contrast_idx)

@@ -25,8 +25,20 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
     cg = dict(c, N=N_loc * world)                       # global bank
     opt = make_opt(cg)
     torch.manual_seed(SEED + rank)
-    crit = pkg.ShardedCRDLoss(opt, local_negatives=True).to(dev)
+    # exchanges: "p2p" = single kernels over NVLink peer memory (default), "nccl" = torch.distributed collectives
+    comm = os.environ.get("CRDPN_COMM", "p2p")
+    crit = pkg.ShardedCRDLoss(opt, local_negatives=True, comm="p2p" if comm == "p2p" else "dist").to(dev)
     mem = crit.contrast
+    if comm == "p2p":  # collective set-up; if CUDA IPC is unavailable on ANY rank, every rank says so and uses NCCL
+        ok = torch.ones(1, device=dev)
+        try:
+            mem._peer_exchange(B, D, dev)
+        except Exception as exc:
+            print(f"[bench_multi] rank {rank}: peer-memory exchange unavailable ({exc}); using NCCL", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            comm, mem.comm = "nccl", "dist"
     lo, hi = mem.row_begin, mem.row_end
     # global batch, identical on every rank (seeded); each rank embeds its slice of the anchors
     g = torch.Generator().manual_seed(SEED)
@@ -106,7 +118,7 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
     lib.crdpn_timing_enable(0)
     kms = torch.tensor([tot.value / max(n.value, 1)], dtype=torch.float64, device=dev)
     dist.all_reduce(kms, op=dist.ReduceOp.MAX)
-    launches = (pkg._native.launch_count() - l0) if not use_graph else 2 * args.steps  # graph replays: 2 of ours/step
+    launches = (pkg._native.launch_count() - l0) if not use_graph else (4 if comm == "p2p" else 2) * args.steps  # graph replays
 
     # end to end through the public API with pinned HOST inputs on every rank
     host = [t.pin_memory() for t in (f_s[sl].contiguous(), f_t[sl].contiguous(), y[sl].contiguous(), cidx)]
@@ -152,7 +164,10 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
             "e2e": {"value": total_scores / (e2e_ms.item() * 1e-3), "unit": "scores/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms.item(),
                     "api": "ShardedCRDLoss(f_s_loc, f_t_loc, idx_loc, contrast_idx_loc).backward(), pinned host inputs"},
-            "gpu_launches": launches, "collectives_per_step": 2, "cuda_graph": use_graph,
+            "gpu_launches": launches, "comm": ("NVLink peer-memory kernels (all-gather + one-shot all-reduce), no NCCL call in the step"
+                                               if comm == "p2p" else "nccl"),
+            "collectives_per_step": 0 if comm == "p2p" else 2, "exchange_kernels_per_step": 2 if comm == "p2p" else 0,
+            "cuda_graph": use_graph,
             "clocks": clocks,
         }
         print(json.dumps(line))

@@ -136,6 +136,30 @@ int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int 
                               float momentum, float one_minus_momentum, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Exchanges of the row-sharded CRD step over NVLink peer memory (one process per GPU; no counterpart in the
+ * single-GPU reference -- SURVEY.md section 8e).  Each rank allocates one exchange buffer, exports its CUDA IPC
+ * handle (64 bytes, exchanged by the caller through any host channel), imports the peers' handles, and passes the
+ * HOST array of the `world` base pointers (its own at index `rank`) to the two exchange kernels.  Bmax / Dmax fix the
+ * buffer layout and must be the same on every rank.  world <= 8.  Every rank must issue the same sequence of calls.
+ *   crdpn_p2p_allgather_anchors: local rows v1/v2 [b_loc,D] f32, y [b_loc] i64 -> all B rows in rank order;
+ *                                offs_host[world+1] = prefix sums of the per-rank batch sizes.
+ *   crdpn_p2p_allreduce_f32:     out[i] = sum over ranks (in rank order: same bits on every rank) of partial[i];
+ *                                the payload is n_main floats followed by n_tail doubles (sent as floats: the step's
+ *                                8 result scalars), out has n_main + n_tail floats.
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_p2p_buffer_bytes(int64_t Bmax, int64_t Dmax, int world, size_t* bytes);
+int crdpn_p2p_alloc(size_t bytes, void** dev_ptr);
+int crdpn_p2p_free(void* dev_ptr);
+int crdpn_p2p_export(void* dev_ptr, void* handle64_host);
+int crdpn_p2p_import(const void* handle64_host, void** peer_ptr);
+int crdpn_p2p_close(void* peer_ptr);
+int crdpn_p2p_allgather_anchors(const float* v1, const float* v2, const int64_t* y, int64_t D,
+                                const int32_t* offs_host, void* const* peer_bufs_host, int rank, int world,
+                                int64_t Bmax, int64_t Dmax, float* out_v1, float* out_v2, int64_t* out_y, void* stream);
+int crdpn_p2p_allreduce_f32(const float* partial, int64_t n_main, const double* tail_f64, int64_t n_tail, float* out,
+                            void* const* peer_bufs_host, int rank, int world, int64_t Bmax, int64_t Dmax, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * PointNet encoder, eval-mode BatchNorm (the KD-time teacher, KD/common/base_class.py:317,363).
  * Replaces: ShapeEncoderPC.forward, auxiliary/model.py:174-180 (conv1/bn1/relu, conv2/bn2/relu,
  * conv3/bn3, max over points), BN folded into the weights by crdpn_pointnet_pack.

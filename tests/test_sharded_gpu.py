@@ -66,7 +66,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker(rank, world, port, q, comm="dist"):
     try:
         import torch.distributed as dist
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -78,7 +78,7 @@ def _nccl_worker(rank, world, port, q):
         opt = _opt(n_data=6001)
         torch.manual_seed(1)
         ref = pkg.CRDLoss(opt).to(dev)                       # the unsharded module, same weights on every rank
-        sh = pkg.ShardedCRDLoss(opt).to(dev)
+        sh = pkg.ShardedCRDLoss(opt, comm=comm).to(dev)
         lo, hi = sh.contrast.row_begin, sh.contrast.row_end
         with torch.no_grad():
             for n_ in ("embed_s", "embed_t"):
@@ -109,12 +109,14 @@ def _nccl_worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_world2_nccl_matches_unsharded(pkg):
+@pytest.mark.parametrize("comm", ["dist", "p2p"])
+def test_world2_nccl_matches_unsharded(pkg, comm):
+    """comm="dist": NCCL collectives; comm="p2p": the two exchanges as single kernels over NVLink peer memory."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, comm)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
