@@ -35,6 +35,16 @@ _SIGNATURES = {
                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                c_float, c_float, c_float, c_float, c_float, c_float,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "crdpn_crd_loss_forward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p,
+                                       c_void_p, c_void_p, c_int64, c_int,
+                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                       c_float, c_float, c_float, c_float, c_float, c_float,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "crdpn_crd_loss_backward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_int64, c_int64] + [c_void_p] * 8),
     "crdpn_crd_momentum_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     "crdpn_pointnet_packed_bytes": (c_int, [c_int64, POINTER(c_size_t)]),

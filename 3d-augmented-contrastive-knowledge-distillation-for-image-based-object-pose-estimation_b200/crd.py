@@ -147,68 +147,114 @@ class _EmbedFunction(torch.autograd.Function):
         return dx, dW, db
 
 
-def _embed_forward(x, weight, bias):
-    """crdpn_embed_forward on detached tensors -> (v, inv_norm, x_contiguous)."""
-    x = x.detach().reshape(x.shape[0], -1).contiguous()
-    weight, bias = weight.detach().contiguous(), bias.detach().contiguous()
-    B, dim_in = x.shape
-    D = weight.shape[0]
-    dev = x.device
-    pre = torch.empty(B, D, dtype=torch.float32, device=dev)
-    v = torch.empty_like(pre)
-    inv = torch.empty(B, dtype=torch.float32, device=dev)
-    with _native.on_device(dev):
-        rc = _native.lib().crdpn_embed_forward(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, dim_in, D,
-                                               pre.data_ptr(), v.data_ptr(), inv.data_ptr(), _stream_ptr(dev))
-    _native.check(rc, "crdpn_embed_forward")
-    return v, inv, x, weight
-
-
-def _embed_backward(x, weight, v, inv, g, scale, need_dx):
-    B, dim_in = x.shape
-    D = weight.shape[0]
-    dev = x.device
-    dW = torch.empty_like(weight)
-    db = torch.empty(D, dtype=torch.float32, device=dev)
-    dx = torch.empty_like(x) if need_dx else None
-    d_pre = torch.empty(B, D, dtype=torch.float32, device=dev)
-    with _native.on_device(dev):
-        rc = _native.lib().crdpn_embed_backward(x.data_ptr(), weight.data_ptr(), v.data_ptr(), inv.data_ptr(),
-                                                g.data_ptr(), scale.data_ptr(), B, dim_in, D, dW.data_ptr(), db.data_ptr(),
-                                                dx.data_ptr() if dx is not None else None, d_pre.data_ptr(),
-                                                _stream_ptr(dev))
-    _native.check(rc, "crdpn_embed_backward")
-    return dx, dW, db
-
-
 class _CRDLossFunction(torch.autograd.Function):
-    """The whole CRD step as one autograd node: embed heads -> (negative draw) -> fused score/loss/backward/update.
-    12 kernel launches per forward+backward; the upstream gradient of the loss is folded into the embed backward
-    (device scalar), so no elementwise torch kernels run at all."""
+    """The whole CRD step as one autograd node and TWO foreign calls: ``crdpn_crd_loss_forward`` (embed heads ->
+    negative draw -> fused score/loss/backward -> reduction + momentum update, 7 launches) and
+    ``crdpn_crd_loss_backward`` (the two embed-head backwards, 5 launches).  Everything the step produces lives in one
+    float32 arena ``[result(16) | pre_s | pre_t | v1 | v2 | grad_v1 | grad_v2 | inv1 | inv2]``; the upstream gradient
+    of the loss is a device scalar folded into the embed backward, so no elementwise torch kernels run at all."""
 
     @staticmethod
     def forward(ctx, f_s, f_t, Ws, bs, Wt, bt, y, contrast_idx, crit):
-        v1, inv1, xs, Wsc = _embed_forward(f_s, Ws, bs)
-        v2, inv2, xt, Wtc = _embed_forward(f_t, Wt, bt)
         mem = crit.contrast
-        v1c, v2c, yc, idx = mem._prepare(v1, v2, y, contrast_idx)
-        loss, g1, g2 = mem._score_and_update(v1c, v2c, yc, idx)
-        ctx.save_for_backward(xs, Wsc, v1, inv1, g1, xt, Wtc, v2, inv2, g2)
+        dev = f_s.device
+        xs = f_s.detach().reshape(f_s.shape[0], -1).contiguous()
+        xt = f_t.detach().reshape(f_t.shape[0], -1).contiguous()
+        Wsc, bsc, Wtc, btc = Ws.detach().contiguous(), bs.detach().contiguous(), Wt.detach().contiguous(), bt.detach().contiguous()
+        B, D = xs.shape[0], Wsc.shape[0]
+        hp = mem._host_params()
+        K1 = hp.K + 1
+        if xt.shape[0] != B or y.numel() != B:
+            raise RuntimeError("f_s, f_t and idx must share the batch dimension")
+        mem._check_device(y, "idx")
+        yc = y.contiguous().to(torch.int64)
+        if contrast_idx is not None:
+            mem._check_device(contrast_idx, "contrast_idx")
+            contrast_idx = contrast_idx.contiguous().to(torch.int64)
+            if contrast_idx.shape != (B, K1):
+                raise RuntimeError(f"contrast_idx must have shape [B, K+1] = {(B, K1)}, got {tuple(contrast_idx.shape)}")
+        BD = B * D
+        Bp = (B + 3) & ~3
+        arena = torch.empty(16 + 6 * BD + 2 * Bp, dtype=torch.float32, device=dev)
+        base = arena.data_ptr()
+        o_pre_s, o_pre_t, o_v1, o_v2, o_g1, o_g2 = (base + 4 * (16 + i * BD) for i in range(6))
+        o_inv1 = base + 4 * (16 + 6 * BD)
+        o_inv2 = o_inv1 + 4 * Bp
+        if hp.Z1 <= 0 or hp.Z2 <= 0:
+            # first call: the published algorithm freezes Z from this batch (one device->host read); run the embed
+            # heads on their own, freeze, then take the fused path below with the SAME drawn negatives
+            lib = _native.lib()
+            with _native.on_device(dev):
+                st = _stream_ptr(dev)
+                _native.check(lib.crdpn_embed_forward(xs.data_ptr(), Wsc.data_ptr(), bsc.data_ptr(), B, xs.shape[1], D,
+                                                      o_pre_s, o_v1, o_inv1, st), "crdpn_embed_forward")
+                _native.check(lib.crdpn_embed_forward(xt.data_ptr(), Wtc.data_ptr(), btc.data_ptr(), B, xt.shape[1], D,
+                                                      o_pre_t, o_v2, o_inv2, st), "crdpn_embed_forward")
+            v1 = arena[16 + 2 * BD:16 + 3 * BD].view(B, D)
+            v2 = arena[16 + 3 * BD:16 + 4 * BD].view(B, D)
+            if contrast_idx is None:
+                contrast_idx = mem.multinomial.draw_contrast(yc, K1)
+            mem._freeze_z(v1, v2, contrast_idx)
+            hp = mem._host_params()
+        m1, m2, stride, dt = mem._banks()
+        ws = mem._workspace(B, K1, D, dev)
+        smp = mem.multinomial
+        if contrast_idx is None:
+            scratch = mem._idx_scratch
+            if scratch is None or scratch.numel() != B * K1 or scratch.device != dev:
+                scratch = mem._idx_scratch = torch.empty(B * K1, dtype=torch.int64, device=dev)
+            cidx_ptr, scratch_ptr = None, scratch.data_ptr()
+        else:
+            cidx_ptr, scratch_ptr = contrast_idx.data_ptr(), None
+        with _native.on_device(dev):
+            rc = _native.lib().crdpn_crd_loss_forward(
+                xs.data_ptr(), xs.shape[1], Wsc.data_ptr(), bsc.data_ptr(),
+                xt.data_ptr(), xt.shape[1], Wtc.data_ptr(), btc.data_ptr(),
+                yc.data_ptr(), cidx_ptr, smp.prob.data_ptr(), smp.alias.data_ptr(), smp.seed, smp.offset, scratch_ptr,
+                m1.data_ptr(), m2.data_ptr(), stride, dt,
+                B, K1, D, mem.nLem, mem.k_total, mem.row_begin, mem.row_end,
+                hp.T, hp.Z1, hp.Z2, EPS, hp.m, 1.0 - hp.m,
+                o_pre_s, o_pre_t, o_v1, o_v2, o_inv1, o_inv2,
+                base, o_g1, o_g2, ws.data_ptr(), ws.numel(), mem.variant, _stream_ptr(dev))
+        _native.check(rc, "crdpn_crd_loss_forward")
+        if contrast_idx is None:
+            smp.offset += B * K1
+        ctx.save_for_backward(arena, xs, xt, Wsc, Wtc)
         ctx.need_dx = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         ctx.in_shapes = (f_s.shape, f_t.shape)
-        return loss
+        return arena[12]  # float32(loss_s + loss_t), written by the reduction kernel into result slot 6
 
     @staticmethod
     def backward(ctx, grad_out):
-        xs, Ws, v1, inv1, g1, xt, Wt, v2, inv2, g2 = ctx.saved_tensors
+        arena, xs, xt, Ws, Wt = ctx.saved_tensors
+        dev = xs.device
+        B, D = xs.shape[0], Ws.shape[0]
+        BD = B * D
+        Bp = (B + 3) & ~3
+        base = arena.data_ptr()
+        o_v1, o_v2, o_g1, o_g2 = (base + 4 * (16 + i * BD) for i in range(2, 6))
+        o_inv1 = base + 4 * (16 + 6 * BD)
+        o_inv2 = o_inv1 + 4 * Bp
         scale = grad_out.detach().to(torch.float32).contiguous()
-        dxs, dWs, dbs = _embed_backward(xs, Ws, v1, inv1, g1, scale, ctx.need_dx[0])
-        dxt, dWt, dbt = _embed_backward(xt, Wt, v2, inv2, g2, scale, ctx.need_dx[1])
+        dWs, dWt = torch.empty_like(Ws), torch.empty_like(Wt)
+        dbs = torch.empty(2 * D, dtype=torch.float32, device=dev)
+        dxs = torch.empty_like(xs) if ctx.need_dx[0] else None
+        dxt = torch.empty_like(xt) if ctx.need_dx[1] else None
+        d_pre = torch.empty(2 * BD, dtype=torch.float32, device=dev)
+        with _native.on_device(dev):
+            rc = _native.lib().crdpn_crd_loss_backward(
+                xs.data_ptr(), xs.shape[1], Ws.data_ptr(), o_v1, o_inv1, o_g1,
+                xt.data_ptr(), xt.shape[1], Wt.data_ptr(), o_v2, o_inv2, o_g2,
+                scale.data_ptr(), B, D,
+                dWs.data_ptr(), dbs.data_ptr(), dxs.data_ptr() if dxs is not None else None,
+                dWt.data_ptr(), dbs.data_ptr() + 4 * D, dxt.data_ptr() if dxt is not None else None,
+                d_pre.data_ptr(), _stream_ptr(dev))
+        _native.check(rc, "crdpn_crd_loss_backward")
         if dxs is not None:
             dxs = dxs.view(ctx.in_shapes[0])
         if dxt is not None:
             dxt = dxt.view(ctx.in_shapes[1])
-        return dxs, dxt, dWs, dbs, dWt, dbt, None, None, None
+        return dxs, dxt, dWs, dbs[:D], dWt, dbs[D:], None, None, None
 
 
 class Embed(nn.Module):
@@ -303,6 +349,7 @@ class ContrastMemory(nn.Module):
         self._ws = None
         self._ws_key = None
         self._res = None
+        self._idx_scratch = None
         # host mirror of params (avoids a device->host read per step once Z is frozen)
         self._host = None
 
@@ -322,6 +369,7 @@ class ContrastMemory(nn.Module):
         self._relayout()  # .cuda()/.to() de-interleave the two views; put them back in one allocation
         self.multinomial.to(self._buffers["memory_v1"].device)
         self._ws = None
+        self._idx_scratch = None
         self._host = None
         return self
 

@@ -543,10 +543,23 @@ __global__ void __launch_bounds__(256) alias_draw_kernel(const float* __restrict
                                                          unsigned long long offset, const long long* __restrict__ y,
                                                          long long K1, long long* __restrict__ out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool small = count < (1ll << 32) && K1 < (1ll << 32);  // 32-bit division: the 64-bit one is a ~100-instruction call
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    if (y != nullptr && (i % K1) == 0) {
-      out[i] = y[i / K1];
-      continue;
+    if (y != nullptr) {
+      long long row;
+      bool first;
+      if (small) {
+        const unsigned q = (unsigned)i / (unsigned)K1;
+        row = q;
+        first = (unsigned)i - q * (unsigned)K1 == 0u;
+      } else {
+        row = i / K1;
+        first = i - row * K1 == 0;
+      }
+      if (first) {
+        out[i] = y[row];
+        continue;
+      }
     }
     unsigned r[4];
     philox4x32_10(seed, offset + (unsigned long long)i, r);

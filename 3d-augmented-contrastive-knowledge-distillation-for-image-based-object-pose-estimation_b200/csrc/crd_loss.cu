@@ -1,0 +1,50 @@
+// crd_loss.cu -- the whole CRDLoss.forward / backward as ONE C call each.
+//
+// A CRD step on B200 is ~0.5 ms of device work made of a dozen launches; driven launch by launch from Python the
+// host needs about as long again (tensor allocations, ctypes marshalling, context managers), and because the KD loop
+// reads the loss back every step (KD/common/base_class.py:400-401) the device cannot run ahead of the host.  These two
+// entry points enqueue every launch of the published CRDLoss.forward (embed heads -> negative draw -> fused
+// score/loss/backward -> reduction + momentum update) and of its backward (the two embed-head backwards) back to back
+// from C, so the host cost of a step is two foreign calls.
+#include "common.cuh"
+
+using namespace crdpn;
+
+extern "C" int crdpn_crd_loss_forward(
+    const float* f_s, int64_t s_dim, const float* Ws, const float* bs,
+    const float* f_t, int64_t t_dim, const float* Wt, const float* bt,
+    const int64_t* y, const int64_t* contrast_idx,
+    const float* alias_prob, const int64_t* alias_alias, uint64_t seed, uint64_t offset, int64_t* idx_scratch,
+    void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+    int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
+    float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+    float* pre_s, float* pre_t, float* v1, float* v2, float* inv1, float* inv2,
+    double* result, float* grad_v1, float* grad_v2,
+    void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  if (!y) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward: null y");
+  int rc = crdpn_embed_forward(f_s, Ws, bs, B, s_dim, D, pre_s, v1, inv1, stream);
+  if (rc) return rc;
+  rc = crdpn_embed_forward(f_t, Wt, bt, B, t_dim, D, pre_t, v2, inv2, stream);
+  if (rc) return rc;
+  const int64_t* idx = contrast_idx;
+  if (idx == nullptr) {
+    if (!idx_scratch) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward: contrast_idx is NULL and so is idx_scratch");
+    rc = crdpn_alias_draw_contrast(alias_prob, alias_alias, n_data, y, B, K1, seed, offset, idx_scratch, stream);
+    if (rc) return rc;
+    idx = idx_scratch;
+  }
+  return crdpn_crd_step(bank1, bank2, row_stride, bank_dtype, v1, v2, idx, y, B, K1, D, n_data, k_total, row_begin,
+                        row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, result, grad_v1, grad_v2, workspace,
+                        workspace_bytes, variant, stream);
+}
+
+extern "C" int crdpn_crd_loss_backward(
+    const float* f_s, int64_t s_dim, const float* Ws, const float* v1, const float* inv1, const float* grad_v1,
+    const float* f_t, int64_t t_dim, const float* Wt, const float* v2, const float* inv2, const float* grad_v2,
+    const float* scale, int64_t B, int64_t D,
+    float* dWs, float* dbs, float* dxs, float* dWt, float* dbt, float* dxt, float* d_pre_scratch, void* stream) {
+  if (!d_pre_scratch) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_backward: null scratch");
+  int rc = crdpn_embed_backward(f_s, Ws, v1, inv1, grad_v1, scale, B, s_dim, D, dWs, dbs, dxs, d_pre_scratch, stream);
+  if (rc) return rc;
+  return crdpn_embed_backward(f_t, Wt, v2, inv2, grad_v2, scale, B, t_dim, D, dWt, dbt, dxt, d_pre_scratch + B * D, stream);
+}

@@ -256,7 +256,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_line(line)
 
 
 def run_own(args):
@@ -296,8 +296,8 @@ def run_own(args):
     abytes = algorithmic_bytes(c)
     achieved = abytes / (r["kernel_ms_avg"] * 1e-3) / 1e9
     if os.environ.get("CRDPN_BENCH_QUICK"):  # profiling runs: just the timed loop
-        print(json.dumps({"quick": True, "ms_per_step": ms_step, "value": value, "kernel_ms": r["kernel_ms_avg"],
-                          "achieved_gbs": achieved}))
+        print_line({"quick": True, "ms_per_step": ms_step, "value": value, "kernel_ms": r["kernel_ms_avg"],
+                    "achieved_gbs": achieved})
         return
     e2e = time_crd_e2e(pkg, torch, dev, c, max(args.steps // 4, 5), args.warmup)
     e2e_h = time_crd_e2e(pkg, torch, dev, c, max(args.steps // 4, 5), args.warmup, host_contrast_idx=True)
@@ -362,7 +362,12 @@ def run_own(args):
             line["roofline"]["traffic"] = json.loads(traffic.read_text()).get("crd_score_kernel_bytes_per_launch")
         except Exception:
             pass
-    print(json.dumps(line))
+    print_line(line)
+
+
+def print_line(obj):
+    sys.__stdout__.write(json.dumps(obj) + "\n")
+    sys.__stdout__.flush()
 
 
 def main():
@@ -372,10 +377,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_own(args)
+    # stdout carries exactly ONE JSON line: everything else the run prints (the published module announces its frozen
+    # normalisation constants on stdout) goes to stderr
+    sys.stdout = sys.stderr
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_own(args)
+    finally:
+        sys.stdout = sys.__stdout__
 
 
 if __name__ == "__main__":

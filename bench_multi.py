@@ -170,7 +170,8 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
             "cuda_graph": use_graph,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        sys.__stdout__.write(json.dumps(line) + "\n")
+        sys.__stdout__.flush()
     faulthandler.cancel_dump_traceback_later()
     # teardown: drop the captured graph before the communicator; never let a stuck teardown eat box time
     import threading

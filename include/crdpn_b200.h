@@ -125,6 +125,32 @@ int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
                    void* workspace, size_t workspace_bytes, int variant, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * The whole published CRDLoss.forward (crd/criterion.py: embed_s, embed_t, ContrastMemory.forward, the two
+ * ContrastLoss terms) and its autograd backward, each as ONE call that enqueues every launch back to back:
+ *   forward : crdpn_embed_forward x2 -> [crdpn_alias_draw_contrast when contrast_idx == NULL, into idx_scratch
+ *             [B,K1] int64] -> crdpn_crd_step.  Same results, bit for bit, as the individual calls.
+ *   backward: crdpn_embed_backward x2 (dxs / dxt may be NULL; d_pre_scratch holds 2*B*D floats).
+ * This is what the reference's KD loop would call at KD/common/base_class.py:387 (forward) and :394 (backward);
+ * the host cost of a step drops from ~30 foreign calls / allocations to two.
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_crd_loss_forward(
+    const float* f_s, int64_t s_dim, const float* Ws, const float* bs,
+    const float* f_t, int64_t t_dim, const float* Wt, const float* bt,
+    const int64_t* y, const int64_t* contrast_idx,
+    const float* alias_prob, const int64_t* alias_alias, uint64_t seed, uint64_t offset, int64_t* idx_scratch,
+    void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+    int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
+    float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+    float* pre_s, float* pre_t, float* v1, float* v2, float* inv1, float* inv2,
+    double* result, float* grad_v1, float* grad_v2,
+    void* workspace, size_t workspace_bytes, int variant, void* stream);
+int crdpn_crd_loss_backward(
+    const float* f_s, int64_t s_dim, const float* Ws, const float* v1, const float* inv1, const float* grad_v1,
+    const float* f_t, int64_t t_dim, const float* Wt, const float* v2, const float* inv2, const float* grad_v2,
+    const float* scale, int64_t B, int64_t D,
+    float* dWs, float* dbs, float* dxs, float* dWt, float* dbt, float* dxt, float* d_pre_scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Momentum update of both banks (ContrastMemory.forward, torch.no_grad block: index_select, mul_, add_,
  * pow/sum/pow, div, index_copy_).  bank[y] <- normalise(m*bank[y] + (1-m)*v), canonical reduction order
  * (oracle/crd_oracle.c), last duplicate of y wins, rows outside the shard untouched.
