@@ -1,11 +1,14 @@
 """crdpn_b200 -- B200-native hot path of 3DAug-Pose's contrastive distillation step.
 
-Two drop-in modules behind the reference's Python surface, both thin shims over the C ABI of
+Drop-in modules and functions behind the reference's Python surface, both thin shims over the C ABI of
 ``libcrdpn_b200.so`` (``include/crdpn_b200.h``, hand-written sm_100a CUDA):
 
 * ``CRDLoss(opt)(f_s, f_t, idx, contrast_idx)`` -- CRD memory-bank NCE step (``crd.py``)
 * ``ShapeEncoderPC(feature_dim)(shapes[B,3,P]) -> [B,feature_dim]`` -- the teacher's PointNet encoder
   (``pointnet.py``; reference ``auxiliary/model.py:154-180``)
+* the loss code either side of them (``kd_losses.py``): ``infoNCE_KD`` / ``poseNCE_KD`` (``auxiliary/model_utils.py:225-285``),
+  ``CELoss`` / ``DeltaLoss`` (``auxiliary/loss.py``), ``TemperatureScaledKLDivLoss`` / ``calculate_kd_loss_new``
+  (``KD/vision/vanilla/vanilla_kd.py``)
 
 The directory name is fixed by the build harness and is not a Python identifier; load it with
 ``__graft_entry__.load_package()`` (registers it as ``crdpn_b200``).
@@ -18,8 +21,10 @@ from .sharded import ShardedContrastMemory, ShardedCRDLoss, shard_bounds  # noqa
 
 __all__ = ["AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", "Normalize",
            "ShardedContrastMemory", "ShardedCRDLoss", "shard_bounds"]
-try:  # added with the PointNet kernels
-    from .pointnet import ShapeEncoderPC  # noqa: F401
-    __all__.append("ShapeEncoderPC")
-except ImportError:  # pragma: no cover
-    pass
+from .pointnet import ShapeEncoderPC  # noqa: F401,E402
+from . import kd_losses  # noqa: F401,E402
+from .kd_losses import (CELoss, DeltaLoss, TemperatureScaledKLDivLoss, calculate_kd_loss_new, infoNCE_KD,  # noqa: F401,E402
+                        poseNCE_KD, student_kd_step_loss)
+
+__all__ += ["ShapeEncoderPC", "CELoss", "DeltaLoss", "TemperatureScaledKLDivLoss", "calculate_kd_loss_new", "infoNCE_KD",
+            "poseNCE_KD", "student_kd_step_loss"]

@@ -56,6 +56,18 @@ _SIGNATURES = {
                                     c_void_p, c_void_p]),
     "crdpn_embed_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "crdpn_nce_kd_workspace_bytes": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
+    "crdpn_nce_kd_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_int, c_float, c_uint64,
+                                     c_uint64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crdpn_nce_kd_backward": (c_int, [c_void_p, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64, c_void_p, c_size_t,
+                                      c_void_p, c_void_p, c_void_p]),
+    "crdpn_kd_mix_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
+    "crdpn_kd_mix_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                     c_void_p, ctypes.c_int32, ctypes.c_uint32, c_float, c_float, c_float, c_float,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crdpn_kd_mix_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                      c_void_p, ctypes.c_int32, ctypes.c_uint32, c_float, c_float, c_float, c_float,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crdpn_p2p_buffer_bytes": (c_int, [c_int64, c_int64, c_int, POINTER(c_size_t)]),
     "crdpn_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "crdpn_p2p_free": (c_int, [c_void_p]),

@@ -523,20 +523,6 @@ __global__ void __launch_bounds__(kFinalizeThreads) crd_finalize_update_kernel(c
 // ------------------------------------------------------------------------------------------------------
 // Alias-method draw: one Philox4x32-10 block per output (identical stream to oracle/crd_oracle.c).
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(unsigned long long seed, unsigned long long ctr, unsigned out[4]) {
-  unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0u, c3 = 0u;
-  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 __global__ void __launch_bounds__(256) alias_draw_kernel(const float* __restrict__ prob,
                                                          const long long* __restrict__ alias, long long n,
                                                          long long count, unsigned long long seed,

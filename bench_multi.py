@@ -148,6 +148,12 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
     total_scores = 2 * B * (K_loc * world + 1)
     per_rank_bytes = algorithmic_bytes(c)
     achieved = per_rank_bytes / (kms.item() * 1e-3) / 1e9
+    also = {}
+    try:  # BASELINE metric's second half at N > 1: PointNet points/s (replicas, no collective)
+        from bench_pointnet import bench_pointnet_replicas
+        also["pointnet"] = bench_pointnet_replicas(pkg, torch, dist, dev, rank, world, max(args.steps // 2, 20), args.warmup)
+    except Exception as exc:
+        also["pointnet"] = {"error": str(exc)}
     if rank == 0:
         line = {
             "metric": "crd_negatives_scored_per_sec", "value": total_scores / (ms_step * 1e-3), "unit": "scores/s",
@@ -169,6 +175,7 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
             "collectives_per_step": 0 if comm == "p2p" else 2, "exchange_kernels_per_step": 2 if comm == "p2p" else 0,
             "cuda_graph": use_graph,
             "clocks": clocks,
+            "also": also,
         }
         sys.__stdout__.write(json.dumps(line) + "\n")
         sys.__stdout__.flush()

@@ -8,13 +8,66 @@ import time
 FLOP_PER_POINT = 2 * (3 * 64 + 64 * 128 + 128 * 1024)  # 278 912
 
 
+def synthetic_state(torch, feature_dim=1024, seed=46):
+    """Synthetic encoder weights: PyTorch-default-like Conv1d init, BN affine and running
+    statistics randomised (gamma ~ N(0,1) incl. negatives) so that folding mistakes would show."""
+    g = torch.Generator().manual_seed(seed)
+    st = {}
+    for cin, cout, n in ((3, 64, 1), (64, 128, 2), (128, feature_dim, 3)):
+        bound = 1.0 / (cin ** 0.5)
+        st[f"conv{n}.weight"] = (torch.rand(cout, cin, 1, generator=g) * 2 - 1) * bound
+        st[f"conv{n}.bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+        st[f"bn{n}.weight"] = torch.randn(cout, generator=g)
+        st[f"bn{n}.bias"] = torch.randn(cout, generator=g)
+        st[f"bn{n}.running_mean"] = torch.randn(cout, generator=g) * 0.2
+        st[f"bn{n}.running_var"] = torch.rand(cout, generator=g) * 1.5 + 0.5
+        st[f"bn{n}.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    return st
+
+
+def synthetic_clouds(torch, B, P, seed=46):
+    """Clouds in [0,1], per-sample global min/max normalised like auxiliary/dataset.py:147-148."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, P, generator=g, dtype=torch.float64)
+    x = x - x.amin(dim=(1, 2), keepdim=True)
+    x = x / x.amax(dim=(1, 2), keepdim=True)
+    return x.to(torch.float32)
+
+
+def bench_pointnet_replicas(pkg, torch, dist, dev, rank, world, steps, warmup, B=160, P=2500, F=1024):
+    """N > 1: the eval-mode encoder does not shard below a cloud and needs no exchange: every rank
+    encodes its own batch of B clouds.  value = clouds of ALL ranks x P / max-over-ranks device time."""
+    enc = pkg.ShapeEncoderPC(F)
+    enc.load_state_dict(synthetic_state(torch, F))
+    enc = enc.to(dev).eval()
+    x = synthetic_clouds(torch, B, P, seed=46 + rank).to(dev)
+    for _ in range(max(warmup, 3)):
+        enc(x)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        enc(x)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    return {"workload": f"pointnet_eval_B{B}_P{P}_3-64-128-{F}_bf16_replicas{world}", "metric": "pointnet_points_per_sec",
+            "value": world * B * P / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "scaling": "weak",
+            "tflops_all_ranks": world * FLOP_PER_POINT * B * P / (ms * 1e-3) / 1e12,
+            "note": "replicas only: one batch of clouds per rank, no collective (clouds are independent in eval mode)"}
+
+
 def bench_pointnet(pkg, torch, dev, args, tf_peak, peak_kind, B=160, P=2500, F=1024):
-    from oracle import pointnet_oracle as po
-    st = po.random_state(F, seed=46)
+    st = synthetic_state(torch, F)
     enc = pkg.ShapeEncoderPC(F)
     enc.load_state_dict(st)
     enc = enc.to(dev).eval()
-    x_host = po.random_clouds(B, P, seed=46).pin_memory()
+    x_host = synthetic_clouds(torch, B, P).pin_memory()
     x = x_host.to(dev)
     lib = pkg._native.lib()
     steps, warmup = max(args.steps // 2, 20), max(args.warmup, 3)
@@ -53,6 +106,7 @@ def bench_pointnet(pkg, torch, dev, args, tf_peak, peak_kind, B=160, P=2500, F=1
                    "d2h_bytes_per_step": B * F * 4}}
     out["train"] = bench_pointnet_train(pkg, torch, dev, st, x, steps, warmup, tf_peak, B, P, F)
     if not os.environ.get("CRDPN_BENCH_QUICK"):
+        from oracle import pointnet_oracle as po  # CPU baseline leg only
         torch.set_num_threads(os.cpu_count() or 1)
         xs = x_host[:16]
         po.forward(xs, st, dtype=torch.float32)

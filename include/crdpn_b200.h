@@ -186,6 +186,56 @@ int crdpn_p2p_allreduce_f32(const float* partial, int64_t n_main, const double* 
                             void* const* peer_bufs_host, int rank, int world, int64_t Bmax, int64_t Dmax, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * In-batch contrastive KD losses: infoNCE_KD and poseNCE_KD,
+ * auxiliary/model_utils.py:225-285, with rotation_err / angles_to_matrix, auxiliary/utils.py:156-202; call sites
+ * training.py:57, KD/common/base_class.py:504-508.
+ *   feat_pos <- dropout(feat_pos, p) (p = 0.3 in infoNCE_KD, 0 in poseNCE_KD); a = normalise(feat_ori), q = normalise(feat_pos)
+ *   loss = mean_n -log( e^{a_n.q_n/tau} / (e^{a_n.q_n/tau} + sum_k w_nk e^{a_n.q_k/tau}) ), k over ALL rows including n
+ *   weighting: 0 none (w = 1, infoNCE_KD); 1 linear, 2 square, 3 sqrt, 4 sin, 5 sinsin of rotation_err(label_n, label_k)/180
+ *              (label [B,3] float32 degrees: azimuth, elevation, in-plane; w_nn = 0 exactly)
+ * The dropout keep-mask is a counter-based stream: element e = n*C + c takes word e%4 of Philox4x32-10 block
+ * (seed, offset + e/4); keep iff (word >> 8) * 2^-24 >= p; kept values are scaled by 1/(1-p).
+ * forward: 2 launches, writes the scalar loss; backward: 1 launch, gradients w.r.t. BOTH inputs (d_pos may be NULL),
+ * scaled by the device scalar grad_loss (NULL = 1).  The workspace carries the normalised rows and soft weights from
+ * forward to backward and must stay untouched in between.  Deterministic (fixed-order reductions).
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_nce_kd_workspace_bytes(int64_t B, int64_t C, size_t* bytes);
+int crdpn_nce_kd_forward(const float* feat_ori, const float* feat_pos, const float* label, int64_t B, int64_t C,
+                         float tau, int weighting, float dropout_p, uint64_t seed, uint64_t offset, float* loss,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int crdpn_nce_kd_backward(const float* grad_loss, int64_t B, int64_t C, float tau, float dropout_p, uint64_t seed,
+                          uint64_t offset, const void* workspace, size_t workspace_bytes, float* d_ori, float* d_pos,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * KD loss mixer: the scalar losses of one student / teacher step in ONE launch, and
+ * their gradients in one more.  Replaces CELoss x3 + DeltaLoss (auxiliary/loss.py:7-34), TemperatureScaledKLDivLoss x7
+ * (KD/vision/vanilla/vanilla_kd.py:8-32) and the weighted sum of calculate_kd_loss_new (vanilla_kd.py:143-164); call
+ * site KD/common/base_class.py:365-387 (training.py:50-54 for the ground-truth part alone).
+ *   loss = w_gt * [ sum_{i<3} CE(out_i, label_i // ce_bin_i) + SmoothL1(5*tanh(out_{3+i}[bin_i])/2, 5*((label_i % delta_bin)/delta_bin - .5)) ]
+ *        + w_kl * sum_{i<6} T^2 KL(softmax(t_i/T) || softmax(s_i/T)) + w_rep * T^2 KL(softmax(tf/T) || softmax(sf/T))
+ * (every term a batch mean, as in the reference).  `terms` selects the parts: bit i (0..5) KL of head i, bit 6 KL of the
+ * features, bit 7+i (i<3) CE of head i, bit 10 the delta term; un-selected inputs may be NULL.  student_out /
+ * teacher_out / d_* are HOST arrays of 6 device pointers ([n, widths[i]] f32 each), widths / ce_bin HOST arrays.
+ * label: [n, label_stride] f32 degrees (column i = angle i).  Gradient outputs may individually be NULL.
+ * workspace: crdpn_kd_mix_workspace_bytes(n) bytes whose first 16 bytes are ZERO before the first call (a ticket that
+ * every call leaves zeroed).
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_kd_mix_workspace_bytes(int64_t n, size_t* bytes);
+int crdpn_kd_mix_forward(const float* const* student_out, const float* const* teacher_out, const int32_t* widths,
+                         const float* student_feat, const float* teacher_feat, int64_t feat_dim,
+                         const float* label, int64_t label_stride, int64_t n, const int32_t* ce_bin,
+                         int32_t delta_bin, uint32_t terms, float temperature, float w_kl, float w_rep, float w_gt,
+                         float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int crdpn_kd_mix_backward(const float* const* student_out, const float* const* teacher_out, const int32_t* widths,
+                          const float* student_feat, const float* teacher_feat, int64_t feat_dim,
+                          const float* label, int64_t label_stride, int64_t n, const int32_t* ce_bin,
+                          int32_t delta_bin, uint32_t terms, float temperature, float w_kl, float w_rep, float w_gt,
+                          const float* grad_loss, float* const* d_student_out, float* const* d_teacher_out,
+                          float* d_student_feat, float* d_teacher_feat, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * PointNet encoder, eval-mode BatchNorm (the KD-time teacher, KD/common/base_class.py:317,363).
  * Replaces: ShapeEncoderPC.forward, auxiliary/model.py:174-180 (conv1/bn1/relu, conv2/bn2/relu,
  * conv3/bn3, max over points), BN folded into the weights by crdpn_pointnet_pack.

@@ -1,0 +1,159 @@
+"""CPU tests pinning oracle/kd_losses_oracle.py to the reference's own loss code: against
+tests/golden/kd_losses_golden.npz (made from the reference by oracle/gen_golden_kd.py) everywhere, and against the
+reference functions themselves where /root/reference is mounted.  Tolerances: the golden values are fp32 results of
+the reference, the oracle runs in fp64 -> 2e-5 relative on losses, 1e-4 of the tensor's max on gradients."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kd_losses_oracle as ko
+
+GOLD = Path(__file__).parent / "golden" / "kd_losses_golden.npz"
+HAVE_REF = Path("/root/reference/auxiliary/model_utils.py").exists()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(GOLD)
+    out = [torch.from_numpy(g[f"in/out{i}"]) for i in range(6)]
+    tout = [torch.from_numpy(g[f"in/tout{i}"]) for i in range(6)]
+    return g, out, tout, torch.from_numpy(g["in/sf"]), torch.from_numpy(g["in/tf"]), torch.from_numpy(g["in/label"])
+
+
+def leaf(t):
+    return t.double().clone().requires_grad_()
+
+
+def close(got, ref, tol=1e-4):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert np.abs(got - ref).max() <= tol * (np.abs(ref).max() + 1e-30), (np.abs(got - ref).max(), np.abs(ref).max())
+
+
+def test_synthetic_step_is_the_golden_input(gold):
+    g, out, tout, sf, tf, label = gold
+    o2, t2, s2, f2, l2 = ko.synthetic_step(int(g["n"]), int(g["C"]), seed=46)
+    assert all(torch.equal(a, b) for a, b in zip(out + tout + [sf, tf, label], o2 + t2 + [s2, f2, l2]))
+
+
+def test_keep_mask_stream(gold):
+    g = gold[0]
+    keep = ko.philox_keep_mask(int(g["seed"]), int(g["offset"]), int(g["n"]) * int(g["C"]), float(g["p_drop"]))
+    assert np.array_equal(keep, g["keep_mask"])
+    assert abs(keep.mean() - 0.7) < 0.03
+    # offset shifts the stream by whole blocks of four elements
+    k2 = ko.philox_keep_mask(int(g["seed"]), int(g["offset"]) + 1, 16, float(g["p_drop"]))
+    assert np.array_equal(k2[:12], keep[4:16])
+
+
+def test_rotation_err_matches_golden(gold):
+    g, *_, label = gold
+    n = label.shape[0]
+    d = ko.rotation_err(label.reshape(-1, 1, 3).repeat(1, n, 1).reshape(-1, 3), label.reshape(1, -1, 3).repeat(n, 1, 1).reshape(-1, 3))
+    ref = g["rotation_err_pairs"].astype(np.float64)
+    # acos is ill-conditioned at 0 degrees: the fp32 reference holds up to ~0.06 degrees of rounding noise on the diagonal
+    assert np.abs(d.numpy() - ref).max() < 0.07
+    off = ~np.eye(n, dtype=bool).reshape(-1)
+    assert np.abs(d.numpy() - ref)[off].max() < 2e-3
+    assert d.reshape(n, n).diagonal().abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("tau", [0.1, 0.5])
+def test_infonce_kd_matches_golden(gold, tau):
+    g, _, _, sf, tf, label = gold
+    a, p = leaf(sf), leaf(tf)
+    l = ko.nce_kd(a, p, None, tau, "none", keep_mask=g["keep_mask"], dropout_p=float(g["p_drop"]))
+    l.backward()
+    close(l.item(), g[f"infonce_kd/tau{tau}/loss"], 2e-5)
+    close(a.grad, g[f"infonce_kd/tau{tau}/d_ori"])
+    close(p.grad, g[f"infonce_kd/tau{tau}/d_pos"])
+
+
+@pytest.mark.parametrize("weighting", ["linear", "square", "sqrt", "sin", "sinsin"])
+def test_posence_kd_matches_golden(gold, weighting):
+    g, _, _, sf, tf, label = gold
+    a, p = leaf(sf), leaf(tf)
+    l = ko.nce_kd(a, p, label, 0.1, weighting)
+    l.backward()
+    # The k = n term has weight f(rotation_err(label_n, label_n)) = f(0) = 0 exactly; the fp32 reference holds acos
+    # rounding noise there (0.028 degrees on 3 of the 12 rows, see test_rotation_err_matches_golden), which `sqrt`
+    # amplifies to a weight of 0.012, `linear` / `sin` to 1.6e-4 / 4.9e-4, while `square` / `sinsin` square it away.
+    # The tolerances below are that noise floor of the REFERENCE, not an error of the restatement.
+    ltol, gtol = {"square": (2e-5, 1e-4), "sinsin": (2e-5, 1e-4), "linear": (5e-4, 5e-4), "sin": (2e-3, 1e-3),
+                  "sqrt": (3e-2, 2e-2)}[weighting]
+    close(l.item(), g[f"posence_kd/{weighting}/loss"], ltol)
+    close(a.grad, g[f"posence_kd/{weighting}/d_ori"], gtol)
+    close(p.grad, g[f"posence_kd/{weighting}/d_pos"], gtol)
+
+
+def test_posence_kd_equals_reference_formula_with_the_references_own_weights(gold):
+    """With the reference's fp32 pairwise distances substituted for the oracle's, every weighting agrees to fp32
+    rounding: the deviation above is entirely the diagonal noise."""
+    g, _, _, sf, tf, label = gold
+    n = label.shape[0]
+    d = torch.from_numpy(g["rotation_err_pairs"].astype(np.float64)).reshape(n, n) / 180.0
+    a, p = ko.normalize(sf.double()), ko.normalize(tf.double())
+    l_pos = torch.exp((a * p).sum(1, keepdim=True) / 0.1)
+    for weighting, w in (("linear", d), ("sqrt", torch.sqrt(d)), ("sin", torch.abs(torch.sin(d * np.pi)))):
+        logits = torch.cat([l_pos, torch.exp(a @ p.t() / 0.1) * w], dim=1)
+        l = (-torch.log(logits[:, 0] / logits.sum(-1))).mean()
+        close(l.item(), g[f"posence_kd/{weighting}/loss"], 2e-5)
+
+
+@pytest.mark.parametrize("T", [1.0, 2.0])
+def test_kl_matches_golden(gold, T):
+    g, out, tout, *_ = gold
+    s, t = leaf(out[0]), leaf(tout[0])
+    l = ko.kl_div_t(s, t, T)
+    l.backward()
+    close(l.item(), g[f"kl/T{T}/loss"], 2e-5)
+    close(s.grad, g[f"kl/T{T}/d_student"])
+    close(t.grad, g[f"kl/T{T}/d_teacher"])
+
+
+def test_ce_and_delta_match_golden(gold):
+    g, out, tout, sf, tf, label = gold
+    s = leaf(out[1])
+    l = ko.ce_loss(s, label[:, 1], 180)
+    l.backward()
+    close(l.item(), g["ce180/loss"], 2e-5)
+    close(s.grad, g["ce180/d_pred"])
+    d = [leaf(out[3]), leaf(out[4]), leaf(out[5])]
+    l = ko.delta_loss(d[0], d[1], d[2], label, 15)
+    l.backward()
+    close(l.item(), g["delta/loss"], 2e-5)
+    for i in range(3):
+        close(d[i].grad, g[f"delta/d_pred{i}"])
+
+
+def test_student_step_loss_matches_golden(gold):
+    g, out, tout, sf, tf, label = gold
+    o, to, a, p = [leaf(t) for t in out], [leaf(t) for t in tout], leaf(sf), leaf(tf)
+    l = ko.student_kd_step_loss(o, to, a, p, label)
+    l.backward()
+    close(l.item(), g["step/loss"], 2e-5)
+    close(ko.gt_loss(out, label).item(), g["step/gt_loss"], 2e-5)
+    for i in range(6):
+        close(o[i].grad, g[f"step/d_out{i}"])
+        close(to[i].grad, g[f"step/d_tout{i}"])
+    close(a.grad, g["step/d_sf"])
+    close(p.grad, g["step/d_tf"])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_against_live_reference_functions():
+    ref = ko.load_reference()
+    out, tout, sf, tf, label = ko.synthetic_step(9, 64, seed=5)
+    keep = ko.philox_keep_mask(3, 11, 9 * 64, 0.3)
+    with ko.fixed_dropout(ref, keep):
+        r = ref.model_utils.infoNCE_KD(sf, tf, label, 0.5)
+    close(ko.nce_kd(sf, tf, None, 0.5, "none", keep, 0.3).item(), r.item(), 2e-5)
+    r = ref.model_utils.poseNCE_KD(sf, tf, label, 0.5, "sinsin")
+    close(ko.nce_kd(sf, tf, label, 0.5, "sinsin").item(), r.item(), 1e-4)
+    r = ref.vanilla_kd.TemperatureScaledKLDivLoss(4.0)(sf, tf)
+    close(ko.kl_div_t(sf, tf, 4.0).item(), r.item(), 2e-5)
+    r = ref.loss.DeltaLoss(15)(out[3], out[4], out[5], label.float())
+    close(ko.delta_loss(out[3], out[4], out[5], label, 15).item(), r.item(), 2e-5)
+    r = ref.loss.CELoss(360)(out[0], label[:, 0])
+    close(ko.ce_loss(out[0], label[:, 0], 360).item(), r.item(), 2e-5)
