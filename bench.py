@@ -328,6 +328,12 @@ def run_own(args):
     except ImportError:
         pass
 
+    try:
+        from bench_kd_losses import bench_kd_losses
+        also["kd_losses"] = bench_kd_losses(pkg, torch, dev, args)
+    except ImportError:
+        pass
+
     # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)

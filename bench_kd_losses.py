@@ -1,0 +1,78 @@
+"""Loss-code leg of the benchmark: the student step's loss mixer and the in-batch NCE KD loss
+at the reference's shapes (batch 46 x 3 views = 138 rows, 200-d features, 24/12/24 angle bins)."""
+from __future__ import annotations
+
+import os
+import time
+
+
+def _synthetic_step(torch, n, C, seed=46, bin_size=15):
+    g = torch.Generator().manual_seed(seed)
+    widths = (360 // bin_size, 180 // bin_size, 360 // bin_size) * 2
+    out = [torch.randn(n, w, generator=g) * 2 for w in widths]
+    tout = [torch.randn(n, w, generator=g) * 2 for w in widths]
+    sf = torch.randn(n, C, generator=g)
+    tf = torch.randn(n, C, generator=g) + 0.5 * sf
+    label = torch.stack((torch.randint(0, 360, (n,), generator=g), torch.randint(0, 180, (n,), generator=g),
+                         torch.randint(0, 360, (n,), generator=g)), dim=1)
+    return out, tout, sf, tf, label
+
+
+def _time(torch, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps * 1e3  # us
+
+
+def bench_kd_losses(pkg, torch, dev, args, n=138, C=200):
+    steps, warmup = max(args.steps // 2, 20), max(args.warmup, 3)
+    out, tout, sf, tf, label = _synthetic_step(torch, n, C)
+    o = [t.to(dev).requires_grad_() for t in out]
+    to = [t.to(dev) for t in tout]
+    a, p, lab = sf.to(dev).requires_grad_(), tf.to(dev), label.to(dev)
+
+    def mixer():
+        for t in o + [a]:
+            t.grad = None
+        pkg.student_kd_step_loss(o, to, a, p, lab).backward()
+
+    b = n // 3
+    a1, p1 = sf[:b].to(dev).requires_grad_(), tf[:b].to(dev).requires_grad_()
+
+    def nce():
+        a1.grad = p1.grad = None
+        pkg.infoNCE_KD(a1, p1, None, 0.5).backward()
+
+    res = {}
+    for name, fn, rows in (("student_step_loss_fwd_bwd", mixer, n), ("infoNCE_KD_fwd_bwd", nce, b)):
+        l0 = pkg._native.launch_count()
+        us = _time(torch, fn, steps, warmup)
+        launches = (pkg._native.launch_count() - l0) // (steps + warmup)
+        res[name] = {"us_per_call": us, "rows": rows, "launches_per_call": launches}
+    res["workload"] = f"kd_losses_n{n}_C{C}_bins24-12-24"
+    res["note"] = ("device time per forward+backward through the public functions (host-launch bound: the work is ~1 MFLOP); "
+                   "the eager formulation is ~50 forward + ~80 backward launches for the mixer")
+    if not os.environ.get("CRDPN_BENCH_QUICK"):
+        from oracle import kd_losses_oracle as ko  # CPU baseline leg only
+        torch.set_num_threads(os.cpu_count() or 1)
+        oc = [t.clone().requires_grad_() for t in out]
+        ac = sf.clone().requires_grad_()
+
+        def cpu_mixer():
+            ko.student_kd_step_loss(oc, tout, ac, tf, label, dtype=torch.float32).backward()
+
+        cpu_mixer()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            cpu_mixer()
+        res["cpu_baseline"] = {"value": (time.perf_counter() - t0) / 10 * 1e6, "unit": "us per student_step_loss fwd+bwd",
+                               "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "the full call (138 rows), fp32 torch ops + autograd on CPU, mean of 10"}
+    return res

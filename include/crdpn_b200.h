@@ -236,6 +236,21 @@ int crdpn_kd_mix_backward(const float* const* student_out, const float* const* t
                           void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Point-cloud input producer: read_pointcloud, auxiliary/dataset.py:121-150 (call sites
+ * dataset.py:299,607), for a whole batch in one launch.  The raw mesh vertices of all M models are resident:
+ * vertices [sum_m V_m, 3] float64 (as pymesh yields them), cloud_offsets [M+1] (prefix sums of V_m, device).
+ * For b < B: cloud cid = cloud_ids[b]; P of its V vertices are taken without replacement -- rows subset[b, :] when
+ * `subset` is given, else the first P images of the keyed Feistel permutation of [0, V) (key: Philox4x32-10 blocks
+ * 2s and 2s+1 of `seed`, s = offset + b; the chosen rows are written to subset_out when non-NULL) --, rotated about z by
+ * rotation_deg[b] degrees when that is non-zero (float64, point_cloud @ R^T), cast to float32, transposed to [3, P],
+ * shifted by the global minimum and divided by the global maximum of the shifted cloud.  out [B, 3, P] float32 in [0, 1].
+ * A cloud with fewer than P vertices (the reference raises) is filled with NaN.  P <= 8192.
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_pointcloud_sample(const double* vertices, const int64_t* cloud_offsets, const int64_t* cloud_ids,
+                            const float* rotation_deg, const int64_t* subset, uint64_t seed, uint64_t offset,
+                            int64_t B, int64_t P, float* out, int64_t* subset_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * PointNet encoder, eval-mode BatchNorm (the KD-time teacher, KD/common/base_class.py:317,363).
  * Replaces: ShapeEncoderPC.forward, auxiliary/model.py:174-180 (conv1/bn1/relu, conv2/bn2/relu,
  * conv3/bn3, max over points), BN folded into the weights by crdpn_pointnet_pack.
