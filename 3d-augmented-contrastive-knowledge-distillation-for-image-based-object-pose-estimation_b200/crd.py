@@ -29,8 +29,7 @@ from . import _native
 EPS = 1e-7
 
 
-def _stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+_stream_ptr = _native.stream_ptr
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -149,8 +148,8 @@ class _EmbedFunction(torch.autograd.Function):
 
 class _CRDLossFunction(torch.autograd.Function):
     """The whole CRD step as one autograd node and TWO foreign calls: ``crdpn_crd_loss_forward`` (embed heads ->
-    negative draw -> fused score/loss/backward -> reduction + momentum update, 7 launches) and
-    ``crdpn_crd_loss_backward`` (the two embed-head backwards, 5 launches).  Everything the step produces lives in one
+    negative draw -> fused score/loss/backward -> reduction + momentum update, 5 launches) and
+    ``crdpn_crd_loss_backward`` (both embed-head backwards, 2 launches).  Everything the step produces lives in one
     float32 arena ``[result(16) | pre_s | pre_t | v1 | v2 | grad_v1 | grad_v2 | inv1 | inv2]``; the upstream gradient
     of the loss is a device scalar folded into the embed backward, so no elementwise torch kernels run at all."""
 
@@ -158,16 +157,19 @@ class _CRDLossFunction(torch.autograd.Function):
     def forward(ctx, f_s, f_t, Ws, bs, Wt, bt, y, contrast_idx, crit):
         mem = crit.contrast
         dev = f_s.device
-        xs = f_s.detach().reshape(f_s.shape[0], -1).contiguous()
-        xt = f_t.detach().reshape(f_t.shape[0], -1).contiguous()
-        Wsc, bsc, Wtc, btc = Ws.detach().contiguous(), bs.detach().contiguous(), Wt.detach().contiguous(), bt.detach().contiguous()
+        xs, xt = f_s.detach(), f_t.detach()
+        if xs.dim() != 2 or not xs.is_contiguous():
+            xs = xs.reshape(xs.shape[0], -1).contiguous()
+        if xt.dim() != 2 or not xt.is_contiguous():
+            xt = xt.reshape(xt.shape[0], -1).contiguous()
+        Wsc, bsc, Wtc, btc = (t.detach() if t.is_contiguous() else t.detach().contiguous() for t in (Ws, bs, Wt, bt))
         B, D = xs.shape[0], Wsc.shape[0]
         hp = mem._host_params()
         K1 = hp.K + 1
         if xt.shape[0] != B or y.numel() != B:
             raise RuntimeError("f_s, f_t and idx must share the batch dimension")
         mem._check_device(y, "idx")
-        yc = y.contiguous().to(torch.int64)
+        yc = y if (y.dtype == torch.int64 and y.is_contiguous()) else y.contiguous().to(torch.int64)
         if contrast_idx is not None:
             mem._check_device(contrast_idx, "contrast_idx")
             contrast_idx = contrast_idx.contiguous().to(torch.int64)
@@ -378,7 +380,7 @@ class ContrastMemory(nn.Module):
         self._host = None
 
     def _banks(self):
-        m1, m2 = self.memory_v1, self.memory_v2
+        m1, m2 = self._buffers["memory_v1"], self._buffers["memory_v2"]
         if m1.stride(1) != 1 or m2.stride(1) != 1 or m1.stride(0) != m2.stride(0) or m1.dtype != m2.dtype:
             self._relayout()
             m1, m2 = self.memory_v1, self.memory_v2

@@ -8,6 +8,16 @@
 // from C, so the host cost of a step is two foreign calls.
 #include "common.cuh"
 
+namespace crdpn {  // embed_kernels.cu
+int embed_forward2(const float* xs, const float* Ws, const float* bs, int64_t s_dim, float* pre_s, float* v1, float* inv1,
+                   const float* xt, const float* Wt, const float* bt, int64_t t_dim, float* pre_t, float* v2, float* inv2,
+                   int64_t B, int64_t D, void* stream);
+int embed_backward2(const float* xs, int64_t s_dim, const float* Ws, const float* v1, const float* inv1, const float* g1,
+                    const float* xt, int64_t t_dim, const float* Wt, const float* v2, const float* inv2, const float* g2,
+                    const float* scale, int64_t B, int64_t D, float* dWs, float* dbs, float* dxs, float* dWt, float* dbt,
+                    float* dxt, float* d_pre, void* stream);
+}  // namespace crdpn
+
 using namespace crdpn;
 
 extern "C" int crdpn_crd_loss_forward(
@@ -22,9 +32,7 @@ extern "C" int crdpn_crd_loss_forward(
     double* result, float* grad_v1, float* grad_v2,
     void* workspace, size_t workspace_bytes, int variant, void* stream) {
   if (!y) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward: null y");
-  int rc = crdpn_embed_forward(f_s, Ws, bs, B, s_dim, D, pre_s, v1, inv1, stream);
-  if (rc) return rc;
-  rc = crdpn_embed_forward(f_t, Wt, bt, B, t_dim, D, pre_t, v2, inv2, stream);
+  int rc = embed_forward2(f_s, Ws, bs, s_dim, pre_s, v1, inv1, f_t, Wt, bt, t_dim, pre_t, v2, inv2, B, D, stream);
   if (rc) return rc;
   const int64_t* idx = contrast_idx;
   if (idx == nullptr) {
@@ -44,7 +52,6 @@ extern "C" int crdpn_crd_loss_backward(
     const float* scale, int64_t B, int64_t D,
     float* dWs, float* dbs, float* dxs, float* dWt, float* dbt, float* dxt, float* d_pre_scratch, void* stream) {
   if (!d_pre_scratch) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_backward: null scratch");
-  int rc = crdpn_embed_backward(f_s, Ws, v1, inv1, grad_v1, scale, B, s_dim, D, dWs, dbs, dxs, d_pre_scratch, stream);
-  if (rc) return rc;
-  return crdpn_embed_backward(f_t, Wt, v2, inv2, grad_v2, scale, B, t_dim, D, dWt, dbt, dxt, d_pre_scratch + B * D, stream);
+  return embed_backward2(f_s, s_dim, Ws, v1, inv1, grad_v1, f_t, t_dim, Wt, v2, inv2, grad_v2, scale, B, D, dWs, dbs, dxs, dWt,
+                         dbt, dxt, d_pre_scratch, stream);
 }

@@ -49,8 +49,7 @@ def _next_dropout_blocks(n_elem: int):
     return _stream_state["seed"], off
 
 
-def _stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+_stream_ptr = _native.stream_ptr
 
 
 def _f32_cuda(t: torch.Tensor, name: str) -> torch.Tensor:

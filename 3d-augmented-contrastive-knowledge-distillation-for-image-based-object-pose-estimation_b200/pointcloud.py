@@ -66,7 +66,7 @@ class PointCloudSampler:
             rc = _native.lib().crdpn_pointcloud_sample(
                 self.vertices.data_ptr(), self.offsets.data_ptr(), ids.data_ptr(), rot.data_ptr() if rot is not None else None,
                 sub.data_ptr() if sub is not None else None, self.seed, self.offset, B, P, out.data_ptr(),
-                sub_out.data_ptr() if sub_out is not None else None, torch.cuda.current_stream(dev).cuda_stream)
+                sub_out.data_ptr() if sub_out is not None else None, _native.stream_ptr(dev))
         _native.check(rc, "crdpn_pointcloud_sample")
         if sub is None:
             self.offset += B

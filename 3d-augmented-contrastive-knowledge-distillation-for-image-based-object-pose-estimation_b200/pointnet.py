@@ -72,7 +72,7 @@ class ShapeEncoderPC(nn.Module):
             ptrs = [t.detach().contiguous().data_ptr() for t in src]
             with _native.on_device(device):
                 rc = _native.lib().crdpn_pointnet_pack(*ptrs, BN_EPS, self.feature_dim, self._packed.data_ptr(),
-                                                       torch.cuda.current_stream(device).cuda_stream)
+                                                       _native.stream_ptr(device))
             _native.check(rc, "crdpn_pointnet_pack")
             self._packed_key = key
         return self._packed
@@ -95,7 +95,7 @@ class ShapeEncoderPC(nn.Module):
         with _native.on_device(dev):
             rc = _native.lib().crdpn_pointnet_forward_eval(x.data_ptr(), B, P, self.feature_dim, packed.data_ptr(),
                                                            out.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
-                                                           self.variant, torch.cuda.current_stream(dev).cuda_stream)
+                                                           self.variant, _native.stream_ptr(dev))
         _native.check(rc, "crdpn_pointnet_forward_eval")
         return out.view(-1, self.feature_dim)
 
@@ -160,7 +160,7 @@ class _PointNetTrainFunction(torch.autograd.Function):
         with _native.on_device(dev):
             rc = lib.crdpn_pointnet_forward_train(*args, float(module.bn1.eps), float(module.bn1.momentum),
                                                   out.data_ptr(), cptr, n.value, module.variant,
-                                                  torch.cuda.current_stream(dev).cuda_stream)
+                                                  _native.stream_ptr(dev))
         _native.check(rc, "crdpn_pointnet_forward_train")
         ctx.save_for_backward(x, *p)
         ctx.train_ctx = (owner, cptr, n.value)
@@ -186,7 +186,7 @@ class _PointNetTrainFunction(torch.autograd.Function):
                 x.data_ptr(), B, P, F, c1w.data_ptr(), c2w.data_ptr(), c3w.data_ptr(),
                 g1.data_ptr(), b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), g3.data_ptr(), b3.data_ptr(),
                 g.data_ptr(), cptr, cbytes, *[t.data_ptr() for t in grads], wptr, n.value,
-                torch.cuda.current_stream(dev).cuda_stream)
+                _native.stream_ptr(dev))
         _native.check(rc, "crdpn_pointnet_backward")
         del owner, ws_owner
         return (None, None, *grads)

@@ -193,8 +193,8 @@ def time_crd_e2e(pkg, torch, dev, c, steps, warmup, host_contrast_idx=False):
         f_s, f_t, y = dev_in[:3]
         cidx = dev_in[3] if host_contrast_idx else None
         f_s.requires_grad_()
-        crit.zero_grad(set_to_none=True)
         loss = crit(f_s, f_t, y, cidx)
+        crit.zero_grad(set_to_none=True)  # the reference's order: forward, zero_grad, backward (base_class.py:387-396)
         loss.backward()
         return loss.item()  # D2H read of the step's result
 

@@ -127,9 +127,9 @@ int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
 /* ---------------------------------------------------------------------------------------------------
  * The whole published CRDLoss.forward (crd/criterion.py: embed_s, embed_t, ContrastMemory.forward, the two
  * ContrastLoss terms) and its autograd backward, each as ONE call that enqueues every launch back to back:
- *   forward : crdpn_embed_forward x2 -> [crdpn_alias_draw_contrast when contrast_idx == NULL, into idx_scratch
- *             [B,K1] int64] -> crdpn_crd_step.  Same results, bit for bit, as the individual calls.
- *   backward: crdpn_embed_backward x2 (dxs / dxt may be NULL; d_pre_scratch holds 2*B*D floats).
+ *   forward : both embed heads (2 launches) -> [crdpn_alias_draw_contrast when contrast_idx == NULL, into idx_scratch
+ *             [B,K1] int64] -> crdpn_crd_step: 5 launches.  Same results, bit for bit, as the individual calls.
+ *   backward: both embed-head backwards in 2 launches (dxs / dxt may be NULL; d_pre_scratch holds 2*B*D floats).
  * This is what the reference's KD loop would call at KD/common/base_class.py:387 (forward) and :394 (backward);
  * the host cost of a step drops from ~30 foreign calls / allocations to two.
  * ------------------------------------------------------------------------------------------------- */
