@@ -55,6 +55,11 @@ class AliasMethod:
                                                       self.alias.data_ptr()), "crdpn_alias_build")
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self.offset = 0
+        # uniform unigrams build prob == 1 everywhere: the draw then never reads the tables (same indices, no gather)
+        self.uniform = bool((self.prob == 1.0).all())
+
+    def table_ptrs(self):
+        return (None, None) if self.uniform else (self.prob.data_ptr(), self.alias.data_ptr())
 
     def cuda(self, device=None):
         self.prob = self.prob.cuda(device)
@@ -70,7 +75,7 @@ class AliasMethod:
         _require_cuda(self.prob, "AliasMethod tables (call .cuda() first)")
         out = torch.empty(N, dtype=torch.int64, device=self.prob.device)
         with _native.on_device(self.prob.device):
-            _native.check(_native.lib().crdpn_alias_draw(self.prob.data_ptr(), self.alias.data_ptr(),
+            _native.check(_native.lib().crdpn_alias_draw(*self.table_ptrs(),
                                                          self.prob.numel(), N, self.seed, self.offset,
                                                          out.data_ptr(), _stream_ptr(self.prob.device)),
                           "crdpn_alias_draw")
@@ -84,7 +89,7 @@ class AliasMethod:
         B = y.numel()
         out = torch.empty(B, K1, dtype=torch.int64, device=self.prob.device)
         with _native.on_device(self.prob.device):
-            _native.check(_native.lib().crdpn_alias_draw_contrast(self.prob.data_ptr(), self.alias.data_ptr(),
+            _native.check(_native.lib().crdpn_alias_draw_contrast(*self.table_ptrs(),
                                                                   self.prob.numel(), y.data_ptr(), B, K1,
                                                                   self.seed, self.offset, out.data_ptr(),
                                                                   _stream_ptr(self.prob.device)),
@@ -212,7 +217,7 @@ class _CRDLossFunction(torch.autograd.Function):
             rc = _native.lib().crdpn_crd_loss_forward(
                 xs.data_ptr(), xs.shape[1], Wsc.data_ptr(), bsc.data_ptr(),
                 xt.data_ptr(), xt.shape[1], Wtc.data_ptr(), btc.data_ptr(),
-                yc.data_ptr(), cidx_ptr, smp.prob.data_ptr(), smp.alias.data_ptr(), smp.seed, smp.offset, scratch_ptr,
+                yc.data_ptr(), cidx_ptr, *smp.table_ptrs(), smp.seed, smp.offset, scratch_ptr,
                 m1.data_ptr(), m2.data_ptr(), stride, dt,
                 B, K1, D, mem.nLem, mem.k_total, mem.row_begin, mem.row_end,
                 hp.T, hp.Z1, hp.Z2, EPS, hp.m, 1.0 - hp.m,
@@ -312,6 +317,51 @@ class _FusedCRDFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         g1, g2 = ctx.saved_tensors
         return grad_out * g1, grad_out * g2, None, None, None
+
+
+class _ContrastOutFunction(torch.autograd.Function):
+    """The unfused published surface, differentiable: (v1, v2) -> (out_v1, out_v2) [B, K+1, 1] with the momentum update
+    as a side effect; backward = crdpn_crd_out_backward (gradients through the PRE-update rows, as the published code's
+    detached copy gives)."""
+
+    @staticmethod
+    def forward(ctx, v1, v2, y, idx, mem):
+        v1c, v2c = v1.detach(), v2.detach()
+        mem._freeze_z(v1c, v2c, idx)
+        hp = mem._host_params()
+        m1, m2, _, _ = mem._banks()
+        rows = mem.row_end - mem.row_begin
+        yl = (y - mem.row_begin).clamp_(0, max(rows - 1, 0))          # rows this shard does not own are never read back
+        old1, old2 = m1.index_select(0, yl).float().contiguous(), m2.index_select(0, yl).float().contiguous()
+        _, _, _, o1, o2 = mem._score(v1c, v2c, idx, hp.Z1, hp.Z2, want_out=True)
+        mem._update(v1c, v2c, y)
+        ctx.save_for_backward(old1, old2, y, idx, o1, o2)
+        ctx.mem = mem
+        return o1.unsqueeze(-1), o2.unsqueeze(-1)
+
+    @staticmethod
+    def backward(ctx, go1, go2):
+        old1, old2, y, idx, o1, o2 = ctx.saved_tensors
+        mem = ctx.mem
+        B, K1 = idx.shape
+        D = old1.shape[1]
+        dev = old1.device
+        m1, m2, stride, dt = mem._banks()
+        go1 = (torch.zeros_like(o1) if go1 is None else go1.reshape(B, K1).to(torch.float32)).contiguous()
+        go2 = (torch.zeros_like(o2) if go2 is None else go2.reshape(B, K1).to(torch.float32)).contiguous()
+        n = ctypes.c_size_t(0)
+        lib = _native.lib()
+        _native.check(lib.crdpn_crd_out_backward_workspace_bytes(B, K1, D, ctypes.byref(n)), "crdpn_crd_out_backward_workspace_bytes")
+        ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
+        g1 = torch.empty(B, D, dtype=torch.float32, device=dev)
+        g2 = torch.empty(B, D, dtype=torch.float32, device=dev)
+        with _native.on_device(dev):
+            rc = lib.crdpn_crd_out_backward(m1.data_ptr(), m2.data_ptr(), stride, dt, old1.data_ptr(), old2.data_ptr(),
+                                            y.data_ptr(), idx.data_ptr(), go1.data_ptr(), go2.data_ptr(), o1.data_ptr(),
+                                            o2.data_ptr(), B, K1, D, mem.row_begin, mem.row_end, mem._host_params().T,
+                                            g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _native.check(rc, "crdpn_crd_out_backward")
+        return g1, g2, None, None, None
 
 
 class ContrastMemory(nn.Module):
@@ -530,14 +580,11 @@ class ContrastMemory(nn.Module):
     def forward(self, v1, v2, y, idx=None):
         """Published surface: returns (out_v1, out_v2), each [B, K+1, 1], and updates the banks.
 
-        The outputs are produced by the same fused pass; they carry no autograd graph (use
-        ``fused_loss`` / ``CRDLoss`` for training, which is what the KD loop calls)."""
-        v1c, v2c, y, idx = self._prepare(v1.detach(), v2.detach(), y, idx)
-        self._freeze_z(v1c, v2c, idx)
-        hp = self._host_params()
-        _, _, _, o1, o2 = self._score(v1c, v2c, idx, hp.Z1, hp.Z2, want_out=True)
-        self._update(v1c, v2c, y)
-        return o1.unsqueeze(-1), o2.unsqueeze(-1)
+        The outputs come out of the same fused scoring pass and are differentiable w.r.t. v1 / v2
+        (``_ContrastOutFunction``), so ``ContrastLoss(out_v1) + ContrastLoss(out_v2)`` -- the published CRDLoss body --
+        trains as written; ``CRDLoss`` / ``fused_loss`` are the fast path (one pass instead of two)."""
+        v1c, v2c, y, idx = self._prepare(v1, v2, y, idx)
+        return _ContrastOutFunction.apply(v1c, v2c, y, idx, self)
 
 
 class CRDLoss(nn.Module):

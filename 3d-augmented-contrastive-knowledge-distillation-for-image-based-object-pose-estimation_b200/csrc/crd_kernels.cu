@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256) alias_draw_kernel(const float* __restrict
     const unsigned long long bits = ((unsigned long long)r[0] << 32) | (unsigned long long)r[1];
     const long long kk = (long long)__umul64hi(bits, (unsigned long long)n);
     const float u = (float)(r[2] >> 8) * 5.9604644775390625e-08f;
-    out[i] = (u < prob[kk]) ? kk : alias[kk];
+    out[i] = (prob == nullptr || u < prob[kk]) ? kk : alias[kk];  // prob == NULL: uniform tables (prob = 1 everywhere)
   }
 }
 
@@ -813,7 +813,7 @@ extern "C" int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_s
 
 static int alias_draw_impl(const float* prob, const int64_t* alias, int64_t n, int64_t count, uint64_t seed,
                            uint64_t offset, const int64_t* y, int64_t K1, int64_t* out, void* stream) {
-  if (!prob || !alias || !out || n <= 0 || count < 0) return fail(CRDPN_E_BADARG, "crdpn_alias_draw: bad argument");
+  if ((prob == nullptr) != (alias == nullptr) || !out || n <= 0 || count < 0) return fail(CRDPN_E_BADARG, "crdpn_alias_draw: bad argument");
   if (count == 0) return CRDPN_OK;
   int device = 0;
   CRDPN_CUDA(cudaGetDevice(&device));

@@ -10,7 +10,8 @@ the point cloud tripled (base_class.py:362), student = VGG-11 trunk -> 2048-d ->
 (model.py:183-272), loss = 0.25 CE + 0.75 sum_6 KL + 0.75 KL(features) (KD/vision/vanilla/vanilla_kd.py:143-164) + CRD.
 The CNN trunks are OUT OF SCOPE of this repo (cuDNN-bound stock convnets): torchvision's vgg11 / resnet50 with random
 weights stand in for auxiliary/vgg.py / resnet.py, which are torchvision-style copies.  Two arms are timed:
-  "dropin": crdpn ShapeEncoderPC (eval, fused kernel) + crdpn CRDLoss
+  "dropin": crdpn PointCloudSampler -> ShapeEncoderPC (eval, fused kernel), crdpn student_kd_step_loss (the step's CE /
+            delta / KL terms in one launch) + crdpn CRDLoss
   "eager" : the same step with the encoder as the reference runs it (nn.Conv1d/BatchNorm1d ops, teacher graph built,
             three identical copies of every cloud), and no CRD term (the reference has none)
 and the share of the step spent in the two hot-path kernels is reported from the library's own event timers.
@@ -115,22 +116,41 @@ def run_arm(torch, pkg, dev, dropin, steps, warmup):
     g = torch.Generator().manual_seed(46)
     im = [torch.randn(b, 3, 224, 224, generator=g).to(dev) for _ in range(3)]
     shapes = torch.rand(b, 3, 2500, generator=g).to(dev)
-    labels = [torch.randint(0, c, (3 * b,), generator=g).to(dev) for c in (24, 12, 24)]
+    label = torch.stack([torch.randint(0, r, (3 * b,), generator=g) for r in (360, 180, 360)], 1).to(dev)   # degrees
     idx = torch.randperm(N, generator=g)[:b].to(dev)
+    sampler = None
+    if dropin:  # the clouds come from the resident meshes through the batch producer (dataset.py:121-150 on the GPU)
+        import numpy as np
+        rng = np.random.default_rng(46)
+        sampler = pkg.PointCloudSampler([rng.normal(size=(int(v), 3)) for v in rng.integers(3000, 40000, 64)], 2500, dev, seed=46)
+        cloud_ids = torch.randint(0, 64, (b,), generator=g)
+        rotations = torch.randint(0, 360, (b,), generator=g).float()
+
+    def eager_losses(out, tout, sfeat, tfeat):
+        """the reference's loss code as it runs today: CELoss x3 + DeltaLoss (loss.py:7-34), calculate_kd_loss_new"""
+        tl = label // 15
+        ce = sum(F.cross_entropy(out[i], tl[:, i]) for i in range(3))
+        ar = torch.arange(out[3].size(0), device=dev)
+        lf = label.float()
+        tdelta = (lf % 15) / 15 - 0.5
+        pd = torch.cat([out[3 + i][ar, tl[:, i]].tanh().div(2).unsqueeze(1) for i in range(3)], 1)
+        gt = ce + F.smooth_l1_loss(5. * pd, 5. * tdelta)
+        return 0.25 * gt + 0.75 * sum(kl(o, t.detach()) for o, t in zip(out, tout)) + 0.75 * kl(sfeat, tfeat.detach())
 
     def step():
         x = torch.cat(im, 0)                                             # base_class.py:350-355 -> 138 images
         out, sfeat = student(x)                                          # :359
         if dropin:
             with torch.no_grad():                                        # the teacher is frozen: no graph, and the three
-                sf = teacher.shape_encoder(shapes).repeat(3, 1)          # copies of a cloud are encoded once (bit-identical)
+                clouds = sampler.sample(cloud_ids, rotations)            # copies of a cloud are encoded once (bit-identical)
+                sf = teacher.shape_encoder(clouds).repeat(3, 1)
                 tout, _, tfeat = teacher(x, shape_feature=sf)
+            # :365-387 in one launch (+1 backward): CE x3, delta term, KL x7, weights
+            loss = pkg.student_kd_step_loss(out, [t.detach() for t in tout], sfeat, tfeat.detach(), label)
+            loss = loss + 0.8 * crd(sfeat, tfeat.detach(), torch.cat([idx] * 3))
         else:
             tout, _, tfeat = teacher(x, torch.cat([shapes] * 3, 0))      # :362-363 as the reference runs it
-        ce = sum(F.cross_entropy(out[i], labels[i]) for i in range(3))   # :366-370 (Huber term on the deltas omitted)
-        loss = 0.25 * ce + 0.75 * sum(kl(o, t.detach()) for o, t in zip(out, tout)) + 0.75 * kl(sfeat, tfeat.detach())
-        if crd is not None:
-            loss = loss + 0.8 * crd(sfeat, tfeat.detach(), torch.cat([idx] * 3))
+            loss = eager_losses(out, tout, sfeat, tfeat)                 # :365-387 as the reference runs it
         optim.zero_grad(set_to_none=True)
         loss.backward()
         optim.step()

@@ -60,7 +60,8 @@ int crdpn_timing_read(int kernel_id, double* total_ms, uint64_t* launches);
  * ------------------------------------------------------------------------------------------------- */
 /* HOST pointers. Vose stack pairing in fp32; prob_out[n] fp32, alias_out[n] int64. */
 int crdpn_alias_build(const float* probs_host, int64_t n, float* prob_out_host, int64_t* alias_out_host);
-/* out[i] = draw(Philox4x32-10 block (seed, offset+i)), i < count. */
+/* out[i] = draw(Philox4x32-10 block (seed, offset+i)), i < count.  prob == alias == NULL means the uniform tables
+ * (prob[k] = 1 for all k, which is what uniform unigrams build): same indices, without the 4-byte gather per draw. */
 int crdpn_alias_draw(const float* prob, const int64_t* alias, int64_t n, int64_t count,
                      uint64_t seed, uint64_t offset, int64_t* out, void* stream);
 /* contrast_idx[B,K1]: as crdpn_alias_draw over B*K1 entries, then column 0 <- y[b]
@@ -149,6 +150,23 @@ int crdpn_crd_loss_backward(
     const float* f_t, int64_t t_dim, const float* Wt, const float* v2, const float* inv2, const float* grad_v2,
     const float* scale, int64_t B, int64_t D,
     float* dWs, float* dbs, float* dxs, float* dWt, float* dbt, float* dxt, float* d_pre_scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Backward of the UNFUSED published surface ContrastMemory.forward -> (out_v1, out_v2) (crd/memory.py), for callers that
+ * put their own criterion on the outputs (CRDLoss does not need it: crdpn_crd_step applies the closed-form NCE gradient in
+ * the scoring pass).  With upstream gradients grad_out_v1/2 [B,K1] and the forward's outputs out_v1/2 [B,K1]:
+ *   grad_v1[b] = sum_k grad_out_v1[b,k] out_v1[b,k] / T * bank2[idx[b,k]],  grad_v2[b] likewise with bank1.
+ * The published code differentiates through a detached COPY of the gathered rows, i.e. the banks BEFORE the momentum
+ * update of the same call: old_rows1/2 [B,D] f32 are the pre-update rows of y, substituted wherever a contrast index
+ * equals some y[j].  Entries outside [row_begin,row_end) are skipped.  feat_dim % 4 == 0, <= 512; B <= 1024.
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_crd_out_backward_workspace_bytes(int64_t B, int64_t K1, int64_t D, size_t* bytes);
+int crdpn_crd_out_backward(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
+                           const float* old_rows1, const float* old_rows2, const int64_t* y,
+                           const int64_t* contrast_idx, const float* grad_out_v1, const float* grad_out_v2,
+                           const float* out_v1, const float* out_v2, int64_t B, int64_t K1, int64_t D,
+                           int64_t row_begin, int64_t row_end, float T, float* grad_v1, float* grad_v2,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Momentum update of both banks (ContrastMemory.forward, torch.no_grad block: index_select, mul_, add_,

@@ -389,3 +389,66 @@ def test_fused_embed_head_matches_eager_linear_l2norm(pkg, cuda, B, dim_in, D):
     emb.zero_grad()
     emb(x).backward(g)
     assert ((emb.linear.weight.grad - want[2]).abs().max() / want[2].abs().max()).item() < 1e-4
+
+
+@pytest.mark.parametrize("dup", [False, True])
+def test_unfused_published_composition_is_differentiable(pkg, oracle, cuda, dup):
+    """ContrastLoss(ContrastMemory(v1, v2, y, idx)) -- the published CRDLoss body, written out -- gives the stock
+    formulation's loss AND gradients over two consecutive steps (the second step's contrast list deliberately hits rows
+    the first step's momentum update rewrote, and rows of its own positives, which the backward must see PRE-update)."""
+    from oracle.crd_oracle import StockCRD
+    opt = _opt()
+    torch.manual_seed(46)
+    crit = pkg.CRDLoss(opt).to(cuda)
+    stock = StockCRD(opt.s_dim, opt.t_dim, opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m)
+    with torch.no_grad():
+        crit.embed_s.linear.weight.copy_(stock.Ws); crit.embed_s.linear.bias.copy_(stock.bs)
+        crit.embed_t.linear.weight.copy_(stock.Wt); crit.embed_t.linear.bias.copy_(stock.bt)
+        crit.contrast.memory_v1.copy_(stock.memory_v1); crit.contrast.memory_v2.copy_(stock.memory_v2)
+    B = 24
+    y_prev = None
+    for step in range(2):
+        g = torch.Generator().manual_seed(300 + step)
+        f_s = torch.randn(B, opt.s_dim, generator=g)
+        f_t = torch.randn(B, opt.t_dim, generator=g)
+        y = torch.randperm(opt.n_data, generator=g)[:B]
+        if dup:
+            y[B // 2:] = y[:B // 2]                      # duplicate positives inside the batch
+        cidx = torch.randint(0, opt.n_data, (B, opt.nce_k + 1), generator=g)
+        cidx[:, 0] = y
+        cidx[:, 5] = y.roll(1)                           # negatives that are other anchors' positives (rewritten this step)
+        if y_prev is not None:
+            cidx[:, 7] = y_prev                          # rows rewritten by the previous step
+        y_prev = y
+        fs_d, ft_d = f_s.to(cuda).requires_grad_(), f_t.to(cuda).requires_grad_()
+        crit.zero_grad()
+        out_s, out_t = crit.contrast(crit.embed_s(fs_d), crit.embed_t(ft_d), y.to(cuda), cidx.to(cuda))
+        assert out_s.shape == (B, opt.nce_k + 1, 1) and out_s.requires_grad
+        loss = (crit.criterion_s(out_s) + crit.criterion_t(out_t)).squeeze()
+        (loss * 0.6).backward()
+        fs_c, ft_c = f_s.clone().requires_grad_(), f_t.clone().requires_grad_()
+        for p in (stock.Ws, stock.bs, stock.Wt, stock.bt):
+            p.grad = None
+        want = stock.loss(fs_c, ft_c, y, cidx)
+        (want * 0.6).backward()
+        assert _rel(loss.item(), want.item()) < REL32
+        assert _rel(fs_d.grad.cpu(), fs_c.grad) < REL32 and _rel(ft_d.grad.cpu(), ft_c.grad) < REL32
+        assert _rel(crit.embed_s.linear.weight.grad.cpu(), stock.Ws.grad) < REL32
+        assert _rel(crit.embed_t.linear.weight.grad.cpu(), stock.Wt.grad) < REL32
+        if not dup:  # (with duplicate positives torch's index_copy_ order is the oracle's "last wins" -- covered elsewhere)
+            assert _rel(crit.contrast.memory_v1.cpu(), stock.memory_v1) < 1e-6
+
+
+def test_alias_uniform_shortcut_draws_the_same_indices(pkg, oracle, cuda):
+    """Uniform unigrams build prob == 1: the draw skips the table gather and must yield the oracle's indices anyway;
+    a skewed distribution keeps using the tables."""
+    N = 5000
+    am = pkg.AliasMethod(torch.ones(N), seed=77).cuda()
+    assert am.uniform and am.table_ptrs() == (None, None)
+    got = am.draw(4096).cpu().numpy()
+    prob, alias = oracle.alias_build(np.ones(N, dtype=np.float32))
+    assert np.array_equal(got, oracle.alias_draw(prob, alias, 4096, 77, 0))
+    skew = pkg.AliasMethod(torch.arange(1, N + 1, dtype=torch.float32), seed=77).cuda()
+    assert not skew.uniform
+    prob, alias = oracle.alias_build(np.arange(1, N + 1, dtype=np.float32))
+    assert np.array_equal(skew.draw(4096).cpu().numpy(), oracle.alias_draw(prob, alias, 4096, 77, 0))
