@@ -87,6 +87,14 @@ _SIGNATURES = {
     "crdpn_pointnet_train_ctx_bytes": (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t)]),
     "crdpn_pointnet_forward_train": (c_int, [c_void_p, c_int64, c_int64, c_int64] + [c_void_p] * 21 +
                                      [c_float, c_float, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "crdpn_pointnet_forward_train_phased": (c_int, [c_void_p, c_int64, c_int64, c_int64] + [c_void_p] * 21 +
+                                            [c_float, c_float, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int64,
+                                             c_void_p]),
+    "crdpn_pointnet_backward_phased": (c_int, [c_void_p, c_int64, c_int64, c_int64] + [c_void_p] * 9 +
+                                       [c_void_p, c_void_p, c_size_t] + [c_void_p] * 12 +
+                                       [c_void_p, c_size_t, c_int, c_int, c_int64, c_void_p]),
+    "crdpn_pointnet_sync_blocks": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_int), POINTER(c_int),
+                                           POINTER(c_size_t), POINTER(c_int64), POINTER(c_int)]),
     "crdpn_pointnet_backward_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t)]),
     "crdpn_pointnet_backward": (c_int, [c_void_p, c_int64, c_int64, c_int64] + [c_void_p] * 9 +
                                 [c_void_p, c_void_p, c_size_t] + [c_void_p] * 12 + [c_void_p, c_size_t, c_void_p]),

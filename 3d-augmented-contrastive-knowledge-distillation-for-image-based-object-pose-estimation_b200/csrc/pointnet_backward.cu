@@ -928,7 +928,35 @@ extern "C" int crdpn_pointnet_backward_workspace_bytes(int64_t B, int64_t P, int
   return CRDPN_OK;
 }
 
-extern "C" int crdpn_pointnet_backward(
+namespace crdpn {
+namespace pn {
+int backward_sync_blocks(int F, int sync_point, int* n_blocks, int* buffer, size_t* byte_offset, int64_t* count, int* is_f64) {
+  const BwdWs W(F, 1);  // the offsets of the reduced blocks do not depend on the grid
+  auto put = [&](int i, int buf, size_t off, int64_t n, int f64) { buffer[i] = buf; byte_offset[i] = off; count[i] = n; is_f64[i] = f64; };
+  switch (sync_point) {
+    case 3:  // after phase 0: dgamma3 / dbeta3 partial sums, sum of h2, arg-max gather for dW3
+      put(0, 1, W.S2, 128, 1); put(1, 1, W.Gs, (int64_t)F * 128, 0); put(2, 2, 0, F, 0); put(3, 3, 0, F, 0);
+      *n_blocks = 4;
+      break;
+    case 4:  // after phase 1: layer-2 accumulators and the reduced second moments T2 | M2 | M1
+      put(0, 1, W.acc2, 256, 1); put(1, 1, W.red, kPartFloats, 0);
+      *n_blocks = 2;
+      break;
+    case 5:  // after phase 2: layer-1 accumulators
+      put(0, 1, W.acc1, 64 * 5, 1);
+      *n_blocks = 1;
+      break;
+    default: return fail(CRDPN_E_BADARG, "crdpn_pointnet_sync_blocks: sync_point must be 0..5");
+  }
+  return CRDPN_OK;
+}
+}  // namespace pn
+}  // namespace crdpn
+
+// Phases (a rank-synchronised run all-reduces the blocks of crdpn_pointnet_sync_blocks(3..5) between them):
+//   0: zero, BN3 reductions, sum of h2, arg-max gather      1: Q / u', dense pass 2, partial reduction
+//   2: covariances, BN2 terms, dense pass 3                  3: parameter gradients
+extern "C" int crdpn_pointnet_backward_phased(
     const float* x, int64_t B, int64_t P, int64_t F,
     const float* conv1_w, const float* conv2_w, const float* conv3_w,
     const float* bn1_w, const float* bn1_b, const float* bn2_w, const float* bn2_b,
@@ -936,8 +964,11 @@ extern "C" int crdpn_pointnet_backward(
     const float* grad_out, const void* ctx, size_t ctx_bytes,
     float* d_conv1_w, float* d_conv1_b, float* d_conv2_w, float* d_conv2_b, float* d_conv3_w, float* d_conv3_b,
     float* d_bn1_w, float* d_bn1_b, float* d_bn2_w, float* d_bn2_b, float* d_bn3_w, float* d_bn3_b,
-    void* workspace, size_t workspace_bytes, void* stream) {
+    void* workspace, size_t workspace_bytes, int phase_begin, int phase_end, int64_t total_points, void* stream) {
   (void)bn3_b;
+  if (phase_begin < 0 || phase_end > 4 || phase_begin >= phase_end || total_points < B * P)
+    return fail(CRDPN_E_BADARG, "crdpn_pointnet_backward: bad phase range / total_points");
+  auto on = [&](int ph) { return phase_begin <= ph && ph < phase_end; };
   if (!x || !conv1_w || !conv2_w || !conv3_w || !bn1_w || !bn1_b || !bn2_w || !bn2_b || !bn3_w || !grad_out || !ctx ||
       !d_conv1_w || !d_conv1_b || !d_conv2_w || !d_conv2_b || !d_conv3_w || !d_conv3_b || !d_bn1_w || !d_bn1_b ||
       !d_bn2_w || !d_bn2_b || !d_bn3_w || !d_bn3_b || !workspace)
@@ -955,7 +986,7 @@ extern "C" int crdpn_pointnet_backward(
   cudaStream_t st = (cudaStream_t)stream;
   const char* c = (const char*)ctx;
   char* w = (char*)workspace;
-  const double M = (double)B * (double)P;
+  const double M = (double)total_points;  // points of ALL ranks
   const float* stats = (const float*)(c + L.stats);
   const float* train_par = (const float*)(c + L.train_par);
   const int* argmax = (const int*)(c + L.argmax);
@@ -977,16 +1008,20 @@ extern "C" int crdpn_pointnet_backward(
     attr_set[device] = true;
   }
 
-  CRDPN_CUDA(cudaMemsetAsync(w + W.zero_begin, 0, W.zero_end - W.zero_begin, st));
-  pn::pn_bwd_l3_reduce_kernel<<<(int)((F + 7) / 8), 256, 0, st>>>(grad_out, yhat3, (int)B, (int)F, d_bn3_w, d_bn3_b);
-  CRDPN_LAUNCH_CHECK("pn_bwd_l3_reduce_kernel");
-  pn::pn_h2_colsum_kernel<<<grid * 4, 256, 0, st>>>(h2img, (int)B, (int)P, L.tiles2, S2);
-  CRDPN_LAUNCH_CHECK("pn_h2_colsum_kernel");
-  pn::QParams qp{conv3_w, bn3_w, d_bn3_w, d_bn3_b, stats, conv2_w, bn2_w, S2, M, (int)F, w + W.qimg, w + W.w2timg, vec};
-  pn::pn_bwd_q_kernel<<<129, 128, 0, st>>>(qp);
-  CRDPN_LAUNCH_CHECK("pn_bwd_q_kernel");
-  pn::pn_bwd_gs_kernel<<<(int)F, 256, 0, st>>>(grad_out, argmax, h2img, (int)B, (int)F, L.tiles2, Gs);
-  CRDPN_LAUNCH_CHECK("pn_bwd_gs_kernel");
+  if (on(0)) {
+    CRDPN_CUDA(cudaMemsetAsync(w + W.zero_begin, 0, W.zero_end - W.zero_begin, st));
+    pn::pn_bwd_l3_reduce_kernel<<<(int)((F + 7) / 8), 256, 0, st>>>(grad_out, yhat3, (int)B, (int)F, d_bn3_w, d_bn3_b);
+    CRDPN_LAUNCH_CHECK("pn_bwd_l3_reduce_kernel");
+    pn::pn_h2_colsum_kernel<<<grid * 4, 256, 0, st>>>(h2img, (int)B, (int)P, L.tiles2, S2);
+    CRDPN_LAUNCH_CHECK("pn_h2_colsum_kernel");
+    pn::pn_bwd_gs_kernel<<<(int)F, 256, 0, st>>>(grad_out, argmax, h2img, (int)B, (int)F, L.tiles2, Gs);
+    CRDPN_LAUNCH_CHECK("pn_bwd_gs_kernel");
+  }
+  if (on(1)) {
+    pn::QParams qp{conv3_w, bn3_w, d_bn3_w, d_bn3_b, stats, conv2_w, bn2_w, S2, M, (int)F, w + W.qimg, w + W.w2timg, vec};
+    pn::pn_bwd_q_kernel<<<129, 128, 0, st>>>(qp);
+    CRDPN_LAUNCH_CHECK("pn_bwd_q_kernel");
+  }
 
   pn::Pass2Params p2;
   p2.x = x; p2.B = (int)B; p2.P = (int)P; p2.F = (int)F;
@@ -997,22 +1032,42 @@ extern "C" int crdpn_pointnet_backward(
   p2.train_par = train_par; p2.qimg = w + W.qimg; p2.w2timg = w + W.w2timg; p2.vec = vec;
   p2.acc2 = acc2; p2.acc1 = acc1; p2.part = (float*)(w + W.part);
   p2.debug = getenv("CRDPN_PN_DEBUG") ? 1 : 0;
-  pn::pn_bwd_pass2_kernel<<<grid, 256, pn::kP2Smem, st>>>(p2);
-  CRDPN_LAUNCH_CHECK("pn_bwd_pass2_kernel");
-  pn::pn_bwd_reduce_partials_kernel<<<(pn::kPartFloats + 255) / 256, 256, 0, st>>>((const float*)(w + W.part), grid, red);
-  CRDPN_LAUNCH_CHECK("pn_bwd_reduce_partials_kernel");
-  pn::pn_bwd_cov_kernel<<<(128 * 128 + 64 * 64 + 192 + 255) / 256, 256, 0, st>>>(red, S2, M, (float*)(w + W.cov));
-  CRDPN_LAUNCH_CHECK("pn_bwd_cov_kernel");
-  pn::MidParams mp{conv2_w, bn2_w, stats, acc2, red, (const float*)(w + W.cov), M, w + W.q1img, vec, d_bn2_w, d_bn2_b};
-  pn::pn_bwd_mid_kernel<<<64, 64, 0, st>>>(mp);
-  CRDPN_LAUNCH_CHECK("pn_bwd_mid_kernel");
-  pn::Pass3Params p3{x, (int)B, (int)P, L.tiles2, p2.nA, train_par, w + W.q1img, vec, acc1};
-  pn::pn_bwd_pass3_kernel<<<grid, 256, pn::kP3Smem, st>>>(p3);
-  CRDPN_LAUNCH_CHECK("pn_bwd_pass3_kernel");
+  if (on(1)) {
+    pn::pn_bwd_pass2_kernel<<<grid, 256, pn::kP2Smem, st>>>(p2);
+    CRDPN_LAUNCH_CHECK("pn_bwd_pass2_kernel");
+    pn::pn_bwd_reduce_partials_kernel<<<(pn::kPartFloats + 255) / 256, 256, 0, st>>>((const float*)(w + W.part), grid, red);
+    CRDPN_LAUNCH_CHECK("pn_bwd_reduce_partials_kernel");
+  }
+  if (on(2)) {
+    pn::pn_bwd_cov_kernel<<<(128 * 128 + 64 * 64 + 192 + 255) / 256, 256, 0, st>>>(red, S2, M, (float*)(w + W.cov));
+    CRDPN_LAUNCH_CHECK("pn_bwd_cov_kernel");
+    pn::MidParams mp{conv2_w, bn2_w, stats, acc2, red, (const float*)(w + W.cov), M, w + W.q1img, vec, d_bn2_w, d_bn2_b};
+    pn::pn_bwd_mid_kernel<<<64, 64, 0, st>>>(mp);
+    CRDPN_LAUNCH_CHECK("pn_bwd_mid_kernel");
+    pn::Pass3Params p3{x, (int)B, (int)P, L.tiles2, p2.nA, train_par, w + W.q1img, vec, acc1};
+    pn::pn_bwd_pass3_kernel<<<grid, 256, pn::kP3Smem, st>>>(p3);
+    CRDPN_LAUNCH_CHECK("pn_bwd_pass3_kernel");
+  }
+  if (!on(3)) return CRDPN_OK;
   pn::FinalParams fp{conv1_w, conv2_w, conv3_w, bn1_w, bn1_b, bn2_w, bn3_w, stats, S2, acc2, acc1, (const double*)(c + L.xstat),
                      red, (const float*)(w + W.cov), Gs, M, (int)F, d_bn3_w, d_bn3_b, d_bn2_w,
                      d_conv1_w, d_conv1_b, d_conv2_w, d_conv2_b, d_conv3_w, d_conv3_b, d_bn1_w, d_bn1_b};
   pn::pn_bwd_final_kernel<<<(int)F + 129, 128, 0, st>>>(fp);
   CRDPN_LAUNCH_CHECK("pn_bwd_final_kernel");
   return CRDPN_OK;
+}
+
+extern "C" int crdpn_pointnet_backward(
+    const float* x, int64_t B, int64_t P, int64_t F,
+    const float* conv1_w, const float* conv2_w, const float* conv3_w,
+    const float* bn1_w, const float* bn1_b, const float* bn2_w, const float* bn2_b,
+    const float* bn3_w, const float* bn3_b,
+    const float* grad_out, const void* ctx, size_t ctx_bytes,
+    float* d_conv1_w, float* d_conv1_b, float* d_conv2_w, float* d_conv2_b, float* d_conv3_w, float* d_conv3_b,
+    float* d_bn1_w, float* d_bn1_b, float* d_bn2_w, float* d_bn2_b, float* d_bn3_w, float* d_bn3_b,
+    void* workspace, size_t workspace_bytes, void* stream) {
+  return crdpn_pointnet_backward_phased(x, B, P, F, conv1_w, conv2_w, conv3_w, bn1_w, bn1_b, bn2_w, bn2_b, bn3_w, bn3_b, grad_out,
+                                        ctx, ctx_bytes, d_conv1_w, d_conv1_b, d_conv2_w, d_conv2_b, d_conv3_w, d_conv3_b,
+                                        d_bn1_w, d_bn1_b, d_bn2_w, d_bn2_b, d_bn3_w, d_bn3_b, workspace, workspace_bytes, 0, 4,
+                                        B * P, stream);
 }

@@ -341,14 +341,20 @@ extern "C" int crdpn_pointnet_train_ctx_bytes(int64_t B, int64_t P, int64_t F, s
   return CRDPN_OK;
 }
 
-extern "C" int crdpn_pointnet_forward_train(
+// Phases (a rank-synchronised run all-reduces the named accumulators between them; see crdpn_pointnet_sync_blocks):
+//   0: zero, x moments, operand images            -> sum over ranks: xmom
+//   1: BN1 fold, layer-2 statistics pass          -> sum over ranks: sum2 | sq2
+//   2: BN2 fold, fused forward                    -> sum over ranks: sum3 | sq3
+//   3: BN3 statistics -> output, running stats
+extern "C" int crdpn_pointnet_forward_train_phased(
     const float* x, int64_t B, int64_t P, int64_t F,
     const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
     const float* conv3_w, const float* conv3_b,
     const float* bn1_w, const float* bn1_b, float* bn1_mean, float* bn1_var, int64_t* bn1_nbt,
     const float* bn2_w, const float* bn2_b, float* bn2_mean, float* bn2_var, int64_t* bn2_nbt,
     const float* bn3_w, const float* bn3_b, float* bn3_mean, float* bn3_var, int64_t* bn3_nbt,
-    float bn_eps, float bn_momentum, float* out, void* ctx, size_t ctx_bytes, int variant, void* stream) {
+    float bn_eps, float bn_momentum, float* out, void* ctx, size_t ctx_bytes, int variant,
+    int phase_begin, int phase_end, int64_t total_points, void* stream) {
   if (!x || !conv1_w || !conv1_b || !conv2_w || !conv2_b || !conv3_w || !conv3_b || !bn1_w || !bn1_b || !bn1_mean ||
       !bn1_var || !bn1_nbt || !bn2_w || !bn2_b || !bn2_mean || !bn2_var || !bn2_nbt || !bn3_w || !bn3_b || !bn3_mean ||
       !bn3_var || !bn3_nbt || !out || !ctx)
@@ -368,7 +374,10 @@ extern "C" int crdpn_pointnet_forward_train(
   if (di.max_smem_optin < (int)pn::kSmemAlloc) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet_forward_train: not enough shared memory");
   cudaStream_t st = (cudaStream_t)stream;
   char* c = (char*)ctx;
-  const double M = (double)B * (double)P;
+  if (phase_begin < 0 || phase_end > 4 || phase_begin >= phase_end || total_points < B * P)
+    return fail(CRDPN_E_BADARG, "crdpn_pointnet_forward_train: bad phase range / total_points");
+  auto on = [&](int ph) { return phase_begin <= ph && ph < phase_end; };
+  const double M = (double)total_points;  // points of ALL ranks: the batch the statistics are taken over
   double* xmom = (double*)(c + L.xmom);
   double* sum2 = (double*)(c + L.sum2);
   double* sq2 = (double*)(c + L.sq2);
@@ -377,20 +386,24 @@ extern "C" int crdpn_pointnet_forward_train(
   float* stats = (float*)(c + L.stats);
   float* train_par = (float*)(c + L.train_par);
 
-  CRDPN_CUDA(cudaMemsetAsync(c + L.zero_begin, 0, L.zero_end - L.zero_begin, st));
-  pn::pn_xmoments_kernel<<<di.sms * 2, 256, 0, st>>>(x, (int)B, (int)P, xmom);
-  CRDPN_LAUNCH_CHECK("pn_xmoments_kernel");
-  pn::pn_pack_train_kernel<<<di.sms, 256, 0, st>>>(conv2_w, conv3_w, bn3_w, (int)F, c + L.packed);
-  CRDPN_LAUNCH_CHECK("pn_pack_train_kernel");
+  if (on(0)) {
+    CRDPN_CUDA(cudaMemsetAsync(c + L.zero_begin, 0, L.zero_end - L.zero_begin, st));
+    pn::pn_xmoments_kernel<<<di.sms * 2, 256, 0, st>>>(x, (int)B, (int)P, xmom);
+    CRDPN_LAUNCH_CHECK("pn_xmoments_kernel");
+    pn::pn_pack_train_kernel<<<di.sms, 256, 0, st>>>(conv2_w, conv3_w, bn3_w, (int)F, c + L.packed);
+    CRDPN_LAUNCH_CHECK("pn_pack_train_kernel");
+  }
   pn::Fold1Params f1{conv1_w, conv1_b, bn1_w, bn1_b, bn1_mean, bn1_var, (long long*)bn1_nbt, (long long*)bn2_nbt,
                      (long long*)bn3_nbt, xmom, M, bn_eps, bn_momentum, stats, train_par, (double*)(c + L.xstat)};
-  pn::pn_fold1_kernel<<<1, 64, 0, st>>>(f1);
-  CRDPN_LAUNCH_CHECK("pn_fold1_kernel");
+  if (on(1)) {
+    pn::pn_fold1_kernel<<<1, 64, 0, st>>>(f1);
+    CRDPN_LAUNCH_CHECK("pn_fold1_kernel");
+  }
 
   const int tiles_per_cloud = (int)((P + pn::kUnitPts - 1) / pn::kUnitPts);
   const int total_units = (int)B * tiles_per_cloud;
   const int grid = total_units < di.sms ? total_units : di.sms;
-  {
+  if (on(1)) {
     static bool attr_set[64] = {false};
     if (!attr_set[device]) {
       CRDPN_CUDA(cudaFuncSetAttribute(pn::pn_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn::kS2Smem));
@@ -401,8 +414,10 @@ extern "C" int crdpn_pointnet_forward_train(
     CRDPN_LAUNCH_CHECK("pn_stats2_kernel");
   }
   pn::Fold2Params f2{conv2_b, bn2_w, bn2_b, bn2_mean, bn2_var, sum2, sq2, M, bn_eps, bn_momentum, stats, train_par};
-  pn::pn_fold2_kernel<<<1, 128, 0, st>>>(f2);
-  CRDPN_LAUNCH_CHECK("pn_fold2_kernel");
+  if (on(2)) {
+    pn::pn_fold2_kernel<<<1, 128, 0, st>>>(f2);
+    CRDPN_LAUNCH_CHECK("pn_fold2_kernel");
+  }
 
   pn::FwdParams fp;
   fp.x = x; fp.B = (int)B; fp.P = (int)P; fp.F = (int)F;
@@ -417,13 +432,51 @@ extern "C" int crdpn_pointnet_forward_train(
   fp.enc64 = (unsigned long long*)(c + L.enc64);
   fp.sum3 = sum3;
   fp.sq3 = sq3;
-  rc = pn::launch_fwd(fp, grid, st);
-  if (rc) return rc;
+  if (on(2)) {
+    rc = pn::launch_fwd(fp, grid, st);
+    if (rc) return rc;
+  }
 
   pn::FinalizeParams fz{(const unsigned long long*)(c + L.enc64), sum3, sq3, conv3_b, bn3_w, bn3_b, bn3_mean, bn3_var,
                         M, bn_eps, bn_momentum, (int)B, (int)F, stats, (int*)(c + L.argmax), (float*)(c + L.yhat3), out};
   const int n = (int)(B * F);
-  pn::pn_train_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(fz);
-  CRDPN_LAUNCH_CHECK("pn_train_finalize_kernel");
+  if (on(3)) {
+    pn::pn_train_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(fz);
+    CRDPN_LAUNCH_CHECK("pn_train_finalize_kernel");
+  }
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_pointnet_forward_train(
+    const float* x, int64_t B, int64_t P, int64_t F,
+    const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+    const float* conv3_w, const float* conv3_b,
+    const float* bn1_w, const float* bn1_b, float* bn1_mean, float* bn1_var, int64_t* bn1_nbt,
+    const float* bn2_w, const float* bn2_b, float* bn2_mean, float* bn2_var, int64_t* bn2_nbt,
+    const float* bn3_w, const float* bn3_b, float* bn3_mean, float* bn3_var, int64_t* bn3_nbt,
+    float bn_eps, float bn_momentum, float* out, void* ctx, size_t ctx_bytes, int variant, void* stream) {
+  return crdpn_pointnet_forward_train_phased(x, B, P, F, conv1_w, conv1_b, conv2_w, conv2_b, conv3_w, conv3_b, bn1_w, bn1_b,
+                                             bn1_mean, bn1_var, bn1_nbt, bn2_w, bn2_b, bn2_mean, bn2_var, bn2_nbt, bn3_w,
+                                             bn3_b, bn3_mean, bn3_var, bn3_nbt, bn_eps, bn_momentum, out, ctx, ctx_bytes,
+                                             variant, 0, 4, B * P, stream);
+}
+
+// Accumulators a rank-synchronised (SyncBN-style) run must SUM over ranks after forward phase 0 / 1 / 2 (sync points
+// 0..2) and backward phase 0 / 1 / 2 (sync points 3..5).  buffer: 0 = train ctx, 1 = backward workspace, 2 = d_bn3_w,
+// 3 = d_bn3_b (the caller's gradient outputs, F floats each).
+extern "C" int crdpn_pointnet_sync_blocks(int64_t B, int64_t P, int64_t F, int sync_point, int* n_blocks, int* buffer,
+                                          size_t* byte_offset, int64_t* count, int* is_f64) {
+  if (!n_blocks || !buffer || !byte_offset || !count || !is_f64 || B <= 0 || P <= 0)
+    return fail(CRDPN_E_BADARG, "crdpn_pointnet_sync_blocks: bad argument");
+  if (!pn::pointnet_f_ok(F)) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet: feature_dim must be 128, 256, 512 or 1024");
+  const pn::TrainCtx L((int)B, (int)P, (int)F);
+  auto put = [&](int i, int buf, size_t off, int64_t n, int f64) { buffer[i] = buf; byte_offset[i] = off; count[i] = n; is_f64[i] = f64; };
+  switch (sync_point) {
+    case 0: put(0, 0, L.xmom, 16, 1); *n_blocks = 1; break;
+    case 1: put(0, 0, L.sum2, 256, 1); *n_blocks = 1; break;                 // sum2 | sq2 are adjacent
+    case 2: put(0, 0, L.sum3, 2 * F, 1); *n_blocks = 1; break;               // sum3 | sq3 are adjacent
+    case 3: case 4: case 5: return pn::backward_sync_blocks((int)F, sync_point, n_blocks, buffer, byte_offset, count, is_f64);
+    default: return fail(CRDPN_E_BADARG, "crdpn_pointnet_sync_blocks: sync_point must be 0..5");
+  }
   return CRDPN_OK;
 }

@@ -51,5 +51,8 @@ struct TrainCtx {
   }
 };
 
+// pointnet_backward.cu: sum-over-ranks blocks of the backward workspace (sync points 3..5)
+int backward_sync_blocks(int F, int sync_point, int* n_blocks, int* buffer, size_t* byte_offset, int64_t* count, int* is_f64);
+
 }  // namespace pn
 }  // namespace crdpn

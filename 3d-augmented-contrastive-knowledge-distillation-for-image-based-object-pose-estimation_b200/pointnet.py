@@ -44,6 +44,7 @@ class ShapeEncoderPC(nn.Module):
         self.bn3 = torch.nn.BatchNorm1d(feature_dim)
         self.feature_dim = feature_dim
         self.variant = 0
+        self._sync = None   # (process group, world size) once sync_batchnorm() is called
         self._packed = None
         self._packed_key = None
         self._ws = None
@@ -113,6 +114,17 @@ class ShapeEncoderPC(nn.Module):
                 self.conv3.bias, self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias,
                 self.bn3.weight, self.bn3.bias]
 
+    def sync_batchnorm(self, group=None, enabled: bool = True):
+        """Train-mode statistics over the clouds of ALL ranks of `group` (SyncBN-style).
+
+        Forward and backward then run in phases with a sum over ranks of the per-channel accumulators in between
+        (``crdpn_pointnet_sync_blocks``: <= 2F doubles per hand-off, three hand-offs each way).  The parameter gradients
+        returned on every rank are the gradients of the SUM over ranks of the local losses and are identical on all
+        ranks -- do not average them again (no DDP wrapper); scale the loss by 1/world_size for a global mean."""
+        import torch.distributed as dist
+        self._sync = (group, dist.get_world_size(group)) if enabled else None
+        return self
+
     def forward_train(self, shapes: torch.Tensor) -> torch.Tensor:
         """Batch-statistics BatchNorm forward (``training.py:30,47``); differentiable w.r.t. the 12 parameters
         (``training.py:75``); running statistics and ``num_batches_tracked`` are updated in place."""
@@ -132,6 +144,31 @@ def _aligned(nbytes: int, device) -> tuple[torch.Tensor, int]:
     """A uint8 buffer with a 1024-byte aligned start; returns (owner tensor, aligned pointer)."""
     buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
     return buf, (buf.data_ptr() + 1023) & ~1023
+
+
+def _global_points(local_points: int, device, group) -> int:
+    import torch.distributed as dist
+    t = torch.tensor([local_points], dtype=torch.int64, device=device)
+    dist.all_reduce(t, group=group)
+    return int(t.item())
+
+
+def _sum_over_ranks(lib, dims, sync_point: int, group, buffers) -> None:
+    """All-reduce (SUM) the accumulators named by crdpn_pointnet_sync_blocks(sync_point).  `buffers`: id -> (owner
+    tensor, base pointer); the blocks are viewed in place through the owner's storage, so the collective runs on the
+    kernels' own memory on the current stream."""
+    import torch.distributed as dist
+    nb = ctypes.c_int(0)
+    buf, off, cnt, f64 = (ctypes.c_int * 4)(), (ctypes.c_size_t * 4)(), (ctypes.c_int64 * 4)(), (ctypes.c_int * 4)()
+    _native.check(lib.crdpn_pointnet_sync_blocks(*dims, sync_point, ctypes.byref(nb), buf, off, cnt, f64), "crdpn_pointnet_sync_blocks")
+    for i in range(nb.value):
+        owner, base = buffers[buf[i]]
+        flat = owner.view(-1)
+        start = base - flat.data_ptr() + off[i]                      # byte offset inside the owner tensor
+        esz = flat.element_size()
+        nbytes = cnt[i] * (8 if f64[i] else 4)
+        view = flat[start // esz:(start + nbytes) // esz].view(torch.float64 if f64[i] else torch.float32)
+        dist.all_reduce(view, group=group)
 
 
 class _PointNetTrainFunction(torch.autograd.Function):
@@ -157,14 +194,28 @@ class _PointNetTrainFunction(torch.autograd.Function):
         for i, bn in enumerate(bns):
             args += [p[6 + 2 * i].data_ptr(), p[7 + 2 * i].data_ptr(), bn.running_mean.data_ptr(),
                      bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr()]
+        sync = module._sync
+        total = B * P
+        if sync is not None:
+            total = _global_points(B * P, dev, sync[0])
         with _native.on_device(dev):
-            rc = lib.crdpn_pointnet_forward_train(*args, float(module.bn1.eps), float(module.bn1.momentum),
-                                                  out.data_ptr(), cptr, n.value, module.variant,
-                                                  _native.stream_ptr(dev))
-        _native.check(rc, "crdpn_pointnet_forward_train")
+            if sync is None:
+                rc = lib.crdpn_pointnet_forward_train(*args, float(module.bn1.eps), float(module.bn1.momentum),
+                                                      out.data_ptr(), cptr, n.value, module.variant,
+                                                      _native.stream_ptr(dev))
+                _native.check(rc, "crdpn_pointnet_forward_train")
+            else:
+                for ph in range(4):
+                    rc = lib.crdpn_pointnet_forward_train_phased(*args, float(module.bn1.eps), float(module.bn1.momentum),
+                                                                 out.data_ptr(), cptr, n.value, module.variant, ph, ph + 1,
+                                                                 total, _native.stream_ptr(dev))
+                    _native.check(rc, "crdpn_pointnet_forward_train_phased")
+                    if ph < 3:
+                        _sum_over_ranks(lib, (B, P, F), ph, sync[0], {0: (owner, cptr)})
         ctx.save_for_backward(x, *p)
         ctx.train_ctx = (owner, cptr, n.value)
         ctx.dims = (B, P, F)
+        ctx.sync = (sync, total)
         return out
 
     @staticmethod
@@ -181,12 +232,20 @@ class _PointNetTrainFunction(torch.autograd.Function):
         ws_owner, wptr = _aligned(n.value, dev)
         grads = [torch.empty_like(t) for t in p]
         c1w, c1b, c2w, c2b, c3w, c3b, g1, b1, g2, b2, g3, b3 = p
+        sync, total = ctx.sync
+        bargs = (x.data_ptr(), B, P, F, c1w.data_ptr(), c2w.data_ptr(), c3w.data_ptr(),
+                 g1.data_ptr(), b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), g3.data_ptr(), b3.data_ptr(),
+                 g.data_ptr(), cptr, cbytes, *[t.data_ptr() for t in grads], wptr, n.value)
         with _native.on_device(dev):
-            rc = lib.crdpn_pointnet_backward(
-                x.data_ptr(), B, P, F, c1w.data_ptr(), c2w.data_ptr(), c3w.data_ptr(),
-                g1.data_ptr(), b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), g3.data_ptr(), b3.data_ptr(),
-                g.data_ptr(), cptr, cbytes, *[t.data_ptr() for t in grads], wptr, n.value,
-                _native.stream_ptr(dev))
-        _native.check(rc, "crdpn_pointnet_backward")
+            if sync is None:
+                rc = lib.crdpn_pointnet_backward(*bargs, _native.stream_ptr(dev))
+                _native.check(rc, "crdpn_pointnet_backward")
+            else:
+                for ph in range(4):
+                    rc = lib.crdpn_pointnet_backward_phased(*bargs, ph, ph + 1, total, _native.stream_ptr(dev))
+                    _native.check(rc, "crdpn_pointnet_backward_phased")
+                    if ph < 3:
+                        _sum_over_ranks(lib, (B, P, F), 3 + ph, sync[0],
+                                        {1: (ws_owner, wptr), 2: (grads[10], grads[10].data_ptr()), 3: (grads[11], grads[11].data_ptr())})
         del owner, ws_owner
         return (None, None, *grads)

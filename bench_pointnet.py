@@ -56,10 +56,41 @@ def bench_pointnet_replicas(pkg, torch, dist, dev, rank, world, steps, warmup, B
     ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
-    return {"workload": f"pointnet_eval_B{B}_P{P}_3-64-128-{F}_bf16_replicas{world}", "metric": "pointnet_points_per_sec",
-            "value": world * B * P / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "scaling": "weak",
-            "tflops_all_ranks": world * FLOP_PER_POINT * B * P / (ms * 1e-3) / 1e12,
-            "note": "replicas only: one batch of clouds per rank, no collective (clouds are independent in eval mode)"}
+    res = {"workload": f"pointnet_eval_B{B}_P{P}_3-64-128-{F}_bf16_replicas{world}", "metric": "pointnet_points_per_sec",
+           "value": world * B * P / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "scaling": "weak",
+           "tflops_all_ranks": world * FLOP_PER_POINT * B * P / (ms * 1e-3) / 1e12,
+           "note": "replicas only: one batch of clouds per rank, no collective (clouds are independent in eval mode)"}
+    # train mode over all ranks: batch statistics of the GLOBAL batch (sync_batchnorm), gradients summed over ranks
+    try:
+        tr = pkg.ShapeEncoderPC(F)
+        tr.load_state_dict(synthetic_state(torch, F))
+        tr = tr.to(dev).train().sync_batchnorm()
+        gout = torch.randn(B, F, device=dev)
+
+        def step():
+            for p_ in tr.parameters():
+                p_.grad = None
+            tr(x).backward(gout)
+
+        for _ in range(max(warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        tms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        res["train_sync_batchnorm"] = {"ms_per_step": tms.item(), "points_per_sec": world * B * P / (tms.item() * 1e-3),
+                                       "exchanges_per_step": 6 + 1,
+                                       "note": "forward+backward, per-channel accumulators summed over ranks at 3+3 hand-offs "
+                                               "(NCCL all-reduce of <= 2F doubles; the gradients come out globally summed)"}
+    except Exception as exc:
+        res["train_sync_batchnorm"] = {"error": str(exc)}
+    return res
 
 
 def bench_pointnet(pkg, torch, dev, args, tf_peak, peak_kind, B=160, P=2500, F=1024):

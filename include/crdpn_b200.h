@@ -324,6 +324,37 @@ int crdpn_pointnet_backward(
     float* d_bn1_w, float* d_bn1_b, float* d_bn2_w, float* d_bn2_b, float* d_bn3_w, float* d_bn3_b,
     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Rank-synchronised (SyncBN-style) PointNet training over several GPUs (no counterpart in the
+ * single-GPU reference).  The *_phased variants run phases [phase_begin, phase_end) of the same launch sequence as
+ * crdpn_pointnet_forward_train / crdpn_pointnet_backward (which are phases 0..4 with total_points = B*P) and take the
+ * number of points of ALL ranks, over which the batch statistics are defined.  Between phase k and k+1 (k = 0, 1, 2) the
+ * caller SUMS over ranks the accumulators that crdpn_pointnet_sync_blocks(sync_point = k for the forward, 3 + k for the
+ * backward) names: buffer 0 = train ctx, 1 = backward workspace, 2 = d_bn3_w, 3 = d_bn3_b; byte offset, element count and
+ * float64 flag per block (at most 4 blocks).  Every rank then holds the statistics of the global batch, and the parameter
+ * gradients come out already summed over ranks (identical on every rank): no separate gradient all-reduce.
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_pointnet_sync_blocks(int64_t B, int64_t P, int64_t F, int sync_point, int* n_blocks, int* buffer,
+                               size_t* byte_offset, int64_t* count, int* is_f64);
+int crdpn_pointnet_forward_train_phased(
+    const float* x, int64_t B, int64_t P, int64_t F,
+    const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+    const float* conv3_w, const float* conv3_b,
+    const float* bn1_w, const float* bn1_b, float* bn1_mean, float* bn1_var, int64_t* bn1_num_batches_tracked,
+    const float* bn2_w, const float* bn2_b, float* bn2_mean, float* bn2_var, int64_t* bn2_num_batches_tracked,
+    const float* bn3_w, const float* bn3_b, float* bn3_mean, float* bn3_var, int64_t* bn3_num_batches_tracked,
+    float bn_eps, float bn_momentum, float* out, void* ctx, size_t ctx_bytes, int variant,
+    int phase_begin, int phase_end, int64_t total_points, void* stream);
+int crdpn_pointnet_backward_phased(
+    const float* x, int64_t B, int64_t P, int64_t F,
+    const float* conv1_w, const float* conv2_w, const float* conv3_w,
+    const float* bn1_w, const float* bn1_b, const float* bn2_w, const float* bn2_b,
+    const float* bn3_w, const float* bn3_b,
+    const float* grad_out, const void* ctx, size_t ctx_bytes,
+    float* d_conv1_w, float* d_conv1_b, float* d_conv2_w, float* d_conv2_b, float* d_conv3_w, float* d_conv3_b,
+    float* d_bn1_w, float* d_bn1_b, float* d_bn2_w, float* d_bn2_b, float* d_bn3_w, float* d_bn3_b,
+    void* workspace, size_t workspace_bytes, int phase_begin, int phase_end, int64_t total_points, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
