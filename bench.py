@@ -372,8 +372,12 @@ def run_own(args):
 
 
 def print_line(obj):
-    sys.__stdout__.write(json.dumps(obj) + "\n")
-    sys.__stdout__.flush()
+    """The ONE JSON line, written to the process's original stdout (see main: fd 1 itself is pointed at stderr so that
+    nothing else -- Python prints, NCCL's version banner from C -- can land in front of it)."""
+    data = (json.dumps(obj) + "\n").encode()
+    fd = int(os.environ.get("CRDPN_BENCH_STDOUT_FD", "1"))
+    while data:
+        data = data[os.write(fd, data):]
 
 
 def main():
@@ -383,16 +387,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     args = ap.parse_args()
-    # stdout carries exactly ONE JSON line: everything else the run prints (the published module announces its frozen
-    # normalisation constants on stdout) goes to stderr
-    sys.stdout = sys.stderr
-    try:
-        if args.impl == "reference":
-            run_reference(args)
-        else:
-            run_own(args)
-    finally:
-        sys.stdout = sys.__stdout__
+    # stdout carries exactly ONE JSON line: keep a duplicate of the real stdout for it and point fd 1 at stderr, so that
+    # the published module's "normalization constant ..." prints and NCCL's C-level version banner go to stderr
+    sys.stdout.flush()
+    os.environ["CRDPN_BENCH_STDOUT_FD"] = str(os.dup(1))
+    os.dup2(2, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ import json
 import os
 import time
 
-from bench import (HEADLINE, SEED, ClockSampler, algorithmic_bytes, make_opt, scores_per_step, workload_name)
+from bench import (HEADLINE, SEED, ClockSampler, algorithmic_bytes, make_opt, print_line, scores_per_step, workload_name)
 
 
 def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
@@ -185,8 +185,7 @@ def run_multi(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
             "clocks": clocks,
             "also": also,
         }
-        sys.__stdout__.write(json.dumps(line) + "\n")
-        sys.__stdout__.flush()
+        print_line(line)
     faulthandler.cancel_dump_traceback_later()
     # teardown: drop the captured graph before the communicator; never let a stuck teardown eat box time
     import threading
