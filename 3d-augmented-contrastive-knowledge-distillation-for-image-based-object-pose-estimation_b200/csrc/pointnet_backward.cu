@@ -118,44 +118,56 @@ struct QParams {
   char *qimg, *w2timg;
   float* vec;
 };
-__global__ void __launch_bounds__(128) pn_bwd_q_kernel(const QParams a) {
+// 512 threads: thread (part, j) sums channels [part*F/4, (part+1)*F/4) for column j with 8 loads in flight; the four
+// parts fold through shared memory (the single 1024-deep dependent chain of the first version cost 58 us).
+__global__ void __launch_bounds__(512) pn_bwd_q_kernel(const QParams a) {
   const int t = threadIdx.x;
   __shared__ float red[128];
   if (blockIdx.x == 128) {
     // W2T[j][k] = a2[k] W2[k][j], a2 = gamma2 * istd2 (BN2's scale on the way back); rows j >= 64 are zero
-    for (int i = t; i < 128 * 128; i += 128) {
+    for (int i = t; i < 128 * 128; i += 512) {
       const int j = i >> 7, k = i & 127;
       const float v = j < 64 ? a.c2w[k * 64 + j] * (a.g2[k] * a.stats[kStatIstd2 + k]) : 0.f;
       *reinterpret_cast<__nv_bfloat16*>(a.w2timg + (k >> 6) * kKBlockBytes + sw128_off(j, k & 63)) = __float2bfloat16_rn(v);
     }
-    a.vec[128 + t] = a.g2[t] * a.stats[kStatIstd2 + t];
+    if (t < 128) a.vec[128 + t] = a.g2[t] * a.stats[kStatIstd2 + t];
     return;
   }
-  const int k = blockIdx.x, j = t;
+  const int k = blockIdx.x, j = t & 127, part = t >> 7;
   const float* istd3 = a.stats + kStatIstd3(a.F);
   __shared__ float cqw[1024], cuw[1024];  // per channel c: coefficient * W3[c][k]
-  for (int c = t; c < a.F; c += 128) {
+  __shared__ float qpart[4][128], upart[4][128];
+  for (int c = t; c < a.F; c += 512) {
     const float a3 = a.g3[c] * istd3[c];
     const float wk = __ldg(a.c3w + c * 128 + k);
     cqw[c] = a3 * a.dgamma3[c] * istd3[c] * wk;
     cuw[c] = a3 * a.dbeta3[c] * wk;
   }
   __syncthreads();
-  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, u = 0.f;
-#pragma unroll 4
-  for (int c = 0; c < a.F; c += 4) {
-    q0 = fmaf(cqw[c + 0], __ldg(a.c3w + (c + 0) * 128 + j), q0);
-    q1 = fmaf(cqw[c + 1], __ldg(a.c3w + (c + 1) * 128 + j), q1);
-    q2 = fmaf(cqw[c + 2], __ldg(a.c3w + (c + 2) * 128 + j), q2);
-    q3 = fmaf(cqw[c + 3], __ldg(a.c3w + (c + 3) * 128 + j), q3);
+  const int c0 = part * (a.F >> 2), c1 = c0 + (a.F >> 2);   // F is a multiple of 128
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, q4 = 0.f, q5 = 0.f, q6 = 0.f, q7 = 0.f;
+  for (int c = c0; c < c1; c += 8) {
+    const float w0 = __ldg(a.c3w + (c + 0) * 128 + j), w1 = __ldg(a.c3w + (c + 1) * 128 + j);
+    const float w2 = __ldg(a.c3w + (c + 2) * 128 + j), w3 = __ldg(a.c3w + (c + 3) * 128 + j);
+    const float w4 = __ldg(a.c3w + (c + 4) * 128 + j), w5 = __ldg(a.c3w + (c + 5) * 128 + j);
+    const float w6 = __ldg(a.c3w + (c + 6) * 128 + j), w7 = __ldg(a.c3w + (c + 7) * 128 + j);
+    q0 = fmaf(cqw[c + 0], w0, q0); q1 = fmaf(cqw[c + 1], w1, q1); q2 = fmaf(cqw[c + 2], w2, q2); q3 = fmaf(cqw[c + 3], w3, q3);
+    q4 = fmaf(cqw[c + 4], w4, q4); q5 = fmaf(cqw[c + 5], w5, q5); q6 = fmaf(cqw[c + 6], w6, q6); q7 = fmaf(cqw[c + 7], w7, q7);
   }
-  const float q = (q0 + q1) + (q2 + q3);
-  for (int c = j; c < a.F; c += 128) u += cuw[c];
-  const float invM = (float)(-1.0 / a.M);
-  const __nv_bfloat16 qb = __float2bfloat16_rn(q * invM);
-  *reinterpret_cast<__nv_bfloat16*>(a.qimg + (j >> 6) * kKBlockBytes + sw128_off(k, j & 63)) = qb;
-  // u'[k] = sum_j ( u_partial[j] * invM - Q_bf16[k][j] * m2[j] )
-  red[t] = u * invM - __bfloat162float(qb) * (float)(a.S2[j] / a.M);
+  qpart[part][j] = ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7));
+  float u = 0.f;
+  for (int c = c0 + j; c < c1; c += 128) u += cuw[c];
+  upart[part][j] = u;
+  __syncthreads();
+  if (t < 128) {
+    const float q = (qpart[0][j] + qpart[1][j]) + (qpart[2][j] + qpart[3][j]);
+    const float us = (upart[0][j] + upart[1][j]) + (upart[2][j] + upart[3][j]);
+    const float invM = (float)(-1.0 / a.M);
+    const __nv_bfloat16 qb = __float2bfloat16_rn(q * invM);
+    *reinterpret_cast<__nv_bfloat16*>(a.qimg + (j >> 6) * kKBlockBytes + sw128_off(k, j & 63)) = qb;
+    // u'[k] = sum_j ( u_partial[j] * invM - Q_bf16[k][j] * m2[j] )
+    red[t] = us * invM - __bfloat162float(qb) * (float)(a.S2[j] / a.M);
+  }
   __syncthreads();
   for (int off = 64; off >= 1; off >>= 1) {
     if (t < off) red[t] += red[t + off];
@@ -171,13 +183,35 @@ __global__ void __launch_bounds__(256) pn_bwd_gs_kernel(const float* __restrict_
   const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = lane * 4;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int b = warp; b < B; b += 8) {
-    const int n = __ldg(argmax + (size_t)b * F + c);
-    const float gv = __ldg(g + (size_t)b * F + c);
-    const char* tb = h2img + ((size_t)b * tiles2 + (n >> 7)) * kTileBytes + (k0 >> 6) * kKBlockBytes;
-    const uint2 v = *reinterpret_cast<const uint2*>(tb + sw128_off(n & 127, k0 & 63));
-    a0 = fmaf(gv, bf16_lo(v.x), a0); a1 = fmaf(gv, bf16_hi(v.x), a1);
-    a2 = fmaf(gv, bf16_lo(v.y), a2); a3 = fmaf(gv, bf16_hi(v.y), a3);
+  // warp w owns clouds b = w + 8 i.  Lane i first fetches (arg-max point, gradient) of cloud i of the current group of 32,
+  // then the warp walks the group four clouds at a time so that four independent row gathers are in flight
+  for (int base = 0; base < B; base += 256) {
+    const int bl = base + warp + 8 * lane;
+    int n_l = 0;
+    float g_l = 0.f;
+    if (bl < B) {
+      n_l = __ldg(argmax + (size_t)bl * F + c);
+      g_l = __ldg(g + (size_t)bl * F + c);
+    }
+    const int cnt = min(32, (B - base - warp + 7) / 8);   // clouds of this warp in the group
+    for (int i = 0; i < cnt; i += 4) {
+      uint2 v[4];
+      float gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int src = min(i + u, 31);
+        const int n = __shfl_sync(0xffffffffu, n_l, src);
+        gv[u] = (i + u < cnt) ? __shfl_sync(0xffffffffu, g_l, src) : 0.f;
+        const int b = base + warp + 8 * min(i + u, cnt - 1);
+        const char* tb = h2img + ((size_t)b * tiles2 + (n >> 7)) * kTileBytes + (k0 >> 6) * kKBlockBytes;
+        v[u] = *reinterpret_cast<const uint2*>(tb + sw128_off(n & 127, k0 & 63));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a0 = fmaf(gv[u], bf16_lo(v[u].x), a0); a1 = fmaf(gv[u], bf16_hi(v[u].x), a1);
+        a2 = fmaf(gv[u], bf16_lo(v[u].y), a2); a3 = fmaf(gv[u], bf16_hi(v[u].y), a3);
+      }
+    }
   }
   __shared__ float4 red[8][32];
   red[warp][lane] = make_float4(a0, a1, a2, a3);
@@ -1019,7 +1053,7 @@ extern "C" int crdpn_pointnet_backward_phased(
   }
   if (on(1)) {
     pn::QParams qp{conv3_w, bn3_w, d_bn3_w, d_bn3_b, stats, conv2_w, bn2_w, S2, M, (int)F, w + W.qimg, w + W.w2timg, vec};
-    pn::pn_bwd_q_kernel<<<129, 128, 0, st>>>(qp);
+    pn::pn_bwd_q_kernel<<<129, 512, 0, st>>>(qp);
     CRDPN_LAUNCH_CHECK("pn_bwd_q_kernel");
   }
 
