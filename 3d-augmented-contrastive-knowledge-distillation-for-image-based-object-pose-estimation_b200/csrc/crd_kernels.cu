@@ -50,6 +50,7 @@ struct ScoreParams {
   float* slots;
   int maxseg;
   unsigned int* ticket;
+  long long nw;         // warps the pair space is cut over (<= resident warps; the rest idle)
 };
 
 struct FinalizeParams {
@@ -125,12 +126,13 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / LPR, j = lane % LPR;
-  const long long NW = (long long)gridDim.x * kWarps;
+  const long long NW = p.nw;
   const long long gw = (long long)blockIdx.x * kWarps + warp;
   const long long P = (long long)p.B * p.K1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.ticket = 0u;  // finalize runs after us in stream order
+  if (gw >= NW) return;
   long long lo = P * gw / NW;
   const long long hi = P * (gw + 1) / NW;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.ticket = 0u;  // finalize runs after us in stream order
   int2* q = queue_smem[warp];
   const bool store_out = (p.out_v1 != nullptr);
   int seg = 0;
@@ -693,6 +695,11 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
       ((size_t)row_stride * esz) % 16 != 0 || (D * 4) % 16 != 0)
     return fail(CRDPN_E_ALIGN, "crdpn_crd_score: banks, embeddings, workspace and row pitch must be 16-byte aligned");
   Variant var;
+  // bit 8 of `variant`: anchor-aligned partition -- every anchor's list is cut into the same number S of slices, one per
+  // warp (B*S <= resident warps), so that slice s of EVERY anchor starts at the same time; with row-sorted lists the
+  // warps of a slice then walk the same band of bank rows together and each row comes from HBM once.
+  const bool aligned = (variant & 0x100) != 0;
+  variant &= 0xff;
   if (!pick_variant(bank_dtype, (int)D, variant, &var))
     return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_score: no kernel for this (dtype, feat_dim, variant); feat_dim in {32,64,128,256,512}");
 
@@ -702,7 +709,8 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   int rc = device_info(device, &di);
   if (rc) return rc;
   const int grid = di.sms * var.bps;
-  const long long NW = (long long)grid * kWarps;
+  long long NW = (long long)grid * kWarps;
+  if (aligned && NW >= B) NW = (NW / B) * B;
   const long long P = B * K1;
   const size_t need = workspace_bytes_for(B, K1, D, NW);
   if (workspace_bytes < need) return fail(CRDPN_E_WORKSPACE, "crdpn_crd_score: workspace too small");
@@ -737,6 +745,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.slots = slots;
   sp.maxseg = maxseg_for(P, NW, K1);
   sp.ticket = ticket;
+  sp.nw = NW;
 
   cudaStream_t st = (cudaStream_t)stream;
   {
