@@ -26,6 +26,7 @@ _SIGNATURES = {
     "crdpn_alias_draw_contrast": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_uint64,
                                           c_uint64, c_void_p, c_void_p]),
     "crdpn_crd_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
+    "crdpn_crd_stream_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
     "crdpn_crd_score": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                 c_float, c_float, c_float, c_float,

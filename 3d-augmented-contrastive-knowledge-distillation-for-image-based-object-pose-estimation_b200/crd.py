@@ -204,7 +204,8 @@ class _CRDLossFunction(torch.autograd.Function):
             mem._freeze_z(v1, v2, contrast_idx)
             hp = mem._host_params()
         m1, m2, stride, dt = mem._banks()
-        ws = mem._workspace(B, K1, D, dev)
+        variant = mem._step_variant(B, K1, D)
+        ws = mem._workspace(B, K1, D, dev, variant)
         smp = mem.multinomial
         if contrast_idx is None:
             scratch = mem._idx_scratch
@@ -222,7 +223,7 @@ class _CRDLossFunction(torch.autograd.Function):
                 B, K1, D, mem.nLem, mem.k_total, mem.row_begin, mem.row_end,
                 hp.T, hp.Z1, hp.Z2, EPS, hp.m, 1.0 - hp.m,
                 o_pre_s, o_pre_t, o_v1, o_v2, o_inv1, o_inv2,
-                base, o_g1, o_g2, ws.data_ptr(), ws.numel(), mem.variant, _stream_ptr(dev))
+                base, o_g1, o_g2, ws.data_ptr(), ws.numel(), variant, _stream_ptr(dev))
         _native.check(rc, "crdpn_crd_loss_forward")
         if contrast_idx is None:
             smp.offset += B * K1
@@ -390,6 +391,7 @@ class ContrastMemory(nn.Module):
         self.K = K
         self.k_total = 0   # negatives per anchor over all shards (0: the K+1 columns of contrast_idx are all of them)
         self.variant = 0
+        self.streaming = False   # True: experimental bank-streaming step (see _step_variant)
         self.register_buffer("params", torch.tensor([K, T, -1, -1, momentum], dtype=torch.float32))
         stdv = 1.0 / math.sqrt(inputSize / 3)
         rows = self.row_end - self.row_begin
@@ -399,7 +401,7 @@ class ContrastMemory(nn.Module):
         self.register_buffer("memory_v2", m2)
         self._relayout()
         self._ws = None
-        self._ws_key = None
+        self._ws_cache = {}
         self._res = None
         self._idx_scratch = None
         # host mirror of params (avoids a device->host read per step once Z is frozen)
@@ -421,6 +423,7 @@ class ContrastMemory(nn.Module):
         self._relayout()  # .cuda()/.to() de-interleave the two views; put them back in one allocation
         self.multinomial.to(self._buffers["memory_v1"].device)
         self._ws = None
+        self._ws_cache = {}
         self._idx_scratch = None
         self._host = None
         return self
@@ -445,14 +448,36 @@ class ContrastMemory(nn.Module):
             self._host = SimpleNamespace(K=int(p[0]), T=float(p[1]), Z1=float(p[2]), Z2=float(p[3]), m=float(p[4]))
         return self._host
 
-    def _workspace(self, B, K1, D, device):
-        key = (B, K1, D, device)
-        if self._ws_key != key or self._ws is None:
+    STREAM = 0x200   # variant bit: bank-streaming formulation of the step (csrc/crd_stream.cuh)
+
+    def _step_variant(self, B, K1, D):
+        """Variant passed to crdpn_crd_step.  ``self.streaming = True`` selects the bank-streaming formulation
+        (EXPERIMENTAL: reads every resident row once -- 1.04 GB instead of 2.9 GB of DRAM traffic at the headline config --
+        but is instruction-bound and currently 2x slower than the gather kernel)."""
+        if self.variant & self.STREAM:
+            return self.variant
+        if not self.streaming:
+            return self.variant
+        rows = self.row_end - self.row_begin
+        if not (D == 128 and 1 <= B <= 48 and rows >= 1 and self._buffers["memory_v1"].dtype == torch.float32):
+            raise RuntimeError("streaming CRD step needs fp32 banks, feat_dim 128 and batch <= 48")
+        return self.variant | self.STREAM
+
+    def _workspace(self, B, K1, D, device, variant=0):
+        stream = bool(variant & self.STREAM)
+        key = (B, K1, D, device, stream)
+        cache = self._ws_cache
+        if cache.get(stream, (None, None))[0] != key:
             n = ctypes.c_size_t(0)
-            _native.check(_native.lib().crdpn_crd_workspace_bytes(B, K1, D, device.index or 0, ctypes.byref(n)),
-                          "crdpn_crd_workspace_bytes")
-            self._ws = torch.empty(n.value, dtype=torch.uint8, device=device)
-            self._ws_key = key
+            if stream:
+                _native.check(_native.lib().crdpn_crd_stream_workspace_bytes(B, K1, D, self.row_end - self.row_begin,
+                                                                            device.index or 0, ctypes.byref(n)),
+                              "crdpn_crd_stream_workspace_bytes")
+            else:
+                _native.check(_native.lib().crdpn_crd_workspace_bytes(B, K1, D, device.index or 0, ctypes.byref(n)),
+                              "crdpn_crd_workspace_bytes")
+            cache[stream] = (key, torch.empty(n.value, dtype=torch.uint8, device=device))
+        self._ws = cache[stream][1]
         if self._res is None or self._res.device != device:
             self._res = torch.zeros(8, dtype=torch.float64, device=device)
         return self._ws
@@ -499,7 +524,8 @@ class ContrastMemory(nn.Module):
         B, K1 = idx.shape
         D = v1.shape[1]
         dev = v1.device
-        ws = self._workspace(B, K1, D, dev)
+        variant = self._step_variant(B, K1, D)
+        ws = self._workspace(B, K1, D, dev, variant)
         res = torch.empty(8, dtype=torch.float64, device=dev)  # fresh: the returned loss is a view into it
         g1, g2 = self._grad_buffers(v1, v2)
         hp = self._host_params()
@@ -507,7 +533,7 @@ class ContrastMemory(nn.Module):
             rc = _native.lib().crdpn_crd_step(
                 m1.data_ptr(), m2.data_ptr(), stride, dt, v1.data_ptr(), v2.data_ptr(), idx.data_ptr(), y.data_ptr(),
                 B, K1, D, self.nLem, self.k_total, self.row_begin, self.row_end, hp.T, Z1, Z2, EPS, hp.m, 1.0 - hp.m,
-                res.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), ws.numel(), self.variant, _stream_ptr(dev))
+                res.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), ws.numel(), variant, _stream_ptr(dev))
         _native.check(rc, "crdpn_crd_step")
         return res, g1, g2
 

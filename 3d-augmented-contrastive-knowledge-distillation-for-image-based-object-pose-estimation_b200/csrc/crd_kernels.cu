@@ -522,6 +522,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) crd_finalize_update_kernel(c
   else update_body<T>(u, ((int)blockIdx.x - f.B) * (kFinalizeThreads / 32) + (threadIdx.x >> 5));
 }
 
+#include "crd_stream.cuh"
+
 // ------------------------------------------------------------------------------------------------------
 // Alias-method draw: one Philox4x32-10 block per output (identical stream to oracle/crd_oracle.c).
 // ------------------------------------------------------------------------------------------------------
@@ -785,6 +787,126 @@ extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row
                     nullptr, stream);
 }
 
+// ---- bank-streaming step (crd_stream.cuh) ------------------------------------------------------------------------
+struct TsLayout {
+  size_t count, off, cursor, records, partial, loss_part, total;
+  int T, G;
+  TsLayout(long long B, long long K1, long long rows, int sms) {
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    T = (int)((rows + ts::kTR - 1) / ts::kTR);
+    G = sms;
+    size_t o = 0;
+    count = o; o += up((size_t)(T + 1) * 4);
+    off = o; o += up((size_t)(T + 1) * 4);
+    cursor = o; o += up((size_t)(T + 1) * 4);
+    records = o; o += up((size_t)(B * K1 + 8) * 4);
+    partial = o; o += up((size_t)G * B * 2 * ts::kD * 4);
+    loss_part = o; o += up((size_t)G * ts::kWarpsTS * 2 * 4);
+    total = o;
+  }
+};
+
+// can the streaming formulation run this problem?  (fp32, D = 128, B <= 48, interleaved or dense banks, tile table fits)
+static bool ts_supported(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype, int64_t B, int64_t K1,
+                         int64_t D, int64_t rows, int sms) {
+  if (bank_dtype != CRDPN_F32 || D != ts::kD || B < 1 || B > ts::kMaxB || rows < 1 || B * K1 >= (1ll << 31)) return false;
+  const bool inter = row_stride == 2 * D && (const char*)bank2 == (const char*)bank1 + D * 4;
+  const bool dense = row_stride == D;
+  if (!inter && !dense) return false;
+  const long long T = (rows + ts::kTR - 1) / ts::kTR;
+  return (T + sms - 1) / sms + 1 <= ts::kMaxTilesPerCta;
+}
+
+extern "C" int crdpn_crd_stream_workspace_bytes(int64_t B, int64_t K1, int64_t D, int64_t rows_local, int device, size_t* bytes) {
+  if (!bytes || B <= 0 || K1 <= 0 || D <= 0 || rows_local <= 0) return fail(CRDPN_E_BADARG, "crdpn_crd_stream_workspace_bytes: bad argument");
+  DeviceInfo di;
+  int rc = device_info(device, &di);
+  if (rc) return rc;
+  *bytes = TsLayout(B, K1, rows_local, di.sms).total;
+  return CRDPN_OK;
+}
+
+static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int bank_dtype, const float* v1, const float* v2,
+                            const int64_t* contrast_idx, int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
+                            int64_t row_begin, int64_t row_end, float T, float Z1, float Z2, float eps, double* result,
+                            float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes, const UpdateParams& upd,
+                            void* stream) {
+  if (!v1 || !v2 || !contrast_idx || !result || !grad_v1 || !grad_v2 || !workspace || !bank1 || !bank2)
+    return fail(CRDPN_E_BADARG, "crdpn_crd_step (streaming): null pointer");
+  if (B <= 0 || K1 <= 0 || n_data <= 0 || row_end <= row_begin || !(T > 0.f) || k_total < 0)
+    return fail(CRDPN_E_BADARG, "crdpn_crd_step (streaming): bad size");
+  if (((uintptr_t)bank1 | (uintptr_t)bank2 | (uintptr_t)v1 | (uintptr_t)v2 | (uintptr_t)workspace) & 15)
+    return fail(CRDPN_E_ALIGN, "crdpn_crd_step (streaming): 16-byte alignment required");
+  int device = 0;
+  CRDPN_CUDA(cudaGetDevice(&device));
+  DeviceInfo di;
+  int rc = device_info(device, &di);
+  if (rc) return rc;
+  const int64_t rows = row_end - row_begin;
+  if (!ts_supported(bank1, bank2, row_stride, bank_dtype, B, K1, D, rows, di.sms))
+    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): needs fp32 banks, feat_dim 128, batch <= 48, interleaved or dense banks");
+  if (di.max_smem_optin < ts::kSmemBytes) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): not enough shared memory");
+  const TsLayout L(B, K1, rows, di.sms);
+  if (workspace_bytes < L.total) return fail(CRDPN_E_WORKSPACE, "crdpn_crd_step (streaming): workspace too small (crdpn_crd_stream_workspace_bytes)");
+  char* ws = (char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  ts::BucketParams bp;
+  bp.idx = (const long long*)contrast_idx;
+  bp.P = B * K1;
+  bp.K1 = (unsigned)K1;
+  bp.row_begin = row_begin; bp.row_end = row_end;
+  bp.count = (unsigned*)(ws + L.count); bp.off = (unsigned*)(ws + L.off); bp.cursor = (unsigned*)(ws + L.cursor);
+  bp.records = (unsigned*)(ws + L.records);
+  bp.T = L.T;
+
+  const double Kd = (double)(k_total > 0 ? k_total : (K1 - 1));
+  const double Pn = 1.0 / (double)n_data;
+  const float mPn_f = (float)(Kd * Pn);
+  const float c_f = (float)(Kd * Pn + (double)eps);
+  ts::StreamParams sp;
+  sp.bank1 = (const char*)bank1; sp.bank2 = (const char*)bank2;
+  sp.interleaved = row_stride == 2 * D ? 1 : 0;
+  sp.rows = rows; sp.B = (int)B; sp.T = L.T;
+  sp.v1 = v1; sp.v2 = v2;
+  sp.tile_off = bp.off; sp.records = bp.records;
+  sp.k_exp = (float)(1.4426950408889634 / (double)T);
+  sp.inv_Z1 = (float)(1.0 / (double)Z1); sp.inv_Z2 = (float)(1.0 / (double)Z2);
+  sp.c = c_f;
+  sp.inv_mPn = (Kd > 0) ? (float)(1.0 / (double)mPn_f) : 0.f;
+  sp.eps_over_mPn = (Kd > 0) ? (float)(((double)c_f - (double)mPn_f) / (double)mPn_f) : 0.f;
+  sp.inv_BT = (float)(1.0 / ((double)B * (double)T));
+  sp.partial = (float*)(ws + L.partial);
+  sp.loss_part = (float*)(ws + L.loss_part);
+
+  static bool attr_set[64] = {false};
+  if (!attr_set[device]) {
+    CRDPN_CUDA(cudaFuncSetAttribute(ts::crd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmemBytes));
+    attr_set[device] = true;
+  }
+  {
+    ScopedKernelTimer tm(CRDPN_K_CRD_SCORE, st);   // the bucketing is part of what replaces the gather pass
+    CRDPN_CUDA(cudaMemsetAsync(bp.count, 0, (size_t)(L.T + 1) * 4, st));
+    const int pre_grid = di.sms * 8;
+    ts::ts_hist_kernel<<<pre_grid, 256, 0, st>>>(bp);
+    CRDPN_LAUNCH_CHECK("ts_hist_kernel");
+    ts::ts_scan_kernel<<<1, 1024, 0, st>>>(bp);
+    CRDPN_LAUNCH_CHECK("ts_scan_kernel");
+    ts::ts_scatter_kernel<<<pre_grid, 256, 0, st>>>(bp);
+    CRDPN_LAUNCH_CHECK("ts_scatter_kernel");
+    ts::crd_stream_kernel<<<L.G, ts::kThreadsTS, ts::kSmemBytes, st>>>(sp);
+    CRDPN_LAUNCH_CHECK("crd_stream_kernel");
+  }
+  ts::TsFinalizeParams fp;
+  fp.partial = sp.partial; fp.loss_part = sp.loss_part; fp.tile_off = bp.off;
+  fp.G = L.G; fp.B = (int)B; fp.T = L.T;
+  fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2; fp.result = result;
+  const int ublocks = (int)((2 * B + 7) / 8);
+  ts::ts_finalize_update_kernel<float><<<(int)B + ublocks, 256, 0, st>>>(fp, upd);
+  CRDPN_LAUNCH_CHECK("ts_finalize_update_kernel");
+  return CRDPN_OK;
+}
+
 extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
                               const float* v1, const float* v2, const int64_t* contrast_idx, const int64_t* y,
                               int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
@@ -797,6 +919,9 @@ extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int 
   if (rc) return rc;
   const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end,
                                             momentum, one_minus_momentum);
+  if (variant & 0x200)  // bank-streaming formulation (crd_stream.cuh); the workspace is crdpn_crd_stream_workspace_bytes
+    return stream_step_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin,
+                            row_end, T, Z1, Z2, eps, result, grad_v1, grad_v2, workspace, workspace_bytes, u, stream);
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin, row_end,
                     T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant,
                     &u, stream);

@@ -1,0 +1,394 @@
+// crd_stream.cuh -- bank-STREAMING formulation of the CRD scoring pass (included by crd_kernels.cu).
+//
+// The gather formulation (crd_score_kernel) reads one bank row pair per sampled (anchor, negative): B*(K+1) KB.  When
+// B*(K+1) exceeds the number of resident rows every row is sampled several times per step (3x at the headline config),
+// and the 126 MB L2 cannot hold on to a 1 GB bank between two visits (measured hit rate 6 %).  Here the samples are
+// first bucketed by ROW TILE (32 rows = 32 KB of the interleaved banks) and the banks are then streamed through shared
+// memory exactly once, tile by tile, with bulk copies:
+//   ts_hist / ts_scan / ts_scatter   counting sort of the B*(K+1) samples by tile: one 32-bit record per sample
+//                                    (row inside the tile | anchor | positive flag)
+//   crd_stream_kernel                persistent CTAs, 16 warps; a producer thread keeps a 4-deep ring of (tile rows,
+//                                    tile records) bulk copies in flight; warp w owns anchors {w, w+16, w+32} and keeps
+//                                    their embeddings AND their gradient accumulators in registers, picks its own
+//                                    records out of the tile's list by ballot and scores them two at a time (one per
+//                                    half-warp) against the rows in shared memory
+//   ts_finalize_update               fixed-order sum of the per-CTA partials + the momentum update
+// HBM traffic: resident rows * row bytes (1.02 GB at the headline config instead of 2.9 GB) + 12 B per sample.
+// STATUS (round 1, measured on B200, profiles/r1_crd_stream_ncu.csv): correct (tests/test_crd_stream_gpu.py) and the DRAM
+// traffic is what was designed (1.036 GB read per step instead of 2.90 GB), but the streaming kernel executes 426 M warp
+// instructions (141 per sample: with ~0.7 records per (32-record chunk, anchor) the two half-warps almost never find a
+// pair, and every warp scans every record) and takes 0.78 ms, plus 0.13 ms of bucketing -- 2x SLOWER than the gather
+// kernel (0.43 ms), whose per-sample arithmetic hides under its memory time.  Opt-in only (variant | 0x200); the default
+// path is crd_score_kernel.  What this formulation needs to pay off is the per-sample dot products and gradient updates
+// off the CUDA cores: scores of a tile as rows x V^T and gradients as C^T x rows on tcgen05 (TF32, TMA-swizzled tiles),
+// leaving ~35 scalar instructions per sample -- see DESIGN.md section 8.
+// Restrictions: fp32 banks, D = 128, B <= 48, banks interleaved [rows][2][D] or two dense [rows][D] arrays, step mode
+// only (no out_v, Z frozen).  The accumulation order inside one (tile, anchor) group follows the scatter's atomic order,
+// so results are equal to the gather kernel's to fp32 rounding but not bit-reproducible run to run.
+#pragma once
+
+namespace ts {
+
+constexpr int kTR = 32;                    // bank rows per tile
+constexpr int kWarpsTS = 16;
+constexpr int kThreadsTS = kWarpsTS * 32;
+constexpr int kSlots = 3;                  // anchors per warp: b = warp + 16 * slot
+constexpr int kMaxB = kWarpsTS * kSlots;   // 48
+constexpr int kStages = 4;
+constexpr int kD = 128;
+constexpr int kRowsBytes = kTR * 2 * kD * 4;  // 32768: both banks' rows of one tile
+constexpr int kRecCap = 1024;                 // records staged per tile (4 KB); longer lists spill to global reads
+constexpr int kStageBytes = kRowsBytes + kRecCap * 4;
+constexpr int kMaxTilesPerCta = 2047;
+constexpr int kSmemBytes = kStages * kStageBytes + (kMaxTilesPerCta + 1) * 4 + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol bug, never a legitimate wait
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// record: bits [0,5) row inside the tile | [5,15) anchor | bit 31 positive
+__device__ __forceinline__ unsigned make_record(unsigned row_in_tile, unsigned b, bool pos) {
+  return row_in_tile | (b << 5) | (pos ? 0x80000000u : 0u);
+}
+
+struct BucketParams {
+  const long long* idx;   // [B, K1]
+  long long P;            // B * K1
+  unsigned K1;
+  long long row_begin, row_end;
+  unsigned* count;        // [T + 1], zeroed before ts_hist
+  unsigned* off;          // [T + 1]
+  unsigned* cursor;       // [T + 1]
+  unsigned* records;      // [P + 8]
+  int T;
+};
+
+__global__ void __launch_bounds__(256) ts_hist_kernel(const BucketParams p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P; i += stride) {
+    const long long r = p.idx[i];
+    if (r >= p.row_begin && r < p.row_end) atomicAdd(p.count + ((r - p.row_begin) >> 5), 1u);
+  }
+}
+
+// one CTA: exclusive scan of count[0..T) -> off[0..T], cursor = off
+__global__ void __launch_bounds__(1024) ts_scan_kernel(const BucketParams p) {
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0u;
+  __syncthreads();
+  for (int base = 0; base < p.T; base += 1024 * 4) {
+    const int i0 = base + threadIdx.x * 4;
+    unsigned c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[q] = (i0 + q < p.T) ? p.count[i0 + q] : 0u;
+    const unsigned tsum = c[0] + c[1] + c[2] + c[3];
+    unsigned incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+    unsigned run = carry_s + wbase + incl - tsum;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (i0 + q < p.T) { p.off[i0 + q] = run; p.cursor[i0 + q] = run; }
+      run += c[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.off[p.T] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) ts_scatter_kernel(const BucketParams p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P; i += stride) {
+    const long long r = p.idx[i];
+    if (r < p.row_begin || r >= p.row_end) continue;
+    const unsigned local = (unsigned)(r - p.row_begin);
+    const unsigned b = (unsigned)i / p.K1;                 // P < 2^31 (checked on the host)
+    const bool pos = (unsigned)i - b * p.K1 == 0u;
+    const unsigned slot = atomicAdd(p.cursor + (local >> 5), 1u);
+    p.records[slot] = make_record(local & 31u, b, pos);
+  }
+}
+
+struct StreamParams {
+  const char* bank1;
+  const char* bank2;
+  int interleaved;        // 1: one [rows][2][D] allocation (bank2 == bank1 + D floats, pitch 2D); 0: two dense [rows][D]
+  long long rows;         // resident rows
+  int B, T;
+  const float* v1;
+  const float* v2;
+  const unsigned* tile_off;
+  const unsigned* records;
+  float k_exp, inv_Z1, inv_Z2, c, inv_mPn, eps_over_mPn, inv_BT;
+  float* partial;         // [grid][B][2 * D]
+  float* loss_part;       // [grid][kWarpsTS][2]
+};
+
+__global__ void __launch_bounds__(kThreadsTS, 1) crd_stream_kernel(const StreamParams p) {
+  extern __shared__ __align__(128) unsigned char ts_smem[];
+  constexpr unsigned kFull = 0xffffffffu;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, h = lane >> 4, j = lane & 15;
+  unsigned* offs = reinterpret_cast<unsigned*>(ts_smem + kStages * kStageBytes);
+  const uint32_t sbase = smem_u32(ts_smem);
+  const uint32_t bar_full = sbase + kStages * kStageBytes + (kMaxTilesPerCta + 1) * 4;
+  const uint32_t bar_empty = bar_full + 8 * kStages;
+
+  const int t_begin = (int)((long long)p.T * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long long)p.T * (blockIdx.x + 1) / gridDim.x);
+  const int ntiles = t_end - t_begin;
+  for (int i = tid; i <= ntiles; i += kThreadsTS) offs[i] = p.tile_off[t_begin + i];
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kWarpsTS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // this warp's anchors: embeddings and gradient accumulators live in registers for the whole kernel.
+  // lane (h, j): half-warp h scores one sample; lane j holds elements [4j, 4j+4) and [64+4j, 64+4j+4)
+  float v1r[kSlots][8], v2r[kSlots][8], g1r[kSlots][8], g2r[kSlots][8];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int b = warp + kWarpsTS * s;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
+      if (b < p.B) {
+        a = *reinterpret_cast<const float4*>(p.v1 + (size_t)b * kD + 64 * q + 4 * j);
+        c4 = *reinterpret_cast<const float4*>(p.v2 + (size_t)b * kD + 64 * q + 4 * j);
+      }
+      v1r[s][4 * q + 0] = a.x; v1r[s][4 * q + 1] = a.y; v1r[s][4 * q + 2] = a.z; v1r[s][4 * q + 3] = a.w;
+      v2r[s][4 * q + 0] = c4.x; v2r[s][4 * q + 1] = c4.y; v2r[s][4 * q + 2] = c4.z; v2r[s][4 * q + 3] = c4.w;
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { g1r[s][n] = 0.f; g2r[s][n] = 0.f; }
+  }
+  float ls = 0.f, lt = 0.f;
+
+  const uint32_t row_pitch = p.interleaved ? 1024u : 512u;   // bytes between consecutive rows of one bank in a stage
+  const uint32_t bank2_off = p.interleaved ? 512u : 16384u;
+
+  auto issue = [&](int it) {   // thread 0 only
+    const int s = it % kStages;
+    const long long t = t_begin + it;
+    const unsigned n0 = offs[it], n1 = offs[it + 1];
+    const uint32_t dst = sbase + s * kStageBytes;
+    if (n1 == n0) {              // nobody sampled this tile: its rows are never read
+      mbar_arrive(bar_full + 8 * s);
+      return;
+    }
+    const long long left = p.rows - t * kTR;
+    const uint32_t nrows = (uint32_t)(left < kTR ? left : kTR);
+    const unsigned w0 = n0 & ~3u;
+    unsigned w1 = (n1 + 3u) & ~3u;
+    if (w1 - w0 > (unsigned)kRecCap) w1 = w0 + kRecCap;
+    const uint32_t rec_bytes = (w1 - w0) * 4u;
+    mbar_expect_tx(bar_full + 8 * s, nrows * 1024u + rec_bytes);
+    if (p.interleaved) {
+      bulk_g2s(dst, p.bank1 + t * (long long)kRowsBytes, nrows * 1024u, bar_full + 8 * s);
+    } else {
+      bulk_g2s(dst, p.bank1 + t * (long long)(kRowsBytes / 2), nrows * 512u, bar_full + 8 * s);
+      bulk_g2s(dst + 16384u, p.bank2 + t * (long long)(kRowsBytes / 2), nrows * 512u, bar_full + 8 * s);
+    }
+    bulk_g2s(dst + kRowsBytes, p.records + w0, rec_bytes, bar_full + 8 * s);
+  };
+
+  if (tid == 0) {
+    for (int it = 0; it < kStages - 1 && it < ntiles; ++it) issue(it);
+  }
+
+  for (int it = 0; it < ntiles; ++it) {
+    const int s = it % kStages;
+    if (tid == 0) {
+      const int nxt = it + kStages - 1;
+      if (nxt < ntiles) {
+        if (it >= 1) mbar_wait(bar_empty + 8 * ((it - 1) % kStages), (uint32_t)(((it - 1) / kStages) & 1));
+        issue(nxt);
+      }
+    }
+    __syncwarp();
+    const unsigned n0 = offs[it], n1 = offs[it + 1];
+    mbar_wait(bar_full + 8 * s, (uint32_t)((it / kStages) & 1));
+    if (n1 != n0) {
+      const unsigned char* rows = ts_smem + s * kStageBytes;
+      const unsigned* recs = reinterpret_cast<const unsigned*>(rows + kRowsBytes);
+      const unsigned w0 = n0 & ~3u;
+      for (unsigned base = n0; base < n1; base += 32) {
+        const unsigned i = base + lane;
+        unsigned rec = 0x7fffffffu;   // anchor field all ones: matches no warp
+        if (i < n1) rec = (i - w0 < (unsigned)kRecCap) ? recs[i - w0] : __ldg(p.records + i);
+        const unsigned recb = (rec >> 5) & 0x3ffu;
+#pragma unroll
+        for (int sl = 0; sl < kSlots; ++sl) {
+          unsigned m = __ballot_sync(kFull, recb == (unsigned)(warp + kWarpsTS * sl));
+          while (m) {
+            const int i0 = __ffs(m) - 1;
+            m &= m - 1;
+            int i1 = -1;
+            if (m) { i1 = __ffs(m) - 1; m &= m - 1; }
+            const bool valid = (h == 0) || (i1 >= 0);
+            const unsigned r = __shfl_sync(kFull, rec, (h == 0 || i1 < 0) ? i0 : i1);
+            const bool is_pos = (r >> 31) != 0u;
+            const unsigned char* rp = rows + (r & 31u) * row_pitch + 16 * j;
+            const float4 a0 = *reinterpret_cast<const float4*>(rp);                    // bank1 row, elements [4j, 4j+4)
+            const float4 a1 = *reinterpret_cast<const float4*>(rp + 256);              //            [64+4j, 64+4j+4)
+            const float4 c0 = *reinterpret_cast<const float4*>(rp + bank2_off);        // bank2 row
+            const float4 c1 = *reinterpret_cast<const float4*>(rp + bank2_off + 256);
+            const float w1f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float w2f[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            float d1s = 0.f, d2s = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+              d1s = fmaf(w2f[n], v1r[sl][n], d1s);   // out_v1 direction: bank2 row . v1
+              d2s = fmaf(w1f[n], v2r[sl][n], d2s);   // out_v2 direction: bank1 row . v2
+            }
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) {
+              d1s += __shfl_xor_sync(kFull, d1s, o);
+              d2s += __shfl_xor_sync(kFull, d2s, o);
+            }
+            const float e1 = ex2_approx(d1s * p.k_exp), e2 = ex2_approx(d2s * p.k_exp);
+            const float o1 = e1 * p.inv_Z1, o2 = e2 * p.inv_Z2;
+            const float rc1 = rcp_approx(o1 + p.c), rc2 = rcp_approx(o2 + p.c);
+            const float mk = valid ? 1.f : 0.f;
+            const float sc = p.inv_BT * mk;
+            const float dd1 = (is_pos ? -p.c : o1) * rc1 * sc;
+            const float dd2 = (is_pos ? -p.c : o2) * rc2 * sc;
+            float t1, t2;
+            if (is_pos) {
+              t1 = logf(__fdiv_rn(o1, o1 + p.c));
+              t2 = logf(__fdiv_rn(o2, o2 + p.c));
+            } else {
+              t1 = -log1p_pos(fmaf(o1, p.inv_mPn, p.eps_over_mPn));
+              t2 = -log1p_pos(fmaf(o2, p.inv_mPn, p.eps_over_mPn));
+            }
+            ls = fmaf(t1, mk, ls);
+            lt = fmaf(t2, mk, lt);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+              g1r[sl][n] = fmaf(dd1, w2f[n], g1r[sl][n]);
+              g2r[sl][n] = fmaf(dd2, w1f[n], g2r[sl][n]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+  }
+
+  // ---- flush: the two half-warps' gradient partials fold, then one [B][2D] block per CTA
+  float* part = p.partial + (size_t)blockIdx.x * p.B * 2 * kD;
+#pragma unroll
+  for (int sl = 0; sl < kSlots; ++sl) {
+    const int b = warp + kWarpsTS * sl;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      g1r[sl][n] += __shfl_xor_sync(kFull, g1r[sl][n], 16);
+      g2r[sl][n] += __shfl_xor_sync(kFull, g2r[sl][n], 16);
+    }
+    if (b < p.B && h == 0) {
+      float* dst = part + (size_t)b * 2 * kD;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        *reinterpret_cast<float4*>(dst + 64 * q + 4 * j) = make_float4(g1r[sl][4 * q], g1r[sl][4 * q + 1], g1r[sl][4 * q + 2], g1r[sl][4 * q + 3]);
+        *reinterpret_cast<float4*>(dst + kD + 64 * q + 4 * j) = make_float4(g2r[sl][4 * q], g2r[sl][4 * q + 1], g2r[sl][4 * q + 2], g2r[sl][4 * q + 3]);
+      }
+    }
+  }
+  // every lane of a half-warp holds the same loss terms: take lanes 0 and 16
+  const float ls_w = __shfl_sync(kFull, ls, 0) + __shfl_sync(kFull, ls, 16);
+  const float lt_w = __shfl_sync(kFull, lt, 0) + __shfl_sync(kFull, lt, 16);
+  if (lane == 0) {
+    p.loss_part[((size_t)blockIdx.x * kWarpsTS + warp) * 2 + 0] = ls_w;
+    p.loss_part[((size_t)blockIdx.x * kWarpsTS + warp) * 2 + 1] = lt_w;
+  }
+}
+
+struct TsFinalizeParams {
+  const float* partial;     // [G][B][2D]
+  const float* loss_part;   // [G][kWarpsTS][2]
+  const unsigned* tile_off; // off[T] = samples scored on this shard
+  int G, B, T;
+  float* grad_v1;
+  float* grad_v2;
+  double* result;
+};
+
+// blocks [0, B): column-parallel fixed-order sum over the G CTA partials of anchor b (block 0 also folds the loss);
+// remaining blocks: momentum update (update_body), as in crd_finalize_update_kernel
+template <typename T>
+__global__ void __launch_bounds__(256) ts_finalize_update_kernel(const TsFinalizeParams f, const UpdateParams u) {
+  if ((int)blockIdx.x >= f.B) {
+    update_body<T>(u, ((int)blockIdx.x - f.B) * 8 + (threadIdx.x >> 5));
+    return;
+  }
+  const int b = blockIdx.x, col = threadIdx.x;
+  double acc = 0.0;
+  for (int g = 0; g < f.G; ++g) acc += (double)f.partial[((size_t)g * f.B + b) * 2 * kD + col];
+  if (col < kD) f.grad_v1[(size_t)b * kD + col] = (float)acc;
+  else f.grad_v2[(size_t)b * kD + (col - kD)] = (float)acc;
+  if (b == 0) {
+    __shared__ double red[2][256];
+    const int n = f.G * kWarpsTS;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) { s0 += (double)f.loss_part[2 * i]; s1 += (double)f.loss_part[2 * i + 1]; }
+    red[0][threadIdx.x] = s0;
+    red[1][threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int i = 0; i < 256; ++i) { t0 += red[0][i]; t1 += red[1][i]; }
+      const double l_s = -t0 / (double)f.B, l_t = -t1 / (double)f.B;
+      f.result[0] = l_s;
+      f.result[1] = l_t;
+      f.result[2] = 0.0;
+      f.result[3] = 0.0;
+      f.result[4] = (double)f.tile_off[f.T];
+      f.result[5] = l_s + l_t;
+      f.result[6] = 0.0;
+      reinterpret_cast<float*>(&f.result[6])[0] = (float)(l_s + l_t);
+      f.result[7] = 0.0;
+    }
+  }
+}
+
+}  // namespace ts

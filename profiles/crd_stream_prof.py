@@ -1,0 +1,21 @@
+"""Program profiled for the bank-streaming CRD step at the headline config: 3 steps."""
+import sys, torch
+sys.path.insert(0, '.')
+import bench
+import __graft_entry__ as ge
+pkg = ge.load_package()
+dev = torch.device('cuda:0')
+c = bench.HEADLINE
+torch.manual_seed(bench.SEED)
+crit = pkg.CRDLoss(bench.make_opt(c)).to(dev)
+f_s, f_t, y, cidx = [t.to(dev) for t in bench.synth_inputs(c, torch)]
+with torch.no_grad():
+    v1 = crit.embed_s(f_s).contiguous(); v2 = crit.embed_t(f_t).contiguous()
+mem = crit.contrast
+mem._freeze_z(v1, v2, cidx)
+hp = mem._host_params()
+mem.streaming = True
+for _ in range(3):
+    mem._step(v1, v2, y, cidx, hp.Z1, hp.Z2)
+torch.cuda.synchronize()
+print("ok")
