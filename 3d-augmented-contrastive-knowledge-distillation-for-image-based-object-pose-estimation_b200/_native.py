@@ -43,6 +43,17 @@ _SIGNATURES = {
                                        c_float, c_float, c_float, c_float, c_float, c_float,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "crdpn_alias_draw_contrast_local": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_uint64,
+                                                c_uint64, c_void_p, c_void_p]),
+    "crdpn_crd_loss_forward_sharded": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64,
+                                               c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p,
+                                               c_void_p, c_void_p, c_int64, c_int,
+                                               c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                               c_float, c_float, c_float, c_float, c_float, c_float,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_size_t, c_int, c_void_p]),
     "crdpn_crd_loss_backward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_int64] + [c_void_p] * 8),

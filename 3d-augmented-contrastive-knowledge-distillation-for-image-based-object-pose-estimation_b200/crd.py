@@ -82,18 +82,18 @@ class AliasMethod:
         self.offset += N
         return out
 
-    def draw_contrast(self, y: torch.Tensor, K1: int) -> torch.Tensor:
-        """[B, K1] contrast indices with column 0 = y (ContrastMemory.forward when idx is None)."""
+    def draw_contrast(self, y: torch.Tensor, K1: int, row_base: int = 0) -> torch.Tensor:
+        """[B, K1] contrast indices with column 0 = y (ContrastMemory.forward when idx is None); `row_base` is added to
+        the drawn columns (a shard's sampler draws local rows, the contrast list holds global ones)."""
         _require_cuda(self.prob, "AliasMethod tables (call .cuda() first)")
         y = y.contiguous()
         B = y.numel()
         out = torch.empty(B, K1, dtype=torch.int64, device=self.prob.device)
         with _native.on_device(self.prob.device):
-            _native.check(_native.lib().crdpn_alias_draw_contrast(*self.table_ptrs(),
-                                                                  self.prob.numel(), y.data_ptr(), B, K1,
-                                                                  self.seed, self.offset, out.data_ptr(),
-                                                                  _stream_ptr(self.prob.device)),
-                          "crdpn_alias_draw_contrast")
+            _native.check(_native.lib().crdpn_alias_draw_contrast_local(*self.table_ptrs(), self.prob.numel(), int(row_base),
+                                                                        y.data_ptr(), B, K1, self.seed, self.offset,
+                                                                        out.data_ptr(), _stream_ptr(self.prob.device)),
+                          "crdpn_alias_draw_contrast_local")
         self.offset += B * K1
         return out
 

@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(256) alias_draw_kernel(const float* __restrict
                                                          const long long* __restrict__ alias, long long n,
                                                          long long count, unsigned long long seed,
                                                          unsigned long long offset, const long long* __restrict__ y,
-                                                         long long K1, long long* __restrict__ out) {
+                                                         long long K1, long long row_base, long long* __restrict__ out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool small = count < (1ll << 32) && K1 < (1ll << 32);  // 32-bit division: the 64-bit one is a ~100-instruction call
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) alias_draw_kernel(const float* __restrict
     const unsigned long long bits = ((unsigned long long)r[0] << 32) | (unsigned long long)r[1];
     const long long kk = (long long)__umul64hi(bits, (unsigned long long)n);
     const float u = (float)(r[2] >> 8) * 5.9604644775390625e-08f;
-    out[i] = (prob == nullptr || u < prob[kk]) ? kk : alias[kk];  // prob == NULL: uniform tables (prob = 1 everywhere)
+    out[i] = row_base + ((prob == nullptr || u < prob[kk]) ? kk : alias[kk]);  // prob == NULL: uniform tables (prob = 1 everywhere)
   }
 }
 
@@ -946,7 +946,7 @@ extern "C" int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_s
 }
 
 static int alias_draw_impl(const float* prob, const int64_t* alias, int64_t n, int64_t count, uint64_t seed,
-                           uint64_t offset, const int64_t* y, int64_t K1, int64_t* out, void* stream) {
+                           uint64_t offset, const int64_t* y, int64_t K1, int64_t row_base, int64_t* out, void* stream) {
   if ((prob == nullptr) != (alias == nullptr) || !out || n <= 0 || count < 0) return fail(CRDPN_E_BADARG, "crdpn_alias_draw: bad argument");
   if (count == 0) return CRDPN_OK;
   int device = 0;
@@ -958,19 +958,26 @@ static int alias_draw_impl(const float* prob, const int64_t* alias, int64_t n, i
   const long long cap = (long long)di.sms * 8;
   if (blocks > cap) blocks = cap;
   alias_draw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(prob, (const long long*)alias, n, count, seed, offset,
-                                                                  (const long long*)y, K1, (long long*)out);
+                                                                  (const long long*)y, K1, row_base, (long long*)out);
   CRDPN_LAUNCH_CHECK("alias_draw_kernel");
   return CRDPN_OK;
 }
 
 extern "C" int crdpn_alias_draw(const float* prob, const int64_t* alias, int64_t n, int64_t count,
                                 uint64_t seed, uint64_t offset, int64_t* out, void* stream) {
-  return alias_draw_impl(prob, alias, n, count, seed, offset, nullptr, 1, out, stream);
+  return alias_draw_impl(prob, alias, n, count, seed, offset, nullptr, 1, 0, out, stream);
 }
 
 extern "C" int crdpn_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t n, const int64_t* y,
                                          int64_t B, int64_t K1, uint64_t seed, uint64_t offset, int64_t* out,
                                          void* stream) {
   if (!y || B <= 0 || K1 <= 0) return fail(CRDPN_E_BADARG, "crdpn_alias_draw_contrast: bad argument");
-  return alias_draw_impl(prob, alias, n, B * K1, seed, offset, y, K1, out, stream);
+  return alias_draw_impl(prob, alias, n, B * K1, seed, offset, y, K1, 0, out, stream);
+}
+
+extern "C" int crdpn_alias_draw_contrast_local(const float* prob, const int64_t* alias, int64_t n_local, int64_t row_base,
+                                               const int64_t* y, int64_t B, int64_t K1, uint64_t seed, uint64_t offset,
+                                               int64_t* out, void* stream) {
+  if (!y || B <= 0 || K1 <= 0 || row_base < 0) return fail(CRDPN_E_BADARG, "crdpn_alias_draw_contrast_local: bad argument");
+  return alias_draw_impl(prob, alias, n_local, B * K1, seed, offset, y, K1, row_base, out, stream);
 }

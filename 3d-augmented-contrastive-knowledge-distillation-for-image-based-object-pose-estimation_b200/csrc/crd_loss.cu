@@ -55,3 +55,44 @@ extern "C" int crdpn_crd_loss_backward(
   return embed_backward2(f_s, s_dim, Ws, v1, inv1, grad_v1, f_t, t_dim, Wt, v2, inv2, grad_v2, scale, B, D, dWs, dbs, dxs, dWt,
                          dbt, dxt, d_pre_scratch, stream);
 }
+
+// Row-sharded banks, one process per GPU: local embed heads -> all-gather of the anchors over NVLink peer memory ->
+// (in-shard negative draw) -> scoring pass over this rank's shard + owner-only momentum update -> one-shot all-reduce of
+// the packed partials [grad_v1 | grad_v2 | 8 result scalars].  7 launches, one foreign call.
+extern "C" int crdpn_crd_loss_forward_sharded(
+    const float* f_s, int64_t s_dim, const float* Ws, const float* bs,
+    const float* f_t, int64_t t_dim, const float* Wt, const float* bt,
+    const int64_t* y_local, const int32_t* offs_host, void* const* peer_bufs_host, int rank, int world, int64_t Bmax,
+    int64_t Dmax,
+    const int64_t* contrast_idx, const float* alias_prob, const int64_t* alias_alias, uint64_t seed, uint64_t offset,
+    int64_t* idx_scratch,
+    void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+    int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
+    float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+    float* pre_s, float* pre_t, float* v1_local, float* v2_local, float* inv1, float* inv2,
+    float* v1_all, float* v2_all, int64_t* y_all, float* partial, double* result, float* reduced,
+    void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  if (!y_local || !offs_host || !peer_bufs_host || !v1_all || !v2_all || !y_all || !partial || !result || !reduced)
+    return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward_sharded: null pointer");
+  if (world < 1 || rank < 0 || rank >= world) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward_sharded: bad rank / world");
+  const int64_t B_loc = offs_host[rank + 1] - offs_host[rank], B = offs_host[world];
+  if (B_loc <= 0 || B <= 0) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward_sharded: every rank must hold at least one anchor");
+  int rc = embed_forward2(f_s, Ws, bs, s_dim, pre_s, v1_local, inv1, f_t, Wt, bt, t_dim, pre_t, v2_local, inv2, B_loc, D, stream);
+  if (rc) return rc;
+  rc = crdpn_p2p_allgather_anchors(v1_local, v2_local, y_local, D, offs_host, peer_bufs_host, rank, world, Bmax, Dmax, v1_all,
+                                   v2_all, y_all, stream);
+  if (rc) return rc;
+  const int64_t* idx = contrast_idx;
+  if (idx == nullptr) {  // K1-1 negatives drawn inside this rank's shard; column 0 stays the global positive index
+    if (!idx_scratch) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward_sharded: contrast_idx is NULL and so is idx_scratch");
+    rc = crdpn_alias_draw_contrast_local(alias_prob, alias_alias, row_end - row_begin, row_begin, y_all, B, K1, seed, offset,
+                                         idx_scratch, stream);
+    if (rc) return rc;
+    idx = idx_scratch;
+  }
+  rc = crdpn_crd_step(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, idx, y_all, B, K1, D, n_data, k_total, row_begin,
+                      row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, result, partial, partial + B * D, workspace,
+                      workspace_bytes, variant, stream);
+  if (rc) return rc;
+  return crdpn_p2p_allreduce_f32(partial, 2 * B * D, result, 8, reduced, peer_bufs_host, rank, world, Bmax, Dmax, stream);
+}

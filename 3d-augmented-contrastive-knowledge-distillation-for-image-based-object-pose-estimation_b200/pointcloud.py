@@ -46,8 +46,8 @@ class PointCloudSampler:
         Returns shapes [B, 3, P] float32 (and the chosen vertex rows [B, P] when return_subset)."""
         dev = self.device
         ids = torch.as_tensor(cloud_ids, dtype=torch.int64)
-        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= len(self.counts)) and not ids.is_cuda:
-            raise IndexError("cloud id out of range")
+        if not ids.is_cuda and ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= len(self.counts)):
+            raise IndexError("cloud id out of range")   # (device-resident ids are not read back: no hidden sync)
         ids = ids.to(dev).contiguous()
         B, P = ids.numel(), self.point_num
         rot = None

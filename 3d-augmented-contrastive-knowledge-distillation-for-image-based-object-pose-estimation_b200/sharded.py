@@ -215,13 +215,25 @@ class ShardedContrastMemory(ContrastMemory):
             self._px = PeerExchange(self.group, self.rank, self.world_size, device, max(B, 64), max(D, 128))
         return self._px
 
+    def _ensure_counts(self, b_loc, device):
+        """Per-rank batch sizes (collective, but only when this rank's batch size changes)."""
+        if self._counts is None or self._counts[self.rank] != b_loc:
+            cnt = torch.zeros(self.world_size, dtype=torch.int64, device=device)
+            cnt[self.rank] = b_loc
+            self._counts = self._all_reduce(cnt).tolist()
+        return self._counts
+
+    def _ensure_local_sampler(self, device):
+        """In-shard negatives come from this rank's own Philox stream."""
+        if getattr(self, "_local_sampler", None) is None:
+            from .crd import AliasMethod
+            self._local_sampler = AliasMethod(torch.ones(self.row_end - self.row_begin), seed=self.multinomial.seed + 7919 * (self.rank + 1))
+            self._local_sampler.to(device)
+        return self._local_sampler
+
     def _gather(self, v1, v2, y):
         """ONE packed exchange before the kernel: local anchors -> all anchors (uneven B_loc allowed)."""
-        if self._counts is None or self._counts[self.rank] != v1.shape[0]:
-            cnt = torch.zeros(self.world_size, dtype=torch.int64, device=v1.device)
-            cnt[self.rank] = v1.shape[0]
-            self._counts = self._all_reduce(cnt).tolist()  # once per batch-shape change
-        counts = self._counts
+        counts = self._ensure_counts(v1.shape[0], v1.device)
         rows = max(counts)
         self._anchor_offset = sum(counts[:self.rank])
         d = v1.shape[1]
@@ -239,14 +251,8 @@ class ShardedContrastMemory(ContrastMemory):
     def _prepare(self, v1, v2, y, idx):
         if idx is None and self.local_negatives:
             # in-shard negatives from this rank's own Philox stream; column 0 stays the global positive index
-            rows = self.row_end - self.row_begin
             K1 = self._host_params().K + 1
-            if getattr(self, "_local_sampler", None) is None:
-                from .crd import AliasMethod
-                self._local_sampler = AliasMethod(torch.ones(rows), seed=self.multinomial.seed + 7919 * (self.rank + 1))
-                self._local_sampler.to(v1.device)
-            idx = self._local_sampler.draw_contrast(y.contiguous().to(torch.int64), K1)
-            idx[:, 1:] += self.row_begin
+            idx = self._ensure_local_sampler(v1.device).draw_contrast(y.contiguous().to(torch.int64), K1, row_base=self.row_begin)
         return super()._prepare(v1, v2, y, idx)
 
     def fused_loss(self, v1, v2, y, idx=None):
@@ -254,6 +260,110 @@ class ShardedContrastMemory(ContrastMemory):
         g1, g2, gy = _GatherAnchors.apply(v1, v2, y, self)
         g1c, g2c, gy, idx = self._prepare(g1, g2, gy, idx)
         return _FusedCRDFunction.apply(g1c, g2c, gy, idx, self)
+
+
+class _ShardedCRDLossFunction(torch.autograd.Function):
+    """The sharded step with the peer-memory exchanges as one autograd node and two foreign calls
+    (``crdpn_crd_loss_forward_sharded``: 7 launches; ``crdpn_crd_loss_backward`` on the local rows: 2 launches)."""
+
+    @staticmethod
+    def forward(ctx, f_s, f_t, Ws, bs, Wt, bt, y, contrast_idx, crit):
+        from .crd import EPS
+        mem = crit.contrast
+        dev = f_s.device
+        xs, xt = f_s.detach(), f_t.detach()
+        if xs.dim() != 2 or not xs.is_contiguous():
+            xs = xs.reshape(xs.shape[0], -1).contiguous()
+        if xt.dim() != 2 or not xt.is_contiguous():
+            xt = xt.reshape(xt.shape[0], -1).contiguous()
+        Wsc, bsc, Wtc, btc = (t.detach() if t.is_contiguous() else t.detach().contiguous() for t in (Ws, bs, Wt, bt))
+        B_loc, D = xs.shape[0], Wsc.shape[0]
+        yc = y if (y.dtype == torch.int64 and y.is_contiguous()) else y.contiguous().to(torch.int64)
+        counts = mem._ensure_counts(B_loc, dev)
+        B = sum(counts)
+        a0 = sum(counts[:mem.rank])
+        hp = mem._host_params()
+        K1 = hp.K + 1
+        px = mem._peer_exchange(B, D, dev)
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        offs_c = (ctypes.c_int32 * (mem.world_size + 1))(*offs)
+        BD, BlD = B * D, B_loc * D
+        Bp = (B_loc + 3) & ~3
+        # one fp32 arena: [result(16) | pre_s | pre_t | v1_loc | v2_loc | inv1 | inv2 | v1_all | v2_all | partial(2BD) | reduced(2BD+8)]
+        arena = torch.empty(16 + 4 * BlD + 2 * Bp + 2 * BD + 2 * BD + 2 * BD + 8, dtype=torch.float32, device=dev)
+        base = arena.data_ptr()
+        o_pre_s, o_pre_t, o_v1l, o_v2l = (base + 4 * (16 + i * BlD) for i in range(4))
+        o_inv1 = base + 4 * (16 + 4 * BlD)
+        o_inv2 = o_inv1 + 4 * Bp
+        f_all = 16 + 4 * BlD + 2 * Bp
+        o_v1a, o_v2a, o_part = base + 4 * f_all, base + 4 * (f_all + BD), base + 4 * (f_all + 2 * BD)
+        f_red = f_all + 4 * BD
+        o_red = base + 4 * f_red
+        y_all = torch.empty(B, dtype=torch.int64, device=dev)
+        if contrast_idx is not None:
+            mem._check_device(contrast_idx, "contrast_idx")
+            contrast_idx = contrast_idx.contiguous().to(torch.int64)
+            if contrast_idx.shape != (B, K1):
+                raise RuntimeError(f"contrast_idx must have shape [B, K+1] = {(B, K1)}, got {tuple(contrast_idx.shape)}")
+            cidx_ptr, scratch_ptr, tables, seed, offset = contrast_idx.data_ptr(), None, (None, None), 0, 0
+        else:
+            smp = mem._ensure_local_sampler(dev)
+            scratch = mem._idx_scratch
+            if scratch is None or scratch.numel() != B * K1 or scratch.device != dev:
+                scratch = mem._idx_scratch = torch.empty(B * K1, dtype=torch.int64, device=dev)
+            cidx_ptr, scratch_ptr, tables, seed, offset = None, scratch.data_ptr(), smp.table_ptrs(), smp.seed, smp.offset
+        m1, m2, stride, dt = mem._banks()
+        variant = mem._step_variant(B, K1, D)
+        ws = mem._workspace(B, K1, D, dev, variant)
+        with _native.on_device(dev):
+            rc = _native.lib().crdpn_crd_loss_forward_sharded(
+                xs.data_ptr(), xs.shape[1], Wsc.data_ptr(), bsc.data_ptr(), xt.data_ptr(), xt.shape[1], Wtc.data_ptr(), btc.data_ptr(),
+                yc.data_ptr(), offs_c, px._ptrs, mem.rank, mem.world_size, px.Bmax, px.Dmax,
+                cidx_ptr, tables[0], tables[1], seed, offset, scratch_ptr,
+                m1.data_ptr(), m2.data_ptr(), stride, dt, K1, D, mem.nLem, mem.k_total, mem.row_begin, mem.row_end,
+                hp.T, hp.Z1, hp.Z2, EPS, hp.m, 1.0 - hp.m,
+                o_pre_s, o_pre_t, o_v1l, o_v2l, o_inv1, o_inv2, o_v1a, o_v2a, y_all.data_ptr(), o_part, base, o_red,
+                ws.data_ptr(), ws.numel(), variant, _stream_ptr(dev))
+        _native.check(rc, "crdpn_crd_loss_forward_sharded")
+        if contrast_idx is None:
+            smp.offset += B * K1
+        ctx.save_for_backward(arena, xs, xt, Wsc, Wtc)
+        ctx.geom = (B, B_loc, D, a0, f_red, f_s.shape, f_t.shape)
+        ctx.need_dx = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return arena[f_red + 2 * BD + 5]   # loss_s + loss_t of the WHOLE batch, summed over ranks
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        arena, xs, xt, Ws, Wt = ctx.saved_tensors
+        B, B_loc, D, a0, f_red, shp_s, shp_t = ctx.geom
+        dev = xs.device
+        BD, BlD = B * D, B_loc * D
+        Bp = (B_loc + 3) & ~3
+        base = arena.data_ptr()
+        o_v1l, o_v2l = base + 4 * (16 + 2 * BlD), base + 4 * (16 + 3 * BlD)
+        o_inv1 = base + 4 * (16 + 4 * BlD)
+        o_inv2 = o_inv1 + 4 * Bp
+        o_g1 = base + 4 * (f_red + a0 * D)            # this rank's rows of the rank-summed gradients
+        o_g2 = base + 4 * (f_red + BD + a0 * D)
+        scale = grad_out.detach().to(torch.float32).contiguous()
+        dWs, dWt = torch.empty_like(Ws), torch.empty_like(Wt)
+        dbs = torch.empty(2 * D, dtype=torch.float32, device=dev)
+        dxs = torch.empty_like(xs) if ctx.need_dx[0] else None
+        dxt = torch.empty_like(xt) if ctx.need_dx[1] else None
+        d_pre = torch.empty(2 * BlD, dtype=torch.float32, device=dev)
+        with _native.on_device(dev):
+            rc = _native.lib().crdpn_crd_loss_backward(
+                xs.data_ptr(), xs.shape[1], Ws.data_ptr(), o_v1l, o_inv1, o_g1,
+                xt.data_ptr(), xt.shape[1], Wt.data_ptr(), o_v2l, o_inv2, o_g2,
+                scale.data_ptr(), B_loc, D,
+                dWs.data_ptr(), dbs.data_ptr(), dxs.data_ptr() if dxs is not None else None,
+                dWt.data_ptr(), dbs.data_ptr() + 4 * D, dxt.data_ptr() if dxt is not None else None,
+                d_pre.data_ptr(), _stream_ptr(dev))
+        _native.check(rc, "crdpn_crd_loss_backward")
+        return (dxs.view(shp_s) if dxs is not None else None, dxt.view(shp_t) if dxt is not None else None,
+                dWs, dbs[:D], dWt, dbs[D:], None, None, None)
 
 
 class ShardedCRDLoss(nn.Module):
@@ -273,7 +383,15 @@ class ShardedCRDLoss(nn.Module):
                                               comm=comm, **memory_kwargs)
 
     def forward(self, f_s, f_t, idx, contrast_idx=None):
-        return self.contrast.fused_loss(self.embed_s(f_s), self.embed_t(f_t), idx, contrast_idx)
+        mem = self.contrast
+        hp = mem._host_params()
+        fast = (mem.comm == "p2p" and mem.world_size > 1 and hp.Z1 > 0 and hp.Z2 > 0 and f_s.is_cuda and f_t.is_cuda
+                and f_s.dtype == torch.float32 and f_t.dtype == torch.float32
+                and (contrast_idx is not None or mem.local_negatives))
+        if fast:   # (the first call freezes Z through the general path below)
+            return _ShardedCRDLossFunction.apply(f_s, f_t, self.embed_s.linear.weight, self.embed_s.linear.bias,
+                                                 self.embed_t.linear.weight, self.embed_t.linear.bias, idx, contrast_idx, self)
+        return mem.fused_loss(self.embed_s(f_s), self.embed_t(f_t), idx, contrast_idx)
 
     def allreduce_embed_grads(self):
         grads = [p.grad for p in list(self.embed_s.parameters()) + list(self.embed_t.parameters()) if p.grad is not None]

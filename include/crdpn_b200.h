@@ -277,6 +277,29 @@ int crdpn_pointcloud_sample(const double* vertices, const int64_t* cloud_offsets
                             const float* rotation_deg, const int64_t* subset, uint64_t seed, uint64_t offset,
                             int64_t B, int64_t P, float* out, int64_t* subset_out, void* stream);
 
+/* The sharded step's forward as ONE call (one process per GPU, exchanges over NVLink peer memory as above): both embed
+ * heads on the LOCAL anchors -> crdpn_p2p_allgather_anchors -> [contrast_idx == NULL: crdpn_alias_draw_contrast_local,
+ * K1-1 negatives per anchor inside this rank's shard] -> crdpn_crd_step over the shard (gradients into `partial`
+ * [2*B*D]) -> crdpn_p2p_allreduce_f32 into `reduced` [2*B*D + 8] (the 8 result scalars ride behind the gradients as
+ * fp32 words; word 5 is the loss of the whole batch).  7 launches.  The backward is crdpn_crd_loss_backward on the local
+ * rows of `reduced`.  offs_host[world+1] = prefix sums of the per-rank batch sizes; B = offs_host[world]. */
+int crdpn_alias_draw_contrast_local(const float* prob, const int64_t* alias, int64_t n_local, int64_t row_base,
+                                    const int64_t* y, int64_t B, int64_t K1, uint64_t seed, uint64_t offset,
+                                    int64_t* out, void* stream);
+int crdpn_crd_loss_forward_sharded(
+    const float* f_s, int64_t s_dim, const float* Ws, const float* bs,
+    const float* f_t, int64_t t_dim, const float* Wt, const float* bt,
+    const int64_t* y_local, const int32_t* offs_host, void* const* peer_bufs_host, int rank, int world, int64_t Bmax,
+    int64_t Dmax,
+    const int64_t* contrast_idx, const float* alias_prob, const int64_t* alias_alias, uint64_t seed, uint64_t offset,
+    int64_t* idx_scratch,
+    void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+    int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
+    float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+    float* pre_s, float* pre_t, float* v1_local, float* v2_local, float* inv1, float* inv2,
+    float* v1_all, float* v2_all, int64_t* y_all, float* partial, double* result, float* reduced,
+    void* workspace, size_t workspace_bytes, int variant, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * PointNet encoder, eval-mode BatchNorm (the KD-time teacher, KD/common/base_class.py:317,363).
  * Replaces: ShapeEncoderPC.forward, auxiliary/model.py:174-180 (conv1/bn1/relu, conv2/bn2/relu,

@@ -108,7 +108,7 @@ void oracle_alias_draw_contrast(const float* prob, const int64_t* alias, int64_t
 /* ------------------------------------------------------------------------------------------------
  * ContrastMemory.forward scoring + ContrastLoss + closed-form backward, fp64 accumulation.
  *   s1[b,k] = <bank2[idx[b,k]], v1[b]>,  s2[b,k] = <bank1[idx[b,k]], v2[b]>
- *   e = exp(s / T);  o = e / Z;  c = K*Pn + eps,  Pn = 1/n_data,  K = K1-1 (or k_total when the
+ *   e = exp(s / T);  o = e / Z;  c = fp32(K*Pn + eps),  K*Pn as fp32,  Pn = 1/n_data,  K = K1-1 (or k_total when the
  *   negatives of an anchor are split over several shards, each with its own index list)
  *   loss_x = -( sum_b log(o_b0/(o_b0+c)) + sum_b sum_{k>=1} log(K*Pn/(o_bk+c)) ) / B
  *   dL/ds: positive -c/(B*T*(o+c)), negative +o/(B*T*(o+c));  grad_v1[b] = sum_k dL/ds1 * bank2[row], ...
@@ -125,8 +125,12 @@ void oracle_crd_score(const float* bank1, const float* bank2, int64_t row_stride
                       double* out_v1, double* out_v2, double* res, double* grad_v1, double* grad_v2) {
   const double K = (double)(k_total > 0 ? k_total : (K1 - 1)); /* negatives per anchor over all shards */
   const double Pn = 1.0 / (double)n_data;
-  const double c = K * Pn + eps;
-  const double mPn = K * Pn;
+  /* The published ContrastLoss works on fp32 tensors: `P_pos.add(m * Pn + eps)` and `P_neg.clone().fill_(m * Pn)` round the
+   * two Python-float constants to float32 before they meet the data.  With eps = 1e-7 next to K*Pn ~ 0.07 that rounding
+   * moves eps by up to 4 % (float spacing 7.5e-9), and over K = 65536 negatives it shifts the loss by ~3e-3: part of the
+   * published arithmetic, so the oracle uses the same float32 constants (everything else stays fp64). */
+  const double c = (double)(float)(K * Pn + eps);
+  const double mPn = (double)(float)(K * Pn);
   double ls = 0.0, lt = 0.0, se1 = 0.0, se2 = 0.0, cnt = 0.0;
   if (grad_v1) memset(grad_v1, 0, sizeof(double) * (size_t)(B * D));
   if (grad_v2) memset(grad_v2, 0, sizeof(double) * (size_t)(B * D));

@@ -37,13 +37,17 @@ def _case(B, K1, D, N, seed=0, dup_positive=False):
 
 def _score(pkg, dev, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=0, row_end=None, want_out=True, variant=0,
            dtype=torch.float32, interleaved=True, k_total=0):
-    """Direct C-ABI call. `bank` is the FULL [N,2,D] fp32 CPU tensor; the shard slice is uploaded."""
+    """Direct C-ABI call. `bank` is the FULL [N,2,D] fp32 tensor; a CPU bank's shard slice is uploaded, a bank that
+    already lives on the device (fp32, interleaved) is used in place."""
     lib = pkg._native.lib()
     row_end = N if row_end is None else row_end
     B, K1 = idx.shape
     D = v1.shape[1]
     shard = bank[row_begin:row_end].to(dtype)
-    if interleaved:
+    if bank.is_cuda:
+        assert interleaved and dtype == torch.float32
+        b1, b2, stride = shard[:, 0, :], shard[:, 1, :], 2 * D
+    elif interleaved:
         dbank = shard.contiguous().to(dev)
         b1, b2, stride = dbank[:, 0, :], dbank[:, 1, :], 2 * D
     else:
@@ -452,3 +456,55 @@ def test_alias_uniform_shortcut_draws_the_same_indices(pkg, oracle, cuda):
     assert not skew.uniform
     prob, alias = oracle.alias_build(np.arange(1, N + 1, dtype=np.float32))
     assert np.array_equal(skew.draw(4096).cpu().numpy(), oracle.alias_draw(prob, alias, 4096, 77, 0))
+
+
+def test_headline_config_properties_full_size(pkg, oracle, cuda):
+    """BASELINE configs[3] on one GPU (B=46, D=128, K=65536, N=1M rows x 2 banks) -- far too big for the scalar oracle as a
+    whole, so parity is carried by properties that do not depend on the size:
+      * two anchors scored by the oracle (their K+1 entries against the full 1M-row banks): gradient rows and the
+        anchors' loss terms equal the kernel's (a gradient row depends on its own anchor only);
+      * anchor additivity: loss(all 46) = sum_b loss(anchor b alone) / 46;
+      * shard additivity: four row shards' losses, counts and gradients add up to the unsharded result;
+      * permuting the K negative columns changes nothing beyond fp32 summation order;
+      * bit-reproducibility run to run."""
+    B, K1, D, N, T, Z1, Z2 = 46, 65537, 128, 1_000_000, 0.07, 2.1e6, 2.2e6
+    bank_cpu, v1, v2, y, idx = _case(B, K1, D, N, seed=46)
+    bank = bank_cpu.to(cuda)          # 1 GB, uploaded once
+    full = _score(pkg, cuda, bank, v1, v2, idx, N, T, Z1, Z2, want_out=False)
+    again = _score(pkg, cuda, bank, v1, v2, idx, N, T, Z1, Z2, want_out=False)
+    assert np.array_equal(full["res"], again["res"]) and np.array_equal(full["g1"], again["g1"])
+    assert full["res"][4] == B * K1
+    # (1) oracle on two anchors
+    sh = bank_cpu.numpy()
+    tot_s = tot_t = 0.0
+    single = {}
+    for b in range(B):
+        one = _score(pkg, cuda, bank, v1[b:b + 1], v2[b:b + 1], idx[b:b + 1], N, T, Z1, Z2, want_out=False)
+        single[b] = one
+        tot_s += one["res"][0] / B
+        tot_t += one["res"][1] / B
+        # a one-anchor batch scales dL/ds by 1/(1*T) instead of 1/(46*T)
+        assert _rel(one["g1"][0] / B, full["g1"][b]) < 1e-5 and _rel(one["g2"][0] / B, full["g2"][b]) < 1e-5
+    for b in (0, 45):
+        want = oracle.crd_score(sh[:, 0, :], sh[:, 1, :], v1[b:b + 1].numpy(), v2[b:b + 1].numpy(), idx[b:b + 1].numpy(),
+                                N, T, Z1, Z2, want_out=False)
+        assert _rel(single[b]["res"][0], want["loss_s"]) < REL32 and _rel(single[b]["res"][1], want["loss_t"]) < REL32
+        assert _rel(single[b]["g1"], want["grad_v1"]) < REL32 and _rel(single[b]["g2"], want["grad_v2"]) < REL32
+    # (2) anchor additivity
+    assert _rel(tot_s, full["res"][0]) < 1e-6 and _rel(tot_t, full["res"][1]) < 1e-6
+    # (3) shard additivity
+    acc = dict(ls=0.0, lt=0.0, cnt=0.0, g1=np.zeros((B, D)), g2=np.zeros((B, D)))
+    for r in range(4):
+        lo, hi = N * r // 4, N * (r + 1) // 4
+        part = _score(pkg, cuda, bank, v1, v2, idx, N, T, Z1, Z2, row_begin=lo, row_end=hi, want_out=False)
+        acc["ls"] += part["res"][0]; acc["lt"] += part["res"][1]; acc["cnt"] += part["res"][4]
+        acc["g1"] += part["g1"]; acc["g2"] += part["g2"]
+    assert acc["cnt"] == B * K1
+    assert _rel(acc["ls"], full["res"][0]) < 1e-6 and _rel(acc["lt"], full["res"][1]) < 1e-6
+    assert _rel(acc["g1"], full["g1"]) < 1e-5 and _rel(acc["g2"], full["g2"]) < 1e-5
+    # (4) column permutation
+    perm = torch.randperm(K1 - 1, generator=torch.Generator().manual_seed(1)) + 1
+    idx_p = idx.clone()
+    idx_p[:, 1:] = idx[:, perm]
+    p = _score(pkg, cuda, bank, v1, v2, idx_p, N, T, Z1, Z2, want_out=False)
+    assert _rel(p["res"][0], full["res"][0]) < 1e-6 and _rel(p["g1"], full["g1"]) < 1e-5 and _rel(p["g2"], full["g2"]) < 1e-5

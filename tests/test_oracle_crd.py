@@ -103,8 +103,9 @@ def test_tiny_hand_computed_case(oracle):
     s2 = [f(0.6) * f(0.8) - f(0.8) * f(0.6), f(0.8), -f(0.8)]           # bank1[idx] . v2
     o1 = [math.exp(s / T) / Z1 for s in s1]
     o2 = [math.exp(s / T) / Z2 for s in s2]
-    mPn = 2 / N
-    c = mPn + eps
+    # the published ContrastLoss adds / fills these two Python floats into fp32 tensors: they act as float32 values
+    mPn = f(2 / N)
+    c = f(2 / N + eps)
     nce = lambda o: -(math.log(o[0] / (o[0] + c)) + sum(math.log(mPn / (x + c)) for x in o[1:])) / 1
     res = oracle.crd_score(bank1, bank2, v1, v2, idx, N, T, Z1, Z2, eps)
     assert res["loss_s"] == pytest.approx(nce(o1), rel=1e-12)
