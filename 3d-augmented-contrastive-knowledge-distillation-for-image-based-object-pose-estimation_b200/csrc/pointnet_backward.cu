@@ -329,7 +329,9 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t bar_ld = base + kP2Bar, bar_mma = base + kP2Bar + 8;
+  // bar_mma: the accumulator the next epilogue reads (D1, then D3); bar_acc: the persistent accumulators T2 / M1 / M2,
+  // whose MMAs run on under epilogue 3 and are only waited for before their operands are overwritten
+  const uint32_t bar_ld = base + kP2Bar, bar_mma = base + kP2Bar + 8, bar_acc = base + kP2Bar + 16;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kP2Bar + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hf = warp >> 2;
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
   if (tid == 0) {
     mbar_init(bar_ld, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512u);
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
   const float* istd3 = p.stats + kStatIstd3(p.F);
   constexpr uint32_t kI128 = make_idesc(128, 128), kI80 = make_idesc(128, 80);
 
-  uint32_t n_ld = 0, n_mma = 0;       // completed phases of the two barriers (uniform across the CTA)
+  uint32_t n_ld = 0, n_mma = 0, n_acc = 0;   // completed phases of the barriers (uniform across the CTA)
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tph = clock64();
   auto mark = [&](int i) { if (p.debug) { const long long t = clock64(); ph[i] += t - tph; tph = t; } };
@@ -448,6 +451,24 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
     x_prefetched = false;
     __syncthreads();
     mark(0);
+    // ---- MMA phase 1 (stream A): D1 = Q h2^T is issued now and runs under the h1^T build below
+    if (A && warp == 0) {
+      mbar_wait(bar_ld, n_ld & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dq = umma_desc_sw128(base + kP2Q), dh2 = umma_desc_sw128(base + kP2H2);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tmem, dq + koff128(kk), dh2 + koff128(kk), kI128, kk > 0);
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    // the previous tile's T2 / M1 / M2 MMAs still read H1T, GZT and H2T: they must have retired before those are rewritten
+    if (ntiles_done > 1) {
+      mbar_wait(bar_acc, n_acc & 1u);
+      ++n_acc;
+      tc_fence_after();
+    }
     // ---- h1^T operand image: rows j < 64 = relu(bn1(conv1 x)) (bf16), row 64 = 1 for real points
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -484,23 +505,10 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
     __syncthreads();
     tc_fence_after();
     mark(1);
-    // ---- MMA phase 1 (stream A): D1 = Q h2^T, M1 += h1^T h1
     if (A) {
-      mbar_wait(bar_ld, n_ld & 1u);
+      mbar_wait(bar_ld, n_ld & 1u);     // every thread reads h2 from shared memory in epilogue 1
       ++n_ld;
-      if (warp == 0) {
-        if (elect_one()) {
-          const uint64_t dq = umma_desc_sw128(base + kP2Q), dh2 = umma_desc_sw128(base + kP2H2);
-          const uint64_t dh1t = umma_desc_sw128(base + kP2H1T);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_f16(tmem, dq + koff128(kk), dh2 + koff128(kk), kI128, kk > 0);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + kTmM1, dh1t + koff128(kk), dh1t + koff128(kk), kI128, (m_started || kk > 0) ? 1u : 0u);
-          umma_commit(bar_mma);
-        }
-        __syncwarp();
-      }
-      mbar_wait(bar_mma, n_mma & 1u);
+      mbar_wait(bar_mma, n_mma & 1u);   // D1
       ++n_mma;
       tc_fence_after();
     }
@@ -517,7 +525,8 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
     __syncthreads();
     tc_fence_after();
     mark(3);
-    // ---- MMA phase 2: T2 += gz2^T [h1 | 1] ; (A) M2 += h2^T h2 ; D3 = (a2 W2)^T gz2^T
+    // ---- MMA phase 2: D3 = (a2 W2)^T gz2^T first (epilogue 3 waits for it alone), then the persistent accumulators
+    //      T2 += gz2^T [h1 | 1] ; (A) M1 += h1^T h1, M2 += h2^T h2, which run on under epilogue 3
     if (warp == 0) {
       if (elect_one()) {
         const uint64_t dgzt = umma_desc_sw128(base + kP2GZT), dh1t = umma_desc_sw128(base + kP2H1T);
@@ -525,13 +534,16 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
         const uint64_t dgy = umma_desc_sw128(base + kP2H2);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_f16(tmem, dw2t + koff128(kk), dgy + koff128(kk), kI128, kk > 0);
+        umma_commit(bar_mma);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + kTmT2, dgzt + koff128(kk), dh1t + koff128(kk), kI80, (t2_started || kk > 0) ? 1u : 0u);
         if (A) {
 #pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + kTmM1, dh1t + koff128(kk), dh1t + koff128(kk), kI128, (m_started || kk > 0) ? 1u : 0u);
+#pragma unroll
           for (int kk = 0; kk < 8; ++kk) umma_f16(tmem + kTmM2, dh2t + koff128(kk), dh2t + koff128(kk), kI128, (m_started || kk > 0) ? 1u : 0u);
         }
-        umma_commit(bar_mma);
+        umma_commit(bar_acc);
       }
       __syncwarp();
     }
@@ -598,6 +610,10 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
     printf("pass2 cta0 t%d tiles %d cycles: load %lld h1t %lld mma1 %lld e1 %lld mma2 %lld e3+sync %lld\n", tid, ntiles_done,
            ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]);
   // ---- flush: per-CTA partials of the three persistent accumulators, per-thread channel sums
+  if (ntiles_done > 0) {
+    mbar_wait(bar_acc, n_acc & 1u);
+    tc_fence_after();
+  }
   {
     float* part = p.part + (size_t)blockIdx.x * kPartFloats;
     uint32_t r[32];
