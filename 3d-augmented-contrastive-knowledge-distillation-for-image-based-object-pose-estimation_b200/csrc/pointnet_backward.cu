@@ -392,8 +392,38 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
   };
   int tile = (int)blockIdx.x - (int)gridDim.x;
   tile = next_tile(tile);
-  bool h2_prefetched = false, x_prefetched = false;
+  bool h2_prefetched = false, x_prefetched = false, b_prefetched = false;
   float px0 = 0.f, px1 = 0.f, px2 = 0.f;
+  // stream-B gather of one virtual-point row (thread = (row r, 64-channel half)): arg-max indirection, then the h2 row,
+  // the point's coordinates and the entry's coefficient, all into registers -- issued one tile ahead under epilogue 3
+  uint4 brow[8];
+  int bc = 0;
+  float bcoef = 0.f;
+  int bn = 0, bbb = 0;
+  size_t bge = 0;
+  auto gather_b_index = [&](int t) {   // stage 1: which point? (issued before the MMA wait so that its latency hides there)
+    const int r = tid >> 1;
+    if (r >= tile_valid(t)) return;
+    const long long e = (long long)(t - p.nA) * 128 + r;
+    bc = (int)(e / p.B);               // channel-major: a tile sees <= 2 channels
+    bbb = (int)(e - (long long)bc * p.B);
+    bge = (size_t)bbb * p.F + bc;
+    bn = p.argmax[bge];
+  };
+  auto gather_b_rows = [&](int t) {    // stage 2: the h2 row, the point's coordinates, the entry's coefficient
+    const int r = tid >> 1, part = tid & 1;
+    if (r >= tile_valid(t)) return;
+    const char* src = p.h2img + ((size_t)bbb * p.tiles2 + (bn >> 7)) * kTileBytes + part * kKBlockBytes;
+    const int sr = bn & 127;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) brow[jj] = *reinterpret_cast<const uint4*>(src + sw128_off(sr, jj * 8));
+    if (part == 0) {
+      const float* xc = p.x + (size_t)bbb * 3 * p.P;
+      px0 = __ldg(xc + bn); px1 = __ldg(xc + p.P + bn); px2 = __ldg(xc + 2 * p.P + bn);
+      bcoef = p.g3[bc] * istd3[bc] * p.g[bge];
+    }
+  };
+  auto gather_b = [&](int t) { gather_b_index(t); gather_b_rows(t); };
 
   while (tile < ntot) {
     const bool A = tile < p.nA;
@@ -422,24 +452,15 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
       }
     } else {
       const int r = tid >> 1, part = tid & 1;
-      const long long e = (long long)(tile - p.nA) * 128 + r;
       uint8_t* dst = sm + kP2H2 + part * kKBlockBytes;
       if (r < nvalid) {
-        const int c = (int)(e / p.B), bb = (int)(e - (long long)c * p.B);   // channel-major: a tile sees <= 2 channels
-        const size_t ge = (size_t)bb * p.F + c;
-        const int n = p.argmax[ge];
-        const char* src = p.h2img + ((size_t)bb * p.tiles2 + (n >> 7)) * kTileBytes + part * kKBlockBytes;
-        const int sr = n & 127;
-        uint4 row[8];
+        if (!b_prefetched) gather_b(tile);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) row[jj] = *reinterpret_cast<const uint4*>(src + sw128_off(sr, jj * 8));
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(dst + sw128_off(r, jj * 8)) = row[jj];
+        for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(dst + sw128_off(r, jj * 8)) = brow[jj];
         if (part == 0) {
-          const float* xc = p.x + (size_t)bb * 3 * p.P;
-          xs[r] = __ldg(xc + n); xs[128 + r] = __ldg(xc + p.P + n); xs[256 + r] = __ldg(xc + 2 * p.P + n);
-          centry[r] = c;
-          coefs[r] = p.g3[c] * istd3[c] * p.g[ge];
+          xs[r] = px0; xs[128 + r] = px1; xs[256 + r] = px2;
+          centry[r] = bc;
+          coefs[r] = bcoef;
         }
       } else {
 #pragma unroll
@@ -449,6 +470,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
     }
     h2_prefetched = false;
     x_prefetched = false;
+    b_prefetched = false;
     __syncthreads();
     mark(0);
     // ---- MMA phase 1 (stream A): D1 = Q h2^T is issued now and runs under the h1^T build below
@@ -549,6 +571,7 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
     }
     t2_started = true;
     if (A) m_started = true;
+    if (nxt >= p.nA && nxt < ntot) gather_b_index(nxt);
     mbar_wait(bar_mma, n_mma & 1u);
     ++n_mma;
     tc_fence_after();
@@ -572,6 +595,9 @@ __global__ void __launch_bounds__(256, 1) pn_bwd_pass2_kernel(const Pass2Params 
         px1 = ok ? __ldg(xc + p.P + n) : 0.f;
         px2 = ok ? __ldg(xc + 2 * p.P + n) : 0.f;
       }
+    } else if (nxt < ntot) {
+      gather_b_rows(nxt);
+      b_prefetched = true;
     }
     // ---- epilogue 3: thread = layer-1 channel j < 64, its half of the points
     if (q < 2) {
