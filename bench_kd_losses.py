@@ -57,8 +57,10 @@ def bench_kd_losses(pkg, torch, dev, args, n=138, C=200):
         launches = (pkg._native.launch_count() - l0) // (steps + warmup)
         res[name] = {"us_per_call": us, "rows": rows, "launches_per_call": launches}
     res["workload"] = f"kd_losses_n{n}_C{C}_bins24-12-24"
-    res["note"] = ("device time per forward+backward through the public functions (host-launch bound: the work is ~1 MFLOP); "
-                   "the eager formulation is ~50 forward + ~80 backward launches for the mixer")
+    res["note"] = ("time per forward+backward through the public autograd functions, i.e. host-bound (autograd node + 7 leaf "
+                   "accumulations); the kernels themselves take 12 + 12 us (mixer) and 4.5 + 14 + 20 us (infoNCE_KD), see "
+                   "profiles/r1_launches_kd_losses_pointcloud.csv; the eager formulation is ~50 forward + ~80 backward "
+                   "launches for the mixer")
     if not os.environ.get("CRDPN_BENCH_QUICK"):
         from oracle import kd_losses_oracle as ko  # CPU baseline leg only
         torch.set_num_threads(os.cpu_count() or 1)
