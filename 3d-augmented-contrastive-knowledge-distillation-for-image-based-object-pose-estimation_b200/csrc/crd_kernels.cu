@@ -861,6 +861,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
   bp.count = (unsigned*)(ws + L.count); bp.off = (unsigned*)(ws + L.off); bp.cursor = (unsigned*)(ws + L.cursor);
   bp.records = (unsigned*)(ws + L.records);
   bp.T = L.T;
+  bp.vec_ok = ((uintptr_t)contrast_idx & 15) == 0 ? 1 : 0;
 
   const double Kd = (double)(k_total > 0 ? k_total : (K1 - 1));
   const double Pn = 1.0 / (double)n_data;
@@ -884,6 +885,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
   static bool attr_set[64] = {false};
   if (!attr_set[device]) {
     CRDPN_CUDA(cudaFuncSetAttribute(ts::crd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmemBytes));
+    CRDPN_CUDA(cudaFuncSetAttribute(ts::ts_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kScanSmemMax * 4));
     attr_set[device] = true;
   }
   {
@@ -892,7 +894,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
     const int pre_grid = di.sms * 8;
     ts::ts_hist_kernel<<<pre_grid, 256, 0, st>>>(bp);
     CRDPN_LAUNCH_CHECK("ts_hist_kernel");
-    ts::ts_scan_kernel<<<1, 1024, 0, st>>>(bp);
+    ts::ts_scan_kernel<<<1, 1024, L.T <= ts::kScanSmemMax ? (size_t)L.T * 4 : 0, st>>>(bp);
     CRDPN_LAUNCH_CHECK("ts_scan_kernel");
     ts::ts_scatter_kernel<<<pre_grid, 256, 0, st>>>(bp);
     CRDPN_LAUNCH_CHECK("ts_scatter_kernel");

@@ -85,21 +85,65 @@ struct BucketParams {
   unsigned* cursor;       // [T + 1]
   unsigned* records;      // [P + 8]
   int T;
+  int vec_ok;             // idx is 16-byte aligned: 128-bit index loads
 };
 
+// four indices per thread per iteration (two 16-byte loads in flight, then four independent atomics)
 __global__ void __launch_bounds__(256) ts_hist_kernel(const BucketParams p) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P; i += stride) {
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = p.vec_ok ? p.P / 4 : 0;
+  const longlong2* idx2 = reinterpret_cast<const longlong2*>(p.idx);
+  for (long long g = t0; g < n4; g += stride) {
+    const longlong2 a = __ldg(idx2 + 2 * g), b = __ldg(idx2 + 2 * g + 1);
+    const long long r[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (r[q] >= p.row_begin && r[q] < p.row_end) atomicAdd(p.count + ((r[q] - p.row_begin) >> 5), 1u);
+  }
+  for (long long i = 4 * n4 + t0; i < p.P; i += stride) {
     const long long r = p.idx[i];
     if (r >= p.row_begin && r < p.row_end) atomicAdd(p.count + ((r - p.row_begin) >> 5), 1u);
   }
 }
 
-// one CTA: exclusive scan of count[0..T) -> off[0..T], cursor = off
+// one CTA: exclusive scan of count[0..T) -> off[0..T], cursor = off.  T <= kScanSmemMax: the counts are staged in shared
+// memory with every load in flight at once and each thread scans a contiguous (odd-length: conflict-free) segment;
+// larger T falls back to a chunked loop.
+constexpr int kScanSmemMax = 48 * 1024;
 __global__ void __launch_bounds__(1024) ts_scan_kernel(const BucketParams p) {
+  extern __shared__ unsigned scan_smem[];
   __shared__ unsigned warp_tot[32];
   __shared__ unsigned carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.T <= kScanSmemMax) {
+    for (int i = threadIdx.x; i < p.T; i += 1024) scan_smem[i] = p.count[i];
+    __syncthreads();
+    const int seg = ((p.T + 1023) / 1024) | 1;   // odd segment length
+    const int i0 = threadIdx.x * seg, i1 = min(i0 + seg, p.T);
+    unsigned tsum = 0;
+    for (int i = i0; i < i1; ++i) tsum += scan_smem[i];
+    unsigned incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+    unsigned run = wbase + incl - tsum;
+    for (int i = i0; i < i1; ++i) {
+      const unsigned c = scan_smem[i];
+      scan_smem[i] = run;
+      run += c;
+    }
+    if (threadIdx.x == 1023) carry_s = wbase + incl;
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.T; i += 1024) { const unsigned v = scan_smem[i]; p.off[i] = v; p.cursor[i] = v; }
+    if (threadIdx.x == 0) p.off[p.T] = carry_s;
+    return;
+  }
   if (threadIdx.x == 0) carry_s = 0u;
   __syncthreads();
   for (int base = 0; base < p.T; base += 1024 * 4) {
@@ -131,17 +175,27 @@ __global__ void __launch_bounds__(1024) ts_scan_kernel(const BucketParams p) {
   if (threadIdx.x == 0) p.off[p.T] = carry_s;
 }
 
+__device__ __forceinline__ void ts_scatter_one(const BucketParams& p, long long i, long long r) {
+  if (r < p.row_begin || r >= p.row_end) return;
+  const unsigned local = (unsigned)(r - p.row_begin);
+  const unsigned b = (unsigned)i / p.K1;                 // P < 2^31 (checked on the host)
+  const bool pos = (unsigned)i - b * p.K1 == 0u;
+  const unsigned slot = atomicAdd(p.cursor + (local >> 5), 1u);
+  p.records[slot] = make_record(local & 31u, b, pos);
+}
+
 __global__ void __launch_bounds__(256) ts_scatter_kernel(const BucketParams p) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P; i += stride) {
-    const long long r = p.idx[i];
-    if (r < p.row_begin || r >= p.row_end) continue;
-    const unsigned local = (unsigned)(r - p.row_begin);
-    const unsigned b = (unsigned)i / p.K1;                 // P < 2^31 (checked on the host)
-    const bool pos = (unsigned)i - b * p.K1 == 0u;
-    const unsigned slot = atomicAdd(p.cursor + (local >> 5), 1u);
-    p.records[slot] = make_record(local & 31u, b, pos);
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = p.vec_ok ? p.P / 4 : 0;
+  const longlong2* idx2 = reinterpret_cast<const longlong2*>(p.idx);
+  for (long long g = t0; g < n4; g += stride) {
+    const longlong2 a = __ldg(idx2 + 2 * g), b = __ldg(idx2 + 2 * g + 1);
+    ts_scatter_one(p, 4 * g + 0, a.x);
+    ts_scatter_one(p, 4 * g + 1, a.y);
+    ts_scatter_one(p, 4 * g + 2, b.x);
+    ts_scatter_one(p, 4 * g + 3, b.y);
   }
+  for (long long i = 4 * n4 + t0; i < p.P; i += stride) ts_scatter_one(p, i, p.idx[i]);
 }
 
 struct StreamParams {

@@ -247,6 +247,12 @@ def test_alias_draw_bit_exact(pkg, oracle, cuda):
     y = torch.tensor([5, 999, 0, 17], device=cuda)
     c = am.draw_contrast(y, 1025).cpu().numpy()
     assert np.array_equal(c, oracle.alias_draw_contrast(prob, alias, y.cpu().numpy(), 1025, seed=1234, offset=100080))
+    # a shard's sampler: local draws shifted by the shard's first row, column 0 still the GLOBAL positive index
+    c2 = am.draw_contrast(y + 70000, 513, row_base=70000).cpu().numpy()
+    want = oracle.alias_draw_contrast(prob, alias, y.cpu().numpy(), 513, seed=1234, offset=100080 + 4 * 1025)
+    want[:, 1:] += 70000
+    want[:, 0] = y.cpu().numpy() + 70000
+    assert np.array_equal(c2, want)
     # uniform unigrams over a large N: every value in range, all residues reachable
     am2 = pkg.AliasMethod(torch.ones(90000), seed=7).cuda()
     d = am2.draw(1 << 20)
