@@ -107,28 +107,31 @@ __global__ void __launch_bounds__(256) embed_bwd_prep2_kernel(const BwdHead h0, 
   embed_bwd_prep_body(h.g, h.v, h.inv, scale, D, h.d_pre, blockIdx.x, red);
 }
 
-// grid (D, ceil(dim_in/256)), 256 threads: dW[d][i] = sum_b d_pre[b][d] x[b][i];  db[d] = sum_b d_pre[b][d]
+// grid (ceil(D/4), ceil(dim_in/256)), 256 threads: dW[d][i] = sum_b d_pre[b][d] x[b][i];  db[d] = sum_b d_pre[b][d].
+// Each thread keeps FOUR outputs (d0..d0+3, same column i): one coalesced x load feeds four FMAs, so the L2 traffic on x
+// (the operand every block re-reads) is a quarter of the one-output version's.
+constexpr int kEmbedR = 4;
 __device__ __forceinline__ void embed_bwd_wgrad_body(const float* __restrict__ d_pre, const float* __restrict__ x,
                                                      int B, int dim_in, int D, float* __restrict__ dW, float* __restrict__ db,
                                                      int bx, int by) {
-  const int d = bx, i = by * 256 + threadIdx.x;
+  const int d0 = bx * kEmbedR, i = by * 256 + threadIdx.x;
   if (i < dim_in) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int b = 0;
-    for (; b + 3 < B; b += 4) {
-      a0 = fmaf(__ldg(d_pre + (size_t)b * D + d), __ldg(x + (size_t)b * dim_in + i), a0);
-      a1 = fmaf(__ldg(d_pre + (size_t)(b + 1) * D + d), __ldg(x + (size_t)(b + 1) * dim_in + i), a1);
-      a2 = fmaf(__ldg(d_pre + (size_t)(b + 2) * D + d), __ldg(x + (size_t)(b + 2) * dim_in + i), a2);
-      a3 = fmaf(__ldg(d_pre + (size_t)(b + 3) * D + d), __ldg(x + (size_t)(b + 3) * dim_in + i), a3);
+    float acc[kEmbedR] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) {
+      const float xv = __ldg(x + (size_t)b * dim_in + i);
+#pragma unroll
+      for (int q = 0; q < kEmbedR; ++q)
+        if (d0 + q < D) acc[q] = fmaf(__ldg(d_pre + (size_t)b * D + d0 + q), xv, acc[q]);
     }
-    for (; b < B; ++b) a0 = fmaf(__ldg(d_pre + (size_t)b * D + d), __ldg(x + (size_t)b * dim_in + i), a0);
-    a0 += a2; a1 += a3;
-    dW[(size_t)d * dim_in + i] = a0 + a1;
+#pragma unroll
+    for (int q = 0; q < kEmbedR; ++q)
+      if (d0 + q < D) dW[(size_t)(d0 + q) * dim_in + i] = acc[q];
   }
-  if (by == 0 && threadIdx.x == 0) {
+  if (by == 0 && threadIdx.x < kEmbedR && d0 + (int)threadIdx.x < D) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += d_pre[(size_t)b * D + d];
-    db[d] = s;
+    for (int b = 0; b < B; ++b) s += d_pre[(size_t)b * D + d0 + threadIdx.x];
+    db[d0 + threadIdx.x] = s;
   }
 }
 __global__ void __launch_bounds__(256) embed_bwd_wgrad_kernel(const float* __restrict__ d_pre, const float* __restrict__ x,
@@ -136,27 +139,27 @@ __global__ void __launch_bounds__(256) embed_bwd_wgrad_kernel(const float* __res
   embed_bwd_wgrad_body(d_pre, x, B, dim_in, D, dW, db, blockIdx.x, blockIdx.y);
 }
 
-// grid (B, ceil(dim_in/256)), 256 threads: dx[b][i] = sum_d d_pre[b][d] W[d][i]
+// grid (ceil(B/4), ceil(dim_in/256)), 256 threads: dx[b][i] = sum_d d_pre[b][d] W[d][i], four rows b per thread (one
+// coalesced W load feeds four FMAs)
 __device__ __forceinline__ void embed_bwd_dgrad_body(const float* __restrict__ d_pre, const float* __restrict__ W,
-                                                     int dim_in, int D, float* __restrict__ dx, int bx, int by) {
-  const int b = bx, i = by * 256 + threadIdx.x;
+                                                     int B, int dim_in, int D, float* __restrict__ dx, int bx, int by) {
+  const int b0 = bx * kEmbedR, i = by * 256 + threadIdx.x;
   if (i >= dim_in) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int d = 0;
-#pragma unroll 2
-  for (; d + 3 < D; d += 4) {
-    a0 = fmaf(__ldg(d_pre + (size_t)b * D + d), __ldg(W + (size_t)d * dim_in + i), a0);
-    a1 = fmaf(__ldg(d_pre + (size_t)b * D + d + 1), __ldg(W + (size_t)(d + 1) * dim_in + i), a1);
-    a2 = fmaf(__ldg(d_pre + (size_t)b * D + d + 2), __ldg(W + (size_t)(d + 2) * dim_in + i), a2);
-    a3 = fmaf(__ldg(d_pre + (size_t)b * D + d + 3), __ldg(W + (size_t)(d + 3) * dim_in + i), a3);
+  float acc[kEmbedR] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int d = 0; d < D; ++d) {
+    const float wv = __ldg(W + (size_t)d * dim_in + i);
+#pragma unroll
+    for (int q = 0; q < kEmbedR; ++q)
+      if (b0 + q < B) acc[q] = fmaf(__ldg(d_pre + (size_t)(b0 + q) * D + d), wv, acc[q]);
   }
-  for (; d < D; ++d) a0 = fmaf(__ldg(d_pre + (size_t)b * D + d), __ldg(W + (size_t)d * dim_in + i), a0);
-  a0 += a2; a1 += a3;
-  dx[(size_t)b * dim_in + i] = a0 + a1;
+#pragma unroll
+  for (int q = 0; q < kEmbedR; ++q)
+    if (b0 + q < B) dx[(size_t)(b0 + q) * dim_in + i] = acc[q];
 }
 __global__ void __launch_bounds__(256) embed_bwd_dgrad_kernel(const float* __restrict__ d_pre, const float* __restrict__ W,
-                                                              int dim_in, int D, float* __restrict__ dx) {
-  embed_bwd_dgrad_body(d_pre, W, dim_in, D, dx, blockIdx.x, blockIdx.y);
+                                                              int B, int dim_in, int D, float* __restrict__ dx) {
+  embed_bwd_dgrad_body(d_pre, W, B, dim_in, D, dx, blockIdx.x, blockIdx.y);
 }
 // wgrad and dgrad of BOTH heads in one launch (they only depend on d_pre): 1-D grid cut into four block ranges
 // [wgrad head 0 | wgrad head 1 | dgrad head 0 | dgrad head 1]; n_* = blocks of each range (0 when that gradient is off)
@@ -167,9 +170,9 @@ __global__ void __launch_bounds__(256) embed_bwd_grads2_kernel(const BwdHead h0,
   blk -= n_w0;
   if (blk < n_w1) { embed_bwd_wgrad_body(h1.d_pre, h1.x, B, h1.dim_in, D, h1.dW, h1.db, blk / tiles1, blk % tiles1); return; }
   blk -= n_w1;
-  if (blk < n_d0) { embed_bwd_dgrad_body(h0.d_pre, h0.W, h0.dim_in, D, h0.dx, blk / tiles0, blk % tiles0); return; }
+  if (blk < n_d0) { embed_bwd_dgrad_body(h0.d_pre, h0.W, B, h0.dim_in, D, h0.dx, blk / tiles0, blk % tiles0); return; }
   blk -= n_d0;
-  embed_bwd_dgrad_body(h1.d_pre, h1.W, h1.dim_in, D, h1.dx, blk / tiles1, blk % tiles1);
+  embed_bwd_dgrad_body(h1.d_pre, h1.W, B, h1.dim_in, D, h1.dx, blk / tiles1, blk % tiles1);
 }
 
 }  // namespace embed
@@ -202,10 +205,10 @@ extern "C" int crdpn_embed_backward(const float* x, const float* W, const float*
   embed::embed_bwd_prep_kernel<<<(unsigned)B, 256, 0, st>>>(grad_v, v, inv_norm, scale, (int)D, d_pre);
   CRDPN_LAUNCH_CHECK("embed_bwd_prep_kernel");
   const unsigned tiles = (unsigned)((dim_in + 255) / 256);
-  embed::embed_bwd_wgrad_kernel<<<dim3((unsigned)D, tiles), 256, 0, st>>>(d_pre, x, (int)B, (int)dim_in, (int)D, dW, db);
+  embed::embed_bwd_wgrad_kernel<<<dim3((unsigned)((D + embed::kEmbedR - 1) / embed::kEmbedR), tiles), 256, 0, st>>>(d_pre, x, (int)B, (int)dim_in, (int)D, dW, db);
   CRDPN_LAUNCH_CHECK("embed_bwd_wgrad_kernel");
   if (dx) {
-    embed::embed_bwd_dgrad_kernel<<<dim3((unsigned)B, tiles), 256, 0, st>>>(d_pre, W, (int)dim_in, (int)D, dx);
+    embed::embed_bwd_dgrad_kernel<<<dim3((unsigned)((B + embed::kEmbedR - 1) / embed::kEmbedR), tiles), 256, 0, st>>>(d_pre, W, (int)B, (int)dim_in, (int)D, dx);
     CRDPN_LAUNCH_CHECK("embed_bwd_dgrad_kernel");
   }
   return CRDPN_OK;
@@ -246,7 +249,8 @@ int embed_backward2(const float* xs, int64_t s_dim, const float* Ws, const float
   embed::embed_bwd_prep2_kernel<<<dim3((unsigned)B, 2), 256, 0, st>>>(h0, h1, scale, (int)D);
   CRDPN_LAUNCH_CHECK("embed_bwd_prep2_kernel");
   const long long t0 = (s_dim + 255) / 256, t1 = (t_dim + 255) / 256;
-  const long long n_w0 = D * t0, n_w1 = D * t1, n_d0 = dxs ? B * t0 : 0, n_d1 = dxt ? B * t1 : 0;
+  const long long dg = (D + embed::kEmbedR - 1) / embed::kEmbedR, bg = (B + embed::kEmbedR - 1) / embed::kEmbedR;
+  const long long n_w0 = dg * t0, n_w1 = dg * t1, n_d0 = dxs ? bg * t0 : 0, n_d1 = dxt ? bg * t1 : 0;
   const long long total = n_w0 + n_w1 + n_d0 + n_d1;
   if (total >= (1ll << 31)) return fail(CRDPN_E_UNSUPPORTED, "embed_backward2: grid too large");
   embed::embed_bwd_grads2_kernel<<<(unsigned)total, 256, 0, st>>>(h0, h1, (int)B, (int)D, (int)t0, (int)t1, (int)n_w0, (int)n_w1,
