@@ -339,6 +339,8 @@ def run_own(args):
     try:
         from bench_kd_losses import bench_kd_losses
         also["kd_losses"] = bench_kd_losses(pkg, torch, dev, args)
+        from bench_kd_losses import bench_pose_tail
+        also["pose_tail"] = bench_pose_tail(pkg, torch, dev, args)
     except ImportError:
         pass
 
