@@ -33,10 +33,13 @@ class FrozenPoseTail(nn.Module):
     weights.  With ``graph=True`` (default) the launch sequence is captured once per batch size and replayed; the returned
     tensors are then the graph's static outputs and are overwritten by the next call."""
 
-    def __init__(self, folded: dict, shape_dim: int, head_sizes, graph: bool = True):
+    def __init__(self, folded: dict, shape_dim: int, head_sizes, graph: bool = True, dtype=torch.float32):
         super().__init__()
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("FrozenPoseTail dtype must be float32 (reference parity) or bfloat16 (1e-2 tolerance mode)")
+        self.dtype = dtype
         for k, v in folded.items():
-            self.register_buffer(k, v.contiguous())
+            self.register_buffer(k, v.to(dtype).contiguous())
         self.shape_dim = shape_dim
         self.head_sizes = [int(h) for h in head_sizes]
         self.graph = graph
@@ -65,9 +68,11 @@ class FrozenPoseTail(nn.Module):
         return out, out["W1t"].shape[0] - img_dim, head_sizes
 
     @classmethod
-    def from_state_dict(cls, sd: dict, prefix: str = "", graph: bool = True) -> "FrozenPoseTail":
+    def from_state_dict(cls, sd: dict, prefix: str = "", graph: bool = True, dtype=torch.float32) -> "FrozenPoseTail":
+        """dtype=torch.bfloat16 stores the folded weights and runs the GEMMs in bf16 (fp32 accumulate, tensor cores): the
+        north_star's 1e-2 tolerance mode; the default float32 reproduces the reference to fp32 rounding."""
         folded, shape_dim, head_sizes = cls.fold_state_dict(sd, prefix)
-        m = cls(folded, shape_dim, head_sizes, graph)
+        m = cls(folded, shape_dim, head_sizes, graph, dtype)
         m._source = (sd, prefix)
         return m
 
@@ -77,7 +82,7 @@ class FrozenPoseTail(nn.Module):
             sd, prefix = self._source
         folded, _, _ = self.fold_state_dict(sd, prefix or "")
         for k, v in folded.items():
-            getattr(self, k).copy_(v)
+            getattr(self, k).copy_(v.to(self.dtype))
         self._graphs = {}
         return self
 
@@ -106,10 +111,10 @@ class FrozenPoseTail(nn.Module):
     def forward(self, shape_feature, img_feature):
         if not (shape_feature.is_cuda and img_feature.is_cuda):
             raise RuntimeError("FrozenPoseTail inputs must be CUDA tensors: this package has no CPU fallback")
-        sf, img = shape_feature.detach().float().contiguous(), img_feature.detach().float().contiguous()
+        sf, img = shape_feature.detach().to(self.dtype).contiguous(), img_feature.detach().to(self.dtype).contiguous()
         if not self.graph:
             heads, x, p = self._run(sf, img)
-            return self._split(heads), x, p
+            return self._split(heads.float()), x.float(), p.float()
         key = (sf.shape[0], sf.device)
         entry = self._graphs.get(key)
         if entry is None:
@@ -123,7 +128,8 @@ class FrozenPoseTail(nn.Module):
             torch.cuda.current_stream(sf.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                outs = self._run(s_sf, s_img)
+                heads, x, p = self._run(s_sf, s_img)
+                outs = (heads.float(), x.float(), p.float())  # no-ops in float32 mode
             entry = self._graphs[key] = (graph, s_sf, s_img, outs)
         graph, s_sf, s_img, (heads, x, p) = entry
         s_sf.copy_(sf)

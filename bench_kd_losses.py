@@ -124,8 +124,14 @@ def bench_pose_tail(pkg, torch, dev, args, B=138, Fs=1024, Fi=1024):
         def run_tail():
             tail(sf, img)
 
+        tail16 = pkg.FrozenPoseTail.from_state_dict(eager.state_dict(), dtype=torch.bfloat16).to(dev)
+
+        def run_tail16():
+            tail16(sf, img)
+
         return {"workload": f"pose_tail_B{B}_{Fs}+{Fi}", "eager_us": _time(torch, run_eager, steps, warmup),
                 "frozen_tail_us": _time(torch, run_tail, steps, warmup), "max_rel_diff_vs_eager": err,
+                "frozen_tail_bf16_us": _time(torch, run_tail16, steps, warmup),
                 "note": "eval-mode teacher tail: BN folded, concat as split-K, six heads as one GEMM, one CUDA graph (library "
                         "GEMMs, full fp32; the eager arm's 1x1 convolutions run cuDNN's default TF32 path, which is where "
                         "max_rel_diff_vs_eager comes from -- against the fp64 oracle the tail is within 2e-5)"}

@@ -60,3 +60,12 @@ def test_reference_size_and_new_inputs_through_the_graph(pkg, cuda):
     assert len(tail._graphs) == 2
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         tail(torch.zeros(2, 1024), torch.zeros(2, 1024))
+    # bf16 mode: north_star's 1e-2 tolerance
+    tail16 = pkg.FrozenPoseTail.from_state_dict(sd, dtype=torch.bfloat16).to(cuda)
+    g = torch.Generator().manual_seed(9)
+    sf, img = torch.randn(138, 1024, generator=g), torch.randn(138, 1024, generator=g)
+    outs, x, p = tail16(sf.to(cuda), img.to(cuda))
+    w_outs, w_x, w_p = pto.forward(sd, sf, img)
+    assert x.dtype == torch.float32
+    assert _rel(x.cpu().numpy(), w_x.numpy()) < 2e-2 and _rel(p.cpu().numpy(), w_p.numpy()) < 2e-2
+    assert all(_rel(a.cpu().numpy(), b.numpy()) < 2e-2 for a, b in zip(outs, w_outs))
