@@ -176,14 +176,21 @@ class _KdMixFunction(torch.autograd.Function):
         with _native.on_device(dev):
             rc = _native.lib().crdpn_kd_mix_forward(*args, loss.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
         _native.check(rc, "crdpn_kd_mix_forward")
+        # the raw pointers in `args` stay valid as long as the saved tensors live; save_for_backward also makes autograd
+        # refuse a backward after one of the inputs was modified in place (the backward kernel re-reads them)
+        present = [i for i, t in enumerate(ts) if t is not None]
+        ctx.save_for_backward(*[ts[i] for i in present], *([lab] if lab is not None else []))
+        ctx.present = present
         ctx.args = args
-        ctx.keep = (ts, lab)          # the raw pointers in `args` stay valid as long as these live
         ctx.shapes = [(t.shape if t is not None else None) for t in tensors]
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        ts, lab = ctx.keep
+        saved = ctx.saved_tensors
+        ts = [None] * 14
+        for i, t in zip(ctx.present, saved):
+            ts[i] = t
         dev = grad_out.device
         g = grad_out.detach().to(torch.float32).contiguous()
         need = ctx.needs_input_grad[2:]
