@@ -10,8 +10,8 @@ the point cloud tripled (base_class.py:362), student = VGG-11 trunk -> 2048-d ->
 (model.py:183-272), loss = 0.25 CE + 0.75 sum_6 KL + 0.75 KL(features) (KD/vision/vanilla/vanilla_kd.py:143-164) + CRD.
 The CNN trunks are OUT OF SCOPE of this repo (cuDNN-bound stock convnets): torchvision's vgg11 / resnet50 with random
 weights stand in for auxiliary/vgg.py / resnet.py, which are torchvision-style copies.  Two arms are timed:
-  "dropin": crdpn PointCloudSampler -> ShapeEncoderPC (eval, fused kernel), crdpn student_kd_step_loss (the step's CE /
-            delta / KL terms in one launch) + crdpn CRDLoss
+  "dropin": crdpn PointCloudSampler -> ShapeEncoderPC (eval, fused kernel) -> FrozenPoseTail (the teacher's tail as one CUDA
+            graph), crdpn student_kd_step_loss (the step's CE / delta / KL terms in one launch) + crdpn CRDLoss
   "eager" : the same step with the encoder as the reference runs it (nn.Conv1d/BatchNorm1d ops, teacher graph built,
             three identical copies of every cloud), and no CRD term (the reference has none)
 and the share of the step spent in the two hot-path kernels is reported from the library's own event timers.
@@ -45,35 +45,41 @@ def build(torch, pkg, dev, dropin: bool):
             x = self.bn3(self.conv3(x))
             return torch.max(x, 2)[0]
 
-    class DeformNet(nn.Module):  # model.py:183-203 (Conv1d k=1 on length-1 = Linear)
+    class DeformNet(nn.Module):  # model.py:183-203, same sub-module names (1x1 Conv1d on a length-1 sequence)
         def __init__(self, n):
             super().__init__()
-            self.l = nn.ModuleList([nn.Linear(n, n), nn.Linear(n, n // 2), nn.Linear(n // 2, n // 4), nn.Linear(n // 4, 200)])
-            self.bn = nn.ModuleList([nn.BatchNorm1d(n), nn.BatchNorm1d(n // 2), nn.BatchNorm1d(n // 4)])
+            self.conv1, self.conv2, self.conv3, self.conv4 = (nn.Conv1d(n, n, 1), nn.Conv1d(n, n // 2, 1), nn.Conv1d(n // 2, n // 4, 1),
+                                                              nn.Conv1d(n // 4, 200, 1))
+            self.bn1, self.bn2, self.bn3 = nn.BatchNorm1d(n), nn.BatchNorm1d(n // 2), nn.BatchNorm1d(n // 4)
 
         def forward(self, x):
-            for lin, bn in zip(self.l[:3], self.bn):
-                x = F.relu(bn(lin(x)))
-            return torch.tanh(self.l[3](x))
+            x = F.relu(self.bn1(self.conv1(x)))
+            x = F.relu(self.bn2(self.conv2(x)))
+            x = F.relu(self.bn3(self.conv3(x)))
+            return torch.tanh(self.conv4(x)).view(-1, 200)
+
+    HEAD_NAMES = ("fc_cls_azi", "fc_cls_ele", "fc_cls_inp", "fc_reg_azi", "fc_reg_ele", "fc_reg_inp")
 
     def heads():
         return nn.ModuleList([nn.Linear(200, c) for c in (24, 12, 24, 24, 12, 24)])
 
-    class Teacher(nn.Module):
+    class Teacher(nn.Module):   # model.py:205-272, same sub-module names for the tail
         def __init__(self):
             super().__init__()
             self.img = torchvision.models.resnet50(num_classes=1024)
             self.shape_encoder = pkg.ShapeEncoderPC(1024) if dropin else EagerShapeEncoderPC(1024)
-            self.deform = DeformNet(2048)
-            self.heads = heads()
+            self.deformNet = DeformNet(2048)
+            for h, c in zip(HEAD_NAMES, (24, 12, 24, 24, 12, 24)):
+                setattr(self, h, nn.Linear(200, c))
             self.projector = nn.Sequential(nn.Linear(1024, 800), nn.BatchNorm1d(800), nn.ReLU(True), nn.Linear(800, 400),
                                            nn.BatchNorm1d(400), nn.ReLU(True), nn.Linear(400, 200))
 
         def forward(self, im, shape=None, shape_feature=None):
             f = self.img(im)
             sf = self.shape_encoder(shape) if shape_feature is None else shape_feature
-            x = self.deform(torch.cat((sf, f), 1))
-            return [h(x) for h in self.heads], x, self.projector(f)
+            g = torch.cat((sf, f), 1)
+            x = self.deformNet(g.view(-1, g.size(1), 1))
+            return [getattr(self, h)(x) for h in HEAD_NAMES], x, self.projector(f)
 
     class Student(nn.Module):
         def __init__(self):
@@ -118,8 +124,9 @@ def run_arm(torch, pkg, dev, dropin, steps, warmup):
     shapes = torch.rand(b, 3, 2500, generator=g).to(dev)
     label = torch.stack([torch.randint(0, r, (3 * b,), generator=g) for r in (360, 180, 360)], 1).to(dev)   # degrees
     idx = torch.randperm(N, generator=g)[:b].to(dev)
-    sampler = None
-    if dropin:  # the clouds come from the resident meshes through the batch producer (dataset.py:121-150 on the GPU)
+    sampler = tail = None
+    if dropin:  # the frozen teacher's tail as one CUDA graph; the clouds come from the resident meshes (dataset.py:121-150)
+        tail = pkg.FrozenPoseTail.from_state_dict(teacher.state_dict()).to(dev)
         import numpy as np
         rng = np.random.default_rng(46)
         sampler = pkg.PointCloudSampler([rng.normal(size=(int(v), 3)) for v in rng.integers(3000, 40000, 64)], 2500, dev, seed=46)
@@ -144,7 +151,7 @@ def run_arm(torch, pkg, dev, dropin, steps, warmup):
             with torch.no_grad():                                        # the teacher is frozen: no graph, and the three
                 clouds = sampler.sample(cloud_ids, rotations)            # copies of a cloud are encoded once (bit-identical)
                 sf = teacher.shape_encoder(clouds).repeat(3, 1)
-                tout, _, tfeat = teacher(x, shape_feature=sf)
+                tout, _, tfeat = tail(sf, teacher.img(x))                # :363 after the encoders, one graph launch
             # :365-387 in one launch (+1 backward): CE x3, delta term, KL x7, weights
             loss = pkg.student_kd_step_loss(out, [t.detach() for t in tout], sfeat, tfeat.detach(), label)
             loss = loss + 0.8 * crd(sfeat, tfeat.detach(), torch.cat([idx] * 3))
