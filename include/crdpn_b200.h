@@ -387,6 +387,17 @@ int crdpn_pointnet_backward_phased(
     float* d_bn1_w, float* d_bn1_b, float* d_bn2_w, float* d_bn2_b, float* d_bn3_w, float* d_bn3_b,
     void* workspace, size_t workspace_bytes, int phase_begin, int phase_end, int64_t total_points, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Development probe (not a product path; no reference counterpart): one tile of the tensor-core formulation planned for the
+ * bank-streaming CRD step -- tcgen05.mma kind::tf32 on an fp32 tile stored once in the K-major
+ * SWIZZLE_128B image and read both K-major (scores = rows . [V2 | V1]^T) and MN-major (gradients^T = rows^T . C).
+ * rows1, rows2 [64,128]; v1, v2 [48,128]; c1, c2 [64,48] (f32, device); out [128,192]: columns [0,96) scores of the 128
+ * stacked rows (64 of bank 1, then 64 of bank 2) against [V2 | V1], [96,144) G2^T[e][b] = sum_r rows1[r][e] c2[r][b],
+ * [144,192) G1^T[e][b] = sum_r rows2[r][e] c1[r][b].
+ * ------------------------------------------------------------------------------------------------- */
+int crdpn_umma_tf32_probe(const float* rows1, const float* rows2, const float* v1, const float* v2, const float* c1,
+                          const float* c2, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
