@@ -86,7 +86,7 @@ _SIGNATURES = {
     "crdpn_crd_out_backward": (c_int, [c_void_p, c_void_p, c_int64, c_int] + [c_void_p] * 8 +
                                [c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                 c_void_p]),
-    "crdpn_umma_tf32_probe": (c_int, [c_void_p] * 8),
+    "crdpn_umma_tf32_probe": (c_int, [c_void_p] * 7 + [c_int, c_void_p]),
     "crdpn_p2p_buffer_bytes": (c_int, [c_int64, c_int64, c_int, POINTER(c_size_t)]),
     "crdpn_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "crdpn_p2p_free": (c_int, [c_void_p]),

@@ -56,7 +56,7 @@ constexpr uint32_t kSmem = kBar + 64 + 1024;
 __global__ void __launch_bounds__(128, 1) umma_tf32_probe_kernel(const float* __restrict__ rows1, const float* __restrict__ rows2,
                                                                  const float* __restrict__ v1, const float* __restrict__ v2,
                                                                  const float* __restrict__ c1, const float* __restrict__ c2,
-                                                                 float* __restrict__ out) {
+                                                                 float* __restrict__ out, int mode) {
   using namespace pn;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_probe_kernel(const float* __
   if (warp == 0) {
     if (elect_one()) {
       // (1) scores: M = 128, N = 96, K = 128 -> 16 steps of K = 8 (32 bytes inside a 128-byte row; 4 steps per K-block)
-      constexpr uint32_t i_s = make_idesc_tf32(128, 96, 0, 0);
+      //     mode 1: the same with M = 64 (only the first 64 stacked rows), to record where M = 64 accumulators live in TMEM
+      const uint32_t i_s = mode == 1 ? make_idesc_tf32(64, 96, 0, 0) : make_idesc_tf32(128, 96, 0, 0);
       for (int kk = 0; kk < 16; ++kk) {
         const uint64_t da = umma_desc(base + kA + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
         const uint64_t db = umma_desc(base + kBV + (kk >> 2) * (96 * 128) + (kk & 3) * 32, 16, 1024);
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_probe_kernel(const float* __
 using namespace crdpn;
 
 extern "C" int crdpn_umma_tf32_probe(const float* rows1, const float* rows2, const float* v1, const float* v2, const float* c1,
-                                     const float* c2, float* out, void* stream) {
+                                     const float* c2, float* out, int mode, void* stream) {
   if (!rows1 || !rows2 || !v1 || !v2 || !c1 || !c2 || !out) return fail(CRDPN_E_BADARG, "crdpn_umma_tf32_probe: null pointer");
   int device = 0;
   CRDPN_CUDA(cudaGetDevice(&device));
@@ -156,7 +157,7 @@ extern "C" int crdpn_umma_tf32_probe(const float* rows1, const float* rows2, con
   if (rc) return rc;
   if (di.max_smem_optin < (int)probe::kSmem) return fail(CRDPN_E_UNSUPPORTED, "crdpn_umma_tf32_probe: not enough shared memory");
   CRDPN_CUDA(cudaFuncSetAttribute(probe::umma_tf32_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe::kSmem));
-  probe::umma_tf32_probe_kernel<<<1, 128, probe::kSmem, (cudaStream_t)stream>>>(rows1, rows2, v1, v2, c1, c2, out);
+  probe::umma_tf32_probe_kernel<<<1, 128, probe::kSmem, (cudaStream_t)stream>>>(rows1, rows2, v1, v2, c1, c2, out, mode);
   CRDPN_LAUNCH_CHECK("umma_tf32_probe_kernel");
   return CRDPN_OK;
 }
