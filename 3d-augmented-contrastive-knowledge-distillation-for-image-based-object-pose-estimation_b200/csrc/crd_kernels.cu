@@ -832,7 +832,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
                             const int64_t* contrast_idx, int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
                             int64_t row_begin, int64_t row_end, float T, float Z1, float Z2, float eps, double* result,
                             float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes, const UpdateParams& upd,
-                            void* stream) {
+                            int copy_only, void* stream) {
   if (!v1 || !v2 || !contrast_idx || !result || !grad_v1 || !grad_v2 || !workspace || !bank1 || !bank2)
     return fail(CRDPN_E_BADARG, "crdpn_crd_step (streaming): null pointer");
   if (B <= 0 || K1 <= 0 || n_data <= 0 || row_end <= row_begin || !(T > 0.f) || k_total < 0)
@@ -881,6 +881,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
   sp.inv_BT = (float)(1.0 / ((double)B * (double)T));
   sp.partial = (float*)(ws + L.partial);
   sp.loss_part = (float*)(ws + L.loss_part);
+  sp.copy_only = copy_only;
 
   static bool attr_set[64] = {false};
   if (!attr_set[device]) {
@@ -925,7 +926,8 @@ extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int 
                                             momentum, one_minus_momentum);
   if (variant & 0x200)  // bank-streaming formulation (crd_stream.cuh); the workspace is crdpn_crd_stream_workspace_bytes
     return stream_step_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin,
-                            row_end, T, Z1, Z2, eps, result, grad_v1, grad_v2, workspace, workspace_bytes, u, stream);
+                            row_end, T, Z1, Z2, eps, result, grad_v1, grad_v2, workspace, workspace_bytes, u,
+                            (variant & 0x800) ? 1 : 0, stream);
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin, row_end,
                     T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant,
                     &u, stream);

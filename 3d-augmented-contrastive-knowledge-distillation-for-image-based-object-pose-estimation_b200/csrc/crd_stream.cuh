@@ -211,6 +211,7 @@ struct StreamParams {
   float k_exp, inv_Z1, inv_Z2, c, inv_mPn, eps_over_mPn, inv_BT;
   float* partial;         // [grid][B][2 * D]
   float* loss_part;       // [grid][kWarpsTS][2]
+  int copy_only;          // measurement aid (variant | 0x800): stream the tiles through the ring, score nothing
 };
 
 __global__ void __launch_bounds__(kThreadsTS, 1) crd_stream_kernel(const StreamParams p) {
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kThreadsTS, 1) crd_stream_kernel(const StreamP
     __syncwarp();
     const unsigned n0 = offs[it], n1 = offs[it + 1];
     mbar_wait(bar_full + 8 * s, (uint32_t)((it / kStages) & 1));
-    if (n1 != n0) {
+    if (n1 != n0 && !p.copy_only) {
       const unsigned char* rows = ts_smem + s * kStageBytes;
       const unsigned* recs = reinterpret_cast<const unsigned*>(rows + kRowsBytes);
       const unsigned w0 = n0 & ~3u;
