@@ -26,7 +26,7 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_committed_own_arm_line_has_the_contract_keys():
-    d = json.loads((ROOT / "profiles" / "r1_bench_1gpu_v6.json").read_text().strip().splitlines()[-1])
+    d = json.loads((ROOT / "profiles" / "r1_bench_1gpu_final.json").read_text().strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert key in d, key
