@@ -791,17 +791,23 @@ extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row
 
 // ---- bank-streaming step (crd_stream.cuh) ------------------------------------------------------------------------
 struct TsLayout {
-  size_t count, off, cursor, records, partial, loss_part, total;
-  int T, G;
+  size_t count, off, cursor, records, ahist, aoff, coarse_off, keys, partial, loss_part, total;
+  int T, G, NB, GA;
   TsLayout(long long B, long long K1, long long rows, int sms) {
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     T = (int)((rows + ts::kTR - 1) / ts::kTR);
     G = sms;
+    NB = (T + (1 << ts::kCoarseShift) - 1) >> ts::kCoarseShift;
+    GA = sms * 2;   // pass-A CTAs: the two passes over idx are latency-bound per CTA, the scan is limited to 48 K (CTA, bucket) pairs
     size_t o = 0;
     count = o; o += up((size_t)(T + 1) * 4);
     off = o; o += up((size_t)(T + 1) * 4);
     cursor = o; o += up((size_t)(T + 1) * 4);
     records = o; o += up((size_t)(B * K1 + 8) * 4);
+    ahist = o; o += up((size_t)GA * NB * 4);
+    aoff = o; o += up((size_t)GA * NB * 4);
+    coarse_off = o; o += up((size_t)(NB + 1) * 4);
+    keys = o; o += up((size_t)(B * K1 + 8) * 4);
     partial = o; o += up((size_t)G * B * 2 * ts::kD * 4);
     loss_part = o; o += up((size_t)G * ts::kWarpsTS * 2 * 4);
     total = o;
@@ -887,18 +893,37 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
   if (!attr_set[device]) {
     CRDPN_CUDA(cudaFuncSetAttribute(ts::crd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmemBytes));
     CRDPN_CUDA(cudaFuncSetAttribute(ts::ts_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kScanSmemMax * 4));
+    CRDPN_CUDA(cudaFuncSetAttribute(ts::ts_coarse_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kPartScanMax * 4));
     attr_set[device] = true;
   }
   {
     ScopedKernelTimer tm(CRDPN_K_CRD_SCORE, st);   // the bucketing is part of what replaces the gather pass
-    CRDPN_CUDA(cudaMemsetAsync(bp.count, 0, (size_t)(L.T + 1) * 4, st));
-    const int pre_grid = di.sms * 8;
-    ts::ts_hist_kernel<<<pre_grid, 256, 0, st>>>(bp);
-    CRDPN_LAUNCH_CHECK("ts_hist_kernel");
-    ts::ts_scan_kernel<<<1, 1024, L.T <= ts::kScanSmemMax ? (size_t)L.T * 4 : 0, st>>>(bp);
-    CRDPN_LAUNCH_CHECK("ts_scan_kernel");
-    ts::ts_scatter_kernel<<<pre_grid, 256, 0, st>>>(bp);
-    CRDPN_LAUNCH_CHECK("ts_scatter_kernel");
+    if ((long long)L.NB * L.GA <= ts::kPartScanMax && L.NB * 4 <= 48 * 1024) {
+      // two-pass partition: shared-memory atomics only
+      ts::PartParams pp;
+      pp.idx = bp.idx; pp.P = bp.P; pp.K1 = bp.K1; pp.row_begin = row_begin; pp.row_end = row_end;
+      pp.T = L.T; pp.NB = L.NB; pp.GA = L.GA;
+      pp.ahist = (unsigned*)(ws + L.ahist); pp.aoff = (unsigned*)(ws + L.aoff); pp.coarse_off = (unsigned*)(ws + L.coarse_off);
+      pp.keys = (unsigned*)(ws + L.keys); pp.tile_off = bp.off; pp.records = bp.records;
+      const size_t sh = (size_t)L.NB * 4;
+      ts::ts_coarse_hist_kernel<<<L.GA, ts::kPartThreads, sh, st>>>(pp);
+      CRDPN_LAUNCH_CHECK("ts_coarse_hist_kernel");
+      ts::ts_coarse_scan_kernel<<<1, 1024, (size_t)L.NB * L.GA * 4, st>>>(pp);
+      CRDPN_LAUNCH_CHECK("ts_coarse_scan_kernel");
+      ts::ts_coarse_scatter_kernel<<<L.GA, ts::kPartThreads, sh, st>>>(pp);
+      CRDPN_LAUNCH_CHECK("ts_coarse_scatter_kernel");
+      ts::ts_fine_kernel<<<L.NB, 512, 0, st>>>(pp);
+      CRDPN_LAUNCH_CHECK("ts_fine_kernel");
+    } else {  // very large shards: global-atomic counting sort
+      CRDPN_CUDA(cudaMemsetAsync(bp.count, 0, (size_t)(L.T + 1) * 4, st));
+      const int pre_grid = di.sms * 8;
+      ts::ts_hist_kernel<<<pre_grid, 256, 0, st>>>(bp);
+      CRDPN_LAUNCH_CHECK("ts_hist_kernel");
+      ts::ts_scan_kernel<<<1, 1024, L.T <= ts::kScanSmemMax ? (size_t)L.T * 4 : 0, st>>>(bp);
+      CRDPN_LAUNCH_CHECK("ts_scan_kernel");
+      ts::ts_scatter_kernel<<<pre_grid, 256, 0, st>>>(bp);
+      CRDPN_LAUNCH_CHECK("ts_scatter_kernel");
+    }
     ts::crd_stream_kernel<<<L.G, ts::kThreadsTS, ts::kSmemBytes, st>>>(sp);
     CRDPN_LAUNCH_CHECK("crd_stream_kernel");
   }

@@ -5,8 +5,9 @@
 // and the 126 MB L2 cannot hold on to a 1 GB bank between two visits (measured hit rate 6 %).  Here the samples are
 // first bucketed by ROW TILE (32 rows = 32 KB of the interleaved banks) and the banks are then streamed through shared
 // memory exactly once, tile by tile, with bulk copies:
-//   ts_hist / ts_scan / ts_scatter   counting sort of the B*(K+1) samples by tile: one 32-bit record per sample
-//                                    (row inside the tile | anchor | positive flag)
+//   ts_coarse_* / ts_fine            two-pass partition of the B*(K+1) samples by tile: one 32-bit record per sample
+//                                    (row inside the tile | anchor | positive flag); ts_hist / ts_scan / ts_scatter are the
+//                                    global-atomic fallback for very large shards
 //   crd_stream_kernel                persistent CTAs, 16 warps; a producer thread keeps a 4-deep ring of (tile rows,
 //                                    tile records) bulk copies in flight; warp w owns anchors {w, w+16, w+32} and keeps
 //                                    their embeddings AND their gradient accumulators in registers, picks its own
@@ -17,7 +18,8 @@
 // STATUS (round 1, measured on B200, profiles/r1_crd_stream_ncu.csv): correct (tests/test_crd_stream_gpu.py) and the DRAM
 // traffic is what was designed (1.036 GB read per step instead of 2.90 GB), but the streaming kernel executes 426 M warp
 // instructions (141 per sample: with ~0.7 records per (32-record chunk, anchor) the two half-warps almost never find a
-// pair, and every warp scans every record) and takes 0.78 ms, plus 0.13 ms of bucketing -- 2x SLOWER than the gather
+// pair, and every warp scans every record) and takes 0.75 ms, plus 0.08 ms of bucketing (two-pass partition below; the
+// first version, a global-atomic counting sort, took 0.13 ms) -- 2x SLOWER than the gather
 // kernel (0.43 ms), whose per-sample arithmetic hides under its memory time.  Opt-in only (variant | 0x200); the default
 // path is crd_score_kernel.  What this formulation needs to pay off is the per-sample dot products and gradient updates
 // off the CUDA cores: scores of a tile as rows x V^T and gradients as C^T x rows on tcgen05 (TF32, TMA-swizzled tiles),
@@ -196,6 +198,129 @@ __global__ void __launch_bounds__(256) ts_scatter_kernel(const BucketParams p) {
     ts_scatter_one(p, 4 * g + 3, b.y);
   }
   for (long long i = 4 * n4 + t0; i < p.P; i += stride) ts_scatter_one(p, i, p.idx[i]);
+}
+
+// ---- two-pass partition (the default bucketing): the global-atomic counting sort above spends ~100 us on 6 M atomics;
+// here the samples are first split into COARSE buckets of 256 tiles with per-CTA shared-memory histograms (pass A: count,
+// scan over (bucket, CTA), scatter 32-bit keys), then every coarse bucket is counting-sorted by tile inside one CTA (pass
+// B, 256 shared-memory bins).  Only shared-memory atomics; idx is read twice, keys written and read once.
+constexpr int kCoarseShift = 8;                  // 256 tiles per coarse bucket
+constexpr int kPartThreads = 256;
+constexpr int kPartScanMax = 48 * 1024;          // (CTAs x coarse buckets) entries the single-CTA scan stages in smem
+
+struct PartParams {
+  const long long* idx;
+  long long P;
+  unsigned K1;
+  long long row_begin, row_end;
+  int T, NB, GA;
+  unsigned* ahist;       // [NB][GA] (bucket-major: the scan reads it linearly)
+  unsigned* aoff;        // [NB][GA]
+  unsigned* coarse_off;  // [NB + 1]
+  unsigned* keys;        // [P]: row_in_tile | b << 5 | tile_in_coarse << 15 | pos << 31
+  unsigned* tile_off;    // [T + 1]
+  unsigned* records;     // [P + 8]
+};
+
+__global__ void __launch_bounds__(kPartThreads) ts_coarse_hist_kernel(const PartParams p) {
+  extern __shared__ unsigned part_sh[];
+  for (int i = threadIdx.x; i < p.NB; i += kPartThreads) part_sh[i] = 0u;
+  __syncthreads();
+  const long long lo = p.P * blockIdx.x / p.GA, hi = p.P * (blockIdx.x + 1) / p.GA;
+  for (long long i = lo + threadIdx.x; i < hi; i += kPartThreads) {
+    const long long r = p.idx[i];
+    if (r >= p.row_begin && r < p.row_end) atomicAdd(part_sh + (((r - p.row_begin) >> 5) >> kCoarseShift), 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.NB; i += kPartThreads) p.ahist[(size_t)i * p.GA + blockIdx.x] = part_sh[i];
+}
+
+// one CTA: exclusive scan of ahist in (bucket-major, CTA-minor) order -> aoff; coarse_off[nb]; tile_off[T] = total
+__global__ void __launch_bounds__(1024) ts_coarse_scan_kernel(const PartParams p) {
+  extern __shared__ unsigned part_sh[];
+  __shared__ unsigned warp_tot[32];
+  const int n = p.NB * p.GA, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < n; i += 1024) part_sh[i] = p.ahist[i];
+  __syncthreads();
+  const int seg = ((n + 1023) / 1024) | 1;
+  const int i0 = threadIdx.x * seg, i1 = min(i0 + seg, n);
+  unsigned tsum = 0;
+  for (int i = i0; i < i1; ++i) tsum += part_sh[i];
+  unsigned incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned wbase = 0;
+  for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+  unsigned run = wbase + incl - tsum;
+  for (int i = i0; i < i1; ++i) {
+    const unsigned c = part_sh[i];
+    part_sh[i] = run;
+    run += c;
+  }
+  if (threadIdx.x == 1023) { p.coarse_off[p.NB] = wbase + incl; p.tile_off[p.T] = wbase + incl; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 1024) p.aoff[i] = part_sh[i];
+  for (int nb = threadIdx.x; nb < p.NB; nb += 1024) p.coarse_off[nb] = part_sh[(size_t)nb * p.GA];
+}
+
+__global__ void __launch_bounds__(kPartThreads) ts_coarse_scatter_kernel(const PartParams p) {
+  extern __shared__ unsigned part_sh[];
+  for (int i = threadIdx.x; i < p.NB; i += kPartThreads) part_sh[i] = p.aoff[(size_t)i * p.GA + blockIdx.x];
+  __syncthreads();
+  const long long lo = p.P * blockIdx.x / p.GA, hi = p.P * (blockIdx.x + 1) / p.GA;
+  for (long long i = lo + threadIdx.x; i < hi; i += kPartThreads) {
+    const long long r = p.idx[i];
+    if (r < p.row_begin || r >= p.row_end) continue;
+    const unsigned local = (unsigned)(r - p.row_begin), tile = local >> 5;
+    const unsigned b = (unsigned)i / p.K1;
+    const bool pos = (unsigned)i - b * p.K1 == 0u;
+    const unsigned slot = atomicAdd(part_sh + (tile >> kCoarseShift), 1u);
+    p.keys[slot] = (local & 31u) | (b << 5) | ((tile & ((1u << kCoarseShift) - 1u)) << 15) | (pos ? 0x80000000u : 0u);
+  }
+}
+
+// one CTA per coarse bucket: counting sort of its keys by tile (256 shared-memory bins) -> tile_off, records
+__global__ void __launch_bounds__(512) ts_fine_kernel(const PartParams p) {
+  constexpr int kBins = 1 << kCoarseShift;
+  constexpr unsigned kBinMask = kBins - 1;
+  __shared__ unsigned cnt[kBins], cur[kBins], wsum[kBins / 32];
+  const int nb = blockIdx.x, t = threadIdx.x;
+  const unsigned lo = p.coarse_off[nb], hi = p.coarse_off[nb + 1];
+  if (t < kBins) cnt[t] = 0u;
+  __syncthreads();
+  for (unsigned i = lo + t; i < hi; i += 512) atomicAdd(cnt + ((p.keys[i] >> 15) & kBinMask), 1u);
+  __syncthreads();
+  unsigned mine = 0, incl = 0;
+  if (t < kBins) {
+    mine = cnt[t];
+    incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) wsum[t >> 5] = incl;
+  }
+  __syncthreads();
+  if (t < kBins) {
+    unsigned wbase = 0;
+    for (int w = 0; w < (t >> 5); ++w) wbase += wsum[w];
+    const unsigned excl = lo + wbase + incl - mine;
+    cur[t] = excl;
+    const int tile = (nb << kCoarseShift) + t;
+    if (tile < p.T) p.tile_off[tile] = excl;
+  }
+  __syncthreads();
+  for (unsigned i = lo + t; i < hi; i += 512) {
+    const unsigned k = p.keys[i];
+    const unsigned slot = atomicAdd(cur + ((k >> 15) & kBinMask), 1u);
+    p.records[slot] = k & 0x80007fffu;     // row | anchor | positive flag: the record format of make_record
+  }
 }
 
 struct StreamParams {
