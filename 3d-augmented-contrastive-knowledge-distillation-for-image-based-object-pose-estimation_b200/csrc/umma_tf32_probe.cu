@@ -142,6 +142,97 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_probe_kernel(const float* __
   }
 }
 
+// ---- mode 2: the same two GEMMs with bf16 operands (kind::f16) from ONE K-major SWIZZLE_128B image of the stacked rows:
+// 16-bit operands may be read MN-major from the ordinary SWIZZLE_128B layout, so a single image serves both GEMMs.
+constexpr uint32_t kA16 = 0;                   // 2 K-blocks x [128 rows x 128 B] = 32 KB
+constexpr uint32_t kBV16 = 32768;              // [V2 | V1]: 2 K-blocks x [96 x 128 B] = 24 KB
+constexpr uint32_t kBC216 = kBV16 + 24576;     // C2^T: [48 anchors x 64 rows] bf16 = one K-block, 6 KB
+constexpr uint32_t kBC116 = kBC216 + 6144;
+constexpr uint32_t kBar16 = kBC116 + 6144;
+constexpr uint32_t kSmem16 = kBar16 + 64 + 1024;
+
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(128, 1) umma_bf16_probe_kernel(const float* __restrict__ rows1, const float* __restrict__ rows2,
+                                                                 const float* __restrict__ v1, const float* __restrict__ v2,
+                                                                 const float* __restrict__ c1, const float* __restrict__ c2,
+                                                                 float* __restrict__ out) {
+  using namespace pn;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar = base + kBar16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kBar16 + 32);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  auto put = [&](uint32_t region, int kblock_rows, int row, int k, float v) {   // bf16 element (row, k) of a K-major SW128 image
+    *reinterpret_cast<__nv_bfloat16*>(sm + region + (k >> 6) * (kblock_rows * 128) + sw128_off(row, k & 63)) = __float2bfloat16_rn(v);
+  };
+  for (int i = tid; i < 128 * 128; i += 128) {
+    const int m = i >> 7, e = i & 127;
+    put(kA16, 128, m, e, m < 64 ? rows1[m * 128 + e] : rows2[(m - 64) * 128 + e]);
+  }
+  for (int i = tid; i < 96 * 128; i += 128) {
+    const int n = i >> 7, e = i & 127;
+    put(kBV16, 96, n, e, n < 48 ? v2[n * 128 + e] : v1[(n - 48) * 128 + e]);
+  }
+  for (int i = tid; i < 48 * 64; i += 128) {
+    const int b = i >> 6, r = i & 63;
+    put(kBC216, 48, b, r, c2[r * 48 + b]);
+    put(kBC116, 48, b, r, c1[r * 48 + b]);
+  }
+  fence_proxy_async();
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t i_s = make_idesc_bf16(128, 96, 0, 0);
+      for (int kk = 0; kk < 8; ++kk) {          // K = 128 in steps of 16 bf16 = 32 bytes; 4 steps per 64-wide K-block
+        const uint64_t da = umma_desc(base + kA16 + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
+        const uint64_t db = umma_desc(base + kBV16 + (kk >> 2) * (96 * 128) + (kk & 3) * 32, 16, 1024);
+        umma_f16(tmem, da, db, i_s, kk > 0);
+      }
+      // gradients: the SAME image read MN-major: M = 128 features = 2 blocks of 64 bf16 (LBO = one K-block = 16384 B),
+      // K = rows, 16 per step = two 8-row atoms (SBO = 1024 B)
+      constexpr uint32_t i_g = make_idesc_bf16(128, 48, 1, 0);
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t da1 = umma_desc(base + kA16 + kk * 2048, 16384, 1024);
+        const uint64_t da2 = umma_desc(base + kA16 + 64 * 128 + kk * 2048, 16384, 1024);
+        const uint64_t dc2 = umma_desc(base + kBC216 + kk * 32, 16, 1024);
+        const uint64_t dc1 = umma_desc(base + kBC116 + kk * 32, 16, 1024);
+        umma_f16(tmem + 96, da1, dc2, i_g, kk > 0);
+        umma_f16(tmem + 144, da2, dc1, i_g, kk > 0);
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < 192; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(trow + (uint32_t)c0, r);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) out[(size_t)tid * 192 + c0 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256u);
+  }
+}
+
 }  // namespace probe
 }  // namespace crdpn
 
@@ -157,6 +248,12 @@ extern "C" int crdpn_umma_tf32_probe(const float* rows1, const float* rows2, con
   if (rc) return rc;
   if (di.max_smem_optin < (int)probe::kSmem) return fail(CRDPN_E_UNSUPPORTED, "crdpn_umma_tf32_probe: not enough shared memory");
   CRDPN_CUDA(cudaFuncSetAttribute(probe::umma_tf32_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe::kSmem));
+  CRDPN_CUDA(cudaFuncSetAttribute(probe::umma_bf16_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe::kSmem16));
+  if (mode == 2) {
+    probe::umma_bf16_probe_kernel<<<1, 128, probe::kSmem16, (cudaStream_t)stream>>>(rows1, rows2, v1, v2, c1, c2, out);
+    CRDPN_LAUNCH_CHECK("umma_bf16_probe_kernel");
+    return CRDPN_OK;
+  }
   probe::umma_tf32_probe_kernel<<<1, 128, probe::kSmem, (cudaStream_t)stream>>>(rows1, rows2, v1, v2, c1, c2, out, mode);
   CRDPN_LAUNCH_CHECK("umma_tf32_probe_kernel");
   return CRDPN_OK;

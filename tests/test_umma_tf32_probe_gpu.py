@@ -52,3 +52,25 @@ def test_m64_accumulator_placement(pkg, cuda):
         lane_of_row.append(hits[0])
     print("M=64 accumulator: row -> TMEM lane", lane_of_row)
     assert lane_of_row == list(range(64)) or lane_of_row == [16 * (r // 16) * 2 + r % 16 for r in range(64)], lane_of_row
+
+
+def test_bf16_single_image_serves_both_gemms(pkg, cuda):
+    """mode 2: 16-bit operands may be read MN-major from the ordinary SWIZZLE_128B image (no second copy of the tile)."""
+    lib = pkg._native.lib()
+    rng = np.random.default_rng(3)
+    bf = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+    rows1, rows2 = bf(rng.normal(size=(64, 128)).astype(np.float32)), bf(rng.normal(size=(64, 128)).astype(np.float32))
+    v1, v2 = bf(rng.normal(size=(48, 128)).astype(np.float32)), bf(rng.normal(size=(48, 128)).astype(np.float32))
+    c1, c2 = bf(rng.normal(size=(64, 48)).astype(np.float32)), bf(rng.normal(size=(64, 48)).astype(np.float32))
+    d = [torch.from_numpy(a).to(cuda) for a in (rows1, rows2, v1, v2, c1, c2)]
+    out = torch.full((128, 192), float("nan"), device=cuda)
+    assert lib.crdpn_umma_tf32_probe(*[t.data_ptr() for t in d], out.data_ptr(), 2, torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float64)
+    vcat = np.concatenate([v2, v1]).astype(np.float64)
+    want = {"scores": (got[:, :96], np.concatenate([rows1, rows2]).astype(np.float64) @ vcat.T),
+            "G2^T": (got[:, 96:144], rows1.astype(np.float64).T @ c2.astype(np.float64)),
+            "G1^T": (got[:, 144:], rows2.astype(np.float64).T @ c1.astype(np.float64))}
+    for name, (g, w) in want.items():      # operands are exactly representable in bf16: only fp32 accumulation error
+        err = np.abs(g - w).max() / np.abs(w).max()
+        assert np.isfinite(g).all() and err < 1e-5, (name, err)
