@@ -452,15 +452,16 @@ class ContrastMemory(nn.Module):
 
     def _step_variant(self, B, K1, D):
         """Variant passed to crdpn_crd_step.  ``self.streaming = True`` selects the bank-streaming formulation
-        (EXPERIMENTAL: reads every resident row once -- 1.04 GB instead of 2.9 GB of DRAM traffic at the headline config --
-        but is instruction-bound and currently 2x slower than the gather kernel)."""
+        (EXPERIMENTAL: reads every resident row once -- 1.04 GB instead of 2.9 GB of DRAM traffic at the headline config.
+        fp32 banks: register kernel, instruction-bound and currently 2x slower than the gather kernel; bf16 banks: the
+        tcgen05 tensor-core kernel of csrc/crd_tc_stream.cuh.  See DESIGN.md section 8)."""
         if self.variant & self.STREAM:
             return self.variant
         if not self.streaming:
             return self.variant
         rows = self.row_end - self.row_begin
-        if not (D == 128 and 1 <= B <= 48 and rows >= 1 and self._buffers["memory_v1"].dtype == torch.float32):
-            raise RuntimeError("streaming CRD step needs fp32 banks, feat_dim 128 and batch <= 48")
+        if not (D == 128 and 1 <= B <= 48 and rows >= 1):
+            raise RuntimeError("streaming CRD step needs feat_dim 128 and batch <= 48")
         return self.variant | self.STREAM
 
     def _workspace(self, B, K1, D, device, variant=0):

@@ -21,6 +21,7 @@
 // this rank's bank shard, compacts the survivors into a per-warp shared-memory queue and consumes the
 // queue R rows x U steps at a time with all 2*CH*U 128-bit loads of a step group issued before first use.
 #include "common.cuh"
+#include "pointnet_common.cuh"   // tcgen05 / TMEM / mbarrier helpers (crd_tc_stream.cuh)
 
 namespace crdpn {
 
@@ -523,6 +524,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) crd_finalize_update_kernel(c
 }
 
 #include "crd_stream.cuh"
+#include "crd_tc_stream.cuh"
 
 // ------------------------------------------------------------------------------------------------------
 // Alias-method draw: one Philox4x32-10 block per output (identical stream to oracle/crd_oracle.c).
@@ -793,9 +795,9 @@ extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row
 struct TsLayout {
   size_t count, off, cursor, records, ahist, aoff, coarse_off, keys, partial, loss_part, total;
   int T, G, NB, GA;
-  TsLayout(long long B, long long K1, long long rows, int sms) {
+  TsLayout(long long B, long long K1, long long rows, int sms, int tile_rows = ts::kTR) {
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    T = (int)((rows + ts::kTR - 1) / ts::kTR);
+    T = (int)((rows + tile_rows - 1) / tile_rows);
     G = sms;
     NB = (T + (1 << ts::kCoarseShift) - 1) >> ts::kCoarseShift;
     GA = sms * 2;   // pass-A CTAs: the two passes over idx are latency-bound per CTA, the scan is limited to 48 K (CTA, bucket) pairs
@@ -814,15 +816,20 @@ struct TsLayout {
   }
 };
 
-// can the streaming formulation run this problem?  (fp32, D = 128, B <= 48, interleaved or dense banks, tile table fits)
+// can the streaming formulation run this problem?  (D = 128, B <= 48, interleaved or dense banks, tile table fits;
+// fp32 banks: register kernel, 32-row tiles; bf16 banks: tensor-core kernel, 64-row tiles)
 static bool ts_supported(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype, int64_t B, int64_t K1,
                          int64_t D, int64_t rows, int sms) {
-  if (bank_dtype != CRDPN_F32 || D != ts::kD || B < 1 || B > ts::kMaxB || rows < 1 || B * K1 >= (1ll << 31)) return false;
-  const bool inter = row_stride == 2 * D && (const char*)bank2 == (const char*)bank1 + D * 4;
+  if ((bank_dtype != CRDPN_F32 && bank_dtype != CRDPN_BF16) || D != ts::kD || B < 1 || B > ts::kMaxB || rows < 1 ||
+      B * K1 >= (1ll << 31))
+    return false;
+  const int64_t esz = bank_dtype == CRDPN_F32 ? 4 : 2;
+  const bool inter = row_stride == 2 * D && (const char*)bank2 == (const char*)bank1 + D * esz;
   const bool dense = row_stride == D;
   if (!inter && !dense) return false;
-  const long long T = (rows + ts::kTR - 1) / ts::kTR;
-  return (T + sms - 1) / sms + 1 <= ts::kMaxTilesPerCta;
+  const long long tr = bank_dtype == CRDPN_F32 ? ts::kTR : tc::kRows;
+  const long long T = (rows + tr - 1) / tr;
+  return (T + sms - 1) / sms + 1 <= (bank_dtype == CRDPN_F32 ? ts::kMaxTilesPerCta : tc::kMaxTilesPerCta);
 }
 
 extern "C" int crdpn_crd_stream_workspace_bytes(int64_t B, int64_t K1, int64_t D, int64_t rows_local, int device, size_t* bytes) {
@@ -852,9 +859,13 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
   if (rc) return rc;
   const int64_t rows = row_end - row_begin;
   if (!ts_supported(bank1, bank2, row_stride, bank_dtype, B, K1, D, rows, di.sms))
-    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): needs fp32 banks, feat_dim 128, batch <= 48, interleaved or dense banks");
-  if (di.max_smem_optin < ts::kSmemBytes) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): not enough shared memory");
-  const TsLayout L(B, K1, rows, di.sms);
+    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): needs feat_dim 128, batch <= 48, interleaved or dense banks");
+  const bool use_tc = bank_dtype == CRDPN_BF16;   // bf16 banks: tensor-core kernel (crd_tc_stream.cuh), 64-row tiles
+  if (use_tc && copy_only) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): copy-only probe is fp32 only");
+  if (di.max_smem_optin < (use_tc ? (int)tc::kSmem : (int)ts::kSmemBytes))
+    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): not enough shared memory");
+  const int tshift = use_tc ? 6 : 5;
+  const TsLayout L(B, K1, rows, di.sms, 1 << tshift);
   if (workspace_bytes < L.total) return fail(CRDPN_E_WORKSPACE, "crdpn_crd_step (streaming): workspace too small (crdpn_crd_stream_workspace_bytes)");
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
@@ -868,6 +879,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
   bp.records = (unsigned*)(ws + L.records);
   bp.T = L.T;
   bp.vec_ok = ((uintptr_t)contrast_idx & 15) == 0 ? 1 : 0;
+  bp.tshift = tshift;
 
   const double Kd = (double)(k_total > 0 ? k_total : (K1 - 1));
   const double Pn = 1.0 / (double)n_data;
@@ -892,6 +904,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
   static bool attr_set[64] = {false};
   if (!attr_set[device]) {
     CRDPN_CUDA(cudaFuncSetAttribute(ts::crd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmemBytes));
+    CRDPN_CUDA(cudaFuncSetAttribute(tc::crd_tc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmem));
     CRDPN_CUDA(cudaFuncSetAttribute(ts::ts_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kScanSmemMax * 4));
     CRDPN_CUDA(cudaFuncSetAttribute(ts::ts_coarse_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kPartScanMax * 4));
     attr_set[device] = true;
@@ -902,7 +915,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
       // two-pass partition: shared-memory atomics only
       ts::PartParams pp;
       pp.idx = bp.idx; pp.P = bp.P; pp.K1 = bp.K1; pp.row_begin = row_begin; pp.row_end = row_end;
-      pp.T = L.T; pp.NB = L.NB; pp.GA = L.GA;
+      pp.T = L.T; pp.NB = L.NB; pp.GA = L.GA; pp.tshift = tshift;
       pp.ahist = (unsigned*)(ws + L.ahist); pp.aoff = (unsigned*)(ws + L.aoff); pp.coarse_off = (unsigned*)(ws + L.coarse_off);
       pp.keys = (unsigned*)(ws + L.keys); pp.tile_off = bp.off; pp.records = bp.records;
       const size_t sh = (size_t)L.NB * 4;
@@ -924,15 +937,26 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
       ts::ts_scatter_kernel<<<pre_grid, 256, 0, st>>>(bp);
       CRDPN_LAUNCH_CHECK("ts_scatter_kernel");
     }
-    ts::crd_stream_kernel<<<L.G, ts::kThreadsTS, ts::kSmemBytes, st>>>(sp);
-    CRDPN_LAUNCH_CHECK("crd_stream_kernel");
+    if (use_tc) {
+      tc::TcParams tp;
+      tp.bank1 = sp.bank1; tp.bank2 = sp.bank2; tp.interleaved = sp.interleaved; tp.rows = rows; tp.B = (int)B; tp.T = L.T;
+      tp.v1 = v1; tp.v2 = v2; tp.tile_off = sp.tile_off; tp.records = sp.records;
+      tp.k_exp = sp.k_exp; tp.inv_Z1 = sp.inv_Z1; tp.inv_Z2 = sp.inv_Z2; tp.c = sp.c; tp.inv_mPn = sp.inv_mPn;
+      tp.eps_over_mPn = sp.eps_over_mPn; tp.inv_BT = sp.inv_BT; tp.partial = sp.partial; tp.loss_part = sp.loss_part;
+      tc::crd_tc_stream_kernel<<<L.G, tc::kThreads, tc::kSmem, st>>>(tp);
+      CRDPN_LAUNCH_CHECK("crd_tc_stream_kernel");
+    } else {
+      ts::crd_stream_kernel<<<L.G, ts::kThreadsTS, ts::kSmemBytes, st>>>(sp);
+      CRDPN_LAUNCH_CHECK("crd_stream_kernel");
+    }
   }
   ts::TsFinalizeParams fp;
   fp.partial = sp.partial; fp.loss_part = sp.loss_part; fp.tile_off = bp.off;
   fp.G = L.G; fp.B = (int)B; fp.T = L.T;
   fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2; fp.result = result;
   const int ublocks = (int)((2 * B + 7) / 8);
-  ts::ts_finalize_update_kernel<float><<<(int)B + ublocks, 256, 0, st>>>(fp, upd);
+  if (use_tc) ts::ts_finalize_update_kernel<__nv_bfloat16><<<(int)B + ublocks, 256, 0, st>>>(fp, upd);
+  else ts::ts_finalize_update_kernel<float><<<(int)B + ublocks, 256, 0, st>>>(fp, upd);
   CRDPN_LAUNCH_CHECK("ts_finalize_update_kernel");
   return CRDPN_OK;
 }

@@ -72,9 +72,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// record: bits [0,5) row inside the tile | [5,15) anchor | bit 31 positive
+// record: bits [0,6) row inside the tile (tiles of 32 or 64 rows) | [6,16) anchor | bit 31 positive
 __device__ __forceinline__ unsigned make_record(unsigned row_in_tile, unsigned b, bool pos) {
-  return row_in_tile | (b << 5) | (pos ? 0x80000000u : 0u);
+  return row_in_tile | (b << 6) | (pos ? 0x80000000u : 0u);
 }
 
 struct BucketParams {
@@ -88,6 +88,7 @@ struct BucketParams {
   unsigned* records;      // [P + 8]
   int T;
   int vec_ok;             // idx is 16-byte aligned: 128-bit index loads
+  int tshift;             // log2(rows per tile): 5 or 6
 };
 
 // four indices per thread per iteration (two 16-byte loads in flight, then four independent atomics)
@@ -100,11 +101,11 @@ __global__ void __launch_bounds__(256) ts_hist_kernel(const BucketParams p) {
     const long long r[4] = {a.x, a.y, b.x, b.y};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (r[q] >= p.row_begin && r[q] < p.row_end) atomicAdd(p.count + ((r[q] - p.row_begin) >> 5), 1u);
+      if (r[q] >= p.row_begin && r[q] < p.row_end) atomicAdd(p.count + ((r[q] - p.row_begin) >> p.tshift), 1u);
   }
   for (long long i = 4 * n4 + t0; i < p.P; i += stride) {
     const long long r = p.idx[i];
-    if (r >= p.row_begin && r < p.row_end) atomicAdd(p.count + ((r - p.row_begin) >> 5), 1u);
+    if (r >= p.row_begin && r < p.row_end) atomicAdd(p.count + ((r - p.row_begin) >> p.tshift), 1u);
   }
 }
 
@@ -182,8 +183,8 @@ __device__ __forceinline__ void ts_scatter_one(const BucketParams& p, long long 
   const unsigned local = (unsigned)(r - p.row_begin);
   const unsigned b = (unsigned)i / p.K1;                 // P < 2^31 (checked on the host)
   const bool pos = (unsigned)i - b * p.K1 == 0u;
-  const unsigned slot = atomicAdd(p.cursor + (local >> 5), 1u);
-  p.records[slot] = make_record(local & 31u, b, pos);
+  const unsigned slot = atomicAdd(p.cursor + (local >> p.tshift), 1u);
+  p.records[slot] = make_record(local & ((1u << p.tshift) - 1u), b, pos);
 }
 
 __global__ void __launch_bounds__(256) ts_scatter_kernel(const BucketParams p) {
@@ -214,10 +215,11 @@ struct PartParams {
   unsigned K1;
   long long row_begin, row_end;
   int T, NB, GA;
+  int tshift;            // log2(rows per tile): 5 or 6
   unsigned* ahist;       // [NB][GA] (bucket-major: the scan reads it linearly)
   unsigned* aoff;        // [NB][GA]
   unsigned* coarse_off;  // [NB + 1]
-  unsigned* keys;        // [P]: row_in_tile | b << 5 | tile_in_coarse << 15 | pos << 31
+  unsigned* keys;        // [P]: row_in_tile | b << 6 | tile_in_coarse << 16 | pos << 31
   unsigned* tile_off;    // [T + 1]
   unsigned* records;     // [P + 8]
 };
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(kPartThreads) ts_coarse_hist_kernel(const Part
   const long long lo = p.P * blockIdx.x / p.GA, hi = p.P * (blockIdx.x + 1) / p.GA;
   for (long long i = lo + threadIdx.x; i < hi; i += kPartThreads) {
     const long long r = p.idx[i];
-    if (r >= p.row_begin && r < p.row_end) atomicAdd(part_sh + (((r - p.row_begin) >> 5) >> kCoarseShift), 1u);
+    if (r >= p.row_begin && r < p.row_end) atomicAdd(part_sh + (((r - p.row_begin) >> p.tshift) >> kCoarseShift), 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < p.NB; i += kPartThreads) p.ahist[(size_t)i * p.GA + blockIdx.x] = part_sh[i];
@@ -276,11 +278,11 @@ __global__ void __launch_bounds__(kPartThreads) ts_coarse_scatter_kernel(const P
   for (long long i = lo + threadIdx.x; i < hi; i += kPartThreads) {
     const long long r = p.idx[i];
     if (r < p.row_begin || r >= p.row_end) continue;
-    const unsigned local = (unsigned)(r - p.row_begin), tile = local >> 5;
+    const unsigned local = (unsigned)(r - p.row_begin), tile = local >> p.tshift;
     const unsigned b = (unsigned)i / p.K1;
     const bool pos = (unsigned)i - b * p.K1 == 0u;
     const unsigned slot = atomicAdd(part_sh + (tile >> kCoarseShift), 1u);
-    p.keys[slot] = (local & 31u) | (b << 5) | ((tile & ((1u << kCoarseShift) - 1u)) << 15) | (pos ? 0x80000000u : 0u);
+    p.keys[slot] = (local & ((1u << p.tshift) - 1u)) | (b << 6) | ((tile & ((1u << kCoarseShift) - 1u)) << 16) | (pos ? 0x80000000u : 0u);
   }
 }
 
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(512) ts_fine_kernel(const PartParams p) {
   const unsigned lo = p.coarse_off[nb], hi = p.coarse_off[nb + 1];
   if (t < kBins) cnt[t] = 0u;
   __syncthreads();
-  for (unsigned i = lo + t; i < hi; i += 512) atomicAdd(cnt + ((p.keys[i] >> 15) & kBinMask), 1u);
+  for (unsigned i = lo + t; i < hi; i += 512) atomicAdd(cnt + ((p.keys[i] >> 16) & kBinMask), 1u);
   __syncthreads();
   unsigned mine = 0, incl = 0;
   if (t < kBins) {
@@ -318,8 +320,8 @@ __global__ void __launch_bounds__(512) ts_fine_kernel(const PartParams p) {
   __syncthreads();
   for (unsigned i = lo + t; i < hi; i += 512) {
     const unsigned k = p.keys[i];
-    const unsigned slot = atomicAdd(cur + ((k >> 15) & kBinMask), 1u);
-    p.records[slot] = k & 0x80007fffu;     // row | anchor | positive flag: the record format of make_record
+    const unsigned slot = atomicAdd(cur + ((k >> 16) & kBinMask), 1u);
+    p.records[slot] = k & 0x8000ffffu;     // row | anchor | positive flag: the record format of make_record
   }
 }
 
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(kThreadsTS, 1) crd_stream_kernel(const StreamP
         const unsigned i = base + lane;
         unsigned rec = 0x7fffffffu;   // anchor field all ones: matches no warp
         if (i < n1) rec = (i - w0 < (unsigned)kRecCap) ? recs[i - w0] : __ldg(p.records + i);
-        const unsigned recb = (rec >> 5) & 0x3ffu;
+        const unsigned recb = (rec >> 6) & 0x3ffu;
 #pragma unroll
         for (int sl = 0; sl < kSlots; ++sl) {
           unsigned m = __ballot_sync(kFull, recb == (unsigned)(warp + kWarpsTS * sl));
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(kThreadsTS, 1) crd_stream_kernel(const StreamP
             const bool valid = (h == 0) || (i1 >= 0);
             const unsigned r = __shfl_sync(kFull, rec, (h == 0 || i1 < 0) ? i0 : i1);
             const bool is_pos = (r >> 31) != 0u;
-            const unsigned char* rp = rows + (r & 31u) * row_pitch + 16 * j;
+            const unsigned char* rp = rows + (r & 63u) * row_pitch + 16 * j;
             const float4 a0 = *reinterpret_cast<const float4*>(rp);                    // bank1 row, elements [4j, 4j+4)
             const float4 a1 = *reinterpret_cast<const float4*>(rp + 256);              //            [64+4j, 64+4j+4)
             const float4 c0 = *reinterpret_cast<const float4*>(rp + bank2_off);        // bank2 row

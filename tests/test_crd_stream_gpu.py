@@ -111,3 +111,78 @@ def test_streaming_refuses_what_it_cannot_do(pkg, cuda):
         mem._step(v1, v2, y, cidx, 10.0, 10.0)
     mem.streaming = False
     assert not (mem._step_variant(49, 256, 128) & 0x200)
+
+
+# ---- bf16 banks: the tensor-core formulation (csrc/crd_tc_stream.cuh) -------------------------------------------------
+RELBF = 1e-2   # north_star's bf16 tolerance
+
+
+@pytest.mark.parametrize("N,K,B,interleave", [(4096, 1023, 46, True), (4099, 2048, 48, True), (4100, 777, 5, False),
+                                              (40000, 4096, 17, True), (1055, 300, 1, True), (63, 200, 3, True),
+                                              (20000, 16384, 46, True)])
+def test_tensor_core_stream_step_bf16_banks(pkg, oracle, cuda, N, K, B, interleave):
+    """bf16 banks + streaming = the tcgen05 kernel: loss / gradients within the bf16 tolerance of the oracle evaluated on
+    the same (bf16-valued) banks, close to the bf16 gather kernel, sample count exact, updated rows bit-identical."""
+    torch.manual_seed(3)
+    mem = pkg.ContrastMemory(128, N, K, 0.07, 0.5, interleave=interleave, bank_dtype=torch.bfloat16).to(cuda)
+    g = torch.Generator().manual_seed(4)
+    v1 = torch.nn.functional.normalize(torch.randn(B, 128, generator=g), dim=1).to(cuda)
+    v2 = torch.nn.functional.normalize(torch.randn(B, 128, generator=g), dim=1).to(cuda)
+    y = torch.randperm(N, generator=g)[:B].to(cuda)
+    cidx = torch.randint(0, N, (B, K + 1), generator=g).to(cuda)
+    if N == 40000:
+        cidx[:, 1:] = cidx[:, 1:] % 20000
+    if N == 20000:
+        cidx[:, 1:200] = cidx[:, 1:2]   # many anchors' samples on one row: the shared-memory coefficient atomics collide
+    cidx[:, 0] = y
+    b1 = mem.memory_v1.float().cpu().numpy().copy(); b2 = mem.memory_v2.float().cpu().numpy().copy()
+    mem._freeze_z(v1, v2, cidx)
+    hp = mem._host_params()
+    want = oracle.crd_score(b1, b2, v1.cpu().numpy(), v2.cpu().numpy(), cidx.cpu().numpy(), N, 0.07, hp.Z1, hp.Z2)
+    banks0 = (mem.memory_v1.clone(), mem.memory_v2.clone())
+    mem.streaming = False
+    res_g, g1_g, g2_g = mem._step(v1, v2, y, cidx, hp.Z1, hp.Z2)
+    res_g, g1_g, g2_g = res_g.clone(), g1_g.clone(), g2_g.clone()
+    after_g = (mem.memory_v1.clone(), mem.memory_v2.clone())
+    with torch.no_grad():
+        mem.memory_v1.copy_(banks0[0]); mem.memory_v2.copy_(banks0[1])
+    mem.streaming = True
+    assert mem._step_variant(B, K + 1, 128) & 0x200
+    res_s, g1_s, g2_s = mem._step(v1, v2, y, cidx, hp.Z1, hp.Z2)
+    torch.cuda.synchronize()
+    assert res_s[4].item() == B * (K + 1)
+    assert _rel(res_s[0].item(), want["loss_s"]) < RELBF and _rel(res_s[1].item(), want["loss_t"]) < RELBF
+    assert _rel(g1_s.cpu(), want["grad_v1"]) < RELBF and _rel(g2_s.cpu(), want["grad_v2"]) < RELBF
+    assert _rel(res_s[5].item(), res_g[5].item()) < RELBF
+    assert _rel(g1_s, g1_g) < RELBF and _rel(g2_s, g2_g) < RELBF
+    assert torch.equal(mem.memory_v1, after_g[0]) and torch.equal(mem.memory_v2, after_g[1])
+    # second step on the updated banks: the TMEM accumulators and barriers start clean every launch
+    res_2, g1_2, _ = mem._step(v1, v2, y, cidx, hp.Z1, hp.Z2)
+    mem.streaming = False
+    with torch.no_grad():
+        mem.memory_v1.copy_(after_g[0]); mem.memory_v2.copy_(after_g[1])
+    res_3, g1_3, _ = mem._step(v1, v2, y, cidx, hp.Z1, hp.Z2)
+    assert _rel(res_2[5].item(), res_3[5].item()) < RELBF and _rel(g1_2, g1_3) < RELBF
+
+
+def test_tensor_core_stream_on_a_shard(pkg, oracle, cuda):
+    N, K, B = 9000, 1500, 24
+    lo, hi = 3000, 7003
+    torch.manual_seed(3)
+    mem = pkg.ContrastMemory(128, N, K, 0.07, 0.5, row_begin=lo, row_end=hi, bank_dtype=torch.bfloat16).to(cuda)
+    g = torch.Generator().manual_seed(4)
+    v1 = torch.nn.functional.normalize(torch.randn(B, 128, generator=g), dim=1).to(cuda)
+    v2 = torch.nn.functional.normalize(torch.randn(B, 128, generator=g), dim=1).to(cuda)
+    y = torch.randperm(N, generator=g)[:B].to(cuda)
+    y[B // 2:] = y[:B // 2]
+    cidx = torch.randint(0, N, (B, K + 1), generator=g).to(cuda)
+    cidx[:, 0] = y
+    loc1, loc2 = mem.memory_v1.float().cpu().numpy().copy(), mem.memory_v2.float().cpu().numpy().copy()
+    Z1, Z2 = 1234.5, 987.6
+    want = oracle.crd_score(loc1, loc2, v1.cpu().numpy(), v2.cpu().numpy(), cidx.cpu().numpy(), N, 0.07, Z1, Z2,
+                            row_begin=lo, row_end=hi)
+    mem.streaming = True
+    res, g1, g2 = mem._step(v1, v2, y, cidx, Z1, Z2)
+    assert _rel(res[0].item(), want["loss_s"]) < RELBF and _rel(res[1].item(), want["loss_t"]) < RELBF
+    assert _rel(g1.cpu(), want["grad_v1"]) < RELBF and _rel(g2.cpu(), want["grad_v2"]) < RELBF
+    assert res[4].item() == ((cidx >= lo) & (cidx < hi)).sum().item()
