@@ -7,9 +7,13 @@
 //   gradients  G2^T[128 x 48] += bank1 rows^T (the same image, MN-major) . C2     4 MMAs (M 128 features, N 48, K 16 rows)
 //              G1^T[128 x 48] += bank2 rows^T . C1                                  4 MMAs
 // where C1 / C2 [row][anchor] are the sparse coefficient matrices dL/ds the sample stage builds from the tile's records
-// (one thread per sample: a shared-memory score lookup, ~35 scalar instructions, one atomicAdd into C).  The gradient
+// (one thread per sample: a shared-memory score lookup, ~60 scalar instructions, one bf16x2 atomicAdd straight into the
+// coefficient operand image; the same thread clears its entry again once the gradient MMAs have read it).  The gradient
 // accumulators stay in TMEM for the whole kernel.  Tiles are written into the SWIZZLE_128B operand image directly by
-// 16-byte cp.async (3-stage ring); with 16-bit operands the one image serves both GEMMs (csrc/umma_tf32_probe.cu, mode 2).
+// 16-byte cp.async (4-stage ring); with 16-bit operands the one image serves both GEMMs (csrc/umma_tf32_probe.cu, mode 2).
+// Software pipeline, iteration `it`: dump S(it) TMEM -> smem | issue score MMAs of tile it+1 | sample stage of tile it
+// (overlaps those MMAs) | retire tile it-1 (wait its gradient MMAs, clear its coefficients, refill its stage with tile
+// it+3) | issue gradient MMAs of tile it (overlap the next dump).  Two __syncthreads per tile.
 // Restrictions: bf16 banks (north_star's 1e-2 tolerance mode: the anchors' embeddings and the coefficients are rounded to
 // bf16 for the MMAs too), D = 128, B <= 48, interleaved or dense banks, step mode only.  fp32 banks need TF32 with
 // round-to-nearest staging and a second (BASE32B) image for the MN-major operand: next round.
@@ -21,19 +25,19 @@ using namespace pn;   // tcgen05 / mbarrier helpers of pointnet_common.cuh
 
 constexpr int kRows = 64;                       // bank rows per tile
 constexpr int kThreads = 256;
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr uint32_t kAStage = 32768;             // 2 K-blocks x [128 stacked rows x 128 B]
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffBV = kStages * kAStage;                  // [V2 | V1]: 2 K-blocks x [96 x 128 B] = 24576
-constexpr uint32_t kOffC2 = kOffBV + 24576;                     // C2^T image [48 anchors x 64 rows] bf16 = 6144
-constexpr uint32_t kOffC1 = kOffC2 + 6144;
-constexpr uint32_t kOffCf = kOffC1 + 6144;                      // fp32 staging of both C^T: [2][48][64] = 24576
+constexpr uint32_t kCImg = 6144;                                // one coefficient image: [48 anchors x 64 rows] bf16
+constexpr uint32_t kOffC = kOffBV + 24576;                      // [tile parity][C2^T | C1^T]
 constexpr uint32_t kSdPitch = 49;                               // floats per row of the score dump (odd: conflict-free)
-constexpr uint32_t kOffSd = kOffCf + 24576;                     // scores [2 banks][64 rows][49] fp32 = 25088
+constexpr uint32_t kOffSd = kOffC + 4 * kCImg;                  // scores [2 banks][64 rows][49] fp32 = 25088
 constexpr int kMaxTilesPerCta = 2047;
 constexpr uint32_t kOffTab = kOffSd + 2 * 64 * kSdPitch * 4;    // tile_off slice of this CTA
 constexpr uint32_t kOffBar = kOffTab + (kMaxTilesPerCta + 1) * 4;
 constexpr uint32_t kSmem = kOffBar + 64 + 1024;
+constexpr int kRecRegs = 2;                     // records per thread per tile kept in registers (more: re-read from L2)
 
 struct TcParams {
   const char* bank1;
@@ -70,16 +74,17 @@ __device__ __forceinline__ uint64_t desc128(uint32_t saddr, uint32_t lbo_bytes, 
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// byte offset (inside one coefficient image) of the bf16 PAIR holding (anchor b, bank row r)
+__device__ __forceinline__ uint32_t coef_off(unsigned b, unsigned r) { return sw128_off((int)b, (int)(r & ~1u)); }
 
 __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t bar_s = base + kOffBar, bar_g = base + kOffBar + 8;
+  const uint32_t bar_s = base + kOffBar, bar_g0 = base + kOffBar + 8, bar_g1 = base + kOffBar + 16;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kOffBar + 32);
   unsigned* offs = reinterpret_cast<unsigned*>(sm + kOffTab);
-  float* Cf = reinterpret_cast<float*>(sm + kOffCf);      // [0]: C2^T (bank-1 rows -> grad_v2), [1]: C1^T
   float* Sd = reinterpret_cast<float*>(sm + kOffSd);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -87,18 +92,18 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   const int t_end = (int)((long long)p.T * (blockIdx.x + 1) / gridDim.x);
   const int ntiles = t_end - t_begin;
   for (int i = tid; i <= ntiles; i += kThreads) offs[i] = p.tile_off[t_begin + i];
-  // [V2 | V1] operand image (bf16, anchors >= B are zero rows) and zeroed coefficient staging
+  // [V2 | V1] operand image (bf16, anchors >= B are zero rows) and zeroed coefficient images
   for (int i = tid; i < 96 * 128; i += kThreads) {
     const int n = i >> 7, e = i & 127;
     const int b = n < 48 ? n : n - 48;
     const float v = b < p.B ? (n < 48 ? p.v2[(size_t)b * 128 + e] : p.v1[(size_t)b * 128 + e]) : 0.f;
     *reinterpret_cast<__nv_bfloat16*>(sm + kOffBV + (e >> 6) * (96 * 128) + sw128_off(n, e & 63)) = __float2bfloat16_rn(v);
   }
-  for (int i = tid; i < 2 * 48 * 64; i += kThreads) Cf[i] = 0.f;
-  fence_proxy_async();
+  for (int i = tid; i < (int)(4 * kCImg / 16); i += kThreads) reinterpret_cast<uint4*>(sm + kOffC)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     mbar_init(bar_s, 1);
-    mbar_init(bar_g, 1);
+    mbar_init(bar_g0, 1);
+    mbar_init(bar_g1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256u);
@@ -107,15 +112,15 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  auto active = [&](int j) { return j >= 0 && j < ntiles && offs[j + 1] != offs[j]; };   // somebody sampled tile j
   // one tile = 64 rows x (256 B of bank 1 | 256 B of bank 2) = 2048 16-byte chunks: 8 per thread, written straight into
-  // the K-major SWIZZLE_128B image of the stacked operand (row m = bank * 64 + r)
-  auto load_tile = [&](int it) {
-    const int s = it % kStages;
-    if (offs[it + 1] != offs[it]) {   // nobody sampled this tile: nothing to load
-      const long long t = t_begin + it;
+  // the K-major SWIZZLE_128B image of the stacked operand (row m = bank * 64 + r).  Always commits one group.
+  auto load_tile = [&](int j) {
+    if (active(j)) {
+      const long long t = t_begin + j;
       const long long left = p.rows - t * kRows;
       const int nrows = (int)(left < kRows ? left : kRows);
-      const uint32_t dst0 = base + kOffA + s * kAStage;
+      const uint32_t dst0 = base + kOffA + (uint32_t)(j % kStages) * kAStage;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int g = tid + q * kThreads;
@@ -132,49 +137,52 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     }
     cp_async_commit();
   };
+  constexpr uint32_t kIS = idesc_bf16(128, 96, 0), kIG = idesc_bf16(128, 48, 1);
+  auto issue_scores = [&](int j) {   // warp 0, converged
+    if (elect_one()) {
+      const uint32_t a_img = base + kOffA + (uint32_t)(j % kStages) * kAStage;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        umma_f16(tmem, desc128(a_img + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                 desc128(base + kOffBV + (kk >> 2) * (96 * 128) + (kk & 3) * 32, 16, 1024), kIS, kk > 0);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+  };
 
   float ls = 0.f, lt = 0.f;
-  uint32_t n_s = 0, n_g = 0;        // completed phases of the two barriers
-  bool g_pending = false, g_started = false;
-  constexpr uint32_t kIS = idesc_bf16(128, 96, 0), kIG = idesc_bf16(128, 48, 1);
-
-  // two groups are always committed up front so that wait_group<2> inside the loop means "tile `it` has landed"
-  if (ntiles > 0) load_tile(0); else cp_async_commit();
-  if (ntiles > 1) load_tile(1); else cp_async_commit();
-  for (int it = 0; it < ntiles; ++it) {
-    const int s = it % kStages;
-    // the stage tile it+2 goes into held tile it-1: its gradient MMAs (and the C images they read) must have retired
-    if (g_pending) {
-      mbar_wait(bar_g, n_g & 1u);
-      ++n_g;
-      tc_fence_after();
-      g_pending = false;
-    }
-    if (it + 2 < ntiles) load_tile(it + 2); else cp_async_commit();
-    const unsigned n0 = offs[it], n1 = offs[it + 1];
-    if (n1 == n0) continue;           // (uniform across the CTA)
-    cp_async_wait<2>();
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t a_img = base + kOffA + s * kAStage;
-    if (warp == 0) {
-      if (elect_one()) {
+  uint32_t n_s = 0, n_g0 = 0, n_g1 = 0;   // waits done on each barrier (= its completed phases consumed)
+  bool g_started = false;
+  unsigned prev_rec[kRecRegs];            // this thread's records of tile it-1 (their coefficients are cleared at retire)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem, desc128(a_img + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                   desc128(base + kOffBV + (kk >> 2) * (96 * 128) + (kk & 3) * 32, 16, 1024), kIS, kk > 0);
-        umma_commit(bar_s);
-      }
-      __syncwarp();
+  for (int j = 0; j < kRecRegs; ++j) prev_rec[j] = 0u;
+
+  load_tile(0);
+  load_tile(1);
+  load_tile(2);
+  cp_async_wait<2>();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0 && active(0)) issue_scores(0);
+
+  for (int it = 0; it < ntiles; ++it) {
+    const bool act = active(it);
+    const unsigned n0 = offs[it], n1 = offs[it + 1];
+    unsigned rec[kRecRegs];
+#pragma unroll
+    for (int j = 0; j < kRecRegs; ++j) {
+      const unsigned i = n0 + tid + j * kThreads;
+      rec[j] = i < n1 ? __ldg(p.records + i) : 0u;
     }
-    mbar_wait(bar_s, n_s & 1u);
-    ++n_s;
-    tc_fence_after();
-    {  // score dump: thread = stacked row m (TMEM lane); bank-1 rows keep the V2 columns, bank-2 rows the V1 columns
+    // ---- scores of tile it: TMEM -> shared memory
+    if (act) {
+      mbar_wait(bar_s, n_s & 1u);
+      ++n_s;
+      tc_fence_after();
       const int q = warp & 3, half = warp >> 2;
-      const int m = q * 32 + lane, bank = m >> 6, r = m & 63;
+      const int m = q * 32 + lane, bank = m >> 6, r = m & 63;   // stacked row = TMEM lane; bank-1 rows keep the V2 columns
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bank * 48 + half * 24);
       uint32_t v[24];
       tmem_ld16(taddr, v);
@@ -184,66 +192,92 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
 #pragma unroll
       for (int i = 0; i < 24; ++i) dst[i] = __uint_as_float(v[i]);
     }
-    tc_fence_before();
-    __syncthreads();
-    // sample stage: one thread per record
-    for (unsigned i = n0 + tid; i < n1; i += kThreads) {
-      const unsigned rec = __ldg(p.records + i);
-      const unsigned r = rec & 63u, b = (rec >> 6) & 0x3ffu;
-      const bool is_pos = (rec >> 31) != 0u;
-      const float s2 = Sd[(size_t)r * kSdPitch + b];               // bank-1 row . v2  (out_v2 direction)
-      const float s1 = Sd[(size_t)(64 + r) * kSdPitch + b];        // bank-2 row . v1  (out_v1 direction)
-      const float e1 = ex2_approx(s1 * p.k_exp), e2 = ex2_approx(s2 * p.k_exp);
-      const float o1 = e1 * p.inv_Z1, o2 = e2 * p.inv_Z2;
-      const float rc1 = rcp_approx(o1 + p.c), rc2 = rcp_approx(o2 + p.c);
-      const float d1 = (is_pos ? -p.c : o1) * rc1 * p.inv_BT;
-      const float d2 = (is_pos ? -p.c : o2) * rc2 * p.inv_BT;
-      float t1, t2;
-      if (is_pos) {
-        t1 = logf(__fdiv_rn(o1, o1 + p.c));
-        t2 = logf(__fdiv_rn(o2, o2 + p.c));
-      } else {
-        t1 = -log1p_pos(fmaf(o1, p.inv_mPn, p.eps_over_mPn));
-        t2 = -log1p_pos(fmaf(o2, p.inv_mPn, p.eps_over_mPn));
-      }
-      ls += t1;
-      lt += t2;
-      atomicAdd(Cf + (size_t)b * 64 + r, d2);                 // C2^T[b][r]: bank-1 row r -> grad_v2[b]
-      atomicAdd(Cf + 48 * 64 + (size_t)b * 64 + r, d1);       // C1^T[b][r]: bank-2 row r -> grad_v1[b]
-    }
-    __syncthreads();
-    // coefficient images (bf16, K-major SWIZZLE_128B: row = anchor, k = bank row); the staging is re-zeroed on the way
-    for (int i = tid; i < 2 * 48 * 32; i += kThreads) {
-      const int which = i / (48 * 32), j = i - which * (48 * 32), b = j >> 5, r2 = (j & 31) * 2;
-      float* src = Cf + which * (48 * 64) + b * 64 + r2;
-      const float2 v = *reinterpret_cast<const float2*>(src);
-      *reinterpret_cast<float2*>(src) = make_float2(0.f, 0.f);
-      *reinterpret_cast<uint32_t*>(sm + (which ? kOffC1 : kOffC2) + sw128_off(b, r2)) = pack_bf16(v.x, v.y);
-    }
+    cp_async_wait<1>();          // tile it+1 has landed (only tile it+2 may still be in flight)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 0) {
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {   // 16 bank rows per step = two 8-row swizzle atoms of the same image, read MN-major
-          const uint32_t acc = (g_started || kk > 0) ? 1u : 0u;
-          umma_f16(tmem + 96, desc128(a_img + kk * 2048, 16384, 1024), desc128(base + kOffC2 + kk * 32, 16, 1024), kIG, acc);
-          umma_f16(tmem + 144, desc128(a_img + 64 * 128 + kk * 2048, 16384, 1024), desc128(base + kOffC1 + kk * 32, 16, 1024), kIG, acc);
+    if (warp == 0 && active(it + 1)) issue_scores(it + 1);   // runs under the sample stage below
+    // ---- sample stage of tile it: one thread per record
+    if (act) {
+      uint8_t* cimg = sm + kOffC + (uint32_t)(it & 1) * 2 * kCImg;
+      auto sample = [&](unsigned rc) {
+        const unsigned r = rc & 63u, b = (rc >> 6) & 0x3ffu;
+        const bool is_pos = (rc >> 31) != 0u;
+        const float s2 = Sd[(size_t)r * kSdPitch + b];               // bank-1 row . v2  (out_v2 direction)
+        const float s1 = Sd[(size_t)(64 + r) * kSdPitch + b];        // bank-2 row . v1  (out_v1 direction)
+        const float e1 = ex2_approx(s1 * p.k_exp), e2 = ex2_approx(s2 * p.k_exp);
+        const float o1 = e1 * p.inv_Z1, o2 = e2 * p.inv_Z2;
+        const float rc1 = rcp_approx(o1 + p.c), rc2 = rcp_approx(o2 + p.c);
+        const float d1 = (is_pos ? -p.c : o1) * rc1 * p.inv_BT;
+        const float d2 = (is_pos ? -p.c : o2) * rc2 * p.inv_BT;
+        float t1, t2;
+        if (is_pos) {
+          t1 = logf(__fdiv_rn(o1, o1 + p.c));
+          t2 = logf(__fdiv_rn(o2, o2 + p.c));
+        } else {
+          t1 = -log1p_pos(fmaf(o1, p.inv_mPn, p.eps_over_mPn));
+          t2 = -log1p_pos(fmaf(o2, p.inv_mPn, p.eps_over_mPn));
         }
-        umma_commit(bar_g);
-      }
-      __syncwarp();
+        ls += t1;
+        lt += t2;
+        const uint32_t co = coef_off(b, r);
+        const bool hi = (r & 1u) != 0u;
+        // C2^T[b][r]: bank-1 row r -> grad_v2[b];  C1^T[b][r]: bank-2 row r -> grad_v1[b]   (atomic: the same (b, row) can repeat)
+        atomicAdd(reinterpret_cast<__nv_bfloat162*>(cimg + co), hi ? __floats2bfloat162_rn(0.f, d2) : __floats2bfloat162_rn(d2, 0.f));
+        atomicAdd(reinterpret_cast<__nv_bfloat162*>(cimg + kCImg + co), hi ? __floats2bfloat162_rn(0.f, d1) : __floats2bfloat162_rn(d1, 0.f));
+      };
+#pragma unroll
+      for (int j = 0; j < kRecRegs; ++j)
+        if (n0 + tid + j * kThreads < n1) sample(rec[j]);
+      for (unsigned i = n0 + tid + kRecRegs * kThreads; i < n1; i += kThreads) sample(__ldg(p.records + i));
     }
-    g_started = true;
-    g_pending = true;
+    // ---- retire tile it-1: its gradient MMAs are done -> clear its coefficients, reuse its stage for tile it+3
+    if (active(it - 1)) {
+      if ((it - 1) & 1) { mbar_wait(bar_g1, n_g1 & 1u); ++n_g1; } else { mbar_wait(bar_g0, n_g0 & 1u); ++n_g0; }
+      uint8_t* cimg = sm + kOffC + (uint32_t)((it - 1) & 1) * 2 * kCImg;
+      const unsigned z0 = offs[it - 1], z1 = offs[it];
+      auto clear = [&](unsigned rc) {
+        const uint32_t co = coef_off((rc >> 6) & 0x3ffu, rc & 63u);
+        *reinterpret_cast<uint32_t*>(cimg + co) = 0u;
+        *reinterpret_cast<uint32_t*>(cimg + kCImg + co) = 0u;
+      };
+#pragma unroll
+      for (int j = 0; j < kRecRegs; ++j)
+        if (z0 + tid + j * kThreads < z1) clear(prev_rec[j]);
+      for (unsigned i = z0 + tid + kRecRegs * kThreads; i < z1; i += kThreads) clear(__ldg(p.records + i));
+    }
+    load_tile(it + 3);
+#pragma unroll
+    for (int j = 0; j < kRecRegs; ++j) prev_rec[j] = rec[j];
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // ---- gradient MMAs of tile it (overlap the next iteration's dump)
+    if (act) {
+      if (warp == 0) {
+        if (elect_one()) {
+          const uint32_t a_img = base + kOffA + (uint32_t)(it % kStages) * kAStage;
+          const uint32_t c_img = base + kOffC + (uint32_t)(it & 1) * 2 * kCImg;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {   // 16 bank rows per step = two 8-row swizzle atoms of the same image, read MN-major
+            const uint32_t acc = (g_started || kk > 0) ? 1u : 0u;
+            umma_f16(tmem + 96, desc128(a_img + kk * 2048, 16384, 1024), desc128(c_img + kk * 32, 16, 1024), kIG, acc);
+            umma_f16(tmem + 144, desc128(a_img + 64 * 128 + kk * 2048, 16384, 1024), desc128(c_img + kCImg + kk * 32, 16, 1024), kIG, acc);
+          }
+          umma_commit((it & 1) ? bar_g1 : bar_g0);
+        }
+        __syncwarp();
+      }
+      g_started = true;
+    }
   }
   cp_async_wait<0>();
-  if (g_pending) {
-    mbar_wait(bar_g, n_g & 1u);
-    tc_fence_after();
-  }
+  if (active(ntiles - 1)) {   // the last commit covers every MMA issued before it
+    if ((ntiles - 1) & 1) mbar_wait(bar_g1, n_g1 & 1u); else mbar_wait(bar_g0, n_g0 & 1u);
+  }   // (an active tile ntiles-2 was retired inside the loop)
+  tc_fence_after();
   // ---- flush: G2^T / G1^T (lane = feature e) -> partial[cta][b][0..127 grad_v1 | 128..255 grad_v2]
   {
     const int q = warp & 3, which = warp >> 2;            // which 0: G2^T (cols 96..143), 1: G1^T (cols 144..191)
