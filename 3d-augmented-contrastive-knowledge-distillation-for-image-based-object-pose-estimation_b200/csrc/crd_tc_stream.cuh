@@ -6,14 +6,20 @@
 //   scores     S[128 x 96]   = rows (K-major)  . [V2 | V1]^T          8 MMAs (M 128, N 96, K 16)
 //   gradients  G2^T[128 x 48] += bank1 rows^T (the same image, MN-major) . C2     4 MMAs (M 128 features, N 48, K 16 rows)
 //              G1^T[128 x 48] += bank2 rows^T . C1                                  4 MMAs
-// where C1 / C2 [row][anchor] are the sparse coefficient matrices dL/ds the sample stage builds from the tile's records
-// (one thread per sample: a shared-memory score lookup, ~60 scalar instructions, one bf16x2 atomicAdd straight into the
-// coefficient operand image; the same thread clears its entry again once the gradient MMAs have read it).  The gradient
-// accumulators stay in TMEM for the whole kernel.  Tiles are written into the SWIZZLE_128B operand image directly by
-// 16-byte cp.async (4-stage ring); with 16-bit operands the one image serves both GEMMs (csrc/umma_tf32_probe.cu, mode 2).
-// Software pipeline, iteration `it`: dump S(it) TMEM -> smem | issue score MMAs of tile it+1 | sample stage of tile it
-// (overlaps those MMAs) | retire tile it-1 (wait its gradient MMAs, clear its coefficients, refill its stage with tile
-// it+3) | issue gradient MMAs of tile it (overlap the next dump).  Two __syncthreads per tile.
+// where C1 / C2 [row][anchor] are the sparse coefficient matrices dL/ds the sample stage builds from the tile's records:
+// one thread per record looks its two scores up in the shared-memory dump of S, adds the loss terms, and COUNTS itself on
+// its (anchor, row) slot with a native integer atomic.  Records that repeat a slot (sampling with replacement) share the
+// score, so the slot's coefficient is count x d: after a barrier the slot's first record stores that product, rounded to
+// bf16 once, into the coefficient operand image (no floating-point atomics anywhere), and clears it again when the
+// gradient MMAs have read it.  The gradient accumulators stay in TMEM for the whole kernel.  Tiles are written into the
+// SWIZZLE_128B operand image directly by 16-byte cp.async (4-stage ring); with 16-bit operands the one image serves both
+// GEMMs (csrc/umma_tf32_probe.cu, mode 2).
+// Roles: warps 0..7 load, dump and sample; warp 8 issues the MMAs.  Iteration `it`, two __syncthreads per tile:
+//   (a) dump S(it) TMEM -> smem                                  | #1 |
+//   (b) workers: count + loss of tile it   ;  MMA warp: gradient MMAs of tile it-1, score MMAs of tile it+1      | #2 |
+//   (c) workers: slot owners store coefficients of tile it; retire tile it-1 (clear its coefficients, refill its stage
+//       with tile it+3)
+// Tiles with more records than two per thread (small banks, large K) take a generic three-barrier path.
 // Restrictions: bf16 banks (north_star's 1e-2 tolerance mode: the anchors' embeddings and the coefficients are rounded to
 // bf16 for the MMAs too), D = 128, B <= 48, interleaved or dense banks, step mode only.  fp32 banks need TF32 with
 // round-to-nearest staging and a second (BASE32B) image for the MN-major operand: next round.
@@ -24,7 +30,8 @@ namespace tc {
 using namespace pn;   // tcgen05 / mbarrier helpers of pointnet_common.cuh
 
 constexpr int kRows = 64;                       // bank rows per tile
-constexpr int kThreads = 256;
+constexpr int kWorkers = 256;                   // warps 0..7: loads, score dump, sample stage
+constexpr int kThreads = kWorkers + 32;         // warp 8: issues the MMAs
 constexpr int kStages = 4;
 constexpr uint32_t kAStage = 32768;             // 2 K-blocks x [128 stacked rows x 128 B]
 constexpr uint32_t kOffA = 0;
@@ -33,11 +40,13 @@ constexpr uint32_t kCImg = 6144;                                // one coefficie
 constexpr uint32_t kOffC = kOffBV + 24576;                      // [tile parity][C2^T | C1^T]
 constexpr uint32_t kSdPitch = 49;                               // floats per row of the score dump (odd: conflict-free)
 constexpr uint32_t kOffSd = kOffC + 4 * kCImg;                  // scores [2 banks][64 rows][49] fp32 = 25088
+constexpr uint32_t kOffCnt = kOffSd + 2 * 64 * kSdPitch * 4;    // records per (anchor, row) slot of the current tile: [48][64] u32
+constexpr uint32_t kPosOne = 1u << 28;                          // ... negatives counted in bits [0, 28), the positive above
 constexpr int kMaxTilesPerCta = 2047;
-constexpr uint32_t kOffTab = kOffSd + 2 * 64 * kSdPitch * 4;    // tile_off slice of this CTA
+constexpr uint32_t kOffTab = kOffCnt + 48 * 64 * 4;             // tile_off slice of this CTA
 constexpr uint32_t kOffBar = kOffTab + (kMaxTilesPerCta + 1) * 4;
 constexpr uint32_t kSmem = kOffBar + 64 + 1024;
-constexpr int kRecRegs = 2;                     // records per thread per tile kept in registers (more: re-read from L2)
+constexpr int kRecRegs = 2;                     // records per thread per tile handled on the fast path
 
 struct TcParams {
   const char* bank1;
@@ -74,8 +83,8 @@ __device__ __forceinline__ uint64_t desc128(uint32_t saddr, uint32_t lbo_bytes, 
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-// byte offset (inside one coefficient image) of the bf16 PAIR holding (anchor b, bank row r)
-__device__ __forceinline__ uint32_t coef_off(unsigned b, unsigned r) { return sw128_off((int)b, (int)(r & ~1u)); }
+// byte offset (inside one coefficient image) of the bf16 holding (anchor b, bank row r)
+__device__ __forceinline__ uint32_t coef_off(unsigned b, unsigned r) { return sw128_off((int)b, (int)r); }
 
 __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -85,14 +94,16 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   const uint32_t bar_s = base + kOffBar, bar_g0 = base + kOffBar + 8, bar_g1 = base + kOffBar + 16;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kOffBar + 32);
   unsigned* offs = reinterpret_cast<unsigned*>(sm + kOffTab);
+  unsigned* cnt = reinterpret_cast<unsigned*>(sm + kOffCnt);
   float* Sd = reinterpret_cast<float*>(sm + kOffSd);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool worker = warp < 8;
 
   const int t_begin = (int)((long long)p.T * blockIdx.x / gridDim.x);
   const int t_end = (int)((long long)p.T * (blockIdx.x + 1) / gridDim.x);
   const int ntiles = t_end - t_begin;
   for (int i = tid; i <= ntiles; i += kThreads) offs[i] = p.tile_off[t_begin + i];
-  // [V2 | V1] operand image (bf16, anchors >= B are zero rows) and zeroed coefficient images
+  // [V2 | V1] operand image (bf16, anchors >= B are zero rows), zeroed coefficient images and slot counters
   for (int i = tid; i < 96 * 128; i += kThreads) {
     const int n = i >> 7, e = i & 127;
     const int b = n < 48 ? n : n - 48;
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     *reinterpret_cast<__nv_bfloat16*>(sm + kOffBV + (e >> 6) * (96 * 128) + sw128_off(n, e & 63)) = __float2bfloat16_rn(v);
   }
   for (int i = tid; i < (int)(4 * kCImg / 16); i += kThreads) reinterpret_cast<uint4*>(sm + kOffC)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 48 * 64; i += kThreads) cnt[i] = 0u;
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_g0, 1);
@@ -113,32 +125,35 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   const uint32_t tmem = *tmem_slot;
 
   auto active = [&](int j) { return j >= 0 && j < ntiles && offs[j + 1] != offs[j]; };   // somebody sampled tile j
-  // one tile = 64 rows x (256 B of bank 1 | 256 B of bank 2) = 2048 16-byte chunks: 8 per thread, written straight into
-  // the K-major SWIZZLE_128B image of the stacked operand (row m = bank * 64 + r).  Always commits one group.
+  // one tile = 64 rows x (256 B of bank 1 | 256 B of bank 2) = 2048 16-byte chunks, 8 per worker thread, written straight
+  // into the K-major SWIZZLE_128B image of the stacked operand (row m = bank * 64 + r).  Thread (r0 = tid / 32, c = tid % 32)
+  // moves chunk c of rows r0, r0 + 8, ...: the swizzle term depends on r0 only.  Always commits one group.
+  const int ld_c = tid & 31, ld_r0 = (tid >> 5) & 7, ld_bank = ld_c >> 4, ld_cc = ld_c & 15, ld_m0 = ld_bank * 64 + ld_r0;
+  const uint32_t ld_dst = base + kOffA + (ld_cc >> 3) * 16384 + (ld_m0 >> 3) * 1024 + (ld_m0 & 7) * 128 + (((ld_cc & 7) ^ (ld_m0 & 7)) << 4);
+  const size_t ld_rowb = p.interleaved ? 512 : 256;
+  const char* ld_src = (p.interleaved ? p.bank1 + ld_c * 16 : (ld_bank ? p.bank2 : p.bank1) + ld_cc * 16) +
+                       ((size_t)t_begin * kRows + ld_r0) * ld_rowb;
   auto load_tile = [&](int j) {
     if (active(j)) {
-      const long long t = t_begin + j;
-      const long long left = p.rows - t * kRows;
-      const int nrows = (int)(left < kRows ? left : kRows);
-      const uint32_t dst0 = base + kOffA + (uint32_t)(j % kStages) * kAStage;
+      const long long left = p.rows - ((long long)t_begin + j) * kRows;
+      const uint32_t dst0 = ld_dst + (uint32_t)(j % kStages) * kAStage;
+      const char* src0 = ld_src + (size_t)j * kRows * ld_rowb;
+      if (left >= kRows) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int g = tid + q * kThreads;
-        const int r = g >> 5, c = g & 31, bank = c >> 4, cc = c & 15, m = bank * 64 + r;
-        const uint32_t dst = dst0 + (cc >> 3) * 16384 + (m >> 3) * 1024 + (m & 7) * 128 + (((cc & 7) ^ (m & 7)) << 4);
-        if (r < nrows) {
-          const char* src = p.interleaved ? p.bank1 + ((size_t)(t * kRows + r) * 512 + c * 16)
-                                          : (bank ? p.bank2 : p.bank1) + ((size_t)(t * kRows + r) * 256 + cc * 16);
-          cp_async16(dst, src);
-        } else {
-          *reinterpret_cast<uint4*>(sm + (dst - base)) = make_uint4(0u, 0u, 0u, 0u);   // 0 * C must stay 0 in the gradient GEMM
+        for (int q = 0; q < 8; ++q) cp_async16(dst0 + q * 1024, src0 + (size_t)q * 8 * ld_rowb);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (ld_r0 + 8 * q < (int)left) cp_async16(dst0 + q * 1024, src0 + (size_t)q * 8 * ld_rowb);
+          else *reinterpret_cast<uint4*>(sm + (dst0 + q * 1024 - base)) = make_uint4(0u, 0u, 0u, 0u);   // 0 * C stays 0
         }
       }
     }
     cp_async_commit();
   };
   constexpr uint32_t kIS = idesc_bf16(128, 96, 0), kIG = idesc_bf16(128, 48, 1);
-  auto issue_scores = [&](int j) {   // warp 0, converged
+  bool g_started = false;   // (MMA warp) the gradient accumulators hold something
+  auto issue_scores = [&](int j) {   // MMA warp, converged
     if (elect_one()) {
       const uint32_t a_img = base + kOffA + (uint32_t)(j % kStages) * kAStage;
 #pragma unroll
@@ -149,137 +164,199 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     }
     __syncwarp();
   };
+  auto issue_grads = [&](int j) {    // MMA warp, converged
+    if (elect_one()) {
+      const uint32_t a_img = base + kOffA + (uint32_t)(j % kStages) * kAStage;
+      const uint32_t c_img = base + kOffC + (uint32_t)(j & 1) * 2 * kCImg;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {   // 16 bank rows per step = two 8-row swizzle atoms of the same image, read MN-major
+        const uint32_t acc = (g_started || kk > 0) ? 1u : 0u;
+        umma_f16(tmem + 96, desc128(a_img + kk * 2048, 16384, 1024), desc128(c_img + kk * 32, 16, 1024), kIG, acc);
+        umma_f16(tmem + 144, desc128(a_img + 64 * 128 + kk * 2048, 16384, 1024), desc128(c_img + kCImg + kk * 32, 16, 1024), kIG, acc);
+      }
+      umma_commit((j & 1) ? bar_g1 : bar_g0);
+    }
+    __syncwarp();
+    g_started = true;
+  };
 
   float ls = 0.f, lt = 0.f;
-  uint32_t n_s = 0, n_g0 = 0, n_g1 = 0;   // waits done on each barrier (= its completed phases consumed)
-  bool g_started = false;
+  uint32_t n_s = 0, n_g0 = 0, n_g1 = 0;   // (workers) waits done on each barrier = its completed phases consumed
   unsigned prev_rec[kRecRegs];            // this thread's records of tile it-1 (their coefficients are cleared at retire)
 #pragma unroll
   for (int j = 0; j < kRecRegs; ++j) prev_rec[j] = 0u;
 
-  load_tile(0);
-  load_tile(1);
-  load_tile(2);
-  cp_async_wait<2>();
-  fence_proxy_async();
+  // one record: its loss terms, and d(loss)/d(score) of its (anchor, row) slot for a negative (dn) and for the positive (dp).
+  // Repeats of a slot (sampling with replacement) share the score, so the slot's coefficient is count * dn (+ dp): the
+  // sample stage only COUNTS records per slot (native integer atomics) and the product is rounded to bf16 once.
+  struct Coef { float dn1, dn2, dp1, dp2; };
+  auto eval = [&](unsigned rc, bool with_loss) {
+    const unsigned r = rc & 63u, b = (rc >> 6) & 0x3ffu;
+    const float s2 = Sd[(size_t)r * kSdPitch + b];               // bank-1 row . v2  (out_v2 direction)
+    const float s1 = Sd[(size_t)(64 + r) * kSdPitch + b];        // bank-2 row . v1  (out_v1 direction)
+    const float e1 = ex2_approx(s1 * p.k_exp), e2 = ex2_approx(s2 * p.k_exp);
+    const float o1 = e1 * p.inv_Z1, o2 = e2 * p.inv_Z2;
+    const float rc1 = rcp_approx(o1 + p.c) * p.inv_BT, rc2 = rcp_approx(o2 + p.c) * p.inv_BT;
+    if (with_loss) {
+      float t1, t2;
+      if ((rc >> 31) != 0u) {
+        t1 = logf(__fdiv_rn(o1, o1 + p.c));
+        t2 = logf(__fdiv_rn(o2, o2 + p.c));
+      } else {
+        t1 = -log1p_pos(fmaf(o1, p.inv_mPn, p.eps_over_mPn));
+        t2 = -log1p_pos(fmaf(o2, p.inv_mPn, p.eps_over_mPn));
+      }
+      ls += t1;
+      lt += t2;
+    }
+    return Coef{o1 * rc1, o2 * rc2, -p.c * rc1, -p.c * rc2};
+  };
+  // the slot's coefficients from its final count -> the two operand images (C2^T[b][r]: bank-1 row -> grad_v2[b]; C1^T: bank 2)
+  auto store_slot = [&](uint8_t* cimg, unsigned rc, const Coef& k) {
+    const unsigned r = rc & 63u, b = (rc >> 6) & 0x3ffu;
+    const unsigned n = cnt[b * 64 + r];
+    const float nn = (float)(n & (kPosOne - 1u)), np = (float)(n >> 28);
+    const uint32_t co = coef_off(b, r);
+    *reinterpret_cast<__nv_bfloat16*>(cimg + co) = __float2bfloat16_rn(fmaf(nn, k.dn2, np * k.dp2));
+    *reinterpret_cast<__nv_bfloat16*>(cimg + kCImg + co) = __float2bfloat16_rn(fmaf(nn, k.dn1, np * k.dp1));
+  };
+
+  if (worker) {
+    load_tile(0);
+    load_tile(1);
+    load_tile(2);
+    cp_async_wait<2>();
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0 && active(0)) issue_scores(0);
+  if (warp == 8 && active(0)) issue_scores(0);
 
   for (int it = 0; it < ntiles; ++it) {
     const bool act = active(it);
     const unsigned n0 = offs[it], n1 = offs[it + 1];
     unsigned rec[kRecRegs];
+    if (worker) {
 #pragma unroll
-    for (int j = 0; j < kRecRegs; ++j) {
-      const unsigned i = n0 + tid + j * kThreads;
-      rec[j] = i < n1 ? __ldg(p.records + i) : 0u;
-    }
-    // ---- scores of tile it: TMEM -> shared memory
-    if (act) {
-      mbar_wait(bar_s, n_s & 1u);
-      ++n_s;
-      tc_fence_after();
-      const int q = warp & 3, half = warp >> 2;
-      const int m = q * 32 + lane, bank = m >> 6, r = m & 63;   // stacked row = TMEM lane; bank-1 rows keep the V2 columns
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bank * 48 + half * 24);
-      uint32_t v[24];
-      tmem_ld16(taddr, v);
-      tmem_ld8(taddr + 16, v + 16);
-      tmem_ld_wait();
-      float* dst = Sd + (size_t)(bank * 64 + r) * kSdPitch + half * 24;
-#pragma unroll
-      for (int i = 0; i < 24; ++i) dst[i] = __uint_as_float(v[i]);
-    }
-    cp_async_wait<1>();          // tile it+1 has landed (only tile it+2 may still be in flight)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 0 && active(it + 1)) issue_scores(it + 1);   // runs under the sample stage below
-    // ---- sample stage of tile it: one thread per record
-    if (act) {
-      uint8_t* cimg = sm + kOffC + (uint32_t)(it & 1) * 2 * kCImg;
-      auto sample = [&](unsigned rc) {
-        const unsigned r = rc & 63u, b = (rc >> 6) & 0x3ffu;
-        const bool is_pos = (rc >> 31) != 0u;
-        const float s2 = Sd[(size_t)r * kSdPitch + b];               // bank-1 row . v2  (out_v2 direction)
-        const float s1 = Sd[(size_t)(64 + r) * kSdPitch + b];        // bank-2 row . v1  (out_v1 direction)
-        const float e1 = ex2_approx(s1 * p.k_exp), e2 = ex2_approx(s2 * p.k_exp);
-        const float o1 = e1 * p.inv_Z1, o2 = e2 * p.inv_Z2;
-        const float rc1 = rcp_approx(o1 + p.c), rc2 = rcp_approx(o2 + p.c);
-        const float d1 = (is_pos ? -p.c : o1) * rc1 * p.inv_BT;
-        const float d2 = (is_pos ? -p.c : o2) * rc2 * p.inv_BT;
-        float t1, t2;
-        if (is_pos) {
-          t1 = logf(__fdiv_rn(o1, o1 + p.c));
-          t2 = logf(__fdiv_rn(o2, o2 + p.c));
-        } else {
-          t1 = -log1p_pos(fmaf(o1, p.inv_mPn, p.eps_over_mPn));
-          t2 = -log1p_pos(fmaf(o2, p.inv_mPn, p.eps_over_mPn));
-        }
-        ls += t1;
-        lt += t2;
-        const uint32_t co = coef_off(b, r);
-        const bool hi = (r & 1u) != 0u;
-        // C2^T[b][r]: bank-1 row r -> grad_v2[b];  C1^T[b][r]: bank-2 row r -> grad_v1[b]   (atomic: the same (b, row) can repeat)
-        atomicAdd(reinterpret_cast<__nv_bfloat162*>(cimg + co), hi ? __floats2bfloat162_rn(0.f, d2) : __floats2bfloat162_rn(d2, 0.f));
-        atomicAdd(reinterpret_cast<__nv_bfloat162*>(cimg + kCImg + co), hi ? __floats2bfloat162_rn(0.f, d1) : __floats2bfloat162_rn(d1, 0.f));
-      };
-#pragma unroll
-      for (int j = 0; j < kRecRegs; ++j)
-        if (n0 + tid + j * kThreads < n1) sample(rec[j]);
-      for (unsigned i = n0 + tid + kRecRegs * kThreads; i < n1; i += kThreads) sample(__ldg(p.records + i));
-    }
-    // ---- retire tile it-1: its gradient MMAs are done -> clear its coefficients, reuse its stage for tile it+3
-    if (active(it - 1)) {
-      if ((it - 1) & 1) { mbar_wait(bar_g1, n_g1 & 1u); ++n_g1; } else { mbar_wait(bar_g0, n_g0 & 1u); ++n_g0; }
-      uint8_t* cimg = sm + kOffC + (uint32_t)((it - 1) & 1) * 2 * kCImg;
-      const unsigned z0 = offs[it - 1], z1 = offs[it];
-      auto clear = [&](unsigned rc) {
-        const uint32_t co = coef_off((rc >> 6) & 0x3ffu, rc & 63u);
-        *reinterpret_cast<uint32_t*>(cimg + co) = 0u;
-        *reinterpret_cast<uint32_t*>(cimg + kCImg + co) = 0u;
-      };
-#pragma unroll
-      for (int j = 0; j < kRecRegs; ++j)
-        if (z0 + tid + j * kThreads < z1) clear(prev_rec[j]);
-      for (unsigned i = z0 + tid + kRecRegs * kThreads; i < z1; i += kThreads) clear(__ldg(p.records + i));
-    }
-    load_tile(it + 3);
-#pragma unroll
-    for (int j = 0; j < kRecRegs; ++j) prev_rec[j] = rec[j];
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    // ---- gradient MMAs of tile it (overlap the next iteration's dump)
-    if (act) {
-      if (warp == 0) {
-        if (elect_one()) {
-          const uint32_t a_img = base + kOffA + (uint32_t)(it % kStages) * kAStage;
-          const uint32_t c_img = base + kOffC + (uint32_t)(it & 1) * 2 * kCImg;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {   // 16 bank rows per step = two 8-row swizzle atoms of the same image, read MN-major
-            const uint32_t acc = (g_started || kk > 0) ? 1u : 0u;
-            umma_f16(tmem + 96, desc128(a_img + kk * 2048, 16384, 1024), desc128(c_img + kk * 32, 16, 1024), kIG, acc);
-            umma_f16(tmem + 144, desc128(a_img + 64 * 128 + kk * 2048, 16384, 1024), desc128(c_img + kCImg + kk * 32, 16, 1024), kIG, acc);
-          }
-          umma_commit((it & 1) ? bar_g1 : bar_g0);
-        }
-        __syncwarp();
+      for (int j = 0; j < kRecRegs; ++j) {
+        const unsigned i = n0 + tid + j * kWorkers;
+        rec[j] = i < n1 ? __ldg(p.records + i) : 0u;
       }
-      g_started = true;
+      // ---- (a) scores of tile it: TMEM -> shared memory
+      if (act) {
+        mbar_wait(bar_s, n_s & 1u);
+        ++n_s;
+        tc_fence_after();
+        const int q = warp & 3, half = warp >> 2;
+        const int m = q * 32 + lane, bank = m >> 6, r = m & 63;   // stacked row = TMEM lane; bank-1 rows keep the V2 columns
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bank * 48 + half * 24);
+        uint32_t v[24];
+        tmem_ld16(taddr, v);
+        tmem_ld8(taddr + 16, v + 16);
+        tmem_ld_wait();
+        float* dst = Sd + (size_t)(bank * 64 + r) * kSdPitch + half * 24;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) dst[i] = __uint_as_float(v[i]);
+      }
+      cp_async_wait<1>();          // tile it+1 has landed (only tile it+2 may still be in flight)
+      fence_proxy_async();         // ... and the coefficient stores of tile it-1 (steps b, c of the previous iteration)
+    }
+    tc_fence_before();
+    __syncthreads();               // #1
+    tc_fence_after();
+    Coef ck[kRecRegs];
+    unsigned own = 0u;
+    const bool dense_tile = n1 - n0 > (unsigned)(kRecRegs * kWorkers);   // more records than the fast path holds (small banks)
+    uint8_t* cimg_it = sm + kOffC + (uint32_t)(it & 1) * 2 * kCImg;
+    if (!worker) {
+      // ---- (b, MMA warp) gradient MMAs of tile it-1, score MMAs of tile it+1: both run under the sample stage
+      if (act) ++n_s;   // (keeps this warp's phase count of bar_s equal to the workers')
+      if (active(it - 1)) issue_grads(it - 1);
+      if (active(it + 1)) issue_scores(it + 1);
+    } else if (act && dense_tile) {
+      // ---- (b, workers) crowded tile, generic path: count, then (after the barrier) every record stores its slot's value
+      for (unsigned i = n0 + tid; i < n1; i += kWorkers) {
+        const unsigned rc = __ldg(p.records + i);
+        atomicAdd(cnt + ((rc >> 6) & 0x3ffu) * 64 + (rc & 63u), (rc >> 31) ? kPosOne : 1u);
+        eval(rc, true);
+      }
+    } else if (act) {
+      // ---- (b, workers) sample stage of tile it, fast path: the first record to count itself on a slot owns the slot
+#pragma unroll
+      for (int j = 0; j < kRecRegs; ++j) {
+        if (n0 + tid + j * kWorkers < n1) {
+          const unsigned rc = rec[j];
+          const unsigned old = atomicAdd(cnt + ((rc >> 6) & 0x3ffu) * 64 + (rc & 63u), (rc >> 31) ? kPosOne : 1u);
+          ck[j] = eval(rc, true);
+          if (old == 0u) own |= 1u << j;
+        }
+      }
+    }
+    __syncthreads();               // #2
+    if (worker && act) {
+      // ---- (c) the counts are final: owners write their slot's coefficients and reset its counter
+      if (!dense_tile) {
+#pragma unroll
+        for (int j = 0; j < kRecRegs; ++j)
+          if (own & (1u << j)) {
+            store_slot(cimg_it, rec[j], ck[j]);
+            cnt[((rec[j] >> 6) & 0x3ffu) * 64 + (rec[j] & 63u)] = 0u;
+          }
+      } else {
+        for (unsigned i = n0 + tid; i < n1; i += kWorkers) {   // (repeats store the same value)
+          const unsigned rc = __ldg(p.records + i);
+          store_slot(cimg_it, rc, eval(rc, false));
+        }
+      }
+    }
+    if (dense_tile) {   // (uniform) the generic path reads the counters and the score dump from every record's thread
+      __syncthreads();
+      if (worker && act)
+        for (unsigned i = n0 + tid; i < n1; i += kWorkers) {
+          const unsigned rc = __ldg(p.records + i);
+          cnt[((rc >> 6) & 0x3ffu) * 64 + (rc & 63u)] = 0u;
+        }
+    }
+    if (worker) {
+      // ---- retire tile it-1: its gradient MMAs (issued in step b) are done -> clear its coefficients, refill its stage
+      if (active(it - 1)) {
+        if ((it - 1) & 1) { mbar_wait(bar_g1, n_g1 & 1u); ++n_g1; } else { mbar_wait(bar_g0, n_g0 & 1u); ++n_g0; }
+        uint8_t* cimg = sm + kOffC + (uint32_t)((it - 1) & 1) * 2 * kCImg;
+        const unsigned z0 = offs[it - 1], z1 = offs[it];
+        auto clear = [&](unsigned rc) {
+          const uint32_t co = coef_off((rc >> 6) & 0x3ffu, rc & 63u);
+          *reinterpret_cast<unsigned short*>(cimg + co) = 0;
+          *reinterpret_cast<unsigned short*>(cimg + kCImg + co) = 0;
+        };
+#pragma unroll
+        for (int j = 0; j < kRecRegs; ++j)
+          if (z0 + tid + j * kWorkers < z1) clear(prev_rec[j]);
+        for (unsigned i = z0 + tid + kRecRegs * kWorkers; i < z1; i += kWorkers) clear(__ldg(p.records + i));
+      }
+      load_tile(it + 3);
+#pragma unroll
+      for (int j = 0; j < kRecRegs; ++j) prev_rec[j] = rec[j];
     }
   }
-  cp_async_wait<0>();
-  if (active(ntiles - 1)) {   // the last commit covers every MMA issued before it
-    if ((ntiles - 1) & 1) mbar_wait(bar_g1, n_g1 & 1u); else mbar_wait(bar_g0, n_g0 & 1u);
-  }   // (an active tile ntiles-2 was retired inside the loop)
+  // ---- the last tile's gradient MMAs, then everything issued has to retire before the accumulators are read
+  if (worker) {
+    cp_async_wait<0>();
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
   tc_fence_after();
+  if (warp == 8) {
+    if (active(ntiles - 1)) issue_grads(ntiles - 1);
+    if (elect_one()) umma_commit(bar_s);
+    __syncwarp();
+  }
+  mbar_wait(bar_s, n_s & 1u);
+  tc_fence_after();
+  const bool any_grad = offs[ntiles] != offs[0];
   // ---- flush: G2^T / G1^T (lane = feature e) -> partial[cta][b][0..127 grad_v1 | 128..255 grad_v2]
-  {
+  if (worker) {
     const int q = warp & 3, which = warp >> 2;            // which 0: G2^T (cols 96..143), 1: G1^T (cols 144..191)
     const int e = q * 32 + lane;
     float* part = p.partial + (size_t)blockIdx.x * p.B * 256 + (which == 0 ? 128 : 0) + e;
@@ -287,17 +364,17 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
 #pragma unroll
     for (int c0 = 0; c0 < 48; c0 += 16) {
       uint32_t v[16];
-      if (g_started) { tmem_ld16(taddr + c0, v); tmem_ld_wait(); }
+      if (any_grad) { tmem_ld16(taddr + c0, v); tmem_ld_wait(); }
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (c0 + i < p.B) part[(size_t)(c0 + i) * 256] = g_started ? __uint_as_float(v[i]) : 0.f;
+        if (c0 + i < p.B) part[(size_t)(c0 + i) * 256] = any_grad ? __uint_as_float(v[i]) : 0.f;
     }
   }
   for (int o = 16; o >= 1; o >>= 1) {
     ls += __shfl_xor_sync(0xffffffffu, ls, o);
     lt += __shfl_xor_sync(0xffffffffu, lt, o);
   }
-  if (lane == 0) {
+  if (lane == 0 && worker) {
     float* lp = p.loss_part + (size_t)blockIdx.x * 32;
     lp[2 * warp] = ls; lp[2 * warp + 1] = lt;
     lp[2 * (warp + 8)] = 0.f; lp[2 * (warp + 8) + 1] = 0.f;   // ts_finalize sums 16 slots per CTA

@@ -18,13 +18,16 @@ for dt in (torch.bfloat16,):
         c[:, 0] = y
     mem._freeze_z(v1, v2, idxs[0])
     hp = mem._host_params()
-    for name, streaming in (("gather", False), ("tc_stream", True)):
+    modes = (("gather", False), ("tc_stream", True))
+    if os.environ.get("TC_ONLY"):
+        modes = (("tc_stream", True),)
+    for name, streaming in modes:
         mem.streaming = streaming
         for i in range(5):
             r = mem._step(v1, v2, y, idxs[i % 8], hp.Z1, hp.Z2)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 40
+        n = int(os.environ.get('TC_ITERS', '40'))
         e0.record()
         for i in range(n):
             r = mem._step(v1, v2, y, idxs[i % 8], hp.Z1, hp.Z2)

@@ -119,7 +119,7 @@ RELBF = 1e-2   # north_star's bf16 tolerance
 
 @pytest.mark.parametrize("N,K,B,interleave", [(4096, 1023, 46, True), (4099, 2048, 48, True), (4100, 777, 5, False),
                                               (40000, 4096, 17, True), (1055, 300, 1, True), (63, 200, 3, True),
-                                              (20000, 16384, 46, True)])
+                                              (20000, 16384, 46, True), (200000, 8192, 46, True)])
 def test_tensor_core_stream_step_bf16_banks(pkg, oracle, cuda, N, K, B, interleave):
     """bf16 banks + streaming = the tcgen05 kernel: loss / gradients within the bf16 tolerance of the oracle evaluated on
     the same (bf16-valued) banks, close to the bf16 gather kernel, sample count exact, updated rows bit-identical."""
@@ -132,8 +132,9 @@ def test_tensor_core_stream_step_bf16_banks(pkg, oracle, cuda, N, K, B, interlea
     cidx = torch.randint(0, N, (B, K + 1), generator=g).to(cuda)
     if N == 40000:
         cidx[:, 1:] = cidx[:, 1:] % 20000
-    if N == 20000:
-        cidx[:, 1:200] = cidx[:, 1:2]   # many anchors' samples on one row: the shared-memory coefficient atomics collide
+    if N >= 20000:   # repeats of one row per anchor: the crowded-tile path (N = 20000) and the fast path's claim bits (N = 200000)
+        cidx[:, 1:200] = cidx[:, 1:2]
+        cidx[:, 300:340] = cidx[:, 300:301] ^ 1   # ... and of its pair-mate row (same 32-bit word of the operand image)
     cidx[:, 0] = y
     b1 = mem.memory_v1.float().cpu().numpy().copy(); b2 = mem.memory_v2.float().cpu().numpy().copy()
     mem._freeze_z(v1, v2, cidx)
