@@ -943,6 +943,8 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
       tp.v1 = v1; tp.v2 = v2; tp.tile_off = sp.tile_off; tp.records = sp.records;
       tp.k_exp = sp.k_exp; tp.inv_Z1 = sp.inv_Z1; tp.inv_Z2 = sp.inv_Z2; tp.c = sp.c; tp.inv_mPn = sp.inv_mPn;
       tp.eps_over_mPn = sp.eps_over_mPn; tp.inv_BT = sp.inv_BT; tp.partial = sp.partial; tp.loss_part = sp.loss_part;
+      static const int tc_prof = getenv("CRDPN_TC_PROF") ? 1 : 0;
+      tp.prof = tc_prof;
       tc::crd_tc_stream_kernel<<<L.G, tc::kThreads, tc::kSmem, st>>>(tp);
       CRDPN_LAUNCH_CHECK("crd_tc_stream_kernel");
     } else {

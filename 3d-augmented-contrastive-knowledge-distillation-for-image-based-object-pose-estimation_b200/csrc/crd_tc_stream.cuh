@@ -61,8 +61,12 @@ struct TcParams {
   float k_exp, inv_Z1, inv_Z2, c, inv_mPn, eps_over_mPn, inv_BT;
   float* partial;           // [grid][B][256]
   float* loss_part;         // [grid][16][2]
+  int prof;                 // 1: CTA 0 prints its per-phase cycle counts (CRDPN_TC_PROF=1; debugging aid)
 };
 
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {   // named barrier: ids 1 (all 9 warps) and 2 (the 8 worker warps)
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -104,11 +108,12 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   const int ntiles = t_end - t_begin;
   for (int i = tid; i <= ntiles; i += kThreads) offs[i] = p.tile_off[t_begin + i];
   // [V2 | V1] operand image (bf16, anchors >= B are zero rows), zeroed coefficient images and slot counters
-  for (int i = tid; i < 96 * 128; i += kThreads) {
-    const int n = i >> 7, e = i & 127;
+  for (int i = tid; i < 96 * 32; i += kThreads) {
+    const int n = i >> 5, e = (i & 31) * 4;
     const int b = n < 48 ? n : n - 48;
-    const float v = b < p.B ? (n < 48 ? p.v2[(size_t)b * 128 + e] : p.v1[(size_t)b * 128 + e]) : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(sm + kOffBV + (e >> 6) * (96 * 128) + sw128_off(n, e & 63)) = __float2bfloat16_rn(v);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < p.B) v = *reinterpret_cast<const float4*>((n < 48 ? p.v2 : p.v1) + (size_t)b * 128 + e);
+    *reinterpret_cast<uint2*>(sm + kOffBV + (e >> 6) * (96 * 128) + sw128_off(n, e & 63)) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
   for (int i = tid; i < (int)(4 * kCImg / 16); i += kThreads) reinterpret_cast<uint4*>(sm + kOffC)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < 48 * 64; i += kThreads) cnt[i] = 0u;
@@ -233,6 +238,16 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   tc_fence_after();
   if (warp == 8 && active(0)) issue_scores(0);
 
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
+  const bool prof = p.prof != 0 && blockIdx.x == 0 && tid == 0;
+  auto tick = [&](int k) {
+    if (prof) {
+      const long long t = clock64();
+      pc[k] += t - pt;
+      pt = t;
+    }
+  };
+  if (prof) pt = clock64();
   for (int it = 0; it < ntiles; ++it) {
     const bool act = active(it);
     const unsigned n0 = offs[it], n1 = offs[it + 1];
@@ -248,6 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
         mbar_wait(bar_s, n_s & 1u);
         ++n_s;
         tc_fence_after();
+        tick(0);
         const int q = warp & 3, half = warp >> 2;
         const int m = q * 32 + lane, bank = m >> 6, r = m & 63;   // stacked row = TMEM lane; bank-1 rows keep the V2 columns
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bank * 48 + half * 24);
@@ -261,10 +277,12 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
       }
       cp_async_wait<1>();          // tile it+1 has landed (only tile it+2 may still be in flight)
       fence_proxy_async();         // ... and the coefficient stores of tile it-1 (steps b, c of the previous iteration)
+      tick(1);
     }
     tc_fence_before();
-    __syncthreads();               // #1
+    bar_sync(1, kThreads);         // #1
     tc_fence_after();
+    tick(2);
     Coef ck[kRecRegs];
     unsigned own = 0u;
     const bool dense_tile = n1 - n0 > (unsigned)(kRecRegs * kWorkers);   // more records than the fast path holds (small banks)
@@ -293,7 +311,9 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
         }
       }
     }
-    __syncthreads();               // #2
+    tick(3);
+    if (worker) bar_sync(2, kWorkers);   // #2 (the MMA warp is not part of the count -> store hand-off)
+    tick(4);
     if (worker && act) {
       // ---- (c) the counts are final: owners write their slot's coefficients and reset its counter
       if (!dense_tile) {
@@ -310,18 +330,20 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
         }
       }
     }
-    if (dense_tile) {   // (uniform) the generic path reads the counters and the score dump from every record's thread
-      __syncthreads();
-      if (worker && act)
+    if (dense_tile && worker) {   // the generic path reads the counters and the score dump from every record's thread
+      bar_sync(2, kWorkers);
+      if (act)
         for (unsigned i = n0 + tid; i < n1; i += kWorkers) {
           const unsigned rc = __ldg(p.records + i);
           cnt[((rc >> 6) & 0x3ffu) * 64 + (rc & 63u)] = 0u;
         }
     }
+    tick(5);
     if (worker) {
       // ---- retire tile it-1: its gradient MMAs (issued in step b) are done -> clear its coefficients, refill its stage
       if (active(it - 1)) {
         if ((it - 1) & 1) { mbar_wait(bar_g1, n_g1 & 1u); ++n_g1; } else { mbar_wait(bar_g0, n_g0 & 1u); ++n_g0; }
+        tick(6);
         uint8_t* cimg = sm + kOffC + (uint32_t)((it - 1) & 1) * 2 * kCImg;
         const unsigned z0 = offs[it - 1], z1 = offs[it];
         auto clear = [&](unsigned rc) {
@@ -338,7 +360,11 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
 #pragma unroll
       for (int j = 0; j < kRecRegs; ++j) prev_rec[j] = rec[j];
     }
+    tick(7);
   }
+  if (prof)
+    printf("crd_tc_stream CTA 0: %d tiles; cycles wait_scores %lld dump+fence %lld bar1 %lld sample %lld bar2 %lld store %lld wait_grads %lld clear+load %lld\n",
+           ntiles, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
   // ---- the last tile's gradient MMAs, then everything issued has to retire before the accumulators are read
   if (worker) {
     cp_async_wait<0>();
