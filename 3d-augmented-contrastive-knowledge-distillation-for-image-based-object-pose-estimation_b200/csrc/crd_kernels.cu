@@ -20,6 +20,7 @@
 // anchor by anchor; per anchor it scans 32 contrast indices at a time, drops entries that fall outside
 // this rank's bank shard, compacts the survivors into a per-warp shared-memory queue and consumes the
 // queue R rows x U steps at a time with all 2*CH*U 128-bit loads of a step group issued before first use.
+#include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
 #include "common.cuh"
 #include "pointnet_common.cuh"   // tcgen05 / TMEM / mbarrier helpers (crd_tc_stream.cuh)
 
@@ -841,6 +842,30 @@ extern "C" int crdpn_crd_stream_workspace_bytes(int64_t B, int64_t K1, int64_t D
   return CRDPN_OK;
 }
 
+// SWIZZLE_128B tensor map over one bf16 bank [rows][128] with a row stride of row_stride elements, box {64, 64}
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_bank_tensor_map(CUtensorMap* tm, const void* bank, int64_t rows, int64_t row_stride) {
+  static TensorMapEncodeTiledFn encode = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (TensorMapEncodeTiledFn)f;
+  }();
+  if (!encode) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): cuTensorMapEncodeTiled is not available in this driver");
+  const cuuint64_t dims[2] = {128, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_stride * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)tc::kRows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(bank), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step (streaming): cuTensorMapEncodeTiled rejected the bank layout");
+  return CRDPN_OK;
+}
+
 static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int bank_dtype, const float* v1, const float* v2,
                             const int64_t* contrast_idx, int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
                             int64_t row_begin, int64_t row_end, float T, float Z1, float Z2, float eps, double* result,
@@ -945,7 +970,10 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
       tp.eps_over_mPn = sp.eps_over_mPn; tp.inv_BT = sp.inv_BT; tp.partial = sp.partial; tp.loss_part = sp.loss_part;
       static const int tc_prof = getenv("CRDPN_TC_PROF") ? 1 : 0;
       tp.prof = tc_prof;
-      tc::crd_tc_stream_kernel<<<L.G, tc::kThreads, tc::kSmem, st>>>(tp);
+      CUtensorMap tm1, tm2;
+      if ((rc = make_bank_tensor_map(&tm1, bank1, rows, row_stride)) != CRDPN_OK) return rc;
+      if ((rc = make_bank_tensor_map(&tm2, bank2, rows, row_stride)) != CRDPN_OK) return rc;
+      tc::crd_tc_stream_kernel<<<L.G, tc::kThreads, tc::kSmem, st>>>(tp, tm1, tm2);
       CRDPN_LAUNCH_CHECK("crd_tc_stream_kernel");
     } else {
       ts::crd_stream_kernel<<<L.G, ts::kThreadsTS, ts::kSmemBytes, st>>>(sp);

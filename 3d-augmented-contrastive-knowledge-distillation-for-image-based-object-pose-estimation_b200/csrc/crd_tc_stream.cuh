@@ -11,14 +11,14 @@
 // its (anchor, row) slot with a native integer atomic.  Records that repeat a slot (sampling with replacement) share the
 // score, so the slot's coefficient is count x d: after a barrier the slot's first record stores that product, rounded to
 // bf16 once, into the coefficient operand image (no floating-point atomics anywhere), and clears it again when the
-// gradient MMAs have read it.  The gradient accumulators stay in TMEM for the whole kernel.  Tiles are written into the
-// SWIZZLE_128B operand image directly by 16-byte cp.async (4-stage ring); with 16-bit operands the one image serves both
-// GEMMs (csrc/umma_tf32_probe.cu, mode 2).
-// Roles: warps 0..7 load, dump and sample; warp 8 issues the MMAs.  Iteration `it`, two __syncthreads per tile:
+// gradient MMAs have read it.  The gradient accumulators stay in TMEM for the whole kernel.  Tiles arrive by TMA: four
+// SWIZZLE_128B tensor-map boxes per tile land as the operand image (4-stage ring, one mbarrier per stage); with 16-bit
+// operands the one image serves both GEMMs (csrc/umma_tf32_probe.cu, mode 2).
+// Roles: warps 0..7 dump and sample; warp 8 issues the TMA loads and the MMAs.  Iteration `it`, two __syncthreads per tile:
 //   (a) dump S(it) TMEM -> smem                                  | #1 |
 //   (b) workers: count + loss of tile it   ;  MMA warp: gradient MMAs of tile it-1, score MMAs of tile it+1      | #2 |
-//   (c) workers: slot owners store coefficients of tile it; retire tile it-1 (clear its coefficients, refill its stage
-//       with tile it+3)
+//       ... then refills the stage of tile it-1 with tile it+3
+//   (c) workers: slot owners store coefficients of tile it; clear the coefficients of tile it-1
 // Tiles with more records than two per thread (small banks, large K) take a generic three-barrier path.
 // Restrictions: bf16 banks (north_star's 1e-2 tolerance mode: the anchors' embeddings and the coefficients are rounded to
 // bf16 for the MMAs too), D = 128, B <= 48, interleaved or dense banks, step mode only.  fp32 banks need TF32 with
@@ -67,12 +67,11 @@ struct TcParams {
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {   // named barrier: ids 1 (all 9 warps) and 2 (the 8 worker warps)
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+// one SWIZZLE_128B box {64 bf16, 64 rows} of a bank -> 8 KB of the operand image; completes on the stage's mbarrier
+__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -90,13 +89,15 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32
 // byte offset (inside one coefficient image) of the bf16 holding (anchor b, bank row r)
 __device__ __forceinline__ uint32_t coef_off(unsigned b, unsigned r) { return sw128_off((int)b, (int)r); }
 
-__global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm1,
+                                                                    const __grid_constant__ CUtensorMap tm2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   const uint32_t bar_s = base + kOffBar, bar_g0 = base + kOffBar + 8, bar_g1 = base + kOffBar + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kOffBar + 32);
+  const uint32_t bar_full = base + kOffBar + 24;   // [kStages]: the tile's four TMA boxes have landed
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kOffBar + 56);
   unsigned* offs = reinterpret_cast<unsigned*>(sm + kOffTab);
   unsigned* cnt = reinterpret_cast<unsigned*>(sm + kOffCnt);
   float* Sd = reinterpret_cast<float*>(sm + kOffSd);
@@ -117,10 +118,12 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   }
   for (int i = tid; i < (int)(4 * kCImg / 16); i += kThreads) reinterpret_cast<uint4*>(sm + kOffC)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < 48 * 64; i += kThreads) cnt[i] = 0u;
+  fence_proxy_async();
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_g0, 1);
     mbar_init(bar_g1, 1);
+    for (int i = 0; i < kStages; ++i) mbar_init(bar_full + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256u);
@@ -130,31 +133,18 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   const uint32_t tmem = *tmem_slot;
 
   auto active = [&](int j) { return j >= 0 && j < ntiles && offs[j + 1] != offs[j]; };   // somebody sampled tile j
-  // one tile = 64 rows x (256 B of bank 1 | 256 B of bank 2) = 2048 16-byte chunks, 8 per worker thread, written straight
-  // into the K-major SWIZZLE_128B image of the stacked operand (row m = bank * 64 + r).  Thread (r0 = tid / 32, c = tid % 32)
-  // moves chunk c of rows r0, r0 + 8, ...: the swizzle term depends on r0 only.  Always commits one group.
-  const int ld_c = tid & 31, ld_r0 = (tid >> 5) & 7, ld_bank = ld_c >> 4, ld_cc = ld_c & 15, ld_m0 = ld_bank * 64 + ld_r0;
-  const uint32_t ld_dst = base + kOffA + (ld_cc >> 3) * 16384 + (ld_m0 >> 3) * 1024 + (ld_m0 & 7) * 128 + (((ld_cc & 7) ^ (ld_m0 & 7)) << 4);
-  const size_t ld_rowb = p.interleaved ? 512 : 256;
-  const char* ld_src = (p.interleaved ? p.bank1 + ld_c * 16 : (ld_bank ? p.bank2 : p.bank1) + ld_cc * 16) +
-                       ((size_t)t_begin * kRows + ld_r0) * ld_rowb;
+  // one tile = 64 rows x (256 B of bank 1 | 256 B of bank 2): four TMA boxes of 64 bf16 x 64 rows, each landing as one
+  // 8 KB (bank, K-block) quarter of the stacked K-major SWIZZLE_128B operand image (row m = bank * 64 + r); rows past the
+  // end of the shard are zero-filled by the tensor map (0 * C stays 0 in the gradient GEMM).  Every tile of the CTA is
+  // loaded, sampled or not, so that stage j % kStages sees exactly one barrier phase per tile.  One thread (MMA warp).
   auto load_tile = [&](int j) {
-    if (active(j)) {
-      const long long left = p.rows - ((long long)t_begin + j) * kRows;
-      const uint32_t dst0 = ld_dst + (uint32_t)(j % kStages) * kAStage;
-      const char* src0 = ld_src + (size_t)j * kRows * ld_rowb;
-      if (left >= kRows) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) cp_async16(dst0 + q * 1024, src0 + (size_t)q * 8 * ld_rowb);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (ld_r0 + 8 * q < (int)left) cp_async16(dst0 + q * 1024, src0 + (size_t)q * 8 * ld_rowb);
-          else *reinterpret_cast<uint4*>(sm + (dst0 + q * 1024 - base)) = make_uint4(0u, 0u, 0u, 0u);   // 0 * C stays 0
-        }
-      }
-    }
-    cp_async_commit();
+    const uint32_t dst = base + kOffA + (uint32_t)(j % kStages) * kAStage, bar = bar_full + 8 * (uint32_t)(j % kStages);
+    const int y = (t_begin + j) * kRows;
+    mbar_expect_tx(bar, kAStage);
+    tma_box(dst, &tm1, 0, y, bar);
+    tma_box(dst + 8192, &tm2, 0, y, bar);
+    tma_box(dst + 16384, &tm1, 64, y, bar);
+    tma_box(dst + 16384 + 8192, &tm2, 64, y, bar);
   };
   constexpr uint32_t kIS = idesc_bf16(128, 96, 0), kIG = idesc_bf16(128, 48, 1);
   bool g_started = false;   // (MMA warp) the gradient accumulators hold something
@@ -226,17 +216,32 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     *reinterpret_cast<__nv_bfloat16*>(cimg + kCImg + co) = __float2bfloat16_rn(fmaf(nn, k.dn1, np * k.dp1));
   };
 
-  if (worker) {
-    load_tile(0);
-    load_tile(1);
-    load_tile(2);
-    cp_async_wait<2>();
-    fence_proxy_async();
+  // records of the next two tiles ride in registers: a load issued two iterations ahead has landed when it is needed
+  auto fetch_records = [&](int j, unsigned* out) {
+#pragma unroll
+    for (int k = 0; k < kRecRegs; ++k) {
+      out[k] = 0u;
+      if (worker && j < ntiles) {
+        const unsigned i = offs[j] + tid + k * kWorkers;
+        if (i < offs[j + 1]) out[k] = __ldg(p.records + i);
+      }
+    }
+  };
+  unsigned rec_a[kRecRegs], rec_b[kRecRegs];
+  fetch_records(0, rec_a);
+  fetch_records(1, rec_b);
+  uint32_t m_g0 = 0, m_g1 = 0;   // (MMA warp) its own phase counts of the gradient barriers
+  if (warp == 8 && ntiles > 0) {
+    if (elect_one()) {
+      load_tile(0);
+      if (ntiles > 1) load_tile(1);
+      if (ntiles > 2) load_tile(2);
+    }
+    __syncwarp();
+    mbar_wait(bar_full, 0);
+    tc_fence_after();
+    if (active(0)) issue_scores(0);
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 8 && active(0)) issue_scores(0);
 
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
   const bool prof = p.prof != 0 && blockIdx.x == 0 && tid == 0;
@@ -252,12 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     const bool act = active(it);
     const unsigned n0 = offs[it], n1 = offs[it + 1];
     unsigned rec[kRecRegs];
-    if (worker) {
 #pragma unroll
-      for (int j = 0; j < kRecRegs; ++j) {
-        const unsigned i = n0 + tid + j * kWorkers;
-        rec[j] = i < n1 ? __ldg(p.records + i) : 0u;
-      }
+    for (int j = 0; j < kRecRegs; ++j) { rec[j] = rec_a[j]; rec_a[j] = rec_b[j]; }
+    fetch_records(it + 2, rec_b);
+    if (worker) {
       // ---- (a) scores of tile it: TMEM -> shared memory
       if (act) {
         mbar_wait(bar_s, n_s & 1u);
@@ -275,8 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
 #pragma unroll
         for (int i = 0; i < 24; ++i) dst[i] = __uint_as_float(v[i]);
       }
-      cp_async_wait<1>();          // tile it+1 has landed (only tile it+2 may still be in flight)
-      fence_proxy_async();         // ... and the coefficient stores of tile it-1 (steps b, c of the previous iteration)
+      fence_proxy_async();         // the coefficient stores of tile it-1 (steps b, c of the previous iteration) -> async proxy
       tick(1);
     }
     tc_fence_before();
@@ -291,7 +293,19 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
       // ---- (b, MMA warp) gradient MMAs of tile it-1, score MMAs of tile it+1: both run under the sample stage
       if (act) ++n_s;   // (keeps this warp's phase count of bar_s equal to the workers')
       if (active(it - 1)) issue_grads(it - 1);
-      if (active(it + 1)) issue_scores(it + 1);
+      if (it + 1 < ntiles) {
+        mbar_wait(bar_full + 8 * (uint32_t)((it + 1) % kStages), (uint32_t)(((it + 1) / kStages) & 1));
+        tc_fence_after();
+        if (active(it + 1)) issue_scores(it + 1);
+      }
+      // the stage of tile it-1 is free once its gradient MMAs have retired: refill it with tile it+3
+      if (active(it - 1)) {
+        if ((it - 1) & 1) { mbar_wait(bar_g1, m_g1 & 1u); ++m_g1; } else { mbar_wait(bar_g0, m_g0 & 1u); ++m_g0; }
+      }
+      if (it + 3 < ntiles) {
+        if (elect_one()) load_tile(it + 3);
+        __syncwarp();
+      }
     } else if (act && dense_tile) {
       // ---- (b, workers) crowded tile, generic path: count, then (after the barrier) every record stores its slot's value
       for (unsigned i = n0 + tid; i < n1; i += kWorkers) {
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     }
     tick(5);
     if (worker) {
-      // ---- retire tile it-1: its gradient MMAs (issued in step b) are done -> clear its coefficients, refill its stage
+      // ---- retire tile it-1: its gradient MMAs (issued in step b) are done -> clear its coefficients
       if (active(it - 1)) {
         if ((it - 1) & 1) { mbar_wait(bar_g1, n_g1 & 1u); ++n_g1; } else { mbar_wait(bar_g0, n_g0 & 1u); ++n_g0; }
         tick(6);
@@ -356,20 +370,16 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
           if (z0 + tid + j * kWorkers < z1) clear(prev_rec[j]);
         for (unsigned i = z0 + tid + kRecRegs * kWorkers; i < z1; i += kWorkers) clear(__ldg(p.records + i));
       }
-      load_tile(it + 3);
 #pragma unroll
       for (int j = 0; j < kRecRegs; ++j) prev_rec[j] = rec[j];
     }
     tick(7);
   }
   if (prof)
-    printf("crd_tc_stream CTA 0: %d tiles; cycles wait_scores %lld dump+fence %lld bar1 %lld sample %lld bar2 %lld store %lld wait_grads %lld clear+load %lld\n",
+    printf("crd_tc_stream CTA 0: %d tiles; cycles wait_scores %lld dump+fence %lld bar1 %lld sample %lld bar2 %lld store %lld wait_grads %lld clear %lld\n",
            ntiles, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
   // ---- the last tile's gradient MMAs, then everything issued has to retire before the accumulators are read
-  if (worker) {
-    cp_async_wait<0>();
-    fence_proxy_async();
-  }
+  if (worker) fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
