@@ -795,13 +795,18 @@ extern "C" int crdpn_crd_score(const void* bank1, const void* bank2, int64_t row
 // ---- bank-streaming step (crd_stream.cuh) ------------------------------------------------------------------------
 struct TsLayout {
   size_t count, off, cursor, records, ahist, aoff, coarse_off, keys, partial, loss_part, total;
-  int T, G, NB, GA;
+  int T, G, NB, GA, cshift;
   TsLayout(long long B, long long K1, long long rows, int sms, int tile_rows = ts::kTR) {
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     T = (int)((rows + tile_rows - 1) / tile_rows);
     G = sms;
-    NB = (T + (1 << ts::kCoarseShift) - 1) >> ts::kCoarseShift;
-    GA = sms * 2;   // pass-A CTAs: the two passes over idx are latency-bound per CTA, the scan is limited to 48 K (CTA, bucket) pairs
+    GA = sms * 2;
+    // coarse buckets: pass B runs one CTA per bucket, so aim at >= ~0.8 CTAs per SM while the (CTA, bucket) table fits the scan
+    cshift = ts::kCoarseShift;
+    while (cshift > 5 && ((T + (1 << cshift) - 1) >> cshift) * 5 < sms * 4 &&
+           (long long)((T + (1 << (cshift - 1)) - 1) >> (cshift - 1)) * GA <= ts::kPartScanMax)
+      --cshift;
+    NB = (T + (1 << cshift) - 1) >> cshift;   // pass-A CTAs: the two passes over idx are latency-bound per CTA, the scan is limited to 48 K (CTA, bucket) pairs
     size_t o = 0;
     count = o; o += up((size_t)(T + 1) * 4);
     off = o; o += up((size_t)(T + 1) * 4);
@@ -940,7 +945,7 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
       // two-pass partition: shared-memory atomics only
       ts::PartParams pp;
       pp.idx = bp.idx; pp.P = bp.P; pp.K1 = bp.K1; pp.row_begin = row_begin; pp.row_end = row_end;
-      pp.T = L.T; pp.NB = L.NB; pp.GA = L.GA; pp.tshift = tshift;
+      pp.T = L.T; pp.NB = L.NB; pp.GA = L.GA; pp.tshift = tshift; pp.cshift = L.cshift;
       pp.ahist = (unsigned*)(ws + L.ahist); pp.aoff = (unsigned*)(ws + L.aoff); pp.coarse_off = (unsigned*)(ws + L.coarse_off);
       pp.keys = (unsigned*)(ws + L.keys); pp.tile_off = bp.off; pp.records = bp.records;
       const size_t sh = (size_t)L.NB * 4;

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) ts_scatter_kernel(const BucketParams p) {
 // here the samples are first split into COARSE buckets of 256 tiles with per-CTA shared-memory histograms (pass A: count,
 // scan over (bucket, CTA), scatter 32-bit keys), then every coarse bucket is counting-sorted by tile inside one CTA (pass
 // B, 256 shared-memory bins).  Only shared-memory atomics; idx is read twice, keys written and read once.
-constexpr int kCoarseShift = 8;                  // 256 tiles per coarse bucket
+constexpr int kCoarseShift = 8;                  // at most 256 tiles per coarse bucket (PartParams::cshift <= 8)
 constexpr int kPartThreads = 256;
 constexpr int kPartScanMax = 48 * 1024;          // (CTAs x coarse buckets) entries the single-CTA scan stages in smem
 
@@ -216,6 +216,7 @@ struct PartParams {
   long long row_begin, row_end;
   int T, NB, GA;
   int tshift;            // log2(rows per tile): 5 or 6
+  int cshift;            // log2(tiles per coarse bucket): <= kCoarseShift; chosen so that pass B has about one CTA per SM
   unsigned* ahist;       // [NB][GA] (bucket-major: the scan reads it linearly)
   unsigned* aoff;        // [NB][GA]
   unsigned* coarse_off;  // [NB + 1]
@@ -229,9 +230,19 @@ __global__ void __launch_bounds__(kPartThreads) ts_coarse_hist_kernel(const Part
   for (int i = threadIdx.x; i < p.NB; i += kPartThreads) part_sh[i] = 0u;
   __syncthreads();
   const long long lo = p.P * blockIdx.x / p.GA, hi = p.P * (blockIdx.x + 1) / p.GA;
-  for (long long i = lo + threadIdx.x; i < hi; i += kPartThreads) {
+  const int sh = p.tshift + p.cshift;
+  long long i = lo + threadIdx.x;
+  for (; i + 3 * kPartThreads < hi; i += 4 * kPartThreads) {   // four independent loads in flight per thread
+    long long r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = p.idx[i + q * kPartThreads];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (r[q] >= p.row_begin && r[q] < p.row_end) atomicAdd(part_sh + ((r[q] - p.row_begin) >> sh), 1u);
+  }
+  for (; i < hi; i += kPartThreads) {
     const long long r = p.idx[i];
-    if (r >= p.row_begin && r < p.row_end) atomicAdd(part_sh + (((r - p.row_begin) >> p.tshift) >> kCoarseShift), 1u);
+    if (r >= p.row_begin && r < p.row_end) atomicAdd(part_sh + ((r - p.row_begin) >> sh), 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < p.NB; i += kPartThreads) p.ahist[(size_t)i * p.GA + blockIdx.x] = part_sh[i];
@@ -275,27 +286,46 @@ __global__ void __launch_bounds__(kPartThreads) ts_coarse_scatter_kernel(const P
   for (int i = threadIdx.x; i < p.NB; i += kPartThreads) part_sh[i] = p.aoff[(size_t)i * p.GA + blockIdx.x];
   __syncthreads();
   const long long lo = p.P * blockIdx.x / p.GA, hi = p.P * (blockIdx.x + 1) / p.GA;
-  for (long long i = lo + threadIdx.x; i < hi; i += kPartThreads) {
-    const long long r = p.idx[i];
-    if (r < p.row_begin || r >= p.row_end) continue;
+  const unsigned cmask = (1u << p.cshift) - 1u, rmask = (1u << p.tshift) - 1u;
+  auto put = [&](long long i, long long r) {
+    if (r < p.row_begin || r >= p.row_end) return;
     const unsigned local = (unsigned)(r - p.row_begin), tile = local >> p.tshift;
     const unsigned b = (unsigned)i / p.K1;
     const bool pos = (unsigned)i - b * p.K1 == 0u;
-    const unsigned slot = atomicAdd(part_sh + (tile >> kCoarseShift), 1u);
-    p.keys[slot] = (local & ((1u << p.tshift) - 1u)) | (b << 6) | ((tile & ((1u << kCoarseShift) - 1u)) << 16) | (pos ? 0x80000000u : 0u);
+    const unsigned slot = atomicAdd(part_sh + (tile >> p.cshift), 1u);
+    p.keys[slot] = (local & rmask) | (b << 6) | ((tile & cmask) << 16) | (pos ? 0x80000000u : 0u);
+  };
+  long long i = lo + threadIdx.x;
+  for (; i + 3 * kPartThreads < hi; i += 4 * kPartThreads) {
+    long long r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = p.idx[i + q * kPartThreads];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) put(i + q * kPartThreads, r[q]);
   }
+  for (; i < hi; i += kPartThreads) put(i, p.idx[i]);
 }
 
 // one CTA per coarse bucket: counting sort of its keys by tile (256 shared-memory bins) -> tile_off, records
 __global__ void __launch_bounds__(512) ts_fine_kernel(const PartParams p) {
   constexpr int kBins = 1 << kCoarseShift;
-  constexpr unsigned kBinMask = kBins - 1;
+  const unsigned kBinMask = (1u << p.cshift) - 1u;   // (bins past 1 << cshift stay empty)
   __shared__ unsigned cnt[kBins], cur[kBins], wsum[kBins / 32];
   const int nb = blockIdx.x, t = threadIdx.x;
   const unsigned lo = p.coarse_off[nb], hi = p.coarse_off[nb + 1];
   if (t < kBins) cnt[t] = 0u;
   __syncthreads();
-  for (unsigned i = lo + t; i < hi; i += 512) atomicAdd(cnt + ((p.keys[i] >> 16) & kBinMask), 1u);
+  {
+    unsigned i = lo + t;
+    for (; i + 3 * 512 < hi; i += 4 * 512) {
+      unsigned k[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) k[q] = p.keys[i + q * 512];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) atomicAdd(cnt + ((k[q] >> 16) & kBinMask), 1u);
+    }
+    for (; i < hi; i += 512) atomicAdd(cnt + ((p.keys[i] >> 16) & kBinMask), 1u);
+  }
   __syncthreads();
   unsigned mine = 0, incl = 0;
   if (t < kBins) {
@@ -314,11 +344,19 @@ __global__ void __launch_bounds__(512) ts_fine_kernel(const PartParams p) {
     for (int w = 0; w < (t >> 5); ++w) wbase += wsum[w];
     const unsigned excl = lo + wbase + incl - mine;
     cur[t] = excl;
-    const int tile = (nb << kCoarseShift) + t;
-    if (tile < p.T) p.tile_off[tile] = excl;
+    const int tile = (nb << p.cshift) + t;
+    if (t < (1 << p.cshift) && tile < p.T) p.tile_off[tile] = excl;
   }
   __syncthreads();
-  for (unsigned i = lo + t; i < hi; i += 512) {
+  unsigned i = lo + t;
+  for (; i + 3 * 512 < hi; i += 4 * 512) {
+    unsigned k[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) k[q] = p.keys[i + q * 512];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p.records[atomicAdd(cur + ((k[q] >> 16) & kBinMask), 1u)] = k[q] & 0x8000ffffu;
+  }
+  for (; i < hi; i += 512) {
     const unsigned k = p.keys[i];
     const unsigned slot = atomicAdd(cur + ((k >> 16) & kBinMask), 1u);
     p.records[slot] = k & 0x8000ffffu;     // row | anchor | positive flag: the record format of make_record

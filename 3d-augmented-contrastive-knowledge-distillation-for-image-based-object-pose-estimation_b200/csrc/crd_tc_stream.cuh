@@ -64,6 +64,17 @@ struct TcParams {
   int prof;                 // 1: CTA 0 prints its per-phase cycle counts (CRDPN_TC_PROF=1; debugging aid)
 };
 
+// mbarrier wait whose common case (the phase has already completed) costs one try_wait: the clocked, trapping loop of
+// pn::mbar_wait only starts when the first probe fails
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  if (!done) mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {   // named barrier: ids 1 (all 9 warps) and 2 (the 8 worker warps)
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -238,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
       if (ntiles > 2) load_tile(2);
     }
     __syncwarp();
-    mbar_wait(bar_full, 0);
+    wait_bar(bar_full, 0);
     tc_fence_after();
     if (active(0)) issue_scores(0);
   }
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     if (worker) {
       // ---- (a) scores of tile it: TMEM -> shared memory
       if (act) {
-        mbar_wait(bar_s, n_s & 1u);
+        wait_bar(bar_s, n_s & 1u);
         ++n_s;
         tc_fence_after();
         tick(0);
@@ -294,13 +305,13 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
       if (act) ++n_s;   // (keeps this warp's phase count of bar_s equal to the workers')
       if (active(it - 1)) issue_grads(it - 1);
       if (it + 1 < ntiles) {
-        mbar_wait(bar_full + 8 * (uint32_t)((it + 1) % kStages), (uint32_t)(((it + 1) / kStages) & 1));
+        wait_bar(bar_full + 8 * (uint32_t)((it + 1) % kStages), (uint32_t)(((it + 1) / kStages) & 1));
         tc_fence_after();
         if (active(it + 1)) issue_scores(it + 1);
       }
       // the stage of tile it-1 is free once its gradient MMAs have retired: refill it with tile it+3
       if (active(it - 1)) {
-        if ((it - 1) & 1) { mbar_wait(bar_g1, m_g1 & 1u); ++m_g1; } else { mbar_wait(bar_g0, m_g0 & 1u); ++m_g0; }
+        if ((it - 1) & 1) { wait_bar(bar_g1, m_g1 & 1u); ++m_g1; } else { wait_bar(bar_g0, m_g0 & 1u); ++m_g0; }
       }
       if (it + 3 < ntiles) {
         if (elect_one()) load_tile(it + 3);
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     if (worker) {
       // ---- retire tile it-1: its gradient MMAs (issued in step b) are done -> clear its coefficients
       if (active(it - 1)) {
-        if ((it - 1) & 1) { mbar_wait(bar_g1, n_g1 & 1u); ++n_g1; } else { mbar_wait(bar_g0, n_g0 & 1u); ++n_g0; }
+        if ((it - 1) & 1) { wait_bar(bar_g1, n_g1 & 1u); ++n_g1; } else { wait_bar(bar_g0, n_g0 & 1u); ++n_g0; }
         tick(6);
         uint8_t* cimg = sm + kOffC + (uint32_t)((it - 1) & 1) * 2 * kCImg;
         const unsigned z0 = offs[it - 1], z1 = offs[it];
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     if (elect_one()) umma_commit(bar_s);
     __syncwarp();
   }
-  mbar_wait(bar_s, n_s & 1u);
+  wait_bar(bar_s, n_s & 1u);
   tc_fence_after();
   const bool any_grad = offs[ntiles] != offs[0];
   // ---- flush: G2^T / G1^T (lane = feature e) -> partial[cta][b][0..127 grad_v1 | 128..255 grad_v2]
