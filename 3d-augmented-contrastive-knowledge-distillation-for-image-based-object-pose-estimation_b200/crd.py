@@ -391,7 +391,7 @@ class ContrastMemory(nn.Module):
         self.K = K
         self.k_total = 0   # negatives per anchor over all shards (0: the K+1 columns of contrast_idx are all of them)
         self.variant = 0
-        self.streaming = False   # True: experimental bank-streaming step (see _step_variant)
+        self.streaming = None    # None: automatic (bf16 banks only), True / False: forced (see _step_variant)
         self.register_buffer("params", torch.tensor([K, T, -1, -1, momentum], dtype=torch.float32))
         stdv = 1.0 / math.sqrt(inputSize / 3)
         rows = self.row_end - self.row_begin
@@ -451,16 +451,27 @@ class ContrastMemory(nn.Module):
     STREAM = 0x200   # variant bit: bank-streaming formulation of the step (csrc/crd_stream.cuh)
 
     def _step_variant(self, B, K1, D):
-        """Variant passed to crdpn_crd_step.  ``self.streaming = True`` selects the bank-streaming formulation
-        (EXPERIMENTAL: reads every resident row once -- 1.04 GB instead of 2.9 GB of DRAM traffic at the headline config.
-        fp32 banks: register kernel, instruction-bound and currently 2x slower than the gather kernel; bf16 banks: the
-        tcgen05 tensor-core kernel of csrc/crd_tc_stream.cuh.  See DESIGN.md section 8)."""
+        """Variant passed to crdpn_crd_step.  ``self.streaming`` selects the bank-streaming formulation, which reads every
+        resident row once instead of gathering B*(K+1) rows:
+
+        * ``None`` (default) -- automatic: used for bf16 banks (the tcgen05 tensor-core kernel of csrc/crd_tc_stream.cuh,
+          1.8x faster than the bf16 gather kernel at the headline shape) when feat_dim is 128, the batch is <= 48 and the
+          step draws at least two samples per resident row; never for fp32 banks.
+        * ``True`` -- forced (fp32 banks: the EXPERIMENTAL register kernel of csrc/crd_stream.cuh, instruction-bound and
+          2x slower than the gather kernel); raises if the shape is not supported.
+        * ``False`` -- the gather kernel."""
         if self.variant & self.STREAM:
             return self.variant
-        if not self.streaming:
+        if self.streaming is False:
             return self.variant
         rows = self.row_end - self.row_begin
-        if not (D == 128 and 1 <= B <= 48 and rows >= 1):
+        ok = D == 128 and 1 <= B <= 48 and rows >= 1
+        if self.streaming is None:
+            # samples that land on this shard: all K+1 columns when every rank draws its own rows (k_total > 0), else its share
+            hits = B * K1 if self.k_total > 0 else B * K1 * rows // max(self.nLem, 1)
+            auto = ok and self._buffers["memory_v1"].dtype == torch.bfloat16 and hits >= 2 * rows
+            return self.variant | self.STREAM if auto else self.variant
+        if not ok:
             raise RuntimeError("streaming CRD step needs feat_dim 128 and batch <= 48")
         return self.variant | self.STREAM
 

@@ -46,7 +46,7 @@ constexpr int kMaxTilesPerCta = 2047;
 constexpr uint32_t kOffTab = kOffCnt + 48 * 64 * 4;             // tile_off slice of this CTA
 constexpr uint32_t kOffBar = kOffTab + (kMaxTilesPerCta + 1) * 4;
 constexpr uint32_t kSmem = kOffBar + 64 + 1024;
-constexpr int kRecRegs = 2;                     // records per thread per tile handled on the fast path
+constexpr int kRecRegs = 4;                     // records per thread per tile handled on the fast path (1024 per tile)
 
 struct TcParams {
   const char* bank1;

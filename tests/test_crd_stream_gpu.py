@@ -187,3 +187,41 @@ def test_tensor_core_stream_on_a_shard(pkg, oracle, cuda):
     assert _rel(res[0].item(), want["loss_s"]) < RELBF and _rel(res[1].item(), want["loss_t"]) < RELBF
     assert _rel(g1.cpu(), want["grad_v1"]) < RELBF and _rel(g2.cpu(), want["grad_v2"]) < RELBF
     assert res[4].item() == ((cidx >= lo) & (cidx < hi)).sum().item()
+
+
+def test_streaming_is_automatic_for_bf16_banks_only(pkg, cuda):
+    """streaming=None (the default): bf16 banks stream when the step draws >= 2 samples per resident row; fp32 banks never."""
+    bf = pkg.ContrastMemory(128, 8192, 4096, 0.07, 0.5, bank_dtype=torch.bfloat16).to(cuda)
+    assert bf.streaming is None
+    assert bf._step_variant(46, 4097, 128) & 0x200            # 188 K samples over 8 K rows
+    assert not (bf._step_variant(2, 4097, 128) & 0x200)       # 8 K samples: gathering is cheaper than streaming the bank
+    assert not (bf._step_variant(49, 4097, 128) & 0x200)      # unsupported batch: falls back silently in automatic mode
+    bf.streaming = False
+    assert not (bf._step_variant(46, 4097, 128) & 0x200)
+    f32 = pkg.ContrastMemory(128, 8192, 4096, 0.07, 0.5).to(cuda)
+    assert not (f32._step_variant(46, 4097, 128) & 0x200)
+
+
+def test_crdloss_bf16_banks_default_path_is_the_tensor_core_step(pkg, cuda):
+    """CRDLoss with bf16 banks, default settings: forward + backward run the streaming step and agree with the gather
+    step within the bf16 tolerance; the banks receive bit-identical updates."""
+    opt = type("Opt", (), dict(s_dim=64, t_dim=48, feat_dim=128, n_data=6000, nce_k=4096, nce_t=0.07, nce_m=0.5))()
+    torch.manual_seed(5)
+    a = pkg.CRDLoss(opt, bank_dtype=torch.bfloat16).to(cuda)
+    b = pkg.CRDLoss(opt, bank_dtype=torch.bfloat16).to(cuda)
+    b.load_state_dict(a.state_dict())
+    a.contrast.streaming = False
+    assert b.contrast.streaming is None and b.contrast._step_variant(46, 4097, 128) & 0x200
+    g = torch.Generator().manual_seed(6)
+    for step in range(2):
+        f_s, f_t = torch.randn(46, 64, generator=g).to(cuda), torch.randn(46, 48, generator=g).to(cuda)
+        y = torch.randperm(6000, generator=g)[:46].to(cuda)
+        cidx = torch.randint(0, 6000, (46, 4097), generator=g).to(cuda)
+        cidx[:, 0] = y
+        fa, fb = f_s.clone().requires_grad_(), f_s.clone().requires_grad_()
+        a.zero_grad(); b.zero_grad()
+        la = a(fa, f_t, y, cidx); la.backward()
+        lb = b(fb, f_t, y, cidx); lb.backward()
+        assert _rel(lb.item(), la.item()) < RELBF and _rel(fb.grad, fa.grad) < RELBF
+        assert _rel(b.embed_s.linear.weight.grad, a.embed_s.linear.weight.grad) < RELBF
+        assert torch.equal(a.contrast.memory_v1, b.contrast.memory_v1)
