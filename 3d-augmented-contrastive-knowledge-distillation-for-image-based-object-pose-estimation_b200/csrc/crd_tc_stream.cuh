@@ -228,17 +228,20 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
   };
 
   // records of the next two tiles ride in registers: a load issued two iterations ahead has landed when it is needed
+  // (loops over a thread's record slots stop at the tile's CTA-uniform slot count: one branch skips the unused slots)
+  auto slots_of = [&](unsigned cnt_records) { return (int)min((cnt_records + kWorkers - 1) / kWorkers, (unsigned)kRecRegs); };
   auto fetch_records = [&](int j, unsigned* out) {
+    if (!worker || j >= ntiles) return;
+    const unsigned f0 = offs[j], f1 = offs[j + 1];
+    const int kmax = slots_of(f1 - f0);
 #pragma unroll
     for (int k = 0; k < kRecRegs; ++k) {
-      out[k] = 0u;
-      if (worker && j < ntiles) {
-        const unsigned i = offs[j] + tid + k * kWorkers;
-        if (i < offs[j + 1]) out[k] = __ldg(p.records + i);
-      }
+      if (k >= kmax) break;
+      const unsigned i = f0 + tid + k * kWorkers;
+      if (i < f1) out[k] = __ldg(p.records + i);
     }
   };
-  unsigned rec_a[kRecRegs], rec_b[kRecRegs];
+  unsigned rec_a[kRecRegs] = {}, rec_b[kRecRegs] = {};
   fetch_records(0, rec_a);
   fetch_records(1, rec_b);
   uint32_t m_g0 = 0, m_g1 = 0;   // (MMA warp) its own phase counts of the gradient barriers
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     Coef ck[kRecRegs];
     unsigned own = 0u;
     const bool dense_tile = n1 - n0 > (unsigned)(kRecRegs * kWorkers);   // more records than the fast path holds (small banks)
+    const int jmax = slots_of(n1 - n0);
     uint8_t* cimg_it = sm + kOffC + (uint32_t)(it & 1) * 2 * kCImg;
     if (!worker) {
       // ---- (b, MMA warp) gradient MMAs of tile it-1, score MMAs of tile it+1: both run under the sample stage
@@ -328,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
       // ---- (b, workers) sample stage of tile it, fast path: the first record to count itself on a slot owns the slot
 #pragma unroll
       for (int j = 0; j < kRecRegs; ++j) {
+        if (j >= jmax) break;
         if (n0 + tid + j * kWorkers < n1) {
           const unsigned rc = rec[j];
           const unsigned old = atomicAdd(cnt + ((rc >> 6) & 0x3ffu) * 64 + (rc & 63u), (rc >> 31) ? kPosOne : 1u);
@@ -343,11 +348,13 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
       // ---- (c) the counts are final: owners write their slot's coefficients and reset its counter
       if (!dense_tile) {
 #pragma unroll
-        for (int j = 0; j < kRecRegs; ++j)
+        for (int j = 0; j < kRecRegs; ++j) {
+          if (j >= jmax) break;
           if (own & (1u << j)) {
             store_slot(cimg_it, rec[j], ck[j]);
             cnt[((rec[j] >> 6) & 0x3ffu) * 64 + (rec[j] & 63u)] = 0u;
           }
+        }
       } else {
         for (unsigned i = n0 + tid; i < n1; i += kWorkers) {   // (repeats store the same value)
           const unsigned rc = __ldg(p.records + i);
@@ -376,9 +383,12 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
           *reinterpret_cast<unsigned short*>(cimg + co) = 0;
           *reinterpret_cast<unsigned short*>(cimg + kCImg + co) = 0;
         };
+const int zmax = slots_of(z1 - z0);
 #pragma unroll
-        for (int j = 0; j < kRecRegs; ++j)
+        for (int j = 0; j < kRecRegs; ++j) {
+          if (j >= zmax) break;
           if (z0 + tid + j * kWorkers < z1) clear(prev_rec[j]);
+        }
         for (unsigned i = z0 + tid + kRecRegs * kWorkers; i < z1; i += kWorkers) clear(__ldg(p.records + i));
       }
 #pragma unroll
