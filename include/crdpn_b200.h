@@ -125,12 +125,16 @@ int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
                    double* result, float* grad_v1, float* grad_v2,
                    void* workspace, size_t workspace_bytes, int variant, void* stream);
 
-/* EXPERIMENTAL bank-STREAMING formulation of the same step (variant | 0x200 in crdpn_crd_step / crdpn_crd_loss_forward;
- * opt-in, currently slower than the default gather kernel -- csrc/crd_stream.cuh has the measurements): the samples are
- * bucketed by 32-row bank tile and every resident tile is bulk-copied through shared memory exactly once, so a row that
- * is sampled several times per step (B*K1 > resident rows) is read from HBM once.  Same results as the gather formulation
- * to fp32 rounding (the accumulation order inside a tile follows an atomic scatter, so not bit-reproducible).
- * Requires fp32 banks, D = 128, B <= 48, banks interleaved ([rows][2][D]: bank2 = bank1 + D, row_stride = 2D) or dense
+/* Bank-STREAMING formulation of the same step (variant | 0x200 in crdpn_crd_step / crdpn_crd_loss_forward): the samples
+ * are bucketed by bank tile and every resident tile passes through shared memory exactly once, so a row that is sampled
+ * several times per step (B*K1 > resident rows) is read from HBM once.
+ *   - bf16 banks: tcgen05 tensor-core kernel (csrc/crd_tc_stream.cuh; 64-row tiles by TMA, scores and gradients as bf16
+ *     MMAs with fp32 accumulation in TMEM, integer slot counters -> order-independent results).  1.7x faster than the
+ *     bf16 gather kernel at the headline shape; the Python mirror selects it automatically (ContrastMemory.streaming).
+ *     Results within the bf16 tolerance (1e-2) of the gather formulation; updated bank rows bit-identical.
+ *   - fp32 banks: EXPERIMENTAL register kernel (csrc/crd_stream.cuh; 32-row tiles), opt-in, slower than the gather
+ *     kernel; same results to fp32 rounding (atomic scatter inside a tile: not bit-reproducible).
+ * Requires D = 128, B <= 48, banks interleaved ([rows][2][D]: bank2 = bank1 + D, row_stride = 2D) or dense
  * (row_stride = D); otherwise CRDPN_E_UNSUPPORTED.  The workspace must hold crdpn_crd_stream_workspace_bytes. */
 int crdpn_crd_stream_workspace_bytes(int64_t B, int64_t K1, int64_t D, int64_t rows_local, int device, size_t* bytes);
 
