@@ -990,8 +990,8 @@ static int stream_step_impl(void* bank1, void* bank2, int64_t row_stride, int ba
   fp.G = L.G; fp.B = (int)B; fp.T = L.T;
   fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2; fp.result = result;
   const int ublocks = (int)((2 * B + 7) / 8);
-  if (use_tc) ts::ts_finalize_update_kernel<__nv_bfloat16><<<(int)B + ublocks, 256, 0, st>>>(fp, upd);
-  else ts::ts_finalize_update_kernel<float><<<(int)B + ublocks, 256, 0, st>>>(fp, upd);
+  if (use_tc) ts::ts_finalize_update_kernel<__nv_bfloat16><<<(int)B + ublocks, ts::kTsFinalizeThreads, 0, st>>>(fp, upd);
+  else ts::ts_finalize_update_kernel<float><<<(int)B + ublocks, ts::kTsFinalizeThreads, 0, st>>>(fp, upd);
   CRDPN_LAUNCH_CHECK("ts_finalize_update_kernel");
   return CRDPN_OK;
 }

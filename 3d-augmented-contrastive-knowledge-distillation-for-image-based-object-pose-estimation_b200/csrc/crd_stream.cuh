@@ -573,30 +573,60 @@ struct TsFinalizeParams {
   double* result;
 };
 
-// blocks [0, B): column-parallel fixed-order sum over the G CTA partials of anchor b (block 0 also folds the loss);
-// remaining blocks: momentum update (update_body), as in crd_finalize_update_kernel
+// blocks [0, B): fixed-order sum over the G CTA partials of anchor b -- four groups of 256 column threads each sum a
+// quarter of the partials (eight loads in flight per thread), then the four group sums are added in group order (block 0
+// also folds the loss); remaining blocks: momentum update (update_body, warps 0..7), as in crd_finalize_update_kernel
+constexpr int kTsFinalizeThreads = 1024;
 template <typename T>
-__global__ void __launch_bounds__(256) ts_finalize_update_kernel(const TsFinalizeParams f, const UpdateParams u) {
+__global__ void __launch_bounds__(kTsFinalizeThreads) ts_finalize_update_kernel(const TsFinalizeParams f, const UpdateParams u) {
   if ((int)blockIdx.x >= f.B) {
-    update_body<T>(u, ((int)blockIdx.x - f.B) * 8 + (threadIdx.x >> 5));
+    if (threadIdx.x < 256) update_body<T>(u, ((int)blockIdx.x - f.B) * 8 + (threadIdx.x >> 5));
     return;
   }
-  const int b = blockIdx.x, col = threadIdx.x;
+  __shared__ double gsum[3][256];
+  const int b = blockIdx.x, col = threadIdx.x & 255, grp = threadIdx.x >> 8;
+  const int g0 = f.G * grp / 4, g1 = f.G * (grp + 1) / 4;
   double acc = 0.0;
-  for (int g = 0; g < f.G; ++g) acc += (double)f.partial[((size_t)g * f.B + b) * 2 * kD + col];
-  if (col < kD) f.grad_v1[(size_t)b * kD + col] = (float)acc;
-  else f.grad_v2[(size_t)b * kD + (col - kD)] = (float)acc;
+  {
+    const float* src = f.partial + (size_t)b * 2 * kD + col;
+    const size_t pitch = (size_t)f.B * 2 * kD;
+    int g = g0;
+    for (; g + 8 <= g1; g += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = src[(size_t)(g + q) * pitch];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += (double)v[q];
+    }
+    for (; g < g1; ++g) acc += (double)src[(size_t)g * pitch];
+  }
+  if (grp > 0) gsum[grp - 1][col] = acc;
+  __syncthreads();
+  if (grp == 0) {
+    acc = ((acc + gsum[0][col]) + gsum[1][col]) + gsum[2][col];
+    if (col < kD) f.grad_v1[(size_t)b * kD + col] = (float)acc;
+    else f.grad_v2[(size_t)b * kD + (col - kD)] = (float)acc;
+  }
   if (b == 0) {
     __shared__ double red[2][256];
     const int n = f.G * kWarpsTS;
     double s0 = 0.0, s1 = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) { s0 += (double)f.loss_part[2 * i]; s1 += (double)f.loss_part[2 * i + 1]; }
-    red[0][threadIdx.x] = s0;
-    red[1][threadIdx.x] = s1;
+    if (threadIdx.x < 256) {
+      for (int i = threadIdx.x; i < n; i += 256) { s0 += (double)f.loss_part[2 * i]; s1 += (double)f.loss_part[2 * i + 1]; }
+      red[0][threadIdx.x] = s0;
+      red[1][threadIdx.x] = s1;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {   // fixed-order tree: eight consecutive entries per lane, then xor shuffles
       double t0 = 0.0, t1 = 0.0;
-      for (int i = 0; i < 256; ++i) { t0 += red[0][i]; t1 += red[1][i]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { t0 += red[0][threadIdx.x * 8 + i]; t1 += red[1][threadIdx.x * 8 + i]; }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      }
+      if (threadIdx.x != 0) return;
       const double l_s = -t0 / (double)f.B, l_t = -t1 / (double)f.B;
       f.result[0] = l_s;
       f.result[1] = l_t;
