@@ -19,7 +19,9 @@
 //   (b) workers: count + loss of tile it   ;  MMA warp: gradient MMAs of tile it-1, score MMAs of tile it+1      | #2 |
 //       ... then refills the stage of tile it-1 with tile it+3
 //   (c) workers: slot owners store coefficients of tile it; clear the coefficients of tile it-1
-// Tiles with more records than two per thread (small banks, large K) take a generic three-barrier path.
+// Tiles with more records than kRecRegs = 4 per worker thread (1024 per tile: small banks, large K) take a generic
+// three-barrier path.  Measured phase costs and what bounds the kernel today: DESIGN.md sections 4.13 and 8
+// (CRDPN_TC_PROF=1 prints CTA 0's per-phase cycle counts).
 // Restrictions: bf16 banks (north_star's 1e-2 tolerance mode: the anchors' embeddings and the coefficients are rounded to
 // bf16 for the MMAs too), D = 128, B <= 48, interleaved or dense banks, step mode only.  fp32 banks need TF32 with
 // round-to-nearest staging and a second (BASE32B) image for the MN-major operand: next round.
