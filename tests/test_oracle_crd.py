@@ -226,3 +226,75 @@ def test_sharded_partials_sum_to_unsharded(oracle):
             acc[k] = acc[k] + part[k]
     for k in acc:
         np.testing.assert_allclose(acc[k], full[k], rtol=1e-12)
+
+
+# ---- edge cases: the shapes the kernels' parity tests lean on at their extremes ------------------------------------
+def _plain_nce(bank1, bank2, v1, v2, idx, n_data, T, Z1, Z2, eps=1e-7):
+    """The published loss in plain Python floats (one anchor at a time), float32 constants as in ContrastLoss."""
+    B, K1 = idx.shape
+    m = K1 - 1
+    Pn = 1.0 / float(n_data)
+    mPn = float(np.float32(m * Pn))          # P_neg.clone().fill_(m * Pn): a Python float stored into an fp32 tensor
+    c = float(np.float32(m * Pn + eps))      # x.add(m * Pn + eps): the Python-float sum, rounded to fp32 once
+    ls = lt = 0.0
+    for b in range(B):
+        for k in range(K1):
+            r = int(idx[b, k])
+            o1 = math.exp(float(np.dot(bank2[r].astype(np.float64), v1[b].astype(np.float64))) / T) / Z1
+            o2 = math.exp(float(np.dot(bank1[r].astype(np.float64), v2[b].astype(np.float64))) / T) / Z2
+            if k == 0:
+                ls += math.log(o1 / (o1 + c))
+                lt += math.log(o2 / (o2 + c))
+            else:
+                ls += math.log(mPn / (o1 + c))
+                lt += math.log(mPn / (o2 + c))
+    return -ls / B, -lt / B
+
+
+@pytest.mark.parametrize("B,K", [(1, 7), (3, 0), (1, 0), (5, 1)])
+def test_single_anchor_and_no_negatives(oracle, B, K):
+    """B = 1 and K = 0 (only the positive column): the loss is the positive term alone and every gradient row is the
+    positive's coefficient times its bank row."""
+    rng = np.random.default_rng(11)
+    N, D, T = 37, 8, 0.07
+    b1 = oracle.l2_normalize(rng.standard_normal((N, D)).astype(np.float32))
+    b2 = oracle.l2_normalize(rng.standard_normal((N, D)).astype(np.float32))
+    v1 = oracle.l2_normalize(rng.standard_normal((B, D)).astype(np.float32))
+    v2 = oracle.l2_normalize(rng.standard_normal((B, D)).astype(np.float32))
+    idx = rng.integers(0, N, (B, K + 1))
+    got = oracle.crd_score(b1, b2, v1, v2, idx, N, T, 50.0, 60.0)
+    ws, wt = _plain_nce(b1, b2, v1, v2, idx, N, T, 50.0, 60.0)
+    assert got["count"] == B * (K + 1)
+    np.testing.assert_allclose([got["loss_s"], got["loss_t"]], [ws, wt], rtol=1e-12)
+    if K == 0:
+        c = float(np.float32(1e-7))
+        for b in range(B):
+            r = idx[b, 0]
+            o1 = got["out_v1"][b, 0]
+            coef = -c / (B * T * (o1 + c))
+            np.testing.assert_allclose(got["grad_v1"][b], coef * b2[r].astype(np.float64), rtol=1e-9, atol=1e-300)
+
+
+def test_empty_shard_and_boundary_rows(oracle):
+    """A shard that owns none of the sampled rows contributes exactly nothing; rows on the shard's first and last index
+    are counted by exactly one shard."""
+    rng = np.random.default_rng(12)
+    N, D, B, K, T = 64, 16, 4, 9, 0.07
+    b1 = oracle.l2_normalize(rng.standard_normal((N, D)).astype(np.float32))
+    b2 = oracle.l2_normalize(rng.standard_normal((N, D)).astype(np.float32))
+    v1 = oracle.l2_normalize(rng.standard_normal((B, D)).astype(np.float32))
+    v2 = oracle.l2_normalize(rng.standard_normal((B, D)).astype(np.float32))
+    idx = rng.integers(0, 32, (B, K + 1))          # every sample lives in rows [0, 32)
+    idx[0, 1], idx[1, 2], idx[2, 3], idx[3, 4] = 0, 15, 16, 31   # the boundaries of shards [0,16) and [16,32)
+    empty = oracle.crd_score(b1[32:], b2[32:], v1, v2, idx, N, T, 40.0, 40.0, row_begin=32, row_end=64)
+    assert empty["count"] == 0 and empty["loss_s"] == 0.0 and empty["loss_t"] == 0.0
+    assert not empty["grad_v1"].any() and not empty["grad_v2"].any() and not empty["out_v1"].any()
+    full = oracle.crd_score(b1, b2, v1, v2, idx, N, T, 40.0, 40.0)
+    lo = oracle.crd_score(b1[:16], b2[:16], v1, v2, idx, N, T, 40.0, 40.0, row_begin=0, row_end=16)
+    hi = oracle.crd_score(b1[16:32], b2[16:32], v1, v2, idx, N, T, 40.0, 40.0, row_begin=16, row_end=32)
+    assert lo["count"] + hi["count"] == full["count"] == B * (K + 1)
+    assert lo["count"] == int((idx < 16).sum()) and hi["count"] == int((idx >= 16).sum())
+    np.testing.assert_allclose(lo["grad_v2"] + hi["grad_v2"], full["grad_v2"], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(lo["loss_s"] + hi["loss_s"], full["loss_s"], rtol=1e-12)
+    # the outputs of rows a shard does not own stay zero in that shard's out_v
+    assert not lo["out_v1"][idx >= 16].any() and not hi["out_v1"][idx < 16].any()
