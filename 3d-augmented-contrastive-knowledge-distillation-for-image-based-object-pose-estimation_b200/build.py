@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libcrdpn_b200.so"
-SOURCES = ["host.cu", "crd_kernels.cu", "pointnet_kernels.cu", "pointnet_train.cu", "pointnet_backward.cu", "embed_kernels.cu", "p2p_kernels.cu", "crd_loss.cu", "kd_losses.cu", "pointcloud_sampler.cu", "crd_unfused.cu", "umma_tf32_probe.cu"]
+SOURCES = ["host.cu", "crd_kernels.cu", "pointnet_kernels.cu", "pointnet_train.cu", "pointnet_backward.cu", "embed_kernels.cu", "p2p_kernels.cu", "crd_loss.cu", "kd_losses.cu", "pointcloud_sampler.cu", "crd_unfused.cu", "umma_tf32_probe.cu", "pointnet_train_split.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

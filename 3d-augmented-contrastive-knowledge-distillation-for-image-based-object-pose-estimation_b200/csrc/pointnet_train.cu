@@ -374,6 +374,9 @@ extern "C" int crdpn_pointnet_forward_train_phased(
   if (di.max_smem_optin < (int)pn::kSmemAlloc) return fail(CRDPN_E_UNSUPPORTED, "crdpn_pointnet_forward_train: not enough shared memory");
   cudaStream_t st = (cudaStream_t)stream;
   char* c = (char*)ctx;
+  // variant bit 4 (16): the bf16 recipe of round 1 (one MMA per product, features within 1e-2 but ~1% of the arg-max / ReLU
+  // routing decisions differ from an fp32 run); default: the fp32-accurate split recipe of pointnet_train_split.cu
+  const bool bf16_recipe = (variant & 16) != 0;
   if (phase_begin < 0 || phase_end > 4 || phase_begin >= phase_end || total_points < B * P)
     return fail(CRDPN_E_BADARG, "crdpn_pointnet_forward_train: bad phase range / total_points");
   auto on = [&](int ph) { return phase_begin <= ph && ph < phase_end; };
@@ -390,8 +393,13 @@ extern "C" int crdpn_pointnet_forward_train_phased(
     CRDPN_CUDA(cudaMemsetAsync(c + L.zero_begin, 0, L.zero_end - L.zero_begin, st));
     pn::pn_xmoments_kernel<<<di.sms * 2, 256, 0, st>>>(x, (int)B, (int)P, xmom);
     CRDPN_LAUNCH_CHECK("pn_xmoments_kernel");
-    pn::pn_pack_train_kernel<<<di.sms, 256, 0, st>>>(conv2_w, conv3_w, bn3_w, (int)F, c + L.packed);
-    CRDPN_LAUNCH_CHECK("pn_pack_train_kernel");
+    if (bf16_recipe) {
+      pn::pn_pack_train_kernel<<<di.sms, 256, 0, st>>>(conv2_w, conv3_w, bn3_w, (int)F, c + L.packed);
+      CRDPN_LAUNCH_CHECK("pn_pack_train_kernel");
+    } else {
+      rc = pn::split_pack(conv2_w, conv3_w, bn3_w, (int)F, c + L.packed, di.sms, st);
+      if (rc) return rc;
+    }
   }
   pn::Fold1Params f1{conv1_w, conv1_b, bn1_w, bn1_b, bn1_mean, bn1_var, (long long*)bn1_nbt, (long long*)bn2_nbt,
                      (long long*)bn3_nbt, xmom, M, bn_eps, bn_momentum, stats, train_par, (double*)(c + L.xstat)};
@@ -403,7 +411,10 @@ extern "C" int crdpn_pointnet_forward_train_phased(
   const int tiles_per_cloud = (int)((P + pn::kUnitPts - 1) / pn::kUnitPts);
   const int total_units = (int)B * tiles_per_cloud;
   const int grid = total_units < di.sms ? total_units : di.sms;
-  if (on(1)) {
+  if (on(1) && !bf16_recipe) {
+    rc = pn::split_stats2(x, (int)B, (int)P, c + L.packed, train_par, sum2, sq2, di.sms, st);
+    if (rc) return rc;
+  } else if (on(1)) {
     static bool attr_set[64] = {false};
     if (!attr_set[device]) {
       CRDPN_CUDA(cudaFuncSetAttribute(pn::pn_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn::kS2Smem));
@@ -426,13 +437,17 @@ extern "C" int crdpn_pointnet_forward_train_phased(
   fp.tiles_per_cloud = tiles_per_cloud;
   fp.total_units = total_units;
   fp.dbg = nullptr;
-  fp.flags = variant & ~(4 | 8);
+  fp.flags = variant & ~(4 | 8 | 16);
   fp.train_par = train_par;
   fp.h2img = c + L.h2img;
   fp.enc64 = (unsigned long long*)(c + L.enc64);
   fp.sum3 = sum3;
   fp.sq3 = sq3;
-  if (on(2)) {
+  if (on(2) && !bf16_recipe) {
+    rc = pn::split_forward(x, (int)B, (int)P, (int)F, c + L.packed, train_par, c + L.h2img, (unsigned long long*)(c + L.enc64),
+                           sum3, sq3, di.sms, st);
+    if (rc) return rc;
+  } else if (on(2)) {
     rc = pn::launch_fwd(fp, grid, st);
     if (rc) return rc;
   }

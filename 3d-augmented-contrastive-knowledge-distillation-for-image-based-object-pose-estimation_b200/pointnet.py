@@ -16,6 +16,9 @@ forward(shapes[B,3,P] float32) -> [B, feature_dim] float32.
   (``crdpn_pointnet_forward_train``: analytic BN1 statistics, a tensor-core statistics pass for BN2, the fused
   kernel with BN3's statistics / max / arg-max in the epilogue) and its backward (``crdpn_pointnet_backward``),
   wired into autograd for the 12 parameters; running statistics are updated in place like ``nn.BatchNorm1d``.
+  ``train_precision = "fp32"`` (default) evaluates every tensor-core product as three fp16 hi/lo MMAs so that the
+  arg-max points and ReLU gates that route the gradients are those of the fp32 reference; ``"bf16"`` is the
+  single-MMA recipe (features within 1e-2, gradients re-routed at near-ties).
 
 No CPU fallback: inputs must be CUDA tensors.
 """
@@ -44,6 +47,10 @@ class ShapeEncoderPC(nn.Module):
         self.bn3 = torch.nn.BatchNorm1d(feature_dim)
         self.feature_dim = feature_dim
         self.variant = 0
+        # train-mode arithmetic: "fp32" = every tensor-core product as three fp16 hi/lo MMAs (conv outputs within ~2e-7
+        # of an fp32 run, so arg-max points and ReLU gates -- hence the parameter gradients -- are the reference's);
+        # "bf16" = one bf16 MMA per product (features within 1e-2, faster, gradients re-routed at near-ties)
+        self.train_precision = "fp32"
         self._sync = None   # (process group, world size) once sync_batchnorm() is called
         self._packed = None
         self._packed_key = None
@@ -137,6 +144,8 @@ class ShapeEncoderPC(nn.Module):
         for bn in (self.bn1, self.bn2, self.bn3):
             if bn.momentum is None or not bn.track_running_stats or not bn.affine:
                 raise RuntimeError("ShapeEncoderPC train mode expects nn.BatchNorm1d defaults (momentum, running stats, affine)")
+        if self.train_precision not in ("fp32", "bf16"):
+            raise RuntimeError("ShapeEncoderPC.train_precision must be 'fp32' or 'bf16'")
         return _PointNetTrainFunction.apply(self, shapes, *self._train_params()).view(-1, self.feature_dim)
 
 
@@ -195,19 +204,20 @@ class _PointNetTrainFunction(torch.autograd.Function):
             args += [p[6 + 2 * i].data_ptr(), p[7 + 2 * i].data_ptr(), bn.running_mean.data_ptr(),
                      bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr()]
         sync = module._sync
+        variant = (module.variant & ~16) | (16 if module.train_precision == "bf16" else 0)
         total = B * P
         if sync is not None:
             total = _global_points(B * P, dev, sync[0])
         with _native.on_device(dev):
             if sync is None:
                 rc = lib.crdpn_pointnet_forward_train(*args, float(module.bn1.eps), float(module.bn1.momentum),
-                                                      out.data_ptr(), cptr, n.value, module.variant,
+                                                      out.data_ptr(), cptr, n.value, variant,
                                                       _native.stream_ptr(dev))
                 _native.check(rc, "crdpn_pointnet_forward_train")
             else:
                 for ph in range(4):
                     rc = lib.crdpn_pointnet_forward_train_phased(*args, float(module.bn1.eps), float(module.bn1.momentum),
-                                                                 out.data_ptr(), cptr, n.value, module.variant, ph, ph + 1,
+                                                                 out.data_ptr(), cptr, n.value, variant, ph, ph + 1,
                                                                  total, _native.stream_ptr(dev))
                     _native.check(rc, "crdpn_pointnet_forward_train_phased")
                     if ph < 3:

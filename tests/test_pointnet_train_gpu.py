@@ -1,14 +1,16 @@
 """GPU parity tests of the train-mode PointNet encoder (batch-statistics BatchNorm forward + backward) against
 the oracle pinned to the reference's ShapeEncoderPC (auxiliary/model.py:154-180; training.py:30,47,75).
 
-Tolerances (north_star: 1e-2 relative for the bf16 tensor-core path):
-  * features and running statistics vs the fp reference / golden vectors: <= 1e-2 (measured ~3e-3 / 4e-4)
-  * parameter gradients vs the exact gradient of the SAME bf16 recipe (oracle forward_train_bf16_emulated, fp64
-    arithmetic, straight-through rounding): <= 1e-2 norm-relative on average over the tensors (measured 3e-3 ..
-    6e-3), <= 2e-2 for any single tensor
-  * parameter gradients vs the fp reference: reported, bounded loosely -- bf16 rounding flips near-tied arg-max
-    points and ReLU gates, which re-routes gradients discontinuously (tests/test_oracle_pointnet.py shows the same
-    deviation for the CPU fp64 emulation, and that it vanishes when the routing is forced to agree)."""
+Default train precision ("fp32": every tensor-core product as three fp16 hi/lo MMAs, csrc/pointnet_train_split.cu):
+  * features vs the fp reference / golden vectors: <= 1e-4 (north_star's fp32 bar; measured ~3e-7)
+  * running statistics: <= 1e-5
+  * EVERY parameter gradient vs the reference's own golden gradients / the fp oracle: <= 1e-2 norm-relative
+    (north_star's bf16 bar: the backward GEMMs run on bf16 operands; the ROUTING -- arg-max points, ReLU gates -- is
+    the fp32 one, which is what the 12-18 % deviation of round 1 came from)
+``train_precision = "bf16"`` (round 1's recipe, one MMA per product, ~1.3x faster):
+  * features / statistics <= 1e-2 / 2e-3; gradients vs the exact gradient of the SAME bf16 recipe (oracle
+    forward_train_bf16_emulated) <= 1e-2 on average; vs the fp reference they deviate by the routing effect
+    (tests/test_oracle_pointnet.py) and are only loosely bounded."""
 from pathlib import Path
 
 import numpy as np
@@ -32,9 +34,10 @@ def _maxrel(got, want):
     return ((got - want).abs().max() / want.abs().max()).item()
 
 
-def _encoder(pkg, st, F, dev):
+def _encoder(pkg, st, F, dev, precision="fp32"):
     enc = pkg.ShapeEncoderPC(F)
     enc.load_state_dict({k: v.clone() for k, v in st.items()})
+    enc.train_precision = precision
     return enc.to(dev).train()
 
 
@@ -47,23 +50,26 @@ def _oracle(fn, x, st, gout, dtype=torch.float64):
     return out.detach(), {k: v.grad for k, v in p.items() if getattr(v, "grad", None) is not None}, ns
 
 
-def test_train_golden_vector_from_reference(pkg, cuda):
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_golden_vector_from_reference(pkg, cuda, precision):
     g = np.load(GOLD)
     st = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
-    enc = _encoder(pkg, st, 1024, cuda)
+    enc = _encoder(pkg, st, 1024, cuda, precision)
+    fp32 = precision == "fp32"
     x, gout = torch.from_numpy(g["x"]), torch.from_numpy(g["gout"])
     out = enc(x.to(cuda))
     (out * gout.to(cuda)).sum().backward()
     assert out.shape == (3, 1024) and out.dtype == torch.float32
-    assert _maxrel(out, torch.from_numpy(g["train_out"])) < TOL           # reference module's own train output
+    assert _maxrel(out, torch.from_numpy(g["train_out"])) < (1e-4 if fp32 else TOL)   # reference module's own train output
     for n in (1, 2, 3):
         bn = getattr(enc, f"bn{n}")
-        tol = 1e-5 if n == 1 else 2e-3   # BN1 statistics are analytic in fp64; BN2/BN3 come from the bf16 pipeline
+        tol = 1e-5 if (n == 1 or fp32) else 2e-3   # BN1 statistics are analytic in fp64; BN2/BN3 come from the MMA pipeline
         assert _nrel(bn.running_mean, torch.from_numpy(g[f"after/bn{n}.running_mean"])) < tol
         assert _nrel(bn.running_var, torch.from_numpy(g[f"after/bn{n}.running_var"])) < tol
         assert int(bn.num_batches_tracked) == int(g[f"after/bn{n}.num_batches_tracked"]) == 1
-    # gradients vs the reference's own: BN3's are smooth in the features -> tight; the rest is routed through
-    # arg-max points / ReLU gates that bf16 rounding flips (see module docstring) -> loose bound, values printed
+    # gradients vs the reference's own golden gradients.  fp32 precision: every tensor within north_star's 1e-2.
+    # bf16 recipe: BN3's are smooth in the features -> tight; the rest is routed through arg-max points / ReLU gates
+    # that bf16 rounding flips (see module docstring) -> loose bound, values printed
     dev = {}
     for name, prm in enc.named_parameters():
         ref = torch.from_numpy(g["grad/" + name])
@@ -71,13 +77,41 @@ def test_train_golden_vector_from_reference(pkg, cuda):
             assert prm.grad.abs().max().item() == 0.0   # exactly zero: the batch mean removes the bias
             continue
         dev[name] = _nrel(prm.grad, ref)
-    print("gradient deviation vs fp32 reference:", {k: round(v, 4) for k, v in dev.items()})
+    print(f"gradient deviation vs fp32 reference ({precision}):", {k: round(v, 5) for k, v in dev.items()})
     assert dev["bn3.bias"] < 1e-5 and dev["bn3.weight"] < TOL
-    assert max(dev.values()) < 0.3
+    assert max(dev.values()) < (TOL if fp32 else 0.3), dev
 
 
 @pytest.mark.parametrize("B,P,F", [(1, 64, 128), (2, 50, 128), (3, 333, 1024), (2, 128, 256), (5, 257, 512),
                                     (4, 1000, 256), (149, 40, 128), (8, 2500, 1024)])
+def test_train_forward_backward_vs_fp_oracle(pkg, cuda, B, P, F):
+    """Default (fp32-accurate) train path against the fp oracle pinned to the reference: features 1e-4, running
+    statistics 1e-5, EVERY parameter gradient 1e-2."""
+    st = po.random_state(F, seed=B * 13 + P)
+    x = po.random_clouds(B, P, seed=P + 1)
+    gout = torch.randn(B, F, generator=torch.Generator().manual_seed(F + B))
+    dtype = torch.float64 if B * P * F < 4e6 else torch.float32
+    want, gwant, ns = _oracle(lambda a, p, ns: po.forward(a, p, training=True, new_stats=ns, dtype=dtype), x, st, gout, dtype)
+    enc = _encoder(pkg, st, F, cuda)
+    out = enc(x.to(cuda))
+    (out * gout.to(cuda)).sum().backward()
+    assert out.shape == (B, F)
+    assert _maxrel(out, want) < 1e-4
+    for n in (1, 2, 3):
+        bn = getattr(enc, f"bn{n}")
+        assert _nrel(bn.running_mean, ns[f"bn{n}.running_mean"]) < 1e-5
+        assert _nrel(bn.running_var, ns[f"bn{n}.running_var"]) < 1e-5
+    errs = {}
+    for name, prm in enc.named_parameters():
+        if "conv" in name and name.endswith("bias"):
+            assert prm.grad.abs().max().item() == 0.0
+            continue
+        errs[name] = _nrel(prm.grad, gwant[name])
+    print("gradient deviation vs fp oracle:", {k: round(v, 5) for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+
+
+@pytest.mark.parametrize("B,P,F", [(1, 64, 128), (3, 333, 1024), (5, 257, 512), (149, 40, 128), (8, 2500, 1024)])
 def test_train_forward_backward_vs_bf16_recipe_oracle(pkg, cuda, B, P, F):
     st = po.random_state(F, seed=B * 13 + P)
     x = po.random_clouds(B, P, seed=P + 1)
@@ -85,7 +119,7 @@ def test_train_forward_backward_vs_bf16_recipe_oracle(pkg, cuda, B, P, F):
     dtype = torch.float64 if B * P * F < 4e6 else torch.float32
     want, gwant, ns = _oracle(lambda a, p, ns: po.forward(a, p, training=True, new_stats=ns, dtype=dtype), x, st, gout, dtype)
     ewant, gemu, _ = _oracle(lambda a, p, ns: po.forward_train_bf16_emulated(a, p, dtype=dtype), x, st, gout, dtype)
-    enc = _encoder(pkg, st, F, cuda)
+    enc = _encoder(pkg, st, F, cuda, "bf16")
     out = enc(x.to(cuda))
     (out * gout.to(cuda)).sum().backward()
     assert out.shape == (B, F)
@@ -154,14 +188,40 @@ def test_train_mode_contract(pkg, cuda):
     assert _maxrel(a, b) < 2e-3
 
 
+def _torch_reference_step(st, x, gout):
+    """The reference's own ops (nn.Conv1d + nn.BatchNorm1d in train mode + max, auxiliary/model.py:174-180) in fp32 on
+    the host, whole batch at once; returns (out, grads, module)."""
+    import torch.nn as nn
+
+    class Enc(nn.Module):
+        def __init__(self, F):
+            super().__init__()
+            self.conv1, self.conv2, self.conv3 = nn.Conv1d(3, 64, 1), nn.Conv1d(64, 128, 1), nn.Conv1d(128, F, 1)
+            self.bn1, self.bn2, self.bn3 = nn.BatchNorm1d(64), nn.BatchNorm1d(128), nn.BatchNorm1d(F)
+
+        def forward(self, s):
+            s = torch.relu(self.bn1(self.conv1(s)))
+            s = torch.relu(self.bn2(self.conv2(s)))
+            s = self.bn3(self.conv3(s))
+            return torch.max(s, 2, keepdim=True)[0].view(s.shape[0], -1)
+
+    m = Enc(st["conv3.weight"].shape[0]).train()
+    m.load_state_dict({k: v.clone() for k, v in st.items()})
+    out = m(x)
+    (out * gout).sum().backward()
+    return out.detach(), {k: p.grad for k, p in m.named_parameters()}, m
+
+
 def test_config2_full_size_train_step(pkg, cuda):
-    """BASELINE configs[1] in train mode: batch 160, 2500 points, 1024 features; forward checked against the fp32
-    oracle on a slice of independent evidence (running statistics of all 400k points) and finiteness of all grads."""
+    """BASELINE configs[1] in train mode at FULL size (batch 160, 2500 points, 1024 features): features, running
+    statistics and EVERY parameter gradient against the same layer stack as the reference (nn.Conv1d / nn.BatchNorm1d /
+    max, fp32, host) run over the whole batch."""
     st = po.random_state(1024, seed=46)
     x = po.random_clouds(160, 2500, seed=46)
+    gout = torch.randn(160, 1024, generator=torch.Generator().manual_seed(7))
     enc = _encoder(pkg, st, 1024, cuda)
     out = enc(x.to(cuda))
-    out.sum().backward()
+    (out * gout.to(cuda)).sum().backward()
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     assert all(torch.isfinite(p.grad).all() for p in enc.parameters())
@@ -173,4 +233,18 @@ def test_config2_full_size_train_step(pkg, cuda):
     assert _nrel(enc.bn1.running_mean, 0.9 * st["bn1.running_mean"].double() + 0.1 * mean) < 1e-5
     assert _nrel(enc.bn1.running_var, 0.9 * st["bn1.running_var"].double() + 0.1 * var) < 1e-5
     # bn3.bias gradient = column sums of grad_out (exact)
-    assert _nrel(enc.bn3.bias.grad, torch.full((1024,), 160.0)) < 1e-6
+    assert _nrel(enc.bn3.bias.grad, gout.sum(0)) < 1e-5
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    want, gwant, ref = _torch_reference_step(st, x, gout)
+    assert _maxrel(out, want) < 1e-4
+    for n in (1, 2, 3):
+        bn, rb = getattr(enc, f"bn{n}"), getattr(ref, f"bn{n}")
+        assert _nrel(bn.running_mean, rb.running_mean) < 1e-4
+        assert _nrel(bn.running_var, rb.running_var) < 1e-4
+    errs = {}
+    for name, prm in enc.named_parameters():
+        if "conv" in name and name.endswith("bias"):
+            continue
+        errs[name] = _nrel(prm.grad, gwant[name])
+    print("full-size gradient deviation vs the fp32 layer stack:", {k: round(v, 5) for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
