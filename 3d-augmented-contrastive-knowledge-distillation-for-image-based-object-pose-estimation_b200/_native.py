@@ -54,6 +54,12 @@ _SIGNATURES = {
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_void_p, c_size_t, c_int, c_void_p]),
+    "crdpn_crd_step_sharded": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p,
+                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                       c_float, c_float, c_float, c_float, c_float, c_float,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_int, c_void_p]),
     "crdpn_crd_loss_backward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_int64] + [c_void_p] * 8),
@@ -86,7 +92,6 @@ _SIGNATURES = {
     "crdpn_crd_out_backward": (c_int, [c_void_p, c_void_p, c_int64, c_int] + [c_void_p] * 8 +
                                [c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                 c_void_p]),
-    "crdpn_umma_tf32_probe": (c_int, [c_void_p] * 7 + [c_int, c_void_p]),
     "crdpn_p2p_buffer_bytes": (c_int, [c_int64, c_int64, c_int, POINTER(c_size_t)]),
     "crdpn_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "crdpn_p2p_free": (c_int, [c_void_p]),
@@ -152,6 +157,20 @@ def lib() -> ctypes.CDLL:
         raise RuntimeError("libcrdpn_b200.so ABI version mismatch")
     _LIB = handle
     return handle
+
+
+_DEV = None
+
+
+def dev_lib() -> ctypes.CDLL:
+    """libcrdpn_b200_dev.so: development probes (include/crdpn_b200_dev.h), used by tests / profiling scripts only."""
+    global _DEV
+    if _DEV is None:
+        lib()   # builds both libraries when needed
+        _DEV = ctypes.CDLL(str(_PKG / "libcrdpn_b200_dev.so"))
+        _DEV.crdpn_umma_tf32_probe.restype = c_int
+        _DEV.crdpn_umma_tf32_probe.argtypes = [c_void_p] * 7 + [c_int, c_void_p]
+    return _DEV
 
 
 def check(rc: int, what: str) -> None:

@@ -14,7 +14,10 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libcrdpn_b200.so"
-SOURCES = ["host.cu", "crd_kernels.cu", "pointnet_kernels.cu", "pointnet_train.cu", "pointnet_backward.cu", "embed_kernels.cu", "p2p_kernels.cu", "crd_loss.cu", "kd_losses.cu", "pointcloud_sampler.cu", "crd_unfused.cu", "umma_tf32_probe.cu", "pointnet_train_split.cu"]
+SOURCES = ["host.cu", "crd_kernels.cu", "pointnet_kernels.cu", "pointnet_train.cu", "pointnet_backward.cu", "embed_kernels.cu", "p2p_kernels.cu", "crd_loss.cu", "kd_losses.cu", "pointcloud_sampler.cu", "crd_unfused.cu", "pointnet_train_split.cu"]
+# development probes (include/crdpn_b200_dev.h): their own library, never linked into the product .so
+DEV_LIB = PKG / "libcrdpn_b200_dev.so"
+DEV_SOURCES = ["umma_tf32_probe.cu", "host.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -37,9 +40,9 @@ def sources() -> list[Path]:
 
 
 def needs_build() -> bool:
-    if not LIB.exists():
+    if not LIB.exists() or not DEV_LIB.exists():
         return True
-    t = LIB.stat().st_mtime
+    t = min(LIB.stat().st_mtime, DEV_LIB.stat().st_mtime)
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "crdpn_b200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
@@ -52,7 +55,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     objs = []
     procs = []
-    for src in sources():
+    names = {s.name for s in sources()}
+    for src in sources() + [CSRC / s for s in DEV_SOURCES if s not in names]:
         obj = objdir / (src.stem + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -67,8 +71,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (objdir / "ptxas.log").write_text("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart"]
-    subprocess.check_call(cmd)
+    dev_objs = [str(objdir / (Path(s).stem + ".o")) for s in DEV_SOURCES]
+    prod_objs = [o for o in objs if Path(o).stem + ".cu" in names]
+    subprocess.check_call([nvcc, "-shared", "-o", str(LIB), *prod_objs, "-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-o", str(DEV_LIB), *dev_objs, "-lcudart"])
     return LIB
 
 

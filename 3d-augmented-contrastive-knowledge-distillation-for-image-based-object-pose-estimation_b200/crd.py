@@ -183,6 +183,9 @@ class _CRDLossFunction(torch.autograd.Function):
         BD = B * D
         Bp = (B + 3) & ~3
         arena = torch.empty(16 + 6 * BD + 2 * Bp, dtype=torch.float32, device=dev)
+        # the 8 result doubles live in their own tensor: the returned loss is a view of it, and it is NOT saved for
+        # backward, so an in-place op on the loss (loss /= accum) cannot invalidate the saved arena
+        result = torch.empty(16, dtype=torch.float32, device=dev)
         base = arena.data_ptr()
         o_pre_s, o_pre_t, o_v1, o_v2, o_g1, o_g2 = (base + 4 * (16 + i * BD) for i in range(6))
         o_inv1 = base + 4 * (16 + 6 * BD)
@@ -223,14 +226,14 @@ class _CRDLossFunction(torch.autograd.Function):
                 B, K1, D, mem.nLem, mem.k_total, mem.row_begin, mem.row_end,
                 hp.T, hp.Z1, hp.Z2, EPS, hp.m, 1.0 - hp.m,
                 o_pre_s, o_pre_t, o_v1, o_v2, o_inv1, o_inv2,
-                base, o_g1, o_g2, ws.data_ptr(), ws.numel(), variant, _stream_ptr(dev))
+                result.data_ptr(), o_g1, o_g2, ws.data_ptr(), ws.numel(), variant, _stream_ptr(dev))
         _native.check(rc, "crdpn_crd_loss_forward")
         if contrast_idx is None:
             smp.offset += B * K1
         ctx.save_for_backward(arena, xs, xt, Wsc, Wtc)
         ctx.need_dx = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         ctx.in_shapes = (f_s.shape, f_t.shape)
-        return arena[12]  # float32(loss_s + loss_t), written by the reduction kernel into result slot 6
+        return result[12]  # float32(loss_s + loss_t), written by the reduction kernel into result slot 6
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -269,8 +272,8 @@ class Embed(nn.Module):
     """flatten -> Linear(dim_in, dim_out) -> L2 normalise.
 
     CUDA float32 inputs run the fused kernels; the module keeps the published sub-module names (``linear``,
-    ``l2norm``) so state_dicts and optimiser parameter groups are unchanged.  Host tensors (only the gloo host-logic
-    tests use them) go through the same two sub-modules in eager mode."""
+    ``l2norm``) so state_dicts and optimiser parameter groups are unchanged.  There is no eager / CPU path: anything
+    but a CUDA float32 input raises (the gloo host-logic tests substitute their own subclass)."""
 
     def __init__(self, dim_in: int = 1024, dim_out: int = 128):
         super().__init__()
@@ -279,9 +282,10 @@ class Embed(nn.Module):
 
     def forward(self, x):
         x = x.view(x.shape[0], -1)
-        if x.is_cuda and x.dtype == torch.float32 and self.linear.weight.dtype == torch.float32:
-            return _EmbedFunction.apply(x, self.linear.weight, self.linear.bias)
-        return self.l2norm(self.linear(x))
+        _require_cuda(x, "Embed input")
+        if x.dtype != torch.float32 or self.linear.weight.dtype != torch.float32:
+            raise RuntimeError("Embed runs in float32 only (input and Linear parameters)")
+        return _EmbedFunction.apply(x, self.linear.weight, self.linear.bias)
 
 
 class ContrastLoss(nn.Module):
@@ -641,10 +645,13 @@ class CRDLoss(nn.Module):
         self.criterion_s = ContrastLoss(opt.n_data)
 
     def forward(self, f_s, f_t, idx, contrast_idx=None):
-        if (type(self.contrast) is ContrastMemory and f_s.is_cuda and f_t.is_cuda and f_s.dtype == torch.float32
-                and f_t.dtype == torch.float32):
+        _require_cuda(f_s, "f_s")
+        _require_cuda(f_t, "f_t")
+        if f_s.dtype != torch.float32 or f_t.dtype != torch.float32:
+            raise RuntimeError("CRDLoss expects float32 features (cast f_s / f_t with .float() under autocast)")
+        if type(self.contrast) is ContrastMemory:
             return _CRDLossFunction.apply(f_s, f_t, self.embed_s.linear.weight, self.embed_s.linear.bias,
                                           self.embed_t.linear.weight, self.embed_t.linear.bias, idx, contrast_idx, self)
-        f_s = self.embed_s(f_s)
+        f_s = self.embed_s(f_s)   # a ContrastMemory subclass brings its own step: the per-op path
         f_t = self.embed_t(f_t)
         return self.contrast.fused_loss(f_s, f_t, idx, contrast_idx)

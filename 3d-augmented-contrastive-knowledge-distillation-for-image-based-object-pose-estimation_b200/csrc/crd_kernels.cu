@@ -22,6 +22,7 @@
 // queue R rows x U steps at a time with all 2*CH*U 128-bit loads of a step group issued before first use.
 #include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
 #include "common.cuh"
+#include "p2p_common.cuh"        // LL exchange words: the all-reduce of the sharded step rides in the reduction kernel
 #include "pointnet_common.cuh"   // tcgen05 / TMEM / mbarrier helpers (crd_tc_stream.cuh)
 
 namespace crdpn {
@@ -66,7 +67,23 @@ struct FinalizeParams {
   double* anchor_part;  // [B][8]
   double* result;       // [8]
   unsigned int* ticket;
+  // row-sharded step (crdpn_crd_step_sharded): the sum over ranks rides in this kernel.  Block b pushes anchor b's
+  // reduced gradient rows and loss partials into slot `rank` of every peer (LL words) and sums the `world` slots of its
+  // own buffer in rank order into `reduced` [grad_v1 | grad_v2 | 8 result words]: no separate all-reduce launch.
+  int xchg;
+  int rank, world;
+  p2p::Peers peers;
+  size_t off_ctl, off_slots, parity_stride, slot_words;
+  long long timeout;
+  float* reduced;
 };
+
+int sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dtype, void* const* peer_bufs_host, int rank,
+                      int world, int64_t Bmax, int64_t Dmax, const int64_t* contrast_idx, int64_t B, int64_t K1, int64_t D,
+                      int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end, float T, float Z1, float Z2,
+                      float eps, float momentum, float one_minus_momentum, float* v1_all, float* v2_all, int64_t* y_all,
+                      float* partial, double* result, float* reduced, void* workspace, size_t workspace_bytes, int variant,
+                      void* stream);
 
 __device__ __forceinline__ uint4 ld16_stream(const void* p) {
   uint4 r;
@@ -330,6 +347,9 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
   __shared__ double s_part[kFinalizeScratch];
   __shared__ long long s_first, s_last;
   __shared__ bool is_last;
+  __shared__ uint32_t s_epoch;
+  if (f.xchg && threadIdx.x == 0)   // advanced by the last block only, i.e. after every block has read it
+    s_epoch = *reinterpret_cast<volatile uint32_t*>(f.peers.buf[f.rank] + f.off_ctl + 8) + 1u;
   const long long P = (long long)f.B * f.K1;
   const long long p0 = (long long)b * f.K1, p1 = p0 + f.K1;
   if (threadIdx.x == 0) {
@@ -384,6 +404,24 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
   for (int col = threadIdx.x; col < ncols + 5; col += kFinalizeThreads) {
     double acc = 0.0;
     for (int q = 0; q < parts; ++q) acc += s_part[q * slot_w + col];  // fixed order -> deterministic
+    if (f.xchg) {
+      const uint32_t e = s_epoch;
+      const size_t par = (size_t)(e & 1u) * f.parity_stride + f.off_slots;
+      const size_t BD = (size_t)f.B * f.D;
+      const size_t word = col < f.D ? (size_t)b * f.D + col
+                        : col < ncols ? BD + (size_t)b * f.D + (col - f.D)
+                                      : 2 * BD + 8 + 8 * (size_t)b + (col - ncols);
+      const uint32_t bits = __float_as_uint((float)acc);
+      for (int r = 0; r < f.world; ++r)
+        p2p::ll_store(f.peers.buf[r] + par + ((size_t)f.rank * f.slot_words + word) * 8, bits, e);
+      const char* mine = f.peers.buf[f.rank] + par;
+      float sum = __uint_as_float(p2p::ll_load(mine + word * 8, e, f.timeout));
+      for (int r = 1; r < f.world; ++r)   // rank order: the same bits on every rank
+        sum += __uint_as_float(p2p::ll_load(mine + ((size_t)r * f.slot_words + word) * 8, e, f.timeout));
+      if (col < ncols) f.reduced[word] = sum;
+      else f.anchor_part[b * 8 + (col - ncols)] = (double)sum;
+      continue;
+    }
     if (col < ncols) {
       if (f.full) {
         if (col < f.D) f.grad_v1[(long long)b * f.D + col] = (float)acc;
@@ -413,9 +451,13 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
       f.result[5] = tot;
       f.result[6] = 0.0;
       reinterpret_cast<float*>(&f.result[6])[0] = (float)tot;
+      if (f.xchg) f.reduced[2 * (size_t)f.B * f.D + 5] = (float)tot;
     } else if (threadIdx.x == 7) {
       f.result[7] = 0.0;
+      if (f.xchg)   // every block of this rank has consumed epoch e: publish it (the next exchange uses e + 1)
+        *reinterpret_cast<volatile uint32_t*>(f.peers.buf[f.rank] + f.off_ctl + 8) = s_epoch;
     }
+    if (f.xchg && threadIdx.x < 5) f.reduced[2 * (size_t)f.B * f.D + threadIdx.x] = (float)f.result[threadIdx.x];
   }
 }
 
@@ -685,7 +727,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
                       int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
                       float T, float Z1, float Z2, float eps, float* out_v1, float* out_v2, double* result,
                       float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes, int variant,
-                      const UpdateParams* upd, void* stream) {
+                      const UpdateParams* upd, void* stream, const FinalizeParams* xchg = nullptr) {
   if (!v1 || !v2 || !contrast_idx || !result || !workspace)
     return fail(CRDPN_E_BADARG, "crdpn_crd_score: null pointer");
   if (B <= 0 || K1 <= 0 || D <= 0 || n_data <= 0 || row_end < row_begin || !(T > 0.f))
@@ -766,6 +808,15 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   fp.B = (int)B; fp.K1 = (int)K1; fp.D = (int)D; fp.full = full ? 1 : 0;
   fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2;
   fp.anchor_part = anchor_part; fp.result = result; fp.ticket = ticket;
+  fp.xchg = 0; fp.rank = 0; fp.world = 1; fp.reduced = nullptr;
+  fp.off_ctl = fp.off_slots = fp.parity_stride = fp.slot_words = 0; fp.timeout = 0;
+  for (int r = 0; r < p2p::kMaxWorld; ++r) fp.peers.buf[r] = nullptr;
+  if (xchg != nullptr) {
+    if (!full) return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: Z1 and Z2 must be frozen");
+    fp.xchg = 1; fp.rank = xchg->rank; fp.world = xchg->world; fp.peers = xchg->peers; fp.reduced = xchg->reduced;
+    fp.off_ctl = xchg->off_ctl; fp.off_slots = xchg->off_slots; fp.parity_stride = xchg->parity_stride;
+    fp.slot_words = xchg->slot_words; fp.timeout = xchg->timeout;
+  }
   if (upd != nullptr && upd->row_end > upd->row_begin) {
     const int ublocks = (int)((2 * B + (kFinalizeThreads / 32) - 1) / (kFinalizeThreads / 32));
     if (bank_dtype == CRDPN_F32)
@@ -1015,6 +1066,69 @@ extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int 
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin, row_end,
                     T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant,
                     &u, stream);
+}
+
+// The row-sharded step (one process per GPU) as one call: all-gather of the anchors over NVLink
+// peer memory -> scoring pass over this rank's shard -> ONE kernel that reduces the per-warp partials, momentum-updates
+// the positive rows this rank owns and sums the gradients / loss partials over the ranks (LL words pushed into every
+// peer's slot, summed in rank order).  3 launches.  The bank-streaming variant keeps its own reduction kernel, so there
+// the sum over ranks is the separate crdpn_p2p_allreduce_f32 launch.
+// everything of the sharded step after the all-gather (shared by crdpn_crd_step_sharded and
+// crdpn_crd_loss_forward_sharded, which may draw in-shard negatives in between)
+int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dtype, void* const* peer_bufs_host,
+                             int rank, int world, int64_t Bmax, int64_t Dmax, const int64_t* contrast_idx, int64_t B,
+                             int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
+                             float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+                             float* v1_all, float* v2_all, int64_t* y_all, float* partial, double* result, float* reduced,
+                             void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  int rc;
+  if (variant & 0x200) {
+    rc = crdpn_crd_step(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, contrast_idx, y_all, B, K1, D, n_data, k_total,
+                        row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, result, partial, partial + B * D,
+                        workspace, workspace_bytes, variant, stream);
+    if (rc) return rc;
+    return crdpn_p2p_allreduce_f32(partial, 2 * B * D, result, 8, reduced, peer_bufs_host, rank, world, Bmax, Dmax, stream);
+  }
+  rc = check_update_args(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, y_all, B, D, row_begin, row_end);
+  if (rc) return rc;
+  const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, y_all, B, D, row_begin,
+                                            row_end, momentum, one_minus_momentum);
+  const p2p::Layout L(Bmax, Dmax, world);
+  FinalizeParams x;
+  x.rank = rank; x.world = world; x.reduced = reduced;
+  for (int r = 0; r < p2p::kMaxWorld; ++r) x.peers.buf[r] = r < world ? (char*)peer_bufs_host[r] : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (!x.peers.buf[r]) return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: null peer buffer");
+  x.off_ctl = L.ctl; x.off_slots = L.slots; x.parity_stride = L.parity_stride; x.slot_words = L.slot_words;
+  x.timeout = p2p::poll_timeout_ticks();
+  // an empty shard still takes part in the exchange: score_impl launches the reduction kernel either way
+  return score_impl(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, contrast_idx, B, K1, D, n_data, k_total, row_begin,
+                    row_end, T, Z1, Z2, eps, nullptr, nullptr, result, partial, partial + B * D, workspace, workspace_bytes,
+                    variant, &u, stream, &x);
+}
+
+extern "C" int crdpn_crd_step_sharded(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+                                      const float* v1_local, const float* v2_local, const int64_t* y_local,
+                                      const int32_t* offs_host, void* const* peer_bufs_host, int rank, int world,
+                                      int64_t Bmax, int64_t Dmax, const int64_t* contrast_idx,
+                                      int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
+                                      int64_t row_begin, int64_t row_end,
+                                      float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+                                      float* v1_all, float* v2_all, int64_t* y_all, float* partial, double* result,
+                                      float* reduced, void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  if (!offs_host || !peer_bufs_host || !v1_all || !v2_all || !y_all || !partial || !result || !reduced)
+    return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: null pointer");
+  if (world < 1 || world > p2p::kMaxWorld || rank < 0 || rank >= world)
+    return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: bad rank / world (world <= 8)");
+  if (!(Z1 > 0.f && Z2 > 0.f)) return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: Z1 and Z2 must be frozen (> 0)");
+  const int64_t B = offs_host[world];
+  if (B <= 0 || B > Bmax || D > Dmax) return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: batch does not fit the exchange buffer");
+  int rc = crdpn_p2p_allgather_anchors(v1_local, v2_local, y_local, D, offs_host, peer_bufs_host, rank, world, Bmax, Dmax,
+                                       v1_all, v2_all, y_all, stream);
+  if (rc) return rc;
+  return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, contrast_idx, B, K1, D,
+                           n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all,
+                           y_all, partial, result, reduced, workspace, workspace_bytes, variant, stream);
 }
 
 extern "C" int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,

@@ -16,6 +16,13 @@ int embed_backward2(const float* xs, int64_t s_dim, const float* Ws, const float
                     const float* xt, int64_t t_dim, const float* Wt, const float* v2, const float* inv2, const float* g2,
                     const float* scale, int64_t B, int64_t D, float* dWs, float* dbs, float* dxs, float* dWt, float* dbt,
                     float* dxt, float* d_pre, void* stream);
+// crd_kernels.cu: scoring pass over the shard + reduction / momentum update / sum over ranks in one kernel
+int sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dtype, void* const* peer_bufs_host, int rank,
+                      int world, int64_t Bmax, int64_t Dmax, const int64_t* contrast_idx, int64_t B, int64_t K1, int64_t D,
+                      int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end, float T, float Z1, float Z2,
+                      float eps, float momentum, float one_minus_momentum, float* v1_all, float* v2_all, int64_t* y_all,
+                      float* partial, double* result, float* reduced, void* workspace, size_t workspace_bytes, int variant,
+                      void* stream);
 }  // namespace crdpn
 
 using namespace crdpn;
@@ -58,7 +65,7 @@ extern "C" int crdpn_crd_loss_backward(
 
 // Row-sharded banks, one process per GPU: local embed heads -> all-gather of the anchors over NVLink peer memory ->
 // (in-shard negative draw) -> scoring pass over this rank's shard + owner-only momentum update -> one-shot all-reduce of
-// the packed partials [grad_v1 | grad_v2 | 8 result scalars].  7 launches, one foreign call.
+// the packed partials [grad_v1 | grad_v2 | 8 result scalars], fused into the step's reduction kernel.  6 launches, one foreign call.
 extern "C" int crdpn_crd_loss_forward_sharded(
     const float* f_s, int64_t s_dim, const float* Ws, const float* bs,
     const float* f_t, int64_t t_dim, const float* Wt, const float* bt,
@@ -90,9 +97,7 @@ extern "C" int crdpn_crd_loss_forward_sharded(
     if (rc) return rc;
     idx = idx_scratch;
   }
-  rc = crdpn_crd_step(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, idx, y_all, B, K1, D, n_data, k_total, row_begin,
-                      row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, result, partial, partial + B * D, workspace,
-                      workspace_bytes, variant, stream);
-  if (rc) return rc;
-  return crdpn_p2p_allreduce_f32(partial, 2 * B * D, result, 8, reduced, peer_bufs_host, rank, world, Bmax, Dmax, stream);
+  return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, idx, B, K1, D, n_data,
+                           k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all, y_all,
+                           partial, result, reduced, workspace, workspace_bytes, variant, stream);
 }

@@ -5,65 +5,42 @@
 //               latency.
 //   exchange 2  all-reduce of the packed partials [grad_v1 | grad_v2 | 8 scalars] (47 KB at B=46, D=128): one-shot
 //               push of the partial into slot `rank` of every peer, then every rank sums the R slots in RANK ORDER
-//               (deterministic, identical bits on every rank) -- one launch.
+//               (deterministic, identical bits on every rank) -- one launch.  (crdpn_crd_step_sharded fuses this
+//               exchange into the step's reduction kernel instead: crd_kernels.cu.)
 // Data and flag share one 8-byte store ("LL" words), so there is no fence and no separate flag round trip.
 // Both payloads are far below the size where ring / tree algorithms pay off, so the cost is pure latency: the
 // NCCL path costs two collective launches (~20-30 us each at 8 GPUs); these kernels cost one peer store + one flag.
 // Epoch counters live in device memory and are advanced by the kernels themselves, so a captured CUDA graph can be
-// replayed without patching arguments.  A wait that lasts ~2 s traps instead of hanging the box.
-//
-// Buffer reuse is safe without double buffering because the steps of a rank are stream-ordered and every exchange
-// depends on data from all ranks: a peer can only push epoch e+1 after it has consumed this rank's epoch-e data.
+// replayed without patching arguments.  Payload areas are double-buffered by epoch parity (p2p_common.cuh), so any call
+// sequence is safe as long as every rank issues the same one; a poll that lasts longer than the (configurable,
+// default ten minutes) time-out traps instead of hanging the box.
+#include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "p2p_common.cuh"
 
 namespace crdpn {
 namespace p2p {
 
-constexpr int kMaxWorld = 8;
-struct Peers { char* buf[kMaxWorld]; };
-struct Offs { int off[kMaxWorld + 1]; };   // anchor offsets per rank (prefix sums of the per-rank batch sizes)
-
-// layout of one rank's exchange buffer.  Payload areas hold 8-byte "LL" words {4 bytes of data, 4 bytes of epoch}:
-// data and flag travel in ONE 8-byte store, so the receiver needs no fence and no separate flag -- it polls each
-// word until its epoch matches (the protocol NCCL uses for small messages).
-struct Layout {
-  size_t ctl, v1, v2, y, slots, total;
-  __host__ __device__ Layout(int64_t Bmax, int64_t Dmax, int world) {
-    size_t o = 0;
-    ctl = o; o += 64 * 4;        // [0] epoch of the gathers, [1] ticket, [2] epoch of the reductions, [3] ticket
-    v1 = o; o += (size_t)Bmax * Dmax * 8;
-    v2 = o; o += (size_t)Bmax * Dmax * 8;
-    y = o; o += (size_t)Bmax * 2 * 8;
-    o = (o + 255) / 256 * 256;
-    slots = o; o += (size_t)world * (2 * (size_t)Bmax * Dmax + 8) * 8;
-    total = (o + 255) / 256 * 256;
-  }
-};
-
-__device__ __forceinline__ void ll_store(void* p, uint32_t data, uint32_t epoch) {
-  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(epoch) : "memory");
+long long poll_timeout_ticks() {
+  static const long long ticks = [] {
+    const char* s = getenv("CRDPN_P2P_TIMEOUT_S");
+    double sec = s ? atof(s) : 600.0;
+    if (!(sec > 0.0)) sec = 600.0;
+    return (long long)(sec * 2.0e9);   // SM clock <= 2 GHz
+  }();
+  return ticks;
 }
-__device__ __forceinline__ uint32_t ll_load(const void* p, uint32_t epoch) {
-  uint32_t d, f;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(d), "=r"(f) : "l"(p) : "memory");
-    if (f == epoch) break;
-    if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a peer died or the call sequences diverged
-  }
-  return d;
-}
+
 // push `nwords` 4-byte words to LL area `dst` (8 bytes per word) / poll them out of a local LL area
 // part c of CH: the c-th of CH interleaved thread groups (blocks) covering the same word range
 __device__ __forceinline__ void ll_push(char* dst, const void* src, size_t nwords, uint32_t e, int c, int CH) {
   const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
   for (size_t i = (size_t)c * blockDim.x + threadIdx.x; i < nwords; i += (size_t)CH * blockDim.x) ll_store(dst + i * 8, s[i], e);
 }
-__device__ __forceinline__ void ll_pull(void* out, const char* src, size_t nwords, uint32_t e, int c, int CH) {
+__device__ __forceinline__ void ll_pull(void* out, const char* src, size_t nwords, uint32_t e, int c, int CH, long long to) {
   uint32_t* d = reinterpret_cast<uint32_t*>(out);
-  for (size_t i = (size_t)c * blockDim.x + threadIdx.x; i < nwords; i += (size_t)CH * blockDim.x) d[i] = ll_load(src + i * 8, e);
+  for (size_t i = (size_t)c * blockDim.x + threadIdx.x; i < nwords; i += (size_t)CH * blockDim.x) d[i] = ll_load(src + i * 8, e, to);
 }
 constexpr int kCH = 8;   // blocks per peer: the payloads are latency-bound, so spread the words over many threads
 
@@ -73,7 +50,8 @@ struct GatherParams {
   int D, rank, world;
   Offs offs;
   Peers peers;
-  size_t off_ctl, off_v1, off_v2, off_y;
+  size_t off_ctl, off_v1, off_v2, off_y, parity_stride;
+  long long timeout;
   float *out_v1, *out_v2;
   long long* out_y;
 };
@@ -86,8 +64,10 @@ __global__ void __launch_bounds__(256) p2p_allgather_kernel(const GatherParams a
   uint32_t* ctl = reinterpret_cast<uint32_t*>(me + a.off_ctl);
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(ctl) + 1u;   // advanced only after every block has read it
   const int D = a.D;
+  const size_t par = (size_t)(e & 1u) * a.parity_stride;
+  me += par;
   {
-    char* dst = a.peers.buf[p];
+    char* dst = a.peers.buf[p] + par;
     const int a0 = a.offs.off[a.rank], n = a.offs.off[a.rank + 1] - a0;
     ll_push(dst + a.off_v1 + (size_t)a0 * D * 8, a.v1, (size_t)n * D, e, c, kCH);
     ll_push(dst + a.off_v2 + (size_t)a0 * D * 8, a.v2, (size_t)n * D, e, c, kCH);
@@ -95,9 +75,9 @@ __global__ void __launch_bounds__(256) p2p_allgather_kernel(const GatherParams a
   }
   {
     const int p0 = a.offs.off[p], n = a.offs.off[p + 1] - p0;
-    ll_pull(a.out_v1 + (size_t)p0 * D, me + a.off_v1 + (size_t)p0 * D * 8, (size_t)n * D, e, c, kCH);
-    ll_pull(a.out_v2 + (size_t)p0 * D, me + a.off_v2 + (size_t)p0 * D * 8, (size_t)n * D, e, c, kCH);
-    ll_pull(a.out_y + p0, me + a.off_y + (size_t)p0 * 16, (size_t)n * 2, e, c, kCH);
+    ll_pull(a.out_v1 + (size_t)p0 * D, me + a.off_v1 + (size_t)p0 * D * 8, (size_t)n * D, e, c, kCH, a.timeout);
+    ll_pull(a.out_v2 + (size_t)p0 * D, me + a.off_v2 + (size_t)p0 * D * 8, (size_t)n * D, e, c, kCH, a.timeout);
+    ll_pull(a.out_y + p0, me + a.off_y + (size_t)p0 * 16, (size_t)n * 2, e, c, kCH, a.timeout);
   }
   __syncthreads();
   if (tid == 0) {  // the last block of this rank advances the epoch
@@ -112,8 +92,9 @@ struct ReduceParams {
   float* out;
   int n, n_main, rank, world;
   Peers peers;
-  size_t off_ctl, off_slots;
+  size_t off_ctl, off_slots, parity_stride;
   size_t slot_stride;   // words between slots
+  long long timeout;
 };
 
 // grid = world x kCH blocks: blocks (p, *) push the whole partial to peer p's slot `rank`; then block b reduces the
@@ -124,8 +105,9 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const ReduceParams a
   char* me = a.peers.buf[a.rank];
   uint32_t* ctl = reinterpret_cast<uint32_t*>(me + a.off_ctl) + 2;
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(ctl) + 1u;
+  const size_t par = (size_t)(e & 1u) * a.parity_stride;
   {
-    char* dst = a.peers.buf[p] + a.off_slots + (size_t)a.rank * a.slot_stride * 8;
+    char* dst = a.peers.buf[p] + par + a.off_slots + (size_t)a.rank * a.slot_stride * 8;
     for (int i = c * blockDim.x + tid; i < a.n; i += kCH * blockDim.x) {
       const float v = i < a.n_main ? a.partial[i] : (float)a.tail[i - a.n_main];
       ll_store(dst + (size_t)i * 8, __float_as_uint(v), e);
@@ -134,11 +116,11 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const ReduceParams a
   {
     const int nb = a.world * kCH, b = blockIdx.x;
     const int i0 = (int)((long long)a.n * b / nb), i1 = (int)((long long)a.n * (b + 1) / nb);
-    const char* slots = me + a.off_slots;
+    const char* slots = me + par + a.off_slots;
     for (int i = i0 + tid; i < i1; i += blockDim.x) {
-      float s = __uint_as_float(ll_load(slots + (size_t)i * 8, e));
+      float s = __uint_as_float(ll_load(slots + (size_t)i * 8, e, a.timeout));
       for (int r = 1; r < a.world; ++r)   // rank order: the same bits on every rank
-        s += __uint_as_float(ll_load(slots + ((size_t)r * a.slot_stride + i) * 8, e));
+        s += __uint_as_float(ll_load(slots + ((size_t)r * a.slot_stride + i) * 8, e, a.timeout));
       a.out[i] = s;
     }
   }
@@ -215,7 +197,8 @@ extern "C" int crdpn_p2p_allgather_anchors(const float* v1, const float* v2, con
   const p2p::Layout L(Bmax, Dmax, world);
   a.v1 = v1; a.v2 = v2; a.y = (const long long*)y; a.D = (int)D; a.rank = rank; a.world = world;
   for (int r = 0; r <= p2p::kMaxWorld; ++r) a.offs.off[r] = r <= world ? offs_host[r] : offs_host[world];
-  a.off_ctl = L.ctl; a.off_v1 = L.v1; a.off_v2 = L.v2; a.off_y = L.y;
+  a.off_ctl = L.ctl; a.off_v1 = L.v1; a.off_v2 = L.v2; a.off_y = L.y; a.parity_stride = L.parity_stride;
+  a.timeout = p2p::poll_timeout_ticks();
   a.out_v1 = out_v1; a.out_v2 = out_v2; a.out_y = (long long*)out_y;
   p2p::p2p_allgather_kernel<<<world * p2p::kCH, 256, 0, (cudaStream_t)stream>>>(a);
   CRDPN_LAUNCH_CHECK("p2p_allgather_kernel");
@@ -230,11 +213,12 @@ extern "C" int crdpn_p2p_allreduce_f32(const float* partial, int64_t n_main, con
   p2p::ReduceParams a;
   int rc = fill_peers(peer_bufs_host, rank, world, &a.peers);
   if (rc) return rc;
-  const size_t stride = 2 * (size_t)Bmax * Dmax + 8;
-  if (n <= 0 || (size_t)n > stride) return fail(CRDPN_E_BADARG, "crdpn_p2p_allreduce_f32: payload does not fit the exchange buffer");
   const p2p::Layout L(Bmax, Dmax, world);
+  const size_t stride = L.slot_words;
+  if (n <= 0 || (size_t)n > stride) return fail(CRDPN_E_BADARG, "crdpn_p2p_allreduce_f32: payload does not fit the exchange buffer");
   a.partial = partial; a.tail = tail_f64; a.out = out; a.n = (int)n; a.n_main = (int)n_main; a.rank = rank; a.world = world;
-  a.off_ctl = L.ctl; a.off_slots = L.slots; a.slot_stride = stride;
+  a.off_ctl = L.ctl; a.off_slots = L.slots; a.slot_stride = stride; a.parity_stride = L.parity_stride;
+  a.timeout = p2p::poll_timeout_ticks();
   p2p::p2p_allreduce_kernel<<<world * p2p::kCH, 256, 0, (cudaStream_t)stream>>>(a);
   CRDPN_LAUNCH_CHECK("p2p_allreduce_kernel");
   return CRDPN_OK;

@@ -28,21 +28,6 @@ constexpr uint32_t kNumBars = 32;
 constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16;
 constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;           // slack for manual 1024-byte alignment
 
-namespace v1 {
-enum Bar : int {
-  W3_FULL = 0,   // [3]
-  W3_EMPTY = 3,  // [3]
-  H1_FULL = 6,   // [2]
-  H1_EMPTY = 8,  // [2]
-  A2_FULL = 10,  // [2]
-  A2_EMPTY = 12, // [2]
-  H2_FULL = 14,  // [2]
-  H2_EMPTY = 16, // [2]
-  A3_FULL = 18,  // [2]
-  A3_EMPTY = 20, // [2]
-  W2_FULL = 22   // [1]
-};
-}  // namespace v1
 
 // packed parameter buffer (global), produced by pointnet_pack_kernel
 __host__ __device__ inline size_t packed_off_w3() { return kW2Bytes; }

@@ -4,7 +4,7 @@
 //   layer 1 (3->64,  0.07% of FLOPs)  CUDA cores, fp32 in, BN1 folded, ReLU, bf16 out -> smem (UMMA operand)
 //   layer 2 (64->128, 6%)             tcgen05.mma, M = 128 points, N = 128 channels, K = 64; epilogue adds the
 //                                     folded bias, ReLU, bf16 -> smem as the K-major B operand of layer 3
-//   layer 3 (128->F, 94%)             tcgen05.mma "swap-AB": M = 128 channels (one W3 slab), N = 128 points,
+//   layer 3 (128->F, 94%)             tcgen05.mma "swap-AB": M = 128 channels (one W3 slab), N = 256 points,
 //                                     K = 128; accumulator lanes are channels, so the max over points is a
 //                                     per-thread reduction over TMEM columns; BN3 (scale folded into W3, shift
 //                                     added after the max) commutes with the max because max(a*y) with the sign
@@ -17,298 +17,14 @@
 // one per SM (persistent CTAs).  Each W3 slab (128 channels x 128 k, 32 KB bf16, pre-swizzled image in global
 // memory, L2 resident) is streamed by 1-D bulk async copies through a 3-stage ring and used for both halves.
 //
-// Warp roles (512 threads): w0 bulk-copy producer | w1 MMA issuer | w2 TMEM allocator | w3 idle
-//                           w4-7   layer-3 epilogue A (accumulator ring slot 0 = first half of each unit)
-//                           w8-11  front end (layer 1 on CUDA cores, layer-2 epilogue)
-//                           w12-15 layer-3 epilogue B (ring slot 1 = second half)
-// The layer-2 MMAs of unit u+1 are issued before the last W3 slab of unit u, and h2 is released per half, so
-// the layer-2 epilogue of the next unit overlaps the tail of layer 3 instead of stalling the tensor pipe.
-// TMEM (512 columns): [0,256) two layer-3 accumulators (ring), [256,512) layer-2 accumulators (one per half).
+// Warp roles, TMEM plan and the job pipeline: see pointnet_fwd_kernel_v2 below (the first version, N = 128 MMAs with
+// one epilogue group per half, was limited by the 128 B/clk shared-memory port and has been removed: git history).
 
 #include "pointnet_common.cuh"
 
 namespace crdpn {
 namespace pn {
 
-
-// ---------------------------------------------------------------------------------------------------------
-template <int NSLAB>
-__global__ void __launch_bounds__(kThreads, 1) pointnet_fwd_eval_kernel(const FwdParams p) {
-  using namespace v1;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t bar0 = base + kOffBar;
-  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kOffBar + kNumBars * 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = gridDim.x;
-  const int u_begin = (int)(((long long)p.total_units * blockIdx.x) / G);
-  const int u_end = (int)(((long long)p.total_units * (blockIdx.x + 1)) / G);
-  const int NU = u_end - u_begin;
-  const int rot = (p.flags & 1) ? (int)(blockIdx.x % NSLAB) : 0;  // CTAs walk the W3 slabs out of phase
-
-  // ---- one-time setup ----
-  {
-    const float* par = reinterpret_cast<const float*>(p.packed + packed_off_par(p.F));
-    float* spar = reinterpret_cast<float*>(sm + kOffPar);
-    for (int i = threadIdx.x; i < (int)(kParBytes / 4); i += kThreads) spar[i] = par[i];
-  }
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar(W3_FULL + i), 1); mbar_init(bar(W3_EMPTY + i), 1); }
-    for (int h = 0; h < 2; ++h) {
-      mbar_init(bar(H1_FULL + h), kHalfPts); mbar_init(bar(H1_EMPTY + h), 1);
-      mbar_init(bar(A2_FULL + h), 1);        mbar_init(bar(A2_EMPTY + h), kHalfPts);
-      mbar_init(bar(H2_FULL + h), kHalfPts); mbar_init(bar(H2_EMPTY + h), 1);
-      mbar_init(bar(A3_FULL + h), 1);        mbar_init(bar(A3_EMPTY + h), kHalfPts);
-    }
-    mbar_init(bar(W2_FULL), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    // =========================== bulk-copy producer ===========================
-    if (lane == 0 && NU > 0) {
-      long long dw_p = 0;
-      mbar_expect_tx(bar(W2_FULL), kW2Bytes);
-      bulk_g2s(base + kOffW2, p.packed, kW2Bytes, bar(W2_FULL));
-      const char* w3 = p.packed + packed_off_w3();
-      uint32_t n = 0;
-      for (int u = 0; u < NU; ++u) {
-        for (int s = 0; s < NSLAB; ++s, ++n) {
-          const uint32_t stage = n % kStages, use = n / kStages;
-          mbar_wait_t(bar(W3_EMPTY + stage), (use & 1u) ^ 1u, dw_p);
-          if ((p.flags & 2) && n >= kStages) { mbar_arrive(bar(W3_FULL + stage)); continue; }
-          mbar_expect_tx(bar(W3_FULL + stage), kSlabBytes);
-          const uint32_t dst = base + kOffW3 + stage * kSlabBytes;
-          const char* src = w3 + (size_t)((s + rot) % NSLAB) * kSlabBytes;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) bulk_g2s(dst + c * 8192u, src + c * 8192, 8192u, bar(W3_FULL + stage));
-        }
-      }
-      if (p.dbg) p.dbg[blockIdx.x * 32 + 6] = dw_p;
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer (whole warp converged; one elected lane issues) ==============
-    if (NU > 0) {
-      long long dw[8] = {0};
-      const long long t_role = clock64();
-      mbar_wait(bar(W2_FULL), 0);
-      const uint32_t w2_lo = base + kOffW2;
-      uint32_t slab_n = 0;
-      // layer 2 of unit u: D2[point][channel] = h1[point][k] * W2'[channel][k]^T  (acc2[h] <- 4 MMAs, K = 64)
-      auto issue_layer2 = [&](int u) {
-        const uint32_t uph = (uint32_t)u & 1u;
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait_t(bar(H1_FULL + h), uph, dw[0]);
-          mbar_wait_t(bar(A2_EMPTY + h), uph ^ 1u, dw[1]);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t a_desc = umma_desc_sw128(base + kOffH1 + h * kKBlockBytes);
-            const uint64_t w2_desc = umma_desc_sw128(w2_lo);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem + 256u + 128u * h, a_desc + 2u * k, w2_desc + 2u * k, k > 0);
-            umma_commit(bar(A2_FULL + h));
-            umma_commit(bar(H1_EMPTY + h));
-          }
-          __syncwarp();
-        }
-      };
-      issue_layer2(0);
-      for (int u = 0; u < NU; ++u) {
-        const uint32_t uph = (uint32_t)u & 1u;
-        // layer 3: D3[channel][point] = W3'[channel][k] * h2[point][k]^T, slab by slab, both halves per slab;
-        // half h always lands in accumulator ring slot h (epilogue group h drains it)
-        for (int s = 0; s < NSLAB; ++s, ++slab_n) {
-          if (s == NSLAB - 1 && u + 1 < NU) issue_layer2(u + 1);  // its epilogue overlaps the last slab below
-          const uint32_t stage = slab_n % kStages;
-          mbar_wait_t(bar(W3_FULL + stage), (slab_n / kStages) & 1u, dw[2]);
-          const uint32_t use = (uint32_t)u * NSLAB + (uint32_t)s;  // per-slot use counter
-          for (int h = 0; h < 2; ++h) {
-            if (s == 0) mbar_wait_t(bar(H2_FULL + h), uph, dw[3]);
-            mbar_wait_t(bar(A3_EMPTY + h), (use & 1u) ^ 1u, dw[4]);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t a0 = umma_desc_sw128(base + kOffW3 + stage * kSlabBytes);
-              const uint64_t b0 = umma_desc_sw128(base + kOffH2 + h * kSlabBytes);
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {
-                const uint32_t koff = (uint32_t)(kk >> 2) * (kKBlockBytes >> 4) + (uint32_t)(kk & 3) * 2u;
-                umma_bf16(tmem + 128u * h, a0 + koff, b0 + koff, kk > 0);
-              }
-              umma_commit(bar(A3_FULL + h));
-              if (s == NSLAB - 1) umma_commit(bar(H2_EMPTY + h));  // this half of h2 may be overwritten
-              if (h == 1) umma_commit(bar(W3_EMPTY + stage));
-            }
-            __syncwarp();
-          }
-        }
-      }
-      // commits retire in order: once the last one has landed no asynchronous arrive can hit this CTA's
-      // shared memory after it exits
-      const uint32_t last = slab_n - 1u;  // W3_EMPTY of the last slab is the very last commit
-      mbar_wait(bar(W3_EMPTY + last % kStages), (last / kStages) & 1u);
-      if (p.dbg && lane == 0) {
-        for (int i = 0; i < 5; ++i) p.dbg[blockIdx.x * 32 + i] = dw[i];
-        p.dbg[blockIdx.x * 32 + 5] = clock64() - t_role;
-      }
-    }
-  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
-    // =========================== layer-3 epilogue: running max over points ===========================
-    // group h (warps 4-7: h = 0, warps 12-15: h = 1) drains accumulator ring slot h
-    const int q = warp & 3;
-    const int h = warp >= 12 ? 1 : 0;
-    float rmax[NSLAB];
-#pragma unroll
-    for (int s = 0; s < NSLAB; ++s) rmax[s] = -INFINITY;
-    int cur_cloud = -1;
-    uint32_t use = 0;
-    long long dwait = 0;
-    const long long t_role = clock64();
-    auto flush = [&](int cloud) {
-#pragma unroll
-      for (int s = 0; s < NSLAB; ++s) {
-        atomicMax(p.enc + (size_t)cloud * p.F + ((s + rot) % NSLAB) * 128 + q * 32 + lane, enc_ordered(rmax[s]));
-        rmax[s] = -INFINITY;
-      }
-    };
-    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 128u * h;
-    for (int u = 0; u < NU; ++u) {
-      const int cloud = (u_begin + u) / p.tiles_per_cloud;
-      if (cloud != cur_cloud) {
-        if (cur_cloud >= 0) flush(cur_cloud);
-        cur_cloud = cloud;
-      }
-#pragma unroll
-      for (int s = 0; s < NSLAB; ++s, ++use) {
-        mbar_wait_t(bar(A3_FULL + h), use & 1u, dwait);
-        tc_fence_after();
-        float m0 = rmax[s], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four independent chains
-#pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + 32u * c, r0);
-          tmem_ld32(taddr + 32u * (c + 1), r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            m0 = max3(m0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
-            m1 = max3(m1, __uint_as_float(r0[16 + i]), __uint_as_float(r0[17 + i]));
-            m2 = max3(m2, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
-            m3 = max3(m3, __uint_as_float(r1[16 + i]), __uint_as_float(r1[17 + i]));
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(bar(A3_EMPTY + h));
-        rmax[s] = fmaxf(max3(m0, m1, m2), m3);
-      }
-    }
-    if (cur_cloud >= 0) flush(cur_cloud);
-    if (p.dbg && q == 0 && lane == 0) {
-      p.dbg[blockIdx.x * 32 + 8 + 2 * h] = dwait;
-      p.dbg[blockIdx.x * 32 + 9 + 2 * h] = clock64() - t_role;
-    }
-  } else if (warp >= 8 && warp < 12) {
-    // =========================== front end: layer 1 + layer-2 epilogue ===========================
-    const int t = threadIdx.x - 256;  // point row inside a half; also the TMEM lane
-    const int q = warp & 3;
-    const float4* w1p = reinterpret_cast<const float4*>(sm + kOffPar);
-    const float4* b2f = reinterpret_cast<const float4*>(sm + kOffPar + 64 * 16);
-    long long dw[8] = {0};
-    const long long t_role = clock64();
-
-    auto layer1 = [&](int u) {
-      const int unit = u_begin + u;
-      const int cloud = unit / p.tiles_per_cloud;
-      const int p_base = (unit - cloud * p.tiles_per_cloud) * kUnitPts;
-      const uint32_t uph = (uint32_t)u & 1u;
-      const float* xc = p.x + (size_t)cloud * 3 * p.P;
-      for (int h = 0; h < 2; ++h) {
-        int pt = p_base + h * kHalfPts + t;
-        pt = pt < p.P ? pt : p.P - 1;  // ragged tail: repeat the last real point (max is idempotent)
-        const float x0 = __ldg(xc + pt), x1 = __ldg(xc + p.P + pt), x2 = __ldg(xc + 2 * p.P + pt);
-        mbar_wait_t(bar(H1_EMPTY + h), uph ^ 1u, dw[0]);
-        const long long t_l1 = clock64();
-        uint8_t* dst = sm + kOffH1 + h * kKBlockBytes;
-#pragma unroll
-        for (int cg = 0; cg < 8; ++cg) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w = w1p[cg * 8 + j];
-            v[j] = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
-          }
-          uint4 o;
-          o.x = pack_relu_bf16(v[0], v[1]); o.y = pack_relu_bf16(v[2], v[3]);
-          o.z = pack_relu_bf16(v[4], v[5]); o.w = pack_relu_bf16(v[6], v[7]);
-          *reinterpret_cast<uint4*>(dst + sw128_off(t, cg * 8)) = o;
-        }
-        fence_proxy_async();
-        mbar_arrive(bar(H1_FULL + h));
-        dw[4] += clock64() - t_l1;
-      }
-    };
-
-    if (NU > 0) layer1(0);
-    for (int u = 0; u < NU; ++u) {
-      const uint32_t uph = (uint32_t)u & 1u;
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait_t(bar(A2_FULL + h), uph, dw[1]);
-        mbar_wait_t(bar(H2_EMPTY + h), uph ^ 1u, dw[2]);  // layer 3 of the previous unit has finished reading this half
-        const long long t_e2 = clock64();
-        tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u + 128u * h;
-        uint8_t* dst = sm + kOffH2 + h * kSlabBytes;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {  // 32 channels per TMEM load
-          uint32_t r[32];
-          tmem_ld32(taddr + 32u * c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const int ch = c * 32 + g8 * 8;
-            const float4 ba = b2f[ch / 4], bb = b2f[ch / 4 + 1];
-            uint4 o;
-            o.x = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 0]) + ba.x, __uint_as_float(r[g8 * 8 + 1]) + ba.y);
-            o.y = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 2]) + ba.z, __uint_as_float(r[g8 * 8 + 3]) + ba.w);
-            o.z = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 4]) + bb.x, __uint_as_float(r[g8 * 8 + 5]) + bb.y);
-            o.w = pack_relu_bf16(__uint_as_float(r[g8 * 8 + 6]) + bb.z, __uint_as_float(r[g8 * 8 + 7]) + bb.w);
-            *reinterpret_cast<uint4*>(dst + (ch >> 6) * kKBlockBytes + sw128_off(t, ch & 63)) = o;
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(bar(A2_EMPTY + h));
-        fence_proxy_async();
-        mbar_arrive(bar(H2_FULL + h));
-        dw[5] += clock64() - t_e2;
-      }
-      if (u + 1 < NU) layer1(u + 1);  // overlaps with layer 3 of unit u on the tensor pipe
-    }
-    if (p.dbg && t == 0) {
-      p.dbg[blockIdx.x * 32 + 12] = dw[0]; p.dbg[blockIdx.x * 32 + 13] = dw[1]; p.dbg[blockIdx.x * 32 + 14] = dw[2];
-      p.dbg[blockIdx.x * 32 + 15] = clock64() - t_role; p.dbg[blockIdx.x * 32 + 16] = dw[4]; p.dbg[blockIdx.x * 32 + 17] = dw[5];
-      p.dbg[blockIdx.x * 32 + 18] = NU;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // v2: layer 3 issues N = 256 MMAs (both halves of a unit in one instruction: 12 KB of shared-memory operands per
@@ -873,8 +589,6 @@ static int launch_pointnet(const pn::FwdParams& fp, int grid, cudaStream_t st) {
   int device = 0;
   CRDPN_CUDA(cudaGetDevice(&device));
   if (!attr_set[device]) {
-    CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_eval_kernel<NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)pn::kSmemAlloc));
     CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_kernel_v2<NSLAB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)pn::kSmemAlloc));
     CRDPN_CUDA(cudaFuncSetAttribute(pn::pointnet_fwd_kernel_v2<NSLAB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -883,11 +597,10 @@ static int launch_pointnet(const pn::FwdParams& fp, int grid, cudaStream_t st) {
   }
   {
     ScopedKernelTimer tm(CRDPN_K_POINTNET_FWD, st);
-    if (fp.flags & 8) pn::pointnet_fwd_eval_kernel<NSLAB><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);       // v1: N=128
-    else if (fp.train_par) pn::pointnet_fwd_kernel_v2<NSLAB, true><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);  // train
+    if (fp.train_par) pn::pointnet_fwd_kernel_v2<NSLAB, true><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);  // train
     else pn::pointnet_fwd_kernel_v2<NSLAB, false><<<grid, pn::kThreads, pn::kSmemAlloc, st>>>(fp);                // v2: N=256
   }
-  CRDPN_LAUNCH_CHECK("pointnet_fwd_eval_kernel");
+  CRDPN_LAUNCH_CHECK("pointnet_fwd_kernel_v2");
   return CRDPN_OK;
 }
 

@@ -11,6 +11,7 @@
 // streaming kernel will have to write every tile twice (or convert the gradient operand to 16-bit).
 // Not a product path: a probe that pins the descriptor encodings before the streaming kernel is built on them.
 #include "common.cuh"
+#include "../../include/crdpn_b200_dev.h"
 #include "pointnet_common.cuh"
 
 namespace crdpn {

@@ -77,11 +77,12 @@ class ShapeEncoderPC(nn.Module):
                           "crdpn_pointnet_packed_bytes")
             if self._packed is None or self._packed.numel() != n.value or self._packed.device != device:
                 self._packed = torch.empty(n.value, dtype=torch.uint8, device=device)
-            ptrs = [t.detach().contiguous().data_ptr() for t in src]
+            keep = [t.detach().contiguous() for t in src]   # alive until the pack launch has been enqueued
             with _native.on_device(device):
-                rc = _native.lib().crdpn_pointnet_pack(*ptrs, BN_EPS, self.feature_dim, self._packed.data_ptr(),
-                                                       _native.stream_ptr(device))
+                rc = _native.lib().crdpn_pointnet_pack(*[t.data_ptr() for t in keep], BN_EPS, self.feature_dim,
+                                                       self._packed.data_ptr(), _native.stream_ptr(device))
             _native.check(rc, "crdpn_pointnet_pack")
+            del keep
             self._packed_key = key
         return self._packed
 

@@ -90,8 +90,10 @@ class PeerExchange:
             _native.check(lib.crdpn_p2p_alloc(n.value, ctypes.byref(own)), "crdpn_p2p_alloc")
             handle = ctypes.create_string_buffer(64)
             _native.check(lib.crdpn_p2p_export(own, handle), "crdpn_p2p_export")
-            handles = [None] * world
-            dist.all_gather_object(handles, handle.raw, group=group)
+            handles = [handle.raw]
+            if world > 1:
+                handles = [None] * world
+                dist.all_gather_object(handles, handle.raw, group=group)
             self._own = own
             self._imported = []
             ptrs = []
@@ -105,7 +107,8 @@ class PeerExchange:
                 self._imported.append(peer)
                 ptrs.append(peer.value)
         self._ptrs = (ctypes.c_void_p * world)(*ptrs)
-        dist.barrier(group=group)  # nobody starts writing before every mapping exists
+        if world > 1:
+            dist.barrier(group=group)  # nobody starts writing before every mapping exists
 
     def allgather(self, v1, v2, y, counts):
         B, D = sum(counts), v1.shape[1]
@@ -153,9 +156,13 @@ class ShardedContrastMemory(ContrastMemory):
     """ContrastMemory holding rows [row_begin,row_end) of the global banks; collectives on ``group``."""
 
     def __init__(self, inputSize, outputSize, K, T=0.07, momentum=0.5, group=None, rank=None, world_size=None,
-                 local_negatives=False, comm="dist", **kw):
+                 local_negatives=False, comm="dist", fixed_local_batch=False, **kw):
         """comm: "dist" = torch.distributed collectives (NCCL on GPUs, gloo in the CPU tests);
-        "p2p" = the two per-step exchanges as single kernels over NVLink peer memory (``PeerExchange``)."""
+        "p2p" = the per-step exchanges as kernels over NVLink peer memory (``PeerExchange``; the ranks must then stay
+        within CRDPN_P2P_TIMEOUT_S seconds of each other, default 600 -- see include/crdpn_b200.h).
+        fixed_local_batch: the per-rank batch sizes are exchanged ONCE (first call) instead of every call; a rank whose
+        batch size then changes raises instead of hanging the next collective.  Leave it False when the last batch of
+        an epoch may be ragged."""
         if comm not in ("dist", "p2p"):
             raise ValueError("comm must be 'dist' or 'p2p'")
         self.comm = comm
@@ -163,7 +170,14 @@ class ShardedContrastMemory(ContrastMemory):
         self.group = group
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         self.rank = dist.get_rank(group) if rank is None else rank
+        self.fixed_local_batch = bool(fixed_local_batch)
         lo, hi = shard_bounds(outputSize, self.world_size, self.rank)
+        if kw.get("seed") is None and self.world_size > 1 and dist.is_available() and dist.is_initialized():
+            # replicated negatives (idx=None, local_negatives=False) must be the SAME list on every rank: take rank 0's
+            # sampler seed everywhere (per-process torch.initial_seed() differs when a script seeds by rank)
+            box = [int(torch.initial_seed()) if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            kw["seed"] = box[0]
         super().__init__(inputSize, outputSize, K, T, momentum, row_begin=lo, row_end=hi, **kw)
         self.local_negatives = local_negatives
         if local_negatives:
@@ -200,7 +214,7 @@ class ShardedContrastMemory(ContrastMemory):
             packed = torch.empty(2 * B * D + 8, dtype=torch.float32, device=g1.device)
             packed[:B * D] = g1.reshape(-1)
             packed[B * D:2 * B * D] = g2.reshape(-1)
-        if self.comm == "p2p" and self.world_size > 1:
+        if self.comm == "p2p":
             # one kernel over NVLink peer memory; the 8 fp64 result scalars ride along as fp32 words
             packed = self._peer_exchange(B, D, g1.device).allreduce(packed[:2 * B * D], res)
         else:
@@ -216,12 +230,22 @@ class ShardedContrastMemory(ContrastMemory):
         return self._px
 
     def _ensure_counts(self, b_loc, device):
-        """Per-rank batch sizes (collective, but only when this rank's batch size changes)."""
-        if self._counts is None or self._counts[self.rank] != b_loc:
-            cnt = torch.zeros(self.world_size, dtype=torch.int64, device=device)
-            cnt[self.rank] = b_loc
-            self._counts = self._all_reduce(cnt).tolist()
+        """Per-rank batch sizes.  The exchange is a collective, so it has to be issued by EVERY rank or by none: it runs
+        on every call (one tiny all-reduce + a host read) unless ``fixed_local_batch`` promises constant sizes, in
+        which case it runs once and a later change raises on the rank that sees it."""
+        if self.fixed_local_batch and self._counts is not None:
+            if self._counts[self.rank] != b_loc:
+                raise RuntimeError(f"fixed_local_batch=True but the local batch changed from {self._counts[self.rank]} to "
+                                   f"{b_loc}; call reset_batch_sizes() on every rank first")
+            return self._counts
+        cnt = torch.zeros(self.world_size, dtype=torch.int64, device=device)
+        cnt[self.rank] = b_loc
+        self._counts = self._all_reduce(cnt).tolist()
         return self._counts
+
+    def reset_batch_sizes(self):
+        """Forget the cached per-rank batch sizes (collective in effect: call it on every rank)."""
+        self._counts = None
 
     def _ensure_local_sampler(self, device):
         """In-shard negatives come from this rank's own Philox stream."""
@@ -237,7 +261,7 @@ class ShardedContrastMemory(ContrastMemory):
         rows = max(counts)
         self._anchor_offset = sum(counts[:self.rank])
         d = v1.shape[1]
-        if self.comm == "p2p" and self.world_size > 1:
+        if self.comm == "p2p":
             return self._peer_exchange(sum(counts), d, v1.device).allgather(
                 v1.contiguous(), v2.contiguous(), y.contiguous().to(torch.int64), counts)
         if min(counts) == rows:  # even split: no padding, no compaction
@@ -255,6 +279,48 @@ class ShardedContrastMemory(ContrastMemory):
             idx = self._ensure_local_sampler(v1.device).draw_contrast(y.contiguous().to(torch.int64), K1, row_base=self.row_begin)
         return super()._prepare(v1, v2, y, idx)
 
+    def step_resident(self, v1_loc, v2_loc, y_loc, contrast_idx, out=None):
+        """The sharded step on device-resident LOCAL embeddings through ``crdpn_crd_step_sharded`` (peer-memory
+        all-gather -> scoring pass over this shard -> reduction + momentum update + sum over ranks in one kernel:
+        3 launches, no NCCL call, CUDA-graph capturable).  Z must be frozen.  Returns ``out``: dict with ``reduced``
+        [2*B*D + 8] f32 (grad_v1 | grad_v2 | result words, word 5 = loss of the whole batch), ``v1_all``, ``v2_all``,
+        ``y_all``; pass the returned dict back in to reuse its buffers (needed for graph capture)."""
+        if self.comm != "p2p":
+            raise RuntimeError("step_resident needs comm='p2p'")
+        hp = self._host_params()
+        if hp.Z1 <= 0 or hp.Z2 <= 0:
+            raise RuntimeError("step_resident: freeze Z first (one ordinary forward)")
+        from .crd import EPS
+        dev = v1_loc.device
+        D = v1_loc.shape[1]
+        counts = self._ensure_counts(v1_loc.shape[0], dev)
+        B = sum(counts)
+        K1 = contrast_idx.shape[1]
+        px = self._peer_exchange(B, D, dev)
+        if out is None:
+            out = dict(reduced=torch.empty(2 * B * D + 8, dtype=torch.float32, device=dev),
+                       partial=torch.empty(2 * B * D, dtype=torch.float32, device=dev),
+                       result=torch.empty(8, dtype=torch.float64, device=dev),
+                       v1_all=torch.empty(B, D, dtype=torch.float32, device=dev),
+                       v2_all=torch.empty(B, D, dtype=torch.float32, device=dev),
+                       y_all=torch.empty(B, dtype=torch.int64, device=dev))
+            offs = [0]
+            for c in counts:
+                offs.append(offs[-1] + c)
+            out["offs"] = (ctypes.c_int32 * (self.world_size + 1))(*offs)
+        m1, m2, stride, dt = self._banks()
+        variant = self._step_variant(B, K1, D)
+        ws = self._workspace(B, K1, D, dev, variant)
+        with _native.on_device(dev):
+            rc = _native.lib().crdpn_crd_step_sharded(
+                m1.data_ptr(), m2.data_ptr(), stride, dt, v1_loc.data_ptr(), v2_loc.data_ptr(), y_loc.data_ptr(),
+                out["offs"], px._ptrs, self.rank, self.world_size, px.Bmax, px.Dmax, contrast_idx.data_ptr(),
+                K1, D, self.nLem, self.k_total, self.row_begin, self.row_end, hp.T, hp.Z1, hp.Z2, EPS, hp.m, 1.0 - hp.m,
+                out["v1_all"].data_ptr(), out["v2_all"].data_ptr(), out["y_all"].data_ptr(), out["partial"].data_ptr(),
+                out["result"].data_ptr(), out["reduced"].data_ptr(), ws.data_ptr(), ws.numel(), variant, _stream_ptr(dev))
+        _native.check(rc, "crdpn_crd_step_sharded")
+        return out
+
     def fused_loss(self, v1, v2, y, idx=None):
         """v1, v2, y: this rank's LOCAL anchors; idx: replicated [B, K+1] or per-rank [B, K_loc+1]."""
         g1, g2, gy = _GatherAnchors.apply(v1, v2, y, self)
@@ -264,7 +330,8 @@ class ShardedContrastMemory(ContrastMemory):
 
 class _ShardedCRDLossFunction(torch.autograd.Function):
     """The sharded step with the peer-memory exchanges as one autograd node and two foreign calls
-    (``crdpn_crd_loss_forward_sharded``: 7 launches; ``crdpn_crd_loss_backward`` on the local rows: 2 launches)."""
+    (``crdpn_crd_loss_forward_sharded``: 6 launches, the sum over ranks fused into the reduction kernel;
+    ``crdpn_crd_loss_backward`` on the local rows: 2 launches)."""
 
     @staticmethod
     def forward(ctx, f_s, f_t, Ws, bs, Wt, bt, y, contrast_idx, crit):
@@ -292,6 +359,8 @@ class _ShardedCRDLossFunction(torch.autograd.Function):
         BD, BlD = B * D, B_loc * D
         Bp = (B_loc + 3) & ~3
         # one fp32 arena: [result(16) | pre_s | pre_t | v1_loc | v2_loc | inv1 | inv2 | v1_all | v2_all | partial(2BD) | reduced(2BD+8)]
+        # (carried to backward as a plain attribute: the returned loss is one of its words, and an in-place op on the
+        # loss must not trip autograd's version check on the gradient rows next to it)
         arena = torch.empty(16 + 4 * BlD + 2 * Bp + 2 * BD + 2 * BD + 2 * BD + 8, dtype=torch.float32, device=dev)
         base = arena.data_ptr()
         o_pre_s, o_pre_t, o_v1l, o_v2l = (base + 4 * (16 + i * BlD) for i in range(4))
@@ -329,14 +398,16 @@ class _ShardedCRDLossFunction(torch.autograd.Function):
         _native.check(rc, "crdpn_crd_loss_forward_sharded")
         if contrast_idx is None:
             smp.offset += B * K1
-        ctx.save_for_backward(arena, xs, xt, Wsc, Wtc)
+        ctx.save_for_backward(xs, xt, Wsc, Wtc)
+        ctx.arena = arena
         ctx.geom = (B, B_loc, D, a0, f_red, f_s.shape, f_t.shape)
         ctx.need_dx = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return arena[f_red + 2 * BD + 5]   # loss_s + loss_t of the WHOLE batch, summed over ranks
 
     @staticmethod
     def backward(ctx, grad_out):
-        arena, xs, xt, Ws, Wt = ctx.saved_tensors
+        xs, xt, Ws, Wt = ctx.saved_tensors
+        arena = ctx.arena
         B, B_loc, D, a0, f_red, shp_s, shp_t = ctx.geom
         dev = xs.device
         BD, BlD = B * D, B_loc * D
@@ -374,18 +445,18 @@ class ShardedCRDLoss(nn.Module):
     SUMMED over ranks (``allreduce_embed_grads``) to equal the single-GPU gradients."""
 
     def __init__(self, opt, group=None, rank=None, world_size=None, local_negatives=False, comm="dist",
-                 **memory_kwargs):
+                 fixed_local_batch=False, **memory_kwargs):
         super().__init__()
         self.embed_s = Embed(opt.s_dim, opt.feat_dim)
         self.embed_t = Embed(opt.t_dim, opt.feat_dim)
         self.contrast = ShardedContrastMemory(opt.feat_dim, opt.n_data, opt.nce_k, opt.nce_t, opt.nce_m, group=group,
                                               rank=rank, world_size=world_size, local_negatives=local_negatives,
-                                              comm=comm, **memory_kwargs)
+                                              comm=comm, fixed_local_batch=fixed_local_batch, **memory_kwargs)
 
     def forward(self, f_s, f_t, idx, contrast_idx=None):
         mem = self.contrast
         hp = mem._host_params()
-        fast = (mem.comm == "p2p" and mem.world_size > 1 and hp.Z1 > 0 and hp.Z2 > 0 and f_s.is_cuda and f_t.is_cuda
+        fast = (mem.comm == "p2p" and hp.Z1 > 0 and hp.Z2 > 0 and f_s.is_cuda and f_t.is_cuda
                 and f_s.dtype == torch.float32 and f_t.dtype == torch.float32
                 and (contrast_idx is not None or mem.local_negatives))
         if fast:   # (the first call freezes Z through the general path below)

@@ -178,6 +178,42 @@ def time_crd_resident(pkg, torch, dev, c, steps, warmup, flush_l2=False, variant
                 launches=l1 - l0)
 
 
+def time_shard_emulation(pkg, torch, dev, c, steps, warmup, shards):
+    """ONE rank's share of the strong-scaling step (BASELINE configs[3] over `shards` GPUs) timed on this GPU alone:
+    rows [0, N/shards) resident, the whole replicated contrast_idx scanned, only in-shard entries scored.  No exchange
+    kernels (they need peers): score pass + reduction / momentum update.  Explains the multi-GPU line; not a headline."""
+    torch.manual_seed(SEED)
+    rows = c["N"] // shards
+    mem = pkg.ContrastMemory(c["D"], c["N"], c["K"], c["T"], c["m"], row_begin=0, row_end=rows).to(dev)
+    g = torch.Generator().manual_seed(SEED)
+    v1 = torch.nn.functional.normalize(torch.randn(c["B"], c["D"], generator=g)).to(dev)
+    v2 = torch.nn.functional.normalize(torch.randn(c["B"], c["D"], generator=g)).to(dev)
+    y = torch.randperm(c["N"], generator=g)[:c["B"]].to(dev)
+    cidx = torch.randint(0, c["N"], (c["B"], c["K"] + 1), generator=g).to(dev)
+    cidx[:, 0] = y
+    lib = pkg._native.lib()
+
+    def step():
+        mem._step(v1, v2, y, cidx, 2.0e6, 2.0e6)
+
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    tot, n = ctypes.c_double(), ctypes.c_uint64()
+    lib.crdpn_timing_enable(1)
+    lib.crdpn_timing_read(0, ctypes.byref(tot), ctypes.byref(n))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.crdpn_timing_read(0, ctypes.byref(tot), ctypes.byref(n))
+    lib.crdpn_timing_enable(0)
+    return {"shards": shards, "rows_resident": rows, "ms_per_step": e0.elapsed_time(e1) / steps,
+            "score_kernel_ms": tot.value / max(n.value, 1)}
+
+
 def time_crd_e2e(pkg, torch, dev, c, steps, warmup, host_contrast_idx=False):
     """Public API, pinned HOST inputs: H2D of (f_s, f_t, idx[, contrast_idx]) + forward + backward + D2H of the loss.
 
@@ -329,6 +365,7 @@ def run_own(args):
                           "value": scores_per_step(c) / (rbg["total_ms"] / args.steps * 1e-3)},
         "note": "bank ROWS stored in bf16: north_star's 1e-2 tolerance mode; reported for information, the headline above "
                 "is the fp32-bank run (gather kernel, fp32 arithmetic)"}
+    also["shard_emulation"] = [time_shard_emulation(pkg, torch, dev, c, max(args.steps // 2, 10), 3, r) for r in (2, 4, 8)]
     if os.environ.get("CRDPN_BENCH_VARIANTS"):
         sweep = {}
         for v in [int(x) for x in os.environ["CRDPN_BENCH_VARIANTS"].split(",")]:

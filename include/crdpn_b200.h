@@ -197,7 +197,10 @@ int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int 
  * single-GPU reference -- SURVEY.md section 8e).  Each rank allocates one exchange buffer, exports its CUDA IPC
  * handle (64 bytes, exchanged by the caller through any host channel), imports the peers' handles, and passes the
  * HOST array of the `world` base pointers (its own at index `rank`) to the two exchange kernels.  Bmax / Dmax fix the
- * buffer layout and must be the same on every rank.  world <= 8.  Every rank must issue the same sequence of calls.
+ * buffer layout and must be the same on every rank.  world <= 8.  Every rank must issue the same sequence of calls
+ * (any sequence: the payload areas are double-buffered by epoch parity, so a rank that runs ahead never overwrites words
+ * a slower peer has not read).  A poll that lasts longer than CRDPN_P2P_TIMEOUT_S seconds (environment, default 600)
+ * means a peer died or the sequences diverged: the kernel traps (sticky context error) instead of hanging the box.
  *   crdpn_p2p_allgather_anchors: local rows v1/v2 [b_loc,D] f32, y [b_loc] i64 -> all B rows in rank order;
  *                                offs_host[world+1] = prefix sums of the per-rank batch sizes.
  *   crdpn_p2p_allreduce_f32:     out[i] = sum over ranks (in rank order: same bits on every rank) of partial[i];
@@ -284,8 +287,8 @@ int crdpn_pointcloud_sample(const double* vertices, const int64_t* cloud_offsets
 /* The sharded step's forward as ONE call (one process per GPU, exchanges over NVLink peer memory as above): both embed
  * heads on the LOCAL anchors -> crdpn_p2p_allgather_anchors -> [contrast_idx == NULL: crdpn_alias_draw_contrast_local,
  * K1-1 negatives per anchor inside this rank's shard] -> crdpn_crd_step over the shard (gradients into `partial`
- * [2*B*D]) -> crdpn_p2p_allreduce_f32 into `reduced` [2*B*D + 8] (the 8 result scalars ride behind the gradients as
- * fp32 words; word 5 is the loss of the whole batch).  7 launches.  The backward is crdpn_crd_loss_backward on the local
+ * [2*B*D]) whose reduction kernel also sums over the ranks into `reduced` [2*B*D + 8] (the 8 result scalars ride behind
+ * the gradients as fp32 words; word 5 is the loss of the whole batch).  6 launches.  The backward is crdpn_crd_loss_backward on the local
  * rows of `reduced`.  offs_host[world+1] = prefix sums of the per-rank batch sizes; B = offs_host[world]. */
 int crdpn_alias_draw_contrast_local(const float* prob, const int64_t* alias, int64_t n_local, int64_t row_base,
                                     const int64_t* y, int64_t B, int64_t K1, uint64_t seed, uint64_t offset,
@@ -303,6 +306,23 @@ int crdpn_crd_loss_forward_sharded(
     float* pre_s, float* pre_t, float* v1_local, float* v2_local, float* inv1, float* inv2,
     float* v1_all, float* v2_all, int64_t* y_all, float* partial, double* result, float* reduced,
     void* workspace, size_t workspace_bytes, int variant, void* stream);
+
+/* The sharded step on device-resident embeddings (the per-rank unit of BASELINE configs[3]: K negatives against an
+ * N-row bank sharded over `world` GPUs): crdpn_p2p_allgather_anchors of the local rows -> scoring pass over this rank's
+ * rows [row_begin,row_end) of the replicated (or per-shard) contrast_idx [B,K1] -> ONE kernel that reduces the per-warp
+ * partials, momentum-updates the positive rows this rank owns and sums gradients / loss partials over the ranks (LL
+ * words pushed into every peer's slot and summed in rank order: identical bits on every rank).  3 launches, no NCCL.
+ * Outputs: v1_all / v2_all [B,D], y_all [B]; reduced [2*B*D + 8] f32 = grad_v1 | grad_v2 | {loss_s, loss_t, -, -, -,
+ * loss_s + loss_t, -, -} of the WHOLE batch over ALL shards; partial [2*B*D] and result [8] are this rank's shares.
+ * With variant | 0x200 (bank-streaming kernels) the sum over ranks is a separate crdpn_p2p_allreduce_f32 launch. */
+int crdpn_crd_step_sharded(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+                           const float* v1_local, const float* v2_local, const int64_t* y_local,
+                           const int32_t* offs_host, void* const* peer_bufs_host, int rank, int world,
+                           int64_t Bmax, int64_t Dmax, const int64_t* contrast_idx,
+                           int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
+                           float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+                           float* v1_all, float* v2_all, int64_t* y_all, float* partial, double* result, float* reduced,
+                           void* workspace, size_t workspace_bytes, int variant, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * PointNet encoder, eval-mode BatchNorm (the KD-time teacher, KD/common/base_class.py:317,363).
@@ -390,19 +410,6 @@ int crdpn_pointnet_backward_phased(
     float* d_conv1_w, float* d_conv1_b, float* d_conv2_w, float* d_conv2_b, float* d_conv3_w, float* d_conv3_b,
     float* d_bn1_w, float* d_bn1_b, float* d_bn2_w, float* d_bn2_b, float* d_bn3_w, float* d_bn3_b,
     void* workspace, size_t workspace_bytes, int phase_begin, int phase_end, int64_t total_points, void* stream);
-
-/* ---------------------------------------------------------------------------------------------------
- * Development probe (not a product path; no reference counterpart): one tile of the tensor-core formulation planned for the
- * bank-streaming CRD step -- tcgen05.mma kind::tf32 on an fp32 tile stored once in the K-major
- * SWIZZLE_128B image and read both K-major (scores = rows . [V2 | V1]^T) and MN-major (gradients^T = rows^T . C).
- * rows1, rows2 [64,128]; v1, v2 [48,128]; c1, c2 [64,48] (f32, device); out [128,192]: columns [0,96) scores of the 128
- * stacked rows (64 of bank 1, then 64 of bank 2) against [V2 | V1], [96,144) G2^T[e][b] = sum_r rows1[r][e] c2[r][b],
- * [144,192) G1^T[e][b] = sum_r rows2[r][e] c1[r][b].  mode 0: as described; mode 1: the score MMA with M = 64 (bank-1 rows only),
- * to record the TMEM placement of M = 64 accumulators (the dump still covers all 128 lanes); mode 2: both GEMMs with bf16
- * operands (kind::f16) from ONE K-major SWIZZLE_128B image, read K-major for the scores and MN-major for the gradients.
- * ------------------------------------------------------------------------------------------------- */
-int crdpn_umma_tf32_probe(const float* rows1, const float* rows2, const float* v1, const float* v2, const float* c1,
-                          const float* c2, float* out, int mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ sys.path.insert(0, '.')
 import __graft_entry__ as ge
 
 pkg = ge.load_package()
-lib = pkg._native.lib()
+lib = pkg._native.dev_lib()
 dev = torch.device('cuda:0')
 rng = np.random.default_rng(1)
 rows1, rows2 = rng.uniform(0.5, 1.5, (64, 128)).astype(np.float32), rng.uniform(0.5, 1.5, (64, 128)).astype(np.float32)

@@ -60,6 +60,13 @@ def _worker(rank, world, port, local_negatives, q):
         stock = StockCRD(opt.s_dim, opt.t_dim, D, N, K * (world if local_negatives else 1), 0.07, 0.5, seed=3)
         crit = pkg.ShardedCRDLoss(opt, local_negatives=local_negatives, interleave=False)
         crit.contrast.__class__ = _make_oracle_memory(pkg, oracle)
+
+        class HostEmbed(pkg.Embed):   # the product Embed is CUDA-only; the host logic under test needs a CPU stand-in
+            def forward(self, x):
+                return self.l2norm(self.linear(x.view(x.shape[0], -1)))
+
+        crit.embed_s.__class__ = HostEmbed
+        crit.embed_t.__class__ = HostEmbed
         lo, hi = pkg.shard_bounds(N, world, rank)
         assert (crit.contrast.row_begin, crit.contrast.row_end) == (lo, hi)
         with torch.no_grad():
@@ -77,10 +84,15 @@ def _worker(rank, world, port, local_negatives, q):
             cidx_full = torch.randint(0, N, (B, K + 1), generator=g)
             cidx_full[:, 0] = y
             cidx = cidx_full
-        counts = [4, 3]  # uneven data-parallel split of the 7 anchors
-        a0 = sum(counts[:rank])
-        sl = slice(a0, a0 + counts[rank])
-        for step in range(2):
+        f_s_all, f_t_all, y_all, cidx_all, cidx_full_all = f_s, f_t, y, cidx, cidx_full
+        for step in range(3):
+            # uneven data-parallel split of the 7 anchors; in the last step the batch shrinks ON RANK 1 ONLY (a ragged
+            # final batch): the per-rank sizes must be re-exchanged by every rank, not only by the rank that changed
+            counts = [4, 3] if step < 2 else [4, 2]
+            nb = sum(counts)
+            f_s, f_t, y, cidx, cidx_full = f_s_all[:nb], f_t_all[:nb], y_all[:nb], cidx_all[:nb], cidx_full_all[:nb]
+            a0 = sum(counts[:rank])
+            sl = slice(a0, a0 + counts[rank])
             fs_l = f_s[sl].clone().requires_grad_()
             ft_l = f_t[sl].clone().requires_grad_()
             crit.zero_grad()

@@ -42,6 +42,39 @@ def test_world1_sharded_equals_unsharded(pkg, cuda):
         assert torch.equal(a.contrast.params, b.contrast.params)
 
 
+def test_world1_peer_memory_step_equals_unsharded(pkg, cuda):
+    """comm="p2p" with a single rank: the exchange kernels talk to this rank's own buffer, so the whole sharded call
+    chain (crdpn_crd_loss_forward_sharded / crdpn_crd_step_sharded: all-gather kernel, scoring pass, reduction kernel with
+    the sum over ranks fused in) runs on one GPU and must reproduce the unsharded step: gradients and bank rows bit for
+    bit (one rank: no re-association), loss to fp32 rounding."""
+    opt = _opt()
+    torch.manual_seed(1)
+    a = pkg.CRDLoss(opt).to(cuda)
+    b = pkg.ShardedCRDLoss(opt, rank=0, world_size=1, comm="p2p").to(cuda)
+    b.load_state_dict(a.state_dict(), strict=False)
+    f_s, f_t, y, cidx = [t.to(cuda) for t in _inputs(opt, 46)]
+    for step in range(3):   # step 0 freezes Z through the general path, steps 1-2 take the one-call path
+        fa, fb = f_s.clone().requires_grad_(), f_s.clone().requires_grad_()
+        la = a(fa, f_t, y, cidx); la.backward()
+        lb = b(fb, f_t, y, cidx); lb.backward()
+        assert abs(la.item() - lb.item()) <= 2e-7 * abs(la.item())
+        assert torch.equal(fa.grad, fb.grad)
+        assert torch.equal(a.contrast.memory_v1, b.contrast.memory_v1) and torch.equal(a.contrast.memory_v2, b.contrast.memory_v2)
+    # the device-resident entry point (what bench.py times at N > 1), twice in a row (same-kind exchanges back to back)
+    with torch.no_grad():
+        v1, v2 = a.embed_s(f_s).contiguous(), a.embed_t(f_t).contiguous()
+    hp = a.contrast._host_params()
+    out = None
+    for _ in range(2):
+        res, g1, g2 = a.contrast._step(v1, v2, y, cidx, hp.Z1, hp.Z2)
+        out = b.contrast.step_resident(v1, v2, y, cidx, out)
+        B, D = v1.shape
+        assert torch.equal(out["reduced"][:B * D].view(B, D), g1) and torch.equal(out["reduced"][B * D:2 * B * D].view(B, D), g2)
+        want = (res[0] + res[1]).item()
+        assert abs(out["reduced"][2 * B * D + 5].item() - want) <= 2e-7 * abs(want)
+        assert torch.equal(a.contrast.memory_v1, b.contrast.memory_v1)
+
+
 def test_local_negatives_world1_matches_oracle(pkg, oracle, cuda):
     """local_negatives with internal sampling: indices are in-shard draws of the rank's own Philox stream."""
     opt = _opt(nce_k=512)
@@ -100,6 +133,18 @@ def _nccl_worker(rank, world, port, q, comm="dist"):
             # owner-only momentum update: shard rows are BIT-identical to the unsharded bank's rows
             assert torch.equal(sh.contrast.memory_v1, ref.contrast.memory_v1[lo:hi])
             assert torch.equal(sh.contrast.memory_v2, ref.contrast.memory_v2[lo:hi])
+        if comm == "p2p":   # the device-resident entry point bench.py times: crdpn_crd_step_sharded
+            with torch.no_grad():
+                v1, v2 = ref.embed_s(f_s).contiguous(), ref.embed_t(f_t).contiguous()
+            hp = ref.contrast._host_params()
+            out = None
+            for _ in range(3):
+                res, g1, g2 = ref.contrast._step(v1, v2, y, cidx, hp.Z1, hp.Z2)
+                out = sh.contrast.step_resident(v1[sl].contiguous(), v2[sl].contiguous(), y[sl].contiguous(), cidx, out)
+                red = out["reduced"]
+                assert rel(red[:B * 128].view(B, 128), g1) < 1e-4 and rel(red[B * 128:2 * B * 128].view(B, 128), g2) < 1e-4
+                assert rel(red[2 * B * 128 + 5], res[0] + res[1]) < 1e-5
+                assert torch.equal(sh.contrast.memory_v1, ref.contrast.memory_v1[lo:hi])
         dist.barrier()
         q.put((rank, "ok"))
         dist.destroy_process_group()

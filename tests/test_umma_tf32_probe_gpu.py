@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_scores_and_gradients_from_one_tile(pkg, cuda):
-    lib = pkg._native.lib()
+    lib = pkg._native.dev_lib()
     rng = np.random.default_rng(46)
     rows1, rows2 = rng.normal(size=(64, 128)).astype(np.float32), rng.normal(size=(64, 128)).astype(np.float32)
     v1, v2 = rng.normal(size=(48, 128)).astype(np.float32), rng.normal(size=(48, 128)).astype(np.float32)
@@ -19,7 +19,7 @@ def test_scores_and_gradients_from_one_tile(pkg, cuda):
     d = [torch.from_numpy(a).to(cuda) for a in (rows1, rows2, v1, v2, c1, c2)]
     out = torch.full((128, 192), float("nan"), device=cuda)
     rc = lib.crdpn_umma_tf32_probe(*[t.data_ptr() for t in d], out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
-    assert rc == 0, lib.crdpn_last_error()
+    assert rc == 0, pkg._native.lib().crdpn_last_error()
     torch.cuda.synchronize()
     got = out.cpu().numpy().astype(np.float64)
     vcat = np.concatenate([v2, v1]).astype(np.float64)                      # [96, 128]
@@ -33,7 +33,7 @@ def test_scores_and_gradients_from_one_tile(pkg, cuda):
 
 def test_m64_accumulator_placement(pkg, cuda):
     """M = 64 score MMA (the 64 bank-1 rows): which TMEM lanes hold which rows?  Recorded for the 32-row-tile variant."""
-    lib = pkg._native.lib()
+    lib = pkg._native.dev_lib()
     rng = np.random.default_rng(7)
     rows1, rows2 = rng.normal(size=(64, 128)).astype(np.float32), rng.normal(size=(64, 128)).astype(np.float32)
     v1, v2 = rng.normal(size=(48, 128)).astype(np.float32), rng.normal(size=(48, 128)).astype(np.float32)
@@ -56,7 +56,7 @@ def test_m64_accumulator_placement(pkg, cuda):
 
 def test_bf16_single_image_serves_both_gemms(pkg, cuda):
     """mode 2: 16-bit operands may be read MN-major from the ordinary SWIZZLE_128B image (no second copy of the tile)."""
-    lib = pkg._native.lib()
+    lib = pkg._native.dev_lib()
     rng = np.random.default_rng(3)
     bf = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()
     rows1, rows2 = bf(rng.normal(size=(64, 128)).astype(np.float32)), bf(rng.normal(size=(64, 128)).astype(np.float32))
