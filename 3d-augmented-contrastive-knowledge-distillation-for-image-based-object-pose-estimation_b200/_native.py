@@ -36,6 +36,11 @@ _SIGNATURES = {
                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                c_float, c_float, c_float, c_float, c_float, c_float,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "crdpn_crd_step_drawn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                     c_float, c_float, c_float, c_float, c_float, c_float,
+                                     c_uint64, c_uint64, c_int64, c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "crdpn_crd_loss_forward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p,
                                        c_void_p, c_void_p, c_int64, c_int,

@@ -177,7 +177,9 @@ class _CRDLossFunction(torch.autograd.Function):
         yc = y if (y.dtype == torch.int64 and y.is_contiguous()) else y.contiguous().to(torch.int64)
         if contrast_idx is not None:
             mem._check_device(contrast_idx, "contrast_idx")
-            contrast_idx = contrast_idx.contiguous().to(torch.int64)
+            if contrast_idx.dtype not in (torch.int64, torch.int32):
+                contrast_idx = contrast_idx.to(torch.int64)
+            contrast_idx = contrast_idx.contiguous()   # int32 lists are consumed as they are (half the bytes to copy and scan)
             if contrast_idx.shape != (B, K1):
                 raise RuntimeError(f"contrast_idx must have shape [B, K+1] = {(B, K1)}, got {tuple(contrast_idx.shape)}")
         BD = B * D
@@ -204,13 +206,20 @@ class _CRDLossFunction(torch.autograd.Function):
             v2 = arena[16 + 3 * BD:16 + 4 * BD].view(B, D)
             if contrast_idx is None:
                 contrast_idx = mem.multinomial.draw_contrast(yc, K1)
-            mem._freeze_z(v1, v2, contrast_idx)
+            mem._freeze_z(v1, v2, contrast_idx.to(torch.int64))
             hp = mem._host_params()
         m1, m2, stride, dt = mem._banks()
         variant = mem._step_variant(B, K1, D)
         ws = mem._workspace(B, K1, D, dev, variant)
+        if contrast_idx is not None and contrast_idx.dtype == torch.int32:
+            if variant & mem.STREAM:
+                contrast_idx = contrast_idx.to(torch.int64)   # the bucketing passes of the streaming kernels read int64
+            else:
+                variant |= mem.IDX32
         smp = mem.multinomial
-        if contrast_idx is None:
+        if contrast_idx is None and smp.uniform and not (variant & mem.STREAM):
+            cidx_ptr, scratch_ptr = None, None     # the scoring pass draws the negatives itself: no list in memory
+        elif contrast_idx is None:
             scratch = mem._idx_scratch
             if scratch is None or scratch.numel() != B * K1 or scratch.device != dev:
                 scratch = mem._idx_scratch = torch.empty(B * K1, dtype=torch.int64, device=dev)
@@ -453,6 +462,7 @@ class ContrastMemory(nn.Module):
         return self._host
 
     STREAM = 0x200   # variant bit: bank-streaming formulation of the step (csrc/crd_stream.cuh)
+    IDX32 = 0x1000   # variant bit: contrast_idx is an int32 list
 
     def _step_variant(self, B, K1, D):
         """Variant passed to crdpn_crd_step.  ``self.streaming`` selects the bank-streaming formulation, which reads every

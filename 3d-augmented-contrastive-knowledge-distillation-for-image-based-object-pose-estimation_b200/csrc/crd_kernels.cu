@@ -40,6 +40,15 @@ struct ScoreParams {
   const float* v1;
   const float* v2;
   const long long* idx;
+  // where the contrast indices come from: 0 = the int64 list `idx`; 1 = the int32 list `idx32` (half the bytes to copy and
+  // scan); 2 = drawn HERE, entry (b, k) = draw_base + floor(u64(Philox block (seed, offset + b*K1 + k)) * draw_n / 2^64),
+  // column 0 = y[b] -- bit for bit the list crdpn_alias_draw_contrast would write for uniform tables, without the 8 bytes
+  // written and read back per entry and without the draw launch
+  int idx_mode;
+  const int* idx32;
+  const long long* y;
+  unsigned long long seed, offset;
+  long long draw_n, draw_base;
   int B, K1, D;
   long long row_begin, row_end;
   float k_exp;          // log2(e) / T
@@ -83,7 +92,8 @@ int sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dty
                       int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end, float T, float Z1, float Z2,
                       float eps, float momentum, float one_minus_momentum, float* v1_all, float* v2_all, int64_t* y_all,
                       float* partial, double* result, float* reduced, void* workspace, size_t workspace_bytes, int variant,
-                      void* stream);
+                      void* stream, int idx_mode = 0, uint64_t seed = 0, uint64_t offset = 0, int64_t draw_n = 0,
+                      int64_t draw_base = 0);
 
 __device__ __forceinline__ uint4 ld16_stream(const void* p) {
   uint4 r;
@@ -263,13 +273,22 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       }
     };
 
+    auto fetch_idx = [&](long long pos) -> long long {   // idx_mode is uniform over the grid: no divergence
+      if (p.idx_mode == 0) return p.idx[pos];
+      if (p.idx_mode == 1) return (long long)p.idx32[pos];
+      if (pos == anchor_base) return p.y[b];
+      unsigned rr[4];
+      philox4x32_10(p.seed, p.offset + (unsigned long long)pos, rr);
+      const unsigned long long bits = ((unsigned long long)rr[0] << 32) | (unsigned long long)rr[1];
+      return p.draw_base + (long long)__umul64hi(bits, (unsigned long long)p.draw_n);
+    };
     long long base = lo;
-    long long r_next = (base + lane < seg_hi) ? p.idx[base + lane] : -1;
+    long long r_next = (base + lane < seg_hi) ? fetch_idx(base + lane) : -1;
     while (base < seg_hi) {
       const long long r = r_next;
       const long long pidx = base + lane;
       const long long nbase = base + 32;
-      r_next = (nbase + lane < seg_hi) ? p.idx[nbase + lane] : -1;  // prefetch the next 32 indices
+      r_next = (nbase + lane < seg_hi) ? fetch_idx(nbase + lane) : -1;  // prefetch the next 32 indices
       const bool inrange = pidx < seg_hi;
       const bool valid = inrange && r >= p.row_begin && r < p.row_end;
       const unsigned mask = __ballot_sync(kFull, valid);
@@ -721,15 +740,29 @@ static UpdateParams make_update_params(void* bank1, void* bank2, int64_t row_str
   return u;
 }
 
+// how the scoring pass obtains contrast_idx when it is not an int64 list (ScoreParams::idx_mode)
+struct IdxSource {
+  int mode;                 // 1: int32 list; 2: drawn inside the kernel (uniform tables)
+  const int* idx32;
+  const int64_t* y;
+  uint64_t seed, offset;
+  int64_t draw_n, draw_base;
+};
+
 // score (+ finalize); when `upd` is given the momentum update rides in the finalize launch.
 static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
                       const float* v1, const float* v2, const int64_t* contrast_idx,
                       int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
                       float T, float Z1, float Z2, float eps, float* out_v1, float* out_v2, double* result,
                       float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes, int variant,
-                      const UpdateParams* upd, void* stream, const FinalizeParams* xchg = nullptr) {
-  if (!v1 || !v2 || !contrast_idx || !result || !workspace)
+                      const UpdateParams* upd, void* stream, const FinalizeParams* xchg = nullptr,
+                      const IdxSource* src = nullptr) {
+  if (!v1 || !v2 || (!contrast_idx && !src) || !result || !workspace)
     return fail(CRDPN_E_BADARG, "crdpn_crd_score: null pointer");
+  if (src && ((src->mode == 1 && !src->idx32) || (src->mode == 2 && (!src->y || src->draw_n <= 0)) || (src->mode != 1 && src->mode != 2)))
+    return fail(CRDPN_E_BADARG, "crdpn_crd_score: bad index source");
+  if (src && (out_v1 || out_v2) && src->mode == 2)
+    return fail(CRDPN_E_BADARG, "crdpn_crd_score: per-entry outputs need a materialised contrast_idx");
   if (B <= 0 || K1 <= 0 || D <= 0 || n_data <= 0 || row_end < row_begin || !(T > 0.f))
     return fail(CRDPN_E_BADARG, "crdpn_crd_score: bad size");
   if (row_end > row_begin && (!bank1 || !bank2)) return fail(CRDPN_E_BADARG, "crdpn_crd_score: null bank");
@@ -781,6 +814,11 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.row_stride_bytes = (long long)row_stride * (long long)esz;
   sp.v1 = v1; sp.v2 = v2;
   sp.idx = (const long long*)contrast_idx;
+  sp.idx_mode = src ? src->mode : 0;
+  sp.idx32 = src ? src->idx32 : nullptr;
+  sp.y = src ? (const long long*)src->y : nullptr;
+  sp.seed = src ? src->seed : 0; sp.offset = src ? src->offset : 0;
+  sp.draw_n = src ? src->draw_n : 0; sp.draw_base = src ? src->draw_base : 0;
   sp.B = (int)B; sp.K1 = (int)K1; sp.D = (int)D;
   sp.row_begin = row_begin; sp.row_end = row_end;
   sp.k_exp = (float)(1.4426950408889634 / (double)T);
@@ -1059,13 +1097,43 @@ extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int 
   if (rc) return rc;
   const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end,
                                             momentum, one_minus_momentum);
+  if ((variant & 0x200) && (variant & 0x1000))
+    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step: the bank-streaming kernels take an int64 contrast_idx");
   if (variant & 0x200)  // bank-streaming formulation (crd_stream.cuh); the workspace is crdpn_crd_stream_workspace_bytes
     return stream_step_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin,
                             row_end, T, Z1, Z2, eps, result, grad_v1, grad_v2, workspace, workspace_bytes, u,
                             (variant & 0x800) ? 1 : 0, stream);
+  if (variant & 0x1000) {   // contrast_idx is an int32 list
+    const IdxSource src{1, (const int*)contrast_idx, nullptr, 0, 0, 0, 0};
+    return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, nullptr, B, K1, D, n_data, k_total, row_begin, row_end,
+                      T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant & ~0x1000,
+                      &u, stream, nullptr, &src);
+  }
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin, row_end,
                     T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant,
                     &u, stream);
+}
+
+// crdpn_crd_step whose negatives are drawn INSIDE the scoring pass (uniform sampler): no index list exists in memory.
+extern "C" int crdpn_crd_step_drawn(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+                                    const float* v1, const float* v2, const int64_t* y,
+                                    int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
+                                    int64_t row_begin, int64_t row_end,
+                                    float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+                                    uint64_t seed, uint64_t offset, int64_t draw_n, int64_t draw_base,
+                                    double* result, float* grad_v1, float* grad_v2,
+                                    void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  if (!(Z1 > 0.f && Z2 > 0.f)) return fail(CRDPN_E_BADARG, "crdpn_crd_step_drawn: Z1 and Z2 must be frozen (> 0) before a full step");
+  if (variant & 0x200) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step_drawn: the bank-streaming kernels need a materialised contrast_idx");
+  if (draw_n <= 0 || draw_base < 0) return fail(CRDPN_E_BADARG, "crdpn_crd_step_drawn: bad sampler range");
+  int rc = check_update_args(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end);
+  if (rc) return rc;
+  const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end,
+                                            momentum, one_minus_momentum);
+  const IdxSource src{2, nullptr, y, seed, offset, draw_n, draw_base};
+  return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, nullptr, B, K1, D, n_data, k_total, row_begin, row_end,
+                    T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant & 0xfff,
+                    &u, stream, nullptr, &src);
 }
 
 // The row-sharded step (one process per GPU) as one call: all-gather of the anchors over NVLink
@@ -1080,8 +1148,11 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
                              int64_t K1, int64_t D, int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end,
                              float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
                              float* v1_all, float* v2_all, int64_t* y_all, float* partial, double* result, float* reduced,
-                             void* workspace, size_t workspace_bytes, int variant, void* stream) {
+                             void* workspace, size_t workspace_bytes, int variant, void* stream, int idx_mode, uint64_t seed,
+                             uint64_t offset, int64_t draw_n, int64_t draw_base) {
   int rc;
+  if ((variant & 0x200) && idx_mode != 0)
+    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step_sharded: the bank-streaming kernels need a materialised int64 contrast_idx");
   if (variant & 0x200) {
     rc = crdpn_crd_step(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, contrast_idx, y_all, B, K1, D, n_data, k_total,
                         row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, result, partial, partial + B * D,
@@ -1102,9 +1173,10 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
   x.off_ctl = L.ctl; x.off_slots = L.slots; x.parity_stride = L.parity_stride; x.slot_words = L.slot_words;
   x.timeout = p2p::poll_timeout_ticks();
   // an empty shard still takes part in the exchange: score_impl launches the reduction kernel either way
-  return score_impl(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, contrast_idx, B, K1, D, n_data, k_total, row_begin,
-                    row_end, T, Z1, Z2, eps, nullptr, nullptr, result, partial, partial + B * D, workspace, workspace_bytes,
-                    variant, &u, stream, &x);
+  const IdxSource src{idx_mode, (const int*)contrast_idx, y_all, seed, offset, draw_n, draw_base};
+  return score_impl(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, idx_mode == 0 ? contrast_idx : nullptr, B, K1, D,
+                    n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, nullptr, nullptr, result, partial, partial + B * D,
+                    workspace, workspace_bytes, variant & 0xfff, &u, stream, &x, idx_mode == 0 ? nullptr : &src);
 }
 
 extern "C" int crdpn_crd_step_sharded(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
@@ -1128,7 +1200,8 @@ extern "C" int crdpn_crd_step_sharded(void* bank1, void* bank2, int64_t row_stri
   if (rc) return rc;
   return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, contrast_idx, B, K1, D,
                            n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all,
-                           y_all, partial, result, reduced, workspace, workspace_bytes, variant, stream);
+                           y_all, partial, result, reduced, workspace, workspace_bytes, variant & ~0x1000, stream,
+                           (variant & 0x1000) ? 1 : 0);
 }
 
 extern "C" int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,

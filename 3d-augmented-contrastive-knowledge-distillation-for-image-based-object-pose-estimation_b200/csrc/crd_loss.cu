@@ -22,7 +22,8 @@ int sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dty
                       int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end, float T, float Z1, float Z2,
                       float eps, float momentum, float one_minus_momentum, float* v1_all, float* v2_all, int64_t* y_all,
                       float* partial, double* result, float* reduced, void* workspace, size_t workspace_bytes, int variant,
-                      void* stream);
+                      void* stream, int idx_mode = 0, uint64_t seed = 0, uint64_t offset = 0, int64_t draw_n = 0,
+                      int64_t draw_base = 0);
 }  // namespace crdpn
 
 using namespace crdpn;
@@ -42,6 +43,11 @@ extern "C" int crdpn_crd_loss_forward(
   int rc = embed_forward2(f_s, Ws, bs, s_dim, pre_s, v1, inv1, f_t, Wt, bt, t_dim, pre_t, v2, inv2, B, D, stream);
   if (rc) return rc;
   const int64_t* idx = contrast_idx;
+  if (idx == nullptr && alias_prob == nullptr && alias_alias == nullptr && !(variant & 0x200))
+    // uniform sampler: the scoring pass draws the negatives itself (same Philox stream, same indices, no list in memory)
+    return crdpn_crd_step_drawn(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, K1, D, n_data, k_total, row_begin, row_end, T,
+                                Z1, Z2, eps, momentum, one_minus_momentum, seed, offset, n_data, 0, result, grad_v1, grad_v2,
+                                workspace, workspace_bytes, variant, stream);
   if (idx == nullptr) {
     if (!idx_scratch) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward: contrast_idx is NULL and so is idx_scratch");
     rc = crdpn_alias_draw_contrast(alias_prob, alias_alias, n_data, y, B, K1, seed, offset, idx_scratch, stream);
@@ -90,6 +96,12 @@ extern "C" int crdpn_crd_loss_forward_sharded(
                                    v2_all, y_all, stream);
   if (rc) return rc;
   const int64_t* idx = contrast_idx;
+  if (idx == nullptr && alias_prob == nullptr && alias_alias == nullptr && !(variant & 0x200))
+    // K1-1 negatives per anchor inside this rank's shard, drawn by the scoring pass itself (uniform sampler)
+    return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, nullptr, B, K1, D,
+                             n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all,
+                             y_all, partial, result, reduced, workspace, workspace_bytes, variant, stream, 2, seed, offset,
+                             row_end - row_begin, row_begin);
   if (idx == nullptr) {  // K1-1 negatives drawn inside this rank's shard; column 0 stays the global positive index
     if (!idx_scratch) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward_sharded: contrast_idx is NULL and so is idx_scratch");
     rc = crdpn_alias_draw_contrast_local(alias_prob, alias_alias, row_end - row_begin, row_begin, y_all, B, K1, seed, offset,
@@ -99,5 +111,6 @@ extern "C" int crdpn_crd_loss_forward_sharded(
   }
   return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, idx, B, K1, D, n_data,
                            k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all, y_all,
-                           partial, result, reduced, workspace, workspace_bytes, variant, stream);
+                           partial, result, reduced, workspace, workspace_bytes, variant & ~0x1000, stream,
+                           (contrast_idx != nullptr && (variant & 0x1000)) ? 1 : 0);
 }

@@ -371,21 +371,29 @@ class _ShardedCRDLossFunction(torch.autograd.Function):
         f_red = f_all + 4 * BD
         o_red = base + 4 * f_red
         y_all = torch.empty(B, dtype=torch.int64, device=dev)
+        m1, m2, stride, dt = mem._banks()
+        variant = mem._step_variant(B, K1, D)
+        ws = mem._workspace(B, K1, D, dev, variant)
         if contrast_idx is not None:
             mem._check_device(contrast_idx, "contrast_idx")
-            contrast_idx = contrast_idx.contiguous().to(torch.int64)
+            if contrast_idx.dtype == torch.int32 and not (variant & mem.STREAM):
+                variant |= mem.IDX32                      # consumed as it is: half the bytes to copy and scan
+            else:
+                contrast_idx = contrast_idx.to(torch.int64)
+            contrast_idx = contrast_idx.contiguous()
             if contrast_idx.shape != (B, K1):
                 raise RuntimeError(f"contrast_idx must have shape [B, K+1] = {(B, K1)}, got {tuple(contrast_idx.shape)}")
             cidx_ptr, scratch_ptr, tables, seed, offset = contrast_idx.data_ptr(), None, (None, None), 0, 0
         else:
             smp = mem._ensure_local_sampler(dev)
-            scratch = mem._idx_scratch
-            if scratch is None or scratch.numel() != B * K1 or scratch.device != dev:
-                scratch = mem._idx_scratch = torch.empty(B * K1, dtype=torch.int64, device=dev)
-            cidx_ptr, scratch_ptr, tables, seed, offset = None, scratch.data_ptr(), smp.table_ptrs(), smp.seed, smp.offset
-        m1, m2, stride, dt = mem._banks()
-        variant = mem._step_variant(B, K1, D)
-        ws = mem._workspace(B, K1, D, dev, variant)
+            if smp.uniform and not (variant & mem.STREAM):
+                scratch_ptr = None                        # the scoring pass draws the in-shard negatives itself
+            else:
+                scratch = mem._idx_scratch
+                if scratch is None or scratch.numel() != B * K1 or scratch.device != dev:
+                    scratch = mem._idx_scratch = torch.empty(B * K1, dtype=torch.int64, device=dev)
+                scratch_ptr = scratch.data_ptr()
+            cidx_ptr, tables, seed, offset = None, smp.table_ptrs(), smp.seed, smp.offset
         with _native.on_device(dev):
             rc = _native.lib().crdpn_crd_loss_forward_sharded(
                 xs.data_ptr(), xs.shape[1], Wsc.data_ptr(), bsc.data_ptr(), xt.data_ptr(), xt.shape[1], Wtc.data_ptr(), btc.data_ptr(),

@@ -125,6 +125,24 @@ int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
                    double* result, float* grad_v1, float* grad_v2,
                    void* workspace, size_t workspace_bytes, int variant, void* stream);
 
+/* Where the contrast indices of a step may come from besides an int64 list:
+ *   variant | 0x1000 (crdpn_crd_step, crdpn_crd_step_sharded): contrast_idx points at an INT32 [B,K1] list -- half the
+ *     bytes to copy from the host and to scan (row indices of any bank that fits one GPU are < 2^31).
+ *   crdpn_crd_step_drawn: no list at all -- the scoring pass draws entry (b, k) itself as
+ *     draw_base + floor(u64(Philox4x32-10 block (seed, offset + b*K1 + k)) * draw_n / 2^64), column 0 = y[b]: bit for bit the
+ *     list crdpn_alias_draw_contrast / _local writes for UNIFORM tables (prob = alias = NULL), i.e. the published
+ *     ContrastMemory.forward(idx=None) with its all-ones unigram table, without 16 bytes of index traffic per entry and
+ *     without the draw launch.  crdpn_crd_loss_forward(_sharded) take this route when contrast_idx, alias_prob and
+ *     alias_alias are all NULL.  Not available for the bank-streaming kernels (variant | 0x200). */
+int crdpn_crd_step_drawn(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,
+                         const float* v1, const float* v2, const int64_t* y,
+                         int64_t B, int64_t K1, int64_t D, int64_t n_data, int64_t k_total,
+                         int64_t row_begin, int64_t row_end,
+                         float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
+                         uint64_t seed, uint64_t offset, int64_t draw_n, int64_t draw_base,
+                         double* result, float* grad_v1, float* grad_v2,
+                         void* workspace, size_t workspace_bytes, int variant, void* stream);
+
 /* Bank-STREAMING formulation of the same step (variant | 0x200 in crdpn_crd_step / crdpn_crd_loss_forward): the samples
  * are bucketed by bank tile and every resident tile passes through shared memory exactly once, so a row that is sampled
  * several times per step (B*K1 > resident rows) is read from HBM once.

@@ -514,3 +514,39 @@ def test_headline_config_properties_full_size(pkg, oracle, cuda):
     idx_p[:, 1:] = idx[:, perm]
     p = _score(pkg, cuda, bank, v1, v2, idx_p, N, T, Z1, Z2, want_out=False)
     assert _rel(p["res"][0], full["res"][0]) < 1e-6 and _rel(p["g1"], full["g1"]) < 1e-5 and _rel(p["g2"], full["g2"]) < 1e-5
+
+
+def test_int32_contrast_idx_and_in_kernel_draw_are_bit_identical_to_the_int64_list(pkg, cuda):
+    """Three sources of the same contrast indices -- an int64 list, the same list as int32, and no list at all (the scoring
+    pass draws the entries itself from the sampler's Philox stream) -- must give the same bits: loss, gradients, bank rows."""
+    opt = type("Opt", (), dict(s_dim=64, t_dim=48, feat_dim=128, n_data=5000, nce_k=1500, nce_t=0.07, nce_m=0.5))()
+    g = torch.Generator().manual_seed(9)
+    B = 23
+    f_s, f_t = torch.randn(B, 64, generator=g).to(cuda), torch.randn(B, 48, generator=g).to(cuda)
+    y = torch.randperm(5000, generator=g)[:B].to(cuda)
+    mods = []
+    for _ in range(3):
+        torch.manual_seed(4)
+        mods.append(pkg.CRDLoss(opt, seed=1234).to(cuda))
+    outs = []
+    for mode, m in zip(("drawn", "int64", "int32"), mods):
+        rows = []
+        for step in range(3):   # step 0 freezes Z (general path), steps 1-2 run the one-call path
+            if mode == "drawn":
+                cidx = None
+            else:
+                smp = pkg.AliasMethod(torch.ones(5000), seed=1234).cuda()
+                smp.offset = step * B * 1501
+                cidx = smp.draw_contrast(y, 1501)
+                if mode == "int32":
+                    cidx = cidx.to(torch.int32)
+            fs = f_s.clone().requires_grad_()
+            loss = m(fs, f_t, y, cidx)
+            loss.backward()
+            rows.append((loss.detach().clone(), fs.grad.clone(), m.embed_t.linear.weight.grad.clone(), m.contrast.memory_v1.clone()))
+            m.zero_grad()
+        outs.append(rows)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            for ta, tb in zip(a, b):
+                assert torch.equal(ta, tb)
