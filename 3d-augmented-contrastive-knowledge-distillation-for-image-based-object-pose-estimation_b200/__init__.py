@@ -30,5 +30,7 @@ from . import kd_losses  # noqa: F401,E402
 from .kd_losses import (CELoss, DeltaLoss, TemperatureScaledKLDivLoss, calculate_kd_loss_new, infoNCE_KD,  # noqa: F401,E402
                         poseNCE_KD, student_kd_step_loss)
 
-__all__ += ["ShapeEncoderPC", "PointCloudSampler", "FrozenPoseTail", "CELoss", "DeltaLoss", "TemperatureScaledKLDivLoss", "calculate_kd_loss_new", "infoNCE_KD",
+from .pipeline import StepPipeline  # noqa: F401,E402
+
+__all__ += ["StepPipeline", "ShapeEncoderPC", "PointCloudSampler", "FrozenPoseTail", "CELoss", "DeltaLoss", "TemperatureScaledKLDivLoss", "calculate_kd_loss_new", "infoNCE_KD",
             "poseNCE_KD", "student_kd_step_loss"]

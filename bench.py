@@ -121,7 +121,7 @@ def make_opt(c):
 
 
 def time_crd_resident(pkg, torch, dev, c, steps, warmup, flush_l2=False, variant=0, interleave=True, dist=None,
-                      bank_dtype=None, streaming=None):
+                      bank_dtype=None, streaming=None, dup=1):
     """Device-resident inputs; returns dict(total_ms, kernel_ms_avg, launches)."""
     torch.manual_seed(SEED)
     kw = {} if bank_dtype is None else {"bank_dtype": bank_dtype}
@@ -129,6 +129,9 @@ def time_crd_resident(pkg, torch, dev, c, steps, warmup, flush_l2=False, variant
     crit.contrast.variant = variant
     crit.contrast.streaming = streaming   # None: the module's own choice (bank-streaming tensor-core kernel for bf16 banks)
     f_s, f_t, y, cidx = [t.to(dev) for t in synth_inputs(c, torch)]
+    if dup > 1:   # every idx `dup` times (the KD loop feeds 3 views of each sample)
+        y = y[:c["B"] // dup].repeat(dup)
+        cidx[:, 0] = y
     with torch.no_grad():
         v1 = crit.embed_s(f_s).contiguous()
         v2 = crit.embed_t(f_t).contiguous()
@@ -214,41 +217,61 @@ def time_shard_emulation(pkg, torch, dev, c, steps, warmup, shards):
             "score_kernel_ms": tot.value / max(n.value, 1)}
 
 
-def time_crd_e2e(pkg, torch, dev, c, steps, warmup, host_contrast_idx=False):
-    """Public API, pinned HOST inputs: H2D of (f_s, f_t, idx[, contrast_idx]) + forward + backward + D2H of the loss.
+def time_crd_e2e(pkg, torch, dev, c, steps, warmup, host_contrast_idx=False, idx_dtype=None, pipelined=True):
+    """Public API, pinned HOST inputs every step: H2D of (f_s, f_t, idx[, contrast_idx]) + CRDLoss forward + backward +
+    a D2H read of the loss.
 
-    host_contrast_idx=False: CRDLoss(f_s, f_t, idx) -- the K negatives are drawn on the GPU by the alias sampler
-    (the published module's own default when the dataset supplies no contrast_idx).  True: the [B, K+1] int64 index
-    list comes from the host every step (24.7 MB at the headline config)."""
+    host_contrast_idx=False: CRDLoss(f_s, f_t, idx) -- the K negatives are drawn on the GPU by the module's sampler (the
+    published module's own default when the dataset supplies no contrast_idx).  True: the [B, K+1] index list comes from
+    the host every step (int64: 24.7 MB at the headline config; idx_dtype=torch.int32: half of that).
+    pipelined=True: the step loop a throughput-minded user writes with ``StepPipeline`` -- the NEXT batch's copies are
+    staged on a copy stream while this step runs, and the loss of step i is read after step i+1 has been launched (every
+    loss is read, one step late).  pipelined=False: the reference loop verbatim (copy, forward, backward, loss.item())."""
     torch.manual_seed(SEED)
     crit = pkg.CRDLoss(make_opt(c)).to(dev)
-    host = synth_inputs(c, torch, pin=True)
-    if not host_contrast_idx:
-        host = host[:3]
+    host = synth_inputs(c, torch, pin=False)
+    if idx_dtype is not None:
+        host[3] = host[3].to(idx_dtype)
+    host = [t.pin_memory() for t in (host if host_contrast_idx else host[:3])]
     h2d = sum(t.numel() * t.element_size() for t in host)
 
-    def step():
-        dev_in = [t.to(dev, non_blocking=True) for t in host]
+    def fwd_bwd(dev_in):
         f_s, f_t, y = dev_in[:3]
         cidx = dev_in[3] if host_contrast_idx else None
         f_s.requires_grad_()
         loss = crit(f_s, f_t, y, cidx)
         crit.zero_grad(set_to_none=True)  # the reference's order: forward, zero_grad, backward (base_class.py:387-396)
         loss.backward()
-        return loss.item()  # D2H read of the step's result
+        return loss
+
+    def strict_step():
+        return fwd_bwd([t.to(dev, non_blocking=True) for t in host]).item()  # D2H read of the step's result
 
     for _ in range(max(warmup, 1)):
-        step()
+        strict_step()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        step()
+    if pipelined:
+        pipe = pkg.StepPipeline(dev)
+        pipe.stage(*host)
+        for i in range(steps):
+            dev_in = pipe.take()
+            if i + 1 < steps:
+                pipe.stage(*host)          # next step's H2D overlaps this step's kernels
+            pipe.publish(fwd_bwd(dev_in))  # async D2H of this step's loss
+            if pipe.pending() > 1:
+                pipe.collect()             # loss of the previous step
+        while pipe.pending():
+            pipe.collect()
+    else:
+        for _ in range(steps):
+            strict_step()
     e1.record()
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
-    ms = max(e0.elapsed_time(e1), wall)  # host-side stalls (the .item() sync) count
+    ms = max(e0.elapsed_time(e1), wall)  # host-side stalls count
     return dict(ms_per_step=ms / steps, h2d=h2d, d2h=4)
 
 
@@ -283,14 +306,15 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     c = HEADLINE
-    sample_B = int(os.environ.get("CRDPN_REF_SAMPLE_B", "8"))
+    sample_B = int(os.environ.get("CRDPN_REF_SAMPLE_B", str(c["B"])))   # default: the WHOLE batch, i.e. the same config
     val, dt, b = cpu_stock_crd(c, torch, args.steps, args.warmup, sample_B=sample_B)
-    sample = f"{b} of {c['B']} anchors per step (all K+1={c['K']+1} entries each, full N), fwd+bwd+update"
+    sample = (f"all {b} anchors per step" if b == c["B"] else f"{b} of {c['B']} anchors per step") + \
+             f" (all K+1={c['K']+1} entries each, full N), fwd+bwd+update"
     line = {
         "impl": "reference", "metric": "crd_negatives_scored_per_sec", "value": val, "unit": "scores/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(c), "sample": sample},
+        "config": {"workload": workload_name(c), "B": b, "D": c["D"], "K": c["K"], "N": c["N"], "banks": 2, "sample": sample},
         "cpu_baseline": {"value": val, "unit": "scores/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -338,8 +362,12 @@ def run_own(args):
         print_line({"quick": True, "ms_per_step": ms_step, "value": value, "kernel_ms": r["kernel_ms_avg"],
                     "achieved_gbs": achieved})
         return
-    e2e = time_crd_e2e(pkg, torch, dev, c, max(args.steps // 4, 5), args.warmup)
-    e2e_h = time_crd_e2e(pkg, torch, dev, c, max(args.steps // 4, 5), args.warmup, host_contrast_idx=True)
+    esteps = max(args.steps, 20)
+    e2e = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup)
+    e2e_strict = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, pipelined=False)
+    e2e_h = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True)
+    e2e_h32 = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True, idx_dtype=torch.int32)
+    e2e_h_strict = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True, pipelined=False)
 
     also = {}
     r0 = time_crd_resident(pkg, torch, dev, CONFIG0, args.steps, args.warmup, flush_l2=True)
@@ -354,6 +382,14 @@ def run_own(args):
         "value": scores_per_step(CONFIG0) / (r0w["total_ms"] / args.steps * 1e-3), "unit": "scores/s",
         "kernel_ms": r0w["kernel_ms_avg"], "achieved_gbs": algorithmic_bytes(CONFIG0) / (r0w["kernel_ms_avg"] * 1e-3) / 1e9,
         "note": "rows served from L2 (each row reused ~8x per step): above-HBM figure is expected"}
+    # SURVEY 8(d) config-1 variant at the headline size: the KD loop's real batch of 138 = 46 x 3 views, every idx three times
+    c138 = dict(c, B=138)
+    r138 = time_crd_resident(pkg, torch, dev, c138, max(args.steps // 2, 10), args.warmup, dup=3)
+    also["B138_duplicate_idx"] = {
+        "workload": workload_name(c138) + "_idx_x3", "ms_per_step": r138["total_ms"] / max(args.steps // 2, 10),
+        "value": scores_per_step(c138) / (r138["total_ms"] / max(args.steps // 2, 10) * 1e-3), "unit": "scores/s",
+        "kernel_ms": r138["kernel_ms_avg"], "achieved_gbs": algorithmic_bytes(c138) / (r138["kernel_ms_avg"] * 1e-3) / 1e9,
+        "note": "138 anchors, 46 distinct bank rows each listed 3x (last occurrence wins the momentum update)"}
     rb = time_crd_resident(pkg, torch, dev, c, args.steps, args.warmup, bank_dtype=torch.bfloat16)
     rbg = time_crd_resident(pkg, torch, dev, c, args.steps, args.warmup, bank_dtype=torch.bfloat16, streaming=False)
     also["headline_bf16_banks"] = {
@@ -390,8 +426,8 @@ def run_own(args):
     # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_B = int(os.environ.get("CRDPN_REF_SAMPLE_B", "8"))
-    cval, cdt, cb = cpu_stock_crd(c, torch, 2, 1, sample_B=sample_B)
+    sample_B = int(os.environ.get("CRDPN_REF_SAMPLE_B", str(c["B"])))
+    cval, cdt, cb = cpu_stock_crd(c, torch, 3, 1, sample_B=sample_B)
 
     line = {
         "metric": "crd_negatives_scored_per_sec", "value": value, "unit": "scores/s",
@@ -404,13 +440,21 @@ def run_own(args):
                      "traffic": None, "peak_kind": peak_kind, "kernel": "crd_score_kernel",
                      "kernel_ms": r["kernel_ms_avg"], "algorithmic_bytes": abytes},
         "cpu_baseline": {"value": cval, "unit": "scores/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{cb} of {c['B']} anchors per step, full K and N, fwd+bwd+update, 2 steps ({cdt:.2f} s/step)"},
+                         "sample": f"{cb} of {c['B']} anchors per step, full K and N, fwd+bwd+update, 3 steps ({cdt:.2f} s/step)"},
         "e2e": {"value": scores_per_step(c) / (e2e["ms_per_step"] * 1e-3), "unit": "scores/s",
                 "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms_per_step"],
-                "api": "CRDLoss(f_s, f_t, idx).backward(): pinned host features + indices in, negatives drawn on the GPU "
-                       "(alias sampler), loss.item() out",
+                "api": "CRDLoss(f_s, f_t, idx).backward() every step: pinned host features + indices in (next batch staged on a "
+                       "copy stream by StepPipeline), negatives drawn on the GPU inside the scoring pass, every step's loss read "
+                       "back (one step late, after the next step has been launched)",
+                "sync_each_step": {"value": scores_per_step(c) / (e2e_strict["ms_per_step"] * 1e-3), "unit": "scores/s",
+                                   "ms_per_step": e2e_strict["ms_per_step"],
+                                   "note": "the reference loop verbatim: copy, forward, backward, loss.item() before the next copy"},
                 "with_host_contrast_idx": {"value": scores_per_step(c) / (e2e_h["ms_per_step"] * 1e-3), "unit": "scores/s",
-                                           "h2d_bytes_per_step": e2e_h["h2d"], "ms_per_step": e2e_h["ms_per_step"]}},
+                                           "h2d_bytes_per_step": e2e_h["h2d"], "ms_per_step": e2e_h["ms_per_step"],
+                                           "int32_list": {"value": scores_per_step(c) / (e2e_h32["ms_per_step"] * 1e-3),
+                                                          "h2d_bytes_per_step": e2e_h32["h2d"], "ms_per_step": e2e_h32["ms_per_step"]},
+                                           "sync_each_step": {"value": scores_per_step(c) / (e2e_h_strict["ms_per_step"] * 1e-3),
+                                                              "ms_per_step": e2e_h_strict["ms_per_step"]}}},
         "gpu_launches": r["launches"],
         "clocks": clocks,
         "also": also,
@@ -418,7 +462,9 @@ def run_own(args):
     traffic = ROOT / "profiles" / "traffic.json"
     if traffic.exists():
         try:
-            line["roofline"]["traffic"] = json.loads(traffic.read_text()).get("crd_score_kernel_bytes_per_launch")
+            tj = json.loads(traffic.read_text())
+            line["roofline"]["traffic"] = tj.get("crd_score_kernel_bytes_per_launch")
+            line["roofline"]["traffic_source"] = "static: " + tj.get("source", "profiles/traffic.json (ncu --set full capture, committed)")
         except Exception:
             pass
     print_line(line)

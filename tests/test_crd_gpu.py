@@ -550,3 +550,41 @@ def test_int32_contrast_idx_and_in_kernel_draw_are_bit_identical_to_the_int64_li
         for a, b in zip(outs[0], other):
             for ta, tb in zip(a, b):
                 assert torch.equal(ta, tb)
+
+
+def test_step_pipeline_reads_every_loss_and_changes_no_bits(pkg, cuda):
+    """StepPipeline (staged H2D copies on a copy stream, losses read one step late) against the reference loop verbatim
+    (copy, forward, backward, loss.item()): the same losses, bit for bit, and the same bank contents afterwards."""
+    opt = type("Opt", (), dict(s_dim=64, t_dim=48, feat_dim=128, n_data=4000, nce_k=1000, nce_t=0.07, nce_m=0.5))()
+    g = torch.Generator().manual_seed(3)
+    B, steps = 16, 6
+    batches = [(torch.randn(B, 64, generator=g).pin_memory(), torch.randn(B, 48, generator=g).pin_memory(),
+                torch.randperm(4000, generator=g)[:B].pin_memory()) for _ in range(steps)]
+    mods = []
+    for _ in range(2):
+        torch.manual_seed(8)
+        mods.append(pkg.CRDLoss(opt, seed=99).to(cuda))
+
+    def fwd_bwd(m, dev_in):
+        f_s, f_t, y = dev_in
+        f_s.requires_grad_()
+        loss = m(f_s, f_t, y)
+        m.zero_grad(set_to_none=True)
+        loss.backward()
+        return loss
+
+    strict = [fwd_bwd(mods[0], [t.to(cuda, non_blocking=True) for t in b]).item() for b in batches]
+    pipe, got = pkg.StepPipeline(cuda), []
+    pipe.stage(*batches[0])
+    for i in range(steps):
+        dev_in = pipe.take()
+        if i + 1 < steps:
+            pipe.stage(*batches[i + 1])
+        pipe.publish(fwd_bwd(mods[1], dev_in))
+        if pipe.pending() > 1:
+            got.append(pipe.collect())
+    while pipe.pending():
+        got.append(pipe.collect())
+    assert got == strict
+    assert torch.equal(mods[0].contrast.memory_v1, mods[1].contrast.memory_v1)
+    assert torch.equal(mods[0].contrast.memory_v2, mods[1].contrast.memory_v2)
