@@ -63,12 +63,15 @@ struct ScoreParams {
   int maxseg;
   unsigned int* ticket;
   long long nw;         // warps the pair space is cut over (<= resident warps; the rest idle)
+  int cta_reduce;       // 1: the 8 warps of a CTA fold their partials in shared memory (fixed order) and the CTA writes
+                        //    at most two slots (its range covers <= 2 anchors): 8x fewer partials for the reduction kernel
 };
 
 struct FinalizeParams {
   const float* slots;
   int maxseg;
   long long NW;
+  int group;            // warps per slot-writing unit: 1 (every warp writes its own slots) or kWarps (ScoreParams::cta_reduce)
   int B, K1, D;
   int full;
   float* grad_v1;
@@ -152,6 +155,10 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
   static_assert(R * U + 32 <= kQueueCap, "queue too small");
 
   __shared__ int2 queue_smem[kWarps][kQueueCap];
+  constexpr int kD = NV * LPR;                      // feature dimension of this instantiation
+  constexpr int kSW = 2 * kD + kSlotExtra;          // floats per slot
+  constexpr bool kCanReduce = kD <= 256;            // [8 warps][2 anchors][slot] must fit static shared memory
+  __shared__ __align__(16) float red_smem[kCanReduce ? kWarps * 2 * kSW : 4];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / LPR, j = lane % LPR;
@@ -159,9 +166,18 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
   const long long gw = (long long)blockIdx.x * kWarps + warp;
   const long long P = (long long)p.B * p.K1;
   if (blockIdx.x == 0 && threadIdx.x == 0) *p.ticket = 0u;  // finalize runs after us in stream order
-  if (gw >= NW) return;
-  long long lo = P * gw / NW;
-  const long long hi = P * (gw + 1) / NW;
+  const bool cta_red = kCanReduce && p.cta_reduce != 0;
+  int b_first_cta = 0;
+  if (cta_red) {
+    for (int i = threadIdx.x; i < kWarps * 2 * kSW; i += kThreads) red_smem[i] = 0.f;
+    const long long w0 = (long long)blockIdx.x * kWarps;
+    b_first_cta = (int)((P * (w0 < NW ? w0 : NW) / NW) / p.K1);
+    __syncthreads();
+  } else if (gw >= NW) {
+    return;
+  }
+  long long lo = gw < NW ? P * gw / NW : 0;
+  const long long hi = gw < NW ? P * (gw + 1) / NW : 0;
   int2* q = queue_smem[warp];
   const bool store_out = (p.out_v1 != nullptr);
   int seg = 0;
@@ -283,30 +299,43 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       return p.draw_base + (long long)__umul64hi(bits, (unsigned long long)p.draw_n);
     };
     long long base = lo;
-    long long r_next = (base + lane < seg_hi) ? fetch_idx(base + lane) : -1;
+    // the index loads run kPF scan steps (32 entries each) ahead of their use: on a shard that owns 1/8 of the rows a scan
+    // step yields ~4 survivors, so the scan is a chain of dependent index loads unless several of them are in flight
+    constexpr int kPF = 4;
+    auto fetch_local = [&](long long pos) -> int {   // local row of the entry, -1 when another shard owns it (rows < 2^31)
+      const long long r = fetch_idx(pos);
+      return (r >= p.row_begin && r < p.row_end) ? (int)(r - p.row_begin) : -1;
+    };
+    int rr[kPF];
+#pragma unroll
+    for (int i = 0; i < kPF; ++i) rr[i] = (base + 32 * i + lane < seg_hi) ? fetch_local(base + 32 * i + lane) : -1;
     while (base < seg_hi) {
-      const long long r = r_next;
-      const long long pidx = base + lane;
-      const long long nbase = base + 32;
-      r_next = (nbase + lane < seg_hi) ? fetch_idx(nbase + lane) : -1;  // prefetch the next 32 indices
-      const bool inrange = pidx < seg_hi;
-      const bool valid = inrange && r >= p.row_begin && r < p.row_end;
-      const unsigned mask = __ballot_sync(kFull, valid);
-      if (valid) {
-        const int slot = (qtail + __popc(mask & ((1u << lane) - 1u))) & (kQueueCap - 1);
-        q[slot] = make_int2((int)(r - p.row_begin), (int)(pidx - lo));
-      } else if (inrange && store_out) {
-        p.out_v1[pidx] = 0.f;
-        p.out_v2[pidx] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kPF; ++i) {
+        if (base >= seg_hi) break;
+        const int r = rr[i];
+        const long long pidx = base + lane;
+        const long long ppos = base + 32 * kPF + lane;
+        rr[i] = (ppos < seg_hi) ? fetch_local(ppos) : -1;
+        const bool inrange = pidx < seg_hi;
+        const bool valid = r >= 0;
+        const unsigned mask = __ballot_sync(kFull, valid);
+        if (valid) {
+          const int slot = (qtail + __popc(mask & ((1u << lane) - 1u))) & (kQueueCap - 1);
+          q[slot] = make_int2(r, (int)(pidx - lo));
+        } else if (inrange && store_out) {
+          p.out_v1[pidx] = 0.f;
+          p.out_v2[pidx] = 0.f;
+        }
+        qtail += __popc(mask);
+        __syncwarp();
+        while (qtail - qhead >= R * U) {
+          consume(R * U);
+          qhead += R * U;
+        }
+        __syncwarp();
+        base += 32;
       }
-      qtail += __popc(mask);
-      __syncwarp();
-      while (qtail - qhead >= R * U) {
-        consume(R * U);
-        qhead += R * U;
-      }
-      __syncwarp();
-      base = nbase;
     }
     while (qtail - qhead > 0) {
       const int avail = qtail - qhead;
@@ -329,7 +358,8 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       se2 += __shfl_xor_sync(kFull, se2, off);
       cnt += __shfl_xor_sync(kFull, cnt, off);
     }
-    float* slot = p.slots + ((long long)gw * p.maxseg + seg) * (2 * p.D + kSlotExtra);
+    float* slot = cta_red ? red_smem + (warp * 2 + (b - b_first_cta)) * kSW
+                          : p.slots + ((long long)gw * p.maxseg + seg) * (2 * p.D + kSlotExtra);
     if (g == 0) {
       if constexpr (FULL) {
 #pragma unroll
@@ -352,6 +382,18 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
     lo = seg_hi;
     ++seg;
   }
+  if (cta_red) {
+    // fold the 8 warps' partials in fixed order (bit-reproducible) and write this CTA's two slots
+    __syncthreads();
+    float* out = p.slots + (long long)blockIdx.x * 2 * kSW;
+    for (int i = threadIdx.x; i < 2 * kSW; i += kThreads) {
+      const int sg = i / kSW, col = i - sg * kSW;
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) acc += red_smem[(w * 2 + sg) * kSW + col];
+      out[i] = acc;
+    }
+  }
 }
 
 // One CTA per anchor: fixed-order sum of the warp partials that intersect the anchor's K1 pairs; the last
@@ -371,14 +413,22 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
     s_epoch = *reinterpret_cast<volatile uint32_t*>(f.peers.buf[f.rank] + f.off_ctl + 8) + 1u;
   const long long P = (long long)f.B * f.K1;
   const long long p0 = (long long)b * f.K1, p1 = p0 + f.K1;
+  // slot-writing units: single warps (group = 1) or whole CTAs of `group` warps; unit u covers pairs [bnd(u), bnd(u+1))
+  const long long G = f.group, NU = (f.NW + G - 1) / G;
+  auto bnd = [&](long long u) -> long long {
+    const long long w = u * G < f.NW ? u * G : f.NW;
+    return (P * w) / f.NW;
+  };
   if (threadIdx.x == 0) {
-    long long first = (p0 * f.NW) / P;
-    while (first > 0 && (P * first) / f.NW > p0) --first;
-    while (first + 1 < f.NW && (P * (first + 1)) / f.NW <= p0) ++first;
-    long long last = (p1 * f.NW + P - 1) / P - 1;  // largest w with floor(P*w/NW) < p1
-    if (last >= f.NW) last = f.NW - 1;
-    while (last + 1 < f.NW && (P * (last + 1)) / f.NW < p1) ++last;
-    while (last > first && (P * last) / f.NW >= p1) --last;
+    long long first = ((p0 * f.NW) / P) / G;
+    if (first >= NU) first = NU - 1;
+    while (first > 0 && bnd(first) > p0) --first;
+    while (first + 1 < NU && bnd(first + 1) <= p0) ++first;
+    long long last = ((p1 * f.NW + P - 1) / P - 1) / G;  // near the largest u with bnd(u) < p1
+    if (last >= NU) last = NU - 1;
+    if (last < first) last = first;
+    while (last + 1 < NU && bnd(last + 1) < p1) ++last;
+    while (last > first && bnd(last) >= p1) --last;
     s_first = first;
     s_last = last;
   }
@@ -395,8 +445,8 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
     const int n = (int)((last - chunk + 1 < kFinalizeList) ? (last - chunk + 1) : kFinalizeList);
     for (int i = threadIdx.x; i < n; i += kFinalizeThreads) {
       const long long w = chunk + i;
-      const long long lo = (P * w) / f.NW;
-      const long long hi = (P * (w + 1)) / f.NW;
+      const long long lo = bnd(w);
+      const long long hi = bnd(w + 1);
       const bool valid = hi > p0 && hi > lo && lo < p1;
       s_off[i] = valid ? (w * f.maxseg + (b - (int)(lo / f.K1))) * (long long)slot_w : -1;
     }
@@ -781,7 +831,8 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   // warp (B*S <= resident warps), so that slice s of EVERY anchor starts at the same time; with row-sorted lists the
   // warps of a slice then walk the same band of bank rows together and each row comes from HBM once.
   const bool aligned = (variant & 0x100) != 0;
-  variant &= 0xff;
+  const bool no_cta_fold = (variant & 0x80) != 0;   // bit 7: keep one slot per (warp, anchor) (A/B timing of the CTA-level fold)
+  variant &= 0x7f;
   if (!pick_variant(bank_dtype, (int)D, variant, &var))
     return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_score: no kernel for this (dtype, feat_dim, variant); feat_dim in {32,64,128,256,512}");
 
@@ -794,6 +845,9 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   long long NW = (long long)grid * kWarps;
   if (aligned && NW >= B) NW = (NW / B) * B;
   const long long P = B * K1;
+  // CTA-level fold of the warp partials: possible when a CTA's range of pairs spans at most two anchors and its slots fit
+  // static shared memory; not for the per-entry outputs mode (kept on the original layout) or the aligned partition
+  const bool cta_reduce = !aligned && D <= 256 && out_v1 == nullptr && (P * kWarps + NW - 1) / NW + 1 <= K1 && !no_cta_fold;
   const size_t need = workspace_bytes_for(B, K1, D, NW);
   if (workspace_bytes < need) return fail(CRDPN_E_WORKSPACE, "crdpn_crd_score: workspace too small");
 
@@ -830,9 +884,10 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.inv_BT = (float)(1.0 / ((double)B * (double)T));
   sp.out_v1 = out_v1; sp.out_v2 = out_v2;
   sp.slots = slots;
-  sp.maxseg = maxseg_for(P, NW, K1);
+  sp.maxseg = cta_reduce ? 2 : maxseg_for(P, NW, K1);
   sp.ticket = ticket;
   sp.nw = NW;
+  sp.cta_reduce = cta_reduce ? 1 : 0;
 
   cudaStream_t st = (cudaStream_t)stream;
   {
@@ -842,7 +897,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   CRDPN_LAUNCH_CHECK("crd_score_kernel");
 
   FinalizeParams fp;
-  fp.slots = slots; fp.maxseg = sp.maxseg; fp.NW = NW;
+  fp.slots = slots; fp.maxseg = sp.maxseg; fp.NW = NW; fp.group = cta_reduce ? kWarps : 1;
   fp.B = (int)B; fp.K1 = (int)K1; fp.D = (int)D; fp.full = full ? 1 : 0;
   fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2;
   fp.anchor_part = anchor_part; fp.result = result; fp.ticket = ticket;

@@ -130,18 +130,23 @@ def bench_pointnet(pkg, torch, dev, args, tf_peak, peak_kind, B=160, P=2500, F=1
         enc(x_host.to(dev, non_blocking=True)).cpu()
     e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / steps
     pipe = pkg.StepPipeline(dev)
+
+    def loop(n):
+        pipe.stage(x_host)
+        for i in range(n):
+            (xd,) = pipe.take()
+            if i + 1 < n:
+                pipe.stage(x_host)
+            pipe.publish(enc(xd))
+            if pipe.pending() > 1:
+                pipe.collect()
+        while pipe.pending():
+            pipe.collect()
+
+    loop(4)   # one-time costs (streams, pinned result slots, device input slots) stay outside the timed region
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pipe.stage(x_host)
-    for i in range(steps):
-        (xd,) = pipe.take()
-        if i + 1 < steps:
-            pipe.stage(x_host)
-        pipe.publish(enc(xd))
-        if pipe.pending() > 1:
-            pipe.collect()
-    while pipe.pending():
-        pipe.collect()
+    loop(steps)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
     tflops = FLOP_PER_POINT * B * P / (kms * 1e-3) / 1e12
