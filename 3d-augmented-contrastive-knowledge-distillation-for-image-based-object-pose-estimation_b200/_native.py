@@ -107,6 +107,7 @@ _SIGNATURES = {
                                             c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "crdpn_p2p_allreduce_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64,
                                         c_void_p]),
+    "crdpn_p2p_allreduce_blocks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p]),
     "crdpn_pointnet_train_ctx_bytes": (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t)]),
     "crdpn_pointnet_forward_train": (c_int, [c_void_p, c_int64, c_int64, c_int64] + [c_void_p] * 21 +
                                      [c_float, c_float, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

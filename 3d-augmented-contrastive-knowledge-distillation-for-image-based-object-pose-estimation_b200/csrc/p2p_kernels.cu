@@ -131,6 +131,71 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const ReduceParams a
   }
 }
 
+
+// In-place sum over the ranks of up to four blocks of float32 / float64 accumulators in ONE launch (the hand-offs of the
+// rank-synchronised PointNet training step).  The payload travels as 32-bit LL words (a double as two); each word -- each
+// PAIR of words of a double -- is owned by one thread, which reads it, pushes it into slot `rank` of every peer, polls the
+// `world` slots of its own buffer and writes the rank-ordered sum back in place: no other thread touches that element, so
+// the update needs no scratch copy, and every rank ends up with identical bits.
+struct BlocksParams {
+  char* ptr[4];
+  int first[4];     // first 32-bit word of block i in the flattened payload
+  int units[4];     // elements of block i
+  int f64[4];
+  int n_blocks, total_units;
+  int rank, world;
+  Peers peers;
+  size_t off_ctl, off_slots, parity_stride, slot_stride;
+  long long timeout;
+};
+
+__global__ void __launch_bounds__(256) p2p_allreduce_blocks_kernel(const BlocksParams a) {
+  char* me = a.peers.buf[a.rank];
+  uint32_t* ctl = reinterpret_cast<uint32_t*>(me + a.off_ctl) + 2;
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(ctl) + 1u;
+  const size_t par = (size_t)(e & 1u) * a.parity_stride + a.off_slots;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < a.total_units; u += gridDim.x * blockDim.x) {
+    int b = 0, base_unit = 0;
+    while (b + 1 < a.n_blocks && u >= base_unit + a.units[b]) { base_unit += a.units[b]; ++b; }
+    const int i = u - base_unit;
+    if (a.f64[b]) {
+      double* p = reinterpret_cast<double*>(a.ptr[b]) + i;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(*p);
+      const size_t w = (size_t)a.first[b] + 2 * (size_t)i;
+      for (int r = 0; r < a.world; ++r) {
+        char* dst = a.peers.buf[r] + par + ((size_t)a.rank * a.slot_stride + w) * 8;
+        ll_store(dst, (uint32_t)bits, e);
+        ll_store(dst + 8, (uint32_t)(bits >> 32), e);
+      }
+      double sum = 0.0;
+      for (int r = 0; r < a.world; ++r) {   // rank order: the same bits on every rank
+        const char* src = me + par + ((size_t)r * a.slot_stride + w) * 8;
+        const unsigned long long lo = ll_load(src, e, a.timeout), hi = ll_load(src + 8, e, a.timeout);
+        const double v = __longlong_as_double((long long)(lo | (hi << 32)));
+        sum = r == 0 ? v : sum + v;
+      }
+      *p = sum;
+    } else {
+      float* p = reinterpret_cast<float*>(a.ptr[b]) + i;
+      const uint32_t bits = __float_as_uint(*p);
+      const size_t w = (size_t)a.first[b] + (size_t)i;
+      for (int r = 0; r < a.world; ++r)
+        ll_store(a.peers.buf[r] + par + ((size_t)a.rank * a.slot_stride + w) * 8, bits, e);
+      float sum = 0.f;
+      for (int r = 0; r < a.world; ++r) {
+        const float v = __uint_as_float(ll_load(me + par + ((size_t)r * a.slot_stride + w) * 8, e, a.timeout));
+        sum = r == 0 ? v : sum + v;
+      }
+      *p = sum;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ctl + 1, 1u) == gridDim.x - 1) { ctl[1] = 0u; *reinterpret_cast<volatile uint32_t*>(ctl) = e; }
+  }
+}
+
 }  // namespace p2p
 }  // namespace crdpn
 
@@ -221,5 +286,38 @@ extern "C" int crdpn_p2p_allreduce_f32(const float* partial, int64_t n_main, con
   a.timeout = p2p::poll_timeout_ticks();
   p2p::p2p_allreduce_kernel<<<world * p2p::kCH, 256, 0, (cudaStream_t)stream>>>(a);
   CRDPN_LAUNCH_CHECK("p2p_allreduce_kernel");
+  return CRDPN_OK;
+}
+
+extern "C" int crdpn_p2p_allreduce_blocks(void* const* block_ptrs_host, const int64_t* counts_host, const int* is_f64_host,
+                                          int n_blocks, void* const* peer_bufs_host, int rank, int world, int64_t Bmax,
+                                          int64_t Dmax, void* stream) {
+  if (!block_ptrs_host || !counts_host || !is_f64_host || n_blocks < 1 || n_blocks > 4)
+    return fail(CRDPN_E_BADARG, "crdpn_p2p_allreduce_blocks: 1..4 blocks");
+  p2p::BlocksParams a;
+  int rc = fill_peers(peer_bufs_host, rank, world, &a.peers);
+  if (rc) return rc;
+  const p2p::Layout L(Bmax, Dmax, world);
+  size_t words = 0;
+  int units = 0;
+  for (int i = 0; i < 4; ++i) { a.ptr[i] = nullptr; a.first[i] = 0; a.units[i] = 0; a.f64[i] = 0; }
+  for (int i = 0; i < n_blocks; ++i) {
+    if (!block_ptrs_host[i] || counts_host[i] <= 0 || counts_host[i] >= (1 << 28)) return fail(CRDPN_E_BADARG, "crdpn_p2p_allreduce_blocks: bad block");
+    if ((uintptr_t)block_ptrs_host[i] & (is_f64_host[i] ? 7 : 3)) return fail(CRDPN_E_ALIGN, "crdpn_p2p_allreduce_blocks: block alignment");
+    a.ptr[i] = (char*)block_ptrs_host[i];
+    a.first[i] = (int)words;
+    a.units[i] = (int)counts_host[i];
+    a.f64[i] = is_f64_host[i] ? 1 : 0;
+    words += (size_t)counts_host[i] * (is_f64_host[i] ? 2 : 1);
+    units += (int)counts_host[i];
+  }
+  if (words > L.slot_words) return fail(CRDPN_E_BADARG, "crdpn_p2p_allreduce_blocks: payload does not fit the exchange buffer");
+  a.n_blocks = n_blocks; a.total_units = units; a.rank = rank; a.world = world;
+  a.off_ctl = L.ctl; a.off_slots = L.slots; a.parity_stride = L.parity_stride; a.slot_stride = L.slot_words;
+  a.timeout = p2p::poll_timeout_ticks();
+  int grid = (units + 255) / 256;
+  if (grid > 148) grid = 148;
+  p2p::p2p_allreduce_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  CRDPN_LAUNCH_CHECK("p2p_allreduce_blocks_kernel");
   return CRDPN_OK;
 }

@@ -224,7 +224,14 @@ int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int 
  *   crdpn_p2p_allreduce_f32:     out[i] = sum over ranks (in rank order: same bits on every rank) of partial[i];
  *                                the payload is n_main floats followed by n_tail doubles (sent as floats: the step's
  *                                8 result scalars), out has n_main + n_tail floats.
+ *   crdpn_p2p_allreduce_blocks:  IN-PLACE sum over ranks (rank order) of up to 4 blocks of float32 / float64 accumulators in
+ *                                one launch (the hand-offs of the rank-synchronised PointNet training step,
+ *                                crdpn_pointnet_sync_blocks); block_ptrs / counts / is_f64 are HOST arrays; the payload
+ *                                (one LL word per float, two per double) must fit a reduction slot of the exchange buffer:
+ *                                2*Bmax*Dmax + 8 + 8*Bmax words.
  * ------------------------------------------------------------------------------------------------- */
+int crdpn_p2p_allreduce_blocks(void* const* block_ptrs_host, const int64_t* counts_host, const int* is_f64_host, int n_blocks,
+                               void* const* peer_bufs_host, int rank, int world, int64_t Bmax, int64_t Dmax, void* stream);
 int crdpn_p2p_buffer_bytes(int64_t Bmax, int64_t Dmax, int world, size_t* bytes);
 int crdpn_p2p_alloc(size_t bytes, void** dev_ptr);
 int crdpn_p2p_free(void* dev_ptr);
