@@ -126,6 +126,18 @@ __device__ __forceinline__ float log1p_pos(float x) {
   return log1pf(x);
 }
 
+// packed pair arithmetic (sm_100 FFMA2: two fp32 FMAs per issue slot): acc.{lo,hi} += a.{lo,hi} * b.{lo,hi}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+  return r;
+}
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float lo2(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi2(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
 template <typename T> struct Unpack;
 template <> struct Unpack<float> {
   static constexpr int VEC = 4;
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
   constexpr int R = 32 / LPR;
   constexpr int NV = VEC * CH;
   constexpr unsigned kFull = 0xffffffffu;
-  static_assert(R * U + 32 <= kQueueCap, "queue too small");
+  static_assert(R * U + 64 <= kQueueCap, "queue too small");
 
   __shared__ int2 queue_smem[kWarps][kQueueCap];
   constexpr int kD = NV * LPR;                      // feature dimension of this instantiation
@@ -200,9 +212,15 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
         v2c[i * VEC + t + 0] = c4.x; v2c[i * VEC + t + 1] = c4.y; v2c[i * VEC + t + 2] = c4.z; v2c[i * VEC + t + 3] = c4.w;
       }
     }
-    float g1[NV], g2[NV];
+    // the per-row arithmetic runs on packed pairs (FFMA2): the kernel issues ~1.2 instructions per cycle and SM at the
+    // headline shape, i.e. it is as close to its issue limit as to the HBM roofline, so halving the FMA count pays
+    unsigned long long v1p[NV / 2], v2p[NV / 2], g1p[NV / 2], g2p[NV / 2];
 #pragma unroll
-    for (int n = 0; n < NV; ++n) { g1[n] = 0.f; g2[n] = 0.f; }
+    for (int n = 0; n < NV / 2; ++n) {
+      v1p[n] = pack2(v1c[2 * n], v1c[2 * n + 1]);
+      v2p[n] = pack2(v2c[2 * n], v2c[2 * n + 1]);
+      g1p[n] = 0ull; g2p[n] = 0ull;
+    }
     float ls = 0.f, lt = 0.f, se1 = 0.f, se2 = 0.f, cnt = 0.f;
 
     int qhead = 0, qtail = 0;
@@ -237,12 +255,15 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
           Unpack<T>::run(w1r[u][i], &w1f[i * VEC]);
           Unpack<T>::run(w2r[u][i], &w2f[i * VEC]);
         }
-        float a1 = 0.f, a2 = 0.f;
+        unsigned long long w1p[NV / 2], w2p[NV / 2], A1 = 0ull, A2 = 0ull;
 #pragma unroll
-        for (int n = 0; n < NV; ++n) {
-          a1 = fmaf(w2f[n], v1c[n], a1);  // out_v1 direction: bank2 row . v1
-          a2 = fmaf(w1f[n], v2c[n], a2);  // out_v2 direction: bank1 row . v2
+        for (int n = 0; n < NV / 2; ++n) {
+          w1p[n] = pack2(w1f[2 * n], w1f[2 * n + 1]);
+          w2p[n] = pack2(w2f[2 * n], w2f[2 * n + 1]);
+          ffma2(A1, w2p[n], v1p[n]);  // out_v1 direction: bank2 row . v1
+          ffma2(A2, w1p[n], v2p[n]);  // out_v2 direction: bank1 row . v2
         }
+        float a1 = lo2(A1) + hi2(A1), a2 = lo2(A2) + hi2(A2);
 #pragma unroll
         for (int off = LPR / 2; off >= 1; off >>= 1) {
           a1 += __shfl_xor_sync(kFull, a1, off);
@@ -271,10 +292,11 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
           }
           ls = fmaf(t1, m, ls);
           lt = fmaf(t2, m, lt);
+          const unsigned long long d1p = pack2(d1, d1), d2p = pack2(d2, d2);
 #pragma unroll
-          for (int n = 0; n < NV; ++n) {
-            g1[n] = fmaf(d1, w2f[n], g1[n]);
-            g2[n] = fmaf(d2, w1f[n], g2[n]);
+          for (int n = 0; n < NV / 2; ++n) {
+            ffma2(g1p[n], d1p, w2p[n]);
+            ffma2(g2p[n], d2p, w1p[n]);
           }
           if (store_out && ev[u] && j == 0) {
             p.out_v1[lo + ent[u].y] = o1;
@@ -299,44 +321,38 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       return p.draw_base + (long long)__umul64hi(bits, (unsigned long long)p.draw_n);
     };
     long long base = lo;
-    // the index loads run kPF scan steps (32 entries each) ahead of their use: on a shard that owns 1/8 of the rows a scan
-    // step yields ~4 survivors, so the scan is a chain of dependent index loads unless several of them are in flight
-    constexpr int kPF = 4;
+    // a scan step covers 64 entries (two per lane: half the loop iterations, ballots and queue bookkeeping per entry -- the
+    // scan is pure instruction overhead on a shard that owns 1/R of the rows); the index loads run two steps ahead of
+    // their use in a rotating register window (not an unrolled loop: the body contains the whole consume step, and four
+    // copies of it made the kernel instruction-fetch bound, 0.43 -> 0.63 ms at the headline shape)
     auto fetch_local = [&](long long pos) -> int {   // local row of the entry, -1 when another shard owns it (rows < 2^31)
+      if (pos >= seg_hi) return -1;
       const long long r = fetch_idx(pos);
       return (r >= p.row_begin && r < p.row_end) ? (int)(r - p.row_begin) : -1;
     };
-    // (a rotating register window, not an unrolled loop: the body contains the whole consume step, and four copies of
-    // it made the kernel instruction-fetch bound -- 0.43 -> 0.63 ms at the headline shape)
-    int rr0 = (base + lane < seg_hi) ? fetch_local(base + lane) : -1;
-    int rr1 = (base + 32 + lane < seg_hi) ? fetch_local(base + 32 + lane) : -1;
-    int rr2 = (base + 64 + lane < seg_hi) ? fetch_local(base + 64 + lane) : -1;
-    int rr3 = (base + 96 + lane < seg_hi) ? fetch_local(base + 96 + lane) : -1;
+    int ra0 = fetch_local(base + 2 * lane), rb0 = fetch_local(base + 2 * lane + 1);
+    int ra1 = fetch_local(base + 64 + 2 * lane), rb1 = fetch_local(base + 64 + 2 * lane + 1);
 #pragma unroll 1
     while (base < seg_hi) {
-      const int r = rr0;
-      const long long pidx = base + lane;
-      const long long ppos = base + 32 * kPF + lane;
-      rr0 = rr1; rr1 = rr2; rr2 = rr3;
-      rr3 = (ppos < seg_hi) ? fetch_local(ppos) : -1;
-      const bool inrange = pidx < seg_hi;
-      const bool valid = r >= 0;
-      const unsigned mask = __ballot_sync(kFull, valid);
-      if (valid) {
-        const int slot = (qtail + __popc(mask & ((1u << lane) - 1u))) & (kQueueCap - 1);
-        q[slot] = make_int2(r, (int)(pidx - lo));
-      } else if (inrange && store_out) {
-        p.out_v1[pidx] = 0.f;
-        p.out_v2[pidx] = 0.f;
-      }
-      qtail += __popc(mask);
+      const int ra = ra0, rb = rb0;
+      const long long pidx = base + 2 * lane;
+      ra0 = ra1; rb0 = rb1;
+      ra1 = fetch_local(pidx + 128);
+      rb1 = fetch_local(pidx + 129);
+      const unsigned ma = __ballot_sync(kFull, ra >= 0), mb = __ballot_sync(kFull, rb >= 0);
+      const unsigned below = (1u << lane) - 1u;
+      if (ra >= 0) q[(qtail + __popc(ma & below)) & (kQueueCap - 1)] = make_int2(ra, (int)(pidx - lo));
+      else if (store_out && pidx < seg_hi) { p.out_v1[pidx] = 0.f; p.out_v2[pidx] = 0.f; }
+      if (rb >= 0) q[(qtail + __popc(ma) + __popc(mb & below)) & (kQueueCap - 1)] = make_int2(rb, (int)(pidx + 1 - lo));
+      else if (store_out && pidx + 1 < seg_hi) { p.out_v1[pidx + 1] = 0.f; p.out_v2[pidx + 1] = 0.f; }
+      qtail += __popc(ma) + __popc(mb);
       __syncwarp();
       while (qtail - qhead >= R * U) {
         consume(R * U);
         qhead += R * U;
       }
       __syncwarp();
-      base += 32;
+      base += 64;
     }
     while (qtail - qhead > 0) {
       const int avail = qtail - qhead;
@@ -346,6 +362,12 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
     __syncwarp();
 
     // ---- flush this (warp, anchor) partial ----
+    float g1[NV], g2[NV];
+#pragma unroll
+    for (int n = 0; n < NV / 2; ++n) {
+      g1[2 * n] = lo2(g1p[n]); g1[2 * n + 1] = hi2(g1p[n]);
+      g2[2 * n] = lo2(g2p[n]); g2[2 * n + 1] = hi2(g2p[n]);
+    }
 #pragma unroll
     for (int off = 16; off >= LPR; off >>= 1) {
 #pragma unroll

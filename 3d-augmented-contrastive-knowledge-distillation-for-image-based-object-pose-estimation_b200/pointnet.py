@@ -52,6 +52,7 @@ class ShapeEncoderPC(nn.Module):
         # "bf16" = one bf16 MMA per product (features within 1e-2, faster, gradients re-routed at near-ties)
         self.train_precision = "fp32"
         self._sync = None   # (process group, world size) once sync_batchnorm() is called
+        self._sync_comm, self._sync_equal, self._sync_px = "dist", False, None
         self._packed = None
         self._packed_key = None
         self._ws = None
@@ -122,16 +123,39 @@ class ShapeEncoderPC(nn.Module):
                 self.conv3.bias, self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias,
                 self.bn3.weight, self.bn3.bias]
 
-    def sync_batchnorm(self, group=None, enabled: bool = True):
+    def sync_batchnorm(self, group=None, enabled: bool = True, comm: str = "dist", equal_batches: bool = False):
         """Train-mode statistics over the clouds of ALL ranks of `group` (SyncBN-style).
 
         Forward and backward then run in phases with a sum over ranks of the per-channel accumulators in between
         (``crdpn_pointnet_sync_blocks``: <= 2F doubles per hand-off, three hand-offs each way).  The parameter gradients
         returned on every rank are the gradients of the SUM over ranks of the local losses and are identical on all
-        ranks -- do not average them again (no DDP wrapper); scale the loss by 1/world_size for a global mean."""
+        ranks -- do not average them again (no DDP wrapper); scale the loss by 1/world_size for a global mean.
+
+        comm="dist": the hand-offs are torch.distributed all-reduces on the kernels' own memory (10 small collectives per
+        step).  comm="p2p": each hand-off is ONE kernel over NVLink peer memory (``crdpn_p2p_allreduce_blocks``: every
+        element is pushed into each peer's slot and summed in rank order, in place; 6 launches per step, no NCCL call; the
+        ranks must stay within CRDPN_P2P_TIMEOUT_S of each other).
+        equal_batches=True promises that every rank feeds the same number of points per step, so the global point count
+        is world_size x local instead of one more all-reduce and host read per forward."""
         import torch.distributed as dist
+        if comm not in ("dist", "p2p"):
+            raise ValueError("comm must be 'dist' or 'p2p'")
         self._sync = (group, dist.get_world_size(group)) if enabled else None
+        self._sync_comm = comm
+        self._sync_equal = bool(equal_batches)
+        self._sync_px = None
         return self
+
+    def _sync_exchange(self, device):
+        """Peer-memory exchange buffers of the hand-offs (collective set-up on first use)."""
+        if self._sync_px is None:
+            import torch.distributed as dist
+            from .sharded import PeerExchange
+            group = self._sync[0]
+            # a reduction slot holds 2*Bmax*Dmax + 8 + 8*Bmax words; the largest hand-off is F*128 floats + 2F + 256
+            bmax = max(64, (self.feature_dim * 128 + 2 * self.feature_dim + 256 + 255) // 256 + 16)
+            self._sync_px = PeerExchange(group, dist.get_rank(group), self._sync[1], device, bmax, 128)
+        return self._sync_px
 
     def forward_train(self, shapes: torch.Tensor) -> torch.Tensor:
         """Batch-statistics BatchNorm forward (``training.py:30,47``); differentiable w.r.t. the 12 parameters
@@ -163,14 +187,23 @@ def _global_points(local_points: int, device, group) -> int:
     return int(t.item())
 
 
-def _sum_over_ranks(lib, dims, sync_point: int, group, buffers) -> None:
+def _sum_over_ranks(lib, dims, sync_point: int, group, buffers, px=None) -> None:
     """All-reduce (SUM) the accumulators named by crdpn_pointnet_sync_blocks(sync_point).  `buffers`: id -> (owner
     tensor, base pointer); the blocks are viewed in place through the owner's storage, so the collective runs on the
-    kernels' own memory on the current stream."""
+    kernels' own memory on the current stream.  With a PeerExchange `px` all blocks of the hand-off are summed by one
+    kernel over NVLink peer memory instead."""
     import torch.distributed as dist
     nb = ctypes.c_int(0)
     buf, off, cnt, f64 = (ctypes.c_int * 4)(), (ctypes.c_size_t * 4)(), (ctypes.c_int64 * 4)(), (ctypes.c_int * 4)()
     _native.check(lib.crdpn_pointnet_sync_blocks(*dims, sync_point, ctypes.byref(nb), buf, off, cnt, f64), "crdpn_pointnet_sync_blocks")
+    if px is not None:
+        ptrs = (ctypes.c_void_p * 4)(*[buffers[buf[i]][1] + off[i] if i < nb.value else None for i in range(4)])
+        dev = px.device
+        with _native.on_device(dev):
+            rc = lib.crdpn_p2p_allreduce_blocks(ptrs, cnt, f64, nb.value, px._ptrs, px.rank, px.world, px.Bmax, px.Dmax,
+                                                _native.stream_ptr(dev))
+        _native.check(rc, "crdpn_p2p_allreduce_blocks")
+        return
     for i in range(nb.value):
         owner, base = buffers[buf[i]]
         flat = owner.view(-1)
@@ -207,8 +240,10 @@ class _PointNetTrainFunction(torch.autograd.Function):
         sync = module._sync
         variant = (module.variant & ~16) | (16 if module.train_precision == "bf16" else 0)
         total = B * P
+        px = None
         if sync is not None:
-            total = _global_points(B * P, dev, sync[0])
+            total = B * P * sync[1] if module._sync_equal else _global_points(B * P, dev, sync[0])
+            px = module._sync_exchange(dev) if module._sync_comm == "p2p" else None
         with _native.on_device(dev):
             if sync is None:
                 rc = lib.crdpn_pointnet_forward_train(*args, float(module.bn1.eps), float(module.bn1.momentum),
@@ -222,11 +257,11 @@ class _PointNetTrainFunction(torch.autograd.Function):
                                                                  total, _native.stream_ptr(dev))
                     _native.check(rc, "crdpn_pointnet_forward_train_phased")
                     if ph < 3:
-                        _sum_over_ranks(lib, (B, P, F), ph, sync[0], {0: (owner, cptr)})
+                        _sum_over_ranks(lib, (B, P, F), ph, sync[0], {0: (owner, cptr)}, px)
         ctx.save_for_backward(x, *p)
         ctx.train_ctx = (owner, cptr, n.value)
         ctx.dims = (B, P, F)
-        ctx.sync = (sync, total)
+        ctx.sync = (sync, total, px)
         return out
 
     @staticmethod
@@ -243,7 +278,7 @@ class _PointNetTrainFunction(torch.autograd.Function):
         ws_owner, wptr = _aligned(n.value, dev)
         grads = [torch.empty_like(t) for t in p]
         c1w, c1b, c2w, c2b, c3w, c3b, g1, b1, g2, b2, g3, b3 = p
-        sync, total = ctx.sync
+        sync, total, px = ctx.sync
         bargs = (x.data_ptr(), B, P, F, c1w.data_ptr(), c2w.data_ptr(), c3w.data_ptr(),
                  g1.data_ptr(), b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), g3.data_ptr(), b3.data_ptr(),
                  g.data_ptr(), cptr, cbytes, *[t.data_ptr() for t in grads], wptr, n.value)
@@ -257,6 +292,6 @@ class _PointNetTrainFunction(torch.autograd.Function):
                     _native.check(rc, "crdpn_pointnet_backward_phased")
                     if ph < 3:
                         _sum_over_ranks(lib, (B, P, F), 3 + ph, sync[0],
-                                        {1: (ws_owner, wptr), 2: (grads[10], grads[10].data_ptr()), 3: (grads[11], grads[11].data_ptr())})
+                                        {1: (ws_owner, wptr), 2: (grads[10], grads[10].data_ptr()), 3: (grads[11], grads[11].data_ptr())}, px)
         del owner, ws_owner
         return (None, None, *grads)

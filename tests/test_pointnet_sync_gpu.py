@@ -40,7 +40,7 @@ def _rel(a, b):
     return ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30)).item()
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, comm="dist"):
     try:
         import torch.distributed as dist
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -55,7 +55,7 @@ def _worker(rank, world, port, q):
         gout = torch.randn(B, F, generator=g).to(dev)
         st = _state(F)
         ref = pkg.ShapeEncoderPC(F); ref.load_state_dict(st); ref = ref.to(dev).train()
-        syn = pkg.ShapeEncoderPC(F); syn.load_state_dict(st); syn = syn.to(dev).train().sync_batchnorm()
+        syn = pkg.ShapeEncoderPC(F); syn.load_state_dict(st); syn = syn.to(dev).train().sync_batchnorm(comm=comm, equal_batches=(comm == "p2p"))
         counts = [B * (r + 1) // world - B * r // world for r in range(world)]
         a0 = sum(counts[:rank]); sl = slice(a0, a0 + counts[rank])
         for step in range(2):
@@ -94,12 +94,12 @@ def _worker(rank, world, port, q):
         q.put((rank, traceback.format_exc()))
 
 
-def _run(world):
+def _run(world, comm="dist"):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, comm)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
@@ -109,13 +109,17 @@ def _run(world):
         assert msg == "ok", f"rank {rank}: {msg}"
 
 
-def test_world1_phased_equals_one_call_bitwise(pkg):
-    _run(1)
+@pytest.mark.parametrize("comm", ["dist", "p2p"])
+def test_world1_phased_equals_one_call_bitwise(pkg, comm):
+    """comm="p2p": the hand-offs run through crdpn_p2p_allreduce_blocks against this rank's own exchange buffer (in-place
+    sum of one rank = identity, bit for bit, float32 and float64 blocks alike)."""
+    _run(1, comm)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_world2_sync_matches_single_gpu_full_batch(pkg):
-    _run(2)
+@pytest.mark.parametrize("comm", ["dist", "p2p"])
+def test_world2_sync_matches_single_gpu_full_batch(pkg, comm):
+    _run(2, comm)
 
 
 def test_sync_blocks_table(pkg):
