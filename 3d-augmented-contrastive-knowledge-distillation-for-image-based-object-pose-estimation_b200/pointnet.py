@@ -152,8 +152,11 @@ class ShapeEncoderPC(nn.Module):
             import torch.distributed as dist
             from .sharded import PeerExchange
             group = self._sync[0]
-            # a reduction slot holds 2*Bmax*Dmax + 8 + 8*Bmax words; the largest hand-off is F*128 floats + 2F + 256
-            bmax = max(64, (self.feature_dim * 128 + 2 * self.feature_dim + 256 + 255) // 256 + 16)
+            # a reduction slot holds 2*Bmax*Dmax + 8 + 8*Bmax 32-bit words (a double takes two).  Largest hand-offs
+            # (crdpn_pointnet_sync_blocks): backward phase 0 = 128 doubles + F*128 + 2F floats; backward phase 1 = 256
+            # doubles + 128*64 + 2*128*128 floats
+            words = max(self.feature_dim * 128 + 2 * self.feature_dim + 256, 128 * 64 + 2 * 128 * 128 + 512)
+            bmax = max(64, (words + 255) // 256 + 1)
             self._sync_px = PeerExchange(group, dist.get_rank(group), self._sync[1], device, bmax, 128)
         return self._sync_px
 
