@@ -65,13 +65,26 @@ struct ScoreParams {
   long long nw;         // warps the pair space is cut over (<= resident warps; the rest idle)
   int cta_reduce;       // 1: the 8 warps of a CTA fold their partials in shared memory (fixed order) and the CTA writes
                         //    at most two slots (its range covers <= 2 anchors): 8x fewer partials for the reduction kernel
+  // compact mode (row-sharded step): crd_shard_filter_kernel has already dropped the entries other shards own.  Unit
+  // u = b * (NC + 1) + c of anchor b: c = 0 the positive (k = 0), c >= 1 the survivors of the kFilterChunk entries
+  // k in [1 + (c-1) kFilterChunk, ...) in list order: local rows cl[(b NC + c-1) kFilterChunk ...], ucount[b NC + c-1] of them.
+  // The warps cut the COMPACT space into equal ranges (exactly balanced, no scan), warp w writes slot w + b for anchor b.
+  int compact;
+  int NC;
+  const int* cl;
+  const int* ucount;
+  long long* anchor_start;   // [B + 1] out: start of every anchor in the compact space (for the reduction kernel)
 };
+constexpr int kFilterChunk = 2048;   // entries per filter unit (one CTA of 256 threads, 8 entries per thread)
+constexpr int kMaxUnits = 4096;      // unit-count prefix lives in shared memory
 
 struct FinalizeParams {
   const float* slots;
   int maxseg;
   long long NW;
   int group;            // warps per slot-writing unit: 1 (every warp writes its own slots) or kWarps (ScoreParams::cta_reduce)
+  const long long* anchor_start;   // compact mode (ScoreParams::compact): anchor b owns [anchor_start[b], anchor_start[b+1]) of the
+                                   // compact space cut over NW warps, warp w's partial for anchor b is slot w + b; else null
   int B, K1, D;
   int full;
   float* grad_v1;
@@ -138,6 +151,64 @@ __device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long lon
 __device__ __forceinline__ float lo2(unsigned long long v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi2(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
+// global row index of contrast entry `pos` = b * K1 + k (ScoreParams::idx_mode)
+__device__ __forceinline__ long long contrast_entry(const ScoreParams& p, long long pos, int b, long long anchor_base) {
+  if (p.idx_mode == 0) return p.idx[pos];
+  if (p.idx_mode == 1) return (long long)p.idx32[pos];
+  if (pos == anchor_base) return p.y[b];
+  unsigned rr[4];
+  philox4x32_10(p.seed, p.offset + (unsigned long long)pos, rr);
+  const unsigned long long bits = ((unsigned long long)rr[0] << 32) | (unsigned long long)rr[1];
+  return p.draw_base + (long long)__umul64hi(bits, (unsigned long long)p.draw_n);
+}
+
+// Row-sharded step, pre-pass: one CTA per (anchor, chunk of kFilterChunk entries k >= 1).  Every thread loads its 8 entries
+// at once (one memory latency for the whole chunk), the survivors -- entries whose row this shard owns -- are written in
+// list order (ballots + a 64-entry prefix), so the scoring pass that follows neither scans nor skips anything and its
+// result does not depend on timing.  3M entries take ~6 us this way; inside the scoring pass the same scan is a chain of
+// dependent steps per warp that costs ~20 us of a 75 us kernel on a shard that owns 1/8 of the rows.
+__global__ void __launch_bounds__(256) crd_shard_filter_kernel(const ScoreParams p, int* __restrict__ cl, int* __restrict__ ucount) {
+  __shared__ int s_cnt[64], s_pre[65];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / p.NC, c = blockIdx.x - b * p.NC;
+  const long long anchor_base = (long long)b * p.K1;
+  const int k0 = 1 + c * kFilterChunk;
+  int row[8];
+  unsigned mask[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k0 + j * 256 + tid;
+    long long r = -1;
+    if (k < p.K1) r = contrast_entry(p, anchor_base + k, b, anchor_base);
+    row[j] = (r >= p.row_begin && r < p.row_end) ? (int)(r - p.row_begin) : -1;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mask[j] = __ballot_sync(0xffffffffu, row[j] >= 0);
+    if (lane == 0) s_cnt[j * 8 + warp] = __popc(mask[j]);
+  }
+  __syncthreads();
+  if (warp == 0) {   // exclusive prefix over the 64 (slice, warp) counts, in list order
+    int a = s_cnt[lane], b2 = s_cnt[32 + lane];
+    int ia = a, ib = b2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= o) { ia += ta; ib += tb; }
+    }
+    const int tot_a = __shfl_sync(0xffffffffu, ia, 31);
+    s_pre[lane] = ia - a;
+    s_pre[32 + lane] = tot_a + ib - b2;
+    if (lane == 31) s_pre[64] = tot_a + ib;
+  }
+  __syncthreads();
+  int* dst = cl + (size_t)blockIdx.x * kFilterChunk;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (row[j] >= 0) dst[s_pre[j * 8 + warp] + __popc(mask[j] & ((1u << lane) - 1u))] = row[j];
+  if (tid == 0) ucount[blockIdx.x] = s_pre[64];
+}
+
 template <typename T> struct Unpack;
 template <> struct Unpack<float> {
   static constexpr int VEC = 4;
@@ -170,7 +241,12 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
   constexpr int kD = NV * LPR;                      // feature dimension of this instantiation
   constexpr int kSW = 2 * kD + kSlotExtra;          // floats per slot
   constexpr bool kCanReduce = kD <= 256;            // [8 warps][2 anchors][slot] must fit static shared memory
-  __shared__ __align__(16) float red_smem[kCanReduce ? kWarps * 2 * kSW : 4];
+  // one buffer, two mutually exclusive uses: the CTA-level fold of the warp partials, or compact mode's unit-count prefix
+  constexpr int kRedBytes = kCanReduce ? kWarps * 2 * kSW * 4 : 16;
+  constexpr int kPreBytes = (kMaxUnits + 1) * 4;
+  __shared__ __align__(16) unsigned char shbuf[kRedBytes > kPreBytes ? kRedBytes : kPreBytes];
+  float* red_smem = reinterpret_cast<float*>(shbuf);
+  int* s_upre = reinterpret_cast<int*>(shbuf);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / LPR, j = lane % LPR;
@@ -185,20 +261,83 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
     const long long w0 = (long long)blockIdx.x * kWarps;
     b_first_cta = (int)((P * (w0 < NW ? w0 : NW) / NW) / p.K1);
     __syncthreads();
-  } else if (gw >= NW) {
+  } else if (gw >= NW && p.compact == 0) {
     return;
   }
   long long lo = gw < NW ? P * gw / NW : 0;
-  const long long hi = gw < NW ? P * (gw + 1) / NW : 0;
+  long long hi = gw < NW ? P * (gw + 1) / NW : 0;
   int2* q = queue_smem[warp];
   const bool store_out = (p.out_v1 != nullptr);
   int seg = 0;
 
+  // ---- compact mode: exclusive prefix of the unit counts (shared memory), then equal ranges of the COMPACT space ----
+  __shared__ int s_wsum[kWarps];
+  const bool compact = p.compact != 0;
+  const int UPA = p.NC + 1;                 // units per anchor: the positive, then NC filtered chunks
+  int cu = 0;                               // current unit
+  if (compact) {   // (cta_reduce is off in this mode, so every thread is still here)
+    const int NUt = p.B * UPA;
+    constexpr int kPer = kMaxUnits / kThreads;   // 16 consecutive units per thread
+    int cntv[kPer], local = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int u = threadIdx.x * kPer + i;
+      int cv = 0;
+      if (u < NUt) {
+        const int ub = u / UPA, uc = u - ub * UPA;
+        if (uc == 0) {
+          const long long r = contrast_entry(p, (long long)ub * p.K1, ub, (long long)ub * p.K1);
+          cv = (r >= p.row_begin && r < p.row_end) ? 1 : 0;
+        } else {
+          cv = p.ucount[ub * p.NC + uc - 1];
+        }
+      }
+      cntv[i] = cv;
+      local += cv;
+    }
+    int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    int wbase = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) wbase += (w < warp) ? s_wsum[w] : 0;
+    int run = wbase + inc - local;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int u = threadIdx.x * kPer + i;
+      if (u <= NUt) s_upre[u] = run;
+      run += cntv[i];
+    }
+    __syncthreads();
+    const long long Tc = s_upre[NUt];
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i <= p.B; i += kThreads) p.anchor_start[i] = s_upre[i * UPA];
+    if (gw >= NW) return;
+    lo = Tc * gw / NW;
+    hi = Tc * (gw + 1) / NW;
+    if (lo < hi) {   // largest unit whose start is <= lo (binary search; empty units are skipped in the loop below)
+      int a = 0, z = NUt;
+      while (z - a > 1) {
+        const int mid = (a + z) >> 1;
+        if ((long long)s_upre[mid] <= lo) a = mid; else z = mid;
+      }
+      cu = a;
+    }
+  }
+
   while (lo < hi) {
-    const int b = (int)(lo / p.K1);
+    if (compact)
+      while ((long long)s_upre[cu + 1] <= lo) ++cu;
+    const int b = compact ? cu / UPA : (int)(lo / p.K1);
     const long long anchor_base = (long long)b * p.K1;
-    const long long seg_hi = (hi < anchor_base + p.K1) ? hi : (anchor_base + p.K1);
-    const int pos_off = (anchor_base == lo) ? 0 : -1;  // queue offset of the positive (k == 0) entry
+    const long long seg_hi = compact ? ((hi < (long long)s_upre[(b + 1) * UPA]) ? hi : (long long)s_upre[(b + 1) * UPA])
+                                     : ((hi < anchor_base + p.K1) ? hi : (anchor_base + p.K1));
+    const int pos_off = compact ? 0 : ((anchor_base == lo) ? 0 : -1);  // queue tag of the positive (k == 0) entry
 
     float v1c[NV], v2c[NV];
 #pragma unroll
@@ -311,15 +450,35 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       }
     };
 
-    auto fetch_idx = [&](long long pos) -> long long {   // idx_mode is uniform over the grid: no divergence
-      if (p.idx_mode == 0) return p.idx[pos];
-      if (p.idx_mode == 1) return (long long)p.idx32[pos];
-      if (pos == anchor_base) return p.y[b];
-      unsigned rr[4];
-      philox4x32_10(p.seed, p.offset + (unsigned long long)pos, rr);
-      const unsigned long long bits = ((unsigned long long)rr[0] << 32) | (unsigned long long)rr[1];
-      return p.draw_base + (long long)__umul64hi(bits, (unsigned long long)p.draw_n);
-    };
+    auto fetch_idx = [&](long long pos) -> long long { return contrast_entry(p, pos, b, anchor_base); };
+    if (compact) {
+      // entries of this segment, unit by unit: every one of them is scored (the filter kernel dropped the rest)
+      long long cur = lo;
+      while (cur < seg_hi) {
+        while ((long long)s_upre[cu + 1] <= cur) ++cu;
+        const int uc = cu - b * UPA;
+        const long long uend = (seg_hi < (long long)s_upre[cu + 1]) ? seg_hi : (long long)s_upre[cu + 1];
+        const int off = (int)(cur - s_upre[cu]), n = (int)(uend - cur);
+        const int* src = p.cl + ((size_t)b * p.NC + (uc > 0 ? uc - 1 : 0)) * kFilterChunk + off;
+#pragma unroll 1
+        for (int i = 0; i < n; i += 32) {
+          if (i + lane < n) {
+            int row;
+            if (uc == 0) row = (int)(contrast_entry(p, anchor_base, b, anchor_base) - p.row_begin);
+            else row = src[i + lane];
+            q[(qtail + lane) & (kQueueCap - 1)] = make_int2(row, uc == 0 ? 0 : 1);
+          }
+          qtail += (n - i < 32) ? (n - i) : 32;
+          __syncwarp();
+          while (qtail - qhead >= R * U) {
+            consume(R * U);
+            qhead += R * U;
+          }
+          __syncwarp();
+        }
+        cur = uend;
+      }
+    } else {
     long long base = lo;
     // a scan step covers 64 entries (two per lane: half the loop iterations, ballots and queue bookkeeping per entry -- the
     // scan is pure instruction overhead on a shard that owns 1/R of the rows); the index loads run two steps ahead of
@@ -354,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       __syncwarp();
       base += 64;
     }
+    }
     while (qtail - qhead > 0) {
       const int avail = qtail - qhead;
       consume(avail);
@@ -382,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       cnt += __shfl_xor_sync(kFull, cnt, off);
     }
     float* slot = cta_red ? red_smem + (warp * 2 + (b - b_first_cta)) * kSW
+                : compact ? p.slots + ((long long)gw + b) * (2 * p.D + kSlotExtra)
                           : p.slots + ((long long)gw * p.maxseg + seg) * (2 * p.D + kSlotExtra);
     if (g == 0) {
       if constexpr (FULL) {
@@ -434,15 +595,22 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
   __shared__ uint32_t s_epoch;
   if (f.xchg && threadIdx.x == 0)   // advanced by the last block only, i.e. after every block has read it
     s_epoch = *reinterpret_cast<volatile uint32_t*>(f.peers.buf[f.rank] + f.off_ctl + 8) + 1u;
-  const long long P = (long long)f.B * f.K1;
-  const long long p0 = (long long)b * f.K1, p1 = p0 + f.K1;
+  // pair space: B*K1 entries, anchor b = [b K1, (b+1) K1); compact mode: the entries this shard owns, anchor b =
+  // [anchor_start[b], anchor_start[b+1]) as the scoring pass measured them
+  const bool compact = f.anchor_start != nullptr;
+  const long long P = compact ? f.anchor_start[f.B] : (long long)f.B * f.K1;
+  const long long p0 = compact ? f.anchor_start[b] : (long long)b * f.K1;
+  const long long p1 = compact ? f.anchor_start[b + 1] : p0 + f.K1;
   // slot-writing units: single warps (group = 1) or whole CTAs of `group` warps; unit u covers pairs [bnd(u), bnd(u+1))
   const long long G = f.group, NU = (f.NW + G - 1) / G;
   auto bnd = [&](long long u) -> long long {
     const long long w = u * G < f.NW ? u * G : f.NW;
     return (P * w) / f.NW;
   };
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && p1 <= p0) {   // (compact mode) nothing of this anchor lives in this shard
+    s_first = 1;
+    s_last = 0;
+  } else if (threadIdx.x == 0) {
     long long first = ((p0 * f.NW) / P) / G;
     if (first >= NU) first = NU - 1;
     while (first > 0 && bnd(first) > p0) --first;
@@ -471,7 +639,8 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
       const long long lo = bnd(w);
       const long long hi = bnd(w + 1);
       const bool valid = hi > p0 && hi > lo && lo < p1;
-      s_off[i] = valid ? (w * f.maxseg + (b - (int)(lo / f.K1))) * (long long)slot_w : -1;
+      s_off[i] = !valid ? -1 : compact ? (w + b) * (long long)slot_w
+                                       : (w * f.maxseg + (b - (int)(lo / f.K1))) * (long long)slot_w;
     }
     __syncthreads();
     if (active) {
@@ -768,11 +937,18 @@ static int maxseg_for(long long P, long long NW, long long K1) {
   return (int)((len_max + K1 - 1) / K1 + 1);
 }
 
-static size_t workspace_bytes_for(long long B, long long K1, long long D, long long NW) {
+static inline long long filter_chunks(long long K1) { return (K1 - 1 + kFilterChunk - 1) / kFilterChunk; }
+static size_t workspace_slots_end(long long B, long long K1, long long D, long long NW) {
   const long long P = B * K1;
   const size_t head = 16 + align_up((size_t)B * 8 * sizeof(double), 16);
   const size_t slots = (size_t)NW * (size_t)maxseg_for(P, NW, K1) * (size_t)(2 * D + kSlotExtra) * sizeof(float);
-  return head + slots;
+  return align_up(head + slots, 256);
+}
+// behind the slots: the compact lists of the row-sharded step (anchor_start [B+1] i64 | ucount [B*NC] i32 | cl [B*NC*chunk] i32)
+static size_t workspace_bytes_for(long long B, long long K1, long long D, long long NW) {
+  const long long NC = filter_chunks(K1);
+  return workspace_slots_end(B, K1, D, NW) + align_up((size_t)(B + 1) * 8, 256) + align_up((size_t)(B * NC) * 4, 256) +
+         (size_t)(B * NC) * kFilterChunk * 4;
 }
 
 }  // namespace crdpn
@@ -815,11 +991,12 @@ static UpdateParams make_update_params(void* bank1, void* bank2, int64_t row_str
 
 // how the scoring pass obtains contrast_idx when it is not an int64 list (ScoreParams::idx_mode)
 struct IdxSource {
-  int mode;                 // 1: int32 list; 2: drawn inside the kernel (uniform tables)
+  int mode;                 // 0: int64 list (score_impl's contrast_idx); 1: int32 list; 2: drawn inside the kernel (uniform tables)
   const int* idx32;
   const int64_t* y;
   uint64_t seed, offset;
   int64_t draw_n, draw_base;
+  int compact;              // row-sharded step: run crd_shard_filter_kernel first and score the compact lists (y must be set)
 };
 
 // score (+ finalize); when `upd` is given the momentum update rides in the finalize launch.
@@ -830,9 +1007,10 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
                       float* grad_v1, float* grad_v2, void* workspace, size_t workspace_bytes, int variant,
                       const UpdateParams* upd, void* stream, const FinalizeParams* xchg = nullptr,
                       const IdxSource* src = nullptr) {
-  if (!v1 || !v2 || (!contrast_idx && !src) || !result || !workspace)
+  if (!v1 || !v2 || (!contrast_idx && (!src || src->mode == 0)) || !result || !workspace)
     return fail(CRDPN_E_BADARG, "crdpn_crd_score: null pointer");
-  if (src && ((src->mode == 1 && !src->idx32) || (src->mode == 2 && (!src->y || src->draw_n <= 0)) || (src->mode != 1 && src->mode != 2)))
+  if (src && ((src->mode == 1 && !src->idx32) || (src->mode == 2 && (!src->y || src->draw_n <= 0)) || src->mode < 0 || src->mode > 2 ||
+              (src->mode == 0 && !contrast_idx)))
     return fail(CRDPN_E_BADARG, "crdpn_crd_score: bad index source");
   if (src && (out_v1 || out_v2) && src->mode == 2)
     return fail(CRDPN_E_BADARG, "crdpn_crd_score: per-entry outputs need a materialised contrast_idx");
@@ -855,7 +1033,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   // warps of a slice then walk the same band of bank rows together and each row comes from HBM once.
   const bool aligned = (variant & 0x100) != 0;
   const bool no_cta_fold = (variant & 0x80) != 0;   // bit 7: keep one slot per (warp, anchor) (A/B timing of the CTA-level fold)
-  variant &= 0x7f;
+  variant &= 0x1f;   // (bits 5 / 6 steer the sharded step's pre-pass and mean nothing here)
   if (!pick_variant(bank_dtype, (int)D, variant, &var))
     return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_score: no kernel for this (dtype, feat_dim, variant); feat_dim in {32,64,128,256,512}");
 
@@ -870,7 +1048,10 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   const long long P = B * K1;
   // CTA-level fold of the warp partials: possible when a CTA's range of pairs spans at most two anchors and its slots fit
   // static shared memory; not for the per-entry outputs mode (kept on the original layout) or the aligned partition
-  const bool cta_reduce = !aligned && D <= 256 && out_v1 == nullptr && (P * kWarps + NW - 1) / NW + 1 <= K1 && !no_cta_fold;
+  const long long NC = filter_chunks(K1);
+  const bool compact = src != nullptr && src->compact != 0 && src->y != nullptr && full && !aligned && out_v1 == nullptr && NC >= 1 &&
+                       B * (NC + 1) < kMaxUnits && B <= NW && row_end > row_begin;
+  const bool cta_reduce = !compact && !aligned && D <= 256 && out_v1 == nullptr && (P * kWarps + NW - 1) / NW + 1 <= K1 && !no_cta_fold;
   const size_t need = workspace_bytes_for(B, K1, D, NW);
   if (workspace_bytes < need) return fail(CRDPN_E_WORKSPACE, "crdpn_crd_score: workspace too small");
 
@@ -911,8 +1092,20 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.ticket = ticket;
   sp.nw = NW;
   sp.cta_reduce = cta_reduce ? 1 : 0;
+  sp.compact = compact ? 1 : 0;
+  sp.NC = (int)NC;
+  char* cbase = ws + workspace_slots_end(B, K1, D, NW);
+  long long* anchor_start = (long long*)cbase;
+  int* ucount = (int*)(cbase + align_up((size_t)(B + 1) * 8, 256));
+  int* cl = (int*)((char*)ucount + align_up((size_t)(B * NC) * 4, 256));
+  sp.cl = cl; sp.ucount = ucount; sp.anchor_start = anchor_start;
 
   cudaStream_t st = (cudaStream_t)stream;
+  if (compact) {   // pre-pass: drop the entries other shards own, keep list order
+    if (sp.idx_mode != 2) sp.y = (const long long*)src->y;
+    crd_shard_filter_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
+    CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
+  }
   {
     ScopedKernelTimer tm(CRDPN_K_CRD_SCORE, st);
     (full ? var.full : var.sums)<<<grid, kThreads, 0, st>>>(sp);
@@ -921,6 +1114,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
 
   FinalizeParams fp;
   fp.slots = slots; fp.maxseg = sp.maxseg; fp.NW = NW; fp.group = cta_reduce ? kWarps : 1;
+  fp.anchor_start = compact ? anchor_start : nullptr;
   fp.B = (int)B; fp.K1 = (int)K1; fp.D = (int)D; fp.full = full ? 1 : 0;
   fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2;
   fp.anchor_part = anchor_part; fp.result = result; fp.ticket = ticket;
@@ -1182,7 +1376,7 @@ extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int 
                             row_end, T, Z1, Z2, eps, result, grad_v1, grad_v2, workspace, workspace_bytes, u,
                             (variant & 0x800) ? 1 : 0, stream);
   if (variant & 0x1000) {   // contrast_idx is an int32 list
-    const IdxSource src{1, (const int*)contrast_idx, nullptr, 0, 0, 0, 0};
+    const IdxSource src{1, (const int*)contrast_idx, nullptr, 0, 0, 0, 0, 0};
     return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, nullptr, B, K1, D, n_data, k_total, row_begin, row_end,
                       T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant & ~0x1000,
                       &u, stream, nullptr, &src);
@@ -1208,7 +1402,7 @@ extern "C" int crdpn_crd_step_drawn(void* bank1, void* bank2, int64_t row_stride
   if (rc) return rc;
   const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end,
                                             momentum, one_minus_momentum);
-  const IdxSource src{2, nullptr, y, seed, offset, draw_n, draw_base};
+  const IdxSource src{2, nullptr, y, seed, offset, draw_n, draw_base, 0};
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, nullptr, B, K1, D, n_data, k_total, row_begin, row_end,
                     T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant & 0xfff,
                     &u, stream, nullptr, &src);
@@ -1251,10 +1445,14 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
   x.off_ctl = L.ctl; x.off_slots = L.slots; x.parity_stride = L.parity_stride; x.slot_words = L.slot_words;
   x.timeout = p2p::poll_timeout_ticks();
   // an empty shard still takes part in the exchange: score_impl launches the reduction kernel either way
-  const IdxSource src{idx_mode, (const int*)contrast_idx, y_all, seed, offset, draw_n, draw_base};
+  // the pre-pass pays when most of the list belongs to other shards (measured: it costs ~6 us and removes a ~20 us chain of
+  // dependent scan steps per warp at 1/8 of the rows; at 1/2 the scan is hidden behind the row traffic anyway);
+  // variant bit 6 forces it on (single-GPU tests), bit 5 forces it off
+  const bool want_compact = !(variant & 0x20) && ((variant & 0x40) || (row_end - row_begin) * 3 <= n_data);
+  const IdxSource src{idx_mode, (const int*)contrast_idx, y_all, seed, offset, draw_n, draw_base, want_compact ? 1 : 0};
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, idx_mode == 0 ? contrast_idx : nullptr, B, K1, D,
                     n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, nullptr, nullptr, result, partial, partial + B * D,
-                    workspace, workspace_bytes, variant & 0xfff, &u, stream, &x, idx_mode == 0 ? nullptr : &src);
+                    workspace, workspace_bytes, variant & 0xf9f, &u, stream, &x, &src);
 }
 
 extern "C" int crdpn_crd_step_sharded(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,

@@ -311,6 +311,10 @@ class ShardedContrastMemory(ContrastMemory):
         m1, m2, stride, dt = self._banks()
         variant = self._step_variant(B, K1, D)
         ws = self._workspace(B, K1, D, dev, variant)
+        if contrast_idx.dtype == torch.int32 and not (variant & self.STREAM):
+            variant |= self.IDX32
+        elif contrast_idx.dtype != torch.int64:
+            raise RuntimeError("step_resident: contrast_idx must be int64 (or int32 for the gather kernels)")
         with _native.on_device(dev):
             rc = _native.lib().crdpn_crd_step_sharded(
                 m1.data_ptr(), m2.data_ptr(), stride, dt, v1_loc.data_ptr(), v2_loc.data_ptr(), y_loc.data_ptr(),

@@ -75,6 +75,79 @@ def test_world1_peer_memory_step_equals_unsharded(pkg, cuda):
         assert torch.equal(a.contrast.memory_v1, b.contrast.memory_v1)
 
 
+def _shard_module(pkg, cuda, N, K, lo, hi, variant, seed=3):
+    """One rank's ContrastMemory of a bank sharded three ways, on this GPU alone (exchange kernels talk to themselves)."""
+    m = pkg.ShardedContrastMemory(128, N, K, rank=0, world_size=1, comm="p2p", seed=5).to(cuda)
+    m.row_begin, m.row_end = lo, hi
+    g = torch.Generator().manual_seed(seed)
+    m.memory_v1 = torch.nn.functional.normalize(torch.randn(hi - lo, 128, generator=g)).to(cuda)
+    m.memory_v2 = torch.nn.functional.normalize(torch.randn(hi - lo, 128, generator=g)).to(cuda)
+    m._relayout()
+    with torch.no_grad():
+        m.params[2], m.params[3] = 1.0e5, 1.1e5
+    m._host = None
+    m.variant = variant
+    return m
+
+
+@pytest.mark.parametrize("shape", [dict(B=46, K=2048, N=6000), dict(B=7, K=5000, N=3001), dict(B=64, K=300, N=50000)])
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_compact_prepass_matches_the_scanning_kernel(pkg, oracle, cuda, shape, dtype):
+    """The filter pre-pass of the row-sharded step (crd_shard_filter_kernel + compact scoring; variant bit 6 forces it on,
+    bit 5 off) against the scanning kernel and the CPU oracle on a shard that owns a THIRD of the rows: same loss /
+    gradients up to fp32 summation order, updated rows bit-identical, the same bits run to run; int64 and int32 lists."""
+    B, K, N = shape["B"], shape["K"], shape["N"]
+    lo, hi = N // 3, 2 * N // 3
+    g = torch.Generator().manual_seed(B + K)
+    v1 = torch.nn.functional.normalize(torch.randn(B, 128, generator=g)).to(cuda)
+    v2 = torch.nn.functional.normalize(torch.randn(B, 128, generator=g)).to(cuda)
+    y = torch.randperm(N, generator=g)[:B].to(cuda)
+    y[0] = lo + 1                                      # at least one positive inside the shard
+    cidx = torch.randint(0, N, (B, K + 1), generator=g).to(cuda)
+    cidx[:, 0] = y
+    outs = []
+    for variant in (0x20, 0x40, 0x40):   # scanning kernel, pre-pass, pre-pass again
+        m = _shard_module(pkg, cuda, N, K, lo, hi, variant)
+        if not outs:
+            b1, b2 = m.memory_v1.cpu().numpy().copy(), m.memory_v2.cpu().numpy().copy()
+        out = m.step_resident(v1, v2, y, cidx.to(dtype))
+        torch.cuda.synchronize()
+        outs.append((out["reduced"].clone(), m.memory_v1.clone(), m.memory_v2.clone()))
+    rel = lambda a, b: ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30)).item()
+    n = 2 * B * 128
+    assert rel(outs[1][0][:n], outs[0][0][:n]) < 1e-5
+    assert abs(outs[1][0][n + 5].item() - outs[0][0][n + 5].item()) <= 1e-5 * abs(outs[0][0][n + 5].item())
+    assert torch.equal(outs[1][1], outs[0][1]) and torch.equal(outs[1][2], outs[0][2])
+    assert torch.equal(outs[1][0], outs[2][0])          # deterministic: identical bits run to run
+    r = oracle.crd_score(b1, b2, v1.cpu().numpy(), v2.cpu().numpy(), cidx.cpu().numpy(), N, 0.07, 1.0e5, 1.1e5,
+                         row_begin=lo, row_end=hi, want_out=False)
+    assert rel(outs[1][0][:B * 128].view(B, 128).cpu(), torch.from_numpy(r["grad_v1"])) < 1e-4
+    assert rel(outs[1][0][B * 128:n].view(B, 128).cpu(), torch.from_numpy(r["grad_v2"])) < 1e-4
+    assert abs(outs[1][0][n + 5].item() - (r["loss_s"] + r["loss_t"])) <= 1e-4 * abs(r["loss_s"] + r["loss_t"])
+
+
+@pytest.mark.parametrize("variant", [0x20, 0x40])
+def test_in_shard_negatives_drawn_inside_the_sharded_step(pkg, oracle, cuda, variant):
+    """ShardedCRDLoss(comm="p2p", local_negatives=True), second call: one foreign call in which the scoring pass (bit 5) or
+    the filter pre-pass (bit 6) draws the in-shard negatives itself -- against the oracle's draw + scorer."""
+    import numpy as np
+    opt = _opt(nce_k=700)
+    torch.manual_seed(2)
+    m = pkg.ShardedCRDLoss(opt, rank=0, world_size=1, local_negatives=True, comm="p2p", seed=77).to(cuda)
+    m.contrast.variant = variant
+    f_s, f_t, y, _ = [t.to(cuda) for t in _inputs(opt, 9)]
+    m(f_s, f_t, y, None)                                  # first call: freezes Z (general path), updates the banks
+    b1 = m.contrast.memory_v1.cpu().numpy().copy(); b2 = m.contrast.memory_v2.cpu().numpy().copy()
+    loss = m(f_s, f_t, y, None)
+    prob, alias = oracle.alias_build(np.ones(opt.n_data, np.float32))
+    cidx = oracle.alias_draw_contrast(prob, alias, y.cpu().numpy(), 701, seed=77 + 7919, offset=9 * 701)
+    with torch.no_grad():
+        v1 = m.embed_s(f_s).cpu().numpy(); v2 = m.embed_t(f_t).cpu().numpy()
+    Z1, Z2 = m.contrast.params[2].item(), m.contrast.params[3].item()
+    want = oracle.crd_score(b1, b2, v1, v2, cidx, opt.n_data, 0.07, Z1, Z2)
+    assert abs(loss.item() - (want["loss_s"] + want["loss_t"])) < 1e-4 * abs(want["loss_s"] + want["loss_t"])
+
+
 def test_local_negatives_world1_matches_oracle(pkg, oracle, cuda):
     """local_negatives with internal sampling: indices are in-shard draws of the rank's own Philox stream."""
     opt = _opt(nce_k=512)
