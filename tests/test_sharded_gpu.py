@@ -118,7 +118,7 @@ def test_compact_prepass_matches_the_scanning_kernel(pkg, oracle, cuda, shape, d
     assert rel(outs[1][0][:n], outs[0][0][:n]) < 1e-5
     assert abs(outs[1][0][n + 5].item() - outs[0][0][n + 5].item()) <= 1e-5 * abs(outs[0][0][n + 5].item())
     assert torch.equal(outs[1][1], outs[0][1]) and torch.equal(outs[1][2], outs[0][2])
-    assert torch.equal(outs[1][0], outs[2][0])          # deterministic: identical bits run to run
+    assert torch.equal(outs[1][0][:n + 6], outs[2][0][:n + 6])   # deterministic: identical bits run to run (words 6, 7 unused)
     r = oracle.crd_score(b1, b2, v1.cpu().numpy(), v2.cpu().numpy(), cidx.cpu().numpy(), N, 0.07, 1.0e5, 1.1e5,
                          row_begin=lo, row_end=hi, want_out=False)
     assert rel(outs[1][0][:B * 128].view(B, 128).cpu(), torch.from_numpy(r["grad_v1"])) < 1e-4
