@@ -20,6 +20,7 @@
 // anchor by anchor; per anchor it scans 32 contrast indices at a time, drops entries that fall outside
 // this rank's bank shard, compacts the survivors into a per-warp shared-memory queue and consumes the
 // queue R rows x U steps at a time with all 2*CH*U 128-bit loads of a step group issued before first use.
+#include <string.h>
 #include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
 #include "common.cuh"
 #include "p2p_common.cuh"        // LL exchange words: the all-reduce of the sharded step rides in the reduction kernel
@@ -109,7 +110,8 @@ int sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dty
                       float eps, float momentum, float one_minus_momentum, float* v1_all, float* v2_all, int64_t* y_all,
                       float* partial, double* result, float* reduced, void* workspace, size_t workspace_bytes, int variant,
                       void* stream, int idx_mode = 0, uint64_t seed = 0, uint64_t offset = 0, int64_t draw_n = 0,
-                      int64_t draw_base = 0);
+                      int64_t draw_base = 0, const float* v1_local = nullptr, const float* v2_local = nullptr,
+                      const int64_t* y_local = nullptr, const int32_t* offs_host = nullptr);
 
 __device__ __forceinline__ uint4 ld16_stream(const void* p) {
   uint4 r;
@@ -999,6 +1001,43 @@ struct IdxSource {
   int compact;              // row-sharded step: run crd_shard_filter_kernel first and score the compact lists (y must be set)
 };
 
+// compact lists of the row-sharded step inside the workspace (behind the slots)
+struct CompactPlan {
+  long long NC, NW;
+  long long* anchor_start;
+  int* ucount;
+  int* cl;
+};
+static bool plan_compact(int bank_dtype, int64_t D, int variant, int64_t B, int64_t K1, int64_t row_begin, int64_t row_end,
+                         int sms, void* workspace, CompactPlan* out) {
+  Variant var;
+  if ((variant & 0x100) || !pick_variant(bank_dtype, (int)D, variant & 0x1f, &var)) return false;
+  const long long NW = (long long)sms * var.bps * kWarps, NC = filter_chunks(K1);
+  if (NC < 1 || B * (NC + 1) >= kMaxUnits || B > NW || row_end <= row_begin) return false;
+  char* cbase = (char*)workspace + workspace_slots_end(B, K1, D, NW);
+  out->NC = NC; out->NW = NW;
+  out->anchor_start = (long long*)cbase;
+  out->ucount = (int*)(cbase + align_up((size_t)(B + 1) * 8, 256));
+  out->cl = (int*)((char*)out->ucount + align_up((size_t)(B * NC) * 4, 256));
+  return true;
+}
+// a second stream per device so that the filter pre-pass runs beside the anchors' all-gather (fork / join by events;
+// inside a stream capture the pair becomes two parallel branches of the graph)
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static int side_stream(SideStream** out) {
+  static SideStream side[64];
+  int device = 0;
+  CRDPN_CUDA(cudaGetDevice(&device));
+  SideStream& x = side[device & 63];
+  if (!x.s) {
+    CRDPN_CUDA(cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking));
+    CRDPN_CUDA(cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming));
+    CRDPN_CUDA(cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming));
+  }
+  *out = &x;
+  return CRDPN_OK;
+}
+
 // score (+ finalize); when `upd` is given the momentum update rides in the finalize launch.
 static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, int bank_dtype,
                       const float* v1, const float* v2, const int64_t* contrast_idx,
@@ -1101,10 +1140,12 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.cl = cl; sp.ucount = ucount; sp.anchor_start = anchor_start;
 
   cudaStream_t st = (cudaStream_t)stream;
-  if (compact) {   // pre-pass: drop the entries other shards own, keep list order
+  if (compact) {   // pre-pass: drop the entries other shards own, keep list order (compact == 2: the caller has launched it)
     if (sp.idx_mode != 2) sp.y = (const long long*)src->y;
-    crd_shard_filter_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
-    CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
+    if (src->compact != 2) {
+      crd_shard_filter_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
+      CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
+    }
   }
   {
     ScopedKernelTimer tm(CRDPN_K_CRD_SCORE, st);
@@ -1421,10 +1462,47 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
                              float T, float Z1, float Z2, float eps, float momentum, float one_minus_momentum,
                              float* v1_all, float* v2_all, int64_t* y_all, float* partial, double* result, float* reduced,
                              void* workspace, size_t workspace_bytes, int variant, void* stream, int idx_mode, uint64_t seed,
-                             uint64_t offset, int64_t draw_n, int64_t draw_base) {
+                             uint64_t offset, int64_t draw_n, int64_t draw_base, const float* v1_local, const float* v2_local,
+                             const int64_t* y_local, const int32_t* offs_host) {
   int rc;
   if ((variant & 0x200) && idx_mode != 0)
     return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_step_sharded: the bank-streaming kernels need a materialised int64 contrast_idx");
+  // the pre-pass pays when most of the list belongs to other shards (measured on one rank's share of the headline step:
+  // scoring pass 76 -> 67 us at 1/8 of the rows, nothing at 1/2); variant bit 6 forces it on (single-GPU tests), bit 5 off
+  const bool gather = v1_local != nullptr;
+  bool prefiltered = false;
+  const bool want_compact = !(variant & 0x200) && !(variant & 0x20) && ((variant & 0x40) || (row_end - row_begin) * 3 <= n_data);
+  cudaStream_t st = (cudaStream_t)stream;
+  SideStream* side = nullptr;
+  if (want_compact && gather && workspace != nullptr) {
+    // filter pre-pass on a second stream, beside the all-gather (it needs the index list only, not the anchors)
+    int device = 0;
+    CRDPN_CUDA(cudaGetDevice(&device));
+    DeviceInfo di;
+    if ((rc = device_info(device, &di)) != 0) return rc;
+    CompactPlan cp;
+    if (plan_compact(bank_dtype, D, variant & 0xf9f, B, K1, row_begin, row_end, di.sms, workspace, &cp) &&
+        workspace_bytes >= workspace_bytes_for(B, K1, D, cp.NW) && (idx_mode != 0 || contrast_idx != nullptr)) {
+      if ((rc = side_stream(&side)) != 0) return rc;
+      ScoreParams fpar;
+      memset(&fpar, 0, sizeof(fpar));
+      fpar.idx = (const long long*)contrast_idx; fpar.idx32 = (const int*)contrast_idx; fpar.idx_mode = idx_mode;
+      fpar.seed = seed; fpar.offset = offset; fpar.draw_n = draw_n; fpar.draw_base = draw_base;
+      fpar.B = (int)B; fpar.K1 = (int)K1; fpar.D = (int)D; fpar.row_begin = row_begin; fpar.row_end = row_end; fpar.NC = (int)cp.NC;
+      CRDPN_CUDA(cudaEventRecord(side->fork, st));
+      CRDPN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+      crd_shard_filter_kernel<<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
+      CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
+      CRDPN_CUDA(cudaEventRecord(side->join, side->s));
+      prefiltered = true;
+    }
+  }
+  if (gather) {
+    rc = crdpn_p2p_allgather_anchors(v1_local, v2_local, y_local, D, offs_host, peer_bufs_host, rank, world, Bmax, Dmax, v1_all,
+                                     v2_all, y_all, stream);
+    if (rc) return rc;
+  }
+  if (prefiltered) CRDPN_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   if (variant & 0x200) {
     rc = crdpn_crd_step(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, contrast_idx, y_all, B, K1, D, n_data, k_total,
                         row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, result, partial, partial + B * D,
@@ -1445,11 +1523,8 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
   x.off_ctl = L.ctl; x.off_slots = L.slots; x.parity_stride = L.parity_stride; x.slot_words = L.slot_words;
   x.timeout = p2p::poll_timeout_ticks();
   // an empty shard still takes part in the exchange: score_impl launches the reduction kernel either way
-  // the pre-pass pays when most of the list belongs to other shards (measured: it costs ~6 us and removes a ~20 us chain of
-  // dependent scan steps per warp at 1/8 of the rows; at 1/2 the scan is hidden behind the row traffic anyway);
-  // variant bit 6 forces it on (single-GPU tests), bit 5 forces it off
-  const bool want_compact = !(variant & 0x20) && ((variant & 0x40) || (row_end - row_begin) * 3 <= n_data);
-  const IdxSource src{idx_mode, (const int*)contrast_idx, y_all, seed, offset, draw_n, draw_base, want_compact ? 1 : 0};
+  const IdxSource src{idx_mode, (const int*)contrast_idx, y_all, seed, offset, draw_n, draw_base,
+                      prefiltered ? 2 : (want_compact ? 1 : 0)};
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, idx_mode == 0 ? contrast_idx : nullptr, B, K1, D,
                     n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, nullptr, nullptr, result, partial, partial + B * D,
                     workspace, workspace_bytes, variant & 0xf9f, &u, stream, &x, &src);
@@ -1471,13 +1546,11 @@ extern "C" int crdpn_crd_step_sharded(void* bank1, void* bank2, int64_t row_stri
   if (!(Z1 > 0.f && Z2 > 0.f)) return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: Z1 and Z2 must be frozen (> 0)");
   const int64_t B = offs_host[world];
   if (B <= 0 || B > Bmax || D > Dmax) return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: batch does not fit the exchange buffer");
-  int rc = crdpn_p2p_allgather_anchors(v1_local, v2_local, y_local, D, offs_host, peer_bufs_host, rank, world, Bmax, Dmax,
-                                       v1_all, v2_all, y_all, stream);
-  if (rc) return rc;
+  if (!v1_local || !v2_local || !y_local) return fail(CRDPN_E_BADARG, "crdpn_crd_step_sharded: null pointer");
   return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, contrast_idx, B, K1, D,
                            n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all,
                            y_all, partial, result, reduced, workspace, workspace_bytes, variant & ~0x1000, stream,
-                           (variant & 0x1000) ? 1 : 0);
+                           (variant & 0x1000) ? 1 : 0, 0, 0, 0, 0, v1_local, v2_local, y_local, offs_host);
 }
 
 extern "C" int crdpn_crd_momentum_update(void* bank1, void* bank2, int64_t row_stride, int bank_dtype,

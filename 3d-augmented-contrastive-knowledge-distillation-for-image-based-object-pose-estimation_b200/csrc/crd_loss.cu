@@ -23,7 +23,8 @@ int sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dty
                       float eps, float momentum, float one_minus_momentum, float* v1_all, float* v2_all, int64_t* y_all,
                       float* partial, double* result, float* reduced, void* workspace, size_t workspace_bytes, int variant,
                       void* stream, int idx_mode = 0, uint64_t seed = 0, uint64_t offset = 0, int64_t draw_n = 0,
-                      int64_t draw_base = 0);
+                      int64_t draw_base = 0, const float* v1_local = nullptr, const float* v2_local = nullptr,
+                      const int64_t* y_local = nullptr, const int32_t* offs_host = nullptr);
 }  // namespace crdpn
 
 using namespace crdpn;
@@ -92,16 +93,19 @@ extern "C" int crdpn_crd_loss_forward_sharded(
   if (B_loc <= 0 || B <= 0) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward_sharded: every rank must hold at least one anchor");
   int rc = embed_forward2(f_s, Ws, bs, s_dim, pre_s, v1_local, inv1, f_t, Wt, bt, t_dim, pre_t, v2_local, inv2, B_loc, D, stream);
   if (rc) return rc;
+  const int64_t* idx = contrast_idx;
+  const bool uniform_draw = idx == nullptr && alias_prob == nullptr && alias_alias == nullptr && !(variant & 0x200);
+  if (idx != nullptr || uniform_draw)
+    // the all-gather runs inside the core (with the filter pre-pass beside it); in-shard negatives, when asked for, are
+    // drawn by the scoring pass / the pre-pass itself (uniform sampler)
+    return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, idx, B, K1, D, n_data,
+                             k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all, y_all,
+                             partial, result, reduced, workspace, workspace_bytes, variant & ~0x1000, stream,
+                             uniform_draw ? 2 : ((variant & 0x1000) ? 1 : 0), seed, offset, row_end - row_begin, row_begin,
+                             v1_local, v2_local, y_local, offs_host);
   rc = crdpn_p2p_allgather_anchors(v1_local, v2_local, y_local, D, offs_host, peer_bufs_host, rank, world, Bmax, Dmax, v1_all,
                                    v2_all, y_all, stream);
   if (rc) return rc;
-  const int64_t* idx = contrast_idx;
-  if (idx == nullptr && alias_prob == nullptr && alias_alias == nullptr && !(variant & 0x200))
-    // K1-1 negatives per anchor inside this rank's shard, drawn by the scoring pass itself (uniform sampler)
-    return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, nullptr, B, K1, D,
-                             n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all,
-                             y_all, partial, result, reduced, workspace, workspace_bytes, variant, stream, 2, seed, offset,
-                             row_end - row_begin, row_begin);
   if (idx == nullptr) {  // K1-1 negatives drawn inside this rank's shard; column 0 stays the global positive index
     if (!idx_scratch) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward_sharded: contrast_idx is NULL and so is idx_scratch");
     rc = crdpn_alias_draw_contrast_local(alias_prob, alias_alias, row_end - row_begin, row_begin, y_all, B, K1, seed, offset,
