@@ -7,7 +7,8 @@ Drop-in modules and functions behind the reference's Python surface, both thin s
 * ``ShapeEncoderPC(feature_dim)(shapes[B,3,P]) -> [B,feature_dim]`` -- the teacher's PointNet encoder
   (``pointnet.py``; reference ``auxiliary/model.py:154-180``)
 * ``PointCloudSampler`` -- the encoder's input producer (``pointcloud.py``; reference ``auxiliary/dataset.py:121-150``)
-* ``FrozenPoseTail`` -- the KD-time teacher's tail (``pose_tail.py``; reference ``auxiliary/model.py:183-203, 238-272``)
+* ``FrozenPoseTail`` / ``PoseTail`` -- the ``PoseEstimator`` tail as one tcgen05 chain kernel, frozen and trainable
+  (``pose_tail.py``; reference ``auxiliary/model.py:183-203, 238-272``)
 * the loss code either side of them (``kd_losses.py``): ``infoNCE_KD`` / ``poseNCE_KD`` (``auxiliary/model_utils.py:225-285``),
   ``CELoss`` / ``DeltaLoss`` (``auxiliary/loss.py``), ``TemperatureScaledKLDivLoss`` / ``calculate_kd_loss_new``
   (``KD/vision/vanilla/vanilla_kd.py``)
@@ -25,12 +26,12 @@ __all__ = ["AliasMethod", "ContrastLoss", "ContrastMemory", "CRDLoss", "Embed", 
            "ShardedContrastMemory", "ShardedCRDLoss", "shard_bounds"]
 from .pointnet import ShapeEncoderPC  # noqa: F401,E402
 from .pointcloud import PointCloudSampler  # noqa: F401,E402
-from .pose_tail import FrozenPoseTail  # noqa: F401,E402
+from .pose_tail import FrozenPoseTail, PoseTail  # noqa: F401,E402
 from . import kd_losses  # noqa: F401,E402
 from .kd_losses import (CELoss, DeltaLoss, TemperatureScaledKLDivLoss, calculate_kd_loss_new, infoNCE_KD,  # noqa: F401,E402
                         poseNCE_KD, student_kd_step_loss)
 
 from .pipeline import StepPipeline  # noqa: F401,E402
 
-__all__ += ["StepPipeline", "ShapeEncoderPC", "PointCloudSampler", "FrozenPoseTail", "CELoss", "DeltaLoss", "TemperatureScaledKLDivLoss", "calculate_kd_loss_new", "infoNCE_KD",
+__all__ += ["StepPipeline", "ShapeEncoderPC", "PointCloudSampler", "FrozenPoseTail", "PoseTail", "CELoss", "DeltaLoss", "TemperatureScaledKLDivLoss", "calculate_kd_loss_new", "infoNCE_KD",
             "poseNCE_KD", "student_kd_step_loss"]

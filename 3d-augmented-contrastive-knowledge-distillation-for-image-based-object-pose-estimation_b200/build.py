@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libcrdpn_b200.so"
-SOURCES = ["host.cu", "crd_kernels.cu", "pointnet_kernels.cu", "pointnet_train.cu", "pointnet_backward.cu", "embed_kernels.cu", "p2p_kernels.cu", "crd_loss.cu", "kd_losses.cu", "pointcloud_sampler.cu", "crd_unfused.cu", "pointnet_train_split.cu"]
+SOURCES = ["host.cu", "crd_kernels.cu", "pointnet_kernels.cu", "pointnet_train.cu", "pointnet_backward.cu", "embed_kernels.cu", "p2p_kernels.cu", "crd_loss.cu", "kd_losses.cu", "pointcloud_sampler.cu", "crd_unfused.cu", "pointnet_train_split.cu", "pose_tail.cu"]
 # development probes (include/crdpn_b200_dev.h): their own library, never linked into the product .so
 DEV_LIB = PKG / "libcrdpn_b200_dev.so"
 DEV_SOURCES = ["umma_tf32_probe.cu", "host.cu"]

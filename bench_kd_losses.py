@@ -129,9 +129,30 @@ def bench_pose_tail(pkg, torch, dev, args, B=138, Fs=1024, Fi=1024):
         def run_tail16():
             tail16(sf, img)
 
-        return {"workload": f"pose_tail_B{B}_{Fs}+{Fi}", "eager_us": _time(torch, run_eager, steps, warmup),
-                "frozen_tail_us": _time(torch, run_tail, steps, warmup), "max_rel_diff_vs_eager": err,
-                "frozen_tail_bf16_us": _time(torch, run_tail16, steps, warmup),
-                "note": "eval-mode teacher tail: BN folded, concat as split-K, six heads as one GEMM, one CUDA graph (library "
-                        "GEMMs, full fp32; the eager arm's 1x1 convolutions run cuDNN's default TF32 path, which is where "
-                        "max_rel_diff_vs_eager comes from -- against the fp64 oracle the tail is within 2e-5)"}
+        # train mode: PoseTail (same kernel, batch-statistics BatchNorm) forward + backward vs the eager module chain
+        wbytes = sum(p_.numel() for n_, p_ in eager.named_parameters() if n_.endswith("weight") and p_.dim() >= 2) * 4
+        t_eager = _time(torch, run_eager, steps, warmup)
+        t_frozen, t_bf16 = _time(torch, run_tail, steps, warmup), _time(torch, run_tail16, steps, warmup)
+    ptail = pkg.PoseTail(img_feature_dim=Fi, shape_feature_dim=Fs).to(dev)
+    ptail.load_state_dict(eager.state_dict())
+    ptail.train()
+    eager.train()
+    sfg, imgg = sf.clone().requires_grad_(True), img.clone().requires_grad_(True)
+
+    def train_step(mod):
+        def run():
+            outs, x, p = mod(sfg, imgg)
+            (sum(o.sum() for o in outs) + x.sum() + p.sum()).backward()
+        return run
+
+    t_train, t_train_eager = _time(torch, train_step(ptail), steps, warmup), _time(torch, train_step(eager), steps, warmup)
+    return {"workload": f"pose_tail_B{B}_{Fs}+{Fi}", "eager_us": t_eager, "frozen_tail_us": t_frozen,
+            "max_rel_diff_vs_eager": err, "frozen_tail_bf16_us": t_bf16,
+            "weight_bytes_fp32": wbytes, "weight_stream_gbs": wbytes / (t_frozen * 1e-6) / 1e9,
+            "train_fwd_bwd_us": t_train, "train_fwd_bwd_eager_us": t_train_eager,
+            "note": "eval-mode teacher tail as ONE launch of the tcgen05 chain kernel (csrc/pose_tail.cu): BN folded, concat as the "
+                    "first layer's K range, six heads as one layer, weights streamed once as bf16 (hi, lo) images, three MMAs per "
+                    "product (fp32-accurate; bf16 = hi planes only); times are per call through the public module (host included); "
+                    "the eager arm's 1x1 convolutions run cuDNN's default TF32 path, which is where max_rel_diff_vs_eager comes "
+                    "from -- against the fp64 oracle the tail is within 1e-5.  train_*: PoseTail forward + backward (batch-statistics "
+                    "BatchNorm in the same kernel, backward = pull-backs + library GEMMs) vs the eager modules"}

@@ -309,6 +309,53 @@ int crdpn_pointcloud_sample(const double* vertices, const int64_t* cloud_offsets
                             const float* rotation_deg, const int64_t* subset, uint64_t seed, uint64_t offset,
                             int64_t B, int64_t P, float* out, int64_t* subset_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * PoseEstimator tail: cat(shape, img) -> DeformNet (2048 -> 2048 -> 1024 -> 512 -> 200,
+ * three BatchNorm1d + ReLU, tanh) -> six fc_* heads, and projector(img) (1024 -> 800 -> 400 -> 200, two BatchNorm1d).
+ * Replaces: /root/reference/auxiliary/model.py:183-203 (DeformNet.forward), :260-272 (the tail of PoseEstimator.forward);
+ * eval-mode call KD/common/base_class.py:363, train-mode call training.py:47 (model.train() at :30).
+ *
+ * The whole chain is ONE launch of a persistent tcgen05 kernel (csrc/pose_tail.cu): every layer is a set of
+ * (128-output tile, K-split) tasks over all SMs, layers hand over through device-side counters, weights stream once from
+ * HBM as bf16 (hi, lo) operand images -- three MMAs per product, fp32-accurate (outputs within 1e-5 of the fp32
+ * reference); CRDPN_POSE_TAIL_BF16 reads the hi planes only (half the bytes; north_star's 1e-2 tolerance mode).
+ * A chain is described by up to 10 layers; layer l computes act(BN(x_src W^T + bias)):
+ *   weights  : image made by crdpn_pose_tail_pack_weights from W [O, I] fp32 (row_scale: eval-mode BatchNorm folded in)
+ *   src      : -1 = cat(shape_feature, img_feature), -2 = img_feature, k >= 0 = the output of layer k (k < l)
+ *   act      : 0 none, 1 ReLU, 2 tanh
+ *   out      : [B, O] fp32 or NULL (intermediate activations are kept as operand images in the workspace only)
+ *   gamma .. : with CRDPN_POSE_TAIL_TRAIN and gamma != NULL the layer applies batch-statistics BatchNorm (biased variance
+ *              over the B rows, eps), writes save_mean / save_istd [O] and xhat [B, O] (may be NULL) for the backward, and
+ *              updates running_mean / running_var in place (momentum, unbiased variance) when they are non-NULL.
+ * B <= 256 rows per call.  The workspace (crdpn_pose_tail_workspace_bytes, 1024-byte aligned) must be ZERO when first used
+ * (its first 1 KB holds the hand-over counters, which the kernel leaves zero again) and belongs to one stream at a time.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct crdpn_pose_tail_layer {
+  const void* weights;
+  const float* bias;
+  int64_t O, I;
+  int32_t src, act;
+  float* out;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* save_mean;
+  float* save_istd;
+  float* xhat;
+} crdpn_pose_tail_layer;
+/* CRDPN_POSE_TAIL_PROF (debugging aid): per task, eight %globaltimer stamps (accumulator ready, TMEM drained, partial stored, tile
+ * complete, reduce loop left, after the memory fence, after the proxy fence, task done) as uint64 [n_tasks][8] at byte 1024 of the workspace; tasks are numbered in dependency order. */
+enum { CRDPN_POSE_TAIL_BF16 = 1, CRDPN_POSE_TAIL_TRAIN = 2, CRDPN_POSE_TAIL_PROF = 4 };
+int crdpn_pose_tail_image_bytes(int64_t O, int64_t I, size_t* bytes);
+int crdpn_pose_tail_pack_weights(const float* W, const float* row_scale, int64_t O, int64_t I, void* image, void* stream);
+/* layers: HOST array */
+int crdpn_pose_tail_workspace_bytes(const crdpn_pose_tail_layer* layers, int n_layers, int64_t B, int64_t shape_dim,
+                                    int64_t img_dim, size_t* bytes);
+int crdpn_pose_tail_forward(const crdpn_pose_tail_layer* layers, int n_layers, const float* shape_feature,
+                            const float* img_feature, int64_t B, int64_t shape_dim, int64_t img_dim, int flags,
+                            float bn_momentum, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The sharded step's forward as ONE call (one process per GPU, exchanges over NVLink peer memory as above): both embed
  * heads on the LOCAL anchors -> crdpn_p2p_allgather_anchors -> [contrast_idx == NULL: crdpn_alias_draw_contrast_local,
  * K1-1 negatives per anchor inside this rank's shard] -> crdpn_crd_step over the shard (gradients into `partial`

@@ -73,3 +73,70 @@ def reference_forward(m, shape_feature, img_feature):
         x = m.deformNet(gf.view(-1, gf.size(1), 1))
         outs = [getattr(m, k)(x) for k in HEADS]
         return outs, x, m.projector(img_feature)
+
+
+# ---- train mode (training.py:30,47,75): batch-statistics BatchNorm, gradients by autograd -----------------------------
+def _bn_train(x, sd, name, eps=1e-5):
+    mean = x.mean(0)
+    var = x.var(0, unbiased=False)
+    return (x - mean) / torch.sqrt(var + eps) * sd[name + ".weight"] + sd[name + ".bias"], mean, x.var(0, unbiased=True)
+
+
+def forward_train(sd: dict, shape_feature, img_feature, dtype=torch.float64, momentum=0.1):
+    """Train-mode tail in `dtype` on tensors that may require grad (``sd`` values are used as given, so pass float64 leaves
+    to differentiate).  -> (outs, x, p, new_running) where new_running maps '<bn>.running_mean/var' to the values after this
+    step (momentum update with the unbiased batch variance, as nn.BatchNorm1d does)."""
+    new_running = {}
+
+    def bn(x, name):
+        y, mean, uvar = _bn_train(x, sd, name)
+        new_running[name + ".running_mean"] = (1 - momentum) * sd[name + ".running_mean"].to(dtype) + momentum * mean.detach()
+        new_running[name + ".running_var"] = (1 - momentum) * sd[name + ".running_var"].to(dtype) + momentum * uvar.detach()
+        return y
+
+    h = torch.cat((shape_feature.to(dtype), img_feature.to(dtype)), 1)
+    for n in (1, 2, 3):
+        W = sd[f"deformNet.conv{n}.weight"]
+        h = torch.relu(bn(h @ W[:, :, 0].t() + sd[f"deformNet.conv{n}.bias"], f"deformNet.bn{n}"))
+    x = torch.tanh(h @ sd["deformNet.conv4.weight"][:, :, 0].t() + sd["deformNet.conv4.bias"])
+    outs = [x @ sd[k + ".weight"].t() + sd[k + ".bias"] for k in HEADS]
+    p = img_feature.to(dtype)
+    p = torch.relu(bn(p @ sd["projector.0.weight"].t() + sd["projector.0.bias"], "projector.1"))
+    p = torch.relu(bn(p @ sd["projector.3.weight"].t() + sd["projector.3.bias"], "projector.4"))
+    p = p @ sd["projector.6.weight"].t() + sd["projector.6.bias"]
+    return outs, x, p, new_running
+
+
+def train_step_with_grads(sd: dict, shape_feature, img_feature, g_outs, g_x, g_p, dtype=torch.float64):
+    """One train-mode forward + backward of L = sum <out_i, g_i> + <x, g_x> + <p, g_p>.  Returns (outs, x, p, new_running,
+    grads) with grads keyed like the state dict plus 'in/shape_feature', 'in/img_feature'."""
+    leaves = {k: v.detach().to(dtype).clone().requires_grad_(v.is_floating_point() and "running" not in k)
+              for k, v in sd.items() if v.is_floating_point()}
+    sf = shape_feature.detach().to(dtype).clone().requires_grad_(True)
+    img = img_feature.detach().to(dtype).clone().requires_grad_(True)
+    outs, x, p, new_running = forward_train(leaves, sf, img, dtype)
+    loss = sum((o * g.to(dtype)).sum() for o, g in zip(outs, g_outs)) + (x * g_x.to(dtype)).sum() + (p * g_p.to(dtype)).sum()
+    loss.backward()
+    grads = {k: v.grad for k, v in leaves.items() if v.requires_grad and v.grad is not None}
+    grads["in/shape_feature"], grads["in/img_feature"] = sf.grad, img.grad
+    return [o.detach() for o in outs], x.detach(), p.detach(), new_running, grads
+
+
+def reference_train_step(m, shape_feature, img_feature, g_outs, g_x, g_p):
+    """The reference's own modules in train mode (fp32): the same forward + backward.  `m` is modified (running statistics,
+    .grad); returns (outs, x, p, grads) keyed like the tail's state dict plus the two inputs."""
+    m.train()
+    for q in m.parameters():
+        q.grad = None
+    sf = shape_feature.clone().requires_grad_(True)
+    img = img_feature.clone().requires_grad_(True)
+    gf = torch.cat((sf, img), 1)
+    x = m.deformNet(gf.view(-1, gf.size(1), 1))
+    outs = [getattr(m, k)(x) for k in HEADS]
+    p = m.projector(img)
+    loss = sum((o * g).sum() for o, g in zip(outs, g_outs)) + (x * g_x).sum() + (p * g_p).sum()
+    loss.backward()
+    grads = {k: v.grad.detach().clone() for k, v in m.named_parameters()
+             if k.startswith(("deformNet.", "fc_", "projector.")) and v.grad is not None}
+    grads["in/shape_feature"], grads["in/img_feature"] = sf.grad.detach().clone(), img.grad.detach().clone()
+    return [o.detach() for o in outs], x.detach(), p.detach(), grads

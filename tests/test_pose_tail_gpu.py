@@ -1,5 +1,7 @@
-"""GPU parity of FrozenPoseTail (folded weights, split-K concat, concatenated heads, one CUDA graph) against the reference's
-own outputs (tests/golden/pose_tail_golden.npz) and the oracle: fp32, <= 1e-5 of each tensor's max."""
+"""GPU parity of the pose-tail chain kernel (csrc/pose_tail.cu) through FrozenPoseTail / PoseTail against the reference's
+own outputs (tests/golden/pose_tail_golden.npz, made by /root/reference's PoseEstimator modules) and the fp64 oracle.
+fp32-accurate mode (three bf16 hi/lo MMAs per product): <= 1e-4 of each tensor's max (north_star's fp32 tolerance; measured
+~1e-5); bf16 mode: <= 2e-2."""
 from pathlib import Path
 
 import numpy as np
@@ -10,6 +12,7 @@ from oracle import pose_tail_oracle as pto
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden" / "pose_tail_golden.npz"
+TOL = 1e-4
 
 
 def _rel(a, b):
@@ -17,23 +20,26 @@ def _rel(a, b):
     return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_matches_reference_golden(pkg, cuda, graph):
+def _gold():
     g = np.load(GOLD)
-    sd = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
-    tail = pkg.FrozenPoseTail.from_state_dict(sd, graph=graph).to(cuda)
+    return g, {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+
+
+def test_matches_reference_golden(pkg, cuda):
+    g, sd = _gold()
+    tail = pkg.FrozenPoseTail.from_state_dict(sd).to(cuda)
     sf, img = torch.from_numpy(g["in/shape_feature"]).to(cuda), torch.from_numpy(g["in/img_feature"]).to(cuda)
-    for _ in range(2):      # second call replays the captured graph
+    n0 = pkg._native.launch_count()
+    for it in range(3):      # repeated calls reuse the workspace: the hand-over counters must come back to zero
         outs, x, p = tail(sf, img)
-        assert _rel(x.cpu().numpy(), g["out/x"]) < 1e-5 and _rel(p.cpu().numpy(), g["out/projector"]) < 1e-5
+        assert _rel(x.cpu().numpy(), g["out/x"]) < TOL and _rel(p.cpu().numpy(), g["out/projector"]) < TOL
         for i, o in enumerate(outs):
-            assert o.shape == g[f"out/head{i}"].shape and _rel(o.cpu().numpy(), g[f"out/head{i}"]) < 1e-5
+            assert o.shape == g[f"out/head{i}"].shape and _rel(o.cpu().numpy(), g[f"out/head{i}"]) < TOL
+    assert pkg._native.launch_count() - n0 == 8 + 3   # eight weight packs once, then ONE launch per call
 
 
-def test_reference_size_and_new_inputs_through_the_graph(pkg, cuda):
-    """The KD-time shapes (138 rows, 1024 + 1024 features) with random weights vs the oracle; the captured graph must pick
-    up NEW inputs on replay, and a different batch size captures its own graph."""
-    torch.manual_seed(0)
+def _random_reference_size_state(seed=0):
+    torch.manual_seed(seed)
     sd = {}
     C = 2048
     for n, (i, o) in enumerate(((C, C), (C, C // 2), (C // 2, C // 4), (C // 4, 200)), 1):
@@ -49,18 +55,26 @@ def test_reference_size_and_new_inputs_through_the_graph(pkg, cuda):
     for bn, o in ((1, 800), (4, 400)):
         sd.update({f"projector.{bn}.weight": torch.randn(o), f"projector.{bn}.bias": torch.randn(o),
                    f"projector.{bn}.running_mean": torch.randn(o) * 0.2, f"projector.{bn}.running_var": torch.rand(o) + 0.5})
+    return sd
+
+
+def test_reference_size_batches_and_modes(pkg, cuda):
+    """The KD-time shapes (138 rows, 1024 + 1024 features) and the training batch of 160 with random weights vs the oracle;
+    a ragged small batch; more rows than one call takes (chunked); bf16 mode; run-to-run bit reproducibility."""
+    sd = _random_reference_size_state()
     tail = pkg.FrozenPoseTail.from_state_dict(sd).to(cuda)
-    for B, seed in ((138, 1), (138, 2), (46, 3)):
+    for B, seed in ((138, 1), (138, 2), (46, 3), (160, 4), (5, 5), (300, 6)):
         g = torch.Generator().manual_seed(seed)
         sf, img = torch.randn(B, 1024, generator=g), torch.randn(B, 1024, generator=g)
         outs, x, p = tail(sf.to(cuda), img.to(cuda))
         w_outs, w_x, w_p = pto.forward(sd, sf, img)
-        assert _rel(x.cpu().numpy(), w_x.numpy()) < 2e-5 and _rel(p.cpu().numpy(), w_p.numpy()) < 2e-5
-        assert all(_rel(a.cpu().numpy(), b.numpy()) < 2e-5 for a, b in zip(outs, w_outs))
-    assert len(tail._graphs) == 2
+        assert _rel(x.cpu().numpy(), w_x.numpy()) < TOL and _rel(p.cpu().numpy(), w_p.numpy()) < TOL, B
+        assert all(_rel(a.cpu().numpy(), b.numpy()) < TOL for a, b in zip(outs, w_outs)), B
+        first = [t.clone() for t in list(outs) + [x, p]]
+        outs2, x2, p2 = tail(sf.to(cuda), img.to(cuda))
+        assert all(torch.equal(a, b) for a, b in zip(first, list(outs2) + [x2, p2])), "not bit-reproducible"
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         tail(torch.zeros(2, 1024), torch.zeros(2, 1024))
-    # bf16 mode: north_star's 1e-2 tolerance
     tail16 = pkg.FrozenPoseTail.from_state_dict(sd, dtype=torch.bfloat16).to(cuda)
     g = torch.Generator().manual_seed(9)
     sf, img = torch.randn(138, 1024, generator=g), torch.randn(138, 1024, generator=g)
@@ -69,3 +83,84 @@ def test_reference_size_and_new_inputs_through_the_graph(pkg, cuda):
     assert x.dtype == torch.float32
     assert _rel(x.cpu().numpy(), w_x.numpy()) < 2e-2 and _rel(p.cpu().numpy(), w_p.numpy()) < 2e-2
     assert all(_rel(a.cpu().numpy(), b.numpy()) < 2e-2 for a, b in zip(outs, w_outs))
+
+
+def test_trainable_tail_loads_reference_checkpoint_and_matches_golden(pkg, cuda):
+    """PoseTail carries the reference's parameter names: the golden state dict loads strictly; eval output equals the
+    reference's; train mode (training.py:30,47,75) reproduces the reference's outputs, running statistics and EVERY gradient."""
+    g, sd = _gold()
+    tail = pkg.PoseTail(img_feature_dim=64, shape_feature_dim=32)
+    full = dict(sd)
+    for k, v in tail.state_dict().items():
+        if k.endswith("num_batches_tracked"):
+            full.setdefault(k, torch.zeros((), dtype=torch.long))
+    tail.load_state_dict(full, strict=True)
+    tail = tail.to(cuda)
+    sf = torch.from_numpy(g["in/shape_feature"]).to(cuda).requires_grad_(True)
+    img = torch.from_numpy(g["in/img_feature"]).to(cuda).requires_grad_(True)
+    tail.eval()
+    outs, x, p = tail(sf, img)
+    assert _rel(x.cpu().numpy(), g["out/x"]) < TOL and _rel(p.cpu().numpy(), g["out/projector"]) < TOL
+    tail.train()
+    outs, x, p = tail(sf, img)
+    assert _rel(x.detach().cpu().numpy(), g["train/out/x"]) < TOL and _rel(p.detach().cpu().numpy(), g["train/out/projector"]) < TOL
+    for i, o in enumerate(outs):
+        assert _rel(o.detach().cpu().numpy(), g[f"train/out/head{i}"]) < TOL
+    loss = sum((o * torch.from_numpy(g[f"train/gin/head{i}"]).to(cuda)).sum() for i, o in enumerate(outs))
+    loss = loss + (x * torch.from_numpy(g["train/gin/x"]).to(cuda)).sum() + (p * torch.from_numpy(g["train/gin/projector"]).to(cuda)).sum()
+    loss.backward()
+    msd = tail.state_dict()
+    for k in g.files:
+        if k.startswith("train/state/") and "running" in k:
+            assert _rel(msd[k[len("train/state/"):]].cpu().numpy(), g[k]) < TOL, k
+        if k == "train/state/deformNet.bn1.num_batches_tracked":
+            assert int(msd["deformNet.bn1.num_batches_tracked"]) == int(g[k])
+    grads = {n: q.grad for n, q in tail.named_parameters()}
+    grads["in/shape_feature"], grads["in/img_feature"] = sf.grad, img.grad
+    checked = 0
+    for k in g.files:
+        if not k.startswith("train/grad/"):
+            continue
+        name = k[len("train/grad/"):]
+        want, got = g[k], grads[name].detach().cpu().numpy()
+        assert got.shape == want.shape, name
+        if np.abs(want).max() < 1e-4:   # biases in front of train-mode BatchNorm: exactly zero up to rounding, both sides
+            assert np.abs(got).max() < 1e-3, name
+        else:
+            assert _rel(got, want) < 5e-4, name
+        checked += 1
+    assert checked == 38
+
+
+def test_train_mode_reference_size_vs_oracle(pkg, cuda):
+    """Batch 160 x (1024 + 1024): train-mode outputs, saved running statistics and a sample of gradients vs the fp64 oracle."""
+    sd = _random_reference_size_state(seed=3)
+    tail = pkg.PoseTail(img_feature_dim=1024, shape_feature_dim=1024)
+    full = dict(sd)
+    for k in tail.state_dict():
+        if k.endswith("num_batches_tracked"):
+            full[k] = torch.zeros((), dtype=torch.long)
+    tail.load_state_dict(full)
+    tail = tail.to(cuda).train()
+    gen = torch.Generator().manual_seed(11)
+    B = 160
+    sf, img = torch.randn(B, 1024, generator=gen), torch.randn(B, 1024, generator=gen)
+    g_outs = [torch.randn(B, w, generator=gen) for w in (24, 12, 24, 24, 12, 24)]
+    g_x, g_p = torch.randn(B, 200, generator=gen), torch.randn(B, 200, generator=gen)
+    sfd, imgd = sf.to(cuda).requires_grad_(True), img.to(cuda).requires_grad_(True)
+    outs, x, p = tail(sfd, imgd)
+    loss = sum((o * gg.to(cuda)).sum() for o, gg in zip(outs, g_outs)) + (x * g_x.to(cuda)).sum() + (p * g_p.to(cuda)).sum()
+    loss.backward()
+    w_outs, w_x, w_p, new_running, w_grads = pto.train_step_with_grads(sd, sf, img, g_outs, g_x, g_p)
+    assert _rel(x.detach().cpu().numpy(), w_x.numpy()) < TOL and _rel(p.detach().cpu().numpy(), w_p.numpy()) < TOL
+    assert all(_rel(a.detach().cpu().numpy(), b.numpy()) < TOL for a, b in zip(outs, w_outs))
+    msd = tail.state_dict()
+    for k, v in new_running.items():
+        assert _rel(msd[k].cpu().numpy(), v.numpy()) < TOL, k
+    got = {n: q.grad for n, q in tail.named_parameters()}
+    got["in/shape_feature"], got["in/img_feature"] = sfd.grad, imgd.grad
+    for name in ("deformNet.conv1.weight", "deformNet.conv3.weight", "deformNet.bn1.weight", "deformNet.bn2.bias", "deformNet.conv4.bias",
+                 "fc_reg_ele.weight", "fc_cls_azi.bias", "projector.0.weight", "projector.4.weight", "projector.6.weight",
+                 "in/shape_feature", "in/img_feature"):
+        want = w_grads[name].numpy()
+        assert _rel(got[name].detach().cpu().numpy().reshape(want.shape), want) < 5e-4, name
