@@ -14,6 +14,13 @@ _LIB = None
 
 F32, BF16 = 0, 1
 
+
+class PoseTailLayer(ctypes.Structure):   # crdpn_pose_tail_layer (include/crdpn_b200.h)
+    _fields_ = [("weights", c_void_p), ("bias", c_void_p), ("O", c_int64), ("I", c_int64), ("src", ctypes.c_int32),
+                ("act", ctypes.c_int32), ("out", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p),
+                ("running_var", c_void_p), ("save_mean", c_void_p), ("save_istd", c_void_p), ("xhat", c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/crdpn_b200.h one-to-one
 _SIGNATURES = {
     "crdpn_abi_version": (c_int, []),
@@ -120,6 +127,11 @@ _SIGNATURES = {
     "crdpn_pointnet_sync_blocks": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_int), POINTER(c_int),
                                            POINTER(c_size_t), POINTER(c_int64), POINTER(c_int)]),
     "crdpn_pointnet_backward_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t)]),
+    "crdpn_pose_tail_image_bytes": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
+    "crdpn_pose_tail_pack_weights": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "crdpn_pose_tail_workspace_bytes": (c_int, [POINTER(PoseTailLayer), c_int, c_int64, c_int64, c_int64, POINTER(c_size_t)]),
+    "crdpn_pose_tail_forward": (c_int, [POINTER(PoseTailLayer), c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
+                                        c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "crdpn_pointnet_backward": (c_int, [c_void_p, c_int64, c_int64, c_int64] + [c_void_p] * 9 +
                                 [c_void_p, c_void_p, c_size_t] + [c_void_p] * 12 + [c_void_p, c_size_t, c_void_p]),
 }

@@ -22,7 +22,6 @@ There is no CPU path: non-CUDA inputs raise.
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_int32, c_int64, c_void_p
 
 import torch
 from torch import nn
@@ -34,28 +33,11 @@ BF16_FLAG, TRAIN_FLAG = 1, 2
 NONE, RELU, TANH = 0, 1, 2
 
 
-class _Layer(ctypes.Structure):   # crdpn_pose_tail_layer (include/crdpn_b200.h)
-    _fields_ = [("weights", c_void_p), ("bias", c_void_p), ("O", c_int64), ("I", c_int64), ("src", c_int32), ("act", c_int32),
-                ("out", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p),
-                ("running_var", c_void_p), ("save_mean", c_void_p), ("save_istd", c_void_p), ("xhat", c_void_p)]
+_Layer = _native.PoseTailLayer
 
 
 def _bind():
-    lib = _native.lib()
-    if getattr(lib, "_pose_tail_bound", False):
-        return lib
-    lib.crdpn_pose_tail_image_bytes.restype = ctypes.c_int
-    lib.crdpn_pose_tail_image_bytes.argtypes = [c_int64, c_int64, ctypes.POINTER(ctypes.c_size_t)]
-    lib.crdpn_pose_tail_pack_weights.restype = ctypes.c_int
-    lib.crdpn_pose_tail_pack_weights.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]
-    lib.crdpn_pose_tail_workspace_bytes.restype = ctypes.c_int
-    lib.crdpn_pose_tail_workspace_bytes.argtypes = [ctypes.POINTER(_Layer), ctypes.c_int, c_int64, c_int64, c_int64,
-                                                    ctypes.POINTER(ctypes.c_size_t)]
-    lib.crdpn_pose_tail_forward.restype = ctypes.c_int
-    lib.crdpn_pose_tail_forward.argtypes = [ctypes.POINTER(_Layer), ctypes.c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64,
-                                            ctypes.c_int, ctypes.c_float, ctypes.c_float, c_void_p, ctypes.c_size_t, c_void_p]
-    lib._pose_tail_bound = True
-    return lib
+    return _native.lib()
 
 
 def _aligned(nbytes: int, device, zero=False) -> torch.Tensor:
