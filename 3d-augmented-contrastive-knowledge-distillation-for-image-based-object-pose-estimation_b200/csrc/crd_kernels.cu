@@ -76,7 +76,8 @@ struct ScoreParams {
   const int* ucount;
   long long* anchor_start;   // [B + 1] out: start of every anchor in the compact space (for the reduction kernel)
 };
-constexpr int kFilterChunk = 2048;   // entries per filter unit (one CTA of 256 threads, 8 entries per thread)
+constexpr int kFilterEPT = 16;        // entries per thread of the filter pre-pass (multiple of 4)
+constexpr int kFilterChunk = 256 * kFilterEPT;   // entries per filter unit (one CTA of 256 threads)
 constexpr int kMaxUnits = 4096;      // unit-count prefix lives in shared memory
 
 struct FinalizeParams {
@@ -164,51 +165,56 @@ __device__ __forceinline__ long long contrast_entry(const ScoreParams& p, long l
   return p.draw_base + (long long)__umul64hi(bits, (unsigned long long)p.draw_n);
 }
 
-// Row-sharded step, pre-pass: one CTA per (anchor, chunk of kFilterChunk entries k >= 1).  Every thread loads its 8 entries
-// at once (one memory latency for the whole chunk), the survivors -- entries whose row this shard owns -- are written in
-// list order (ballots + a 64-entry prefix), so the scoring pass that follows neither scans nor skips anything and its
-// result does not depend on timing.  3M entries take ~6 us this way; inside the scoring pass the same scan is a chain of
-// dependent steps per warp that costs ~20 us of a 75 us kernel on a shard that owns 1/8 of the rows.
-__global__ void __launch_bounds__(256) crd_shard_filter_kernel(const ScoreParams p, int* __restrict__ cl, int* __restrict__ ucount) {
-  __shared__ int s_cnt[64], s_pre[65];
+// Row-sharded step, pre-pass: one CTA per (anchor, chunk of kFilterChunk entries k >= 1).  Every thread loads its
+// kFilterEPT entries at once (one memory latency for the whole chunk, the whole list in flight across the grid: B * NC CTAs
+// are ONE wave at 5 CTAs per SM), the survivors -- entries whose row this shard owns -- are written in list order (ballots +
+// a prefix over the (slice, warp) counts), so the scoring pass that follows neither scans nor skips anything and its
+// result does not depend on timing.  Inside the scoring pass the same scan is a chain of dependent steps per warp that
+// costs ~20 us of a 75 us kernel on a shard that owns 1/8 of the rows.
+__global__ void __launch_bounds__(256, 5) crd_shard_filter_kernel(const ScoreParams p, int* __restrict__ cl, int* __restrict__ ucount) {
+  constexpr int EPT = kFilterEPT, NCNT = EPT * 8, CPL = NCNT / 32;   // counts: one per (slice of 256 entries, warp)
+  __shared__ int s_cnt[NCNT], s_pre[NCNT + 1];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / p.NC, c = blockIdx.x - b * p.NC;
   const long long anchor_base = (long long)b * p.K1;
   const int k0 = 1 + c * kFilterChunk;
-  int row[8];
-  unsigned mask[8];
+  int row[EPT];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < EPT; ++j) {
     const int k = k0 + j * 256 + tid;
     long long r = -1;
     if (k < p.K1) r = contrast_entry(p, anchor_base + k, b, anchor_base);
     row[j] = (r >= p.row_begin && r < p.row_end) ? (int)(r - p.row_begin) : -1;
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    mask[j] = __ballot_sync(0xffffffffu, row[j] >= 0);
-    if (lane == 0) s_cnt[j * 8 + warp] = __popc(mask[j]);
+  for (int j = 0; j < EPT; ++j) {
+    const unsigned m = __ballot_sync(0xffffffffu, row[j] >= 0);
+    if (lane == 0) s_cnt[j * 8 + warp] = __popc(m);
   }
   __syncthreads();
-  if (warp == 0) {   // exclusive prefix over the 64 (slice, warp) counts, in list order
-    int a = s_cnt[lane], b2 = s_cnt[32 + lane];
-    int ia = a, ib = b2;
+  if (warp == 0) {   // exclusive prefix over the (slice, warp) counts, in list order: CPL consecutive counts per lane
+    int cv[CPL], tot = 0;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { cv[i] = s_cnt[lane * CPL + i]; tot += cv[i]; }
+    int inc = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-      if (lane >= o) { ia += ta; ib += tb; }
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    const int tot_a = __shfl_sync(0xffffffffu, ia, 31);
-    s_pre[lane] = ia - a;
-    s_pre[32 + lane] = tot_a + ib - b2;
-    if (lane == 31) s_pre[64] = tot_a + ib;
+    int run = inc - tot;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { s_pre[lane * CPL + i] = run; run += cv[i]; }
+    if (lane == 31) s_pre[NCNT] = inc;
   }
   __syncthreads();
   int* dst = cl + (size_t)blockIdx.x * kFilterChunk;
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (row[j] >= 0) dst[s_pre[j * 8 + warp] + __popc(mask[j] & ((1u << lane) - 1u))] = row[j];
-  if (tid == 0) ucount[blockIdx.x] = s_pre[64];
+  for (int j = 0; j < EPT; ++j) {
+    const unsigned m = __ballot_sync(0xffffffffu, row[j] >= 0);
+    if (row[j] >= 0) dst[s_pre[j * 8 + warp] + __popc(m & ((1u << lane) - 1u))] = row[j];
+  }
+  if (tid == 0) ucount[blockIdx.x] = s_pre[NCNT];
 }
 
 template <typename T> struct Unpack;

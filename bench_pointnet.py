@@ -61,10 +61,10 @@ def bench_pointnet_replicas(pkg, torch, dist, dev, rank, world, steps, warmup, B
            "tflops_all_ranks": world * FLOP_PER_POINT * B * P / (ms * 1e-3) / 1e12,
            "note": "replicas only: one batch of clouds per rank, no collective (clouds are independent in eval mode)"}
     # train mode over all ranks: batch statistics of the GLOBAL batch (sync_batchnorm), gradients summed over ranks
-    try:
+    def train_leg(comm):
         tr = pkg.ShapeEncoderPC(F)
         tr.load_state_dict(synthetic_state(torch, F))
-        tr = tr.to(dev).train().sync_batchnorm()
+        tr = tr.to(dev).train().sync_batchnorm(comm=comm, equal_batches=(comm == "p2p"))
         gout = torch.randn(B, F, device=dev)
 
         def step():
@@ -84,10 +84,20 @@ def bench_pointnet_replicas(pkg, torch, dist, dev, rank, world, steps, warmup, B
         dist.barrier()
         tms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        res["train_sync_batchnorm"] = {"ms_per_step": tms.item(), "points_per_sec": world * B * P / (tms.item() * 1e-3),
-                                       "exchanges_per_step": 6 + 1,
-                                       "note": "forward+backward, per-channel accumulators summed over ranks at 3+3 hand-offs "
-                                               "(NCCL all-reduce of <= 2F doubles; the gradients come out globally summed)"}
+        return tms.item()
+
+    try:
+        t_p2p = train_leg("p2p")
+        res["train_sync_batchnorm"] = {
+            "ms_per_step": t_p2p, "points_per_sec": world * B * P / (t_p2p * 1e-3), "exchange_kernels_per_step": 6,
+            "note": "forward+backward (fp32-accurate train kernels), per-channel accumulators summed over ranks at 3+3 hand-offs, each "
+                    "ONE kernel over NVLink peer memory (crdpn_p2p_allreduce_blocks, rank-ordered sums); equal batches promised, "
+                    "so no host read per step; the gradients come out globally summed and identical on every rank"}
+        try:
+            t_nccl = train_leg("dist")
+            res["train_sync_batchnorm"]["nccl_hand_offs"] = {"ms_per_step": t_nccl, "points_per_sec": world * B * P / (t_nccl * 1e-3)}
+        except Exception as exc:
+            res["train_sync_batchnorm"]["nccl_hand_offs"] = {"error": str(exc)}
     except Exception as exc:
         res["train_sync_batchnorm"] = {"error": str(exc)}
     return res
