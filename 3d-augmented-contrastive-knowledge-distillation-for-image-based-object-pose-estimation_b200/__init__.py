@@ -31,7 +31,7 @@ from . import kd_losses  # noqa: F401,E402
 from .kd_losses import (CELoss, DeltaLoss, TemperatureScaledKLDivLoss, calculate_kd_loss_new, infoNCE_KD,  # noqa: F401,E402
                         poseNCE_KD, student_kd_step_loss)
 
-from .pipeline import StepPipeline  # noqa: F401,E402
+from .pipeline import GraphedStep, StepPipeline  # noqa: F401,E402
 
-__all__ += ["StepPipeline", "ShapeEncoderPC", "PointCloudSampler", "FrozenPoseTail", "PoseTail", "CELoss", "DeltaLoss", "TemperatureScaledKLDivLoss", "calculate_kd_loss_new", "infoNCE_KD",
+__all__ += ["StepPipeline", "GraphedStep", "ShapeEncoderPC", "PointCloudSampler", "FrozenPoseTail", "PoseTail", "CELoss", "DeltaLoss", "TemperatureScaledKLDivLoss", "calculate_kd_loss_new", "infoNCE_KD",
             "poseNCE_KD", "student_kd_step_loss"]

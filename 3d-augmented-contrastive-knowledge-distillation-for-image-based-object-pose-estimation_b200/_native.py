@@ -15,6 +15,12 @@ _LIB = None
 F32, BF16 = 0, 1
 
 
+class PoseTailBwdLayer(ctypes.Structure):   # crdpn_pose_tail_bwd_layer (include/crdpn_b200.h)
+    _fields_ = [("W", c_void_p), ("y", c_void_p), ("xhat", c_void_p), ("gamma", c_void_p), ("istd", c_void_p), ("g_out", c_void_p),
+                ("dW", c_void_p), ("db", c_void_p), ("dgamma", c_void_p), ("dbeta", c_void_p), ("O", c_int64), ("I", c_int64),
+                ("src", ctypes.c_int32), ("act", ctypes.c_int32)]
+
+
 class PoseTailLayer(ctypes.Structure):   # crdpn_pose_tail_layer (include/crdpn_b200.h)
     _fields_ = [("weights", c_void_p), ("bias", c_void_p), ("O", c_int64), ("I", c_int64), ("src", ctypes.c_int32),
                 ("act", ctypes.c_int32), ("out", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p),
@@ -132,6 +138,9 @@ _SIGNATURES = {
     "crdpn_pose_tail_workspace_bytes": (c_int, [POINTER(PoseTailLayer), c_int, c_int64, c_int64, c_int64, POINTER(c_size_t)]),
     "crdpn_pose_tail_forward": (c_int, [POINTER(PoseTailLayer), c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
                                         c_float, c_float, c_void_p, c_size_t, c_void_p]),
+    "crdpn_pose_tail_backward_workspace_bytes": (c_int, [POINTER(PoseTailBwdLayer), c_int, c_int64, POINTER(c_size_t)]),
+    "crdpn_pose_tail_backward": (c_int, [POINTER(PoseTailBwdLayer), c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crdpn_pointnet_backward": (c_int, [c_void_p, c_int64, c_int64, c_int64] + [c_void_p] * 9 +
                                 [c_void_p, c_void_p, c_size_t] + [c_void_p] * 12 + [c_void_p, c_size_t, c_void_p]),
 }

@@ -217,8 +217,13 @@ class _CRDLossFunction(torch.autograd.Function):
             else:
                 variant |= mem.IDX32
         smp = mem.multinomial
+        dev_offset = None
         if contrast_idx is None and smp.uniform and not (variant & mem.STREAM):
             cidx_ptr, scratch_ptr = None, None     # the scoring pass draws the negatives itself: no list in memory
+            dev_offset = mem._device_offset(dev)
+            if dev_offset is not None:             # CUDA-graph replays: the advancing part of the offset lives on the device
+                variant |= mem.DEVICE_OFFSET
+                scratch_ptr = dev_offset.data_ptr()
         elif contrast_idx is None:
             scratch = mem._idx_scratch
             if scratch is None or scratch.numel() != B * K1 or scratch.device != dev:
@@ -237,7 +242,7 @@ class _CRDLossFunction(torch.autograd.Function):
                 o_pre_s, o_pre_t, o_v1, o_v2, o_inv1, o_inv2,
                 result.data_ptr(), o_g1, o_g2, ws.data_ptr(), ws.numel(), variant, _stream_ptr(dev))
         _native.check(rc, "crdpn_crd_loss_forward")
-        if contrast_idx is None:
+        if contrast_idx is None and dev_offset is None:
             smp.offset += B * K1
         ctx.save_for_backward(arena, xs, xt, Wsc, Wtc)
         ctx.need_dx = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
@@ -417,8 +422,36 @@ class ContrastMemory(nn.Module):
         self._ws_cache = {}
         self._res = None
         self._idx_scratch = None
+        self._dev_offset = None   # see device_sampler_offset
         # host mirror of params (avoids a device->host read per step once Z is frozen)
         self._host = None
+
+    # -- sampler offset on the device (CUDA-graph replays) -----------------------------------------------------
+    def device_sampler_offset(self, enabled: bool = True):
+        """Keep the ADVANCING part of the negative sampler's Philox offset in device memory: the scoring pass adds the
+        counter to the (then fixed) host offset and a one-thread kernel advances it by B * (K+1) after every step.  A step
+        captured in a CUDA graph (``GraphedStep``) then draws fresh negatives on every replay -- the same negatives the
+        eager loop would have drawn -- instead of replaying the offset that was baked in at capture.  Applies to the
+        in-kernel uniform draw (``CRDLoss(f_s, f_t, idx)`` with uniform unigrams).  Disabling folds the counter back into
+        the host offset (one device read)."""
+        if enabled and self._dev_offset is None:
+            self._dev_offset = "pending"      # allocated on the step's device at first use
+        elif not enabled and self._dev_offset is not None:
+            if isinstance(self._dev_offset, torch.Tensor):
+                smp = self._sampler_for_offset()
+                smp.offset += int(self._dev_offset.item())
+            self._dev_offset = None
+        return self
+
+    def _sampler_for_offset(self):
+        return self.multinomial
+
+    def _device_offset(self, device):
+        if self._dev_offset is None:
+            return None
+        if not isinstance(self._dev_offset, torch.Tensor) or self._dev_offset.device != device:
+            self._dev_offset = torch.zeros(1, dtype=torch.int64, device=device)
+        return self._dev_offset
 
     # -- layout ---------------------------------------------------------------------------------------
     def _relayout(self):
@@ -463,6 +496,7 @@ class ContrastMemory(nn.Module):
 
     STREAM = 0x200   # variant bit: bank-streaming formulation of the step (csrc/crd_stream.cuh)
     IDX32 = 0x1000   # variant bit: contrast_idx is an int32 list
+    DEVICE_OFFSET = 0x4000   # variant bit: the sampler offset's advancing part is a device counter (CUDA-graph replays)
 
     def _step_variant(self, B, K1, D):
         """Variant passed to crdpn_crd_step.  ``self.streaming`` selects the bank-streaming formulation, which reads every

@@ -49,6 +49,7 @@ struct ScoreParams {
   const int* idx32;
   const long long* y;
   unsigned long long seed, offset;
+  const unsigned long long* offset_dev;   // optional device-resident addend to `offset` (CUDA-graph replays: see crd_loss.cu)
   long long draw_n, draw_base;
   int B, K1, D;
   long long row_begin, row_end;
@@ -105,6 +106,9 @@ struct FinalizeParams {
   float* reduced;
 };
 
+// set by crdpn_crd_loss_forward{,_sharded} around a step whose sampler offset lives on the device (variant bit 0x4000)
+thread_local const unsigned long long* g_sampler_offset_dev = nullptr;
+
 int sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dtype, void* const* peer_bufs_host, int rank,
                       int world, int64_t Bmax, int64_t Dmax, const int64_t* contrast_idx, int64_t B, int64_t K1, int64_t D,
                       int64_t n_data, int64_t k_total, int64_t row_begin, int64_t row_end, float T, float Z1, float Z2,
@@ -160,7 +164,7 @@ __device__ __forceinline__ long long contrast_entry(const ScoreParams& p, long l
   if (p.idx_mode == 1) return (long long)p.idx32[pos];
   if (pos == anchor_base) return p.y[b];
   unsigned rr[4];
-  philox4x32_10(p.seed, p.offset + (unsigned long long)pos, rr);
+  philox4x32_10(p.seed, p.offset + (p.offset_dev != nullptr ? __ldg(p.offset_dev) : 0ull) + (unsigned long long)pos, rr);
   const unsigned long long bits = ((unsigned long long)rr[0] << 32) | (unsigned long long)rr[1];
   return p.draw_base + (long long)__umul64hi(bits, (unsigned long long)p.draw_n);
 }
@@ -1121,6 +1125,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.idx32 = src ? src->idx32 : nullptr;
   sp.y = src ? (const long long*)src->y : nullptr;
   sp.seed = src ? src->seed : 0; sp.offset = src ? src->offset : 0;
+  sp.offset_dev = (src && src->mode == 2) ? g_sampler_offset_dev : nullptr;
   sp.draw_n = src ? src->draw_n : 0; sp.draw_base = src ? src->draw_base : 0;
   sp.B = (int)B; sp.K1 = (int)K1; sp.D = (int)D;
   sp.row_begin = row_begin; sp.row_end = row_end;
@@ -1494,6 +1499,7 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
       memset(&fpar, 0, sizeof(fpar));
       fpar.idx = (const long long*)contrast_idx; fpar.idx32 = (const int*)contrast_idx; fpar.idx_mode = idx_mode;
       fpar.seed = seed; fpar.offset = offset; fpar.draw_n = draw_n; fpar.draw_base = draw_base;
+      fpar.offset_dev = idx_mode == 2 ? g_sampler_offset_dev : nullptr;
       fpar.B = (int)B; fpar.K1 = (int)K1; fpar.D = (int)D; fpar.row_begin = row_begin; fpar.row_end = row_end; fpar.NC = (int)cp.NC;
       CRDPN_CUDA(cudaEventRecord(side->fork, st));
       CRDPN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));

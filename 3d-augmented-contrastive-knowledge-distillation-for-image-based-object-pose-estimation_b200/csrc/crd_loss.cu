@@ -25,6 +25,16 @@ int sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int bank_dty
                       void* stream, int idx_mode = 0, uint64_t seed = 0, uint64_t offset = 0, int64_t draw_n = 0,
                       int64_t draw_base = 0, const float* v1_local = nullptr, const float* v2_local = nullptr,
                       const int64_t* y_local = nullptr, const int32_t* offs_host = nullptr);
+extern thread_local const unsigned long long* g_sampler_offset_dev;   // crd_kernels.cu
+
+// CUDA-graph replays: with variant bit 0x4000 (CRDPN_VARIANT_DEVICE_OFFSET) and the in-kernel uniform draw, `idx_scratch`
+// is a device uint64 that is ADDED to `offset` by the kernels and advanced by B * K1 after the step, so that a captured
+// step draws fresh negatives on every replay (the host-side `offset` is baked into the graph).
+__global__ void sampler_offset_bump_kernel(unsigned long long* ctr, unsigned long long delta) { *ctr += delta; }
+struct DevOffsetScope {
+  explicit DevOffsetScope(const unsigned long long* p) { g_sampler_offset_dev = p; }
+  ~DevOffsetScope() { g_sampler_offset_dev = nullptr; }
+};
 }  // namespace crdpn
 
 using namespace crdpn;
@@ -44,11 +54,21 @@ extern "C" int crdpn_crd_loss_forward(
   int rc = embed_forward2(f_s, Ws, bs, s_dim, pre_s, v1, inv1, f_t, Wt, bt, t_dim, pre_t, v2, inv2, B, D, stream);
   if (rc) return rc;
   const int64_t* idx = contrast_idx;
-  if (idx == nullptr && alias_prob == nullptr && alias_alias == nullptr && !(variant & 0x200))
+  if (idx == nullptr && alias_prob == nullptr && alias_alias == nullptr && !(variant & 0x200)) {
     // uniform sampler: the scoring pass draws the negatives itself (same Philox stream, same indices, no list in memory)
-    return crdpn_crd_step_drawn(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, K1, D, n_data, k_total, row_begin, row_end, T,
-                                Z1, Z2, eps, momentum, one_minus_momentum, seed, offset, n_data, 0, result, grad_v1, grad_v2,
-                                workspace, workspace_bytes, variant, stream);
+    unsigned long long* ctr = (variant & 0x4000) ? reinterpret_cast<unsigned long long*>(idx_scratch) : nullptr;
+    if ((variant & 0x4000) && !ctr) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward: device sampler offset asked for, idx_scratch is NULL");
+    DevOffsetScope scope(ctr);
+    rc = crdpn_crd_step_drawn(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, K1, D, n_data, k_total, row_begin, row_end, T,
+                              Z1, Z2, eps, momentum, one_minus_momentum, seed, offset, n_data, 0, result, grad_v1, grad_v2,
+                              workspace, workspace_bytes, variant & ~0x4000, stream);
+    if (rc == 0 && ctr) {
+      sampler_offset_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, (unsigned long long)(B * K1));
+      CRDPN_LAUNCH_CHECK("sampler_offset_bump_kernel");
+    }
+    return rc;
+  }
+  if (variant & 0x4000) return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_loss_forward: the device sampler offset needs the in-kernel uniform draw");
   if (idx == nullptr) {
     if (!idx_scratch) return fail(CRDPN_E_BADARG, "crdpn_crd_loss_forward: contrast_idx is NULL and so is idx_scratch");
     rc = crdpn_alias_draw_contrast(alias_prob, alias_alias, n_data, y, B, K1, seed, offset, idx_scratch, stream);
@@ -95,14 +115,25 @@ extern "C" int crdpn_crd_loss_forward_sharded(
   if (rc) return rc;
   const int64_t* idx = contrast_idx;
   const bool uniform_draw = idx == nullptr && alias_prob == nullptr && alias_alias == nullptr && !(variant & 0x200);
-  if (idx != nullptr || uniform_draw)
+  if ((variant & 0x4000) && !(uniform_draw && idx_scratch))
+    return fail(CRDPN_E_UNSUPPORTED, "crdpn_crd_loss_forward_sharded: the device sampler offset needs the in-kernel uniform draw");
+  if (idx != nullptr || uniform_draw) {
     // the all-gather runs inside the core (with the filter pre-pass beside it); in-shard negatives, when asked for, are
     // drawn by the scoring pass / the pre-pass itself (uniform sampler)
-    return sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, idx, B, K1, D, n_data,
+    unsigned long long* ctr = (variant & 0x4000) ? reinterpret_cast<unsigned long long*>(idx_scratch) : nullptr;
+    DevOffsetScope scope(ctr);
+    variant &= ~0x4000;
+    rc = sharded_step_core(bank1, bank2, row_stride, bank_dtype, peer_bufs_host, rank, world, Bmax, Dmax, idx, B, K1, D, n_data,
                              k_total, row_begin, row_end, T, Z1, Z2, eps, momentum, one_minus_momentum, v1_all, v2_all, y_all,
                              partial, result, reduced, workspace, workspace_bytes, variant & ~0x1000, stream,
                              uniform_draw ? 2 : ((variant & 0x1000) ? 1 : 0), seed, offset, row_end - row_begin, row_begin,
                              v1_local, v2_local, y_local, offs_host);
+    if (rc == 0 && ctr) {
+      sampler_offset_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, (unsigned long long)(B * K1));
+      CRDPN_LAUNCH_CHECK("sampler_offset_bump_kernel");
+    }
+    return rc;
+  }
   rc = crdpn_p2p_allgather_anchors(v1_local, v2_local, y_local, D, offs_host, peer_bufs_host, rank, world, Bmax, Dmax, v1_all,
                                    v2_all, y_all, stream);
   if (rc) return rc;

@@ -14,8 +14,8 @@ bf16 (hi, lo) operand images, three MMAs per product = fp32-accurate):
 * ``PoseTail`` -- the trainable tail with the reference's own parameter names (``deformNet.conv1.weight`` ...
   ``projector.6.bias``), so a ``PoseEstimator`` checkpoint loads by key.  ``.eval()`` runs the folded chain; ``.train()``
   runs the same kernel with batch-statistics BatchNorm in its reduce step (running statistics updated in place) and
-  differentiates it: the backward applies the activation / BatchNorm pull-backs and the three GEMMs per layer
-  (library GEMMs on the saved activations).
+  differentiates it: the backward is one more foreign call (``crdpn_pose_tail_backward``: per layer the activation /
+  BatchNorm pull-back, ``dW = g^T x`` and ``dx = g W`` as fp32 FFMA kernels on the saved activations).
 
 There is no CPU path: non-CUDA inputs raise.
 """
@@ -258,8 +258,8 @@ class DeformNet(nn.Module):
 
 
 class _PoseTailTrainFunction(torch.autograd.Function):
-    """Train-mode chain: forward = one launch of the chain kernel with batch-statistics BatchNorm; backward = per layer the
-    activation and BatchNorm pull-backs and dW = g^T x, dx = g W on the activations the forward kept."""
+    """Train-mode chain: forward = eight weight packs + one launch of the chain kernel with batch-statistics BatchNorm;
+    backward = ``crdpn_pose_tail_backward`` (pull-backs, dW = g^T x, dx = g W on the activations the forward kept)."""
 
     @staticmethod
     def forward(ctx, tail, sf, img, *params):
@@ -285,7 +285,7 @@ class _PoseTailTrainFunction(torch.autograd.Function):
         for m in bns.values():
             if m.track_running_stats and m.num_batches_tracked is not None:
                 m.num_batches_tracked += 1
-        ctx.tail, ctx.outs, ctx.bn, ctx.biases_keepalive = tail, outs, bn, biases
+        ctx.tail, ctx.outs, ctx.bn, ctx.biases_keepalive, ctx.lin = tail, outs, bn, biases, lin
         ctx.save_for_backward(sf, img)
         return outs[4], outs[3], outs[7]
 
@@ -294,59 +294,54 @@ class _PoseTailTrainFunction(torch.autograd.Function):
         tail, outs, bn = ctx.tail, ctx.outs, ctx.bn
         sf, img = ctx.saved_tensors
         spec = tail.spec
-        lin, bns = tail._layer_params()
+        dev = img.device
         B = img.shape[0]
-        zero = lambda l: torch.zeros_like(outs[l])
-        g_out = [None] * len(spec)
-        g_out[4] = g_heads if g_heads is not None else zero(4)
-        g_out[3] = g_x
-        g_out[7] = g_p if g_p is not None else zero(7)
-        gW, gb, gG, gB = {}, {}, {}, {}
-        g_sf = g_img = None
-        for l in reversed(range(len(spec))):
-            g = g_out[l]
-            if g is None:
-                g = zero(l)
-            y = outs[l]
-            if spec[l]["act"] == RELU:
-                g = g * (y > 0)
-            elif spec[l]["act"] == TANH:
-                g = g * (1.0 - y * y)
-            if bn[l] is not None:
-                xh = bn[l]["xhat"]
-                gB[l] = g.sum(0)
-                gG[l] = (g * xh).sum(0)
-                g = (bn[l]["gamma"] * bn[l]["istd"]) * (g - gB[l] / B - xh * (gG[l] / B))
-            src = spec[l]["src"]
-            x_in = torch.cat((sf, img), 1) if src == -1 else img if src == -2 else outs[src]
+        lin = ctx.lin
+        f32 = lambda g: None if g is None else g.detach().to(torch.float32).contiguous()
+        g_ext = {3: f32(g_x), 4: f32(g_heads), 7: f32(g_p)}
+        arr = (_native.PoseTailBwdLayer * len(spec))()
+        dW, db, dG, dB = {}, {}, {}, {}
+        keep = []
+        for l, s in enumerate(spec):
             W = lin[l][0].detach()
-            W2 = W[:, :, 0] if W.dim() == 3 else W
-            gW[l] = (g.t() @ x_in).view_as(W)
-            gb[l] = g.sum(0)
-            gx = g @ W2
-            if src == -1:
-                g_sf = gx[:, :tail.shape_dim]
-                g_img = gx[:, tail.shape_dim:] if g_img is None else g_img + gx[:, tail.shape_dim:]
-            elif src == -2:
-                g_img = gx if g_img is None else g_img + gx
-            else:
-                g_out[src] = gx if g_out[src] is None else g_out[src] + gx
+            if not W.is_contiguous():
+                W = W.contiguous()
+                keep.append(W)
+            dW[l], db[l] = torch.empty_like(W), torch.empty(s["O"], dtype=torch.float32, device=dev)
+            a = arr[l]
+            a.W, a.y, a.O, a.I, a.src, a.act = W.data_ptr(), outs[l].data_ptr(), s["O"], s["I"], s["src"], s["act"]
+            a.g_out = _ptr(g_ext.get(l))
+            a.dW, a.db = dW[l].data_ptr(), db[l].data_ptr()
+            if bn[l] is not None:
+                dG[l], dB[l] = torch.empty_like(db[l]), torch.empty_like(db[l])
+                a.xhat, a.gamma, a.istd = bn[l]["xhat"].data_ptr(), bn[l]["gamma"].data_ptr(), bn[l]["istd"].data_ptr()
+                a.dgamma, a.dbeta = dG[l].data_ptr(), dB[l].data_ptr()
+        lib = _bind()
+        nbytes = ctypes.c_size_t()
+        _native.check(lib.crdpn_pose_tail_backward_workspace_bytes(arr, len(spec), B, ctypes.byref(nbytes)),
+                      "crdpn_pose_tail_backward_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        g_sf = torch.empty_like(sf) if ctx.needs_input_grad[1] else None
+        g_img = torch.empty_like(img) if ctx.needs_input_grad[2] else None
+        with _native.on_device(dev):
+            rc = lib.crdpn_pose_tail_backward(arr, len(spec), sf.data_ptr(), img.data_ptr(), B, tail.shape_dim, tail.img_dim,
+                                              _ptr(g_sf), _ptr(g_img), ws.data_ptr(), ws.numel(), _native.stream_ptr(dev))
+        _native.check(rc, "crdpn_pose_tail_backward")
         grads = []
         for kind, l in tail._param_order():
             if kind == "W":
-                grads.append(gW[l] if l != 4 else None)
+                grads.append(dW[l])
             elif kind == "b":
-                grads.append(gb[l] if l != 4 else None)
+                grads.append(db[l])
             elif kind == "G":
-                grads.append(gG[l])
+                grads.append(dG[l])
             elif kind == "B":
-                grads.append(gB[l])
+                grads.append(dB[l])
             elif kind == "HW":     # head h's rows of the concatenated head layer
-                lo = sum(tail.head_sizes[:l]); grads.append(gW[4][lo:lo + tail.head_sizes[l]])
-            elif kind == "Hb":
-                lo = sum(tail.head_sizes[:l]); grads.append(gb[4][lo:lo + tail.head_sizes[l]])
-        return (None, g_sf.contiguous() if ctx.needs_input_grad[1] else None,
-                g_img.contiguous() if ctx.needs_input_grad[2] else None, *grads)
+                lo = sum(tail.head_sizes[:l]); grads.append(dW[4][lo:lo + tail.head_sizes[l]])
+            else:
+                lo = sum(tail.head_sizes[:l]); grads.append(db[4][lo:lo + tail.head_sizes[l]])
+        return (None, g_sf, g_img, *grads)
 
 
 class PoseTail(nn.Module):

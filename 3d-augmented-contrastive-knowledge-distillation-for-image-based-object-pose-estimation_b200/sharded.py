@@ -255,6 +255,9 @@ class ShardedContrastMemory(ContrastMemory):
             self._local_sampler.to(device)
         return self._local_sampler
 
+    def _sampler_for_offset(self):
+        return getattr(self, "_local_sampler", None) or self.multinomial
+
     def _gather(self, v1, v2, y):
         """ONE packed exchange before the kernel: local anchors -> all anchors (uneven B_loc allowed)."""
         counts = self._ensure_counts(v1.shape[0], v1.device)
@@ -375,6 +378,7 @@ class _ShardedCRDLossFunction(torch.autograd.Function):
         f_red = f_all + 4 * BD
         o_red = base + 4 * f_red
         y_all = torch.empty(B, dtype=torch.int64, device=dev)
+        dev_offset = None
         m1, m2, stride, dt = mem._banks()
         variant = mem._step_variant(B, K1, D)
         ws = mem._workspace(B, K1, D, dev, variant)
@@ -392,6 +396,10 @@ class _ShardedCRDLossFunction(torch.autograd.Function):
             smp = mem._ensure_local_sampler(dev)
             if smp.uniform and not (variant & mem.STREAM):
                 scratch_ptr = None                        # the scoring pass draws the in-shard negatives itself
+                dev_offset = mem._device_offset(dev)
+                if dev_offset is not None:                # CUDA-graph replays: advancing part of the offset on the device
+                    variant |= mem.DEVICE_OFFSET
+                    scratch_ptr = dev_offset.data_ptr()
             else:
                 scratch = mem._idx_scratch
                 if scratch is None or scratch.numel() != B * K1 or scratch.device != dev:
@@ -408,7 +416,7 @@ class _ShardedCRDLossFunction(torch.autograd.Function):
                 o_pre_s, o_pre_t, o_v1l, o_v2l, o_inv1, o_inv2, o_v1a, o_v2a, y_all.data_ptr(), o_part, base, o_red,
                 ws.data_ptr(), ws.numel(), variant, _stream_ptr(dev))
         _native.check(rc, "crdpn_crd_loss_forward_sharded")
-        if contrast_idx is None:
+        if contrast_idx is None and dev_offset is None:
             smp.offset += B * K1
         ctx.save_for_backward(xs, xt, Wsc, Wtc)
         ctx.arena = arena

@@ -217,7 +217,7 @@ def time_shard_emulation(pkg, torch, dev, c, steps, warmup, shards):
             "score_kernel_ms": tot.value / max(n.value, 1)}
 
 
-def time_crd_e2e(pkg, torch, dev, c, steps, warmup, host_contrast_idx=False, idx_dtype=None, pipelined=True):
+def time_crd_e2e(pkg, torch, dev, c, steps, warmup, host_contrast_idx=False, idx_dtype=None, pipelined=True, graphed=False):
     """Public API, pinned HOST inputs every step: H2D of (f_s, f_t, idx[, contrast_idx]) + CRDLoss forward + backward +
     a D2H read of the loss.
 
@@ -247,9 +247,21 @@ def time_crd_e2e(pkg, torch, dev, c, steps, warmup, host_contrast_idx=False, idx
     def strict_step():
         return fwd_bwd([t.to(dev, non_blocking=True) for t in host]).item()  # D2H read of the step's result
 
-    pipe = pkg.StepPipeline(dev) if pipelined else None
+    pipe = pkg.StepPipeline(dev) if pipelined and not graphed else None
+    gstep = None
 
     def loop(n):
+        if graphed:
+            gstep.stage(*host)
+            for i in range(n):
+                gstep.run()
+                if i + 1 < n:
+                    gstep.stage(*host)     # next step's H2D overlaps this step's kernels
+                if gstep.pending() > 1:
+                    gstep.collect()        # loss of the previous step
+            while gstep.pending():
+                gstep.collect()
+            return
         if not pipelined:
             for _ in range(n):
                 strict_step()
@@ -266,6 +278,15 @@ def time_crd_e2e(pkg, torch, dev, c, steps, warmup, host_contrast_idx=False, idx
             pipe.collect()
 
     strict_step()                          # first call freezes Z
+    if graphed:
+        crit.contrast.device_sampler_offset()
+
+        def graph_fn(*dev_in):
+            loss = crit(dev_in[0], dev_in[1], dev_in[2], dev_in[3] if host_contrast_idx else None)
+            loss.backward()
+            return loss
+
+        gstep = pkg.GraphedStep(graph_fn, host, dev, grad_inputs=(0,), zero_grad=lambda: crit.zero_grad(set_to_none=True))
     loop(max(warmup, 3))                   # one-time costs (streams, pinned slots, device slots) stay outside the timed region
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -367,10 +388,12 @@ def run_own(args):
                     "achieved_gbs": achieved})
         return
     esteps = max(args.steps, 20)
-    e2e = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup)
+    e2e = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, graphed=True)
+    e2e_pipe = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup)
     e2e_strict = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, pipelined=False)
-    e2e_h = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True)
-    e2e_h32 = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True, idx_dtype=torch.int32)
+    e2e_h = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True, graphed=True)
+    e2e_h32 = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True, idx_dtype=torch.int32, graphed=True)
+    e2e_h_pipe = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True)
     e2e_h_strict = time_crd_e2e(pkg, torch, dev, c, esteps, args.warmup, host_contrast_idx=True, pipelined=False)
 
     also = {}
@@ -447,9 +470,12 @@ def run_own(args):
                          "sample": f"{cb} of {c['B']} anchors per step, full K and N, fwd+bwd+update, 3 steps ({cdt:.2f} s/step)"},
         "e2e": {"value": scores_per_step(c) / (e2e["ms_per_step"] * 1e-3), "unit": "scores/s",
                 "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms_per_step"],
-                "api": "CRDLoss(f_s, f_t, idx).backward() every step: pinned host features + indices in (next batch staged on a "
-                       "copy stream by StepPipeline), negatives drawn on the GPU inside the scoring pass, every step's loss read "
-                       "back (one step late, after the next step has been launched)",
+                "api": "GraphedStep over CRDLoss(f_s, f_t, idx) + backward(): forward and backward captured once in a CUDA graph; "
+                       "every step: pinned host features + indices in (next batch staged on a copy stream), negatives drawn on "
+                       "the GPU inside the scoring pass (fresh on every replay), the step's loss read back one step late",
+                "without_graph": {"value": scores_per_step(c) / (e2e_pipe["ms_per_step"] * 1e-3), "unit": "scores/s",
+                                  "ms_per_step": e2e_pipe["ms_per_step"],
+                                  "note": "the same loop through the per-step Python path (StepPipeline: two foreign calls per step)"},
                 "sync_each_step": {"value": scores_per_step(c) / (e2e_strict["ms_per_step"] * 1e-3), "unit": "scores/s",
                                    "ms_per_step": e2e_strict["ms_per_step"],
                                    "note": "the reference loop verbatim: copy, forward, backward, loss.item() before the next copy"},
@@ -457,6 +483,8 @@ def run_own(args):
                                            "h2d_bytes_per_step": e2e_h["h2d"], "ms_per_step": e2e_h["ms_per_step"],
                                            "int32_list": {"value": scores_per_step(c) / (e2e_h32["ms_per_step"] * 1e-3),
                                                           "h2d_bytes_per_step": e2e_h32["h2d"], "ms_per_step": e2e_h32["ms_per_step"]},
+                                           "without_graph": {"value": scores_per_step(c) / (e2e_h_pipe["ms_per_step"] * 1e-3),
+                                                             "ms_per_step": e2e_h_pipe["ms_per_step"]},
                                            "sync_each_step": {"value": scores_per_step(c) / (e2e_h_strict["ms_per_step"] * 1e-3),
                                                               "ms_per_step": e2e_h_strict["ms_per_step"]}}},
         "gpu_launches": r["launches"],

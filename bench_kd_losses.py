@@ -146,13 +146,32 @@ def bench_pose_tail(pkg, torch, dev, args, B=138, Fs=1024, Fi=1024):
         return run
 
     t_train, t_train_eager = _time(torch, train_step(ptail), steps, warmup), _time(torch, train_step(eager), steps, warmup)
+    try:   # the same step captured once (GraphedStep): the device-bound figure, without the per-call host path
+        def fwd_bwd(a, b):
+            outs, x, p = ptail(a, b)
+            loss = sum(o.sum() for o in outs) + x.sum() + p.sum()
+            loss.backward()
+            return loss
+        gs = pkg.GraphedStep(fwd_bwd, (sf.cpu().pin_memory(), img.cpu().pin_memory()), dev, grad_inputs=(0, 1),
+                             zero_grad=lambda: ptail.zero_grad(set_to_none=True))
+        host_in = (sf.cpu().pin_memory(), img.cpu().pin_memory())
+
+        def run_graphed():
+            gs.stage(*host_in)
+            gs.run()
+            gs.collect()
+        t_train_graph = _time(torch, run_graphed, steps, warmup)
+    except Exception as exc:
+        t_train_graph = f"capture failed: {exc}"[:200]
     return {"workload": f"pose_tail_B{B}_{Fs}+{Fi}", "eager_us": t_eager, "frozen_tail_us": t_frozen,
             "max_rel_diff_vs_eager": err, "frozen_tail_bf16_us": t_bf16,
             "weight_bytes_fp32": wbytes, "weight_stream_gbs": wbytes / (t_frozen * 1e-6) / 1e9,
-            "train_fwd_bwd_us": t_train, "train_fwd_bwd_eager_us": t_train_eager,
+            "train_fwd_bwd_us": t_train, "train_fwd_bwd_graphed_us": t_train_graph, "train_fwd_bwd_eager_us": t_train_eager,
             "note": "eval-mode teacher tail as ONE launch of the tcgen05 chain kernel (csrc/pose_tail.cu): BN folded, concat as the "
                     "first layer's K range, six heads as one layer, weights streamed once as bf16 (hi, lo) images, three MMAs per "
                     "product (fp32-accurate; bf16 = hi planes only); times are per call through the public module (host included); "
                     "the eager arm's 1x1 convolutions run cuDNN's default TF32 path, which is where max_rel_diff_vs_eager comes "
                     "from -- against the fp64 oracle the tail is within 1e-5.  train_*: PoseTail forward + backward (batch-statistics "
-                    "BatchNorm in the same kernel, backward = pull-backs + library GEMMs) vs the eager modules"}
+                    "BatchNorm in the same kernel; backward = crdpn_pose_tail_backward, fp32 FFMA kernels) per call (host-bound: "
+                    "~1 ms of device work), captured in a CUDA graph (GraphedStep: host inputs staged, loss read back), and the "
+                    "eager modules (TF32 convolutions)"}

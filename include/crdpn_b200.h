@@ -164,6 +164,9 @@ int crdpn_crd_stream_workspace_bytes(int64_t B, int64_t K1, int64_t D, int64_t r
  *   backward: both embed-head backwards in 2 launches (dxs / dxt may be NULL; d_pre_scratch holds 2*B*D floats).
  * This is what the reference's KD loop would call at KD/common/base_class.py:387 (forward) and :394 (backward);
  * the host cost of a step drops from ~30 foreign calls / allocations to two.
+ * variant | 0x4000 (CUDA-graph replays; in-kernel uniform draw only, i.e. contrast_idx = alias_prob = alias_alias = NULL):
+ *   idx_scratch is then a DEVICE uint64 counter that the kernels add to `offset`, and a one-thread kernel advances it by
+ *   B * K1 behind the step, so a captured step draws fresh negatives -- the ones the eager loop would draw -- on every replay.
  * ------------------------------------------------------------------------------------------------- */
 int crdpn_crd_loss_forward(
     const float* f_s, int64_t s_dim, const float* Ws, const float* bs,
@@ -355,6 +358,33 @@ int crdpn_pose_tail_workspace_bytes(const crdpn_pose_tail_layer* layers, int n_l
 int crdpn_pose_tail_forward(const crdpn_pose_tail_layer* layers, int n_layers, const float* shape_feature,
                             const float* img_feature, int64_t B, int64_t shape_dim, int64_t img_dim, int flags,
                             float bn_momentum, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Train-mode backward of the same chain (what autograd does for training.py:75) as ONE call: per layer, last to first, the
+ * activation / batch-statistics BatchNorm pull-back (d_gamma, d_beta, d_bias ride in it), dW = g^T x_in, and dx = g W
+ * accumulated into the gradient of the layer's source; fp32 FFMA kernels, 3-5 launches per layer.
+ *   y     : the layer's forward output [B, O] (crdpn_pose_tail_layer.out of the forward call)
+ *   xhat, istd, gamma : the forward's saved BatchNorm values (NULL gamma: the layer has no BatchNorm)
+ *   g_out : gradient w.r.t. this layer's output coming from OUTSIDE the chain (the losses), or NULL
+ *   W     : the raw fp32 weights [O, I];  dW [O, I], db [O], dgamma / dbeta [O] are written (not accumulated)
+ * d_shape_feature [B, shape_dim] / d_img_feature [B, img_dim] may be NULL.  Workspace: crdpn_pose_tail_backward_workspace_bytes. */
+typedef struct crdpn_pose_tail_bwd_layer {
+  const float* W;
+  const float* y;
+  const float* xhat;
+  const float* gamma;
+  const float* istd;
+  const float* g_out;
+  float* dW;
+  float* db;
+  float* dgamma;
+  float* dbeta;
+  int64_t O, I;
+  int32_t src, act;
+} crdpn_pose_tail_bwd_layer;
+int crdpn_pose_tail_backward_workspace_bytes(const crdpn_pose_tail_bwd_layer* layers, int n_layers, int64_t B, size_t* bytes);
+int crdpn_pose_tail_backward(const crdpn_pose_tail_bwd_layer* layers, int n_layers, const float* shape_feature,
+                             const float* img_feature, int64_t B, int64_t shape_dim, int64_t img_dim,
+                             float* d_shape_feature, float* d_img_feature, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The sharded step's forward as ONE call (one process per GPU, exchanges over NVLink peer memory as above): both embed
  * heads on the LOCAL anchors -> crdpn_p2p_allgather_anchors -> [contrast_idx == NULL: crdpn_alias_draw_contrast_local,

@@ -588,3 +588,55 @@ def test_step_pipeline_reads_every_loss_and_changes_no_bits(pkg, cuda):
     assert got == strict
     assert torch.equal(mods[0].contrast.memory_v1, mods[1].contrast.memory_v1)
     assert torch.equal(mods[0].contrast.memory_v2, mods[1].contrast.memory_v2)
+
+
+def test_graphed_step_equals_the_eager_loop(pkg, cuda):
+    """GraphedStep: forward + backward of CRDLoss(f_s, f_t, idx) captured once and replayed from staged host batches must
+    reproduce the eager loop step by step -- fresh negatives on every replay (device-resident sampler offset), the same
+    losses, gradients and bank rows, bit for bit."""
+    B, D, K, N = 12, 128, 511, 6000
+    opt = type("Opt", (), dict(s_dim=96, t_dim=64, feat_dim=D, n_data=N, nce_k=K, nce_t=0.07, nce_m=0.5))()
+    torch.manual_seed(7)
+    a = pkg.CRDLoss(opt, seed=11).to(cuda)
+    torch.manual_seed(7)
+    b = pkg.CRDLoss(opt, seed=11).to(cuda)
+    b.load_state_dict(a.state_dict())
+    gen = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(B, 96, generator=gen).pin_memory(), torch.randn(B, 64, generator=gen).pin_memory(),
+                torch.randperm(N, generator=gen)[:B].pin_memory()) for _ in range(5)]
+    # first call freezes Z on both, eagerly, from the same batch
+    for m in (a, b):
+        f_s = batches[0][0].to(cuda).requires_grad_(True)
+        m(f_s, batches[0][1].to(cuda), batches[0][2].to(cuda)).backward()
+        m.zero_grad(set_to_none=True)
+    b.contrast.device_sampler_offset()
+
+    def fwd_bwd(f_s, f_t, idx):
+        loss = b(f_s, f_t, idx)
+        loss.backward()
+        return loss
+
+    # the warm-up replays inside GraphedStep advance the sampler and the banks: give the eager module the same history
+    warm = 2                      # (the capture pass itself executes nothing)
+    step = pkg.GraphedStep(fwd_bwd, batches[0], cuda, grad_inputs=(0,), zero_grad=lambda: b.zero_grad(set_to_none=True), warmup=warm)
+    for _ in range(warm):
+        f_s = batches[0][0].to(cuda).requires_grad_(True)
+        a(f_s, batches[0][1].to(cuda), batches[0][2].to(cuda)).backward()
+        a.zero_grad(set_to_none=True)
+    step.stage(*batches[1])
+    for i in range(1, 5):
+        step.run()
+        if i + 1 < 5:
+            step.stage(*batches[i + 1])
+        f_s = batches[i][0].to(cuda).requires_grad_(True)
+        a.zero_grad(set_to_none=True)
+        want = a(f_s, batches[i][1].to(cuda), batches[i][2].to(cuda))
+        want.backward()
+        got = step.collect()
+        assert got == want.item(), (i, got, want.item())
+        assert torch.equal(step.static[0].grad, f_s.grad)
+        assert torch.equal(b.embed_s.linear.weight.grad, a.embed_s.linear.weight.grad)
+        assert torch.equal(b.embed_t.linear.bias.grad, a.embed_t.linear.bias.grad)
+    assert torch.equal(b.contrast.memory_v1, a.contrast.memory_v1) and torch.equal(b.contrast.memory_v2, a.contrast.memory_v2)
+    b.contrast.device_sampler_offset(False)
+    assert b.contrast.multinomial.offset == a.contrast.multinomial.offset
