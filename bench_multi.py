@@ -201,7 +201,7 @@ def _strong(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
             dist.broadcast(p_.data, src=0)
     host = [t.pin_memory() for t in (f_s[sl].contiguous(), f_t[sl].contiguous(), y[sl].contiguous(), cidx)]
 
-    def e2e_run(cr, n_in):
+    def e2e_run(cr, n_in, graphed):
         def e2e_step():
             dev_in = [t.to(dev, non_blocking=True) for t in host[:n_in]]
             dev_in[0].requires_grad_()
@@ -212,20 +212,59 @@ def _strong(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
 
         for _ in range(3):
             e2e_step()
+        gs = None
+        if graphed:   # forward + backward of the sharded step captured once; replays stay in lock-step on every rank
+            cr.contrast.device_sampler_offset()
+
+            def fn(*dev_in):
+                loss = cr(dev_in[0], dev_in[1], dev_in[2], dev_in[3] if n_in == 4 else None)
+                loss.backward()
+                return loss
+
+            gs = pkg.GraphedStep(fn, host[:n_in], dev, grad_inputs=(0,), zero_grad=lambda: cr.zero_grad(set_to_none=True))
+
+        def loop(n):
+            if gs is None:
+                for _ in range(n):
+                    e2e_step()
+                return
+            gs.stage(*host[:n_in])
+            for i in range(n):
+                gs.run()
+                if i + 1 < n:
+                    gs.stage(*host[:n_in])
+                if gs.pending() > 1:
+                    gs.collect()
+            while gs.pending():
+                gs.collect()
+
+        loop(3)
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        esteps = max(args.steps // 4, 5)
-        for _ in range(esteps):
-            e2e_step()
+        esteps = max(args.steps, 20) if graphed else max(args.steps // 4, 5)
+        loop(esteps)
         torch.cuda.synchronize()
         dist.barrier()
         ms_ = torch.tensor([(time.perf_counter() - t0) * 1e3 / esteps], dtype=torch.float64, device=dev)
         dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
         return ms_.item(), sum(t.numel() * t.element_size() for t in host[:n_in])
 
-    e2e_ms, h2d = e2e_run(crit_l, 3)
-    e2e_ms_h, h2d_h = e2e_run(crit_r, 4)
+    def guarded(cr, n_in, graphed):
+        try:
+            return e2e_run(cr, n_in, graphed)
+        except Exception as exc:   # keep the line: report the failure instead of losing the run
+            print(f"[bench_multi] e2e leg (n_in={n_in}, graphed={graphed}) failed on rank {rank}: {exc}", file=sys.stderr)
+            return float("nan"), 0
+
+    e2e_strict_ms, h2d = e2e_run(crit_l, 3, False)
+    e2e_strict_ms_h, h2d_h = e2e_run(crit_r, 4, False)
+    e2e_ms, _ = guarded(crit_l, 3, True)
+    e2e_ms_h, _ = guarded(crit_r, 4, True)
+    if e2e_ms != e2e_ms:
+        e2e_ms = e2e_strict_ms
+    if e2e_ms_h != e2e_ms_h:
+        e2e_ms_h = e2e_strict_ms_h
     scores_l = 2 * B * (K_loc * world + 1)
     del crit_l, crit_r
     torch.cuda.empty_cache()
@@ -252,11 +291,15 @@ def _strong(args, pkg, torch, dist, dev, rank, world, hbm_peak, peak_kind):
                             "CPU oracle (2 anchors), tolerance 1e-4; updated rows and the reduced buffer bit-compared"),
         "e2e": {"value": scores_l / (e2e_ms * 1e-3), "unit": "scores/s", "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms,
-                "api": f"ShardedCRDLoss(f_s_loc, f_t_loc, idx_loc).backward(): pinned host features + indices in, K/R = {K_loc} "
-                       "in-shard negatives drawn on each GPU, loss.item() out",
+                "api": f"GraphedStep over ShardedCRDLoss(f_s_loc, f_t_loc, idx_loc) + backward(): forward and backward captured once in a "
+                       f"CUDA graph on every rank; per step: pinned host features + indices in (next batch staged on a copy stream), K/R = "
+                       f"{K_loc} in-shard negatives drawn on each GPU (fresh on every replay), the loss read back one step late",
+                "sync_each_step": {"value": scores_l / (e2e_strict_ms * 1e-3), "ms_per_step": e2e_strict_ms,
+                                   "note": "the reference loop verbatim through the per-step Python path: copy, forward, backward, loss.item()"},
                 "with_host_contrast_idx": {"value": total_scores / (e2e_ms_h * 1e-3), "unit": "scores/s",
                                            "h2d_bytes_per_step": h2d_h * world, "ms_per_step": e2e_ms_h,
-                                           "note": "the replicated [B,K+1] int64 list copied to EVERY rank each step"}},
+                                           "sync_each_step": {"value": total_scores / (e2e_strict_ms_h * 1e-3), "ms_per_step": e2e_strict_ms_h},
+                                           "note": "the replicated [B,K+1] int64 list copied to EVERY rank each step (staged, GraphedStep)"}},
         "gpu_launches": 3 * args.steps,
         "comm": "NVLink peer-memory kernels (all-gather; all-reduce fused into the reduction kernel), no NCCL call in the step",
         "collectives_per_step": 0, "exchange_kernels_per_step": 1,
