@@ -28,10 +28,10 @@ from .pointnet import ShapeEncoderPC  # noqa: F401,E402
 from .pointcloud import PointCloudSampler  # noqa: F401,E402
 from .pose_tail import FrozenPoseTail, PoseTail  # noqa: F401,E402
 from . import kd_losses  # noqa: F401,E402
-from .kd_losses import (CELoss, DeltaLoss, TemperatureScaledKLDivLoss, calculate_kd_loss_new, infoNCE_KD,  # noqa: F401,E402
-                        poseNCE_KD, student_kd_step_loss)
+from .kd_losses import (CELoss, DeltaLoss, TemperatureScaledKLDivLoss, calculate_kd_loss_new, infoNCE, infoNCE_KD,  # noqa: F401,E402
+                        multiposeNCE_KD, poseNCE, poseNCE_KD, singleinfoNCE_KD, student_kd_step_loss)
 
 from .pipeline import GraphedStep, StepPipeline  # noqa: F401,E402
 
 __all__ += ["StepPipeline", "GraphedStep", "ShapeEncoderPC", "PointCloudSampler", "FrozenPoseTail", "PoseTail", "CELoss", "DeltaLoss", "TemperatureScaledKLDivLoss", "calculate_kd_loss_new", "infoNCE_KD",
-            "poseNCE_KD", "student_kd_step_loss"]
+            "poseNCE_KD", "student_kd_step_loss", "infoNCE", "poseNCE", "singleinfoNCE_KD", "multiposeNCE_KD"]

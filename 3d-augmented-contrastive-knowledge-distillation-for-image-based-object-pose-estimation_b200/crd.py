@@ -446,6 +446,21 @@ class ContrastMemory(nn.Module):
     def _sampler_for_offset(self):
         return self.multinomial
 
+    def sampler_state(self) -> dict:
+        """(seed, offset) of the negative sampler's Philox stream.  Not part of ``state_dict`` (its keys stay those of the
+        published module); save it next to a checkpoint and hand it to ``load_sampler_state`` to resume the SAME stream of
+        negatives instead of replaying it from offset 0."""
+        smp = self._sampler_for_offset()
+        extra = int(self._dev_offset.item()) if isinstance(self._dev_offset, torch.Tensor) else 0
+        return {"seed": int(smp.seed), "offset": int(smp.offset) + extra}
+
+    def load_sampler_state(self, state: dict):
+        smp = self._sampler_for_offset()
+        smp.seed, smp.offset = int(state["seed"]), int(state["offset"])
+        if isinstance(self._dev_offset, torch.Tensor):
+            self._dev_offset.zero_()
+        return self
+
     def _device_offset(self, device):
         if self._dev_offset is None:
             return None

@@ -1,7 +1,10 @@
 // kd_losses.cu -- the reference's in-batch contrastive KD losses and its KD loss mixer, each as one or two launches
 // with closed-form gradients (the eager formulation costs ~50 forward + ~80 backward launches on [138, 24] tensors).
 //
-//   nce_kd   : infoNCE_KD / poseNCE_KD, auxiliary/model_utils.py:225-285 (+ rotation_err, auxiliary/utils.py:156-202)
+//   nce_kd   : infoNCE_KD / poseNCE_KD, auxiliary/model_utils.py:225-285 (+ rotation_err, auxiliary/utils.py:156-202), and the
+//              other in-batch variants of the same file: infoNCE / poseNCE (:169-223, negatives = the anchors' own rows),
+//              singleinfoNCE_KD (:288-304, positive term only), multiposeNCE_KD (:307-351, every sample within 30 degrees
+//              of the anchor's pose counts as a positive) -- mode bits on top of the weighting code, same three kernels
 //              dropout(p) on the teacher side -> L2 normalise both -> B x B logits / tau -> pose weights -> -log(pos / sum)
 //   kd_mix   : CELoss x3 + DeltaLoss (auxiliary/loss.py:7-34), TemperatureScaledKLDivLoss x7 and the weighted sum of
 //              calculate_kd_loss_new (KD/vision/vanilla/vanilla_kd.py:8-32, 143-164); call site
@@ -17,6 +20,11 @@ namespace kdl {
 constexpr int kNceThreads = 256;
 constexpr int kMixThreads = 128;
 constexpr float kPi = 3.14159265358979323846f;
+// mode bits carried in the `weighting` argument above the weighting code (bits 0-2)
+constexpr int kNceSelf = 0x100;     // negatives are the anchors' own normalised rows, k = n excluded (infoNCE, poseNCE)
+constexpr int kNceSingle = 0x200;   // loss_n = -s_nn: the positive logit alone (singleinfoNCE_KD)
+constexpr int kNceMulti = 0x400;    // positives = {k : k = n or rotation_err(n, k) <= 30 degrees} (multiposeNCE_KD)
+constexpr float kMultiThresholdDeg = 30.f;
 
 // fixed-order block sum / max (every thread returns the result)
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -80,7 +88,7 @@ __host__ inline NceWs nce_ws_views(void* ws, long long B, long long C) {
 // grid B: dropout + L2 normalise row n of both sides; rotation matrix of label n (utils.py:156-178, fp32 as there)
 __global__ void __launch_bounds__(kNceThreads) nce_prep_kernel(const float* __restrict__ ori, const float* __restrict__ pos,
                                                               const float* __restrict__ label, int C, float p_drop,
-                                                              unsigned long long seed, unsigned long long offset, NceWs ws) {
+                                                              unsigned long long seed, unsigned long long offset, NceWs ws, int mode) {
   __shared__ float red[kNceThreads / 32];
   const int n = blockIdx.x;
   const size_t o = (size_t)n * C;
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(kNceThreads) nce_prep_kernel(const float* __re
   if (threadIdx.x == 0) {
     ws.inv_na[n] = ia;
     ws.inv_np[n] = ip;
-    if (n == 0) *ws.ticket = 0u;
+    if (n == 0) { ws.ticket[0] = 0u; ws.ticket[1] = (unsigned)mode; }   // the backward reads the mode from here
     if (label != nullptr) {
       const float azi = label[3 * n] * kPi / 180.f, ele = (label[3 * n + 1] - 180.f) * kPi / 180.f,
                   rol = (label[3 * n + 2] - 180.f) * kPi / 180.f;
@@ -132,45 +140,87 @@ __device__ __forceinline__ float pose_weight(const float* Rn, const float* Rk, i
   }
 }
 
-// grid B, dynamic smem (C + B) floats: row n of the logits, its soft weights, its loss term; last block reduces the loss
+__device__ __forceinline__ float pose_dist_deg(const float* Rn, const float* Rk) {
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) t = fmaf(Rn[i], Rk[i], t);
+  t = fminf(fmaxf(t, -1.f), 3.f);
+  return acosf((t - 1.f) * 0.5f) * (180.f / kPi);
+}
+
+// grid B, dynamic smem (C + B) floats: row n of the logits, its soft weights (= d loss_n / d s_nk), its loss term; the
+// last block reduces the loss.  `weighting` = weighting code | mode bits (kNceSelf / kNceSingle / kNceMulti).
 __global__ void __launch_bounds__(kNceThreads) nce_rows_kernel(int B, int C, float inv_tau, int weighting, NceWs ws,
                                                               float* __restrict__ loss_out) {
   extern __shared__ float smem[];
   __shared__ float red[kNceThreads / 32];
+  __shared__ float s_pos_sh;
   __shared__ bool last;
   float* s_a = smem;       // [C]
   float* s_e = smem + C;   // [B]
+  const int mode = weighting & ~0xff, wcode = weighting & 0xff;
+  const bool self = (mode & kNceSelf) != 0, single = (mode & kNceSingle) != 0, multi = (mode & kNceMulti) != 0;
+  const float* neg = self ? ws.a_hat : ws.p_hat;
   const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int c = threadIdx.x; c < C; c += blockDim.x) s_a[c] = ws.a_hat[(size_t)n * C + c];
   __syncthreads();
-  for (int k = warp; k < B; k += nw) {
-    const float* pk = ws.p_hat + (size_t)k * C;
+  for (int k = warp; k < B + 1; k += nw) {   // k = B: the positive logit a_n . p_n (its own slot: the self modes need it)
+    const float* pk = k < B ? neg + (size_t)k * C : ws.p_hat + (size_t)n * C;
     float d = 0.f;
     for (int c = lane; c < C; c += 32) d = fmaf(s_a[c], pk[c], d);
     for (int off = 16; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-    if (lane == 0) s_e[k] = d * inv_tau;
+    if (lane == 0) {
+      if (k < B) s_e[k] = d * inv_tau; else s_pos_sh = d * inv_tau;
+    }
   }
   __syncthreads();
-  float m = -INFINITY;
-  for (int k = threadIdx.x; k < B; k += blockDim.x) m = fmaxf(m, s_e[k]);
-  m = block_max(m, red);
-  const float s_nn = s_e[n];
-  __syncthreads();
-  float part = 0.f;
-  for (int k = threadIdx.x; k < B; k += blockDim.x) {
-    float w = 1.0f;
-    if (weighting != 0) w = (k == n) ? 0.f : pose_weight(ws.R + 9 * n, ws.R + 9 * k, weighting);
-    const float e = expf(s_e[k] - m) * w;
-    s_e[k] = e;
-    part += e;
+  const float s_nn = s_pos_sh;
+  float part = 0.f, lpos, S, loss_n;
+  if (single) {
+    for (int k = threadIdx.x; k < B; k += blockDim.x) ws.w[(size_t)n * B + k] = 0.f;
+    lpos = 0.f; S = 1.f; loss_n = -s_nn;          // d loss / d s_nn = pfrac - 1 = -1
+  } else {
+    float m = s_nn;
+    for (int k = threadIdx.x; k < B; k += blockDim.x) m = fmaxf(m, s_e[k]);
+    m = block_max(m, red);
+    __syncthreads();
+    if (multi) {
+      float partp = 0.f;
+      for (int k = threadIdx.x; k < B; k += blockDim.x) {
+        const bool mark = (k == n) || pose_dist_deg(ws.R + 9 * n, ws.R + 9 * k) <= kMultiThresholdDeg;
+        const float e = expf(s_e[k] - m);
+        s_e[k] = mark ? -e : e;     // sign bit carries the mark to the weight pass
+        part += mark ? 2.f * e : e;
+        partp += mark ? e : 0.f;
+      }
+      S = block_sum(part, red);
+      const float Lp = block_sum(partp, red);
+      const float invS = 1.0f / S, invLp = 1.0f / Lp;
+      for (int k = threadIdx.x; k < B; k += blockDim.x) {
+        const float e = fabsf(s_e[k]);
+        ws.w[(size_t)n * B + k] = s_e[k] < 0.f ? e * (2.f * invS - invLp) : e * invS;
+      }
+      lpos = S;                    // pfrac = 1: no separate positive slot
+      loss_n = logf(S) - logf(Lp);
+    } else {
+      for (int k = threadIdx.x; k < B; k += blockDim.x) {
+        float w = 1.0f;
+        if (wcode != 0) w = (k == n) ? 0.f : pose_weight(ws.R + 9 * n, ws.R + 9 * k, wcode);
+        else if (self) w = (k == n) ? 0.f : 1.f;
+        const float e = expf(s_e[k] - m) * w;
+        s_e[k] = e;
+        part += e;
+      }
+      lpos = expf(s_nn - m);
+      S = block_sum(part, red) + lpos;
+      const float invS = 1.0f / S;
+      for (int k = threadIdx.x; k < B; k += blockDim.x) ws.w[(size_t)n * B + k] = s_e[k] * invS;
+      loss_n = logf(S) - (s_nn - m);
+    }
   }
-  const float lpos = expf(s_nn - m);
-  const float S = block_sum(part, red) + lpos;
-  const float invS = 1.0f / S;
-  for (int k = threadIdx.x; k < B; k += blockDim.x) ws.w[(size_t)n * B + k] = s_e[k] * invS;
   if (threadIdx.x == 0) {
-    ws.pfrac[n] = lpos * invS;
-    ws.loss_n[n] = logf(S) - (s_nn - m);
+    ws.pfrac[n] = lpos / S;
+    ws.loss_n[n] = loss_n;
     __threadfence();
     last = atomicAdd(ws.ticket, 1u) == (unsigned)(B - 1);
   }
@@ -206,8 +256,27 @@ __global__ void __launch_bounds__(kNceThreads) nce_grads_kernel(int B, int C, fl
   __syncthreads();
   const float pf = ws.pfrac[n] - 1.0f;
   const size_t o = (size_t)n * C;
+  const bool self = (ws.ticket[1] & (unsigned)kNceSelf) != 0u;   // negatives were the anchors' own rows
   float da = 0.f, dp = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  if (self) {
+    // s_nk = a_n . a_k: row n of the anchors collects both roles, (w[n,k] + w[k,n]) a_k; the positive pairs a_n with p_n
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float ga0 = 0.f, ga1 = 0.f;
+      int k = 0;
+      for (; k + 1 < B; k += 2) {
+        ga0 = fmaf(w_row[k] + w_col[k], ws.a_hat[(size_t)k * C + c], ga0);
+        ga1 = fmaf(w_row[k + 1] + w_col[k + 1], ws.a_hat[(size_t)(k + 1) * C + c], ga1);
+      }
+      if (k < B) ga0 = fmaf(w_row[k] + w_col[k], ws.a_hat[(size_t)k * C + c], ga0);
+      const float an = ws.a_hat[o + c], pn = ws.p_hat[o + c];
+      const float ga = (ga0 + ga1) + pf * pn, gp = pf * an;
+      g_a[c] = ga;
+      g_p[c] = gp;
+      da = fmaf(ga, an, da);
+      dp = fmaf(gp, pn, dp);
+    }
+  }
+  for (int c = threadIdx.x; c < C && !self; c += blockDim.x) {
     float ga0 = 0.f, ga1 = 0.f, gp0 = 0.f, gp1 = 0.f;
     int k = 0;
     for (; k + 1 < B; k += 2) {
@@ -406,13 +475,15 @@ extern "C" int crdpn_nce_kd_forward(const float* feat_ori, const float* feat_pos
                                     float tau, int weighting, float dropout_p, uint64_t seed, uint64_t offset, float* loss,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   if (!feat_ori || !feat_pos || !loss) return fail(CRDPN_E_BADARG, "crdpn_nce_kd_forward: null pointer");
-  if (weighting != 0 && !label) return fail(CRDPN_E_BADARG, "crdpn_nce_kd_forward: pose weighting needs labels");
-  int rc = nce_check(B, C, tau, weighting, dropout_p, workspace, workspace_bytes);
+  if (((weighting & 0xff) != 0 || (weighting & kdl::kNceMulti)) && !label)
+    return fail(CRDPN_E_BADARG, "crdpn_nce_kd_forward: pose weighting / multi-positive mode needs labels");
+  const int mode = weighting & ~0xff;
+  if (mode & ~(kdl::kNceSelf | kdl::kNceSingle | kdl::kNceMulti)) return fail(CRDPN_E_BADARG, "crdpn_nce_kd_forward: unknown mode bits");
+  int rc = nce_check(B, C, tau, weighting & 0xff, dropout_p, workspace, workspace_bytes);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   kdl::NceWs ws = kdl::nce_ws_views(workspace, B, C);
-  kdl::nce_prep_kernel<<<(unsigned)B, kdl::kNceThreads, 0, st>>>(feat_ori, feat_pos, weighting != 0 ? label : nullptr, (int)C,
-                                                                 dropout_p, seed, offset, ws);
+  kdl::nce_prep_kernel<<<(unsigned)B, kdl::kNceThreads, 0, st>>>(feat_ori, feat_pos, label, (int)C, dropout_p, seed, offset, ws, mode);
   CRDPN_LAUNCH_CHECK("nce_prep_kernel");
   const size_t smem = (size_t)(B + C) * sizeof(float);
   if (smem > 48 * 1024) CRDPN_CUDA(cudaFuncSetAttribute(kdl::nce_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

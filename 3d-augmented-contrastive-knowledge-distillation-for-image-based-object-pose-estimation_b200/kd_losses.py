@@ -4,6 +4,10 @@ Same names, argument order and semantics as the reference (SURVEY.md section 8f,
 
     infoNCE_KD(feat_ori, feat_pos, label, tau=0.1, weighting="linear")      auxiliary/model_utils.py:263-285
     poseNCE_KD(feat_ori, feat_pos, label, tau=0.1, weighting="linear")      auxiliary/model_utils.py:225-261
+    infoNCE(feat_ori, feat_pos, tau=0.1), poseNCE(feat_ori, feat_pos, label, tau, weighting)
+                                                                            auxiliary/model_utils.py:169-223
+    singleinfoNCE_KD(feat_ori, feat_pos, label, tau, weighting), multiposeNCE_KD(feat_ori, feat_pos, label, tau)
+                                                                            auxiliary/model_utils.py:288-351
     CELoss(range)(pred, target), DeltaLoss(bin)(azi, ele, rol, target)      auxiliary/loss.py:7-34
     TemperatureScaledKLDivLoss(temperature)(y_pred, y)                      KD/vision/vanilla/vanilla_kd.py:8-32
     calculate_kd_loss_new(y_pred_student, y_pred_teacher, student_features, teacher_features, gt_loss)
@@ -30,6 +34,7 @@ from torch import nn
 from . import _native
 
 WEIGHTINGS = {"none": 0, "linear": 1, "square": 2, "sqrt": 3, "sin": 4, "sinsin": 5}
+MODE_SELF, MODE_SINGLE, MODE_MULTI = 0x100, 0x200, 0x400   # crdpn_nce_kd_forward mode bits (include/crdpn_b200.h)
 INFONCE_DROPOUT_P = 0.3
 
 _stream_state = {"seed": None, "offset": 0}
@@ -73,7 +78,7 @@ class _NceKdFunction(torch.autograd.Function):
         B, C = a.shape
         dev = a.device
         lab = None
-        if weighting != 0:
+        if (weighting & 0xff) != 0 or (weighting & MODE_MULTI):
             lab = label.detach().to(device=dev, dtype=torch.float32).contiguous()
             if lab.shape != (B, 3):
                 raise RuntimeError("label must be [B, 3] (azimuth, elevation, in-plane rotation in degrees)")
@@ -121,6 +126,31 @@ def infoNCE_KD(feat_ori, feat_pos, label=None, tau=0.1, weighting="linear"):
     ``label`` and ``weighting`` are accepted and ignored exactly as there)."""
     seed, offset = _next_dropout_blocks(feat_pos.numel())
     return _NceKdFunction.apply(feat_ori, feat_pos, None, tau, 0, INFONCE_DROPOUT_P, seed, offset)
+
+
+def infoNCE(feat_ori, feat_pos, tau=0.1):
+    """In-batch InfoNCE whose negatives are the OTHER anchors (reference: auxiliary/model_utils.py:169-186): cross-entropy of
+    row n over logits [a_n.a_k / tau for k != n, a_n.q_n / tau at k = n]."""
+    return _NceKdFunction.apply(feat_ori, feat_pos, None, tau, MODE_SELF, 0.0, 0, 0)
+
+
+def poseNCE(feat_ori, feat_pos, label, tau=0.1, weighting="linear"):
+    """Pose-weighted NCE whose negatives are the anchors themselves (reference: auxiliary/model_utils.py:189-223)."""
+    if weighting not in WEIGHTINGS or weighting == "none":
+        raise ValueError(f"weighting must be one of {[w for w in WEIGHTINGS if w != 'none']}")
+    return _NceKdFunction.apply(feat_ori, feat_pos, label, tau, WEIGHTINGS[weighting] | MODE_SELF, 0.0, 0, 0)
+
+
+def singleinfoNCE_KD(feat_ori, feat_pos, label=None, tau=0.1, weighting="linear"):
+    """mean_n -(a_n.q_n) / tau on the normalised embeddings (reference: model_utils.py:288-304; ``label`` / ``weighting`` are
+    accepted and ignored as there)."""
+    return _NceKdFunction.apply(feat_ori, feat_pos, None, tau, MODE_SINGLE, 0.0, 0, 0)
+
+
+def multiposeNCE_KD(feat_ori, feat_pos, label, tau=0.1):
+    """NCE with several positives per anchor: every teacher row whose pose lies within 30 degrees of the anchor's (and the
+    anchor's own) counts as a positive (reference: model_utils.py:307-351)."""
+    return _NceKdFunction.apply(feat_ori, feat_pos, label, tau, MODE_MULTI, 0.0, 0, 0)
 
 
 # ----------------------------------------------------------------------------------------------------------

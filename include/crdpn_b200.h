@@ -257,6 +257,12 @@ int crdpn_p2p_allreduce_f32(const float* partial, int64_t n_main, const double* 
  *              (label [B,3] float32 degrees: azimuth, elevation, in-plane; w_nn = 0 exactly)
  * The dropout keep-mask is a counter-based stream: element e = n*C + c takes word e%4 of Philox4x32-10 block
  * (seed, offset + e/4); keep iff (word >> 8) * 2^-24 >= p; kept values are scaled by 1/(1-p).
+ * Mode bits OR-ed into `weighting` select the file's other in-batch variants on the same kernels:
+ *   0x100  negatives are the anchors' OWN rows, k = n excluded: sum_k becomes sum_{k != n} w_nk e^{a_n.a_k/tau}
+ *          (infoNCE, model_utils.py:169-186, with weighting 0; poseNCE, :189-223, with a pose weighting)
+ *   0x200  loss = mean_n -(a_n.q_n)/tau, the positive logit alone (singleinfoNCE_KD, :288-304)
+ *   0x400  every k with k = n or rotation_err(label_n, label_k) <= 30 degrees is a positive:
+ *          loss = mean_n -log( P_n / (P_n + sum_k e^{a_n.q_k/tau}) ), P_n = sum_{k positive} e^{a_n.q_k/tau} (multiposeNCE_KD, :307-351)
  * forward: 2 launches, writes the scalar loss; backward: 1 launch, gradients w.r.t. BOTH inputs (d_pos may be NULL),
  * scaled by the device scalar grad_loss (NULL = 1).  The workspace carries the normalised rows and soft weights from
  * forward to backward and must stay untouched in between.  Deterministic (fixed-order reductions).

@@ -62,6 +62,27 @@ def main(out_path: Path = ROOT / "tests" / "golden" / "kd_losses_golden.npz") ->
         blob[f"posence_kd/{wt}/loss"] = l.detach().numpy()
         blob[f"posence_kd/{wt}/d_ori"] = a.grad.numpy()
         blob[f"posence_kd/{wt}/d_pos"] = p.grad.numpy()
+    # the other in-batch variants (model_utils.py:169-223, 288-351); .cuda() inside them is made a no-op
+    with ko.cuda_is_identity():
+        a, p = leaf(sf), leaf(tf)
+        l = ref.model_utils.infoNCE(a, p, 0.1)
+        l.backward()
+        blob["infonce/loss"], blob["infonce/d_ori"], blob["infonce/d_pos"] = l.detach().numpy(), a.grad.numpy(), p.grad.numpy()
+        for wt in ("linear", "square", "sinsin"):
+            a, p = leaf(sf), leaf(tf)
+            l = ref.model_utils.poseNCE(a, p, label, 0.1, wt)
+            l.backward()
+            blob[f"posence/{wt}/loss"], blob[f"posence/{wt}/d_ori"], blob[f"posence/{wt}/d_pos"] = l.detach().numpy(), a.grad.numpy(), p.grad.numpy()
+        a, p = leaf(sf), leaf(tf)
+        l = ref.model_utils.singleinfoNCE_KD(a, p, label, 0.1)
+        l.backward()
+        blob["single/loss"], blob["single/d_ori"], blob["single/d_pos"] = l.detach().numpy(), a.grad.numpy(), p.grad.numpy()
+        lab_c = ko.clustered_labels(label)
+        a, p = leaf(sf), leaf(tf)
+        l = ref.model_utils.multiposeNCE_KD(a, p, lab_c, 0.1)
+        l.backward()
+        blob["multipose/label"] = lab_c.numpy()
+        blob["multipose/loss"], blob["multipose/d_ori"], blob["multipose/d_pos"] = l.detach().numpy(), a.grad.numpy(), p.grad.numpy()
     blob["rotation_err_pairs"] = ref.utils.rotation_err(label.reshape(-1, 1, 3).repeat(1, n, 1).reshape(-1, 3),
                                                         label.reshape(1, -1, 3).repeat(n, 1, 1).reshape(-1, 3)).numpy()
     # KL (temperatures 1 and 2), CE, Delta

@@ -7,6 +7,8 @@ Restates, in plain torch ops (fp64 by default, differentiable so that autograd y
 * ``rotation_err``        auxiliary/utils.py:156-202 (``angles_to_matrix`` + geodesic angle, degrees)
 * ``nce_kd``              auxiliary/model_utils.py:225-261 (``poseNCE_KD``) and :263-285 (``infoNCE_KD``: dropout(p=0.3,
                           training=True) on the teacher side, then the same NCE with all weights 1)
+* ``nce_self`` / ``single_nce_kd`` / ``multipose_nce_kd``   auxiliary/model_utils.py:169-223, 288-351 (``infoNCE``, ``poseNCE``,
+                          ``singleinfoNCE_KD``, ``multiposeNCE_KD``)
 * ``kl_div_t``            KD/vision/vanilla/vanilla_kd.py:8-32 (``TemperatureScaledKLDivLoss``)
 * ``ce_loss``/``delta_loss``  auxiliary/loss.py:7-34 (``CELoss``, ``DeltaLoss``: bin classification + SmoothL1 on tanh deltas)
 * ``kd_loss_new``         KD/vision/vanilla/vanilla_kd.py:143-164 (``calculate_kd_loss_new``)
@@ -155,6 +157,77 @@ def student_kd_step_loss(out, teacher_out, student_features, teacher_features, l
 
 
 # ---------------------------------------------------------------------------------------------------------
+# ---- the other in-batch variants of auxiliary/model_utils.py (negatives from the anchors themselves; positive only;
+# ---- several positives per anchor) -----------------------------------------------------------------------------------
+def nce_self(feat_ori, feat_pos, label=None, tau=0.1, weighting="none", dtype=torch.float64, weights=None):
+    """infoNCE (model_utils.py:169-186: cross-entropy of row n over [a_n.a_k/tau for k != n, a_n.p_n/tau at k = n]) and
+    poseNCE (:189-223: the same with pose weights on the a_n.a_k terms; the k = n weight is f(0) = 0):
+    loss = mean_n -log( e^{a_n.p_n/tau} / (e^{a_n.p_n/tau} + sum_{k != n} w_nk e^{a_n.a_k/tau}) ).
+    `weights` overrides the [b,b] weight matrix (the tests substitute the reference's own fp32 distances)."""
+    a, p = normalize(feat_ori.to(dtype)), normalize(feat_pos.to(dtype))
+    b = a.shape[0]
+    if weights is not None:
+        w = weights.to(dtype)
+    elif weighting == "none":
+        w = 1.0 - torch.eye(b, dtype=dtype)
+    else:
+        w = pose_weights(label, weighting, dtype) * (1.0 - torch.eye(b, dtype=dtype))
+    l_pos = torch.exp((a * p).sum(1) / tau)
+    l_neg = (torch.exp(a @ a.t() / tau) * w).sum(1)
+    return (-torch.log(l_pos / (l_pos + l_neg))).mean()
+
+
+def single_nce_kd(feat_ori, feat_pos, tau=0.1, dtype=torch.float64):
+    """singleinfoNCE_KD (model_utils.py:288-304): -log(exp(a_n.p_n/tau)) = -(a_n.p_n)/tau, averaged."""
+    a, p = normalize(feat_ori.to(dtype)), normalize(feat_pos.to(dtype))
+    return (-(a * p).sum(1) / tau).mean()
+
+
+def pairwise_rotation_err(label, dtype=torch.float64):
+    b = label.shape[0]
+    lo = label.reshape(-1, 1, 3).repeat(1, b, 1).reshape(-1, 3)
+    la = label.reshape(1, -1, 3).repeat(b, 1, 1).reshape(-1, 3)
+    return rotation_err(lo, la, dtype).reshape(b, b)
+
+
+def multipose_nce_kd(feat_ori, feat_pos, label, tau=0.1, threshold=30.0, dtype=torch.float64):
+    """multiposeNCE_KD (model_utils.py:307-351): positives of anchor n = {k : k = n or rotation_err(n, k) <= 30 degrees};
+    loss = mean_n -log( P_n / (P_n + sum_k e^{a_n.p_k/tau}) ), P_n = sum over the positives of e^{a_n.p_k/tau}."""
+    a, p = normalize(feat_ori.to(dtype)), normalize(feat_pos.to(dtype))
+    b = a.shape[0]
+    mark = ((pairwise_rotation_err(label, dtype) <= threshold) | torch.eye(b, dtype=torch.bool)).to(dtype)
+    E = torch.exp(a @ p.t() / tau)
+    l_pos = (E * mark).sum(1)
+    return (-torch.log(l_pos / (l_pos + E.sum(1)))).mean()
+
+
+def clustered_labels(label, seed=3):
+    """`label` with rows 1-3 moved to within a few degrees of row 0 and row 5 next to row 4, so that multiposeNCE_KD's
+    30-degree rule finds several positives per anchor (random labels almost never fall that close)."""
+    g = torch.Generator().manual_seed(seed)
+    out = label.clone().float()
+    for dst, src in ((1, 0), (2, 0), (3, 0), (5, 4)):
+        out[dst] = out[src] + (torch.rand(3, generator=g) - 0.5) * 16.0
+    out[:, 0] = out[:, 0] % 360.0
+    out[:, 1] = out[:, 1].clamp(1.0, 179.0)
+    out[:, 2] = out[:, 2] % 360.0
+    return out
+
+
+class cuda_is_identity:
+    """Context manager: ``Tensor.cuda()`` returns the tensor itself, so that the reference functions that move their
+    constants to the GPU (infoNCE's labels, multiposeNCE_KD's mark matrix) run unmodified on CPU tensors."""
+
+    def __enter__(self):
+        self.orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self_, *a, **k: self_
+        return self
+
+    def __exit__(self, *a):
+        torch.Tensor.cuda = self.orig
+        return False
+
+
 def load_reference(root: str = "/root/reference"):
     """Import the reference's own loss code (build container only).  Returns a namespace or None."""
     import sys

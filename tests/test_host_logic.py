@@ -57,3 +57,15 @@ def test_state_dict_surface_and_bank_layout(pkg):
     # a checkpoint written by one layout loads into the other
     dense.load_state_dict(sd)
     assert torch.equal(dense.memory_v1, m1) and torch.equal(dense.memory_v2, m2)
+
+
+def test_sampler_state_round_trip(pkg):
+    """The negative sampler's (seed, offset) is exposed for checkpointing without touching the state_dict keys."""
+    mem = pkg.ContrastMemory(128, 1000, 15, seed=77)
+    mem.multinomial.offset = 12345
+    st = mem.sampler_state()
+    assert st == {"seed": 77, "offset": 12345}
+    other = pkg.ContrastMemory(128, 1000, 15, seed=1)
+    other.load_sampler_state(st)
+    assert other.sampler_state() == st
+    assert not any("extra_state" in k for k in mem.state_dict())

@@ -201,3 +201,70 @@ def test_step_loss_shapes_against_oracle(pkg, cuda, n, C):
     loss3.backward()
     assert loss3.item() == loss.item()
     close(o3[0].grad, o64[0].grad / 0.37)
+
+
+# ---- the other in-batch variants (auxiliary/model_utils.py:169-223, 288-351) -----------------------------------------
+def test_infonce_single_multipose_golden(pkg, cuda, gold):
+    """infoNCE / singleinfoNCE_KD / multiposeNCE_KD against the REFERENCE's fp32 values and input gradients."""
+    g, _, _, sf, tf, label = gold
+    a, p = dleaf(sf, cuda), dleaf(tf, cuda)
+    loss = pkg.infoNCE(a, p, 0.1)
+    (2.0 * loss).backward()
+    close(loss, g["infonce/loss"])
+    close(a.grad / 2.0, g["infonce/d_ori"])
+    close(p.grad / 2.0, g["infonce/d_pos"])
+    a, p = dleaf(sf, cuda), dleaf(tf, cuda)
+    loss = pkg.singleinfoNCE_KD(a, p, label.to(cuda), 0.1)
+    loss.backward()
+    close(loss, g["single/loss"])
+    close(a.grad, g["single/d_ori"])
+    close(p.grad, g["single/d_pos"])
+    a, p = dleaf(sf, cuda), dleaf(tf, cuda)
+    loss = pkg.multiposeNCE_KD(a, p, torch.from_numpy(g["multipose/label"]).to(cuda), 0.1)
+    loss.backward()
+    close(loss, g["multipose/loss"])
+    close(a.grad, g["multipose/d_ori"])
+    close(p.grad, g["multipose/d_pos"])
+
+
+@pytest.mark.parametrize("weighting", ["linear", "square", "sqrt", "sin", "sinsin"])
+def test_posence_oracle_and_golden(pkg, cuda, gold, weighting):
+    """poseNCE against the oracle (1e-4; `sqrt` has an unbounded derivative at distance 0: 2e-3) and, for the weightings
+    that square the reference's diagonal noise away, against its golden values."""
+    g, _, _, sf, tf, label = gold
+    a, p = dleaf(sf, cuda), dleaf(tf, cuda)
+    loss = pkg.poseNCE(a, p, label.to(cuda), 0.1, weighting)
+    loss.backward()
+    a64, p64 = leaf64(sf), leaf64(tf)
+    want = ko.nce_self(a64, p64, label, 0.1, weighting)
+    want.backward()
+    tol = 2e-3 if weighting == "sqrt" else 1e-4
+    close(loss, want, tol)
+    close(a.grad, a64.grad, tol)
+    close(p.grad, p64.grad, tol)
+    if weighting == "square":
+        close(loss, g["posence/square/loss"], 1e-4)
+        close(a.grad, g["posence/square/d_ori"], 3e-4)
+
+
+@pytest.mark.parametrize("B,C,tau", [(46, 200, 0.1), (138, 200, 0.5), (7, 33, 0.07), (1, 16, 0.1)])
+def test_variant_shapes_against_oracle(pkg, cuda, B, C, tau):
+    gen = torch.Generator().manual_seed(B * 1000 + C)
+    sf, tf = torch.randn(B, C, generator=gen), torch.randn(B, C, generator=gen)
+    label = torch.stack([torch.rand(B, generator=gen) * 360, torch.rand(B, generator=gen) * 178 + 1, torch.rand(B, generator=gen) * 360], 1)
+    if B > 6:
+        label = ko.clustered_labels(label, seed=B)
+    cases = [(lambda a, p: pkg.infoNCE(a, p, tau), lambda a, p: ko.nce_self(a, p, None, tau)),
+             (lambda a, p: pkg.poseNCE(a, p, label.to(cuda), tau, "sinsin"), lambda a, p: ko.nce_self(a, p, label, tau, "sinsin")),
+             (lambda a, p: pkg.singleinfoNCE_KD(a, p, None, tau), lambda a, p: ko.single_nce_kd(a, p, tau)),
+             (lambda a, p: pkg.multiposeNCE_KD(a, p, label.to(cuda), tau), lambda a, p: ko.multipose_nce_kd(a, p, label, tau))]
+    for got_fn, want_fn in cases:
+        a, p = dleaf(sf, cuda), dleaf(tf, cuda)
+        got = got_fn(a, p)
+        got.backward()
+        a64, p64 = leaf64(sf), leaf64(tf)
+        want = want_fn(a64, p64)
+        want.backward()
+        close(got, want)
+        close(a.grad, a64.grad, 2e-4)
+        close(p.grad, p64.grad, 2e-4)

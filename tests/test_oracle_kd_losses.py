@@ -157,3 +157,64 @@ def test_against_live_reference_functions():
     close(ko.delta_loss(out[3], out[4], out[5], label, 15).item(), r.item(), 2e-5)
     r = ref.loss.CELoss(360)(out[0], label[:, 0])
     close(ko.ce_loss(out[0], label[:, 0], 360).item(), r.item(), 2e-5)
+
+
+# ---- the other in-batch variants (auxiliary/model_utils.py:169-223, 288-351) -----------------------------------------
+def test_infonce_single_and_multipose_match_golden(gold):
+    g, _, _, sf, tf, label = gold
+    a, p = leaf(sf), leaf(tf)
+    l = ko.nce_self(a, p, None, 0.1)
+    l.backward()
+    close(l.item(), g["infonce/loss"], 2e-5)
+    close(a.grad, g["infonce/d_ori"])
+    close(p.grad, g["infonce/d_pos"])
+    a, p = leaf(sf), leaf(tf)
+    l = ko.single_nce_kd(a, p, 0.1)
+    l.backward()
+    close(l.item(), g["single/loss"], 2e-5)
+    close(a.grad, g["single/d_ori"])
+    close(p.grad, g["single/d_pos"])
+    lab = torch.from_numpy(g["multipose/label"])
+    d = ko.pairwise_rotation_err(lab)
+    assert int(((d <= 30.0).sum() - lab.shape[0]) // 2) >= 5      # the 30-degree rule really finds extra positives
+    assert ((d - 30.0).abs() > 0.5).all()                          # ... none of them a borderline case
+    a, p = leaf(sf), leaf(tf)
+    l = ko.multipose_nce_kd(a, p, lab, 0.1)
+    l.backward()
+    close(l.item(), g["multipose/loss"], 2e-5)
+    close(a.grad, g["multipose/d_ori"])
+    close(p.grad, g["multipose/d_pos"])
+
+
+@pytest.mark.parametrize("weighting", ["linear", "square", "sinsin"])
+def test_posence_matches_golden(gold, weighting):
+    """poseNCE's k = n term is e^{a_n.a_n/tau} = e^{1/tau} (22026 at tau = 0.1) times the weight f(0) = 0.  The fp32 reference
+    holds acos rounding noise on that diagonal (see test_rotation_err_matches_golden), which e^{10} turns into a visible
+    share of the sum for `linear` (8 % of the loss on this batch) and `sinsin` (2e-4).  With the reference's OWN fp32
+    distances substituted the restatement reproduces its numbers; with exact zeros (what oracle and kernel use) the
+    deviation is that artefact."""
+    g, _, _, sf, tf, label = gold
+    n = label.shape[0]
+    d = torch.from_numpy(g["rotation_err_pairs"].astype(np.float64)).reshape(n, n) / 180.0
+    w = {"linear": d, "square": d ** 2, "sinsin": torch.sin(d * np.pi) ** 2}[weighting]
+    a, p = leaf(sf), leaf(tf)
+    l = ko.nce_self(a, p, label, 0.1, weighting, weights=w)
+    l.backward()
+    close(l.item(), g[f"posence/{weighting}/loss"], 2e-5)
+    close(a.grad, g[f"posence/{weighting}/d_ori"], 2e-4)
+    close(p.grad, g[f"posence/{weighting}/d_pos"], 2e-4)
+    exact = ko.nce_self(sf, tf, label, 0.1, weighting).item()
+    tol = {"linear": 0.1, "square": 5e-5, "sinsin": 5e-4}[weighting]
+    close(exact, g[f"posence/{weighting}/loss"], tol)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_variants_against_live_reference_functions():
+    ref = ko.load_reference()
+    out, tout, sf, tf, label = ko.synthetic_step(9, 64, seed=5)
+    lab = ko.clustered_labels(label, seed=9)
+    with ko.cuda_is_identity():
+        close(ko.nce_self(sf, tf, None, 0.5).item(), ref.model_utils.infoNCE(sf, tf, 0.5).item(), 2e-5)
+        close(ko.single_nce_kd(sf, tf, 0.5).item(), ref.model_utils.singleinfoNCE_KD(sf, tf, label, 0.5).item(), 2e-5)
+        close(ko.multipose_nce_kd(sf, tf, lab, 0.5).item(), ref.model_utils.multiposeNCE_KD(sf, tf, lab, 0.5).item(), 2e-5)
+        close(ko.nce_self(sf, tf, label, 0.5, "square").item(), ref.model_utils.poseNCE(sf, tf, label, 0.5, "square").item(), 1e-4)
