@@ -602,7 +602,6 @@ constexpr int kFinalizeScratch = 4096;  // doubles
 __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int b) {
   __shared__ long long s_off[kFinalizeList];
   __shared__ double s_part[kFinalizeScratch];
-  __shared__ long long s_first, s_last;
   __shared__ bool is_last;
   __shared__ uint32_t s_epoch;
   if (f.xchg && threadIdx.x == 0)   // advanced by the last block only, i.e. after every block has read it
@@ -619,24 +618,17 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
     const long long w = u * G < f.NW ? u * G : f.NW;
     return (P * w) / f.NW;
   };
-  if (threadIdx.x == 0 && p1 <= p0) {   // (compact mode) nothing of this anchor lives in this shard
-    s_first = 1;
-    s_last = 0;
-  } else if (threadIdx.x == 0) {
-    long long first = ((p0 * f.NW) / P) / G;
-    if (first >= NU) first = NU - 1;
-    while (first > 0 && bnd(first) > p0) --first;
-    while (first + 1 < NU && bnd(first + 1) <= p0) ++first;
-    long long last = ((p1 * f.NW + P - 1) / P - 1) / G;  // near the largest u with bnd(u) < p1
+  // candidate units: the ones around p0 * NU / P .. p1 * NU / P, one extra on either side (the integer floors of bnd() can be
+  // off by one); units that do not overlap the anchor's range are dropped by the `valid` test below.  Every thread
+  // computes the same bounds: no serial search by one thread, no barrier
+  long long first = 1, last = 0;   // (compact mode) p1 <= p0: nothing of this anchor lives in this shard
+  if (p1 > p0) {
+    first = ((p0 * f.NW) / P) / G - 1;
+    if (first < 0) first = 0;
+    last = ((p1 * f.NW + P - 1) / P) / G + 1;
     if (last >= NU) last = NU - 1;
-    if (last < first) last = first;
-    while (last + 1 < NU && bnd(last + 1) < p1) ++last;
-    while (last > first && bnd(last) >= p1) --last;
-    s_first = first;
-    s_last = last;
+    if (first > last) first = last;
   }
-  __syncthreads();
-  const long long first = s_first, last = s_last;
   const int slot_w = 2 * f.D + kSlotExtra;
   const int ncol4 = slot_w / 4;                       // float4 columns per slot (grad_v1 | grad_v2 | scalars)
   int parts = kFinalizeThreads / ncol4;               // entry-parallel groups of ncol4 threads
@@ -713,13 +705,22 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
   __syncthreads();
   if (is_last) {
     __threadfence();
+    // the per-anchor scalars come into shared memory with ONE load per thread (a chain of B dependent-latency loads by five
+    // threads cost ~3 us); the sums below keep their fixed order
+    const bool staged = f.B * 8 <= kFinalizeScratch;
+    if (staged) {
+      __syncthreads();   // s_part is free: every thread has left the column sums above
+      for (int i = threadIdx.x; i < f.B * 8; i += kFinalizeThreads) s_part[i] = __ldcg(&f.anchor_part[i]);
+      __syncthreads();
+    }
+    auto ap = [&](int i) { return staged ? s_part[i] : __ldcg(&f.anchor_part[i]); };
     if (threadIdx.x < 5) {
       double s = 0.0;
-      for (int a = 0; a < f.B; ++a) s += __ldcg(&f.anchor_part[a * 8 + threadIdx.x]);
+      for (int a = 0; a < f.B; ++a) s += ap(a * 8 + threadIdx.x);
       f.result[threadIdx.x] = (threadIdx.x < 2) ? (f.full ? -s / (double)f.B : 0.0) : s;
     } else if (threadIdx.x == 5) {  // total loss, also as float32 (slot 6) so the caller needs no cast kernel
       double s0 = 0.0, s1 = 0.0;
-      for (int a = 0; a < f.B; ++a) { s0 += __ldcg(&f.anchor_part[a * 8]); s1 += __ldcg(&f.anchor_part[a * 8 + 1]); }
+      for (int a = 0; a < f.B; ++a) { s0 += ap(a * 8); s1 += ap(a * 8 + 1); }
       const double tot = f.full ? (-s0 / (double)f.B) + (-s1 / (double)f.B) : 0.0;
       f.result[5] = tot;
       f.result[6] = 0.0;

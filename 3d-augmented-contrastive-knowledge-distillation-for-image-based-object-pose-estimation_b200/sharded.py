@@ -258,6 +258,14 @@ class ShardedContrastMemory(ContrastMemory):
     def _sampler_for_offset(self):
         return getattr(self, "_local_sampler", None) or self.multinomial
 
+    NO_COMPACT = 0x20   # variant bit: no filter pre-pass (every entry of the list lives in this shard anyway)
+
+    def _step_variant(self, B, K1, D):
+        v = super()._step_variant(B, K1, D)
+        if self.local_negatives and not (v & self.STREAM) and not (self.variant & 0x40):
+            v |= self.NO_COMPACT   # in-shard negatives: nothing to filter out, the pre-pass would only cost its 13 us
+        return v
+
     def _gather(self, v1, v2, y):
         """ONE packed exchange before the kernel: local anchors -> all anchors (uneven B_loc allowed)."""
         counts = self._ensure_counts(v1.shape[0], v1.device)
