@@ -164,3 +164,44 @@ def test_train_mode_reference_size_vs_oracle(pkg, cuda):
                  "in/shape_feature", "in/img_feature"):
         want = w_grads[name].numpy()
         assert _rel(got[name].detach().cpu().numpy().reshape(want.shape), want) < 5e-4, name
+
+
+def _chain_state(Fs, Fi, widths, heads, proj, seed):
+    """A PoseEstimator-shaped tail with arbitrary widths (the reference's are 2048/1024/512/200, 24-12-24 x2, 800/400/200)."""
+    torch.manual_seed(seed)
+    sd = {}
+    dims = [Fs + Fi] + list(widths)
+    for n in range(1, 5):
+        i, o = dims[n - 1], dims[n]
+        sd[f"deformNet.conv{n}.weight"] = torch.randn(o, i, 1) / i ** 0.5
+        sd[f"deformNet.conv{n}.bias"] = torch.randn(o) * 0.1
+        if n < 4:
+            sd.update({f"deformNet.bn{n}.weight": torch.randn(o), f"deformNet.bn{n}.bias": torch.randn(o),
+                       f"deformNet.bn{n}.running_mean": torch.randn(o) * 0.2, f"deformNet.bn{n}.running_var": torch.rand(o) + 0.5})
+    for h, w in zip(pto.HEADS, heads):
+        sd[h + ".weight"], sd[h + ".bias"] = torch.randn(w, dims[4]) / dims[4] ** 0.5, torch.randn(w) * 0.1
+    pd = [Fi] + list(proj)
+    for lin, k in zip((0, 3, 6), range(3)):
+        sd[f"projector.{lin}.weight"], sd[f"projector.{lin}.bias"] = torch.randn(pd[k + 1], pd[k]) / pd[k] ** 0.5, torch.randn(pd[k + 1]) * 0.1
+    for bn, o in ((1, pd[1]), (4, pd[2])):
+        sd.update({f"projector.{bn}.weight": torch.randn(o), f"projector.{bn}.bias": torch.randn(o),
+                   f"projector.{bn}.running_mean": torch.randn(o) * 0.2, f"projector.{bn}.running_var": torch.rand(o) + 0.5})
+    return sd
+
+
+@pytest.mark.parametrize("Fs,Fi,B", [(0, 40, 3), (13, 51, 17), (256, 1024, 64), (70, 190, 200)])
+def test_ragged_widths_and_batches(pkg, cuda, Fs, Fi, B):
+    """Widths that are no multiples of the 64-wide K blocks / 128-wide tiles / 4-wide store groups, an empty shape feature,
+    odd head sizes, batches up to the 256-row limit: the zero padding of the operand images and the scalar tails."""
+    if Fs == 0:
+        pytest.skip("PoseEstimator always concatenates a shape feature")
+    sd = _chain_state(Fs, Fi, (Fs + Fi, 97, 66, 50), (7, 5, 9, 7, 5, 9), (131, 70, 33), seed=Fs + B)
+    tail = pkg.FrozenPoseTail.from_state_dict(sd).to(cuda)
+    g = torch.Generator().manual_seed(B)
+    sf, img = torch.randn(B, Fs, generator=g), torch.randn(B, Fi, generator=g)
+    for _ in range(2):
+        outs, x, p = tail(sf.to(cuda), img.to(cuda))
+        w_outs, w_x, w_p = pto.forward(sd, sf, img)
+        assert _rel(x.cpu().numpy(), w_x.numpy()) < TOL and _rel(p.cpu().numpy(), w_p.numpy()) < TOL
+        assert [tuple(o.shape) for o in outs] == [tuple(o.shape) for o in w_outs]
+        assert all(_rel(a.cpu().numpy(), b.numpy()) < TOL for a, b in zip(outs, w_outs))

@@ -242,3 +242,53 @@ def test_world2_nccl_matches_unsharded(pkg, comm):
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_world1_graphed_sharded_step_equals_the_eager_loop(pkg, cuda):
+    """The sharded forward + backward (peer-memory all-gather, in-shard negatives drawn inside the scoring pass, reduction with
+    the sum over ranks fused in) captured in a CUDA graph by GraphedStep: replays must reproduce the eager loop bit for bit,
+    with fresh negatives on every replay (device-resident sampler offset) -- on one rank, so it runs on the driver's GPU."""
+    opt = _opt(nce_k=1024)
+    B = 16
+    mods = []
+    for _ in range(2):
+        torch.manual_seed(3)
+        mods.append(pkg.ShardedCRDLoss(opt, rank=0, world_size=1, comm="p2p", local_negatives=True, fixed_local_batch=True,
+                                       seed=21).to(cuda))
+    a, b = mods
+    b.load_state_dict(a.state_dict(), strict=False)
+    gen = torch.Generator().manual_seed(8)
+    batches = [(torch.randn(B, opt.s_dim, generator=gen).pin_memory(), torch.randn(B, opt.t_dim, generator=gen).pin_memory(),
+                torch.randperm(opt.n_data, generator=gen)[:B].pin_memory()) for _ in range(4)]
+
+    def eager(m, batch):
+        f_s = batch[0].to(cuda).requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        loss = m(f_s, batch[1].to(cuda), batch[2].to(cuda))
+        loss.backward()
+        return loss, f_s
+
+    for m in (a, b):          # step 0 freezes Z through the general path, step 1 takes the one-call path
+        eager(m, batches[0])
+        eager(m, batches[0])
+    b.contrast.device_sampler_offset()
+
+    def fwd_bwd(f_s, f_t, idx):
+        loss = b(f_s, f_t, idx)
+        loss.backward()
+        return loss
+
+    warm = 2
+    step = pkg.GraphedStep(fwd_bwd, batches[0], cuda, grad_inputs=(0,), zero_grad=lambda: b.zero_grad(set_to_none=True), warmup=warm)
+    for _ in range(warm):
+        eager(a, batches[0])
+    step.stage(*batches[1])
+    for i in range(1, 4):
+        step.run()
+        if i + 1 < 4:
+            step.stage(*batches[i + 1])
+        want, f_s = eager(a, batches[i])
+        assert step.collect() == want.item(), i
+        assert torch.equal(step.static[0].grad, f_s.grad)
+        assert torch.equal(b.embed_s.linear.weight.grad, a.embed_s.linear.weight.grad)
+    assert torch.equal(b.contrast.memory_v1, a.contrast.memory_v1) and torch.equal(b.contrast.memory_v2, a.contrast.memory_v2)
