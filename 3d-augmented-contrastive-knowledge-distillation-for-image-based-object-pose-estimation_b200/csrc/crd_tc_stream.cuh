@@ -160,27 +160,35 @@ __global__ void __launch_bounds__(kThreads, 1) crd_tc_stream_kernel(const TcPara
     tma_box(dst + 16384 + 8192, &tm2, 64, y, bar);
   };
   constexpr uint32_t kIS = idesc_bf16(128, 96, 0), kIG = idesc_bf16(128, 48, 1);
+  // Descriptors: ONE base per operand image, the per-k-step operands are the base plus a compile-time constant in the
+  // 14-bit address field (shared memory is < 256 KB, so the sum never carries into the LBO field).  Building each of the
+  // 32 descriptors of a tile from its address (and, shift, or, pack: a dependent chain in the one issuing thread) was most of
+  // the ~82 cycles a tcgen05.mma cost that thread.
+  const uint64_t bv_desc = desc128(base + kOffBV, 16, 1024);                 // [V2 | V1], K-major, resident
+  const uint64_t c_desc0 = desc128(base + kOffC, 16, 1024);                  // coefficient images of tile parity 0 (C2^T)
+  const uint64_t c_desc1 = desc128(base + kOffC + 2 * kCImg, 16, 1024);      // ... parity 1
   bool g_started = false;   // (MMA warp) the gradient accumulators hold something
   auto issue_scores = [&](int j) {   // MMA warp, converged
     if (elect_one()) {
-      const uint32_t a_img = base + kOffA + (uint32_t)(j % kStages) * kAStage;
+      const uint64_t a0 = desc128(base + kOffA + (uint32_t)(j % kStages) * kAStage, 16, 1024);
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk)
-        umma_f16(tmem, desc128(a_img + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                 desc128(base + kOffBV + (kk >> 2) * (96 * 128) + (kk & 3) * 32, 16, 1024), kIS, kk > 0);
+        umma_f16(tmem, a0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                 bv_desc + (uint64_t)(((kk >> 2) * (96 * 128) + (kk & 3) * 32) >> 4), kIS, kk > 0);
       umma_commit(bar_s);
     }
     __syncwarp();
   };
   auto issue_grads = [&](int j) {    // MMA warp, converged
     if (elect_one()) {
-      const uint32_t a_img = base + kOffA + (uint32_t)(j % kStages) * kAStage;
-      const uint32_t c_img = base + kOffC + (uint32_t)(j & 1) * 2 * kCImg;
+      // the tile image read MN-major: 16 bank rows per step = two 8-row swizzle atoms (LBO 16384: the second K-block)
+      const uint64_t a0 = desc128(base + kOffA + (uint32_t)(j % kStages) * kAStage, 16384, 1024);
+      const uint64_t c0 = (j & 1) ? c_desc1 : c_desc0;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {   // 16 bank rows per step = two 8-row swizzle atoms of the same image, read MN-major
+      for (int kk = 0; kk < 4; ++kk) {
         const uint32_t acc = (g_started || kk > 0) ? 1u : 0u;
-        umma_f16(tmem + 96, desc128(a_img + kk * 2048, 16384, 1024), desc128(c_img + kk * 32, 16, 1024), kIG, acc);
-        umma_f16(tmem + 144, desc128(a_img + 64 * 128 + kk * 2048, 16384, 1024), desc128(c_img + kCImg + kk * 32, 16, 1024), kIG, acc);
+        umma_f16(tmem + 96, a0 + (uint64_t)((kk * 2048) >> 4), c0 + (uint64_t)((kk * 32) >> 4), kIG, acc);
+        umma_f16(tmem + 144, a0 + (uint64_t)((64 * 128 + kk * 2048) >> 4), c0 + (uint64_t)((kCImg + kk * 32) >> 4), kIG, acc);
       }
       umma_commit((j & 1) ? bar_g1 : bar_g0);
     }

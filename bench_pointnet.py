@@ -230,6 +230,18 @@ def bench_pointnet_train(pkg, torch, dev, st, x, steps, warmup, tf_peak, B, P, F
     mma_per_product = 3 if precision == "fp32" else 1
     res["forward"]["tflops_fwd_equiv"] = FLOP_PER_POINT * B * P / (res["forward"]["ms_per_step"] * 1e-3) / 1e12
     res["forward"]["tensor_tflops_issued"] = res["forward"]["tflops_fwd_equiv"] * mma_per_product
+    # roofline of the train step: the tensor work actually issued (forward products x MMAs per product; the backward's dense
+    # stream is 2 x (128 x 128 + 2 x 128 x 64 + 64 x 64) MACs per point, one MMA per product) over the step time, against the
+    # measured sustained bf16 / fp16 dense peak.  The step is NOT tensor-bound: the forward kernel runs at 55 % tensor-pipe
+    # active, the two dense backward passes at 14 % / 6 % (profiles/r2_pointnet_train_ncu_summary.txt: epilogue-bound)
+    bwd_flop = 2 * (128 * 128 + 2 * 128 * 64 + 64 * 64) * 2
+    issued = (FLOP_PER_POINT * mma_per_product + bwd_flop) * B * P
+    t_step = res["forward_backward"]["ms_per_step"] * 1e-3
+    peak = tf_peak if tf_peak else 1666.8
+    res["roofline"] = {"bound": "tensor", "achieved": issued / t_step / 1e12, "peak": peak, "unit": "TFLOP/s",
+                       "frac": issued / t_step / 1e12 / peak, "traffic": None,
+                       "kernel": "train step (forward + backward, 17 launches)",
+                       "note": "issued tensor FLOP of the whole step over its device time; see the ncu summary for per-kernel pipe activity"}
     res["note"] = ("backward never forms the B*F*P tensor: sparse arg-max stream + affine dense stream (128x128 and 64x64 "
                    "per point) on tcgen05; the stock autograd chain needs 2 x 111.6 GFLOP of dgrad/wgrad plus ~10 passes over 1.64 GB")
     return res
