@@ -410,6 +410,7 @@ class ContrastMemory(nn.Module):
         self.k_total = 0   # negatives per anchor over all shards (0: the K+1 columns of contrast_idx are all of them)
         self.variant = 0
         self.streaming = None    # None: automatic (bf16 banks only), True / False: forced (see _step_variant)
+        self.sweep = None        # None: automatic, True / False: forced (band-sorted lists, see _step_variant)
         self.register_buffer("params", torch.tensor([K, T, -1, -1, momentum], dtype=torch.float32))
         stdv = 1.0 / math.sqrt(inputSize / 3)
         rows = self.row_end - self.row_begin
@@ -511,6 +512,7 @@ class ContrastMemory(nn.Module):
 
     STREAM = 0x200   # variant bit: bank-streaming formulation of the step (csrc/crd_stream.cuh)
     IDX32 = 0x1000   # variant bit: contrast_idx is an int32 list
+    SWEEP = 0x400    # variant bit: band-sorted contrast lists (csrc/crd_kernels.cu crd_band_sort_kernel): repeats of a row are L2 hits
     DEVICE_OFFSET = 0x4000   # variant bit: the sampler offset's advancing part is a device counter (CUDA-graph replays)
 
     def _step_variant(self, B, K1, D):
@@ -526,17 +528,34 @@ class ContrastMemory(nn.Module):
         if self.variant & self.STREAM:
             return self.variant
         if self.streaming is False:
-            return self.variant
+            return self._with_sweep(self.variant, B, K1, D)
         rows = self.row_end - self.row_begin
         ok = D == 128 and 1 <= B <= 48 and rows >= 1
         if self.streaming is None:
             # samples that land on this shard: all K+1 columns when every rank draws its own rows (k_total > 0), else its share
             hits = B * K1 if self.k_total > 0 else B * K1 * rows // max(self.nLem, 1)
             auto = ok and self._buffers["memory_v1"].dtype == torch.bfloat16 and hits >= 2 * rows
-            return self.variant | self.STREAM if auto else self.variant
+            return self.variant | self.STREAM if auto else self._with_sweep(self.variant, B, K1, D)
         if not ok:
             raise RuntimeError("streaming CRD step needs feat_dim 128 and batch <= 48")
         return self.variant | self.STREAM
+
+    def _with_sweep(self, variant, B, K1, D):
+        """Adds the SWEEP bit to a gather-kernel variant when the band-sorted formulation pays: the step draws each resident
+        row more than ~1.5 times and the shard is several times larger than the 126 MB L2 (otherwise the repeats are L2 hits
+        already: an 8-way shard of the headline bank, config 0).  Measured at the headline shape: DRAM traffic 2.91 -> 1.02 GB,
+        scoring kernel 0.441 -> 0.381 ms, 19 us of pre-pass (profiles/r2_sweep_ab.py).  ``self.sweep`` forces it on / off."""
+        if variant & (self.SWEEP | 0x20 | 0x40 | 0x100):
+            return variant
+        if self.sweep is False:
+            return variant
+        if self.sweep is None:
+            rows = self.row_end - self.row_begin
+            esz = 2 if self._buffers["memory_v1"].dtype == torch.bfloat16 else 4
+            hits = B * K1 if self.k_total > 0 else B * K1 * rows // max(self.nLem, 1)
+            if not (rows * 2 * D * esz >= (384 << 20) and 2 * hits >= 3 * rows and B * K1 >= (1 << 20)):
+                return variant
+        return variant | self.SWEEP
 
     def _workspace(self, B, K1, D, device, variant=0):
         stream = bool(variant & self.STREAM)

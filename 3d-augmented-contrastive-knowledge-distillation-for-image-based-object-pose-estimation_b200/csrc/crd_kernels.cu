@@ -71,7 +71,9 @@ struct ScoreParams {
   // u = b * (NC + 1) + c of anchor b: c = 0 the positive (k = 0), c >= 1 the survivors of the kFilterChunk entries
   // k in [1 + (c-1) kFilterChunk, ...) in list order: local rows cl[(b NC + c-1) kFilterChunk ...], ucount[b NC + c-1] of them.
   // The warps cut the COMPACT space into equal ranges (exactly balanced, no scan), warp w writes slot w + b for anchor b.
-  int compact;
+  int compact;              // 0 off, 1 compact lists in list order, 3 band-sorted lists + interleaved blocks (see crd_band_sort_kernel)
+  int wpu;                  // compact == 3: warps per (anchor, chunk) unit
+  unsigned band_mul;        // compact == 3: band of local row r = min(31, (r * band_mul) >> 32)
   int NC;
   const int* cl;
   const int* ucount;
@@ -88,6 +90,7 @@ struct FinalizeParams {
   int group;            // warps per slot-writing unit: 1 (every warp writes its own slots) or kWarps (ScoreParams::cta_reduce)
   const long long* anchor_start;   // compact mode (ScoreParams::compact): anchor b owns [anchor_start[b], anchor_start[b+1]) of the
                                    // compact space cut over NW warps, warp w's partial for anchor b is slot w + b; else null
+  int wpa;              // band-sorted mode (ScoreParams::compact == 3): warps per anchor, anchor b's partials are slots [b wpa, (b+1) wpa)
   int B, K1, D;
   int full;
   float* grad_v1;
@@ -221,6 +224,88 @@ __global__ void __launch_bounds__(256, 5) crd_shard_filter_kernel(const ScorePar
   if (tid == 0) ucount[blockIdx.x] = s_pre[NCNT];
 }
 
+// Band-sorted compact lists (ScoreParams::compact == 3).  The gather kernel is at the HBM roofline of B*(K+1) row reads,
+// but at the headline shape every resident row is drawn ~3x per step and the repeats come from HBM again (L2 hit rate 6 %):
+// the warps walk 2 368 unrelated stretches of the lists at once, so the whole bank is the working set.  Here every
+// (anchor, chunk) list is STABLY counting-sorted by row band (32 bands of the shard) and the scoring pass hands the warps of a
+// unit interleaved 32-entry blocks of the sorted list: every warp then sweeps the bank from band 0 to band 31, all of them at
+// the same pace, the working set is the band or two they are in, and a row's repeats within the step are L2 hits.
+// Same shard filter as crd_shard_filter_kernel; order within a band = list order (deterministic: ballot ranks + a prefix
+// over the (band, slice, warp) counts).
+constexpr int kBands = 32;
+// lanes of the warp whose 5-bit `bin` equals this lane's, among the lanes with `valid` set (five ballots: fixed cost, where
+// match.any iterates over the distinct values -- nearly one per lane here)
+__device__ __forceinline__ unsigned same_bin_mask(int bin, bool valid) {
+  unsigned m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int bit = 0; bit < 5; ++bit) {
+    const unsigned bal = __ballot_sync(0xffffffffu, (bin >> bit) & 1);
+    m &= ((bin >> bit) & 1) ? bal : ~bal;
+  }
+  return m;
+}
+__device__ __forceinline__ int band_of(const ScoreParams& p, int row) {
+  const int b = (int)(((unsigned long long)(unsigned)row * (unsigned long long)p.band_mul) >> 32);
+  return b < kBands - 1 ? b : kBands - 1;
+}
+__global__ void __launch_bounds__(256, 5) crd_band_sort_kernel(const ScoreParams p, int* __restrict__ cl, int* __restrict__ ucount) {
+  constexpr int EPT = kFilterEPT, NCNT = kBands * EPT * 8;   // counts: [band][slice of 256 entries][warp]
+  __shared__ int s_cnt[NCNT];
+  __shared__ int s_wsum[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / p.NC, c = blockIdx.x - b * p.NC;
+  const long long anchor_base = (long long)b * p.K1;
+  const int k0 = 1 + c * kFilterChunk;
+  int row[EPT];
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) {
+    const int k = k0 + j * 256 + tid;
+    long long r = -1;
+    if (k < p.K1) r = contrast_entry(p, anchor_base + k, b, anchor_base);
+    row[j] = (r >= p.row_begin && r < p.row_end) ? (int)(r - p.row_begin) : -1;
+  }
+  for (int i = tid; i < NCNT; i += 256) s_cnt[i] = 0;
+  __syncthreads();
+  const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) {
+    const bool valid = row[j] >= 0;
+    const int bin = valid ? band_of(p, row[j]) : 0;
+    const unsigned m = same_bin_mask(bin, valid);
+    if (valid && (m & below) == 0u) s_cnt[(bin * EPT + j) * 8 + warp] = __popc(m);   // the group's first lane
+  }
+  __syncthreads();
+  {   // exclusive prefix over the NCNT counts in (band, slice, warp) order: 16 consecutive counts per thread
+    constexpr int PER = NCNT / 256;
+    int cv[PER], tot = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { cv[i] = s_cnt[tid * PER + i]; tot += cv[i]; }
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    int run = inc - tot;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) run += (w < warp) ? s_wsum[w] : 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { s_cnt[tid * PER + i] = run; run += cv[i]; }
+    if (tid == 255) ucount[blockIdx.x] = run;
+  }
+  __syncthreads();
+  int* dst = cl + (size_t)blockIdx.x * kFilterChunk;
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) {
+    const bool valid = row[j] >= 0;
+    const int bin = valid ? band_of(p, row[j]) : 0;
+    const unsigned m = same_bin_mask(bin, valid);
+    if (valid) dst[s_cnt[(bin * EPT + j) * 8 + warp] + __popc(m & below)] = row[j];
+  }
+}
+
 template <typename T> struct Unpack;
 template <> struct Unpack<float> {
   static constexpr int VEC = 4;
@@ -273,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
     const long long w0 = (long long)blockIdx.x * kWarps;
     b_first_cta = (int)((P * (w0 < NW ? w0 : NW) / NW) / p.K1);
     __syncthreads();
-  } else if (gw >= NW && p.compact == 0) {
+  } else if (gw >= NW && p.compact != 1) {
     return;
   }
   long long lo = gw < NW ? P * gw / NW : 0;
@@ -284,7 +369,8 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
 
   // ---- compact mode: exclusive prefix of the unit counts (shared memory), then equal ranges of the COMPACT space ----
   __shared__ int s_wsum[kWarps];
-  const bool compact = p.compact != 0;
+  const bool compact = p.compact == 1;
+  const bool banded = p.compact == 3;   // band-sorted lists, warp gw = (unit gw / wpu, interleave slot gw % wpu)
   const int UPA = p.NC + 1;                 // units per anchor: the positive, then NC filtered chunks
   int cu = 0;                               // current unit
   if (compact) {   // (cta_reduce is off in this mode, so every thread is still here)
@@ -342,14 +428,16 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
     }
   }
 
+  if (banded) { lo = 0; hi = 1; }   // one pass of the loop below: this warp's share of ONE unit
   while (lo < hi) {
     if (compact)
       while ((long long)s_upre[cu + 1] <= lo) ++cu;
-    const int b = compact ? cu / UPA : (int)(lo / p.K1);
+    const int b = banded ? (int)(gw / p.wpu) / p.NC : compact ? cu / UPA : (int)(lo / p.K1);
     const long long anchor_base = (long long)b * p.K1;
-    const long long seg_hi = compact ? ((hi < (long long)s_upre[(b + 1) * UPA]) ? hi : (long long)s_upre[(b + 1) * UPA])
+    const long long seg_hi = banded ? 1
+                           : compact ? ((hi < (long long)s_upre[(b + 1) * UPA]) ? hi : (long long)s_upre[(b + 1) * UPA])
                                      : ((hi < anchor_base + p.K1) ? hi : (anchor_base + p.K1));
-    const int pos_off = compact ? 0 : ((anchor_base == lo) ? 0 : -1);  // queue tag of the positive (k == 0) entry
+    const int pos_off = (compact || banded) ? 0 : ((anchor_base == lo) ? 0 : -1);  // queue tag of the positive (k == 0) entry
 
     float v1c[NV], v2c[NV];
 #pragma unroll
@@ -463,7 +551,37 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
     };
 
     auto fetch_idx = [&](long long pos) -> long long { return contrast_entry(p, pos, b, anchor_base); };
-    if (compact) {
+    if (banded) {
+      const int unit = (int)(gw / p.wpu), t = (int)(gw - (long long)unit * p.wpu), c = unit - b * p.NC;
+      const int n = p.ucount[unit];
+      const int* src = p.cl + (size_t)unit * kFilterChunk;
+      if (c == 0 && t == 0) {   // the anchor's positive (k = 0) rides with the first warp of its first unit
+        const long long r = contrast_entry(p, anchor_base, b, anchor_base);
+        if (r >= p.row_begin && r < p.row_end) {
+          if (lane == 0) q[qtail & (kQueueCap - 1)] = make_int2((int)(r - p.row_begin), 0);
+          qtail += 1;
+        }
+      }
+      // blocks t, t + wpu, ... of the band-sorted list, 32 entries each; the next block's indices are loaded before this
+      // block's rows are consumed
+      int i = t * 32;
+      int nxt = (i + lane < n) ? src[i + lane] : 0;
+#pragma unroll 1
+      while (i < n) {
+        const int cur_row = nxt, cnt_blk = (n - i < 32) ? (n - i) : 32;
+        const int i2 = i + p.wpu * 32;
+        nxt = (i2 + lane < n) ? src[i2 + lane] : 0;
+        if (lane < cnt_blk) q[(qtail + lane) & (kQueueCap - 1)] = make_int2(cur_row, 1);
+        qtail += cnt_blk;
+        __syncwarp();
+        while (qtail - qhead >= R * U) {
+          consume(R * U);
+          qhead += R * U;
+        }
+        __syncwarp();
+        i = i2;
+      }
+    } else if (compact) {
       // entries of this segment, unit by unit: every one of them is scored (the filter kernel dropped the rest)
       long long cur = lo;
       while (cur < seg_hi) {
@@ -554,6 +672,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       cnt += __shfl_xor_sync(kFull, cnt, off);
     }
     float* slot = cta_red ? red_smem + (warp * 2 + (b - b_first_cta)) * kSW
+                : banded ? p.slots + (long long)gw * (2 * p.D + kSlotExtra)
                 : compact ? p.slots + ((long long)gw + b) * (2 * p.D + kSlotExtra)
                           : p.slots + ((long long)gw * p.maxseg + seg) * (2 * p.D + kSlotExtra);
     if (g == 0) {
@@ -622,7 +741,10 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
   // off by one); units that do not overlap the anchor's range are dropped by the `valid` test below.  Every thread
   // computes the same bounds: no serial search by one thread, no barrier
   long long first = 1, last = 0;   // (compact mode) p1 <= p0: nothing of this anchor lives in this shard
-  if (p1 > p0) {
+  if (f.wpa > 0) {
+    first = (long long)b * f.wpa;
+    last = first + f.wpa - 1;
+  } else if (p1 > p0) {
     first = ((p0 * f.NW) / P) / G - 1;
     if (first < 0) first = 0;
     last = ((p1 * f.NW + P - 1) / P) / G + 1;
@@ -642,8 +764,8 @@ __device__ __forceinline__ void finalize_body(const FinalizeParams& f, const int
       const long long w = chunk + i;
       const long long lo = bnd(w);
       const long long hi = bnd(w + 1);
-      const bool valid = hi > p0 && hi > lo && lo < p1;
-      s_off[i] = !valid ? -1 : compact ? (w + b) * (long long)slot_w
+      const bool valid = f.wpa > 0 || (hi > p0 && hi > lo && lo < p1);
+      s_off[i] = !valid ? -1 : f.wpa > 0 ? w * (long long)slot_w : compact ? (w + b) * (long long)slot_w
                                        : (w * f.maxseg + (b - (int)(lo / f.K1))) * (long long)slot_w;
     }
     __syncthreads();
@@ -1009,7 +1131,8 @@ struct IdxSource {
   const int64_t* y;
   uint64_t seed, offset;
   int64_t draw_n, draw_base;
-  int compact;              // row-sharded step: run crd_shard_filter_kernel first and score the compact lists (y must be set)
+  int compact;              // 1: run crd_shard_filter_kernel first and score the compact lists (y must be set); 2: the caller has
+                            // launched it; 3 / 4: the same with band-sorted lists (crd_band_sort_kernel, ScoreParams::compact == 3)
 };
 
 // compact lists of the row-sharded step inside the workspace (behind the slots)
@@ -1019,6 +1142,16 @@ struct CompactPlan {
   int* ucount;
   int* cl;
 };
+// warps per (anchor, chunk) unit of the band-sorted mode, 0 = not worth it / not possible (too few rows to band, or too few
+// units to occupy the machine)
+static long long banded_wpu(long long B, long long NC, long long NW, long long rows_local) {
+  if (rows_local < 4096 || B * NC < 1) return 0;
+  long long wpu = NW / (B * NC);
+  if (wpu > 8) wpu = 8;
+  if (wpu < 1 || B * NC * wpu * 2 < NW) return 0;
+  return wpu;
+}
+
 static bool plan_compact(int bank_dtype, int64_t D, int variant, int64_t B, int64_t K1, int64_t row_begin, int64_t row_end,
                          int sms, void* workspace, CompactPlan* out) {
   Variant var;
@@ -1099,9 +1232,14 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   // CTA-level fold of the warp partials: possible when a CTA's range of pairs spans at most two anchors and its slots fit
   // static shared memory; not for the per-entry outputs mode (kept on the original layout) or the aligned partition
   const long long NC = filter_chunks(K1);
-  const bool compact = src != nullptr && src->compact != 0 && src->y != nullptr && full && !aligned && out_v1 == nullptr && NC >= 1 &&
-                       B * (NC + 1) < kMaxUnits && B <= NW && row_end > row_begin;
-  const bool cta_reduce = !compact && !aligned && D <= 256 && out_v1 == nullptr && (P * kWarps + NW - 1) / NW + 1 <= K1 && !no_cta_fold;
+  const bool lists_ok = src != nullptr && src->compact != 0 && src->y != nullptr && full && !aligned && out_v1 == nullptr && NC >= 1 &&
+                        B * (NC + 1) < kMaxUnits && B <= NW && row_end > row_begin;
+  // band-sorted lists: wpu warps per (anchor, chunk) unit take interleaved blocks of the unit's sorted list
+  long long wpu = 0;
+  if (lists_ok && src->compact >= 3) wpu = banded_wpu(B, NC, NW, row_end - row_begin);
+  const bool banded = wpu > 0;
+  const bool compact = lists_ok && !banded && src->compact < 3;   // (band sort asked for but not possible: the plain scan)
+  const bool cta_reduce = !compact && !banded && !aligned && D <= 256 && out_v1 == nullptr && (P * kWarps + NW - 1) / NW + 1 <= K1 && !no_cta_fold;
   const size_t need = workspace_bytes_for(B, K1, D, NW);
   if (workspace_bytes < need) return fail(CRDPN_E_WORKSPACE, "crdpn_crd_score: workspace too small");
 
@@ -1143,7 +1281,10 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.ticket = ticket;
   sp.nw = NW;
   sp.cta_reduce = cta_reduce ? 1 : 0;
-  sp.compact = compact ? 1 : 0;
+  sp.compact = banded ? 3 : compact ? 1 : 0;
+  sp.wpu = (int)wpu;
+  sp.band_mul = banded ? (unsigned)((((unsigned long long)kBands) << 32) / (unsigned long long)(row_end - row_begin)) + 1u : 0u;
+  if (banded) sp.nw = B * NC * wpu;
   sp.NC = (int)NC;
   char* cbase = ws + workspace_slots_end(B, K1, D, NW);
   long long* anchor_start = (long long*)cbase;
@@ -1152,10 +1293,11 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.cl = cl; sp.ucount = ucount; sp.anchor_start = anchor_start;
 
   cudaStream_t st = (cudaStream_t)stream;
-  if (compact) {   // pre-pass: drop the entries other shards own, keep list order (compact == 2: the caller has launched it)
+  if (compact || banded) {   // pre-pass: drop the entries other shards own, keep list order / sort by band (compact == 2, 4: the caller has launched it)
     if (sp.idx_mode != 2) sp.y = (const long long*)src->y;
-    if (src->compact != 2) {
-      crd_shard_filter_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
+    if (src->compact != 2 && src->compact != 4) {
+      if (banded) crd_band_sort_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
+      else crd_shard_filter_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
       CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
     }
   }
@@ -1166,8 +1308,9 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   CRDPN_LAUNCH_CHECK("crd_score_kernel");
 
   FinalizeParams fp;
-  fp.slots = slots; fp.maxseg = sp.maxseg; fp.NW = NW; fp.group = cta_reduce ? kWarps : 1;
+  fp.slots = slots; fp.maxseg = sp.maxseg; fp.NW = banded ? sp.nw : NW; fp.group = cta_reduce ? kWarps : 1;
   fp.anchor_start = compact ? anchor_start : nullptr;
+  fp.wpa = banded ? (int)(NC * wpu) : 0;
   fp.B = (int)B; fp.K1 = (int)K1; fp.D = (int)D; fp.full = full ? 1 : 0;
   fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2;
   fp.anchor_part = anchor_part; fp.result = result; fp.ticket = ticket;
@@ -1428,6 +1571,12 @@ extern "C" int crdpn_crd_step(void* bank1, void* bank2, int64_t row_stride, int 
     return stream_step_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, contrast_idx, B, K1, D, n_data, k_total, row_begin,
                             row_end, T, Z1, Z2, eps, result, grad_v1, grad_v2, workspace, workspace_bytes, u,
                             (variant & 0x800) ? 1 : 0, stream);
+  if (variant & 0x400) {    // band-sorted lists (crd_band_sort_kernel): repeats of a row within the step become L2 hits
+    const IdxSource src{(variant & 0x1000) ? 1 : 0, (const int*)contrast_idx, y, 0, 0, 0, 0, 3};
+    return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, (variant & 0x1000) ? nullptr : contrast_idx, B, K1, D, n_data,
+                      k_total, row_begin, row_end, T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace,
+                      workspace_bytes, variant & ~0x1400, &u, stream, nullptr, &src);
+  }
   if (variant & 0x1000) {   // contrast_idx is an int32 list
     const IdxSource src{1, (const int*)contrast_idx, nullptr, 0, 0, 0, 0, 0};
     return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, nullptr, B, K1, D, n_data, k_total, row_begin, row_end,
@@ -1455,7 +1604,7 @@ extern "C" int crdpn_crd_step_drawn(void* bank1, void* bank2, int64_t row_stride
   if (rc) return rc;
   const UpdateParams u = make_update_params(bank1, bank2, row_stride, bank_dtype, v1, v2, y, B, D, row_begin, row_end,
                                             momentum, one_minus_momentum);
-  const IdxSource src{2, nullptr, y, seed, offset, draw_n, draw_base, 0};
+  const IdxSource src{2, nullptr, y, seed, offset, draw_n, draw_base, (variant & 0x400) ? 3 : 0};
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1, v2, nullptr, B, K1, D, n_data, k_total, row_begin, row_end,
                     T, Z1, Z2, eps, nullptr, nullptr, result, grad_v1, grad_v2, workspace, workspace_bytes, variant & 0xfff,
                     &u, stream, nullptr, &src);
@@ -1483,7 +1632,9 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
   // scoring pass 76 -> 67 us at 1/8 of the rows, nothing at 1/2); variant bit 6 forces it on (single-GPU tests), bit 5 off
   const bool gather = v1_local != nullptr;
   bool prefiltered = false;
-  const bool want_compact = !(variant & 0x200) && !(variant & 0x20) && ((variant & 0x40) || (row_end - row_begin) * 3 <= n_data);
+  const bool want_compact = !(variant & 0x200) && !(variant & 0x20) &&
+                            ((variant & 0x40) || (variant & 0x400) || (row_end - row_begin) * 3 <= n_data);
+  bool sweep = false;   // band-sorted lists (variant | 0x400)
   cudaStream_t st = (cudaStream_t)stream;
   SideStream* side = nullptr;
   if (want_compact && gather && workspace != nullptr) {
@@ -1502,9 +1653,12 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
       fpar.seed = seed; fpar.offset = offset; fpar.draw_n = draw_n; fpar.draw_base = draw_base;
       fpar.offset_dev = idx_mode == 2 ? g_sampler_offset_dev : nullptr;
       fpar.B = (int)B; fpar.K1 = (int)K1; fpar.D = (int)D; fpar.row_begin = row_begin; fpar.row_end = row_end; fpar.NC = (int)cp.NC;
+      sweep = (variant & 0x400) && banded_wpu(B, cp.NC, cp.NW, row_end - row_begin) > 0;
+      fpar.band_mul = sweep ? (unsigned)((((unsigned long long)kBands) << 32) / (unsigned long long)(row_end - row_begin)) + 1u : 0u;
       CRDPN_CUDA(cudaEventRecord(side->fork, st));
       CRDPN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
-      crd_shard_filter_kernel<<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
+      if (sweep) crd_band_sort_kernel<<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
+      else crd_shard_filter_kernel<<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
       CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
       CRDPN_CUDA(cudaEventRecord(side->join, side->s));
       prefiltered = true;
@@ -1537,7 +1691,7 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
   x.timeout = p2p::poll_timeout_ticks();
   // an empty shard still takes part in the exchange: score_impl launches the reduction kernel either way
   const IdxSource src{idx_mode, (const int*)contrast_idx, y_all, seed, offset, draw_n, draw_base,
-                      prefiltered ? 2 : (want_compact ? 1 : 0)};
+                      prefiltered ? (sweep ? 4 : 2) : (want_compact ? ((variant & 0x400) ? 3 : 1) : 0)};
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, idx_mode == 0 ? contrast_idx : nullptr, B, K1, D,
                     n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, nullptr, nullptr, result, partial, partial + B * D,
                     workspace, workspace_bytes, variant & 0xf9f, &u, stream, &x, &src);

@@ -262,7 +262,7 @@ class ShardedContrastMemory(ContrastMemory):
 
     def _step_variant(self, B, K1, D):
         v = super()._step_variant(B, K1, D)
-        if self.local_negatives and not (v & self.STREAM) and not (self.variant & 0x40):
+        if self.local_negatives and not (v & self.STREAM) and not (self.variant & 0x40) and not (v & self.SWEEP):
             v |= self.NO_COMPACT   # in-shard negatives: nothing to filter out, the pre-pass would only cost its 13 us
         return v
 

@@ -640,3 +640,58 @@ def test_graphed_step_equals_the_eager_loop(pkg, cuda):
     assert torch.equal(b.contrast.memory_v1, a.contrast.memory_v1) and torch.equal(b.contrast.memory_v2, a.contrast.memory_v2)
     b.contrast.device_sampler_offset(False)
     assert b.contrast.multinomial.offset == a.contrast.multinomial.offset
+
+
+def test_band_sorted_step_matches_the_gather_step(pkg, oracle, cuda):
+    """ContrastMemory.sweep (variant | 0x400): every (anchor, chunk) list stably sorted by row band, the warps of a unit taking
+    interleaved blocks of it.  Same scores, so: loss / gradients equal the gather step's up to fp32 summation order, updated
+    rows bit-identical, bit-reproducible run to run, and (two anchors) equal to the oracle.  Also through CRDLoss with the
+    negatives drawn inside the pre-pass, and with an int32 list."""
+    B, D, K, N, T = 46, 128, 65536, 20000, 0.07
+    gen = torch.Generator().manual_seed(12)
+    bank = torch.nn.functional.normalize(torch.randn(N, 2, D, generator=gen), dim=2)
+    v1 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen)).to(cuda)
+    v2 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen)).to(cuda)
+    y = torch.randperm(N, generator=gen)[:B].to(cuda)
+    cidx = torch.randint(0, N, (B, K + 1), generator=gen)
+    cidx[:, 0] = y.cpu()
+    Z1, Z2 = 4.1e4, 4.3e4
+    runs = {}
+    for name, sweep, lst in (("gather", False, cidx), ("swept", True, cidx), ("swept_again", True, cidx), ("swept_i32", True, cidx.to(torch.int32))):
+        mem = pkg.ContrastMemory(D, N, K, T, 0.5).to(cuda)
+        with torch.no_grad():
+            mem.memory_v1.copy_(bank[:, 0]); mem.memory_v2.copy_(bank[:, 1]); mem.params[2], mem.params[3] = Z1, Z2
+        mem._host = None
+        mem.sweep = sweep
+        if lst.dtype == torch.int32:
+            mem.variant = mem.IDX32       # (ContrastMemory._step takes the list as it is; CRDLoss sets this bit itself)
+        assert bool(mem._step_variant(B, K + 1, D) & mem.SWEEP) == sweep
+        res, g1, g2 = mem._step(v1, v2, y, lst.to(cuda), Z1, Z2)
+        torch.cuda.synchronize()
+        runs[name] = (res.clone(), g1.clone(), g2.clone(), mem.memory_v1[y].clone(), mem.memory_v2[y].clone())
+    a, b = runs["gather"], runs["swept"]
+    assert abs((a[0][5] - b[0][5]).item()) <= 1e-6 * abs(a[0][5].item()) and a[0][4].item() == b[0][4].item() == B * (K + 1)
+    assert _rel(b[1].cpu().numpy(), a[1].cpu().numpy()) < 1e-5 and _rel(b[2].cpu().numpy(), a[2].cpu().numpy()) < 1e-5
+    assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    for other in ("swept_again", "swept_i32"):
+        assert all(torch.equal(p, q) for p, q in zip(b, runs[other])), other
+    sub = [0, B - 1]
+    want = oracle.crd_score(bank[:, 0].contiguous().numpy(), bank[:, 1].contiguous().numpy(), v1[sub].cpu().numpy(), v2[sub].cpu().numpy(),
+                            cidx[sub].numpy(), N, T, Z1, Z2)
+    scale = B / len(sub)
+    assert _rel(b[1][sub].cpu().numpy(), want["grad_v1"] / scale) < REL32 and _rel(b[2][sub].cpu().numpy(), want["grad_v2"] / scale) < REL32
+    # negatives drawn on the GPU (no list in memory): the pre-pass draws them itself, the same ones as the gather step
+    opt = type("Opt", (), dict(s_dim=64, t_dim=48, feat_dim=D, n_data=N, nce_k=K, nce_t=T, nce_m=0.5))()
+    losses = []
+    for sweep in (False, True):
+        torch.manual_seed(4)
+        crit = pkg.CRDLoss(opt, seed=9).to(cuda)
+        crit.contrast.sweep = sweep
+        f_s = torch.randn(B, 64, generator=torch.Generator().manual_seed(1)).to(cuda).requires_grad_(True)
+        f_t = torch.randn(B, 48, generator=torch.Generator().manual_seed(2)).to(cuda)
+        for _ in range(2):
+            loss = crit(f_s, f_t, y)
+        loss.backward()
+        losses.append((loss.item(), f_s.grad.clone(), crit.contrast.memory_v1[y].clone()))
+    assert abs(losses[0][0] - losses[1][0]) <= 1e-6 * abs(losses[0][0])
+    assert _rel(losses[1][1].cpu().numpy(), losses[0][1].cpu().numpy()) < 1e-5 and torch.equal(losses[0][2], losses[1][2])
