@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
   constexpr int R = 32 / LPR;
   constexpr int NV = VEC * CH;
   constexpr unsigned kFull = 0xffffffffu;
+  constexpr bool kFast = FULL && LPR == 16 && U == 4 && R == 2;   // transposed score reduction in consume()
   static_assert(R * U + 64 <= kQueueCap, "queue too small");
 
   __shared__ int2 queue_smem[kWarps][kQueueCap];
@@ -486,6 +487,71 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
           }
         }
       }
+      if constexpr (kFast) {
+        // ---- 16 lanes per row, U = 4: the 8 partial dot products of a lane (4 rows x 2 directions) are reduced over the
+        // row's 16 lanes by a TRANSPOSING butterfly (8 shuffles instead of 32: every step halves the number of values a lane
+        // carries), which leaves value v = (lane >> 1) & 7 = (row step u, direction d) on lane pair (2v, 2v + 1) of the row
+        // group.  exp / rcp / log then run ONCE per consume step on that one value per lane (they ran four times on two
+        // values each, identically on all 16 lanes), and the eight gradient coefficients come back by 8 indexed shuffles.
+        unsigned long long w1p[U][NV / 2], w2p[U][NV / 2];
+        float x[2 * U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float w1f[NV], w2f[NV];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            Unpack<T>::run(w1r[u][i], &w1f[i * VEC]);
+            Unpack<T>::run(w2r[u][i], &w2f[i * VEC]);
+          }
+          unsigned long long A1 = 0ull, A2 = 0ull;
+#pragma unroll
+          for (int n = 0; n < NV / 2; ++n) {
+            w1p[u][n] = pack2(w1f[2 * n], w1f[2 * n + 1]);
+            w2p[u][n] = pack2(w2f[2 * n], w2f[2 * n + 1]);
+            ffma2(A1, w2p[u][n], v1p[n]);  // out_v1 direction: bank2 row . v1
+            ffma2(A2, w1p[u][n], v2p[n]);  // out_v2 direction: bank1 row . v2
+          }
+          x[2 * u] = lo2(A1) + hi2(A1);
+          x[2 * u + 1] = lo2(A2) + hi2(A2);
+        }
+        const bool hb = (lane & 8) != 0, mb = (lane & 4) != 0, lb = (lane & 2) != 0;
+        float y4[4], z2[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y4[k] = (hb ? x[4 + k] : x[k]) + __shfl_xor_sync(kFull, hb ? x[k] : x[4 + k], 8);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) z2[k] = (mb ? y4[2 + k] : y4[k]) + __shfl_xor_sync(kFull, mb ? y4[k] : y4[2 + k], 4);
+        float tot = (lb ? z2[1] : z2[0]) + __shfl_xor_sync(kFull, lb ? z2[0] : z2[1], 2);
+        tot += __shfl_xor_sync(kFull, tot, 1);
+        // this lane's value: row step mu, direction md (0: bank-2 row . v1 -> Z1, 1: bank-1 row . v2 -> Z2)
+        const int mu = (lane >> 2) & 3, md = (lane >> 1) & 1, mq = mu * R + g;
+        const bool mvalid = mq < avail;
+        const int2 ment = q[(qhead + mq) & (kQueueCap - 1)];
+        const float e = ex2_approx(tot * p.k_exp);
+        const float m = mvalid ? 1.f : 0.f;
+        const float o = e * (md ? p.inv_Z2 : p.inv_Z1);
+        const float rc = rcp_approx(o + p.c);
+        const bool is_pos = (ment.y == pos_off);
+        const float coef = (is_pos ? -p.c : o) * rc * (p.inv_BT * m);
+        float t;
+        if (is_pos) t = logf(__fdiv_rn(o, o + p.c));
+        else t = -log1p_pos(fmaf(o, p.inv_mPn, p.eps_over_mPn));
+        if ((lane & 1) == 0) {   // one lane of the pair accounts for the value
+          const float tm = t * m, em = e * m;
+          if (md == 0) { ls += tm; se1 += em; cnt += m; } else { lt += tm; se2 += em; }
+          if (store_out && mvalid) (md ? p.out_v2 : p.out_v1)[lo + ment.y] = o;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float d1 = __shfl_sync(kFull, coef, (4 * u) | (lane & 16));
+          const float d2 = __shfl_sync(kFull, coef, (4 * u + 2) | (lane & 16));
+          const unsigned long long d1p = pack2(d1, d1), d2p = pack2(d2, d2);
+#pragma unroll
+          for (int n = 0; n < NV / 2; ++n) {
+            ffma2(g1p[n], d1p, w2p[u][n]);
+            ffma2(g2p[n], d2p, w1p[u][n]);
+          }
+        }
+      } else {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         float w1f[NV], w2f[NV];
@@ -548,6 +614,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
           }
         }
       }
+          }
     };
 
     auto fetch_idx = [&](long long pos) -> long long { return contrast_entry(p, pos, b, anchor_base); };
@@ -670,6 +737,16 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
       se1 += __shfl_xor_sync(kFull, se1, off);
       se2 += __shfl_xor_sync(kFull, se2, off);
       cnt += __shfl_xor_sync(kFull, cnt, off);
+    }
+    if constexpr (kFast) {   // the scalar sums are spread over the lanes of a row group (one value per lane pair)
+#pragma unroll
+      for (int off = LPR / 2; off >= 1; off >>= 1) {
+        ls += __shfl_xor_sync(kFull, ls, off);
+        lt += __shfl_xor_sync(kFull, lt, off);
+        se1 += __shfl_xor_sync(kFull, se1, off);
+        se2 += __shfl_xor_sync(kFull, se2, off);
+        cnt += __shfl_xor_sync(kFull, cnt, off);
+      }
     }
     float* slot = cta_red ? red_smem + (warp * 2 + (b - b_first_cta)) * kSW
                 : banded ? p.slots + (long long)gw * (2 * p.D + kSlotExtra)

@@ -36,7 +36,7 @@ def timed(step):
 
 # ---- one GPU, whole bank
 res = {}
-for name, variant in [('gather', 0), ('swept', 0x400)] + [(f'swept_v{v}', 0x400 | v) for v in (2, 3, 5, 6, 7)]:
+for name, variant in [('gather', 0), ('swept', 0x400)]:
     mem = pkg.ContrastMemory(c['D'], c['N'], c['K'], c['T'], c['m']).to(dev)
     with torch.no_grad():
         mem.memory_v1.copy_(bank[:, 0]); mem.memory_v2.copy_(bank[:, 1]); mem.params[2], mem.params[3] = 2.0e6, 2.0e6
@@ -55,7 +55,7 @@ out['1gpu_agreement'] = {'loss_rel': abs((a[0][5] - b[0][5]).item()) / abs(a[0][
 # ---- one rank's share at R shards
 for R in (2, 4, 8):
     rows = c['N'] // R
-    for name, variant in (('compact', 0x40), ('swept', 0x400), ('swept_v5', 0x405)):
+    for name, variant in (('scan', 0x20), ('compact', 0x40), ('swept', 0x400)):
         m = pkg.ShardedContrastMemory(c['D'], c['N'], c['K'], rank=0, world_size=1, comm='p2p', seed=5).to(dev)
         m.row_begin, m.row_end = 0, rows
         m.memory_v1 = bank[:rows, 0].contiguous().to(dev); m.memory_v2 = bank[:rows, 1].contiguous().to(dev)
@@ -69,4 +69,5 @@ for R in (2, 4, 8):
         out[key] = timed(lambda: m.step_resident(v1, v2, y, cidx, o))
         del m; torch.cuda.empty_cache()
     out[f'R{R}_agreement'] = rel(res[f'R{R}_swept'][:2 * 46 * 128], res[f'R{R}_compact'][:2 * 46 * 128])
+    mem_probe = None
 print(json.dumps(out, indent=1))
