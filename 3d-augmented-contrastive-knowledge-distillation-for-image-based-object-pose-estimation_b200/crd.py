@@ -542,10 +542,10 @@ class ContrastMemory(nn.Module):
 
     def _with_sweep(self, variant, B, K1, D):
         """Adds the SWEEP bit to a gather-kernel variant when the band-sorted formulation pays: the step draws each resident
-        row more than ~1.5 times and the shard is larger than 1.5x the 126 MB L2 (otherwise the repeats are L2 hits already and
-        the pre-pass costs more than it saves: an 8-way shard of the headline bank, config 0).  Measured at the headline shape:
-        DRAM traffic 2.91 -> 1.02 GB, scoring kernel 0.433 -> 0.296 ms, ~12 us of pre-pass; 2-way / 4-way shards 0.230 -> 0.180 /
-        0.122 -> 0.117 ms per step (profiles/r2_sweep_ab.py).  ``self.sweep`` forces it on / off."""
+        row more than ~1.5 times and the shard is about as large as the 126 MB L2 or larger (a bank well inside the L2 -- config 0,
+        92 MB -- has its repeats as L2 hits already and the pre-pass only costs).  Measured at the headline shape:
+        DRAM traffic 2.91 -> 1.02 GB, scoring kernel 0.433 -> 0.296 ms, ~12 us of pre-pass; 2-way / 4-way / 8-way shards 0.227 -> 0.179 /
+        0.122 -> 0.110 / 0.079 -> 0.076 ms per step (profiles/r2_sweep_ab.py).  ``self.sweep`` forces it on / off."""
         if variant & (self.SWEEP | 0x20 | 0x40 | 0x100):
             return variant
         if self.sweep is False:
@@ -554,7 +554,7 @@ class ContrastMemory(nn.Module):
             rows = self.row_end - self.row_begin
             esz = 2 if self._buffers["memory_v1"].dtype == torch.bfloat16 else 4
             hits = B * K1 if self.k_total > 0 else B * K1 * rows // max(self.nLem, 1)
-            if not (rows * 2 * D * esz >= (192 << 20) and 2 * hits >= 3 * rows and B * K1 >= (1 << 20)):
+            if not (rows * 2 * D * esz >= (120 << 20) and 2 * hits >= 3 * rows and B * K1 >= (1 << 20)):
                 return variant
         return variant | self.SWEEP
 

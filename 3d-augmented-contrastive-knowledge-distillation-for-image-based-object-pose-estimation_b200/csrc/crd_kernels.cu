@@ -248,14 +248,19 @@ __device__ __forceinline__ int band_of(const ScoreParams& p, int row) {
   const int b = (int)(((unsigned long long)(unsigned)row * (unsigned long long)p.band_mul) >> 32);
   return b < kBands - 1 ? b : kBands - 1;
 }
-__global__ void __launch_bounds__(256, 5) crd_band_sort_kernel(const ScoreParams p, int* __restrict__ cl, int* __restrict__ ucount) {
-  constexpr int EPT = kFilterEPT, NCNT = kBands * EPT * 8;   // counts: [band][slice of 256 entries][warp]
-  __shared__ int s_cnt[NCNT];
+// SPARSE (a shard that owns a fraction of the rows): the survivors are first compacted in list order into shared memory
+// (the filter kernel's ballots + prefix), and only ceil(survivors / 256) slices go through the sort -- 2 of 16 on an 8-way shard.
+template <bool SPARSE>
+__global__ void __launch_bounds__(256, SPARSE ? 4 : 5) crd_band_sort_kernel(const ScoreParams p, int* __restrict__ cl, int* __restrict__ ucount) {
+  constexpr int EPT = kFilterEPT;
+  __shared__ int s_cnt[kBands * EPT * 8];   // counts: [band][slice of 256 entries < NS][warp]
   __shared__ int s_wsum[8];
+  __shared__ int s_surv[SPARSE ? kFilterChunk : 1];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / p.NC, c = blockIdx.x - b * p.NC;
   const long long anchor_base = (long long)b * p.K1;
   const int k0 = 1 + c * kFilterChunk;
+  const unsigned below = (1u << lane) - 1u;
   int row[EPT];
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
@@ -264,22 +269,59 @@ __global__ void __launch_bounds__(256, 5) crd_band_sort_kernel(const ScoreParams
     if (k < p.K1) r = contrast_entry(p, anchor_base + k, b, anchor_base);
     row[j] = (r >= p.row_begin && r < p.row_end) ? (int)(r - p.row_begin) : -1;
   }
-  for (int i = tid; i < NCNT; i += 256) s_cnt[i] = 0;
+  int NS = EPT;   // slices that take part in the sort (CTA-uniform)
+  if constexpr (SPARSE) {
+    // ---- survivors, compacted in list order (crd_shard_filter_kernel's scheme), then re-dealt 256 per slice
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, row[j] >= 0);
+      if (lane == 0) s_cnt[j * 8 + warp] = __popc(m);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      constexpr int CPL = EPT * 8 / 32;
+      int cv[CPL], tot = 0;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) { cv[i] = s_cnt[lane * CPL + i]; tot += cv[i]; }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int run = inc - tot;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) { s_cnt[EPT * 8 + lane * CPL + i] = run; run += cv[i]; }
+      if (lane == 31) s_wsum[0] = inc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, row[j] >= 0);
+      if (row[j] >= 0) s_surv[s_cnt[EPT * 8 + j * 8 + warp] + __popc(m & below)] = row[j];
+    }
+    __syncthreads();
+    const int ns = s_wsum[0];
+    NS = (ns + 255) >> 8;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) row[j] = (j < NS && j * 256 + tid < ns) ? s_surv[j * 256 + tid] : -1;
+    __syncthreads();   // s_cnt / s_wsum are reused below
+  }
+  for (int i = tid; i < kBands * NS * 8; i += 256) s_cnt[i] = 0;
   __syncthreads();
-  const unsigned below = (1u << lane) - 1u;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
+    if (j >= NS) break;
     const bool valid = row[j] >= 0;
     const int bin = valid ? band_of(p, row[j]) : 0;
     const unsigned m = same_bin_mask(bin, valid);
-    if (valid && (m & below) == 0u) s_cnt[(bin * EPT + j) * 8 + warp] = __popc(m);   // the group's first lane
+    if (valid && (m & below) == 0u) s_cnt[(bin * NS + j) * 8 + warp] = __popc(m);   // the group's first lane
   }
   __syncthreads();
-  {   // exclusive prefix over the NCNT counts in (band, slice, warp) order: 16 consecutive counts per thread
-    constexpr int PER = NCNT / 256;
-    int cv[PER], tot = 0;
+  {   // exclusive prefix over the 256 * NS counts in (band, slice, warp) order: NS consecutive counts per thread
+    int cv[EPT], tot = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { cv[i] = s_cnt[tid * PER + i]; tot += cv[i]; }
+    for (int i = 0; i < EPT; ++i) { cv[i] = i < NS ? s_cnt[tid * NS + i] : 0; tot += cv[i]; }
     int inc = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -292,17 +334,21 @@ __global__ void __launch_bounds__(256, 5) crd_band_sort_kernel(const ScoreParams
 #pragma unroll
     for (int w = 0; w < 8; ++w) run += (w < warp) ? s_wsum[w] : 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { s_cnt[tid * PER + i] = run; run += cv[i]; }
+    for (int i = 0; i < EPT; ++i) {
+      if (i < NS) s_cnt[tid * NS + i] = run;
+      run += cv[i];
+    }
     if (tid == 255) ucount[blockIdx.x] = run;
   }
   __syncthreads();
   int* dst = cl + (size_t)blockIdx.x * kFilterChunk;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
+    if (j >= NS) break;
     const bool valid = row[j] >= 0;
     const int bin = valid ? band_of(p, row[j]) : 0;
     const unsigned m = same_bin_mask(bin, valid);
-    if (valid) dst[s_cnt[(bin * EPT + j) * 8 + warp] + __popc(m & below)] = row[j];
+    if (valid) dst[s_cnt[(bin * NS + j) * 8 + warp] + __popc(m & below)] = row[j];
   }
 }
 
@@ -1373,7 +1419,8 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   if (compact || banded) {   // pre-pass: drop the entries other shards own, keep list order / sort by band (compact == 2, 4: the caller has launched it)
     if (sp.idx_mode != 2) sp.y = (const long long*)src->y;
     if (src->compact != 2 && src->compact != 4) {
-      if (banded) crd_band_sort_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
+      if (banded && (row_end - row_begin) * 2 <= n_data) crd_band_sort_kernel<true><<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
+      else if (banded) crd_band_sort_kernel<false><<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
       else crd_shard_filter_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
       CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
     }
@@ -1734,7 +1781,8 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
       fpar.band_mul = sweep ? (unsigned)((((unsigned long long)kBands) << 32) / (unsigned long long)(row_end - row_begin)) + 1u : 0u;
       CRDPN_CUDA(cudaEventRecord(side->fork, st));
       CRDPN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
-      if (sweep) crd_band_sort_kernel<<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
+      if (sweep && (row_end - row_begin) * 2 <= n_data) crd_band_sort_kernel<true><<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
+      else if (sweep) crd_band_sort_kernel<false><<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
       else crd_shard_filter_kernel<<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
       CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
       CRDPN_CUDA(cudaEventRecord(side->join, side->s));
