@@ -546,7 +546,7 @@ class ContrastMemory(nn.Module):
         92 MB -- has its repeats as L2 hits already and the pre-pass only costs).  Measured at the headline shape:
         DRAM traffic 2.91 -> 1.02 GB, scoring kernel 0.433 -> 0.296 ms, ~12 us of pre-pass; 2-way / 4-way / 8-way shards 0.227 -> 0.179 /
         0.122 -> 0.110 / 0.079 -> 0.076 ms per step (profiles/r2_sweep_ab.py).  ``self.sweep`` forces it on / off."""
-        if variant & (self.SWEEP | 0x20 | 0x40 | 0x100):
+        if variant & (self.SWEEP | 0x40 | 0x100):
             return variant
         if self.sweep is False:
             return variant

@@ -1256,6 +1256,7 @@ struct IdxSource {
   int64_t draw_n, draw_base;
   int compact;              // 1: run crd_shard_filter_kernel first and score the compact lists (y must be set); 2: the caller has
                             // launched it; 3 / 4: the same with band-sorted lists (crd_band_sort_kernel, ScoreParams::compact == 3)
+  int all_in_shard;         // hint: every entry lives in this shard (in-shard negatives): the band sort skips its survivor compaction
 };
 
 // compact lists of the row-sharded step inside the workspace (behind the slots)
@@ -1419,7 +1420,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   if (compact || banded) {   // pre-pass: drop the entries other shards own, keep list order / sort by band (compact == 2, 4: the caller has launched it)
     if (sp.idx_mode != 2) sp.y = (const long long*)src->y;
     if (src->compact != 2 && src->compact != 4) {
-      if (banded && (row_end - row_begin) * 2 <= n_data) crd_band_sort_kernel<true><<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
+      if (banded && !src->all_in_shard && (row_end - row_begin) * 2 <= n_data) crd_band_sort_kernel<true><<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
       else if (banded) crd_band_sort_kernel<false><<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
       else crd_shard_filter_kernel<<<(int)(B * NC), 256, 0, st>>>(sp, cl, ucount);
       CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
@@ -1756,8 +1757,11 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
   // scoring pass 76 -> 67 us at 1/8 of the rows, nothing at 1/2); variant bit 6 forces it on (single-GPU tests), bit 5 off
   const bool gather = v1_local != nullptr;
   bool prefiltered = false;
-  const bool want_compact = !(variant & 0x200) && !(variant & 0x20) &&
-                            ((variant & 0x40) || (variant & 0x400) || (row_end - row_begin) * 3 <= n_data);
+  // bit 0x20: every entry of the list lives in this shard (in-shard negatives) -- no filter pre-pass; together with 0x400 it
+  // still means band-sorted lists, sorted without the survivor compaction
+  const bool all_in = (variant & 0x20) != 0 || (idx_mode == 2 && draw_base >= row_begin && draw_base + draw_n <= row_end);
+  const bool want_compact = !(variant & 0x200) &&
+                            ((variant & 0x400) || (!(variant & 0x20) && ((variant & 0x40) || (row_end - row_begin) * 3 <= n_data)));
   bool sweep = false;   // band-sorted lists (variant | 0x400)
   cudaStream_t st = (cudaStream_t)stream;
   SideStream* side = nullptr;
@@ -1781,7 +1785,7 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
       fpar.band_mul = sweep ? (unsigned)((((unsigned long long)kBands) << 32) / (unsigned long long)(row_end - row_begin)) + 1u : 0u;
       CRDPN_CUDA(cudaEventRecord(side->fork, st));
       CRDPN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
-      if (sweep && (row_end - row_begin) * 2 <= n_data) crd_band_sort_kernel<true><<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
+      if (sweep && !all_in && (row_end - row_begin) * 2 <= n_data) crd_band_sort_kernel<true><<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
       else if (sweep) crd_band_sort_kernel<false><<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
       else crd_shard_filter_kernel<<<(int)(B * cp.NC), 256, 0, side->s>>>(fpar, cp.cl, cp.ucount);
       CRDPN_LAUNCH_CHECK("crd_shard_filter_kernel");
@@ -1816,7 +1820,7 @@ int crdpn::sharded_step_core(void* bank1, void* bank2, int64_t row_stride, int b
   x.timeout = p2p::poll_timeout_ticks();
   // an empty shard still takes part in the exchange: score_impl launches the reduction kernel either way
   const IdxSource src{idx_mode, (const int*)contrast_idx, y_all, seed, offset, draw_n, draw_base,
-                      prefiltered ? (sweep ? 4 : 2) : (want_compact ? ((variant & 0x400) ? 3 : 1) : 0)};
+                      prefiltered ? (sweep ? 4 : 2) : (want_compact ? ((variant & 0x400) ? 3 : 1) : 0), all_in ? 1 : 0};
   return score_impl(bank1, bank2, row_stride, bank_dtype, v1_all, v2_all, idx_mode == 0 ? contrast_idx : nullptr, B, K1, D,
                     n_data, k_total, row_begin, row_end, T, Z1, Z2, eps, nullptr, nullptr, result, partial, partial + B * D,
                     workspace, workspace_bytes, variant & 0xf9f, &u, stream, &x, &src);

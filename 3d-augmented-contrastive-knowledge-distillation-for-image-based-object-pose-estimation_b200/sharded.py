@@ -262,8 +262,8 @@ class ShardedContrastMemory(ContrastMemory):
 
     def _step_variant(self, B, K1, D):
         v = super()._step_variant(B, K1, D)
-        if self.local_negatives and not (v & self.STREAM) and not (self.variant & 0x40) and not (v & self.SWEEP):
-            v |= self.NO_COMPACT   # in-shard negatives: nothing to filter out, the pre-pass would only cost its 13 us
+        if self.local_negatives and not (v & self.STREAM) and not (self.variant & 0x40):
+            v |= self.NO_COMPACT   # in-shard negatives: nothing to filter out (with SWEEP: band sort without survivor compaction)
         return v
 
     def _gather(self, v1, v2, y):
