@@ -20,6 +20,7 @@
 // anchor by anchor; per anchor it scans 32 contrast indices at a time, drops entries that fall outside
 // this rank's bank shard, compacts the survivors into a per-warp shared-memory queue and consumes the
 // queue R rows x U steps at a time with all 2*CH*U 128-bit loads of a step group issued before first use.
+#include <stdlib.h>
 #include <string.h>
 #include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
 #include "common.cuh"
@@ -72,6 +73,8 @@ struct ScoreParams {
   // k in [1 + (c-1) kFilterChunk, ...) in list order: local rows cl[(b NC + c-1) kFilterChunk ...], ucount[b NC + c-1] of them.
   // The warps cut the COMPACT space into equal ranges (exactly balanced, no scan), warp w writes slot w + b for anchor b.
   int compact;              // 0 off, 1 compact lists in list order, 3 band-sorted lists + interleaved blocks (see crd_band_sort_kernel)
+  int prefetch;             // 1: consume() prefetches the next step's rows into the L2 (CRDPN_SCORE_PREFETCH=1; measured: -4..7 % on
+                            // compact shards, +3 % on the band-sorted step whose rows are L2 hits already: off by default)
   int wpu;                  // compact == 3: warps per (anchor, chunk) unit
   unsigned band_mul;        // compact == 3: band of local row r = min(31, (r * band_mul) >> 32)
   int NC;
@@ -530,6 +533,23 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
           } else {
             w1r[u][i] = make_uint4(0u, 0u, 0u, 0u);
             w2r[u][i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+      if constexpr (kFast && sizeof(T) == 4 && kD == 128) {
+        // the NEXT consume step's rows (queued already) are pulled into the L2 while this step's loads are in flight: the
+        // kernel is bound by load latency at 16 warps per SM, and a prefetch holds no registers.  8 rows x (512 B of bank 1 +
+        // 512 B of bank 2) = 64 lines of 128 B, two per lane
+        if (p.prefetch != 0) {
+          const int ln = lane & 7;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int eidx = R * U + (lane >> 3) + 4 * h;
+            if (qhead + eidx < qtail) {
+              const int prow = q[(qhead + eidx) & (kQueueCap - 1)].x;
+              const char* pa = (ln < 4 ? p.bank1 : p.bank2) + (long long)prow * p.row_stride_bytes + (long long)(ln & 3) * 128;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+            }
           }
         }
       }
@@ -1405,6 +1425,10 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.ticket = ticket;
   sp.nw = NW;
   sp.cta_reduce = cta_reduce ? 1 : 0;
+  {
+    static const int prefetch_on = [] { const char* e = getenv("CRDPN_SCORE_PREFETCH"); return (e && e[0] == '1') ? 1 : 0; }();
+    sp.prefetch = prefetch_on;
+  }
   sp.compact = banded ? 3 : compact ? 1 : 0;
   sp.wpu = (int)wpu;
   sp.band_mul = banded ? (unsigned)((((unsigned long long)kBands) << 32) / (unsigned long long)(row_end - row_begin)) + 1u : 0u;
