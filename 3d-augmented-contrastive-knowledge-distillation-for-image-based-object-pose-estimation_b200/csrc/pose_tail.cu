@@ -22,6 +22,7 @@
 //     in flight while layer l finishes.  One launch for cat + DeformNet + six heads + projector.
 // Train mode (batch-statistics BatchNorm, training.py:30): the reduce step also has every batch row of its channels in
 // hand, so mean / variance over the batch, the running-statistics update and the saved (mean, 1/std) cost no extra pass.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -655,7 +656,16 @@ extern "C" int crdpn_pose_tail_forward(const crdpn_pose_tail_layer* layers, int 
   p.train = train ? 1 : 0;
   p.bn_momentum = bn_momentum;
   p.bn_eps = bn_eps;
-  p.timeout = 4000000000ll;
+  {
+    // how long a CTA may wait for another CTA's counter before it gives up (clock ticks; ~2 GHz).  Generous by default: the
+    // kernel is launched cooperatively, so every CTA is resident and a wait only ever lasts microseconds
+    static const long long ticks = [] {
+      const char* e = getenv("CRDPN_POSE_TAIL_TIMEOUT_S");
+      const double sec = e ? atof(e) : 30.0;
+      return (long long)((sec > 0.01 ? sec : 0.01) * 2.0e9);
+    }();
+    p.timeout = ticks;
+  }
   p.dbg = (flags & CRDPN_POSE_TAIL_PROF) ? reinterpret_cast<unsigned long long*>(ws + pt::kCtrBytes) : nullptr;
   p.in[0] = pt::Input{shape_feature, img_feature, ws + pl.off_in[0], (int)shape_dim, (int)img_dim, pl.in_kb[0]};
   p.in[1] = pt::Input{img_feature, nullptr, ws + pl.off_in[1], (int)img_dim, 0, pl.in_kb[1]};
@@ -689,7 +699,10 @@ extern "C" int crdpn_pose_tail_forward(const crdpn_pose_tail_layer* layers, int 
     CRDPN_CUDA(cudaFuncSetAttribute(pt::pose_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
     attr_set[dev & 63] = true;
   }
-  pt::pose_tail_kernel<<<di.sms, pt::kPtThreads, pl.smem, st>>>(p);
+  // cooperative launch: the CTAs wait for each other on device-side counters, so all of them have to be resident -- the
+  // runtime guarantees it (or refuses the launch) instead of this code assuming an idle GPU
+  void* kargs[] = {(void*)&p};
+  CRDPN_CUDA(cudaLaunchCooperativeKernel((const void*)pt::pose_tail_kernel, dim3(di.sms), dim3(pt::kPtThreads), kargs, pl.smem, st));
   CRDPN_LAUNCH_CHECK("pose_tail_kernel");
   return CRDPN_OK;
 }
