@@ -75,7 +75,7 @@ struct ScoreParams {
   int compact;              // 0 off, 1 compact lists in list order, 3 band-sorted lists + interleaved blocks (see crd_band_sort_kernel)
   int prefetch;             // 1: consume() prefetches the next step's rows into the L2 (CRDPN_SCORE_PREFETCH=1; measured: -4..7 % on
                             // compact shards, +3 % on the band-sorted step whose rows are L2 hits already: off by default)
-  int wpu;                  // compact == 3: warps per (anchor, chunk) unit
+  int wpu;                  // compact == 3: warps per anchor
   unsigned band_mul;        // compact == 3: band of local row r = min(31, (r * band_mul) >> 32)
   int NC;
   const int* cl;
@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
   constexpr int R = 32 / LPR;
   constexpr int NV = VEC * CH;
   constexpr unsigned kFull = 0xffffffffu;
-  constexpr bool kFast = FULL && LPR == 16 && U == 4 && R == 2;   // transposed score reduction in consume()
+  constexpr bool kFast = FULL && (LPR == 16 || LPR == 32) && U == 4;   // transposed score reduction in consume()
+  constexpr int kDupShift = (LPR == 32) ? 2 : 1;                       // ... lanes sharing one reduced value: 1 << kDupShift
   static_assert(R * U + 64 <= kQueueCap, "queue too small");
 
   __shared__ int2 queue_smem[kWarps][kQueueCap];
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
   // ---- compact mode: exclusive prefix of the unit counts (shared memory), then equal ranges of the COMPACT space ----
   __shared__ int s_wsum[kWarps];
   const bool compact = p.compact == 1;
-  const bool banded = p.compact == 3;   // band-sorted lists, warp gw = (unit gw / wpu, interleave slot gw % wpu)
+  const bool banded = p.compact == 3;   // band-sorted lists, warp gw = (anchor gw / wpu, interleave slot gw % wpu)
   const int UPA = p.NC + 1;                 // units per anchor: the positive, then NC filtered chunks
   int cu = 0;                               // current unit
   if (compact) {   // (cta_reduce is off in this mode, so every thread is still here)
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
   while (lo < hi) {
     if (compact)
       while ((long long)s_upre[cu + 1] <= lo) ++cu;
-    const int b = banded ? (int)(gw / p.wpu) / p.NC : compact ? cu / UPA : (int)(lo / p.K1);
+    const int b = banded ? (int)(gw / p.wpu) : compact ? cu / UPA : (int)(lo / p.K1);
     const long long anchor_base = (long long)b * p.K1;
     const long long seg_hi = banded ? 1
                            : compact ? ((hi < (long long)s_upre[(b + 1) * UPA]) ? hi : (long long)s_upre[(b + 1) * UPA])
@@ -554,11 +555,12 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
         }
       }
       if constexpr (kFast) {
-        // ---- 16 lanes per row, U = 4: the 8 partial dot products of a lane (4 rows x 2 directions) are reduced over the
-        // row's 16 lanes by a TRANSPOSING butterfly (8 shuffles instead of 32: every step halves the number of values a lane
-        // carries), which leaves value v = (lane >> 1) & 7 = (row step u, direction d) on lane pair (2v, 2v + 1) of the row
-        // group.  exp / rcp / log then run ONCE per consume step on that one value per lane (they ran four times on two
-        // values each, identically on all 16 lanes), and the eight gradient coefficients come back by 8 indexed shuffles.
+        // ---- 16 (or 32) lanes per row, U = 4: the 8 partial dot products of a lane (4 rows x 2 directions) are reduced over
+        // the row's lanes by a TRANSPOSING butterfly (8 shuffles instead of 32: every step halves the number of values a lane
+        // carries), which leaves value v = (lane >> kDupShift) & 7 = (row step u, direction d) on a group of 2 (4) neighbouring
+        // lanes of the row group.  exp / rcp / log then run ONCE per consume step on that one value per lane (they ran four times
+        // on two values each, identically on all lanes of the row), and the eight gradient coefficients come back by 8 indexed
+        // shuffles.
         unsigned long long w1p[U][NV / 2], w2p[U][NV / 2];
         float x[2 * U];
 #pragma unroll
@@ -580,16 +582,19 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
           x[2 * u] = lo2(A1) + hi2(A1);
           x[2 * u + 1] = lo2(A2) + hi2(A2);
         }
-        const bool hb = (lane & 8) != 0, mb = (lane & 4) != 0, lb = (lane & 2) != 0;
+        constexpr int o1 = LPR / 2, o2 = LPR / 4, o3 = LPR / 8;   // the three halving steps; the remaining ones add duplicates
+        const bool hb = (lane & o1) != 0, mb = (lane & o2) != 0, lb = (lane & o3) != 0;
         float y4[4], z2[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y4[k] = (hb ? x[4 + k] : x[k]) + __shfl_xor_sync(kFull, hb ? x[k] : x[4 + k], 8);
+        for (int k = 0; k < 4; ++k) y4[k] = (hb ? x[4 + k] : x[k]) + __shfl_xor_sync(kFull, hb ? x[k] : x[4 + k], o1);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) z2[k] = (mb ? y4[2 + k] : y4[k]) + __shfl_xor_sync(kFull, mb ? y4[k] : y4[2 + k], 4);
-        float tot = (lb ? z2[1] : z2[0]) + __shfl_xor_sync(kFull, lb ? z2[0] : z2[1], 2);
-        tot += __shfl_xor_sync(kFull, tot, 1);
+        for (int k = 0; k < 2; ++k) z2[k] = (mb ? y4[2 + k] : y4[k]) + __shfl_xor_sync(kFull, mb ? y4[k] : y4[2 + k], o2);
+        float tot = (lb ? z2[1] : z2[0]) + __shfl_xor_sync(kFull, lb ? z2[0] : z2[1], o3);
+#pragma unroll
+        for (int off = o3 / 2; off >= 1; off >>= 1) tot += __shfl_xor_sync(kFull, tot, off);
         // this lane's value: row step mu, direction md (0: bank-2 row . v1 -> Z1, 1: bank-1 row . v2 -> Z2)
-        const int mu = (lane >> 2) & 3, md = (lane >> 1) & 1, mq = mu * R + g;
+        const int vmine = (lane >> kDupShift) & 7;
+        const int mu = vmine >> 1, md = vmine & 1, mq = mu * R + g;
         const bool mvalid = mq < avail;
         const int2 ment = q[(qhead + mq) & (kQueueCap - 1)];
         const float e = ex2_approx(tot * p.k_exp);
@@ -601,15 +606,15 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
         float t;
         if (is_pos) t = logf(__fdiv_rn(o, o + p.c));
         else t = -log1p_pos(fmaf(o, p.inv_mPn, p.eps_over_mPn));
-        if ((lane & 1) == 0) {   // one lane of the pair accounts for the value
+        if ((lane & ((1 << kDupShift) - 1)) == 0) {   // one lane of the group that shares the value accounts for it
           const float tm = t * m, em = e * m;
           if (md == 0) { ls += tm; se1 += em; cnt += m; } else { lt += tm; se2 += em; }
           if (store_out && mvalid) (md ? p.out_v2 : p.out_v1)[lo + ment.y] = o;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const float d1 = __shfl_sync(kFull, coef, (4 * u) | (lane & 16));
-          const float d2 = __shfl_sync(kFull, coef, (4 * u + 2) | (lane & 16));
+          const float d1 = __shfl_sync(kFull, coef, ((2 * u) << kDupShift) | (lane & ~(LPR - 1) & 31));
+          const float d2 = __shfl_sync(kFull, coef, ((2 * u + 1) << kDupShift) | (lane & ~(LPR - 1) & 31));
           const unsigned long long d1p = pack2(d1, d1), d2p = pack2(d2, d2);
 #pragma unroll
           for (int n = 0; n < NV / 2; ++n) {
@@ -685,25 +690,37 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
 
     auto fetch_idx = [&](long long pos) -> long long { return contrast_entry(p, pos, b, anchor_base); };
     if (banded) {
-      const int unit = (int)(gw / p.wpu), t = (int)(gw - (long long)unit * p.wpu), c = unit - b * p.NC;
-      const int n = p.ucount[unit];
-      const int* src = p.cl + (size_t)unit * kFilterChunk;
-      if (c == 0 && t == 0) {   // the anchor's positive (k = 0) rides with the first warp of its first unit
+      // warp i of the anchor's wpu warps takes blocks g = i, i + wpu, ... of the sequence g = blk * NC + c (32-entry block blk of
+      // unit c): every unit list is band-sorted, so the sequence sweeps the bank once, and the anchor's entries are spread
+      // over its warps to within one block whatever NC and the unit lengths are
+      const int i = (int)(gw - (long long)b * p.wpu);
+      const int ncnt = lane < p.NC ? p.ucount[b * p.NC + lane] : 0;   // (NC <= 32: one unit length per lane)
+      int nmax = ncnt;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, off));
+      const int G = ((nmax + 31) >> 5) * p.NC;
+      const int* src = p.cl + (size_t)b * p.NC * kFilterChunk;
+      if (i == 0) {   // the anchor's positive (k = 0) rides with its first warp
         const long long r = contrast_entry(p, anchor_base, b, anchor_base);
         if (r >= p.row_begin && r < p.row_end) {
           if (lane == 0) q[qtail & (kQueueCap - 1)] = make_int2((int)(r - p.row_begin), 0);
           qtail += 1;
         }
       }
-      // blocks t, t + wpu, ... of the band-sorted list, 32 entries each; the next block's indices are loaded before this
-      // block's rows are consumed
-      int i = t * 32;
-      int nxt = (i + lane < n) ? src[i + lane] : 0;
+      auto fetch_block = [&](int gg, int& cnt_blk) -> int {
+        if (gg >= G) { cnt_blk = 0; return 0; }
+        const int blk = gg / p.NC, c = gg - blk * p.NC;
+        const int n = __shfl_sync(kFull, ncnt, c), off = blk * 32;
+        cnt_blk = n - off < 0 ? 0 : (n - off < 32 ? n - off : 32);
+        return lane < cnt_blk ? src[(size_t)c * kFilterChunk + off + lane] : 0;
+      };
+      int g2 = i, cnt_nxt;
+      int nxt = fetch_block(g2, cnt_nxt);   // the next block's indices are loaded before this block's rows are consumed
 #pragma unroll 1
-      while (i < n) {
-        const int cur_row = nxt, cnt_blk = (n - i < 32) ? (n - i) : 32;
-        const int i2 = i + p.wpu * 32;
-        nxt = (i2 + lane < n) ? src[i2 + lane] : 0;
+      while (g2 < G) {
+        const int cur_row = nxt, cnt_blk = cnt_nxt;
+        g2 += p.wpu;
+        nxt = fetch_block(g2, cnt_nxt);
         if (lane < cnt_blk) q[(qtail + lane) & (kQueueCap - 1)] = make_int2(cur_row, 1);
         qtail += cnt_blk;
         __syncwarp();
@@ -712,7 +729,6 @@ __global__ void __launch_bounds__(kThreads, BPS) crd_score_kernel(const ScorePar
           qhead += R * U;
         }
         __syncwarp();
-        i = i2;
       }
     } else if (compact) {
       // entries of this segment, unit by unit: every one of them is scored (the filter kernel dropped the rest)
@@ -1286,14 +1302,11 @@ struct CompactPlan {
   int* ucount;
   int* cl;
 };
-// warps per (anchor, chunk) unit of the band-sorted mode, 0 = not worth it / not possible (too few rows to band, or too few
-// units to occupy the machine)
+// warps per anchor of the band-sorted mode, 0 = not possible (too few rows to band, more than 32 chunks per anchor: the unit
+// lengths ride one per lane, or more anchors than resident warps)
 static long long banded_wpu(long long B, long long NC, long long NW, long long rows_local) {
-  if (rows_local < 4096 || B * NC < 1) return 0;
-  long long wpu = NW / (B * NC);
-  if (wpu > 8) wpu = 8;
-  if (wpu < 1 || B * NC * wpu * 2 < NW) return 0;
-  return wpu;
+  if (rows_local < 4096 || B < 1 || NC < 1 || NC > 32 || B > NW) return 0;
+  return NW / B;
 }
 
 static bool plan_compact(int bank_dtype, int64_t D, int variant, int64_t B, int64_t K1, int64_t row_begin, int64_t row_end,
@@ -1301,7 +1314,7 @@ static bool plan_compact(int bank_dtype, int64_t D, int variant, int64_t B, int6
   Variant var;
   if ((variant & 0x100) || !pick_variant(bank_dtype, (int)D, variant & 0x1f, &var)) return false;
   const long long NW = (long long)sms * var.bps * kWarps, NC = filter_chunks(K1);
-  if (NC < 1 || B * (NC + 1) >= kMaxUnits || B > NW || row_end <= row_begin) return false;
+  if (NC < 1 || (B * (NC + 1) >= kMaxUnits && !(variant & 0x400)) || B > NW || row_end <= row_begin) return false;
   char* cbase = (char*)workspace + workspace_slots_end(B, K1, D, NW);
   out->NC = NC; out->NW = NW;
   out->anchor_start = (long long*)cbase;
@@ -1377,12 +1390,13 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   // static shared memory; not for the per-entry outputs mode (kept on the original layout) or the aligned partition
   const long long NC = filter_chunks(K1);
   const bool lists_ok = src != nullptr && src->compact != 0 && src->y != nullptr && full && !aligned && out_v1 == nullptr && NC >= 1 &&
-                        B * (NC + 1) < kMaxUnits && B <= NW && row_end > row_begin;
-  // band-sorted lists: wpu warps per (anchor, chunk) unit take interleaved blocks of the unit's sorted list
+                        B <= NW && row_end > row_begin;
+  // band-sorted lists: wpu warps per anchor take interleaved blocks of the anchor's sorted unit lists
   long long wpu = 0;
   if (lists_ok && src->compact >= 3) wpu = banded_wpu(B, NC, NW, row_end - row_begin);
   const bool banded = wpu > 0;
-  const bool compact = lists_ok && !banded && src->compact < 3;   // (band sort asked for but not possible: the plain scan)
+  // (band sort asked for but not possible: the plain scan)
+  const bool compact = lists_ok && !banded && src->compact < 3 && B * (NC + 1) < kMaxUnits;
   const bool cta_reduce = !compact && !banded && !aligned && D <= 256 && out_v1 == nullptr && (P * kWarps + NW - 1) / NW + 1 <= K1 && !no_cta_fold;
   const size_t need = workspace_bytes_for(B, K1, D, NW);
   if (workspace_bytes < need) return fail(CRDPN_E_WORKSPACE, "crdpn_crd_score: workspace too small");
@@ -1432,7 +1446,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   sp.compact = banded ? 3 : compact ? 1 : 0;
   sp.wpu = (int)wpu;
   sp.band_mul = banded ? (unsigned)((((unsigned long long)kBands) << 32) / (unsigned long long)(row_end - row_begin)) + 1u : 0u;
-  if (banded) sp.nw = B * NC * wpu;
+  if (banded) sp.nw = B * wpu;
   sp.NC = (int)NC;
   char* cbase = ws + workspace_slots_end(B, K1, D, NW);
   long long* anchor_start = (long long*)cbase;
@@ -1459,7 +1473,7 @@ static int score_impl(const void* bank1, const void* bank2, int64_t row_stride, 
   FinalizeParams fp;
   fp.slots = slots; fp.maxseg = sp.maxseg; fp.NW = banded ? sp.nw : NW; fp.group = cta_reduce ? kWarps : 1;
   fp.anchor_start = compact ? anchor_start : nullptr;
-  fp.wpa = banded ? (int)(NC * wpu) : 0;
+  fp.wpa = banded ? (int)wpu : 0;
   fp.B = (int)B; fp.K1 = (int)K1; fp.D = (int)D; fp.full = full ? 1 : 0;
   fp.grad_v1 = grad_v1; fp.grad_v2 = grad_v2;
   fp.anchor_part = anchor_part; fp.result = result; fp.ticket = ticket;
