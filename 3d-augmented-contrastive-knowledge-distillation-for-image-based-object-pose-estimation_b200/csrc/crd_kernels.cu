@@ -9,7 +9,9 @@
 //                           row of each bank is read exactly once; nothing of size B*K*D is ever written.
 //   2. crd_finalize_kernel  deterministic fixed-order reduction of the per-warp partials.
 //   3. crd_update_kernel    momentum + L2 renormalisation of the B positive rows (after all scoring).
-// crdpn_crd_step runs 2 and 3 as ONE launch (crd_finalize_update_kernel): two launches per training step.
+// crdpn_crd_step runs 2 and 3 as ONE launch (crd_finalize_update_kernel): two launches per training step, three with the
+// band-sort pre-pass (crd_band_sort_kernel, variant | 0x400: the default for banks of about the L2's size and larger), which
+// orders every anchor's list by row band so that all warps sweep the bank together and repeated rows are L2 hits.
 //
 // Data layout in HBM: a bank row is D contiguous elements (fp32 or bf16), 16-byte aligned, row pitch
 // `row_stride` elements.  The Python module allocates both banks interleaved as [N][2][D] so that one

@@ -143,6 +143,17 @@ int crdpn_crd_step_drawn(void* bank1, void* bank2, int64_t row_stride, int bank_
                          double* result, float* grad_v1, float* grad_v2,
                          void* workspace, size_t workspace_bytes, int variant, void* stream);
 
+/* Band-sorted contrast lists (variant | 0x400 in crdpn_crd_step, crdpn_crd_step_drawn, crdpn_crd_step_sharded and the
+ * crdpn_crd_loss_forward calls that end in them): a pre-pass (one CTA per anchor and 4096-entry chunk) keeps the entries whose
+ * row this shard owns and STABLY sorts them by row band (32 bands of the shard); the scoring pass then gives the warps of an
+ * anchor interleaved 32-entry blocks of those lists, so all warps sweep the bank together and a row that is drawn several times
+ * per step comes from HBM once (headline shape: 2.91 -> 1.01 GB of DRAM traffic per step).  Same scores, so loss / gradients
+ * equal the plain step's up to fp32 summation order, updated rows bit-identical, bit-reproducible run to run.  Silently falls
+ * back to the plain step when the shape does not qualify (fewer than 4096 resident rows, more than 32 chunks per anchor,
+ * more anchors than resident warps).  variant | 0x20 beside it promises that EVERY entry lives in this shard (in-shard
+ * negatives): the pre-pass then skips its survivor compaction.  The Python mirror sets the bit by itself for shards of about
+ * the L2's size and larger (ContrastMemory.sweep). */
+
 /* Bank-STREAMING formulation of the same step (variant | 0x200 in crdpn_crd_step / crdpn_crd_loss_forward): the samples
  * are bucketed by bank tile and every resident tile passes through shared memory exactly once, so a row that is sampled
  * several times per step (B*K1 > resident rows) is read from HBM once.
