@@ -695,3 +695,44 @@ def test_band_sorted_step_matches_the_gather_step(pkg, oracle, cuda):
         losses.append((loss.item(), f_s.grad.clone(), crit.contrast.memory_v1[y].clone()))
     assert abs(losses[0][0] - losses[1][0]) <= 1e-6 * abs(losses[0][0])
     assert _rel(losses[1][1].cpu().numpy(), losses[0][1].cpu().numpy()) < 1e-5 and torch.equal(losses[0][2], losses[1][2])
+
+
+@pytest.mark.parametrize("B,K,N,lo,hi", [(7, 300, 5000, 0, 5000), (46, 2048, 6000, 0, 6000), (512, 4096, 9000, 0, 9000),
+                                         (138, 16384, 20000, 0, 20000), (46, 70001, 30000, 0, 30000),
+                                         (46, 65536, 40000, 10000, 20000), (30, 131072, 8192, 0, 8192), (3, 1, 4096, 0, 4096)])
+def test_band_sorted_partition_over_shapes(pkg, cuda, B, K, N, lo, hi):
+    """The band-sorted mode over the shapes that stress its partition: one chunk per anchor, hundreds of anchors (few warps
+    each), 32 chunks per anchor, K + 1 not a multiple of the chunk, a shard in the middle of the bank (survivor compaction),
+    tripled indices, a single negative.  Against the plain step on the same inputs: the entry count is exact (nothing lost or
+    scored twice), loss / gradients agree to fp32 summation order, updated rows are bit-identical."""
+    D, T, Z1, Z2 = 128, 0.07, 3.0e4, 3.1e4
+    gen = torch.Generator().manual_seed(B * 131 + K)
+    rows = hi - lo
+    bank = torch.nn.functional.normalize(torch.randn(rows, 2, D, generator=gen), dim=2)
+    v1 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen)).to(cuda)
+    v2 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen)).to(cuda)
+    y = torch.randint(0, N, (B,), generator=gen)
+    if B == 138:
+        y = y[:46].repeat(3)
+    cidx = torch.randint(0, N, (B, K + 1), generator=gen)
+    cidx[:, 0] = y
+    y, cidx = y.to(cuda), cidx.to(cuda)
+    out = {}
+    for name, sweep in (("plain", False), ("swept", True)):
+        mem = pkg.ContrastMemory(D, N, K, T, 0.5, row_begin=lo, row_end=hi).to(cuda)
+        with torch.no_grad():
+            mem.memory_v1.copy_(bank[:, 0]); mem.memory_v2.copy_(bank[:, 1]); mem.params[2], mem.params[3] = Z1, Z2
+        mem._host = None
+        mem.sweep = sweep
+        l0 = pkg._native.launch_count()
+        res, g1, g2 = mem._step(v1, v2, y, cidx, Z1, Z2)
+        torch.cuda.synchronize()
+        assert pkg._native.launch_count() - l0 == (3 if sweep else 2)   # the band-sort pre-pass really ran (no silent fall-back)
+        out[name] = (res.cpu().numpy().copy(), g1.cpu().numpy().copy(), g2.cpu().numpy().copy(),
+                     mem.memory_v1.clone(), mem.memory_v2.clone())
+    a, b = out["plain"], out["swept"]
+    want_cnt = int(((cidx >= lo) & (cidx < hi)).sum().item())
+    assert a[0][4] == b[0][4] == want_cnt
+    assert abs(a[0][5] - b[0][5]) <= 2e-6 * abs(a[0][5]) + 1e-12
+    assert _rel(b[1], a[1]) < 2e-5 and _rel(b[2], a[2]) < 2e-5
+    assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
