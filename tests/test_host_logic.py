@@ -69,3 +69,24 @@ def test_sampler_state_round_trip(pkg):
     other.load_sampler_state(st)
     assert other.sampler_state() == st
     assert not any("extra_state" in k for k in mem.state_dict())
+
+
+def test_sweep_selection_rules(pkg):
+    """Band-sorted lists are chosen for shards of about the L2's size and larger whose rows repeat within the step, never for
+    small banks, few samples, in-L2 shards, and are forced / forbidden by ``sweep``; in-shard negatives keep the hint bit."""
+    mem = pkg.ContrastMemory(128, 1000, 15)
+
+    def variant(rows, n_data, B, K1, k_total=0, sweep=None, base=0):
+        mem.row_begin, mem.row_end, mem.nLem, mem.k_total, mem.sweep, mem.variant = 0, rows, n_data, k_total, sweep, base
+        return mem._step_variant(B, K1, 128)
+
+    S = mem.SWEEP
+    assert variant(1_000_000, 1_000_000, 46, 65537) & S                 # headline: 1 GB bank, 3 draws per row
+    assert variant(500_000, 1_000_000, 46, 65537) & S                   # 2-way shard
+    assert variant(125_000, 1_000_000, 46, 65537) & S                   # 8-way shard: 128 MB
+    assert not variant(90_000, 90_000, 46, 16385) & S                   # config 0: 92 MB bank inside the L2
+    assert not variant(1_000_000, 1_000_000, 46, 4097) & S              # 188 k samples: no repeats to catch
+    assert not variant(1_000_000, 1_000_000, 46, 65537, sweep=False) & S
+    assert variant(8192, 8192, 8, 256, sweep=True) & S
+    assert not variant(1_000_000, 1_000_000, 46, 65537, base=0x40) & S  # an explicit compact request is kept
+    assert variant(1_000_000, 8_000_000, 46, 65537, k_total=8 * 65536) & S   # weak scaling: every entry in-shard
