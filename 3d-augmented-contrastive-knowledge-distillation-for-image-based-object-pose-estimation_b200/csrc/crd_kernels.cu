@@ -1208,9 +1208,11 @@ static bool pick_variant(int dtype, int D, int variant, Variant* out) {
       case 64:
         *out = make_variant<__nv_bfloat16, 8, 1, 4, 2>(); return variant == 0;
       case 128:
-        // 256-byte rows are transaction-bound, not byte-bound: 8 row-steps in flight (0.367 ms at the headline config)
-        // beat the fp32 kernel's shape (0.506 ms); deeper unrolls / more CTAs spill (profiles/crd_bf16_variant_sweep.py)
-        if (variant == 0 || variant == 2) { *out = make_variant<__nv_bfloat16, 16, 1, 8, 2>(); return true; }
+        // round 1: 256-byte rows are transaction-bound, 8 row-steps in flight (0.367 ms at the headline config) beat the fp32
+        // kernel's shape (0.506 ms).  Round 2: with the transposed score reduction (U = 4 only) the kernel is 39 % shorter in
+        // instructions and the 4-step shape wins: 0.418 -> 0.287 ms, B = 138: 1.21 -> 0.85 ms (profiles/r2_bf16_gather_ab.py)
+        if (variant == 0 || variant == 4) { *out = make_variant<__nv_bfloat16, 16, 1, 4, 2>(); return true; }
+        if (variant == 2) { *out = make_variant<__nv_bfloat16, 16, 1, 8, 2>(); return true; }
         if (variant == 1) { *out = make_variant<__nv_bfloat16, 8, 2, 4, 2>(); return true; }
         if (variant == 3) { *out = make_variant<__nv_bfloat16, 4, 4, 2, 2>(); return true; }
         return false;
