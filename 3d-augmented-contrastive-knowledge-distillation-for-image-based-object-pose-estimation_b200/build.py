@@ -73,8 +73,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         print("\n".join(log))
     dev_objs = [str(objdir / (Path(s).stem + ".o")) for s in DEV_SOURCES]
     prod_objs = [o for o in objs if Path(o).stem + ".cu" in names]
-    subprocess.check_call([nvcc, "-shared", "-o", str(LIB), *prod_objs, "-lcudart"])
-    subprocess.check_call([nvcc, "-shared", "-o", str(DEV_LIB), *dev_objs, "-lcudart"])
+    arch = NVCC_FLAGS[:2]   # the link step too: without it nvcc adds an (empty) device-link stub for its default sm_52
+    subprocess.check_call([nvcc, *arch, "-shared", "-o", str(LIB), *prod_objs, "-lcudart"])
+    subprocess.check_call([nvcc, *arch, "-shared", "-o", str(DEV_LIB), *dev_objs, "-lcudart"])
     return LIB
 
 

@@ -57,3 +57,43 @@ def test_cpu_tensors_are_rejected_loudly(pkg):
     crit.load_state_dict({k: v.clone() for k, v in sd.items()})
     m1, m2 = crit.contrast.memory_v1, crit.contrast.memory_v2
     assert m1.stride(0) == 64 and m2.data_ptr() - m1.data_ptr() == 32 * 4
+
+
+def test_product_library_carries_the_sm100a_tensor_core_and_tma_paths(pkg):
+    """Static check of the shipped .so (cuobjdump -sass, no GPU): the PointNet, pose-tail and bank-streaming kernels issue
+    tcgen05.mma (UTCHMMA) with TMEM loads (LDTM) and bulk / tensor-map copies (UBLKCP / UTMALDG); the gather scoring kernel
+    reads rows with 128-bit loads.  A build that silently lost those paths (wrong arch, a fallback body) fails here."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib_path = pkg._native.LIB_PATH if hasattr(pkg._native, "LIB_PATH") else None
+    if lib_path is None:
+        from pathlib import Path
+        lib_path = Path(pkg.__file__).resolve().parent / "libcrdpn_b200.so"
+    elf = subprocess.run(["cuobjdump", "-lelf", str(lib_path)], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in elf and not re.search(r"sm_(?!100a)\d+", elf), elf   # sm_100a only: no multi-arch fat binary
+    sass = subprocess.run(["cuobjdump", "-sass", str(lib_path)], capture_output=True, text=True, check=True).stdout
+    per, cur = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = per.setdefault(m.group(1), set())
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
+        if m and cur is not None:
+            cur.add(m.group(1))
+            cur.add(m.group(1) + m.group(2))
+
+    def ops(fragment):
+        hit = [v for k, v in per.items() if fragment in k]
+        assert hit, f"no kernel named *{fragment}* in the library"
+        return hit
+
+    for frag in ("pointnet_fwd_kernel_v2", "pointnet_fwd_train_split_kernel", "pn_bwd_pass2_kernel", "pose_tail_kernel"):
+        for o in ops(frag):
+            assert "UTCHMMA" in o and "LDTM" in o and "UBLKCP" in o, (frag, sorted(x for x in o if x.startswith("U")))
+    for o in ops("crd_tc_stream_kernel"):
+        assert "UTCHMMA" in o and "LDTM" in o and "UTMALDG" in o
+    assert any(any(x.startswith("LDG.E.128") or x.startswith("LDG.E.ENL2.256") for x in o) for o in ops("crd_score_kernel"))
