@@ -285,14 +285,26 @@ class _PoseTailTrainFunction(torch.autograd.Function):
         for m in bns.values():
             if m.track_running_stats and m.num_batches_tracked is not None:
                 m.num_batches_tracked += 1
-        ctx.tail, ctx.outs, ctx.bn, ctx.biases_keepalive, ctx.lin = tail, outs, bn, biases, lin
-        ctx.save_for_backward(sf, img)
+        # every tensor the backward reads goes through save_for_backward: three of `outs` are this node's own OUTPUTS, and
+        # an output kept as a plain ctx attribute closes a cycle node -> tensor -> grad_fn -> node that only a garbage-
+        # collector pass breaks -- until then the step's activations stay allocated and the parameters' AccumulateGrad
+        # nodes stay alive on the stream of that step (a later CUDA-graph capture of the same module then fails with
+        # "would make the legacy stream depend on a capturing blocking stream")
+        bn_layers = [l for l in range(len(spec)) if bn[l] is not None]
+        ctx.tail, ctx.lin, ctx.bn_layers, ctx.n_layers = tail, lin, bn_layers, len(spec)
+        ctx.save_for_backward(sf, img, *outs, *[bn[l][k] for l in bn_layers for k in ("xhat", "gamma", "istd")])
         return outs[4], outs[3], outs[7]
 
     @staticmethod
     def backward(ctx, g_heads, g_x, g_p):
-        tail, outs, bn = ctx.tail, ctx.outs, ctx.bn
-        sf, img = ctx.saved_tensors
+        tail = ctx.tail
+        saved = ctx.saved_tensors
+        sf, img = saved[0], saved[1]
+        outs = saved[2:2 + ctx.n_layers]
+        bn = [None] * ctx.n_layers
+        for i, l in enumerate(ctx.bn_layers):
+            xhat, gamma, istd = saved[2 + ctx.n_layers + 3 * i:5 + ctx.n_layers + 3 * i]
+            bn[l] = dict(xhat=xhat, gamma=gamma, istd=istd)
         spec = tail.spec
         dev = img.device
         B = img.shape[0]

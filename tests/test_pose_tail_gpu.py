@@ -205,3 +205,55 @@ def test_ragged_widths_and_batches(pkg, cuda, Fs, Fi, B):
         assert _rel(x.cpu().numpy(), w_x.numpy()) < TOL and _rel(p.cpu().numpy(), w_p.numpy()) < TOL
         assert [tuple(o.shape) for o in outs] == [tuple(o.shape) for o in w_outs]
         assert all(_rel(a.cpu().numpy(), b.numpy()) < TOL for a, b in zip(outs, w_outs))
+
+
+def test_train_step_frees_its_activations_and_captures_after_eager_steps(pkg, cuda):
+    """The autograd node of the train step must not keep itself alive (an output stored as a plain ctx attribute closes a
+    node -> tensor -> grad_fn -> node cycle that only a garbage-collector pass breaks): with the collector off, allocated
+    memory stays flat over eager steps, and a CUDA-graph capture of the same module right after eager steps on the default
+    stream succeeds (with the cycle alive the parameters' AccumulateGrad nodes pin the legacy stream and the capture fails)
+    and replays to the same loss and gradients as the eager step."""
+    import gc
+    torch.manual_seed(5)
+    tail = pkg.PoseTail(img_feature_dim=96, shape_feature_dim=32).to(cuda).train()
+    B = 24
+    sf, img = torch.randn(B, 32, device=cuda), torch.randn(B, 96, device=cuda)
+
+    def fwd_bwd(a, b):
+        outs, x, p = tail(a, b)
+        loss = sum(o.sum() for o in outs) + x.square().sum() + p.sum()
+        loss.backward()
+        return loss
+
+    gc.collect()
+    gc.disable()
+    try:
+        a, b = sf.clone().requires_grad_(True), img.clone().requires_grad_(True)
+        for _ in range(2):
+            tail.zero_grad(set_to_none=True); a.grad = None; b.grad = None
+            fwd_bwd(a, b)
+        torch.cuda.synchronize()
+        m0 = torch.cuda.memory_allocated()
+        for _ in range(6):
+            tail.zero_grad(set_to_none=True); a.grad = None; b.grad = None
+            fwd_bwd(a, b)
+        torch.cuda.synchronize()
+        assert torch.cuda.memory_allocated() <= m0 + (1 << 16), (torch.cuda.memory_allocated(), m0)
+        # reference values of one more eager step from the CURRENT running statistics (train-mode outputs do not depend
+        # on them; the gradients neither)
+        tail.zero_grad(set_to_none=True); a.grad = None; b.grad = None
+        want = fwd_bwd(a, b).item()
+        want_g = {n: p_.grad.clone() for n, p_ in tail.named_parameters() if p_.grad is not None}
+        want_a = a.grad.clone()
+        gs = pkg.GraphedStep(fwd_bwd, (sf.cpu().pin_memory(), img.cpu().pin_memory()), cuda, grad_inputs=(0, 1),
+                             zero_grad=lambda: tail.zero_grad(set_to_none=True))
+    finally:
+        gc.enable()
+    gs.stage(sf.cpu().pin_memory(), img.cpu().pin_memory())
+    gs.run()
+    got = gs.collect()
+    assert abs(got - want) <= 1e-5 * abs(want), (got, want)
+    assert torch.equal(gs.static[0].grad, want_a)
+    for n, p_ in tail.named_parameters():
+        if n in want_g:
+            assert torch.equal(p_.grad, want_g[n]), n
