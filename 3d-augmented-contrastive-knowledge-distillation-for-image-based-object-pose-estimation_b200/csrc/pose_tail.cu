@@ -39,6 +39,7 @@ using namespace pn;
 constexpr int kEpi = 256;              // warps 0-7: epilogue (TMEM lane quadrant = warp % 4, column half = warp / 4) and reduce
 constexpr int kPtThreads = kEpi + 64;  // warp 8: bulk-copy producer, warp 9: MMA issuer
 constexpr int kMaxLayers = 10;
+constexpr int kDxMaxSplits = 16;   // split-K ranges of the backward's dx GEMMs (crdpn_pose_tail_backward)
 constexpr int kMaxTasks = 768;         // kernel-parameter space: 2 bytes per task
 constexpr int kMaxGroups = 200;        // (layer, tile) pairs
 constexpr uint32_t kWPlane = 16384;    // one [128 rows x 64 k] bf16 plane of a weight tile
@@ -779,20 +780,27 @@ __global__ void __launch_bounds__(256) pose_tail_pullback_kernel(const float* __
 
 // C[m, n] (+)= sum_k A(m, k) * Bm[k * ldb + n];  A(m, k) = A[k * lda + m] (AK: "k-major", the g_z^T x case) or A[m * lda + k].
 // 16 x 16 threads, each RM x 4 outputs of a (16 RM) x 64 tile; k in chunks of 16 through shared memory; fp32 FFMA.
+// Split-K: blockIdx.z takes the k range [z * kspan, min(K, (z + 1) * kspan)) (kspan a multiple of 16) and writes its partial
+// product to C + z * zstride; pose_tail_splitk_sum_kernel adds the partials in z order (deterministic).  gridDim.z == 1 with
+// kspan >= K is the plain GEMM.
 template <int RM, bool AK>
 __global__ void __launch_bounds__(256) pose_tail_sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
-                                                              float* __restrict__ C, int ldc, int M, int N, int K, int accumulate) {
+                                                              float* __restrict__ C, int ldc, int M, int N, int Ktot, int accumulate,
+                                                              int kspan, size_t zstride) {
   constexpr int TM = 16 * RM;
   __shared__ float As[16][TM + 4];
   __shared__ __align__(16) float Bs[16][64];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
+  const int kbeg = (int)blockIdx.z * kspan;
+  const int K = min(Ktot, kbeg + kspan);   // end of this CTA's k range
+  C += (size_t)blockIdx.z * zstride;
   float acc[RM][4];
 #pragma unroll
   for (int i = 0; i < RM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
 #pragma unroll
     for (int e = t; e < 16 * TM; e += 256) {
       int k, m;
@@ -840,18 +848,57 @@ __global__ void __launch_bounds__(256) pose_tail_sgemm_kernel(const float* __res
   }
 }
 
+// dst[m, n] (+)= sum_z P[z][m][n], z = 0 .. S-1 in that order;  P: S dense [M, N] partials, dst: pitch lddst.  N % 4 == 0 and
+// 16-byte aligned rows take the float4 path.
+__global__ void __launch_bounds__(256) pose_tail_splitk_sum_kernel(const float* __restrict__ P, int S, size_t zstride, float* __restrict__ dst,
+                                                                   int lddst, int M, int N, int accumulate) {
+  const size_t total = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    float a = accumulate ? dst[(size_t)m * lddst + n] : 0.f;
+    for (int z = 0; z < S; ++z) a += P[(size_t)z * zstride + i];
+    dst[(size_t)m * lddst + n] = a;
+  }
+}
+
 // dW[O, I-range] = g_z^T x   (A = g_z [B, O] read k-major, B = x [B, ldx])
 static int launch_dw(const float* gz, int O, const float* x, int ldx, int ncols, float* dW, int ldw, int B, cudaStream_t st) {
   dim3 grid((ncols + 63) / 64, (O + 63) / 64);
-  pose_tail_sgemm_kernel<4, true><<<grid, 256, 0, st>>>(gz, O, x, ldx, dW, ldw, O, ncols, B, 0);
+  pose_tail_sgemm_kernel<4, true><<<grid, 256, 0, st>>>(gz, O, x, ldx, dW, ldw, O, ncols, B, 0, (B + 15) / 16 * 16, 0);
   CRDPN_LAUNCH_CHECK("pose_tail_sgemm_kernel<dW>");
   return CRDPN_OK;
 }
-// dx[B, ncols] (+)= g_z W[:, col0 : col0 + ncols]   (A = g_z [B, O] row-major, B = W [O, ldw])
-static int launch_dx(const float* gz, int O, const float* W, int ldw, int ncols, float* dx, int lddx, int B, int accumulate, cudaStream_t st) {
-  dim3 grid((ncols + 63) / 64, (B + 31) / 32);
-  pose_tail_sgemm_kernel<2, false><<<grid, 256, 0, st>>>(gz, O, W, ldw, dx, lddx, B, ncols, O, accumulate);
-  CRDPN_LAUNCH_CHECK("pose_tail_sgemm_kernel<dx>");
+// how many k ranges the dx GEMM of a [B, ncols] result over K = O is cut into: its (ncols / 64) x (B / 32) tiles alone leave
+// most SMs idle and make every CTA walk O / 16 dependent load -> sync -> FMA rounds (128 at O = 2048); aim at ~1000 CTAs of
+// >= 4 rounds each
+static int dx_splits(int O, int ncols, int B) {
+  const int tiles = ((ncols + 63) / 64) * ((B + 31) / 32);
+  int S = (1000 + tiles - 1) / tiles;
+  const int smax = (O + 63) / 64;
+  if (S > smax) S = smax;
+  if (S > kDxMaxSplits) S = kDxMaxSplits;
+  return S < 1 ? 1 : S;
+}
+// dx[B, ncols] (+)= g_z W[:, col0 : col0 + ncols]   (A = g_z [B, O] row-major, B = W [O, ldw]); `part`: kDxMaxSplits * B * ncols floats
+static int launch_dx(const float* gz, int O, const float* W, int ldw, int ncols, float* dx, int lddx, int B, int accumulate, float* part,
+                     cudaStream_t st) {
+  const int S = dx_splits(O, ncols, B);
+  if (S <= 1) {
+    dim3 grid((ncols + 63) / 64, (B + 31) / 32);
+    pose_tail_sgemm_kernel<2, false><<<grid, 256, 0, st>>>(gz, O, W, ldw, dx, lddx, B, ncols, O, accumulate, (O + 15) / 16 * 16, 0);
+    CRDPN_LAUNCH_CHECK("pose_tail_sgemm_kernel<dx>");
+    return CRDPN_OK;
+  }
+  const int kspan = ((O + S - 1) / S + 15) / 16 * 16;
+  const int Sz = (O + kspan - 1) / kspan;          // ranges that are not empty (<= S)
+  const size_t zstride = (size_t)B * ncols;
+  dim3 grid((ncols + 63) / 64, (B + 31) / 32, Sz);
+  pose_tail_sgemm_kernel<2, false><<<grid, 256, 0, st>>>(gz, O, W, ldw, part, ncols, B, ncols, O, 0, kspan, zstride);
+  CRDPN_LAUNCH_CHECK("pose_tail_sgemm_kernel<dx, split-K>");
+  const size_t total = zstride;
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  pose_tail_splitk_sum_kernel<<<blocks, 256, 0, st>>>(part, Sz, zstride, dx, lddx, B, ncols, accumulate);
+  CRDPN_LAUNCH_CHECK("pose_tail_splitk_sum_kernel");
   return CRDPN_OK;
 }
 
@@ -860,8 +907,12 @@ static int launch_dx(const float* gz, int O, const float* W, int ldw, int ncols,
 
 extern "C" int crdpn_pose_tail_backward_workspace_bytes(const crdpn_pose_tail_bwd_layer* layers, int n_layers, int64_t B, size_t* bytes) {
   if (!layers || !bytes || n_layers < 1 || n_layers > pt::kMaxLayers || B < 1) return fail(CRDPN_E_BADARG, "crdpn_pose_tail_backward_workspace_bytes: bad argument");
-  size_t tot = 0;
-  for (int l = 0; l < n_layers; ++l) tot += 2 * (((size_t)B * (size_t)layers[l].O * 4 + 255) / 256 * 256);
+  size_t tot = 0, widest = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    tot += 2 * (((size_t)B * (size_t)layers[l].O * 4 + 255) / 256 * 256);
+    if ((size_t)layers[l].I > widest) widest = (size_t)layers[l].I;
+  }
+  tot += (size_t)pt::kDxMaxSplits * (size_t)B * widest * 4;   // split-K partials of the widest dx GEMM
   *bytes = tot;
   return CRDPN_OK;
 }
@@ -889,6 +940,7 @@ extern "C" int crdpn_pose_tail_backward(const crdpn_pose_tail_bwd_layer* layers,
     gz[l] = reinterpret_cast<float*>(ws); ws += sz;
     have[l] = false;
   }
+  float* part = reinterpret_cast<float*>(ws);   // behind the per-layer areas: kDxMaxSplits * B * max(I) floats
   bool have_sf = false, have_img = false;
   const int Bi = (int)B, Fs = (int)shape_dim, Fi = (int)img_dim;
   for (int l = n_layers - 1; l >= 0; --l) {
@@ -912,25 +964,25 @@ extern "C" int crdpn_pose_tail_backward(const crdpn_pose_tail_bwd_layer* layers,
       if (Fs > 0 && (rc = pt::launch_dw(gz[l], O, shape_feature, Fs, Fs, a.dW, I, Bi, st))) return rc;
       if ((rc = pt::launch_dw(gz[l], O, img_feature, Fi, Fi, a.dW + Fs, I, Bi, st))) return rc;
       if (d_shape_feature && Fs > 0) {
-        if ((rc = pt::launch_dx(gz[l], O, a.W, I, Fs, d_shape_feature, Fs, Bi, have_sf ? 1 : 0, st))) return rc;
+        if ((rc = pt::launch_dx(gz[l], O, a.W, I, Fs, d_shape_feature, Fs, Bi, have_sf ? 1 : 0, part, st))) return rc;
         have_sf = true;
       }
       if (d_img_feature) {
-        if ((rc = pt::launch_dx(gz[l], O, a.W + Fs, I, Fi, d_img_feature, Fi, Bi, have_img ? 1 : 0, st))) return rc;
+        if ((rc = pt::launch_dx(gz[l], O, a.W + Fs, I, Fi, d_img_feature, Fi, Bi, have_img ? 1 : 0, part, st))) return rc;
         have_img = true;
       }
     } else if (a.src == -2) {
       if (I != Fi) return fail(CRDPN_E_BADARG, "crdpn_pose_tail_backward: image layer width");
       if ((rc = pt::launch_dw(gz[l], O, img_feature, Fi, Fi, a.dW, I, Bi, st))) return rc;
       if (d_img_feature) {
-        if ((rc = pt::launch_dx(gz[l], O, a.W, I, Fi, d_img_feature, Fi, Bi, have_img ? 1 : 0, st))) return rc;
+        if ((rc = pt::launch_dx(gz[l], O, a.W, I, Fi, d_img_feature, Fi, Bi, have_img ? 1 : 0, part, st))) return rc;
         have_img = true;
       }
     } else {
       const auto& s = layers[a.src];
       if (I != (int)s.O) return fail(CRDPN_E_BADARG, "crdpn_pose_tail_backward: layer input width does not match its source");
       if ((rc = pt::launch_dw(gz[l], O, s.y, I, I, a.dW, I, Bi, st))) return rc;
-      if ((rc = pt::launch_dx(gz[l], O, a.W, I, I, gacc[a.src], I, Bi, have[a.src] ? 1 : 0, st))) return rc;
+      if ((rc = pt::launch_dx(gz[l], O, a.W, I, I, gacc[a.src], I, Bi, have[a.src] ? 1 : 0, part, st))) return rc;
       have[a.src] = true;
     }
   }

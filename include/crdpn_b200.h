@@ -378,7 +378,8 @@ int crdpn_pose_tail_forward(const crdpn_pose_tail_layer* layers, int n_layers, c
 
 /* Train-mode backward of the same chain (what autograd does for training.py:75) as ONE call: per layer, last to first, the
  * activation / batch-statistics BatchNorm pull-back (d_gamma, d_beta, d_bias ride in it), dW = g^T x_in, and dx = g W
- * accumulated into the gradient of the layer's source; fp32 FFMA kernels, 3-5 launches per layer.
+ * accumulated into the gradient of the layer's source; fp32 FFMA kernels, 3-7 launches per layer (the dx products run split-K
+ * with a fixed-order sum of the partials: deterministic).
  *   y     : the layer's forward output [B, O] (crdpn_pose_tail_layer.out of the forward call)
  *   xhat, istd, gamma : the forward's saved BatchNorm values (NULL gamma: the layer has no BatchNorm)
  *   g_out : gradient w.r.t. this layer's output coming from OUTSIDE the chain (the losses), or NULL
